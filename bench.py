@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the contrast-maximisation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fused|solve]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload "fused" (default, BASELINE config 2): one step = one fused warp -> IWE -> cost -> backward
+evaluation (gradient-magnitude objective + 0.5*TV) over one window of 16 Mi synthetic events on a
+1280x720 grid, fp32.  `value` = events/s with the prepared window resident in HBM (inputs 201 MB > L2);
+`e2e` = the same through the public API from pinned HOST buffers (H2D of the raw events, window
+preparation, evaluation, D2H of loss + gradient inside the timed region).
+Workload "solve" (BASELINE config 3): one step = one full per-window flow solve (500 k events, K_it Adam
+iterations), value = windows/s.
+N > 1: every rank processes its own windows (window sharding, no data-path collective) -> weak scaling.
+
+`--impl reference` times the reference's CPU torch path (the oracle port: same torch ops as
+src/warp.py + src/event_image_converter.py + autograd) on the host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 720, 1280
+P_BYTES = H * W * 4
+COST = "gradient_magnitude"
+TV_WEIGHT = 0.5
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cuda_time_ms(fn, reps: int):
+    """Average ms per call of `fn` over `reps` calls, CUDA events on the current stream."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def dist_setup(n_gpus: int):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int) -> float:
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's torch path (oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_fused(n_events: int, steps: int, warmup: int, seed: int = 0):
+    from oracle import spec
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ev = torch.from_numpy(spec.synthetic_events(n_events, (H, W), seed=seed))
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=seed))
+    for _ in range(warmup):
+        spec.cmax_value_and_grad(ev, flow, (H, W), cost=COST, tv_weight=TV_WEIGHT)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        spec.cmax_value_and_grad(ev, flow, (H, W), cost=COST, tv_weight=TV_WEIGHT)
+        times.append(time.perf_counter() - t0)
+    return n_events / float(np.mean(times)), float(np.mean(times)) * 1e3, torch.get_num_threads()
+
+
+def cpu_reference_solve(n_events: int, iters: int, seed: int = 0):
+    from oracle import spec
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ev = torch.from_numpy(spec.synthetic_events(n_events, (H, W), seed=seed))
+    t0 = time.perf_counter()
+    spec.solve_dense_flow(ev, (H, W), iters, COST, TV_WEIGHT)
+    dt = time.perf_counter() - t0
+    return dt / iters, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = args.cpu_events
+    if args.workload == "solve":
+        s_per_it, cores = cpu_reference_solve(args.solve_events, max(2, min(args.steps, 5)))
+        value = 1.0 / (s_per_it * args.solve_iters)
+        line = {"metric": "windows/s full per-window flow solve", "value": value, "unit": "windows/s",
+                "ms_per_step": s_per_it * args.solve_iters * 1e3,
+                "config": {"workload": f"full per-window dense flow solve, {args.solve_events} events, 1280x720, "
+                                       f"{COST}+{TV_WEIGHT}*TV, Adam {args.solve_iters} iterations (extrapolated from "
+                                       f"timed iterations)"},
+                "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
+                                 "sample": f"{max(2, min(args.steps, 5))} Adam iterations timed, x{args.solve_iters}"}}
+    else:
+        value, ms, cores = cpu_reference_fused(n_sample, args.steps, args.warmup)
+        line = {"metric": "events/s fwd+bwd warp->IWE->cost", "value": value, "unit": "events/s", "ms_per_step": ms,
+                "config": {"workload": f"single-window fused warp->IWE->{COST}+{TV_WEIGHT}*TV fwd+bwd, 1280x720, fp32; "
+                                       f"CPU sample {n_sample} events per step"},
+                "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n_sample} events per step, {args.steps} steps"}}
+    line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                 "e2e": {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_fused(args, rank, world, local):
+    from event_based_bos_b200 import _capi, ops
+    from event_based_bos_b200.utils import synthetic_events, synthetic_flow
+
+    n = args.events
+    dev = torch.device("cuda", local)
+    ev_host = torch.from_numpy(synthetic_events(n, (H, W), seed=rank)).pin_memory()
+    flow_host = torch.from_numpy(synthetic_flow((H, W), seed=rank)).pin_memory()
+    ev = ev_host.to(dev, non_blocking=True)
+    flow = flow_host.to(dev, non_blocking=True)
+    window = ops.PreparedWindow(ev, (H, W), "first", True)
+    ws = ops.CmaxWorkspace(H, W, (0, 0), dev)
+
+    def step():
+        ops.cmax_value_and_grad(window, flow, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier(world)
+    with ClockSampler(local) as clocks:
+        ms = cuda_time_ms(step, args.steps)
+        barrier(world)
+        ms = max_over_ranks(ms, world)
+        # per-kernel timing of the two event-streaming kernels (same stream, CUDA events)
+        lib = _capi.load()
+        st = torch.cuda.current_stream().cuda_stream
+        p = _capi.ptr
+
+        def splat_only():
+            lib.ebos_window_splat(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, p(ws.iwe), st)
+
+        def bwd_only():
+            lib.ebos_window_backward(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, p(ws.grad_iwe), _capi.COST_GRADMAG,
+                                     p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), st)
+
+        def cost_only():
+            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws.iwe), H, W, 0, 1.0, p(ws.acc), p(ws.grad_iwe), st)
+
+        def tv_only():
+            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, p(ws.acc), p(ws.dflow), st)
+
+        k_ms = {name: cuda_time_ms(fn, args.steps) for name, fn in
+                (("window_splat(+memset)", splat_only), ("window_backward", bwd_only), ("iwe_cost_gradmag", cost_only),
+                 ("flow_tv", tv_only))}
+    clk = clocks.summary()
+
+    # end to end through the public API with host buffers
+    e2e_ms = None
+    if not args.no_e2e:
+        loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        grad_host = torch.empty((2, H, W), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            e = ev_host.to(dev, non_blocking=True)
+            f = flow_host.to(dev, non_blocking=True)
+            win = ops.PreparedWindow(e, (H, W), "first", True, validate=False)
+            loss, grad = ops.cmax_value_and_grad(win, f, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
+            loss_host.copy_(loss, non_blocking=True)
+            grad_host.copy_(grad, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier(world)
+        e2e_ms = max_over_ranks(cuda_time_ms(e2e_step, max(3, min(args.steps, 10))), world)
+
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak_gbs()
+    alg_bytes_step = 32 * n + 11 * P_BYTES  # 32N + 8P (fwd+cost+bwd) + 3P (TV: flow read 2P + weights P)
+    splat_bytes = 16 * n + 3 * P_BYTES      # events + flow read (2P) + IWE write (P)
+    bwd_bytes = 16 * n + 3 * P_BYTES        # events + dIWE read (P) + dflow write (2P)
+    dom = max(("window_splat(+memset)", "window_backward"), key=lambda k: k_ms[k])
+    dom_bytes = splat_bytes if dom.startswith("window_splat") else bwd_bytes
+    achieved = dom_bytes / (k_ms[dom] * 1e-3) / 1e9
+    line = {
+        "metric": "events/s fwd+bwd warp->IWE->cost", "value": world * n / (ms * 1e-3), "unit": "events/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"single-window fused warp->IWE->{COST}+{TV_WEIGHT}*TV forward+backward microbench, "
+                               f"{n} synthetic events (uniform, flow U(-3,3)), 1280x720, fp32, atomic mode; one window per GPU",
+                   "events_per_window": n, "l2_policy": f"inputs larger than L2 ({12 * n / 1e6:.0f} MB sorted SoA per pass)"
+                   if 12 * n > 126e6 else "inputs fit L2 (warm-L2 number)"},
+        "clocks": clk,
+        "step_roofline": {"algorithmic_bytes": alg_bytes_step, "achieved_gbs": alg_bytes_step / (ms * 1e-3) / 1e9,
+                          "frac": alg_bytes_step / (ms * 1e-3) / 1e9 / peak},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()}},
+        "gpu_launches": 5 * args.steps,
+    }
+    if e2e_ms is not None:
+        line["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "events/s", "ms_per_step": e2e_ms,
+                       "h2d_bytes_per_step": 16 * n + 2 * P_BYTES, "d2h_bytes_per_step": 2 * P_BYTES + 4,
+                       "includes": "H2D raw events+flow, window preparation (sort), fused evaluation, D2H loss+gradient"}
+    if not args.no_cpu:
+        v, cms, cores = cpu_reference_fused(args.cpu_events, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_events} events, mean of 3 evaluations after 1 warm-up "
+                                          f"(oracle torch-CPU restatement of the reference ops, fp32)"}
+    print(json.dumps(line), flush=True)
+
+
+def run_solve(args, rank, world, local):
+    from event_based_bos_b200 import solver
+    from event_based_bos_b200.utils import smooth_flow, synthetic_bos_events
+
+    n, iters = args.solve_events, args.solve_iters
+    cfg = {"outer_padding": 0, "warp_direction": "first", "optimizer": {"method": "Adam", "n_iter": iters},
+           "cmax": {"cost_with_weight": {COST: 1.0, "image_gradient": TV_WEIGHT}, "lr": 0.05}}
+    slv = solver.collections["contrast_maximization"]((H, W), (H, W), {}, cfg, None)
+    gt = smooth_flow((H, W), seed=rank)
+    windows = [synthetic_bos_events(n, (H, W), gt, seed=1000 * rank + i).astype(np.float64) for i in range(2)]
+    for _ in range(max(1, min(args.warmup, 2))):
+        slv.estimate(windows[0])
+    barrier(world)
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            slv.estimate(windows[i % len(windows)])   # host events in, host flow out: this IS the public API
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        barrier(world)
+        ms = max_over_ranks(ms, world)
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak_gbs()
+    alg = iters * (32 * n + 25 * P_BYTES)
+    line = {"metric": "windows/s full per-window flow solve", "value": world / (ms * 1e-3), "unit": "windows/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"full per-window dense flow solve, {n} BOS-like events, 1280x720, {COST}+{TV_WEIGHT}*TV, "
+                                   f"Adam lr 0.05, {iters} iterations, zero init; host events in -> host flow out",
+                       "iterations": iters},
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "whole solve (all kernels)", "achieved": alg / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_kind},
+            "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": 16 * n,
+                    "d2h_bytes_per_step": 2 * P_BYTES},
+            "gpu_launches": args.steps * iters * 7}
+    if not args.no_cpu:
+        s_per_it, cores = cpu_reference_solve(n, 3)
+        line["cpu_baseline"] = {"value": 1.0 / (s_per_it * iters), "unit": "windows/s", "cores": cores, "kind": "port",
+                                "sample": f"3 Adam iterations of the oracle loop timed ({s_per_it:.3f} s/it), x{iters}"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fused", choices=["fused", "solve"])
+    ap.add_argument("--events", type=int, default=1 << 24)
+    ap.add_argument("--cpu-events", type=int, default=1 << 22)
+    ap.add_argument("--solve-events", type=int, default=500000)
+    ap.add_argument("--solve-iters", type=int, default=600)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    rank, world, local = dist_setup(args.gpus)
+    try:
+        (run_solve if args.workload == "solve" else run_fused)(args, rank, world, local)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

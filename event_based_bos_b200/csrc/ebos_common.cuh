@@ -1,0 +1,167 @@
+// Shared device/host helpers for libebos (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+#include <float.h>
+#include <string>
+
+#include "../../include/ebos.h"
+
+namespace ebos {
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* where);
+
+#define EBOS_REQUIRE(cond, msg)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ebos::set_error(msg);                \
+      return EBOS_ERR_BAD_ARG;             \
+    }                                      \
+  } while (0)
+
+#define EBOS_LAUNCH_CHECK(where)                                  \
+  do {                                                            \
+    cudaError_t e__ = cudaGetLastError();                         \
+    if (e__ != cudaSuccess) return ebos::cuda_fail(e__, where);   \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs (cached); grids of streaming kernels are sized from it.
+int sm_count();
+
+// ---- unfused IEEE arithmetic ----------------------------------------------------------------
+// The reference computes every step as a separately rounded torch op (src/warp.py:335,
+// src/event_image_converter.py:586-614).  The intrinsics below are never contracted to FMA.
+template <typename T> struct Rn;
+template <> struct Rn<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float flr(float a) { return floorf(a); }
+  static __device__ __forceinline__ float bias() { return 1e-6f; }
+  static __device__ __forceinline__ bool finite(float a) { return fabsf(a) <= FLT_MAX; }
+};
+template <> struct Rn<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double flr(double a) { return floor(a); }
+  static __device__ __forceinline__ double bias() { return 1e-6; }
+  static __device__ __forceinline__ bool finite(double a) { return fabs(a) <= DBL_MAX; }
+};
+
+// Time reference and period of one window from (tmin, tmax).  src/warp.py:230-262, 283-287.
+//   t_ref per direction; dt = t - t_ref; period = max(dt) - min(dt) = (tmax - t_ref) - (tmin - t_ref)
+//   (fl() is monotone, so max/min of the rounded dt are the rounded dt of tmax/tmin).
+template <typename T> struct TimeRef { T t_ref; T period; };
+template <typename T>
+__device__ __forceinline__ TimeRef<T> make_time_ref(T tmin, T tmax, int direction, double frac) {
+  TimeRef<T> r;
+  if (direction == EBOS_DIR_FIRST) r.t_ref = tmin;
+  else if (direction == EBOS_DIR_LAST) r.t_ref = tmax;
+  else r.t_ref = Rn<T>::add(tmin, Rn<T>::mul(Rn<T>::sub(tmax, tmin), (T)frac));
+  r.period = Rn<T>::sub(Rn<T>::sub(tmax, r.t_ref), Rn<T>::sub(tmin, r.t_ref));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ T event_dt(T t, const TimeRef<T>& tr, int normalize_t) {
+  T d = Rn<T>::sub(t, tr.t_ref);
+  return normalize_t ? Rn<T>::div(d, tr.period) : d;
+}
+
+// ---- bilinear-vote taps ---------------------------------------------------------------------
+// src/event_image_converter.py:586-614.  r/c are the padded integer cell; taps in reference order
+// 0:(r,c) 1:(r+1,c) 2:(r,c+1) 3:(r+1,c+1).
+template <typename T> struct Taps {
+  int r, c;          // saturated int32 (an out-of-range cell is masked either way)
+  T a, b;            // fractional parts (from the un-biased coordinate)
+  T w0, w1, w2, w3;  // weights, before the optional per-event weight
+};
+
+template <typename T>
+__device__ __forceinline__ int sat_add(int v, int p) {
+  long long s = (long long)v + p;
+  return s > INT_MAX ? INT_MAX : (s < INT_MIN ? INT_MIN : (int)s);
+}
+
+template <typename T>
+__device__ __forceinline__ Taps<T> make_taps(T xw, T yw, int pad_h, int pad_w, T bias = Rn<T>::bias()) {
+  // bias: 1e-6 in the tensor branch (src/event_image_converter.py:586), 1e-8 in the numpy branch (:528)
+  Taps<T> t;
+  T fr = Rn<T>::flr(Rn<T>::add(xw, bias));
+  T fc = Rn<T>::flr(Rn<T>::add(yw, bias));
+  t.a = Rn<T>::sub(xw, fr);
+  t.b = Rn<T>::sub(yw, fc);
+  // float->int conversion saturates; NaN converts to 0 and is handled by the caller via `finite`.
+  t.r = sat_add<T>((int)fr, pad_h);
+  t.c = sat_add<T>((int)fc, pad_w);
+  T na = Rn<T>::sub((T)1, t.a), nb = Rn<T>::sub((T)1, t.b);
+  t.w0 = Rn<T>::mul(na, nb);
+  t.w1 = Rn<T>::mul(t.a, nb);
+  t.w2 = Rn<T>::mul(na, t.b);
+  t.w3 = Rn<T>::mul(t.a, t.b);
+  return t;
+}
+
+// no-return global reduction (REDG.E.ADD.F32 / .F64)
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// ---- block reductions (warp shuffle) ----------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Sum `v` over the CTA; result valid in thread 0.  `smem` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// ---- prepared window ----------------------------------------------------------------------------
+// Layout of the caller-owned window buffer (ebos_window_bytes): a 256-byte header followed by
+// 256-byte aligned SoA arrays of the events sorted by origin pixel.
+// The header is written by the device (time statistics are never read back by the host); the
+// array offsets are a pure function of n, recomputed on the host by window_layout().
+struct WindowHeader {
+  float t_ref, period, t_min, t_max;
+  unsigned int enc_min, enc_max;  // order-preserving encodings used by the atomic min/max pass
+};
+static_assert(sizeof(WindowHeader) <= 256, "header must fit its slot");
+
+inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+struct WindowLayout {
+  size_t off_x, off_y, off_d, off_w, off_perm, total;
+};
+inline WindowLayout window_layout(int64_t n) {
+  WindowLayout L;
+  size_t a = align256((size_t)n * 4);
+  L.off_x = 256;
+  L.off_y = L.off_x + a;
+  L.off_d = L.off_y + a;
+  L.off_w = L.off_d + a;
+  L.off_perm = L.off_w + a;
+  L.total = L.off_perm + a;
+  return L;
+}
+
+}  // namespace ebos

@@ -1,0 +1,411 @@
+"""Functional layer over the C-ABI: tensors in, tensors out, autograd wired to the analytic
+backward kernels.  Everything here runs on a CUDA device through libebos.so; there is no CPU path.
+
+Reference interfaces mirrored (paths into the reference tree):
+  warp_dense_flow / warp_2dof      Warp.warp_event                      src/warp.py:193-383
+  iwe_splat                        EventImageConverter.bilinear_vote_tensor   src/event_image_converter.py:562-620
+  PreparedWindow + cmax_value_and_grad   fused warp->IWE->cost->backward (SURVEY.md section 3b composition)
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import check, current_stream, ptr
+
+Direction = Union[str, float]
+
+COST_KINDS = {"image_variance": _capi.COST_VARIANCE, "gradient_magnitude": _capi.COST_GRADMAG}
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _capi.EBOS_F32
+    if t.dtype == torch.float64:
+        return _capi.EBOS_F64
+    raise TypeError(f"event_based_bos_b200 kernels support float32/float64 tensors, got {t.dtype}")
+
+
+def direction_code(direction: Direction) -> Tuple[int, float]:
+    """Map Warp.calculate_reftime's `direction` (src/warp.py:230-262) to (kind, fraction).
+    Like upstream, only a genuine `float` selects the fractional form (an int raises)."""
+    if type(direction) is float:
+        return _capi.DIR_FRAC, direction
+    if direction == "first":
+        return _capi.DIR_FIRST, 0.0
+    if direction == "middle":
+        return _capi.DIR_FRAC, 0.5
+    if direction == "last":
+        return _capi.DIR_LAST, 0.0
+    if direction == "random":
+        return _capi.DIR_FRAC, float(np.random.uniform(low=0.0, high=1.0))
+    if direction == "before":
+        return _capi.DIR_FRAC, -1.0
+    if direction == "after":
+        return _capi.DIR_FRAC, 2.0
+    raise ValueError(f"direction argument should be first, middle, last. Or float. {direction}")
+
+
+def _as_batched(events: torch.Tensor) -> Tuple[torch.Tensor, bool]:
+    if events.dim() == 2:
+        return events[None], False
+    if events.dim() == 3:
+        return events, True
+    raise ValueError(f"events must be [n,4] or [b,n,4], got {tuple(events.shape)}")
+
+
+def _check_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    _capi.require_device()
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("event_based_bos_b200.ops expects CUDA tensors (the drop-in classes move inputs for you)")
+
+
+def time_stats(events: torch.Tensor) -> torch.Tensor:
+    """[b,2] (min t, max t) per batch row.  Replaces nt_min/nt_max (src/types/__init__.py:20-47)."""
+    ev, _ = _as_batched(events)
+    _check_cuda(ev)
+    ev = ev.contiguous()
+    if ev.shape[1] == 0:
+        raise RuntimeError("min()/max() of an empty event array (the reference raises here too)")
+    out = torch.empty((ev.shape[0], 2), dtype=ev.dtype, device=ev.device)
+    check(_capi.load().ebos_time_stats(ptr(ev), ev.shape[1], ev.shape[0], dtype_code(ev), ptr(out), current_stream()),
+          "ebos_time_stats")
+    return out
+
+
+class _WarpDenseFlow(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, events, flow, H, W, dir_kind, dir_frac, normalize_t, validate):
+        ev = events.contiguous()
+        fl = flow.contiguous()
+        b, n = ev.shape[0], ev.shape[1]
+        shared_flow = fl.shape[0] == 1 and b > 1
+        tstats = time_stats(ev)
+        warped = torch.empty_like(ev)
+        status = torch.zeros(1, dtype=torch.int32, device=ev.device)
+        check(_capi.load().ebos_warp_dense_flow(
+            ptr(ev), n, b, ptr(fl), 0 if shared_flow else 2 * H * W, H, W, ptr(tstats), dir_kind, dir_frac,
+            int(normalize_t), dtype_code(ev), ptr(warped), ptr(status), current_stream()), "ebos_warp_dense_flow")
+        if validate and int(status.item()) & _capi.STATUS_PIXEL_OOB:
+            raise RuntimeError("index out of bounds: an event's integer pixel lies outside the flow grid "
+                               "(the reference's torch.gather raises for the same input)")
+        ctx.save_for_backward(ev, tstats)
+        ctx.meta = (H, W, dir_kind, dir_frac, int(normalize_t), fl.shape, shared_flow)
+        return warped
+
+    @staticmethod
+    def backward(ctx, grad_warped):
+        ev, tstats = ctx.saved_tensors
+        H, W, dir_kind, dir_frac, normalize_t, flow_shape, shared_flow = ctx.meta
+        b, n = ev.shape[0], ev.shape[1]
+        gw = grad_warped.contiguous()
+        dflow = torch.zeros(flow_shape, dtype=ev.dtype, device=ev.device)
+        check(_capi.load().ebos_warp_dense_flow_bwd(
+            ptr(ev), n, b, H, W, ptr(tstats), dir_kind, dir_frac, normalize_t, dtype_code(ev), ptr(gw), ptr(dflow),
+            0 if shared_flow else 2 * H * W, current_stream()), "ebos_warp_dense_flow_bwd")
+        return None, dflow, None, None, None, None, None, None
+
+
+def warp_dense_flow(events: torch.Tensor, flow: torch.Tensor, image_size: Tuple[int, int],
+                    direction: Direction = "first", normalize_t: bool = False, validate: bool = True) -> torch.Tensor:
+    """Warped events (x', y', dt, p), same leading shape as `events`; differentiable w.r.t. `flow`."""
+    ev, batched = _as_batched(events)
+    fl = flow if flow.dim() == 4 else flow[None]
+    _check_cuda(ev, fl)
+    H, W = int(image_size[0]), int(image_size[1])
+    if fl.shape[-3] != 2 or fl.shape[-2] * fl.shape[-1] < 1:
+        raise ValueError(f"flow must be [(b,)2,H,W], got {tuple(flow.shape)}")
+    if fl.dtype != ev.dtype:
+        raise TypeError(f"events ({ev.dtype}) and flow ({fl.dtype}) must share a dtype")
+    kind, frac = direction_code(direction)
+    # k = trunc(x)*W + trunc(y) uses image_size[1]; the bound is the flow plane's own size, like
+    # torch.gather on flow.reshape(b, 2, -1) (src/warp.py:333-336).
+    plane = fl.shape[-2] * fl.shape[-1]
+    if plane % W:
+        raise ValueError(f"flow plane {tuple(fl.shape[-2:])} is not a multiple of image width {W}")
+    out = _WarpDenseFlow.apply(ev, fl, plane // W, W, kind, frac, normalize_t, validate)
+    return out if batched else out[0]
+
+
+def warp_2dof(events: torch.Tensor, theta: torch.Tensor, direction: Direction = "first",
+              normalize_t: bool = False) -> torch.Tensor:
+    """x' = x + dt*theta0, y' = y + dt*theta1 (src/warp.py:344-383).  Forward only."""
+    ev, batched = _as_batched(events)
+    _check_cuda(ev, theta)
+    ev = ev.contiguous()
+    th = theta.to(ev.dtype).contiguous()
+    kind, frac = direction_code(direction)
+    tstats = time_stats(ev)
+    out = torch.empty_like(ev)
+    check(_capi.load().ebos_warp_2dof(ptr(ev), ev.shape[1], ev.shape[0], ptr(th), ptr(tstats), kind, frac,
+                                      int(normalize_t), dtype_code(ev), ptr(out), current_stream()), "ebos_warp_2dof")
+    return out if batched else out[0]
+
+
+class _IweSplat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, events, weight, Hp, Wp, pad_h, pad_w, deterministic, floor_bias):
+        ev = events.contiguous()
+        w = None if weight is None else weight.contiguous()
+        b, n = ev.shape[0], ev.shape[1]
+        image = torch.empty((b, Hp, Wp), dtype=ev.dtype, device=ev.device)
+        lib = _capi.load()
+        mode = 1 if deterministic else 0
+        ws_bytes = lib.ebos_splat_workspace_bytes(n, b, Hp, Wp, dtype_code(ev), mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ev.device) if ws_bytes else None
+        check(lib.ebos_iwe_splat(ptr(ev), n, b, Hp, Wp, pad_h, pad_w, ptr(w), floor_bias, dtype_code(ev), mode,
+                                 ptr(image), 0, 0, ptr(ws), ws_bytes, current_stream()), "ebos_iwe_splat")
+        ctx.save_for_backward(ev, w)
+        ctx.meta = (Hp, Wp, pad_h, pad_w, floor_bias)
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        ev, w = ctx.saved_tensors
+        Hp, Wp, pad_h, pad_w, floor_bias = ctx.meta
+        b, n = ev.shape[0], ev.shape[1]
+        g = grad_image.contiguous()
+        gev = torch.empty_like(ev)
+        gw = torch.empty_like(w) if (w is not None and ctx.needs_input_grad[1]) else None
+        check(_capi.load().ebos_iwe_splat_bwd(ptr(ev), n, b, Hp, Wp, pad_h, pad_w, ptr(w), floor_bias, dtype_code(ev),
+                                              ptr(g), ptr(gev), ptr(gw), current_stream()), "ebos_iwe_splat_bwd")
+        return gev, gw, None, None, None, None, None, None
+
+
+def iwe_splat(events: torch.Tensor, padded_size: Tuple[int, int], outer_padding: Tuple[int, int] = (0, 0),
+              weight: Union[float, torch.Tensor] = 1.0, deterministic: bool = False,
+              floor_bias: float = 1e-6) -> torch.Tensor:
+    """Bilinear-vote image [(b,)Hp,Wp]; differentiable w.r.t. the event coordinates and `weight`.
+
+    `deterministic=True` reproduces the reference's sequential tap-major accumulation bit for bit.
+    `floor_bias`: 1e-6 (tensor branch, src/event_image_converter.py:586) or 1e-8 (numpy branch, :528)."""
+    ev, batched = _as_batched(events)
+    _check_cuda(ev)
+    w: Optional[torch.Tensor]
+    if isinstance(weight, torch.Tensor):
+        assert weight.shape == events.shape[:-1]  # same assertion as src/event_image_converter.py:576-577
+        w = weight.to(ev.dtype).reshape(ev.shape[0], ev.shape[1])
+    elif float(weight) == 1.0:
+        w = None
+    else:
+        w = torch.full((ev.shape[0], ev.shape[1]), float(weight), dtype=ev.dtype, device=ev.device)
+    img = _IweSplat.apply(ev, w, int(padded_size[0]), int(padded_size[1]), int(outer_padding[0]), int(outer_padding[1]),
+                          bool(deterministic), float(floor_bias))
+    return img if batched else img[0]
+
+
+def iwe_splat_debug(events: torch.Tensor, padded_size: Tuple[int, int], outer_padding: Tuple[int, int] = (0, 0),
+                    deterministic: bool = False, floor_bias: float = 1e-6):
+    """(image, inds int64 [4n], mask bool [4n]) -- the reference's `inds` / `inds_mask`
+    (src/event_image_converter.py:592-617), for bit-exact parity checks.  Unbatched."""
+    _check_cuda(events)
+    ev = events.contiguous()[None]
+    n = ev.shape[1]
+    Hp, Wp = int(padded_size[0]), int(padded_size[1])
+    image = torch.empty((1, Hp, Wp), dtype=ev.dtype, device=ev.device)
+    inds = torch.empty(4 * n, dtype=torch.int64, device=ev.device)
+    mask = torch.empty(4 * n, dtype=torch.uint8, device=ev.device)
+    lib = _capi.load()
+    mode = 1 if deterministic else 0
+    ws_bytes = lib.ebos_splat_workspace_bytes(n, 1, Hp, Wp, dtype_code(ev), mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ev.device) if ws_bytes else None
+    check(lib.ebos_iwe_splat(ptr(ev), n, 1, Hp, Wp, int(outer_padding[0]), int(outer_padding[1]), 0, float(floor_bias),
+                             dtype_code(ev), mode, ptr(image), ptr(inds), ptr(mask), ptr(ws), ws_bytes, current_stream()),
+          "ebos_iwe_splat")
+    return image[0], inds, mask.bool()
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused path
+# ------------------------------------------------------------------------------------------------------
+class PreparedWindow:
+    """Events of one time window, prepared once for many objective evaluations: time-normalised
+    (src/warp.py:264-288) and stably sorted by origin pixel (src/warp.py:334) into an SoA buffer.
+    fp32.  `events` is [n,4] on the GPU (x=row, y=col, t, p)."""
+
+    def __init__(self, events: torch.Tensor, image_size: Tuple[int, int], direction: Direction = "first",
+                 normalize_t: bool = True, weight: Optional[torch.Tensor] = None, validate: bool = True,
+                 t_min_max: Optional[torch.Tensor] = None):
+        _check_cuda(events, weight, t_min_max)
+        if events.dim() != 2 or events.shape[1] != 4:
+            raise ValueError(f"events must be [n,4], got {tuple(events.shape)}")
+        if events.shape[0] == 0:
+            raise RuntimeError("min()/max() of an empty event array (the reference raises here too)")
+        ev = events.to(torch.float32).contiguous()
+        self.device = ev.device
+        self.n = int(ev.shape[0])
+        self.H, self.W = int(image_size[0]), int(image_size[1])
+        self.direction = direction
+        self.normalize_t = bool(normalize_t)
+        self.has_weight = weight is not None
+        w = None if weight is None else weight.to(torch.float32).contiguous()
+        kind, frac = direction_code(direction)
+        lib = _capi.load()
+        self.buffer = torch.empty(lib.ebos_window_bytes(self.n), dtype=torch.uint8, device=ev.device)
+        ws_bytes = lib.ebos_window_workspace_bytes(self.n, self.H, self.W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ev.device)
+        status = torch.zeros(1, dtype=torch.int32, device=ev.device)
+        # t_min_max: float32 [2] on the device -- the GLOBAL (min t, max t) when this window is one
+        # shard of a larger event set (event-sharded multi-GPU path).
+        tmm = None if t_min_max is None else t_min_max.to(torch.float32).contiguous()
+        check(lib.ebos_window_prepare(ptr(ev), self.n, self.H, self.W, kind, frac, int(self.normalize_t), ptr(w),
+                                      ptr(tmm), ptr(self.buffer), ptr(ws), ws_bytes, ptr(status), current_stream()),
+              "ebos_window_prepare")
+        self._status = status
+        if validate and int(status.item()) & _capi.STATUS_PIXEL_OOB:
+            raise RuntimeError("index out of bounds: an event's integer pixel lies outside the flow grid "
+                               "(the reference's torch.gather raises for the same input)")
+
+    def permutation(self) -> torch.Tensor:
+        """int32 [n]: sorted position -> index of the event in the array the window was built from."""
+        out = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, ptr(out), 0, current_stream()), "ebos_window_info")
+        return out
+
+    def time_info(self) -> torch.Tensor:
+        """float32 [4]: t_ref, period, t_min, t_max as computed on the device."""
+        out = torch.empty(4, dtype=torch.float32, device=self.device)
+        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, 0, ptr(out), current_stream()), "ebos_window_info")
+        return out
+
+
+def window_splat(window: PreparedWindow, flow: torch.Tensor, outer_padding: Tuple[int, int] = (0, 0),
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """IWE [Hp,Wp] of the window warped by `flow` [2,H,W] (fused warp + bilinear vote, atomic mode)."""
+    _check_cuda(flow)
+    _check_flow(window, flow)
+    ph, pw = int(outer_padding[0]), int(outer_padding[1])
+    if out is None:
+        out = torch.empty((window.H + 2 * ph, window.W + 2 * pw), dtype=torch.float32, device=flow.device)
+    check(_capi.load().ebos_window_splat(ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), window.H,
+                                         window.W, ph, pw, ptr(out), current_stream()), "ebos_window_splat")
+    return out
+
+
+def _check_flow(window: PreparedWindow, flow: torch.Tensor) -> None:
+    if flow.dtype != torch.float32 or tuple(flow.shape) != (2, window.H, window.W) or not flow.is_contiguous():
+        raise ValueError(f"flow must be a contiguous float32 [2,{window.H},{window.W}] tensor, got "
+                         f"{flow.dtype} {tuple(flow.shape)}")
+
+
+class CmaxWorkspace:
+    """Scratch planes for `cmax_value_and_grad`, allocated once per (H, W, padding)."""
+
+    def __init__(self, H: int, W: int, outer_padding: Tuple[int, int] = (0, 0), device="cuda"):
+        ph, pw = int(outer_padding[0]), int(outer_padding[1])
+        self.H, self.W, self.ph, self.pw = H, W, ph, pw
+        self.iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=torch.float32, device=device)
+        self.grad_iwe = torch.empty_like(self.iwe)
+        self.dflow = torch.empty((2, H, W), dtype=torch.float32, device=device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=device)
+        self.acc = torch.zeros(8, dtype=torch.float64, device=device)
+
+
+def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
+                        data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
+                        omit_boundary: bool = False, outer_padding: Tuple[int, int] = (0, 0),
+                        workspace: Optional[CmaxWorkspace] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(loss [1], dL/dflow [2,H,W]) of   data_weight * L_cost(IWE(warp(events, flow))) + tv_weight * TV(flow).
+
+    One C call, five kernels, no host synchronisation and no materialised warped events or [4N]
+    temporaries.  The returned tensors alias `workspace` (overwritten by the next call)."""
+    _check_cuda(flow, tv_weights)
+    _check_flow(window, flow)
+    if cost not in COST_KINDS:
+        raise KeyError(f"unknown data cost {cost!r}; available: {sorted(COST_KINDS)}")
+    ws = workspace or CmaxWorkspace(window.H, window.W, outer_padding, flow.device)
+    tvw = None
+    if tv_weights is not None:
+        tvw = tv_weights.to(torch.float32).contiguous()
+        if tuple(tvw.shape) != (window.H, window.W):
+            raise ValueError(f"tv_weights must be [{window.H},{window.W}], got {tuple(tvw.shape)}")
+    check(_capi.load().ebos_cmax_value_and_grad(
+        ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), window.H, window.W, ws.ph, ws.pw,
+        COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), ptr(ws.iwe),
+        ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), current_stream()), "ebos_cmax_value_and_grad")
+    return ws.loss, ws.dflow
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+              step_dev: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.Adam update in place (fp32).  With `step_dev` (int32 [1] on the device) the step
+    counter lives on the GPU so that the call can be captured in a CUDA graph."""
+    _check_cuda(param, grad, exp_avg, exp_avg_sq)
+    lib = _capi.load()
+    if step_dev is not None:
+        check(lib.ebos_adam_step_graph(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, betas[0],
+                                       betas[1], eps, ptr(step_dev), current_stream()), "ebos_adam_step_graph")
+    else:
+        check(lib.ebos_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, betas[0],
+                                 betas[1], eps, int(step), current_stream()), "ebos_adam_step")
+
+
+# operator-level cost kernels (used by the CostBase-style classes) ----------------------------------------
+class _IweCost(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, iwe, kind, omit_boundary):
+        img = iwe.contiguous()
+        Hp, Wp = img.shape
+        acc = torch.empty(8, dtype=torch.float64, device=img.device)
+        grad = torch.empty_like(img)
+        loss = torch.empty(1, dtype=torch.float32, device=img.device)
+        lib = _capi.load()
+        st = current_stream()
+        check(lib.ebos_iwe_cost(kind, ptr(img), Hp, Wp, int(omit_boundary), 1.0, ptr(acc), ptr(grad), st), "ebos_iwe_cost")
+        acc[3] = 0.0
+        check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, 1, 1, int(omit_boundary), 1.0, 0.0, ptr(loss), st),
+              "ebos_loss_finalize")
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None, None
+
+
+def iwe_cost(iwe: torch.Tensor, cost: str, omit_boundary: bool = False) -> torch.Tensor:
+    """Scalar data objective on an fp32 IWE plane, differentiable (analytic gradient kernel)."""
+    _check_cuda(iwe)
+    if iwe.dim() != 2:
+        raise ValueError(f"iwe must be [H,W], got {tuple(iwe.shape)}")
+    out = _IweCost.apply(iwe.to(torch.float32), COST_KINDS[cost], bool(omit_boundary))
+    return out.to(iwe.dtype)
+
+
+class _FlowTv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, weights):
+        fl = flow.contiguous()
+        _, H, W = fl.shape
+        acc = torch.zeros(8, dtype=torch.float64, device=fl.device)
+        dflow = torch.empty_like(fl)
+        check(_capi.load().ebos_flow_tv(ptr(fl), ptr(weights), H, W, 1.0, ptr(acc), ptr(dflow), current_stream()),
+              "ebos_flow_tv")
+        ctx.save_for_backward(dflow)
+        return (acc[3] / (2.0 * H * W)).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dflow,) = ctx.saved_tensors
+        return dflow * grad_out, None
+
+
+def flow_total_variation(flow: torch.Tensor, weights: Union[float, torch.Tensor, None] = None) -> torch.Tensor:
+    """mean(|d flow/d row * w| + |d flow/d col * w|)  (src/costs/image_gradient.py:60-70), differentiable
+    w.r.t. `flow`."""
+    _check_cuda(flow)
+    if flow.dim() != 3 or flow.shape[0] != 2:
+        raise ValueError(f"flow must be [2,H,W], got {tuple(flow.shape)}")
+    w = None
+    if isinstance(weights, torch.Tensor):
+        w = weights.to(device=flow.device, dtype=torch.float32).expand(flow.shape[1], flow.shape[2]).contiguous()
+    elif weights is not None and float(weights) != 1.0:
+        w = torch.full(flow.shape[1:], float(weights), dtype=torch.float32, device=flow.device)
+    out = _FlowTv.apply(flow.to(torch.float32), w)
+    return out.to(flow.dtype)

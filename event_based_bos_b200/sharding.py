@@ -1,0 +1,186 @@
+"""Multi-GPU execution of the path: one process per GPU (torchrun), `torch.distributed` for plumbing.
+
+Two regimes:
+
+* **Window sharding** -- time windows of a sequence are independent (the reference carries no state
+  between windows: src/solver/patch_eklt_pyramid2.py:187-190, bos_event.py:257-258 are commented out).
+  Rank r solves windows r, r+R, ...; there is NO data-path collective, only an optional final gather.
+
+* **Event sharding** of one giant window -- rank r owns a contiguous slice of the events; every
+  objective evaluation builds a partial IWE, all-reduces it (sum, H*W fp32 = 3.7 MB at 1280x720),
+  evaluates cost and dL/dIWE redundantly, runs the backward over its own events into a partial flow
+  gradient and all-reduces that (7.4 MB), so that every rank applies the identical Adam step.
+  The time normalisation uses the GLOBAL (min t, max t), exchanged once per window.
+
+The numerical stages are injectable so that the host-side logic runs under `gloo` on CPU in the tests
+(with oracle stages); in production they are the CUDA kernels of `ops`.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def rank_world() -> Tuple[int, int]:
+    return (dist.get_rank(), dist.get_world_size()) if is_distributed() else (0, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# window sharding
+# ----------------------------------------------------------------------------------------------
+def shard_windows(n_windows: int, rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+    """Indices of the windows rank `rank` solves: round robin (w mod R == r), which balances a
+    sequence whose event rate drifts over time better than contiguous blocks."""
+    r, R = rank_world()
+    rank = r if rank is None else rank
+    world = R if world is None else world
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of size {world}")
+    return list(range(rank, n_windows, world))
+
+
+def solve_windows(solve_fn: Callable[[int], torch.Tensor], n_windows: int, gather: bool = False,
+                  rank: Optional[int] = None, world: Optional[int] = None):
+    """Run `solve_fn(window_index) -> flow [2,H,W]` for this rank's windows.
+
+    Returns {window_index: flow} for the local windows; with `gather=True` every rank receives the
+    flows of ALL windows (all_gather of equally sized blocks, padded with zeros for ranks that own
+    one window fewer) -- the only collective of this regime, and off the solve path."""
+    mine = shard_windows(n_windows, rank, world)
+    local = {w: solve_fn(w) for w in mine}
+    if not gather or not is_distributed():
+        return local
+    r, R = rank_world()
+    per_rank = (n_windows + R - 1) // R
+    proto = next(iter(local.values())) if local else None
+    shape = _broadcast_shape(proto)
+    device = proto.device if proto is not None else _default_device()
+    block = torch.zeros((per_rank,) + shape, dtype=torch.float32, device=device)
+    for j, w in enumerate(mine):
+        block[j].copy_(local[w])
+    blocks = [torch.empty_like(block) for _ in range(R)]
+    dist.all_gather(blocks, block)
+    out = {}
+    for rr in range(R):
+        for j, w in enumerate(range(rr, n_windows, R)):
+            out[w] = blocks[rr][j]
+    return out
+
+
+def _default_device():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def _broadcast_shape(proto: Optional[torch.Tensor]) -> Tuple[int, ...]:
+    """All ranks must agree on the flow shape even if some own no window."""
+    dev = proto.device if proto is not None else _default_device()
+    shp = torch.zeros(4, dtype=torch.int64, device=dev)
+    if proto is not None:
+        shp[0] = proto.dim()
+        shp[1:1 + proto.dim()] = torch.tensor(proto.shape, device=dev)
+    dist.all_reduce(shp, op=dist.ReduceOp.MAX)
+    return tuple(int(v) for v in shp[1:1 + int(shp[0])])
+
+
+# ----------------------------------------------------------------------------------------------
+# event sharding
+# ----------------------------------------------------------------------------------------------
+def shard_events(n_events: int, rank: Optional[int] = None, world: Optional[int] = None) -> Tuple[int, int]:
+    """[start, stop) of the contiguous event slice owned by `rank` (sizes differ by at most one)."""
+    r, R = rank_world()
+    rank = r if rank is None else rank
+    world = R if world is None else world
+    base, rem = divmod(n_events, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def global_time_range(t_local: torch.Tensor) -> torch.Tensor:
+    """float32 [2] = (min t, max t) over the events of ALL ranks (one MIN and one MAX all-reduce)."""
+    lo = t_local.min().reshape(1).to(torch.float32) if t_local.numel() else torch.full((1,), float("inf"), device=t_local.device)
+    hi = t_local.max().reshape(1).to(torch.float32) if t_local.numel() else torch.full((1,), float("-inf"), device=t_local.device)
+    if is_distributed():
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return torch.cat([lo, hi])
+
+
+class EventShardedObjective:
+    """loss and dL/dflow of one window whose events are sharded over the ranks.
+
+    Stages (callables, defaulting to the CUDA kernels):
+        splat(flow)            -> partial IWE of the local events          [Hp,Wp]
+        cost(iwe)              -> (data loss scalar tensor, dL/dIWE)        evaluated redundantly
+        backward(flow, g_iwe)  -> partial dL/dflow of the local events      [2,H,W]
+        regulariser(flow)      -> (tv loss scalar tensor, dTV/dflow)        identical on every rank
+    """
+
+    def __init__(self, splat: Callable, cost: Callable, backward: Callable, regulariser: Optional[Callable] = None):
+        self.splat, self.cost, self.backward, self.regulariser = splat, cost, backward, regulariser
+
+    def value_and_grad(self, flow: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        iwe = self.splat(flow)
+        if is_distributed():
+            dist.all_reduce(iwe, op=dist.ReduceOp.SUM)       # exchange 1: partial IWEs
+        loss, g_iwe = self.cost(iwe)
+        dflow = self.backward(flow, g_iwe)
+        if is_distributed():
+            dist.all_reduce(dflow, op=dist.ReduceOp.SUM)     # exchange 2: partial flow gradients
+        if self.regulariser is not None:
+            tv, dtv = self.regulariser(flow)
+            loss = loss + tv
+            dflow = dflow + dtv
+        return loss, dflow
+
+
+def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[int, int], cost: str = "gradient_magnitude",
+                                 data_weight: float = 1.0, tv_weight: float = 0.0, omit_boundary: bool = False,
+                                 direction="first", outer_padding: Tuple[int, int] = (0, 0)) -> EventShardedObjective:
+    """EventShardedObjective whose stages are the libebos kernels, for the local slice of the events."""
+    from . import _capi, ops
+    from ._capi import check, current_stream, ptr
+
+    H, W = image_size
+    ph, pw = outer_padding
+    tmm = global_time_range(events_local[:, 2])
+    window = ops.PreparedWindow(events_local, (H, W), direction, True, t_min_max=tmm)
+    dev = events_local.device
+    iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=torch.float32, device=dev)
+    g_iwe = torch.empty_like(iwe)
+    dflow = torch.empty((2, H, W), dtype=torch.float32, device=dev)
+    dtv = torch.empty_like(dflow)
+    acc = torch.zeros(8, dtype=torch.float64, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    kind = ops.COST_KINDS[cost]
+    lib = _capi.load()
+
+    def splat(flow):
+        return ops.window_splat(window, flow, outer_padding, out=iwe)
+
+    def cost_fn(img):
+        st = current_stream()
+        check(lib.ebos_iwe_cost(kind, ptr(img), H + 2 * ph, W + 2 * pw, int(omit_boundary), data_weight, ptr(acc),
+                                ptr(g_iwe), st), "ebos_iwe_cost")
+        acc[3] = 0.0
+        check(lib.ebos_loss_finalize(kind, ptr(acc), H + 2 * ph, W + 2 * pw, H, W, int(omit_boundary), data_weight, 0.0,
+                                     ptr(loss), st), "ebos_loss_finalize")
+        return loss.clone(), g_iwe
+
+    def backward(flow, g):
+        dflow.zero_()
+        check(lib.ebos_window_backward(ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), H, W, ph, pw,
+                                       ptr(g), kind, ptr(iwe), ptr(acc), int(omit_boundary), data_weight, ptr(dflow),
+                                       current_stream()), "ebos_window_backward")
+        return dflow
+
+    def regulariser(flow):
+        check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight, ptr(acc), ptr(dtv), current_stream()), "ebos_flow_tv")
+        return (acc[3] * (tv_weight / (2.0 * H * W))).to(torch.float32).reshape(1), dtv
+
+    return EventShardedObjective(splat, cost_fn, backward, regulariser if tv_weight else None)

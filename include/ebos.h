@@ -1,0 +1,193 @@
+/*
+ * ebos.h -- C-ABI of libebos.so: B200 (sm_100a) kernels for the contrast-maximisation hot path of
+ * tub-rip/event_based_bos (warp -> image of warped events -> cost -> analytic backward -> Adam).
+ *
+ * The reference is pure Python and has no FFI; the interface each entry point replaces is the
+ * Python method cited beside it (paths relative to the reference tree).  The ctypes binding a
+ * maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *    the caller owns every buffer, the library allocates nothing persistent;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *    stream-ordered, nothing synchronises unless documented;
+ *  - return value: EBOS_OK (0) or a negative error code; ebos_last_error() gives the text
+ *    (thread-local);  no exceptions, no aborts;
+ *  - `dtype`: EBOS_F32 or EBOS_F64 selects the element type behind `void*` buffers;
+ *  - events are [N,4] array-of-structs rows (x = row, y = col, t, p) exactly as the reference
+ *    passes them; images are row-major [H,W]; flow is [2,H,W] (channel 0 = row flow).
+ *  - arithmetic on coordinates is unfused IEEE (mul then sub, true division) so that pixel
+ *    indices and in-bounds masks are bit-identical to the reference's torch ops.
+ */
+#ifndef EBOS_H_
+#define EBOS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define EBOS_API __attribute__((visibility("default")))
+#else
+#define EBOS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EBOS_VERSION 100
+
+/* error codes */
+#define EBOS_OK 0
+#define EBOS_ERR_BAD_ARG (-1)
+#define EBOS_ERR_CUDA (-2)
+#define EBOS_ERR_WORKSPACE (-3)
+#define EBOS_ERR_UNSUPPORTED (-4)
+
+/* dtypes */
+#define EBOS_F32 0
+#define EBOS_F64 1
+
+/* reference-time selection: Warp.calculate_reftime, src/warp.py:230-262 */
+#define EBOS_DIR_FIRST 0  /* min t */
+#define EBOS_DIR_LAST 1   /* max t */
+#define EBOS_DIR_FRAC 2   /* min t + frac * (max t - min t); 'middle'=0.5, 'before'=-1, 'after'=2 */
+
+/* data objectives (not present upstream) */
+#define EBOS_COST_NONE 0
+#define EBOS_COST_VARIANCE 1  /* L = -var(IWE), unbiased */
+#define EBOS_COST_GRADMAG 2   /* L = -mean((Sobel_x/8)^2 + (Sobel_y/8)^2), replicate border */
+
+/* status word bits written by the kernels into the caller's `status` int32 (device) */
+#define EBOS_STATUS_PIXEL_OOB 1 /* an event's integer pixel is outside the flow grid (reference: gather raises) */
+
+EBOS_API int ebos_version(void);
+EBOS_API const char* ebos_last_error(void);
+/* 1 when a CUDA device is usable from this process, else 0 (never fails). */
+EBOS_API int ebos_device_available(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator level (drop-in for the individual reference operators)
+ * ---------------------------------------------------------------------------------------- */
+
+/* min/max of the timestamp column.  Replaces nt_min/nt_max over events[...,2]
+ * (src/warp.py:218,245-252; src/types/__init__.py:20-47).
+ * out_min_max: [batch,2] of dtype.  events: [batch, n, 4]. */
+EBOS_API int ebos_time_stats(const void* events, int64_t n, int batch, int dtype, void* out_min_max, void* stream);
+
+/* Warp.warp_event(events, flow, "dense-flow", direction) -- src/warp.py:193-228, 264-288, 330-342.
+ * tstats: [batch,2] (min,max) from ebos_time_stats.  dt = t - t_ref; if normalize_t:
+ * dt /= (max(dt)-min(dt)).  k = trunc(x)*W + trunc(y);  x' = x - dt*flow0[k];  y' = y - dt*flow1[k].
+ * warped: [batch,n,4] = (x', y', dt, p).  status: int32[1], OR-ed with EBOS_STATUS_PIXEL_OOB
+ * (such events are passed through un-warped; the Python layer raises like torch.gather does).
+ * flow_batch_stride: elements between consecutive batch flows (0 = shared flow). */
+EBOS_API int ebos_warp_dense_flow(const void* events, int64_t n, int batch, const void* flow, int64_t flow_batch_stride,
+                         int H, int W, const void* tstats, int direction, double direction_frac,
+                         int normalize_t, int dtype, void* warped, int32_t* status, void* stream);
+
+/* Backward of ebos_warp_dense_flow w.r.t. flow: dflow[c][k_i] += -dt_i * grad_warped[i][c], c=0,1.
+ * dflow [batch or 1, 2,H,W] must be zeroed (or hold a running sum) by the caller. */
+EBOS_API int ebos_warp_dense_flow_bwd(const void* events, int64_t n, int batch, int H, int W, const void* tstats,
+                             int direction, double direction_frac, int normalize_t, int dtype,
+                             const void* grad_warped, void* dflow, int64_t dflow_batch_stride, void* stream);
+
+/* Warp.warp_event(events, theta, "2d-translation") -- src/warp.py:344-383:  x' = x + dt*theta0. */
+EBOS_API int ebos_warp_2dof(const void* events, int64_t n, int batch, const void* theta, const void* tstats,
+                   int direction, double direction_frac, int normalize_t, int dtype, void* warped, void* stream);
+
+/* EventImageConverter.bilinear_vote_tensor -- src/event_image_converter.py:562-620.
+ * events: [batch,n,4] (only x,y used).  image: [batch, Hp, Wp] with Hp = H+2*pad_h, Wp = W+2*pad_w
+ * (the CALLER passes the padded size, as EventImageConverter.image_size holds it); fully overwritten.
+ * weight: NULL (1.0) or [batch,n].
+ * floor_bias: the bias added before floor(): 1e-6 for the tensor branch (src/event_image_converter.py:586),
+ * 1e-8 for the numpy branch (src/event_image_converter.py:528).
+ * mode 0 = atomic (fp add order unspecified);  mode 1 = deterministic: bit-identical to the
+ * reference's sequential tap-major scatter_add_ (needs workspace, see ebos_splat_workspace_bytes).
+ * dbg_idx (int64 [batch,4n]) / dbg_mask (uint8 [batch,4n]): optional, the reference's `inds`/`inds_mask`
+ * (src/event_image_converter.py:592-617) for bit-exact checking; NULL to skip. */
+EBOS_API int ebos_iwe_splat(const void* events, int64_t n, int batch, int Hp, int Wp, int pad_h, int pad_w,
+                   const void* weight, double floor_bias, int dtype, int mode, void* image, int64_t* dbg_idx, uint8_t* dbg_mask,
+                   void* workspace, size_t workspace_bytes, void* stream);
+EBOS_API size_t ebos_splat_workspace_bytes(int64_t n, int batch, int Hp, int Wp, int dtype, int mode);
+
+/* Backward of ebos_iwe_splat: grad_events[i] = (dL/dx', dL/dy', 0, 0) and (optional) grad_weight[i],
+ * from grad_image [batch,Hp,Wp].  What autograd derives for src/event_image_converter.py:586-619. */
+EBOS_API int ebos_iwe_splat_bwd(const void* events, int64_t n, int batch, int Hp, int Wp, int pad_h, int pad_w,
+                       const void* weight, double floor_bias, int dtype, const void* grad_image, void* grad_events,
+                       void* grad_weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused contrast-maximisation path (fp32): events of one window are prepared ONCE (sorted by
+ * origin pixel, time-normalised), then every solver iteration runs
+ *    splat (warp+vote fused, warped events never materialised) -> cost -> backward -> [Adam].
+ * ---------------------------------------------------------------------------------------- */
+
+/* Bytes of the caller-owned window buffer / of the temporary workspace used by prepare. */
+EBOS_API size_t ebos_window_bytes(int64_t n);
+EBOS_API size_t ebos_window_workspace_bytes(int64_t n, int H, int W);
+
+/* Build a window from raw events [n,4] fp32: computes t_ref/period on the device
+ * (src/warp.py:230-288), dt_i, k_i, and stores (x, y, dt[, weight]) sorted by k (stable, so the
+ * sensor's time order is kept inside a pixel).  weight: NULL or [n].  status as above.
+ * tminmax: NULL, or float[2] (device) = (min t, max t) to use instead of this call's own
+ * reduction -- for a window whose events are sharded over several GPUs (global min/max). */
+EBOS_API int ebos_window_prepare(const float* events, int64_t n, int H, int W, int direction, double direction_frac,
+                        int normalize_t, const float* weight, const float* tminmax, void* window, void* workspace,
+                        size_t workspace_bytes, int32_t* status, void* stream);
+
+/* Copy the window's event permutation (int32[n]: sorted position -> original event index) and its
+ * time statistics (float[4]: t_ref, period, t_min, t_max) out of the opaque buffer (either may be NULL). */
+EBOS_API int ebos_window_info(const void* window, int64_t n, int32_t* perm_out, float* tinfo_out, void* stream);
+
+/* Fused warp + bilinear vote of a prepared window into iwe [Hp,Wp] (fully overwritten).
+ * `n` and `has_weight` must be the values the window was prepared with. */
+EBOS_API int ebos_window_splat(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
+                      int pad_w, float* iwe, void* stream);
+
+/* Data objective on the IWE: value and gradient.
+ * acc: double[8] device scratch (zeroed by this call).  grad_iwe: [Hp,Wp] written for GRADMAG;
+ * for VARIANCE it may be NULL -- the backward then derives dL/dIWE = c*(IWE-mean) on the fly
+ * from `acc` (pass the same `acc` and `iwe` to ebos_window_backward). */
+EBOS_API int ebos_iwe_cost(int kind, const float* iwe, int Hp, int Wp, int omit_boundary, float scale, double* acc,
+                  float* grad_iwe, void* stream);
+
+/* ImageGradient.calculate_torch -- src/costs/image_gradient.py:60-75 (TV-L1 of the flow with
+ * torch.gradient semantics) value and gradient:  dflow = tv_scale * dTV/dflow  (OVERWRITES dflow,
+ * so it doubles as the zero-fill of the gradient buffer; tv_scale = 0 just zeroes).
+ * weights: NULL (1.0) or [H,W].  acc[3] accumulates the un-normalised |.| sum. */
+EBOS_API int ebos_flow_tv(const float* flow, const float* weights, int H, int W, float tv_scale, double* acc,
+                 float* dflow, void* stream);
+
+/* Analytic backward of the fused splat: re-warps every event, gathers dL/dIWE at
+ * its four taps and accumulates -dt*dL/dx' into dflow[:, k] (ACCUMULATES; run ebos_flow_tv first).
+ * grad_iwe: [Hp,Wp] or NULL with kind == EBOS_COST_VARIANCE (then iwe+acc are used). */
+EBOS_API int ebos_window_backward(const void* window, int64_t n, int has_weight, const float* flow, int H, int W,
+                         int pad_h, int pad_w, const float* grad_iwe, int kind, const float* iwe, const double* acc, int omit_boundary,
+                         float scale, float* dflow, void* stream);
+
+/* loss[0] = data_scale * L_data + tv_scale * TV  from `acc` (float, device). */
+EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W, int omit_boundary,
+                       float data_scale, float tv_scale, float* loss, void* stream);
+
+/* One complete objective evaluation: splat -> cost -> TV -> backward -> loss, stream-ordered,
+ * no host sync (CUDA-graph capturable).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W],
+ * loss float[1], acc double[8]. */
+EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const float* flow, int H, int W,
+                             int pad_h, int pad_w, int kind,
+                             int omit_boundary, float data_scale, float tv_scale, const float* tv_weights,
+                             float* iwe, float* grad_iwe, float* dflow, float* loss, double* acc, void* stream);
+
+/* torch.optim.Adam step (src/solver/patch_eklt_pyramid2.py:262-264,284), in place.  `step` is
+ * 1-based.  Elementwise over n values. */
+EBOS_API int ebos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int step, void* stream);
+
+/* Same, with the step counter read from device memory (`step_dev` int32[1], incremented by the
+ * kernel) so that a captured CUDA graph can be replayed for every iteration. */
+EBOS_API int ebos_adam_step_graph(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                         float beta1, float beta2, float eps, int32_t* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBOS_H_ */

@@ -1,0 +1,195 @@
+"""Operator-level CUDA kernels (through the C-ABI) against the reference goldens and the CPU oracle.
+
+Bars (BASELINE.json north_star):  pixel indices and in-bounds masks bit-exact; deterministic
+sorted-splat IWE bit-exact; atomic-mode IWE within 1e-5 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec
+from tests.conftest import parse_direction
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # north_star tolerance for atomic mode, fp32
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from event_based_bos_b200 import ops as _ops
+
+    return _ops
+
+
+def _case(golden, name):
+    H, W, pad, _ = golden[f"{name}/meta"]
+    return int(H), int(W), int(pad), parse_direction(str(golden[f"{name}/direction"]))
+
+
+def test_warp_bit_exact_vs_reference_golden(golden, ops):
+    for name in golden["warp_cases"]:
+        H, W, pad, direction = _case(golden, name)
+        ev = torch.from_numpy(golden[f"{name}/events"]).cuda()
+        flow = torch.from_numpy(golden[f"{name}/flow"]).cuda()
+        warped = ops.warp_dense_flow(ev, flow, (H, W), direction, normalize_t=True)
+        assert np.array_equal(warped.cpu().numpy(), golden[f"{name}/warped"]), name
+
+
+def test_vote_indices_masks_values_bit_exact(golden, ops):
+    for name in golden["warp_cases"]:
+        H, W, pad, _ = _case(golden, name)
+        warped = torch.from_numpy(golden[f"{name}/warped"])
+        Hp, Wp = H + 2 * pad, W + 2 * pad
+        ref_inds, ref_mask, _ = spec.vote_taps(warped[:, :2], (Hp, Wp), (pad, pad))
+        assert np.array_equal(ref_inds.numpy(), golden[f"{name}/inds"])  # oracle == reference
+        for det in (False, True):
+            iwe, inds, mask = ops.iwe_splat_debug(warped.cuda(), (Hp, Wp), (pad, pad), deterministic=det)
+            assert np.array_equal(inds.cpu().numpy(), golden[f"{name}/inds"]), name
+            assert np.array_equal(mask.cpu().numpy(), ref_mask.numpy()), name
+            if det:  # sorted-splat: bit-identical to the reference's sequential scatter_add_
+                assert np.array_equal(iwe.cpu().numpy(), golden[f"{name}/iwe"]), name
+            else:
+                assert rel_err(iwe.cpu().numpy(), golden[f"{name}/iwe"]) <= REL, name
+
+
+def test_warp_not_normalised_2dof_batched(golden, ops):
+    ev = torch.from_numpy(golden["nonorm/events"]).cuda()
+    w = ops.warp_dense_flow(ev, torch.from_numpy(golden["nonorm/flow"]).cuda(), (32, 48), "first", normalize_t=False)
+    assert np.array_equal(w.cpu().numpy(), golden["nonorm/warped"])
+    w2 = ops.warp_2dof(ev, torch.from_numpy(golden["twodof/theta"]).cuda(), "first", normalize_t=True)
+    assert np.array_equal(w2.cpu().numpy(), golden["twodof/warped"])
+    evb, flb = torch.from_numpy(golden["batched/events"]).cuda(), torch.from_numpy(golden["batched/flow"]).cuda()
+    wb = ops.warp_dense_flow(evb, flb, (32, 48), "middle", normalize_t=True)
+    assert np.array_equal(wb.cpu().numpy(), golden["batched/warped"])
+    ib = ops.iwe_splat(wb, (32, 48), deterministic=True)
+    assert np.array_equal(ib.cpu().numpy(), golden["batched/iwe"])
+    assert rel_err(ops.iwe_splat(wb, (32, 48)).cpu().numpy(), golden["batched/iwe"]) <= REL
+
+
+def test_weighted_vote_and_numpy_branch(golden, ops):
+    ev = torch.from_numpy(golden["weighted/events"]).cuda()
+    wt = torch.from_numpy(golden["weighted/weight"]).cuda()
+    assert np.array_equal(ops.iwe_splat(ev, (48, 64), weight=wt, deterministic=True).cpu().numpy(), golden["weighted/iwe"])
+    assert rel_err(ops.iwe_splat(ev, (48, 64), weight=wt).cpu().numpy(), golden["weighted/iwe"]) <= REL
+    # numpy branch: float64, floor bias 1e-8, np.add.at order == tap-major sequential
+    wn = torch.from_numpy(golden["numpy/warped"]).cuda()
+    img = ops.iwe_splat(wn, (32, 48), deterministic=True, floor_bias=1e-8)
+    assert np.array_equal(img.cpu().numpy(), golden["numpy/iwe_sigma0"])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_inputs_vs_oracle(ops, seed):
+    rng = np.random.default_rng(seed)
+    H, W = int(rng.integers(8, 80)), int(rng.integers(8, 120))
+    n = int(rng.integers(1, 30000))
+    dtype = np.float32 if seed % 3 else np.float64
+    ev = spec.synthetic_events(n, (H, W), seed=seed, dtype=dtype)
+    if seed % 2:  # fractional coordinates, some slightly negative (truncate to pixel 0)
+        ev[:, 0] = np.clip(ev[:, 0] + rng.uniform(-0.9, 0.9, n), -0.9, H - 0.01)
+        ev[:, 1] = np.clip(ev[:, 1] + rng.uniform(-0.9, 0.9, n), -0.9, W - 0.01)
+        ev[ev[:, 0] < 0, 1] = np.abs(ev[ev[:, 0] < 0, 1])  # keep the flat index non-negative
+    flow = spec.synthetic_flow((H, W), seed=seed, max_val=float(rng.uniform(0.5, 25)), dtype=dtype)
+    direction = ["first", "middle", "last", 0.25, "before", "after"][seed % 6]
+    pad = int(seed % 4)
+    tev, tfl = torch.from_numpy(ev), torch.from_numpy(flow)
+    if n < 2:
+        return
+    ref_w = spec.warp_dense_flow(tev, tfl, (H, W), direction, True)
+    w = ops.warp_dense_flow(tev.cuda(), tfl.cuda(), (H, W), direction, True)
+    assert np.array_equal(w.cpu().numpy(), ref_w.numpy(), equal_nan=True)
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    ri, rm, _ = spec.vote_taps(ref_w[:, :2], (Hp, Wp), (pad, pad))
+    iwe, inds, mask = ops.iwe_splat_debug(w, (Hp, Wp), (pad, pad), deterministic=True)
+    assert np.array_equal(inds.cpu().numpy(), ri.numpy()) and np.array_equal(mask.cpu().numpy(), rm.numpy())
+    ref_iwe = spec.bilinear_vote(ref_w, (H, W), (pad, pad))
+    assert np.array_equal(iwe.cpu().numpy(), ref_iwe.numpy())
+    tol = REL if dtype == np.float32 else 1e-12
+    assert rel_err(ops.iwe_splat(w, (Hp, Wp), (pad, pad)).cpu().numpy(), ref_iwe.numpy()) <= tol
+
+
+def test_edge_cases(ops):
+    flow = torch.ones(2, 4, 4).cuda()
+    # all-equal timestamps: period = 0 -> dt = 0/0 = NaN, propagated like upstream (not guarded)
+    ev = torch.tensor([[1.0, 2.0, 0.5, 1.0], [3.0, 1.0, 0.5, 0.0]]).cuda()
+    w = ops.warp_dense_flow(ev, flow, (4, 4), "first", True)
+    assert torch.isnan(w[:, :3]).all()
+    for det in (False, True):
+        iwe = ops.iwe_splat(w, (4, 4), deterministic=det).cpu()
+        ref = spec.bilinear_vote(w.cpu(), (4, 4))
+        assert torch.isnan(iwe[0, 0]) and torch.isfinite(iwe.reshape(-1)[1:]).all()
+        assert np.array_equal(np.isnan(iwe.numpy()), np.isnan(ref.numpy()))
+    # one event
+    one = torch.tensor([[1.25, 2.5, 0.1, 1.0]]).cuda()
+    img = ops.iwe_splat(one, (4, 4), deterministic=True).cpu()
+    assert np.array_equal(img.numpy(), spec.bilinear_vote(one.cpu(), (4, 4)).numpy())
+    # an int direction raises (type(direction) is float upstream)
+    with pytest.raises(ValueError):
+        ops.warp_dense_flow(ev, flow, (4, 4), 1, True)
+    # integer pixel outside the grid: the reference's gather raises
+    bad = torch.tensor([[9.0, 0.0, 0.0, 1.0], [0.0, 0.0, 1.0, 1.0]]).cuda()
+    with pytest.raises(RuntimeError):
+        ops.warp_dense_flow(bad, flow, (4, 4), "first", True)
+    # empty
+    with pytest.raises(RuntimeError):
+        ops.warp_dense_flow(torch.zeros(0, 4).cuda(), flow, (4, 4), "first", True)
+    # a coordinate in (-1, 0) truncates to pixel 0
+    neg = torch.tensor([[-0.5, 0.5, 0.0, 1.0], [0.0, 0.0, 1.0, 1.0]]).cuda()
+    wn = ops.warp_dense_flow(neg, flow, (4, 4), "first", True)
+    assert np.array_equal(wn.cpu().numpy(), spec.warp_dense_flow(neg.cpu(), flow.cpu(), (4, 4)).numpy())
+    # events far outside the image are masked, huge coordinates saturate instead of wrapping
+    far = torch.tensor([[1e20, 3.0, 0, 0], [-1e20, 2.0, 0, 0], [2.0, 1e12, 0, 0], [-5.0, -7.0, 0, 0]]).cuda()
+    assert float(ops.iwe_splat(far, (4, 4)).abs().sum()) == 0.0
+    assert float(ops.iwe_splat(far, (4, 4), deterministic=True).abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-5)])
+def test_autograd_of_operators_vs_oracle(ops, dtype, tol):
+    """d(loss)/d(flow) through warp_dense_flow -> iwe_splat, CUDA analytic backward vs torch autograd
+    on the oracle ops."""
+    H, W, n, pad = 24, 40, 5000, 2
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=3, dtype=npdt))
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=3, max_val=6.0, dtype=npdt))
+    wts = torch.from_numpy(np.random.default_rng(0).uniform(0.5, 1.5, n).astype(npdt))
+    probe = torch.from_numpy(np.random.default_rng(1).standard_normal((H + 2 * pad, W + 2 * pad)).astype(npdt))
+
+    f_ref = flow.clone().requires_grad_()
+    w_ref = wts.clone().requires_grad_()
+    warped = spec.warp_dense_flow(ev, f_ref, (H, W), "middle", True)
+    iwe_ref = spec.bilinear_vote(warped, (H, W), (pad, pad), weight=w_ref)
+    (iwe_ref * probe).sum().backward()
+
+    f = flow.cuda().requires_grad_()
+    wt = wts.cuda().requires_grad_()
+    wd = ops.warp_dense_flow(ev.cuda(), f, (H, W), "middle", True)
+    iwe = ops.iwe_splat(wd, (H + 2 * pad, W + 2 * pad), (pad, pad), weight=wt)
+    (iwe * probe.cuda()).sum().backward()
+    assert rel_err(f.grad.cpu().numpy(), f_ref.grad.numpy()) <= tol
+    assert rel_err(wt.grad.cpu().numpy(), w_ref.grad.numpy()) <= tol
+
+
+def test_full_size_properties(ops):
+    """BASELINE sizes (1280x720, 1 Mi events): size-independent properties instead of a CPU oracle."""
+    H, W, n = 720, 1280, 1 << 20
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=0)).cuda()
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=0)).cuda()
+    w = ops.warp_dense_flow(ev, flow, (H, W), "first", True)
+    iwe = ops.iwe_splat(w, (H, W))
+    det = ops.iwe_splat(w, (H, W), deterministic=True)
+    assert rel_err(iwe.cpu().numpy(), det.cpu().numpy()) <= REL
+    # mass: with a padding that keeps every warped event inside, each event contributes weight 1
+    padded = ops.iwe_splat(w, (H + 16, W + 16), (8, 8)).double().sum().item()
+    assert abs(padded - n) / n < 1e-6
+    # linearity / additivity over disjoint event subsets
+    a, b = ops.iwe_splat(w[: n // 3], (H, W)), ops.iwe_splat(w[n // 3:], (H, W))
+    assert rel_err((a + b).cpu().numpy(), det.cpu().numpy()) <= REL
+    # permutation invariance (atomic mode; deterministic mode depends on event order by design)
+    perm = torch.randperm(n, device="cuda")
+    assert rel_err(ops.iwe_splat(w[perm], (H, W)).cpu().numpy(), det.cpu().numpy()) <= REL
+    # determinism of the sorted mode: identical bits run to run
+    assert torch.equal(det, ops.iwe_splat(w, (H, W), deterministic=True))
