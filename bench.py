@@ -69,6 +69,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def soak(self, fn, min_samples: int = 4, max_s: float = 3.0):
+        """Keep the GPU under the same load until nvidia-smi has produced a few samples (the timed
+        region itself can be shorter than one sampling period)."""
+        t0 = time.perf_counter()
+        while self.proc is not None and len(self.rows) < min_samples and time.perf_counter() - t0 < max_s:
+            for _ in range(20):
+                fn()
+            torch.cuda.synchronize()
+
     def __exit__(self, *a):
         if self.proc is not None:
             self.proc.terminate()
@@ -222,21 +231,22 @@ def run_fused(args, rank, world, local):
         p = _capi.ptr
 
         def splat_only():
-            lib.ebos_window_splat(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, p(ws.iwe), st)
+            lib.ebos_window_splat(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, 0, p(ws.iwe), st)
 
         def bwd_only():
-            lib.ebos_window_backward(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, p(ws.grad_iwe), _capi.COST_GRADMAG,
-                                     p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), st)
+            lib.ebos_window_backward(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, 0, p(ws.grad_iwe),
+                                     _capi.COST_GRADMAG, p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), st)
 
         def cost_only():
-            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws.iwe), H, W, 0, 1.0, p(ws.acc), p(ws.grad_iwe), st)
+            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws.iwe), H, W, 0, 1.0, 0, p(ws.acc), p(ws.grad_iwe), st)
 
         def tv_only():
-            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, p(ws.acc), p(ws.dflow), st)
+            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws.acc), p(ws.dflow), st)
 
         k_ms = {name: cuda_time_ms(fn, args.steps) for name, fn in
                 (("window_splat(+memset)", splat_only), ("window_backward", bwd_only), ("iwe_cost_gradmag", cost_only),
                  ("flow_tv", tv_only))}
+        clocks.soak(step)
     clk = clocks.summary()
 
     # end to end through the public API with host buffers
@@ -319,6 +329,7 @@ def run_solve(args, rank, world, local):
         ms = a.elapsed_time(b) / args.steps
         barrier(world)
         ms = max_over_ranks(ms, world)
+        clocks.soak(lambda: None, max_s=0.5)
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()

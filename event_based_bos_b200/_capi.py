@@ -37,26 +37,26 @@ SIGNATURES = {
     "ebos_splat_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int]),
     "ebos_iwe_splat_bwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_double, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
-    "ebos_window_bytes": (c_size_t, [c_int64]),
+    "ebos_window_bytes": (c_size_t, [c_int64, c_int]),
     "ebos_window_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
-    "ebos_window_prepare": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p,
+    "ebos_window_prepare": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_int,
                                     c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
-    "ebos_window_info": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "ebos_window_splat": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+    "ebos_window_info": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "ebos_window_splat": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),
-    "ebos_iwe_cost": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "ebos_flow_tv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "ebos_window_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
-                                     c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
-    "ebos_loss_finalize": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
-                                   c_void_p]),
+    "ebos_iwe_cost": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "ebos_flow_tv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "ebos_window_backward": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "ebos_loss_finalize": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_int,
+                                   c_void_p, c_void_p]),
     "ebos_cmax_value_and_grad": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                                         c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p]),
-    "ebos_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
-                               c_int, c_void_p]),
-    "ebos_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
-                                     c_float, c_void_p, c_void_p]),
+                                         c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
+    "ebos_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
+                               c_int, c_int, c_void_p]),
+    "ebos_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
+                                     c_double, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

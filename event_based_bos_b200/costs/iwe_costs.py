@@ -30,6 +30,8 @@ class _IweCost(CostBase):
             logger.error(e)
             raise NotImplementedError(e)
         dev = to_device_tensor(iwe)
+        if dev.dtype not in (torch.float32, torch.float64):
+            dev = dev.to(torch.float32)
         loss = ops.iwe_cost(dev, self.kernel_name, omit_boundary)   # minimise-direction value: -contrast
         if loss.device != iwe.device:
             loss = loss.to(iwe.device)

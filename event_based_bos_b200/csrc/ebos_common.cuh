@@ -75,6 +75,19 @@ __device__ __forceinline__ T event_dt(T t, const TimeRef<T>& tr, int normalize_t
   return normalize_t ? Rn<T>::div(d, tr.period) : d;
 }
 
+// ---- order-preserving float <-> unsigned encodings for atomic min/max ---------------------------
+template <typename T> struct Enc;
+template <> struct Enc<float> {
+  using U = unsigned int;
+  static __device__ __forceinline__ U enc(float f) { U b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+  static __device__ __forceinline__ float dec(U u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+};
+template <> struct Enc<double> {
+  using U = unsigned long long;
+  static __device__ __forceinline__ U enc(double f) { U b = (U)__double_as_longlong(f); return (b >> 63) ? ~b : (b | 0x8000000000000000ull); }
+  static __device__ __forceinline__ double dec(U u) { return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u)); }
+};
+
 // ---- bilinear-vote taps ---------------------------------------------------------------------
 // src/event_image_converter.py:586-614.  r/c are the padded integer cell; taps in reference order
 // 0:(r,c) 1:(r+1,c) 2:(r,c+1) 3:(r+1,c+1).
@@ -142,8 +155,8 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 // The header is written by the device (time statistics are never read back by the host); the
 // array offsets are a pure function of n, recomputed on the host by window_layout().
 struct WindowHeader {
-  float t_ref, period, t_min, t_max;
-  unsigned int enc_min, enc_max;  // order-preserving encodings used by the atomic min/max pass
+  double t_ref, period, t_min, t_max;       // stored as double; exact for fp32 windows as well
+  unsigned long long enc_min, enc_max;      // order-preserving encodings used by the atomic min/max pass
 };
 static_assert(sizeof(WindowHeader) <= 256, "header must fit its slot");
 
@@ -152,16 +165,17 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 struct WindowLayout {
   size_t off_x, off_y, off_d, off_w, off_perm, total;
 };
-inline WindowLayout window_layout(int64_t n) {
+inline WindowLayout window_layout(int64_t n, size_t elem) {
   WindowLayout L;
-  size_t a = align256((size_t)n * 4);
+  size_t a = align256((size_t)n * elem);
   L.off_x = 256;
   L.off_y = L.off_x + a;
   L.off_d = L.off_y + a;
   L.off_w = L.off_d + a;
   L.off_perm = L.off_w + a;
-  L.total = L.off_perm + a;
+  L.total = L.off_perm + align256((size_t)n * 4);
   return L;
 }
+inline size_t dtype_size(int dtype) { return dtype == EBOS_F64 ? 8 : 4; }
 
 }  // namespace ebos

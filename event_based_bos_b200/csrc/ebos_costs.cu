@@ -1,4 +1,4 @@
-// Objectives on the IWE / flow planes, Adam, and the fused per-iteration entry point.
+// Objectives on the IWE / flow planes, Adam, and the fused per-iteration entry point (fp32 / fp64).
 //
 //   variance            L = -var(IWE) (unbiased)                    SURVEY.md A.4 (not upstream)
 //   gradient magnitude  L = -mean((Sx/8)^2 + (Sy/8)^2), Sobel 3x3 with replicate padding, kernels of
@@ -14,33 +14,24 @@
 
 namespace ebos {
 
-int window_splat_launch(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                        int pad_w, float* iwe, cudaStream_t st);
-int window_backward_launch(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                           int pad_w, const float* grad_iwe, int kind, const float* iwe, const double* acc,
-                           int omit_boundary, float scale, float* dflow, cudaStream_t st);
+int window_splat_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                        int pad_w, int dtype, void* iwe, cudaStream_t st);
+int window_backward_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                           int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
+                           int omit_boundary, double scale, void* dflow, cudaStream_t st);
 
 // ---- variance: one pass, sum and sum of squares in double --------------------------------------
-__global__ void __launch_bounds__(256) k_var_reduce(const float* __restrict__ iwe, int Hp, int Wp, int omit,
+template <typename T>
+__global__ void __launch_bounds__(256) k_var_reduce(const T* __restrict__ iwe, int Hp, int Wp, int omit,
                                                     double* __restrict__ acc) {
   __shared__ double sm[32];
   const int r_lo = omit ? 1 : 0, r_hi = omit ? Hp - 1 : Hp;
   const int c_lo = omit ? 1 : 0, c_hi = omit ? Wp - 1 : Wp;
-  const int64_t rows = r_hi - r_lo, cols = c_hi - c_lo;
-  const int64_t total = rows > 0 && cols > 0 ? rows * cols : 0;
   double s = 0.0, q = 0.0;
-  if (!omit && (Wp & 3) == 0) {
-    const float4* p4 = reinterpret_cast<const float4*>(iwe);
-    const int64_t n4 = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      float4 v = __ldg(p4 + i);
-      s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-      q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
-    }
-  } else {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-      const int r = r_lo + (int)(i / cols), c = c_lo + (int)(i % cols);
-      const double v = (double)__ldg(iwe + (int64_t)r * Wp + c);
+  for (int r = r_lo + blockIdx.y; r < r_hi; r += gridDim.y) {
+    const T* row = iwe + (int64_t)r * Wp;
+    for (int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x; c < c_hi; c += gridDim.x * blockDim.x) {
+      const double v = (double)__ldg(row + c);
       s += v;
       q += v * v;
     }
@@ -55,32 +46,35 @@ __global__ void __launch_bounds__(256) k_var_reduce(const float* __restrict__ iw
 
 // dL/dIWE for the variance objective as an explicit plane (only needed by the operator-level
 // cost classes; the fused path derives it on the fly inside the backward kernel).
-__global__ void __launch_bounds__(256) k_var_grad(const float* __restrict__ iwe, int Hp, int Wp, int omit, float scale,
-                                                  const double* __restrict__ acc, float* __restrict__ g) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_var_grad(const T* __restrict__ iwe, int Hp, int Wp, int omit, double scale,
+                                                  const double* __restrict__ acc, T* __restrict__ g) {
   const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
-  const float mean = (float)(acc[0] / cnt);
-  const float cv = (float)(-2.0 * (double)scale / (cnt - 1.0));
-  const int64_t total = (int64_t)Hp * Wp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / Wp), c = (int)(i % Wp);
-    const bool border = r == 0 || c == 0 || r == Hp - 1 || c == Wp - 1;
-    g[i] = (omit && border) ? 0.f : cv * (__ldg(iwe + i) - mean);
+  const T mean = (T)(acc[0] / cnt);
+  const T cv = (T)(-2.0 * scale / (cnt - 1.0));
+  for (int r = blockIdx.y; r < Hp; r += gridDim.y) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Wp; c += gridDim.x * blockDim.x) {
+      const bool border = r == 0 || c == 0 || r == Hp - 1 || c == Wp - 1;
+      const int64_t i = (int64_t)r * Wp + c;
+      g[i] = (omit && border) ? (T)0 : cv * (__ldg(iwe + i) - mean);
+    }
   }
 }
 
 // ---- gradient magnitude: Sobel forward + adjoint in one tiled pass ---------------------------------
-constexpr int GT = 32;  // output tile edge
-__global__ void __launch_bounds__(256) k_gradmag(const float* __restrict__ iwe, int Hp, int Wp, int omit, float coef,
-                                                 double* __restrict__ acc, float* __restrict__ g) {
+constexpr int GTH = 16, GTW = 64;  // output tile (rows x cols); 256 threads, 4 pixels each
+template <typename T>
+__global__ void __launch_bounds__(256) k_gradmag(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef,
+                                                 double* __restrict__ acc, T* __restrict__ g) {
   // coef = -2 * scale / (8 * n_el): D = coef * gx is dL/d(Sx) including the forward's 1/8.
-  __shared__ float sI[GT + 4][GT + 4 + 1];
-  __shared__ float sDx[GT + 2][GT + 2 + 1];
-  __shared__ float sDy[GT + 2][GT + 2 + 1];
+  __shared__ T sI[GTH + 4][GTW + 4 + 1];
+  __shared__ T sDx[GTH + 2][GTW + 2 + 1];
+  __shared__ T sDy[GTH + 2][GTW + 2 + 1];
   __shared__ double sm[32];
-  const int r0 = blockIdx.y * GT, c0 = blockIdx.x * GT;
+  const int r0 = blockIdx.y * GTH, c0 = blockIdx.x * GTW;
   // stage 1: image tile with a 2-pixel halo, replicate padding materialised by clamping
-  for (int i = threadIdx.x; i < (GT + 4) * (GT + 4); i += blockDim.x) {
-    const int lr = i / (GT + 4), lc = i % (GT + 4);
+  for (int i = threadIdx.x; i < (GTH + 4) * (GTW + 4); i += blockDim.x) {
+    const int lr = i / (GTW + 4), lc = i - lr * (GTW + 4);
     const int r = min(max(r0 - 2 + lr, 0), Hp - 1), c = min(max(c0 - 2 + lc, 0), Wp - 1);
     sI[lr][lc] = __ldg(iwe + (int64_t)r * Wp + c);
   }
@@ -88,47 +82,56 @@ __global__ void __launch_bounds__(256) k_gradmag(const float* __restrict__ iwe, 
   // stage 2: Sobel/8 on the tile + 1-pixel halo; positions outside the image (or outside the
   // omit_boundary crop) carry no gradient.
   double part = 0.0;
-  for (int i = threadIdx.x; i < (GT + 2) * (GT + 2); i += blockDim.x) {
-    const int lr = i / (GT + 2), lc = i % (GT + 2);
+  for (int i = threadIdx.x; i < (GTH + 2) * (GTW + 2); i += blockDim.x) {
+    const int lr = i / (GTW + 2), lc = i - lr * (GTW + 2);
     const int r = r0 - 1 + lr, c = c0 - 1 + lc;
-    float dx = 0.f, dy = 0.f;
+    T dx = 0, dy = 0;
     const bool inside = r >= 0 && r < Hp && c >= 0 && c < Wp;
     const bool counted = inside && !(omit && (r == 0 || c == 0 || r == Hp - 1 || c == Wp - 1));
     if (counted) {
       // sI index of pixel (r,c) is [lr+1][lc+1]
-      const float i00 = sI[lr][lc], i01 = sI[lr][lc + 1], i02 = sI[lr][lc + 2];
-      const float i10 = sI[lr + 1][lc], i12 = sI[lr + 1][lc + 2];
-      const float i20 = sI[lr + 2][lc], i21 = sI[lr + 2][lc + 1], i22 = sI[lr + 2][lc + 2];
-      const float gx = ((i20 - i00) + 2.f * (i21 - i01) + (i22 - i02)) * 0.125f;  // d/drow
-      const float gy = ((i02 - i00) + 2.f * (i12 - i10) + (i22 - i20)) * 0.125f;  // d/dcol
+      const T i00 = sI[lr][lc], i01 = sI[lr][lc + 1], i02 = sI[lr][lc + 2];
+      const T i10 = sI[lr + 1][lc], i12 = sI[lr + 1][lc + 2];
+      const T i20 = sI[lr + 2][lc], i21 = sI[lr + 2][lc + 1], i22 = sI[lr + 2][lc + 2];
+      const T gx = ((i20 - i00) + (T)2 * (i21 - i01) + (i22 - i02)) * (T)0.125;  // d/drow
+      const T gy = ((i02 - i00) + (T)2 * (i12 - i10) + (i22 - i20)) * (T)0.125;  // d/dcol
       dx = coef * gx;
       dy = coef * gy;
-      if (lr >= 1 && lr <= GT && lc >= 1 && lc <= GT) part += (double)gx * gx + (double)gy * gy;
+      if (lr >= 1 && lr <= GTH && lc >= 1 && lc <= GTW) part += (double)gx * gx + (double)gy * gy;
     }
     sDx[lr][lc] = dx;
     sDy[lr][lc] = dy;
   }
   __syncthreads();
   // stage 3: adjoint.  dI[p] = sum over padded positions pp that clamp to p, over the 3x3 window:
-  //   Kx[u][v]*Dx[pp-(u,v)] + Ky[u][v]*Dy[pp-(u,v)],   with D = 0 outside the image.
-  for (int i = threadIdx.x; i < GT * GT; i += blockDim.x) {
-    const int lr = i / GT, lc = i % GT;
+  //   Kx[u][v]*Dx[pp-(u,v)] + Ky[u][v]*Dy[pp-(u,v)],   with D = 0 outside the image (already zero in
+  //   smem), Kx[u][v] = u*(2-|v|), Ky[u][v] = v*(2-|u|).
+  for (int i = threadIdx.x; i < GTH * GTW; i += blockDim.x) {
+    const int lr = i / GTW, lc = i - lr * GTW;
     const int r = r0 + lr, c = c0 + lc;
     if (r >= Hp || c >= Wp) continue;
-    float out = 0.f;
-    for (int pr = (r == 0 ? -1 : r); pr <= (r == Hp - 1 ? Hp : r); ++pr) {
-      for (int pc = (c == 0 ? -1 : c); pc <= (c == Wp - 1 ? Wp : c); ++pc) {
-#pragma unroll
-        for (int u = -1; u <= 1; ++u) {
-#pragma unroll
-          for (int v = -1; v <= 1; ++v) {
-            const int qr = pr - u, qc = pc - v;
-            if (qr < 0 || qr >= Hp || qc < 0 || qc >= Wp) continue;
-            // Kx[u][v] = u * (2 - |v|),  Ky[u][v] = v * (2 - |u|)
-            const float kx = (float)(u * (2 - (v < 0 ? -v : v)));
-            const float ky = (float)(v * (2 - (u < 0 ? -u : u)));
-            const int sr = qr - (r0 - 1), sc = qc - (c0 - 1);
-            out += kx * sDx[sr][sc] + ky * sDy[sr][sc];
+    T out = 0;
+    if (r > 0 && r < Hp - 1 && c > 0 && c < Wp - 1) {
+      // interior pixel: only pp = p; q = p - (u,v) is inside the image; s index of p is [lr+1][lc+1]
+      const int sr = lr + 1, sc = lc + 1;
+      // u = -1 -> q row r+1 ; u = +1 -> q row r-1
+      out = -(sDx[sr + 1][sc + 1] + (T)2 * sDx[sr + 1][sc] + sDx[sr + 1][sc - 1])
+            + (sDx[sr - 1][sc + 1] + (T)2 * sDx[sr - 1][sc] + sDx[sr - 1][sc - 1])
+            - (sDy[sr + 1][sc + 1] + (T)2 * sDy[sr][sc + 1] + sDy[sr - 1][sc + 1])
+            + (sDy[sr + 1][sc - 1] + (T)2 * sDy[sr][sc - 1] + sDy[sr - 1][sc - 1]);
+    } else {
+      for (int pr = (r == 0 ? -1 : r); pr <= (r == Hp - 1 ? Hp : r); ++pr) {
+        for (int pc = (c == 0 ? -1 : c); pc <= (c == Wp - 1 ? Wp : c); ++pc) {
+          for (int u = -1; u <= 1; ++u) {
+            for (int v = -1; v <= 1; ++v) {
+              const int qr = pr - u, qc = pc - v;
+              if (qr < 0 || qr >= Hp || qc < 0 || qc >= Wp) continue;
+              const int sr = qr - (r0 - 1), sc = qc - (c0 - 1);
+              if (sr < 0 || sr >= GTH + 2 || sc < 0 || sc >= GTW + 2) continue;
+              const T kx = (T)(u * (2 - (v < 0 ? -v : v)));
+              const T ky = (T)(v * (2 - (u < 0 ? -u : u)));
+              out += kx * sDx[sr][sc] + ky * sDy[sr][sc];
+            }
           }
         }
       }
@@ -141,19 +144,21 @@ __global__ void __launch_bounds__(256) k_gradmag(const float* __restrict__ iwe, 
 
 // ---- total variation of the flow: value + gradient -------------------------------------------------
 // torch.gradient (spacing 1, edge_order 1): interior (f[i+1]-f[i-1])/2, edges one-sided.
-__device__ __forceinline__ float grad1d(const float* __restrict__ f, int i, int n, int64_t stride) {
-  if (i == 0) return f[stride] - f[0];
-  if (i == n - 1) return f[(int64_t)(n - 1) * stride] - f[(int64_t)(n - 2) * stride];
-  return (f[(int64_t)(i + 1) * stride] - f[(int64_t)(i - 1) * stride]) * 0.5f;
+template <typename T>
+__device__ __forceinline__ T grad1d(const T* __restrict__ f, int i, int n, int64_t stride) {
+  if (i == 0) return __ldg(f + stride) - __ldg(f);
+  if (i == n - 1) return __ldg(f + (int64_t)(n - 1) * stride) - __ldg(f + (int64_t)(n - 2) * stride);
+  return (__ldg(f + (int64_t)(i + 1) * stride) - __ldg(f + (int64_t)(i - 1) * stride)) * (T)0.5;
 }
-__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+template <typename T>
+__device__ __forceinline__ T sgn(T v) { return (v > (T)0) ? (T)1 : ((v < (T)0) ? (T)-1 : (T)0); }
 
 // adjoint of grad1d along one axis at index i: sum_q s(q) * d grad(q) / d f[i]
-template <typename S>
-__device__ __forceinline__ float grad1d_adjoint(int i, int n, S s) {
-  float out = 0.f;
-  if (i + 1 <= n - 2) out -= 0.5f * s(i + 1);          // interior q = i+1
-  if (i - 1 >= 1) out += 0.5f * s(i - 1);              // interior q = i-1
+template <typename T, typename S>
+__device__ __forceinline__ T grad1d_adjoint(int i, int n, S s) {
+  T out = 0;
+  if (i + 1 <= n - 2) out -= (T)0.5 * s(i + 1);          // interior q = i+1
+  if (i - 1 >= 1) out += (T)0.5 * s(i - 1);              // interior q = i-1
   if (i == 0) out -= s(0);
   if (i == 1) out += s(0);
   if (i == n - 1) out += s(n - 1);
@@ -161,95 +166,87 @@ __device__ __forceinline__ float grad1d_adjoint(int i, int n, S s) {
   return out;
 }
 
-__global__ void __launch_bounds__(256) k_flow_tv(const float* __restrict__ flow, const float* __restrict__ weights, int H,
-                                                 int W, float coef, double* __restrict__ acc, float* __restrict__ dflow) {
+// grid: (ceil(W/256), H, 2 channels); no integer divisions, rows coalesced, neighbours from L1
+template <typename T, bool HAS_WTS>
+__global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, const T* __restrict__ weights, int H, int W,
+                                                 T coef, double* __restrict__ acc, T* __restrict__ dflow) {
   // coef = tv_scale / (2*H*W)
   __shared__ double sm[32];
-  const int64_t hw = (int64_t)H * W;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, ch = blockIdx.z;
   double part = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * hw; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i / hw);
-    const int64_t p = i - (int64_t)ch * hw;
-    const int r = (int)(p / W), c = (int)(p % W);
-    const float* f = flow + (int64_t)ch * hw;
-    auto wgt = [&](int rr, int cc) { return weights ? __ldg(weights + (int64_t)rr * W + cc) : 1.f; };
-    auto s_row = [&](int q) { const float w = wgt(q, c); return sgn(grad1d(f + c, q, H, W) * w) * w; };
-    auto s_col = [&](int q) { const float w = wgt(r, q); return sgn(grad1d(f + (int64_t)r * W, q, W, 1) * w) * w; };
-    const float w_here = wgt(r, c);
-    part += (double)fabsf(grad1d(f + c, r, H, W) * w_here) + (double)fabsf(grad1d(f + (int64_t)r * W, c, W, 1) * w_here);
-    dflow[i] = coef * (grad1d_adjoint(r, H, s_row) + grad1d_adjoint(c, W, s_col));
+  if (c < W) {
+    const T* f = flow + (int64_t)ch * H * W;
+    auto wgt = [&](int rr, int cc) -> T { return HAS_WTS ? __ldg(weights + (int64_t)rr * W + cc) : (T)1; };
+    auto s_row = [&](int q) -> T { const T w = wgt(q, c); return sgn<T>(grad1d<T>(f + c, q, H, W) * w) * w; };
+    auto s_col = [&](int q) -> T { const T w = wgt(r, q); return sgn<T>(grad1d<T>(f + (int64_t)r * W, q, W, 1) * w) * w; };
+    const T w_here = wgt(r, c);
+    const T gr = grad1d<T>(f + c, r, H, W) * w_here, gc = grad1d<T>(f + (int64_t)r * W, c, W, 1) * w_here;
+    part = (double)(gr < 0 ? -gr : gr) + (double)(gc < 0 ? -gc : gc);
+    dflow[(int64_t)ch * H * W + (int64_t)r * W + c] = coef * (grad1d_adjoint<T>(r, H, s_row) + grad1d_adjoint<T>(c, W, s_col));
   }
   part = block_sum(part, sm);
   if (threadIdx.x == 0 && acc) atomicAdd(acc + 3, part);
 }
 
 // ---- loss scalar -------------------------------------------------------------------------------------
+template <typename T>
 __global__ void k_loss_finalize(int kind, const double* __restrict__ acc, int Hp, int Wp, int H, int W, int omit,
-                                float data_scale, float tv_scale, float* __restrict__ loss) {
+                                double data_scale, double tv_scale, T* __restrict__ loss) {
   const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
   double data = 0.0;
   if (kind == EBOS_COST_VARIANCE) data = -((acc[1] - acc[0] * acc[0] / cnt) / (cnt - 1.0));
   else if (kind == EBOS_COST_GRADMAG) data = -(acc[2] / cnt);
   const double tv = acc[3] / (2.0 * (double)H * (double)W);
-  loss[0] = (float)((double)data_scale * data + (double)tv_scale * tv);
+  loss[0] = (T)(data_scale * data + tv_scale * tv);
 }
 
 // ---- Adam ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps,
-                                         float step_size, float inv_bc2_sqrt) {
-  m = m * b1 + (1.f - b1) * g;
-  v = v * b2 + (1.f - b2) * g * g;
-  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+template <typename T>
+__device__ __forceinline__ void adam_one(T& p, T g, T& m, T& v, T b1, T b2, T eps, T step_size, T inv_bc2_sqrt) {
+  m = m * b1 + ((T)1 - b1) * g;
+  v = v * b2 + ((T)1 - b2) * g * g;
+  const T denom = sqrt(v) * inv_bc2_sqrt + eps;
   p -= step_size * (m / denom);
 }
 
-__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                              float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                              int step_host, int32_t* __restrict__ step_dev) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_adam(T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
+                                              T* __restrict__ v, int64_t n, double lr, double b1, double b2, double eps,
+                                              int step_host, const int32_t* __restrict__ step_dev) {
   int step = step_host;
-  if (step_dev) step = *step_dev + 1;  // every thread reads the pre-increment value (bumped by k_adam_bump)
-  const double bc1 = 1.0 - pow((double)b1, (double)step);
-  const double bc2 = 1.0 - pow((double)b2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
-  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  const int64_t n4 = n >> 2;
+  if (step_dev) step = *step_dev + 1;  // pre-increment value; bumped afterwards by k_adam_bump
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2 = 1.0 - pow(b2, (double)step);
+  const T step_size = (T)(lr / bc1);
+  const T inv_bc2_sqrt = (T)(1.0 / sqrt(bc2));
+  const T tb1 = (T)b1, tb2 = (T)b2, teps = (T)eps;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  if ((((size_t)p | (size_t)g | (size_t)m | (size_t)v) & 15) == 0) {
-    for (int64_t i = tid; i < n4; i += nth) {
-      float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
-      adam_one(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, step_size, inv_bc2_sqrt);
-      adam_one(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, step_size, inv_bc2_sqrt);
-      adam_one(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, step_size, inv_bc2_sqrt);
-      adam_one(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, step_size, inv_bc2_sqrt);
-      reinterpret_cast<float4*>(p)[i] = pp;
-      reinterpret_cast<float4*>(m)[i] = mm;
-      reinterpret_cast<float4*>(v)[i] = vv;
-    }
-    for (int64_t i = n4 * 4 + tid; i < n; i += nth) adam_one(p[i], g[i], m[i], v[i], b1, b2, eps, step_size, inv_bc2_sqrt);
-  } else {
-    for (int64_t i = tid; i < n; i += nth) adam_one(p[i], g[i], m[i], v[i], b1, b2, eps, step_size, inv_bc2_sqrt);
+  for (int64_t i = tid; i < n; i += nth) {
+    T pp = p[i], mm = m[i], vv = v[i];
+    adam_one<T>(pp, __ldg(g + i), mm, vv, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+    p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
 __global__ void k_adam_bump(int32_t* step_dev) { *step_dev += 1; }
 
 // ---- launch helpers ----------------------------------------------------------------------------------
-static int plane_grid(int64_t elems, int per_thread = 4) {
-  int64_t blocks = (elems / per_thread + 255) / 256;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sm_count() * 8));
+static dim3 plane_grid2d(int rows, int cols) {
+  int bx = std::max(1, std::min((cols + 255) / 256, 8));
+  int by = std::max(1, std::min(rows, (sm_count() * 8 + bx - 1) / bx));
+  return dim3(bx, by);
 }
 
-int iwe_cost_launch(int kind, const float* iwe, int Hp, int Wp, int omit, float scale, double* acc, float* grad_iwe,
-                    cudaStream_t st) {
+template <typename T>
+int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, double* acc, T* grad_iwe, cudaStream_t st) {
   const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
   if (kind == EBOS_COST_VARIANCE) {
-    k_var_reduce<<<plane_grid((int64_t)Hp * Wp), 256, 0, st>>>(iwe, Hp, Wp, omit, acc);
-    if (grad_iwe) k_var_grad<<<plane_grid((int64_t)Hp * Wp), 256, 0, st>>>(iwe, Hp, Wp, omit, scale, acc, grad_iwe);
+    k_var_reduce<T><<<plane_grid2d(Hp, Wp), 256, 0, st>>>(iwe, Hp, Wp, omit, acc);
+    if (grad_iwe) k_var_grad<T><<<plane_grid2d(Hp, Wp), 256, 0, st>>>(iwe, Hp, Wp, omit, scale, acc, grad_iwe);
   } else if (kind == EBOS_COST_GRADMAG) {
     if (!grad_iwe) { set_error("ebos_iwe_cost: GRADMAG needs grad_iwe"); return EBOS_ERR_BAD_ARG; }
-    const float coef = (float)(-2.0 * (double)scale / (8.0 * cnt));
-    dim3 grid((Wp + GT - 1) / GT, (Hp + GT - 1) / GT);
-    k_gradmag<<<grid, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe);
+    const T coef = (T)(-2.0 * scale / (8.0 * cnt));
+    dim3 grid((Wp + GTW - 1) / GTW, (Hp + GTH - 1) / GTH);
+    k_gradmag<T><<<grid, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe);
   } else if (kind != EBOS_COST_NONE) {
     set_error("ebos_iwe_cost: unknown cost kind");
     return EBOS_ERR_BAD_ARG;
@@ -258,99 +255,145 @@ int iwe_cost_launch(int kind, const float* iwe, int Hp, int Wp, int omit, float 
   return EBOS_OK;
 }
 
-int flow_tv_launch(const float* flow, const float* weights, int H, int W, float tv_scale, double* acc, float* dflow,
-                   cudaStream_t st) {
-  if (tv_scale == 0.f || H < 2 || W < 2) {
-    cudaError_t e = cudaMemsetAsync(dflow, 0, (size_t)2 * H * W * sizeof(float), st);
+template <typename T>
+int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, double* acc, T* dflow, cudaStream_t st) {
+  if (tv_scale == 0.0 || H < 2 || W < 2) {
+    cudaError_t e = cudaMemsetAsync(dflow, 0, (size_t)2 * H * W * sizeof(T), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_flow_tv memset");
-    if (tv_scale == 0.f) return EBOS_OK;
+    if (tv_scale == 0.0) return EBOS_OK;
     set_error("ebos_flow_tv: torch.gradient needs at least 2 samples per axis");
     return EBOS_ERR_BAD_ARG;
   }
-  const float coef = (float)((double)tv_scale / (2.0 * (double)H * (double)W));
-  k_flow_tv<<<plane_grid((int64_t)2 * H * W, 1), 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
+  const T coef = (T)(tv_scale / (2.0 * (double)H * (double)W));
+  dim3 grid((W + 255) / 256, H, 2);
+  if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
+  else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   EBOS_LAUNCH_CHECK("ebos_flow_tv");
   return EBOS_OK;
+}
+
+static int adam_grid(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16));
 }
 
 }  // namespace ebos
 
 using namespace ebos;
 
+#define EBOS_CHECK_DTYPE(dtype, who)                                              \
+  do {                                                                            \
+    if ((dtype) != EBOS_F32 && (dtype) != EBOS_F64) {                             \
+      ebos::set_error(who ": unsupported dtype");                                 \
+      return EBOS_ERR_UNSUPPORTED;                                                \
+    }                                                                             \
+  } while (0)
+
 extern "C" {
 
-int ebos_iwe_cost(int kind, const float* iwe, int Hp, int Wp, int omit_boundary, float scale, double* acc,
-                  float* grad_iwe, void* stream) {
+int ebos_iwe_cost(int kind, const void* iwe, int Hp, int Wp, int omit_boundary, double scale, int dtype, double* acc,
+                  void* grad_iwe, void* stream) {
   EBOS_REQUIRE(iwe && acc && Hp > 0 && Wp > 0, "ebos_iwe_cost: bad argument");
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_iwe_cost: omit_boundary needs an image larger than 2x2");
+  EBOS_CHECK_DTYPE(dtype, "ebos_iwe_cost");
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(acc, 0, 3 * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_iwe_cost memset");
-  return iwe_cost_launch(kind, iwe, Hp, Wp, omit_boundary, scale, acc, grad_iwe, st);
+  if (dtype == EBOS_F64) return iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, scale, acc, (double*)grad_iwe, st);
+  return iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, scale, acc, (float*)grad_iwe, st);
 }
 
-int ebos_flow_tv(const float* flow, const float* weights, int H, int W, float tv_scale, double* acc, float* dflow,
-                 void* stream) {
+int ebos_flow_tv(const void* flow, const void* weights, int H, int W, double tv_scale, int dtype, double* acc,
+                 void* dflow, void* stream) {
   EBOS_REQUIRE(flow && dflow && H > 0 && W > 0, "ebos_flow_tv: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_flow_tv");
   cudaStream_t st = as_stream(stream);
   if (acc) {
     cudaError_t e = cudaMemsetAsync(acc + 3, 0, sizeof(double), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_flow_tv memset");
   }
-  return flow_tv_launch(flow, weights, H, W, tv_scale, acc, dflow, st);
+  if (dtype == EBOS_F64) return flow_tv_t<double>((const double*)flow, (const double*)weights, H, W, tv_scale, acc, (double*)dflow, st);
+  return flow_tv_t<float>((const float*)flow, (const float*)weights, H, W, tv_scale, acc, (float*)dflow, st);
 }
 
-int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W, int omit_boundary, float data_scale,
-                       float tv_scale, float* loss, void* stream) {
+int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W, int omit_boundary, double data_scale,
+                       double tv_scale, int dtype, void* loss, void* stream) {
   EBOS_REQUIRE(acc && loss, "ebos_loss_finalize: bad argument");
-  k_loss_finalize<<<1, 1, 0, as_stream(stream)>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, loss);
+  EBOS_CHECK_DTYPE(dtype, "ebos_loss_finalize");
+  if (dtype == EBOS_F64)
+    k_loss_finalize<double><<<1, 1, 0, as_stream(stream)>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (double*)loss);
+  else
+    k_loss_finalize<float><<<1, 1, 0, as_stream(stream)>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (float*)loss);
   EBOS_LAUNCH_CHECK("ebos_loss_finalize");
   return EBOS_OK;
 }
 
-int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                             int pad_w, int kind, int omit_boundary, float data_scale, float tv_scale,
-                             const float* tv_weights, float* iwe, float* grad_iwe, float* dflow, float* loss, double* acc,
-                             void* stream) {
+int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                             int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
+                             const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
+                             double* acc, void* stream) {
   EBOS_REQUIRE(window && flow && iwe && dflow && loss && acc && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0,
                "ebos_cmax_value_and_grad: bad argument");
   EBOS_REQUIRE(kind == EBOS_COST_VARIANCE || kind == EBOS_COST_GRADMAG, "ebos_cmax_value_and_grad: unknown cost kind");
   EBOS_REQUIRE(kind != EBOS_COST_GRADMAG || grad_iwe, "ebos_cmax_value_and_grad: GRADMAG needs the grad_iwe scratch plane");
+  EBOS_CHECK_DTYPE(dtype, "ebos_cmax_value_and_grad");
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_value_and_grad: omit_boundary needs an image larger than 2x2");
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
-  int rc = window_splat_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, iwe, st);
+  int rc = window_splat_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, iwe, st);
   if (rc) return rc;
   // variance: no gradient plane, the backward derives it from (iwe, acc)
-  rc = iwe_cost_launch(kind, iwe, Hp, Wp, omit_boundary, data_scale, acc, kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr, st);
+  void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
+  if (dtype == EBOS_F64) {
+    rc = iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)gplane, st);
+    if (rc) return rc;
+    rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, st);
+  } else {
+    rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
+    if (rc) return rc;
+    rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, st);
+  }
   if (rc) return rc;
-  rc = flow_tv_launch(flow, tv_weights, H, W, tv_scale, acc, dflow, st);
+  rc = window_backward_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc,
+                              omit_boundary, data_scale, dflow, st);
   if (rc) return rc;
-  rc = window_backward_launch(window, n, has_weight, flow, H, W, pad_h, pad_w,
-                              kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr, kind, iwe, acc, omit_boundary, data_scale,
-                              dflow, st);
-  if (rc) return rc;
-  k_loss_finalize<<<1, 1, 0, st>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, loss);
+  if (dtype == EBOS_F64)
+    k_loss_finalize<double><<<1, 1, 0, st>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (double*)loss);
+  else
+    k_loss_finalize<float><<<1, 1, 0, st>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (float*)loss);
   EBOS_LAUNCH_CHECK("ebos_cmax_value_and_grad");
   return EBOS_OK;
 }
 
-int ebos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                   float beta2, float eps, int step, void* stream) {
+int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr, double beta1,
+                   double beta2, double eps, int step, int dtype, void* stream) {
   EBOS_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "ebos_adam_step: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_adam_step");
   if (n == 0) return EBOS_OK;
-  k_adam<<<plane_grid(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr);
+  if (dtype == EBOS_F64)
+    k_adam<double><<<adam_grid(n), 256, 0, as_stream(stream)>>>((double*)param, (const double*)grad, (double*)exp_avg,
+                                                                 (double*)exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr);
+  else
+    k_adam<float><<<adam_grid(n), 256, 0, as_stream(stream)>>>((float*)param, (const float*)grad, (float*)exp_avg,
+                                                                (float*)exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr);
   EBOS_LAUNCH_CHECK("ebos_adam_step");
   return EBOS_OK;
 }
 
-int ebos_adam_step_graph(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                         float beta1, float beta2, float eps, int32_t* step_dev, void* stream) {
+int ebos_adam_step_graph(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr,
+                         double beta1, double beta2, double eps, int32_t* step_dev, int dtype, void* stream) {
   EBOS_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && n >= 0, "ebos_adam_step_graph: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_adam_step_graph");
   cudaStream_t st = as_stream(stream);
-  if (n > 0) k_adam<<<plane_grid(n), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev);
+  if (n > 0) {
+    if (dtype == EBOS_F64)
+      k_adam<double><<<adam_grid(n), 256, 0, st>>>((double*)param, (const double*)grad, (double*)exp_avg,
+                                                    (double*)exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev);
+    else
+      k_adam<float><<<adam_grid(n), 256, 0, st>>>((float*)param, (const float*)grad, (float*)exp_avg,
+                                                   (float*)exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev);
+  }
   k_adam_bump<<<1, 1, 0, st>>>(step_dev);
   EBOS_LAUNCH_CHECK("ebos_adam_step_graph");
   return EBOS_OK;

@@ -55,19 +55,6 @@ __device__ __forceinline__ void load_xy(const double* ev, int64_t i, double& x, 
   x = v.x; y = v.y;
 }
 
-// ---- order-preserving float <-> unsigned encodings for atomic min/max --------------------------
-template <typename T> struct Enc;
-template <> struct Enc<float> {
-  using U = unsigned int;
-  static __device__ __forceinline__ U enc(float f) { U b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
-  static __device__ __forceinline__ float dec(U u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
-};
-template <> struct Enc<double> {
-  using U = unsigned long long;
-  static __device__ __forceinline__ U enc(double f) { U b = (U)__double_as_longlong(f); return (b >> 63) ? ~b : (b | 0x8000000000000000ull); }
-  static __device__ __forceinline__ double dec(U u) { return __longlong_as_double((long long)((u >> 63) ? (u & 0x7fffffffffffffffull) : ~u)); }
-};
-
 template <typename T>
 __global__ void k_tstats_init(typename Enc<T>::U* out, int batch) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,4 +1,4 @@
-// Fused contrast-maximisation path on a prepared window (fp32).
+// Fused contrast-maximisation path on a prepared window (fp32 fast path, fp64 parity path).
 //
 //   prepare (once per window):  time stats -> dt -> origin pixel key -> stable sort by key -> SoA
 //   splat   (every iteration):  stream the pixel-sorted SoA, gather flow, warp, bilinear vote.
@@ -13,6 +13,8 @@
 // Reference semantics: src/warp.py:283-287,333-337 and src/event_image_converter.py:586-619
 // (SURVEY.md A.1-A.3).  Coordinate arithmetic is unfused so cells/masks match the reference bit
 // for bit; only the floating-point ADD ORDER into a pixel differs (atomic mode, 1e-5 relative).
+// The reference's solvers run in float64 (src/solver/patch_eklt_pyramid2.py:253); the fp64
+// instantiation is the dtype-faithful path used for solve-level parity.
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -20,61 +22,64 @@
 
 namespace ebos {
 
-constexpr int kSplatEpt = 8;  // events per thread, forward
-constexpr int kBwdEpt = 4;    // events per thread, backward
+
+// events per thread (consecutive, so that runs can be combined in registers)
+template <typename T> struct Ept;
+template <> struct Ept<float> { static constexpr int splat = 8, bwd = 4; };
+template <> struct Ept<double> { static constexpr int splat = 4, bwd = 4; };
 
 // ---- prepare --------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int enc_f32(float f) {
-  unsigned int b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float dec_f32(unsigned int u) {
-  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
 __global__ void k_win_hdr_init(WindowHeader* h) {
-  h->enc_min = 0xffffffffu;
-  h->enc_max = 0u;
+  h->enc_min = ~0ull;
+  h->enc_max = 0ull;
 }
 
-__global__ void __launch_bounds__(256) k_win_minmax(const float* __restrict__ ev, int64_t n, WindowHeader* h) {
-  unsigned int lo = 0xffffffffu, hi = 0u;
+template <typename T>
+__global__ void __launch_bounds__(256) k_win_minmax(const T* __restrict__ ev, int64_t n, WindowHeader* h) {
+  using U = typename Enc<T>::U;
+  U lo = ~(U)0, hi = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    unsigned int u = enc_f32(__ldg(ev + 4 * i + 2));
-    lo = min(lo, u);
-    hi = max(hi, u);
+    U u = Enc<T>::enc(__ldg(ev + 4 * i + 2));
+    lo = u < lo ? u : lo;
+    hi = u > hi ? u : hi;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    U l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicMin(&h->enc_min, lo);
-    atomicMax(&h->enc_max, hi);
+    // both encodings are order preserving, so the 64-bit slots can hold either width
+    atomicMin(&h->enc_min, (unsigned long long)lo);
+    atomicMax(&h->enc_max, (unsigned long long)hi);
   }
 }
 
-__global__ void k_win_hdr_final(WindowHeader* h, int direction, double frac, const float* __restrict__ tminmax) {
-  float tmin = tminmax ? tminmax[0] : dec_f32(h->enc_min), tmax = tminmax ? tminmax[1] : dec_f32(h->enc_max);
-  TimeRef<float> tr = make_time_ref<float>(tmin, tmax, direction, frac);
-  h->t_min = tmin;
-  h->t_max = tmax;
-  h->t_ref = tr.t_ref;
-  h->period = tr.period;
+template <typename T>
+__global__ void k_win_hdr_final(WindowHeader* h, int direction, double frac, const T* __restrict__ tminmax) {
+  using U = typename Enc<T>::U;
+  T tmin = tminmax ? tminmax[0] : Enc<T>::dec((U)h->enc_min);
+  T tmax = tminmax ? tminmax[1] : Enc<T>::dec((U)h->enc_max);
+  TimeRef<T> tr = make_time_ref<T>(tmin, tmax, direction, frac);
+  h->t_min = (double)tmin;
+  h->t_max = (double)tmax;
+  h->t_ref = (double)tr.t_ref;
+  h->period = (double)tr.period;
 }
 
 // key = origin pixel k (src/warp.py:334); an event whose k is outside the grid is flagged and
 // parked behind all valid pixels.
-__global__ void __launch_bounds__(256) k_win_keys(const float* __restrict__ ev, int64_t n, int H, int W,
+template <typename T>
+__global__ void __launch_bounds__(256) k_win_keys(const T* __restrict__ ev, int64_t n, int H, int W,
                                                   unsigned int* __restrict__ keys, int* __restrict__ idx,
                                                   int32_t* __restrict__ status) {
   const int64_t hw = (int64_t)H * W;
   bool bad = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float2 xy = __ldg(reinterpret_cast<const float2*>(ev) + 2 * i);
-    int64_t k = (int64_t)xy.x * W + (int64_t)xy.y;
-    bool ok = k >= 0 && k < hw && fabsf(xy.x) <= FLT_MAX && fabsf(xy.y) <= FLT_MAX;
+    T x = __ldg(ev + 4 * i), y = __ldg(ev + 4 * i + 1);
+    int64_t k = (int64_t)x * W + (int64_t)y;
+    bool ok = k >= 0 && k < hw && Rn<T>::finite(x) && Rn<T>::finite(y);
     bad |= !ok;
     keys[i] = ok ? (unsigned int)k : (unsigned int)hw;
     idx[i] = (int)i;
@@ -82,179 +87,162 @@ __global__ void __launch_bounds__(256) k_win_keys(const float* __restrict__ ev, 
   if (bad) atomicOr(status, EBOS_STATUS_PIXEL_OOB);
 }
 
-__global__ void __launch_bounds__(256) k_win_gather(const float* __restrict__ ev, const float* __restrict__ weight,
-                                                    int64_t n, int H, int W, const int* __restrict__ perm,
+template <typename T>
+__global__ void __launch_bounds__(256) k_win_gather(const T* __restrict__ ev, const T* __restrict__ weight, int64_t n,
+                                                    int H, int W, const int* __restrict__ perm,
                                                     const WindowHeader* __restrict__ h, int normalize_t,
-                                                    float* __restrict__ sx, float* __restrict__ sy,
-                                                    float* __restrict__ sd, float* __restrict__ sw) {
-  TimeRef<float> tr{h->t_ref, h->period};
+                                                    T* __restrict__ sx, T* __restrict__ sy, T* __restrict__ sd,
+                                                    T* __restrict__ sw) {
+  TimeRef<T> tr{(T)h->t_ref, (T)h->period};
   const int64_t hw = (int64_t)H * W;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    int i = __ldg(perm + j);
-    float4 e = __ldg(reinterpret_cast<const float4*>(ev) + i);
-    int64_t k = (int64_t)e.x * W + (int64_t)e.y;
-    bool ok = k >= 0 && k < hw && fabsf(e.x) <= FLT_MAX && fabsf(e.y) <= FLT_MAX;
+    const int64_t i = __ldg(perm + j);
+    const T x = __ldg(ev + 4 * i), y = __ldg(ev + 4 * i + 1), t = __ldg(ev + 4 * i + 2);
+    int64_t k = (int64_t)x * W + (int64_t)y;
+    bool ok = k >= 0 && k < hw && Rn<T>::finite(x) && Rn<T>::finite(y);
     // invalid events are parked at a coordinate whose k is negative: the kernels skip them.
-    sx[j] = ok ? e.x : -2.0f;
-    sy[j] = ok ? e.y : -2.0f;
-    sd[j] = event_dt<float>(e.z, tr, normalize_t);
+    sx[j] = ok ? x : (T)-2;
+    sy[j] = ok ? y : (T)-2;
+    sd[j] = event_dt<T>(t, tr, normalize_t);
     if (sw) sw[j] = __ldg(weight + i);
   }
 }
 
+// ---- per-thread event block loads ---------------------------------------------------------------
+__device__ __forceinline__ void load4(const float* p, float* o) {
+  float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double* o) {
+  double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <typename T, int EPT>
+__device__ __forceinline__ void load_block(const T* __restrict__ p, int64_t base, int64_t n, T fill, T (&out)[EPT]) {
+  if (base + EPT <= n) {
+#pragma unroll
+    for (int j = 0; j < EPT; j += 4) load4(p + base + j, out + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) out[j] = (base + j < n) ? p[base + j] : fill;
+  }
+}
+
 // ---- forward: fused warp + bilinear vote -----------------------------------------------------
-__device__ __forceinline__ void flush_cell(float* __restrict__ iwe, int Hp, int Wp, int r, int c, float a0, float a1,
-                                           float a2, float a3) {
+template <typename T>
+__device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, int r, int c, T a0, T a1, T a2, T a3) {
   const bool r0 = (unsigned)r < (unsigned)Hp, r1 = (unsigned)(r + 1) < (unsigned)Hp;
   const bool c0 = (unsigned)c < (unsigned)Wp, c1 = (unsigned)(c + 1) < (unsigned)Wp;
-  float* p = iwe + (int64_t)r * Wp + c;
+  T* p = iwe + (int64_t)r * Wp + c;
   if (r0 & c0) red_add(p, a0);
   if (r1 & c0) red_add(p + Wp, a1);
   if (r0 & c1) red_add(p + 1, a2);
   if (r1 & c1) red_add(p + Wp + 1, a3);
 }
 
-template <bool HAS_W>
-__global__ void __launch_bounds__(256) k_win_splat(const float* __restrict__ sx, const float* __restrict__ sy,
-                                                   const float* __restrict__ sd, const float* __restrict__ sw,
-                                                   int64_t n, const float* __restrict__ flow, int H, int W, int pad_h,
-                                                   int pad_w, float* __restrict__ iwe) {
-  constexpr int EPT = kSplatEpt;
+template <typename T, bool HAS_W>
+__global__ void __launch_bounds__(256) k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy,
+                                                   const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
+                                                   const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
+                                                   T* __restrict__ iwe) {
+  constexpr int EPT = Ept<T>::splat;
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   const int hw = H * W;
-  float x[EPT], y[EPT], d[EPT], wt[EPT];
-  if (base + EPT <= n) {
-#pragma unroll
-    for (int j = 0; j < EPT; j += 4) {
-      float4 vx = __ldg(reinterpret_cast<const float4*>(sx + base + j));
-      float4 vy = __ldg(reinterpret_cast<const float4*>(sy + base + j));
-      float4 vd = __ldg(reinterpret_cast<const float4*>(sd + base + j));
-      x[j] = vx.x; x[j + 1] = vx.y; x[j + 2] = vx.z; x[j + 3] = vx.w;
-      y[j] = vy.x; y[j + 1] = vy.y; y[j + 2] = vy.z; y[j + 3] = vy.w;
-      d[j] = vd.x; d[j + 1] = vd.y; d[j + 2] = vd.z; d[j + 3] = vd.w;
-      if (HAS_W) {
-        float4 vw = __ldg(reinterpret_cast<const float4*>(sw + base + j));
-        wt[j] = vw.x; wt[j + 1] = vw.y; wt[j + 2] = vw.z; wt[j + 3] = vw.w;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      const bool in = base + j < n;
-      x[j] = in ? sx[base + j] : -2.0f;
-      y[j] = in ? sy[base + j] : -2.0f;
-      d[j] = in ? sd[base + j] : 0.0f;
-      if (HAS_W) wt[j] = in ? sw[base + j] : 0.0f;
-    }
-  }
+  T x[EPT], y[EPT], d[EPT], wt[EPT];
+  load_block<T, EPT>(sx, base, n, (T)-2, x);
+  load_block<T, EPT>(sy, base, n, (T)-2, y);
+  load_block<T, EPT>(sd, base, n, (T)0, d);
+  if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
   int cr = INT_MIN, cc = INT_MIN;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
     const int k = (int)x[j] * W + (int)y[j];
     if ((unsigned)k >= (unsigned)hw) continue;  // parked (invalid) event or tail
-    const float xw = __fsub_rn(x[j], __fmul_rn(d[j], __ldg(flow + k)));
-    const float yw = __fsub_rn(y[j], __fmul_rn(d[j], __ldg(flow + hw + k)));
-    Taps<float> t = make_taps<float>(xw, yw, pad_h, pad_w);
+    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
+    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
+    Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
     if (HAS_W) {
-      t.w0 = __fmul_rn(t.w0, wt[j]); t.w1 = __fmul_rn(t.w1, wt[j]);
-      t.w2 = __fmul_rn(t.w2, wt[j]); t.w3 = __fmul_rn(t.w3, wt[j]);
+      t.w0 = Rn<T>::mul(t.w0, wt[j]); t.w1 = Rn<T>::mul(t.w1, wt[j]);
+      t.w2 = Rn<T>::mul(t.w2, wt[j]); t.w3 = Rn<T>::mul(t.w3, wt[j]);
     }
-    if (!(fabsf(xw) <= FLT_MAX && fabsf(yw) <= FLT_MAX)) {
+    if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) {
       // non-finite warped coordinate (e.g. zero-length window: dt = 0/0): the reference masks all
       // four taps and adds vals*0 = NaN to pixel 0.
-      red_add(iwe, __fmul_rn(t.w0, 0.0f));
+      red_add(iwe, Rn<T>::mul(t.w0, (T)0));
       continue;
     }
     if (t.r != cr || t.c != cc) {
-      if (cr != INT_MIN) flush_cell(iwe, Hp, Wp, cr, cc, a0, a1, a2, a3);
+      if (cr != INT_MIN) flush_cell<T>(iwe, Hp, Wp, cr, cc, a0, a1, a2, a3);
       cr = t.r; cc = t.c;
       a0 = t.w0; a1 = t.w1; a2 = t.w2; a3 = t.w3;
     } else {
       a0 += t.w0; a1 += t.w1; a2 += t.w2; a3 += t.w3;
     }
   }
-  if (cr != INT_MIN) flush_cell(iwe, Hp, Wp, cr, cc, a0, a1, a2, a3);
+  if (cr != INT_MIN) flush_cell<T>(iwe, Hp, Wp, cr, cc, a0, a1, a2, a3);
 }
 
 // ---- backward ------------------------------------------------------------------------------------
 // GSRC 0: dL/dIWE read from a plane.  GSRC 1: variance objective, dL/dIWE = cv * (IWE - mean)
 // derived on the fly from the IWE itself (saves writing and re-reading a gradient plane).
-struct VarCoef { float mean, cv; int omit; };
+template <typename T> struct VarCoef { T mean, cv; int omit; };
 
-template <int GSRC>
-__device__ __forceinline__ float fetch_g(const float* __restrict__ g, int Hp, int Wp, int r, int c, const VarCoef& vc) {
-  if ((unsigned)r >= (unsigned)Hp || (unsigned)c >= (unsigned)Wp) return 0.f;
-  float v = __ldg(g + (int64_t)r * Wp + c);
+template <typename T, int GSRC>
+__device__ __forceinline__ T fetch_g(const T* __restrict__ g, int Hp, int Wp, int r, int c, const VarCoef<T>& vc) {
+  if ((unsigned)r >= (unsigned)Hp || (unsigned)c >= (unsigned)Wp) return (T)0;
+  T v = __ldg(g + (int64_t)r * Wp + c);
   if (GSRC == 1) {
-    if (vc.omit && (r == 0 || c == 0 || r == Hp - 1 || c == Wp - 1)) return 0.f;
+    if (vc.omit && (r == 0 || c == 0 || r == Hp - 1 || c == Wp - 1)) return (T)0;
     v = vc.cv * (v - vc.mean);
   }
   return v;
 }
 
-template <int GSRC, bool HAS_W>
-__global__ void __launch_bounds__(256) k_win_bwd(const float* __restrict__ sx, const float* __restrict__ sy,
-                                                 const float* __restrict__ sd, const float* __restrict__ sw, int64_t n,
-                                                 const float* __restrict__ flow, int H, int W, int pad_h, int pad_w,
-                                                 const float* __restrict__ g, const double* __restrict__ acc, int omit,
-                                                 float scale, float* __restrict__ dflow) {
-  constexpr int EPT = kBwdEpt;
+template <typename T, int GSRC, bool HAS_W>
+__global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy,
+                                                 const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
+                                                 const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
+                                                 const T* __restrict__ g, const double* __restrict__ acc, int omit,
+                                                 double scale, T* __restrict__ dflow) {
+  constexpr int EPT = Ept<T>::bwd;
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   const int hw = H * W;
-  VarCoef vc{0.f, 0.f, omit};
+  VarCoef<T> vc{(T)0, (T)0, omit};
   if (GSRC == 1) {
     const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
-    const double mean = acc[0] / cnt;
-    vc.mean = (float)mean;
-    vc.cv = (float)(-2.0 * (double)scale / (cnt - 1.0));
+    vc.mean = (T)(acc[0] / cnt);
+    vc.cv = (T)(-2.0 * scale / (cnt - 1.0));
   }
-  float x[EPT], y[EPT], d[EPT], wt[EPT];
-  if (base + EPT <= n) {
-    float4 vx = __ldg(reinterpret_cast<const float4*>(sx + base));
-    float4 vy = __ldg(reinterpret_cast<const float4*>(sy + base));
-    float4 vd = __ldg(reinterpret_cast<const float4*>(sd + base));
-    x[0] = vx.x; x[1] = vx.y; x[2] = vx.z; x[3] = vx.w;
-    y[0] = vy.x; y[1] = vy.y; y[2] = vy.z; y[3] = vy.w;
-    d[0] = vd.x; d[1] = vd.y; d[2] = vd.z; d[3] = vd.w;
-    if (HAS_W) {
-      float4 vw = __ldg(reinterpret_cast<const float4*>(sw + base));
-      wt[0] = vw.x; wt[1] = vw.y; wt[2] = vw.z; wt[3] = vw.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      const bool in = base + j < n;
-      x[j] = in ? sx[base + j] : -2.0f;
-      y[j] = in ? sy[base + j] : -2.0f;
-      d[j] = in ? sd[base + j] : 0.0f;
-      if (HAS_W) wt[j] = in ? sw[base + j] : 0.0f;
-    }
-  }
+  T x[EPT], y[EPT], d[EPT], wt[EPT];
+  load_block<T, EPT>(sx, base, n, (T)-2, x);
+  load_block<T, EPT>(sy, base, n, (T)-2, y);
+  load_block<T, EPT>(sd, base, n, (T)0, d);
+  if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
   int ck = -1;
-  float s0 = 0.f, s1 = 0.f;
+  T s0 = 0, s1 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
     const int k = (int)x[j] * W + (int)y[j];
     if ((unsigned)k >= (unsigned)hw) continue;
-    const float xw = __fsub_rn(x[j], __fmul_rn(d[j], __ldg(flow + k)));
-    const float yw = __fsub_rn(y[j], __fmul_rn(d[j], __ldg(flow + hw + k)));
-    if (!(fabsf(xw) <= FLT_MAX && fabsf(yw) <= FLT_MAX)) continue;  // all taps masked: zero gradient
-    const Taps<float> t = make_taps<float>(xw, yw, pad_h, pad_w);
-    const float g00 = fetch_g<GSRC>(g, Hp, Wp, t.r, t.c, vc);
-    const float g10 = fetch_g<GSRC>(g, Hp, Wp, t.r + 1, t.c, vc);
-    const float g01 = fetch_g<GSRC>(g, Hp, Wp, t.r, t.c + 1, vc);
-    const float g11 = fetch_g<GSRC>(g, Hp, Wp, t.r + 1, t.c + 1, vc);
-    float dx = (1.f - t.b) * (g10 - g00) + t.b * (g11 - g01);
-    float dy = (1.f - t.a) * (g01 - g00) + t.a * (g11 - g10);
+    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
+    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
+    if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) continue;  // all taps masked: zero gradient
+    const Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
+    const T g00 = fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c, vc);
+    const T g10 = fetch_g<T, GSRC>(g, Hp, Wp, t.r + 1, t.c, vc);
+    const T g01 = fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c + 1, vc);
+    const T g11 = fetch_g<T, GSRC>(g, Hp, Wp, t.r + 1, t.c + 1, vc);
+    T dx = ((T)1 - t.b) * (g10 - g00) + t.b * (g11 - g01);
+    T dy = ((T)1 - t.a) * (g01 - g00) + t.a * (g11 - g10);
     if (HAS_W) { dx *= wt[j]; dy *= wt[j]; }
     if (k != ck) {
       if (ck >= 0) { red_add(dflow + ck, s0); red_add(dflow + hw + ck, s1); }
-      ck = k; s0 = 0.f; s1 = 0.f;
+      ck = k; s0 = 0; s1 = 0;
     }
     s0 -= d[j] * dx;
     s1 -= d[j] * dy;
@@ -282,80 +270,14 @@ static PrepWs prep_ws(int64_t n) {
   return w;
 }
 
-int window_splat_launch(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                        int pad_w, float* iwe, cudaStream_t st) {
-  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
-  cudaError_t e = cudaMemsetAsync(iwe, 0, (size_t)Hp * Wp * sizeof(float), st);
-  if (e != cudaSuccess) return cuda_fail(e, "ebos_window_splat memset");
-  if (n == 0) return EBOS_OK;
-  WindowLayout L = window_layout(n);
-  const char* b = reinterpret_cast<const char*>(window);
-  const float* sx = reinterpret_cast<const float*>(b + L.off_x);
-  const float* sy = reinterpret_cast<const float*>(b + L.off_y);
-  const float* sd = reinterpret_cast<const float*>(b + L.off_d);
-  const float* sw = reinterpret_cast<const float*>(b + L.off_w);
-  int64_t threads = (n + kSplatEpt - 1) / kSplatEpt;
-  unsigned grid = (unsigned)((threads + 255) / 256);
-  if (has_weight) k_win_splat<true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);
-  else k_win_splat<false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);
-  EBOS_LAUNCH_CHECK("ebos_window_splat");
-  return EBOS_OK;
-}
-
-int window_backward_launch(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                           int pad_w, const float* grad_iwe, int kind, const float* iwe, const double* acc,
-                           int omit_boundary, float scale, float* dflow, cudaStream_t st) {
-  if (n == 0) return EBOS_OK;
-  WindowLayout L = window_layout(n);
-  const char* b = reinterpret_cast<const char*>(window);
-  const float* sx = reinterpret_cast<const float*>(b + L.off_x);
-  const float* sy = reinterpret_cast<const float*>(b + L.off_y);
-  const float* sd = reinterpret_cast<const float*>(b + L.off_d);
-  const float* sw = reinterpret_cast<const float*>(b + L.off_w);
-  int64_t threads = (n + kBwdEpt - 1) / kBwdEpt;
-  unsigned grid = (unsigned)((threads + 255) / 256);
-  const bool affine = grad_iwe == nullptr;
-  if (affine) {
-    if (kind != EBOS_COST_VARIANCE || !iwe || !acc) {
-      set_error("ebos_window_backward: grad_iwe == NULL needs kind == VARIANCE with iwe and acc");
-      return EBOS_ERR_BAD_ARG;
-    }
-    if (has_weight) k_win_bwd<1, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe, acc, omit_boundary, scale, dflow);
-    else k_win_bwd<1, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe, acc, omit_boundary, scale, dflow);
-  } else {
-    if (has_weight) k_win_bwd<0, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, grad_iwe, acc, omit_boundary, scale, dflow);
-    else k_win_bwd<0, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, grad_iwe, acc, omit_boundary, scale, dflow);
-  }
-  EBOS_LAUNCH_CHECK("ebos_window_backward");
-  return EBOS_OK;
-}
-
-}  // namespace ebos
-
-using namespace ebos;
-
-extern "C" {
-
-size_t ebos_window_bytes(int64_t n) { return n < 0 ? 0 : window_layout(n).total; }
-
-size_t ebos_window_workspace_bytes(int64_t n, int H, int W) {
-  (void)H; (void)W;
-  return n < 0 ? 0 : prep_ws(n).total;
-}
-
-int ebos_window_prepare(const float* events, int64_t n, int H, int W, int direction, double direction_frac,
-                        int normalize_t, const float* weight, const float* tminmax, void* window, void* workspace,
-                        size_t workspace_bytes, int32_t* status, void* stream) {
-  EBOS_REQUIRE(n >= 0 && n < (int64_t)INT_MAX && H > 0 && W > 0 && window && status && (n == 0 || events),
-               "ebos_window_prepare: bad argument");
-  EBOS_REQUIRE((int64_t)H * W < ((int64_t)1 << 31) - 1, "ebos_window_prepare: grid too large");
-  EBOS_REQUIRE(direction >= EBOS_DIR_FIRST && direction <= EBOS_DIR_FRAC, "ebos_window_prepare: bad direction");
-  EBOS_REQUIRE((reinterpret_cast<size_t>(window) & 255) == 0, "ebos_window_prepare: window buffer must be 256-byte aligned");
-  cudaStream_t st = as_stream(stream);
+template <typename T>
+int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction, double direction_frac, int normalize_t,
+                        const T* weight, const T* tminmax, void* window, void* workspace, size_t workspace_bytes,
+                        int32_t* status, cudaStream_t st) {
   WindowHeader* hdr = reinterpret_cast<WindowHeader*>(window);
   k_win_hdr_init<<<1, 1, 0, st>>>(hdr);
   if (n == 0) {
-    k_win_hdr_final<<<1, 1, 0, st>>>(hdr, direction, direction_frac, tminmax);
+    k_win_hdr_final<T><<<1, 1, 0, st>>>(hdr, direction, direction_frac, tminmax);
     EBOS_LAUNCH_CHECK("ebos_window_prepare");
     return EBOS_OK;
   }
@@ -366,52 +288,163 @@ int ebos_window_prepare(const float* events, int64_t n, int H, int W, int direct
   unsigned int* k_out = reinterpret_cast<unsigned int*>(wp + ws.off_kout);
   int* i_in = reinterpret_cast<int*>(wp + ws.off_iin);
   void* cub_tmp = wp + ws.off_cub;
-  WindowLayout L = window_layout(n);
+  WindowLayout L = window_layout(n, sizeof(T));
   char* b = reinterpret_cast<char*>(window);
   int* perm = reinterpret_cast<int*>(b + L.off_perm);
   int bx = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
-  if (!tminmax) k_win_minmax<<<bx, 256, 0, st>>>(events, n, hdr);
-  k_win_hdr_final<<<1, 1, 0, st>>>(hdr, direction, direction_frac, tminmax);
-  k_win_keys<<<bx, 256, 0, st>>>(events, n, H, W, k_in, i_in, status);
+  if (!tminmax) k_win_minmax<T><<<bx, 256, 0, st>>>(events, n, hdr);
+  k_win_hdr_final<T><<<1, 1, 0, st>>>(hdr, direction, direction_frac, tminmax);
+  k_win_keys<T><<<bx, 256, 0, st>>>(events, n, H, W, k_in, i_in, status);
   size_t cub_bytes = ws.cub_bytes;
   cudaError_t ce = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k_in, k_out, i_in, perm, (int)n, 0,
                                                    key_bits_for((int64_t)H * W), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "ebos_window_prepare(sort)");
-  k_win_gather<<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
-                                   reinterpret_cast<float*>(b + L.off_x), reinterpret_cast<float*>(b + L.off_y),
-                                   reinterpret_cast<float*>(b + L.off_d),
-                                   weight ? reinterpret_cast<float*>(b + L.off_w) : nullptr);
+  k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
+                                      reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
+                                      reinterpret_cast<T*>(b + L.off_d),
+                                      weight ? reinterpret_cast<T*>(b + L.off_w) : nullptr);
   EBOS_LAUNCH_CHECK("ebos_window_prepare");
   return EBOS_OK;
 }
 
-int ebos_window_info(const void* window, int64_t n, int32_t* perm_out, float* tinfo_out, void* stream) {
+template <typename T>
+int window_splat_t(const void* window, int64_t n, int has_weight, const T* flow, int H, int W, int pad_h, int pad_w,
+                   T* iwe, cudaStream_t st) {
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  cudaError_t e = cudaMemsetAsync(iwe, 0, (size_t)Hp * Wp * sizeof(T), st);
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_window_splat memset");
+  if (n == 0) return EBOS_OK;
+  WindowLayout L = window_layout(n, sizeof(T));
+  const char* b = reinterpret_cast<const char*>(window);
+  const T* sx = reinterpret_cast<const T*>(b + L.off_x);
+  const T* sy = reinterpret_cast<const T*>(b + L.off_y);
+  const T* sd = reinterpret_cast<const T*>(b + L.off_d);
+  const T* sw = reinterpret_cast<const T*>(b + L.off_w);
+  int64_t threads = (n + Ept<T>::splat - 1) / Ept<T>::splat;
+  unsigned grid = (unsigned)((threads + 255) / 256);
+  if (has_weight) k_win_splat<T, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);
+  else k_win_splat<T, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);
+  EBOS_LAUNCH_CHECK("ebos_window_splat");
+  return EBOS_OK;
+}
+
+template <typename T>
+int window_backward_t(const void* window, int64_t n, int has_weight, const T* flow, int H, int W, int pad_h, int pad_w,
+                      const T* grad_iwe, int kind, const T* iwe, const double* acc, int omit_boundary, double scale,
+                      T* dflow, cudaStream_t st) {
+  if (n == 0) return EBOS_OK;
+  WindowLayout L = window_layout(n, sizeof(T));
+  const char* b = reinterpret_cast<const char*>(window);
+  const T* sx = reinterpret_cast<const T*>(b + L.off_x);
+  const T* sy = reinterpret_cast<const T*>(b + L.off_y);
+  const T* sd = reinterpret_cast<const T*>(b + L.off_d);
+  const T* sw = reinterpret_cast<const T*>(b + L.off_w);
+  int64_t threads = (n + Ept<T>::bwd - 1) / Ept<T>::bwd;
+  unsigned grid = (unsigned)((threads + 255) / 256);
+  const bool affine = grad_iwe == nullptr;
+  if (affine) {
+    if (kind != EBOS_COST_VARIANCE || !iwe || !acc) {
+      set_error("ebos_window_backward: grad_iwe == NULL needs kind == VARIANCE with iwe and acc");
+      return EBOS_ERR_BAD_ARG;
+    }
+    if (has_weight) k_win_bwd<T, 1, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe, acc, omit_boundary, scale, dflow);
+    else k_win_bwd<T, 1, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe, acc, omit_boundary, scale, dflow);
+  } else {
+    if (has_weight) k_win_bwd<T, 0, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, grad_iwe, acc, omit_boundary, scale, dflow);
+    else k_win_bwd<T, 0, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, grad_iwe, acc, omit_boundary, scale, dflow);
+  }
+  EBOS_LAUNCH_CHECK("ebos_window_backward");
+  return EBOS_OK;
+}
+
+// type-erased entry points used by ebos_costs.cu (fused iteration)
+int window_splat_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                        int pad_w, int dtype, void* iwe, cudaStream_t st) {
+  if (dtype == EBOS_F64)
+    return window_splat_t<double>(window, n, has_weight, (const double*)flow, H, W, pad_h, pad_w, (double*)iwe, st);
+  return window_splat_t<float>(window, n, has_weight, (const float*)flow, H, W, pad_h, pad_w, (float*)iwe, st);
+}
+int window_backward_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                           int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
+                           int omit_boundary, double scale, void* dflow, cudaStream_t st) {
+  if (dtype == EBOS_F64)
+    return window_backward_t<double>(window, n, has_weight, (const double*)flow, H, W, pad_h, pad_w,
+                                     (const double*)grad_iwe, kind, (const double*)iwe, acc, omit_boundary, scale,
+                                     (double*)dflow, st);
+  return window_backward_t<float>(window, n, has_weight, (const float*)flow, H, W, pad_h, pad_w, (const float*)grad_iwe,
+                                  kind, (const float*)iwe, acc, omit_boundary, scale, (float*)dflow, st);
+}
+
+}  // namespace ebos
+
+using namespace ebos;
+
+#define EBOS_CHECK_DTYPE(dtype, who)                                              \
+  do {                                                                            \
+    if ((dtype) != EBOS_F32 && (dtype) != EBOS_F64) {                             \
+      ebos::set_error(who ": unsupported dtype");                                 \
+      return EBOS_ERR_UNSUPPORTED;                                                \
+    }                                                                             \
+  } while (0)
+
+extern "C" {
+
+size_t ebos_window_bytes(int64_t n, int dtype) { return n < 0 ? 0 : window_layout(n, dtype_size(dtype)).total; }
+
+size_t ebos_window_workspace_bytes(int64_t n, int H, int W) {
+  (void)H; (void)W;
+  return n < 0 ? 0 : prep_ws(n).total;
+}
+
+int ebos_window_prepare(const void* events, int64_t n, int H, int W, int direction, double direction_frac,
+                        int normalize_t, const void* weight, const void* tminmax, int dtype, void* window,
+                        void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+  EBOS_REQUIRE(n >= 0 && n < (int64_t)INT_MAX && H > 0 && W > 0 && window && status && (n == 0 || events),
+               "ebos_window_prepare: bad argument");
+  EBOS_REQUIRE((int64_t)H * W < ((int64_t)1 << 31) - 1, "ebos_window_prepare: grid too large");
+  EBOS_REQUIRE(direction >= EBOS_DIR_FIRST && direction <= EBOS_DIR_FRAC, "ebos_window_prepare: bad direction");
+  EBOS_REQUIRE((reinterpret_cast<size_t>(window) & 255) == 0, "ebos_window_prepare: window buffer must be 256-byte aligned");
+  EBOS_CHECK_DTYPE(dtype, "ebos_window_prepare");
+  if (dtype == EBOS_F64)
+    return window_prepare_impl<double>((const double*)events, n, H, W, direction, direction_frac, normalize_t,
+                                       (const double*)weight, (const double*)tminmax, window, workspace,
+                                       workspace_bytes, status, as_stream(stream));
+  return window_prepare_impl<float>((const float*)events, n, H, W, direction, direction_frac, normalize_t,
+                                    (const float*)weight, (const float*)tminmax, window, workspace, workspace_bytes,
+                                    status, as_stream(stream));
+}
+
+int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out, double* tinfo_out, void* stream) {
   EBOS_REQUIRE(window && n >= 0, "ebos_window_info: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_window_info");
   cudaStream_t st = as_stream(stream);
   const char* b = reinterpret_cast<const char*>(window);
   if (perm_out && n > 0) {
-    cudaError_t e = cudaMemcpyAsync(perm_out, b + window_layout(n).off_perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(perm_out, b + window_layout(n, dtype_size(dtype)).off_perm, (size_t)n * 4,
+                                    cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_window_info(perm)");
   }
   if (tinfo_out) {
-    cudaError_t e = cudaMemcpyAsync(tinfo_out, b, 16, cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(tinfo_out, b, 32, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_window_info(tinfo)");
   }
   return EBOS_OK;
 }
 
-int ebos_window_splat(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                      int pad_w, float* iwe, void* stream) {
+int ebos_window_splat(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                      int pad_w, int dtype, void* iwe, void* stream) {
   EBOS_REQUIRE(window && flow && iwe && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "ebos_window_splat: bad argument");
-  return window_splat_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, iwe, as_stream(stream));
+  EBOS_CHECK_DTYPE(dtype, "ebos_window_splat");
+  return window_splat_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, iwe, as_stream(stream));
 }
 
-int ebos_window_backward(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                         int pad_w, const float* grad_iwe, int kind, const float* iwe, const double* acc,
-                         int omit_boundary, float scale, float* dflow, void* stream) {
+int ebos_window_backward(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                         int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
+                         int omit_boundary, double scale, void* dflow, void* stream) {
   EBOS_REQUIRE(window && flow && dflow && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "ebos_window_backward: bad argument");
-  return window_backward_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, grad_iwe, kind, iwe, acc, omit_boundary,
-                                scale, dflow, as_stream(stream));
+  EBOS_CHECK_DTYPE(dtype, "ebos_window_backward");
+  return window_backward_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, grad_iwe, kind, iwe, acc,
+                                omit_boundary, scale, dflow, as_stream(stream));
 }
 
 }  // extern "C"

@@ -222,39 +222,50 @@ def iwe_splat_debug(events: torch.Tensor, padded_size: Tuple[int, int], outer_pa
 # ------------------------------------------------------------------------------------------------------
 # fused path
 # ------------------------------------------------------------------------------------------------------
+def _float_dtype(dtype) -> torch.dtype:
+    if dtype in (torch.float32, "32", 32, "float32"):
+        return torch.float32
+    if dtype in (torch.float64, "64", 64, "float64"):
+        return torch.float64
+    raise TypeError(f"the fused path runs in float32 or float64, got {dtype!r}")
+
+
 class PreparedWindow:
     """Events of one time window, prepared once for many objective evaluations: time-normalised
     (src/warp.py:264-288) and stably sorted by origin pixel (src/warp.py:334) into an SoA buffer.
-    fp32.  `events` is [n,4] on the GPU (x=row, y=col, t, p)."""
+    `events` is [n,4] on the GPU (x=row, y=col, t, p); `dtype` float32 (fast path, default) or float64
+    (the dtype the reference's solvers run in)."""
 
     def __init__(self, events: torch.Tensor, image_size: Tuple[int, int], direction: Direction = "first",
                  normalize_t: bool = True, weight: Optional[torch.Tensor] = None, validate: bool = True,
-                 t_min_max: Optional[torch.Tensor] = None):
+                 t_min_max: Optional[torch.Tensor] = None, dtype=torch.float32):
         _check_cuda(events, weight, t_min_max)
         if events.dim() != 2 or events.shape[1] != 4:
             raise ValueError(f"events must be [n,4], got {tuple(events.shape)}")
         if events.shape[0] == 0:
             raise RuntimeError("min()/max() of an empty event array (the reference raises here too)")
-        ev = events.to(torch.float32).contiguous()
+        self.dtype = _float_dtype(dtype)
+        ev = events.to(self.dtype).contiguous()
         self.device = ev.device
         self.n = int(ev.shape[0])
         self.H, self.W = int(image_size[0]), int(image_size[1])
         self.direction = direction
         self.normalize_t = bool(normalize_t)
         self.has_weight = weight is not None
-        w = None if weight is None else weight.to(torch.float32).contiguous()
+        w = None if weight is None else weight.to(self.dtype).contiguous()
         kind, frac = direction_code(direction)
         lib = _capi.load()
-        self.buffer = torch.empty(lib.ebos_window_bytes(self.n), dtype=torch.uint8, device=ev.device)
+        self.code = dtype_code(ev)
+        self.buffer = torch.empty(lib.ebos_window_bytes(self.n, self.code), dtype=torch.uint8, device=ev.device)
         ws_bytes = lib.ebos_window_workspace_bytes(self.n, self.H, self.W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ev.device)
         status = torch.zeros(1, dtype=torch.int32, device=ev.device)
-        # t_min_max: float32 [2] on the device -- the GLOBAL (min t, max t) when this window is one
-        # shard of a larger event set (event-sharded multi-GPU path).
-        tmm = None if t_min_max is None else t_min_max.to(torch.float32).contiguous()
+        # t_min_max: [2] on the device -- the GLOBAL (min t, max t) when this window is one shard of a
+        # larger event set (event-sharded multi-GPU path).
+        tmm = None if t_min_max is None else t_min_max.to(self.dtype).contiguous()
         check(lib.ebos_window_prepare(ptr(ev), self.n, self.H, self.W, kind, frac, int(self.normalize_t), ptr(w),
-                                      ptr(tmm), ptr(self.buffer), ptr(ws), ws_bytes, ptr(status), current_stream()),
-              "ebos_window_prepare")
+                                      ptr(tmm), self.code, ptr(self.buffer), ptr(ws), ws_bytes, ptr(status),
+                                      current_stream()), "ebos_window_prepare")
         self._status = status
         if validate and int(status.item()) & _capi.STATUS_PIXEL_OOB:
             raise RuntimeError("index out of bounds: an event's integer pixel lies outside the flow grid "
@@ -263,14 +274,22 @@ class PreparedWindow:
     def permutation(self) -> torch.Tensor:
         """int32 [n]: sorted position -> index of the event in the array the window was built from."""
         out = torch.empty(self.n, dtype=torch.int32, device=self.device)
-        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, ptr(out), 0, current_stream()), "ebos_window_info")
+        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, self.code, ptr(out), 0, current_stream()),
+              "ebos_window_info")
         return out
 
     def time_info(self) -> torch.Tensor:
-        """float32 [4]: t_ref, period, t_min, t_max as computed on the device."""
-        out = torch.empty(4, dtype=torch.float32, device=self.device)
-        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, 0, ptr(out), current_stream()), "ebos_window_info")
+        """float64 [4]: t_ref, period, t_min, t_max as computed on the device (exact values of `dtype`)."""
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, self.code, 0, ptr(out), current_stream()),
+              "ebos_window_info")
         return out
+
+
+def _check_flow(window: PreparedWindow, flow: torch.Tensor) -> None:
+    if flow.dtype != window.dtype or tuple(flow.shape) != (2, window.H, window.W) or not flow.is_contiguous():
+        raise ValueError(f"flow must be a contiguous {window.dtype} [2,{window.H},{window.W}] tensor, got "
+                         f"{flow.dtype} {tuple(flow.shape)}")
 
 
 def window_splat(window: PreparedWindow, flow: torch.Tensor, outer_padding: Tuple[int, int] = (0, 0),
@@ -280,28 +299,23 @@ def window_splat(window: PreparedWindow, flow: torch.Tensor, outer_padding: Tupl
     _check_flow(window, flow)
     ph, pw = int(outer_padding[0]), int(outer_padding[1])
     if out is None:
-        out = torch.empty((window.H + 2 * ph, window.W + 2 * pw), dtype=torch.float32, device=flow.device)
+        out = torch.empty((window.H + 2 * ph, window.W + 2 * pw), dtype=window.dtype, device=flow.device)
     check(_capi.load().ebos_window_splat(ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), window.H,
-                                         window.W, ph, pw, ptr(out), current_stream()), "ebos_window_splat")
+                                         window.W, ph, pw, window.code, ptr(out), current_stream()), "ebos_window_splat")
     return out
 
 
-def _check_flow(window: PreparedWindow, flow: torch.Tensor) -> None:
-    if flow.dtype != torch.float32 or tuple(flow.shape) != (2, window.H, window.W) or not flow.is_contiguous():
-        raise ValueError(f"flow must be a contiguous float32 [2,{window.H},{window.W}] tensor, got "
-                         f"{flow.dtype} {tuple(flow.shape)}")
-
-
 class CmaxWorkspace:
-    """Scratch planes for `cmax_value_and_grad`, allocated once per (H, W, padding)."""
+    """Scratch planes for `cmax_value_and_grad`, allocated once per (H, W, padding, dtype)."""
 
-    def __init__(self, H: int, W: int, outer_padding: Tuple[int, int] = (0, 0), device="cuda"):
+    def __init__(self, H: int, W: int, outer_padding: Tuple[int, int] = (0, 0), device="cuda", dtype=torch.float32):
         ph, pw = int(outer_padding[0]), int(outer_padding[1])
         self.H, self.W, self.ph, self.pw = H, W, ph, pw
-        self.iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=torch.float32, device=device)
+        self.dtype = _float_dtype(dtype)
+        self.iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=self.dtype, device=device)
         self.grad_iwe = torch.empty_like(self.iwe)
-        self.dflow = torch.empty((2, H, W), dtype=torch.float32, device=device)
-        self.loss = torch.zeros(1, dtype=torch.float32, device=device)
+        self.dflow = torch.empty((2, H, W), dtype=self.dtype, device=device)
+        self.loss = torch.zeros(1, dtype=self.dtype, device=device)
         self.acc = torch.zeros(8, dtype=torch.float64, device=device)
 
 
@@ -317,32 +331,38 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
     _check_flow(window, flow)
     if cost not in COST_KINDS:
         raise KeyError(f"unknown data cost {cost!r}; available: {sorted(COST_KINDS)}")
-    ws = workspace or CmaxWorkspace(window.H, window.W, outer_padding, flow.device)
+    ws = workspace or CmaxWorkspace(window.H, window.W, outer_padding, flow.device, window.dtype)
+    if ws.dtype != window.dtype:
+        raise TypeError(f"workspace dtype {ws.dtype} does not match the window's {window.dtype}")
     tvw = None
     if tv_weights is not None:
-        tvw = tv_weights.to(torch.float32).contiguous()
+        tvw = tv_weights.to(window.dtype).contiguous()
         if tuple(tvw.shape) != (window.H, window.W):
             raise ValueError(f"tv_weights must be [{window.H},{window.W}], got {tuple(tvw.shape)}")
     check(_capi.load().ebos_cmax_value_and_grad(
         ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), window.H, window.W, ws.ph, ws.pw,
-        COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), ptr(ws.iwe),
-        ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), current_stream()), "ebos_cmax_value_and_grad")
+        COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code,
+        ptr(ws.iwe), ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), current_stream()),
+        "ebos_cmax_value_and_grad")
     return ws.loss, ws.dflow
 
 
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
               step_dev: Optional[torch.Tensor] = None) -> None:
-    """torch.optim.Adam update in place (fp32).  With `step_dev` (int32 [1] on the device) the step
-    counter lives on the GPU so that the call can be captured in a CUDA graph."""
+    """torch.optim.Adam update in place.  With `step_dev` (int32 [1] on the device) the step counter
+    lives on the GPU so that the call can be captured in a CUDA graph."""
     _check_cuda(param, grad, exp_avg, exp_avg_sq)
+    code = dtype_code(param)
+    if not (grad.dtype == exp_avg.dtype == exp_avg_sq.dtype == param.dtype):
+        raise TypeError("adam_step: param, grad and moments must share a dtype")
     lib = _capi.load()
     if step_dev is not None:
         check(lib.ebos_adam_step_graph(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, betas[0],
-                                       betas[1], eps, ptr(step_dev), current_stream()), "ebos_adam_step_graph")
+                                       betas[1], eps, ptr(step_dev), code, current_stream()), "ebos_adam_step_graph")
     else:
         check(lib.ebos_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, betas[0],
-                                 betas[1], eps, int(step), current_stream()), "ebos_adam_step")
+                                 betas[1], eps, int(step), code, current_stream()), "ebos_adam_step")
 
 
 # operator-level cost kernels (used by the CostBase-style classes) ----------------------------------------
@@ -351,14 +371,15 @@ class _IweCost(torch.autograd.Function):
     def forward(ctx, iwe, kind, omit_boundary):
         img = iwe.contiguous()
         Hp, Wp = img.shape
-        acc = torch.empty(8, dtype=torch.float64, device=img.device)
+        code = dtype_code(img)
+        acc = torch.zeros(8, dtype=torch.float64, device=img.device)
         grad = torch.empty_like(img)
-        loss = torch.empty(1, dtype=torch.float32, device=img.device)
+        loss = torch.empty(1, dtype=img.dtype, device=img.device)
         lib = _capi.load()
         st = current_stream()
-        check(lib.ebos_iwe_cost(kind, ptr(img), Hp, Wp, int(omit_boundary), 1.0, ptr(acc), ptr(grad), st), "ebos_iwe_cost")
-        acc[3] = 0.0
-        check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, 1, 1, int(omit_boundary), 1.0, 0.0, ptr(loss), st),
+        check(lib.ebos_iwe_cost(kind, ptr(img), Hp, Wp, int(omit_boundary), 1.0, code, ptr(acc), ptr(grad), st),
+              "ebos_iwe_cost")
+        check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, 1, 1, int(omit_boundary), 1.0, 0.0, code, ptr(loss), st),
               "ebos_loss_finalize")
         ctx.save_for_backward(grad)
         return loss[0]
@@ -370,12 +391,12 @@ class _IweCost(torch.autograd.Function):
 
 
 def iwe_cost(iwe: torch.Tensor, cost: str, omit_boundary: bool = False) -> torch.Tensor:
-    """Scalar data objective on an fp32 IWE plane, differentiable (analytic gradient kernel)."""
+    """Scalar data objective on an IWE plane (fp32/fp64), differentiable (analytic gradient kernel)."""
     _check_cuda(iwe)
     if iwe.dim() != 2:
         raise ValueError(f"iwe must be [H,W], got {tuple(iwe.shape)}")
-    out = _IweCost.apply(iwe.to(torch.float32), COST_KINDS[cost], bool(omit_boundary))
-    return out.to(iwe.dtype)
+    dtype_code(iwe)
+    return _IweCost.apply(iwe, COST_KINDS[cost], bool(omit_boundary))
 
 
 class _FlowTv(torch.autograd.Function):
@@ -385,10 +406,10 @@ class _FlowTv(torch.autograd.Function):
         _, H, W = fl.shape
         acc = torch.zeros(8, dtype=torch.float64, device=fl.device)
         dflow = torch.empty_like(fl)
-        check(_capi.load().ebos_flow_tv(ptr(fl), ptr(weights), H, W, 1.0, ptr(acc), ptr(dflow), current_stream()),
-              "ebos_flow_tv")
+        check(_capi.load().ebos_flow_tv(ptr(fl), ptr(weights), H, W, 1.0, dtype_code(fl), ptr(acc), ptr(dflow),
+                                        current_stream()), "ebos_flow_tv")
         ctx.save_for_backward(dflow)
-        return (acc[3] / (2.0 * H * W)).to(torch.float32)
+        return (acc[3] / (2.0 * H * W)).to(fl.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -398,14 +419,16 @@ class _FlowTv(torch.autograd.Function):
 
 def flow_total_variation(flow: torch.Tensor, weights: Union[float, torch.Tensor, None] = None) -> torch.Tensor:
     """mean(|d flow/d row * w| + |d flow/d col * w|)  (src/costs/image_gradient.py:60-70), differentiable
-    w.r.t. `flow`."""
+    w.r.t. `flow` (fp32/fp64)."""
     _check_cuda(flow)
     if flow.dim() != 3 or flow.shape[0] != 2:
         raise ValueError(f"flow must be [2,H,W], got {tuple(flow.shape)}")
+    if flow.shape[1] < 2 or flow.shape[2] < 2:
+        raise RuntimeError("torch.gradient expected each dimension size to be at least edge_order+1")
+    dtype_code(flow)
     w = None
     if isinstance(weights, torch.Tensor):
-        w = weights.to(device=flow.device, dtype=torch.float32).expand(flow.shape[1], flow.shape[2]).contiguous()
+        w = weights.to(device=flow.device, dtype=flow.dtype).expand(flow.shape[1], flow.shape[2]).contiguous()
     elif weights is not None and float(weights) != 1.0:
-        w = torch.full(flow.shape[1:], float(weights), dtype=torch.float32, device=flow.device)
-    out = _FlowTv.apply(flow.to(torch.float32), w)
-    return out.to(flow.dtype)
+        w = torch.full(flow.shape[1:], float(weights), dtype=flow.dtype, device=flow.device)
+    return _FlowTv.apply(flow, w)

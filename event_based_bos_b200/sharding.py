@@ -102,9 +102,10 @@ def shard_events(n_events: int, rank: Optional[int] = None, world: Optional[int]
 
 
 def global_time_range(t_local: torch.Tensor) -> torch.Tensor:
-    """float32 [2] = (min t, max t) over the events of ALL ranks (one MIN and one MAX all-reduce)."""
-    lo = t_local.min().reshape(1).to(torch.float32) if t_local.numel() else torch.full((1,), float("inf"), device=t_local.device)
-    hi = t_local.max().reshape(1).to(torch.float32) if t_local.numel() else torch.full((1,), float("-inf"), device=t_local.device)
+    """[2] = (min t, max t) over the events of ALL ranks, in t's dtype (one MIN and one MAX all-reduce)."""
+    kw = dict(device=t_local.device, dtype=t_local.dtype)
+    lo = t_local.min().reshape(1) if t_local.numel() else torch.full((1,), float("inf"), **kw)
+    hi = t_local.max().reshape(1) if t_local.numel() else torch.full((1,), float("-inf"), **kw)
     if is_distributed():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -141,7 +142,8 @@ class EventShardedObjective:
 
 def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[int, int], cost: str = "gradient_magnitude",
                                  data_weight: float = 1.0, tv_weight: float = 0.0, omit_boundary: bool = False,
-                                 direction="first", outer_padding: Tuple[int, int] = (0, 0)) -> EventShardedObjective:
+                                 direction="first", outer_padding: Tuple[int, int] = (0, 0),
+                                 dtype=torch.float32) -> EventShardedObjective:
     """EventShardedObjective whose stages are the libebos kernels, for the local slice of the events."""
     from . import _capi, ops
     from ._capi import check, current_stream, ptr
@@ -149,14 +151,14 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
     H, W = image_size
     ph, pw = outer_padding
     tmm = global_time_range(events_local[:, 2])
-    window = ops.PreparedWindow(events_local, (H, W), direction, True, t_min_max=tmm)
+    window = ops.PreparedWindow(events_local, (H, W), direction, True, t_min_max=tmm, dtype=dtype)
     dev = events_local.device
-    iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=torch.float32, device=dev)
+    iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=window.dtype, device=dev)
     g_iwe = torch.empty_like(iwe)
-    dflow = torch.empty((2, H, W), dtype=torch.float32, device=dev)
+    dflow = torch.empty((2, H, W), dtype=window.dtype, device=dev)
     dtv = torch.empty_like(dflow)
     acc = torch.zeros(8, dtype=torch.float64, device=dev)
-    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    loss = torch.zeros(1, dtype=window.dtype, device=dev)
     kind = ops.COST_KINDS[cost]
     lib = _capi.load()
 
@@ -165,22 +167,23 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
 
     def cost_fn(img):
         st = current_stream()
-        check(lib.ebos_iwe_cost(kind, ptr(img), H + 2 * ph, W + 2 * pw, int(omit_boundary), data_weight, ptr(acc),
-                                ptr(g_iwe), st), "ebos_iwe_cost")
+        check(lib.ebos_iwe_cost(kind, ptr(img), H + 2 * ph, W + 2 * pw, int(omit_boundary), data_weight, window.code,
+                                ptr(acc), ptr(g_iwe), st), "ebos_iwe_cost")
         acc[3] = 0.0
         check(lib.ebos_loss_finalize(kind, ptr(acc), H + 2 * ph, W + 2 * pw, H, W, int(omit_boundary), data_weight, 0.0,
-                                     ptr(loss), st), "ebos_loss_finalize")
+                                     window.code, ptr(loss), st), "ebos_loss_finalize")
         return loss.clone(), g_iwe
 
     def backward(flow, g):
         dflow.zero_()
         check(lib.ebos_window_backward(ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), H, W, ph, pw,
-                                       ptr(g), kind, ptr(iwe), ptr(acc), int(omit_boundary), data_weight, ptr(dflow),
-                                       current_stream()), "ebos_window_backward")
+                                       window.code, ptr(g), kind, ptr(iwe), ptr(acc), int(omit_boundary), data_weight,
+                                       ptr(dflow), current_stream()), "ebos_window_backward")
         return dflow
 
     def regulariser(flow):
-        check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight, ptr(acc), ptr(dtv), current_stream()), "ebos_flow_tv")
-        return (acc[3] * (tv_weight / (2.0 * H * W))).to(torch.float32).reshape(1), dtv
+        check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight, window.code, ptr(acc), ptr(dtv), current_stream()),
+              "ebos_flow_tv")
+        return (acc[3] * (tv_weight / (2.0 * H * W))).to(window.dtype).reshape(1), dtv
 
     return EventShardedObjective(splat, cost_fn, backward, regulariser if tv_weight else None)

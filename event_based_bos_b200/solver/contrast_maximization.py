@@ -37,7 +37,8 @@ class ContrastMaximizationDense(SolverBase):
     Reads from `solver_config` (yaml `solver:` block): `warp_direction`, `outer_padding`, `optimizer.n_iter`,
     `optimizer.method` ("Adam"), and the sub-dict `cmax` with `cost_with_weight` (default
     {gradient_magnitude: 1.0, image_gradient: 0.5}), `lr` (0.05), `omit_boundary` (False), `fused` (True),
-    `cuda_graph` (True), `store_history` (False).
+    `cuda_graph` (True), `store_history` (False), `precision` ("32" fast path | "64" = the dtype the
+    reference's solvers run in, src/solver/patch_eklt_pyramid2.py:253).
     """
 
     def __init__(self, orig_image_shape: tuple, crop_image_shape: tuple, calibration_parameter: dict = {},
@@ -51,6 +52,10 @@ class ContrastMaximizationDense(SolverBase):
         self.fused = bool(cm.get("fused", True))
         self.use_cuda_graph = bool(cm.get("cuda_graph", True))
         self.store_history = bool(cm.get("store_history", False))
+        self.precision = str(cm.get("precision", "32"))
+        if self.precision not in ("32", "64"):
+            raise ValueError(f"cmax.precision must be '32' or '64', got {self.precision!r}")
+        self._dtype = torch.float64 if self.precision == "64" else torch.float32
         self.warp_direction = self.slv_config.get("warp_direction", "first")
         opt = self.slv_config.get("optimizer", {})
         self._opt_method = opt.get("method", "Adam")
@@ -65,10 +70,10 @@ class ContrastMaximizationDense(SolverBase):
         """[n,4] events (x=row, y=col, t [s], p) -> flow [2,H,W] float64 (pixel displacement over the window)."""
         H, W = self.orig_image_shape
         # absolute sensor time -> window-relative, in float64, before the fp32 cast
-        ev = torch.from_numpy(utils.rebase_time(np.asarray(events))).to(torch.float32).to(self._device)
-        x0 = torch.zeros((2, H, W), dtype=torch.float32, device=self._device)
+        ev = torch.from_numpy(utils.rebase_time(np.asarray(events))).to(self._dtype).to(self._device)
+        x0 = torch.zeros((2, H, W), dtype=self._dtype, device=self._device)
         if flow0 is not None:
-            x0.copy_(torch.from_numpy(np.asarray(flow0)).to(torch.float32))
+            x0.copy_(torch.from_numpy(np.asarray(flow0)).to(self._dtype))
         self.history = {"loss": []}
         if self.fused:
             flow = self._solve_fused(ev, x0)
@@ -85,12 +90,12 @@ class ContrastMaximizationDense(SolverBase):
     # -- fused CUDA path ---------------------------------------------------------------------------
     def _solve_fused(self, ev: torch.Tensor, x0: torch.Tensor) -> torch.Tensor:
         H, W = self.orig_image_shape
-        window = ops.PreparedWindow(ev, (H, W), self.warp_direction, self.normalize_t_in_batch)
+        window = ops.PreparedWindow(ev, (H, W), self.warp_direction, self.normalize_t_in_batch, dtype=self._dtype)
         pad = (self.padding, self.padding)
-        ws = ops.CmaxWorkspace(H, W, pad, x0.device)
+        ws = ops.CmaxWorkspace(H, W, pad, x0.device, self._dtype)
         m, v = torch.zeros_like(x0), torch.zeros_like(x0)
         step_dev = torch.zeros(1, dtype=torch.int32, device=x0.device)
-        hist = torch.zeros(max(self.n_iter, 1), dtype=torch.float32, device=x0.device) if self.store_history else None
+        hist = torch.zeros(max(self.n_iter, 1), dtype=self._dtype, device=x0.device) if self.store_history else None
 
         def iteration():
             ops.cmax_value_and_grad(window, x0, self.data_cost, self.data_weight, self.tv_weight, None,

@@ -117,75 +117,79 @@ EBOS_API int ebos_iwe_splat_bwd(const void* events, int64_t n, int batch, int Hp
                        void* grad_weight, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Fused contrast-maximisation path (fp32): events of one window are prepared ONCE (sorted by
- * origin pixel, time-normalised), then every solver iteration runs
+ * Fused contrast-maximisation path: events of one window are prepared ONCE (sorted by origin
+ * pixel, time-normalised), then every solver iteration runs
  *    splat (warp+vote fused, warped events never materialised) -> cost -> backward -> [Adam].
+ * dtype EBOS_F32 is the fast path; EBOS_F64 is the dtype the reference's solvers run in
+ * (src/solver/patch_eklt_pyramid2.py:253) and is used for solve-level parity.  All planes, the flow,
+ * the events and the loss share `dtype`; `acc` is always double[8].
  * ---------------------------------------------------------------------------------------- */
 
 /* Bytes of the caller-owned window buffer / of the temporary workspace used by prepare. */
-EBOS_API size_t ebos_window_bytes(int64_t n);
+EBOS_API size_t ebos_window_bytes(int64_t n, int dtype);
 EBOS_API size_t ebos_window_workspace_bytes(int64_t n, int H, int W);
 
-/* Build a window from raw events [n,4] fp32: computes t_ref/period on the device
+/* Build a window from raw events [n,4]: computes t_ref/period on the device
  * (src/warp.py:230-288), dt_i, k_i, and stores (x, y, dt[, weight]) sorted by k (stable, so the
  * sensor's time order is kept inside a pixel).  weight: NULL or [n].  status as above.
- * tminmax: NULL, or float[2] (device) = (min t, max t) to use instead of this call's own
- * reduction -- for a window whose events are sharded over several GPUs (global min/max). */
-EBOS_API int ebos_window_prepare(const float* events, int64_t n, int H, int W, int direction, double direction_frac,
-                        int normalize_t, const float* weight, const float* tminmax, void* window, void* workspace,
-                        size_t workspace_bytes, int32_t* status, void* stream);
+ * tminmax: NULL, or [2] (device, dtype) = (min t, max t) to use instead of this call's own
+ * reduction -- for a window whose events are sharded over several GPUs (global min/max).
+ * window must be 256-byte aligned. */
+EBOS_API int ebos_window_prepare(const void* events, int64_t n, int H, int W, int direction, double direction_frac,
+                        int normalize_t, const void* weight, const void* tminmax, int dtype, void* window,
+                        void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 
 /* Copy the window's event permutation (int32[n]: sorted position -> original event index) and its
- * time statistics (float[4]: t_ref, period, t_min, t_max) out of the opaque buffer (either may be NULL). */
-EBOS_API int ebos_window_info(const void* window, int64_t n, int32_t* perm_out, float* tinfo_out, void* stream);
+ * time statistics (double[4]: t_ref, period, t_min, t_max) out of the opaque buffer (either may be NULL). */
+EBOS_API int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out, double* tinfo_out, void* stream);
 
 /* Fused warp + bilinear vote of a prepared window into iwe [Hp,Wp] (fully overwritten).
- * `n` and `has_weight` must be the values the window was prepared with. */
-EBOS_API int ebos_window_splat(const void* window, int64_t n, int has_weight, const float* flow, int H, int W, int pad_h,
-                      int pad_w, float* iwe, void* stream);
+ * `n`, `has_weight` and `dtype` must be the values the window was prepared with. */
+EBOS_API int ebos_window_splat(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+                      int pad_w, int dtype, void* iwe, void* stream);
 
-/* Data objective on the IWE: value and gradient.
- * acc: double[8] device scratch (zeroed by this call).  grad_iwe: [Hp,Wp] written for GRADMAG;
- * for VARIANCE it may be NULL -- the backward then derives dL/dIWE = c*(IWE-mean) on the fly
- * from `acc` (pass the same `acc` and `iwe` to ebos_window_backward). */
-EBOS_API int ebos_iwe_cost(int kind, const float* iwe, int Hp, int Wp, int omit_boundary, float scale, double* acc,
-                  float* grad_iwe, void* stream);
+/* Data objective on the IWE: value and gradient scaled by `scale`.
+ * acc: double[8] device scratch (entries 0..2 zeroed by this call).  grad_iwe: [Hp,Wp], required for
+ * GRADMAG; for VARIANCE it may be NULL -- the backward then derives dL/dIWE = c*(IWE-mean) on the
+ * fly from `acc` (pass the same `acc` and `iwe` to ebos_window_backward). */
+EBOS_API int ebos_iwe_cost(int kind, const void* iwe, int Hp, int Wp, int omit_boundary, double scale, int dtype,
+                  double* acc, void* grad_iwe, void* stream);
 
 /* ImageGradient.calculate_torch -- src/costs/image_gradient.py:60-75 (TV-L1 of the flow with
  * torch.gradient semantics) value and gradient:  dflow = tv_scale * dTV/dflow  (OVERWRITES dflow,
  * so it doubles as the zero-fill of the gradient buffer; tv_scale = 0 just zeroes).
- * weights: NULL (1.0) or [H,W].  acc[3] accumulates the un-normalised |.| sum. */
-EBOS_API int ebos_flow_tv(const float* flow, const float* weights, int H, int W, float tv_scale, double* acc,
-                 float* dflow, void* stream);
+ * weights: NULL (1.0) or [H,W].  acc[3] (zeroed by this call) accumulates the un-normalised |.| sum. */
+EBOS_API int ebos_flow_tv(const void* flow, const void* weights, int H, int W, double tv_scale, int dtype, double* acc,
+                 void* dflow, void* stream);
 
 /* Analytic backward of the fused splat: re-warps every event, gathers dL/dIWE at
  * its four taps and accumulates -dt*dL/dx' into dflow[:, k] (ACCUMULATES; run ebos_flow_tv first).
- * grad_iwe: [Hp,Wp] or NULL with kind == EBOS_COST_VARIANCE (then iwe+acc are used). */
-EBOS_API int ebos_window_backward(const void* window, int64_t n, int has_weight, const float* flow, int H, int W,
-                         int pad_h, int pad_w, const float* grad_iwe, int kind, const float* iwe, const double* acc, int omit_boundary,
-                         float scale, float* dflow, void* stream);
+ * grad_iwe: [Hp,Wp] or NULL with kind == EBOS_COST_VARIANCE (then iwe+acc+scale are used). */
+EBOS_API int ebos_window_backward(const void* window, int64_t n, int has_weight, const void* flow, int H, int W,
+                         int pad_h, int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe,
+                         const double* acc, int omit_boundary, double scale, void* dflow, void* stream);
 
-/* loss[0] = data_scale * L_data + tv_scale * TV  from `acc` (float, device). */
+/* loss[0] = data_scale * L_data + tv_scale * TV  from `acc` (device scalar of dtype). */
 EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W, int omit_boundary,
-                       float data_scale, float tv_scale, float* loss, void* stream);
+                       double data_scale, double tv_scale, int dtype, void* loss, void* stream);
 
 /* One complete objective evaluation: splat -> cost -> TV -> backward -> loss, stream-ordered,
  * no host sync (CUDA-graph capturable).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W],
- * loss float[1], acc double[8]. */
-EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const float* flow, int H, int W,
-                             int pad_h, int pad_w, int kind,
-                             int omit_boundary, float data_scale, float tv_scale, const float* tv_weights,
-                             float* iwe, float* grad_iwe, float* dflow, float* loss, double* acc, void* stream);
+ * loss [1], acc double[8]. */
+EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const void* flow, int H, int W,
+                             int pad_h, int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
+                             const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
+                             double* acc, void* stream);
 
 /* torch.optim.Adam step (src/solver/patch_eklt_pyramid2.py:262-264,284), in place.  `step` is
  * 1-based.  Elementwise over n values. */
-EBOS_API int ebos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, int step, void* stream);
+EBOS_API int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, int step, int dtype, void* stream);
 
 /* Same, with the step counter read from device memory (`step_dev` int32[1], incremented by the
- * kernel) so that a captured CUDA graph can be replayed for every iteration. */
-EBOS_API int ebos_adam_step_graph(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                         float beta1, float beta2, float eps, int32_t* step_dev, void* stream);
+ * call) so that a captured CUDA graph can be replayed for every iteration. */
+EBOS_API int ebos_adam_step_graph(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr,
+                         double beta1, double beta2, double eps, int32_t* step_dev, int dtype, void* stream);
 
 #ifdef __cplusplus
 }
