@@ -97,11 +97,11 @@ template <typename T> struct Taps {
   T w0, w1, w2, w3;  // weights, before the optional per-event weight
 };
 
+// r = (int)floor + pad.  The float->int conversion saturates; adding a small non-negative pad to a
+// saturated value wraps INT_MAX to a NEGATIVE number and leaves INT_MIN very negative, so a wrapped cell
+// can never alias a valid one: every tap of such an event stays masked, as in the reference.
 template <typename T>
-__device__ __forceinline__ int sat_add(int v, int p) {
-  long long s = (long long)v + p;
-  return s > INT_MAX ? INT_MAX : (s < INT_MIN ? INT_MIN : (int)s);
-}
+__device__ __forceinline__ int sat_add(int v, int p) { return (int)((unsigned)v + (unsigned)p); }
 
 template <typename T>
 __device__ __forceinline__ Taps<T> make_taps(T xw, T yw, int pad_h, int pad_w, T bias = Rn<T>::bias()) {
@@ -122,12 +122,42 @@ __device__ __forceinline__ Taps<T> make_taps(T xw, T yw, int pad_h, int pad_w, T
   return t;
 }
 
+// floor() and (int)floor() at full FP32 issue rate (FRND/F2I run at quarter rate): for |v| < 2^22 adding
+// 1.5*2^23 leaves the round-to-nearest integer in the low mantissa bits; one compare turns it into floor.
+// Bit-identical to floorf()/saturating cast on that range (the sign of a zero result excepted, which
+// cannot change any sum); anything else (huge, Inf, NaN) takes the exact slow path.
+__device__ __forceinline__ float floor_to_int(float v, int& iv) {
+  if (fabsf(v) < 4194304.0f) {
+    const float M = 12582912.0f;
+    float f = __fsub_rn(__fadd_rn(v, M), M);
+    if (f > v) f = __fsub_rn(f, 1.0f);
+    iv = __float_as_int(__fadd_rn(f, M)) - 0x4B400000;
+    return f;
+  }
+  const float f = floorf(v);
+  iv = (int)f;
+  return f;
+}
+__device__ __forceinline__ double floor_to_int(double v, int& iv) {
+  const double f = floor(v);
+  iv = (int)f;
+  return f;
+}
+
 // no-return global reduction (REDG.E.ADD.F32 / .F64)
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// Same without the compiler-level memory clobber: for kernels that never read the accumulation target,
+// so that independent loads may be scheduled across the reductions.
+__device__ __forceinline__ void red_add_nc(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v));
+}
+__device__ __forceinline__ void red_add_nc(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
 
 // ---- block reductions (warp shuffle) ----------------------------------------------------------

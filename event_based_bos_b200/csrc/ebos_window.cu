@@ -16,6 +16,8 @@
 // The reference's solvers run in float64 (src/solver/patch_eklt_pyramid2.py:253); the fp64
 // instantiation is the dtype-faithful path used for solve-level parity.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "ebos_common.cuh"
@@ -27,6 +29,11 @@ namespace ebos {
 template <typename T> struct Ept;
 template <> struct Ept<float> { static constexpr int splat = 8, bwd = 4; };
 template <> struct Ept<double> { static constexpr int splat = 4, bwd = 4; };
+// experiment knob (EBOS_SPLAT_EPT / EBOS_BWD_EPT environment variables; 0 = default)
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
 
 // ---- prepare --------------------------------------------------------------------------------
 __global__ void k_win_hdr_init(WindowHeader* h) {
@@ -129,60 +136,131 @@ __device__ __forceinline__ void load_block(const T* __restrict__ p, int64_t base
 }
 
 // ---- forward: fused warp + bilinear vote -----------------------------------------------------
+// The per-event arithmetic is that of make_taps<T> (ebos_common.cuh, i.e. src/event_image_converter.py:
+// 586-614), arranged for instruction issue: the kernels were issue-bound (ncu r01: 61 % issue active,
+// DRAM 31 %), so
+//  * floor() runs on the FP32 pipe: for |v| < 2^22, (v + 1.5*2^23) - 1.5*2^23 is the round-to-nearest
+//    integer and one compare turns it into floor (FRND/F2I run at quarter rate);
+//  * the current cell is tracked as the two floor VALUES (floats); the integer cell is only formed when
+//    a run is flushed;
+//  * anything unusual (|coordinate| >= 2^22, Inf, NaN, parked events) leaves through one out-of-line
+//    exact path.
+template <typename T> struct FastFloor;
+template <> struct FastFloor<float> {
+  static __device__ __forceinline__ bool in_range(float a, float b) { return fabsf(a) < 4194304.0f && fabsf(b) < 4194304.0f; }
+  static __device__ __forceinline__ float flr(float v) {
+    const float M = 12582912.0f;
+    float f = __fsub_rn(__fadd_rn(v, M), M);
+    return (f > v) ? __fsub_rn(f, 1.0f) : f;
+  }
+  // exact for integer-valued |f| < 2^22
+  static __device__ __forceinline__ int to_int(float f) { return __float_as_int(__fadd_rn(f, 12582912.0f)) - 0x4B400000; }
+};
+template <> struct FastFloor<double> {
+  static __device__ __forceinline__ bool in_range(double a, double b) { return fabs(a) < 1073741824.0 && fabs(b) < 1073741824.0; }
+  static __device__ __forceinline__ double flr(double v) { return floor(v); }
+  static __device__ __forceinline__ int to_int(double f) { return (int)f; }
+};
+
+// Exact (reference-order) handling of one event whose warped coordinate is outside the fast range.
 template <typename T>
-__device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, int r, int c, T a0, T a1, T a2, T a3) {
-  const bool r0 = (unsigned)r < (unsigned)Hp, r1 = (unsigned)(r + 1) < (unsigned)Hp;
-  const bool c0 = (unsigned)c < (unsigned)Wp, c1 = (unsigned)(c + 1) < (unsigned)Wp;
-  T* p = iwe + (int64_t)r * Wp + c;
-  if (r0 & c0) red_add(p, a0);
-  if (r1 & c0) red_add(p + Wp, a1);
-  if (r0 & c1) red_add(p + 1, a2);
-  if (r1 & c1) red_add(p + Wp + 1, a3);
+__device__ __noinline__ void splat_event_exact(T* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w, T xw, T yw,
+                                               T wt) {
+  const Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
+  const bool fin = Rn<T>::finite(xw) && Rn<T>::finite(yw);
+  const int rr[4] = {t.r, t.r + 1, t.r, t.r + 1}, cc[4] = {t.c, t.c, t.c + 1, t.c + 1};
+  const T ww[4] = {t.w0, t.w1, t.w2, t.w3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const T v = Rn<T>::mul(ww[k], wt);
+    const bool m = fin && (unsigned)rr[k] < (unsigned)Hp && (unsigned)cc[k] < (unsigned)Wp &&
+                   !(k & 1 && t.r == INT_MAX) && !(k & 2 && t.c == INT_MAX);
+    if (m) red_add_nc(iwe + ((int64_t)rr[k] * Wp + cc[k]), v);
+    else if (!Rn<T>::finite(v)) red_add_nc(iwe, Rn<T>::mul(v, (T)0));  // vals*mask = NaN lands on pixel 0
+  }
 }
 
-template <typename T, bool HAS_W>
+template <typename T>
+__device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, int Hm1, int Wm1, int r, int c, T a0,
+                                           T a1, T a2, T a3) {
+  if ((unsigned)r < (unsigned)Hm1 && (unsigned)c < (unsigned)Wm1) {
+    // all four taps inside: the common case
+    T* p = iwe + (r * Wp + c);
+    red_add_nc(p, a0);
+    red_add_nc(p + 1, a2);
+    p += Wp;
+    red_add_nc(p, a1);
+    red_add_nc(p + 1, a3);
+  } else {
+    const bool r0 = (unsigned)r < (unsigned)Hp, r1 = (unsigned)(r + 1) < (unsigned)Hp;
+    const bool c0 = (unsigned)c < (unsigned)Wp, c1 = (unsigned)(c + 1) < (unsigned)Wp;
+    T* p = iwe + ((int64_t)r * Wp + c);
+    if (r0 & c0) red_add_nc(p, a0);
+    if (r1 & c0) red_add_nc(p + Wp, a1);
+    if (r0 & c1) red_add_nc(p + 1, a2);
+    if (r1 & c1) red_add_nc(p + Wp + 1, a3);
+  }
+}
+
+template <typename T, bool HAS_W, int EPT>
 __global__ void __launch_bounds__(256) k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy,
                                                    const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
                                                    const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
                                                    T* __restrict__ iwe) {
-  constexpr int EPT = Ept<T>::splat;
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
-  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, Hm1 = Hp - 1, Wm1 = Wp - 1;
   const int hw = H * W;
-  T x[EPT], y[EPT], d[EPT], wt[EPT];
+  T x[EPT], y[EPT], d[EPT], wt[EPT], f0[EPT], f1[EPT];
   load_block<T, EPT>(sx, base, n, (T)-2, x);
   load_block<T, EPT>(sy, base, n, (T)-2, y);
   load_block<T, EPT>(sd, base, n, (T)0, d);
   if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
-  int cr = INT_MIN, cc = INT_MIN;
-  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  // all flow gathers are issued before the first reduction (events of one pixel hit the same sector)
+  bool ok[EPT];
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
     const int k = (int)x[j] * W + (int)y[j];
-    if ((unsigned)k >= (unsigned)hw) continue;  // parked (invalid) event or tail
-    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
-    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
-    Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
-    if (HAS_W) {
-      t.w0 = Rn<T>::mul(t.w0, wt[j]); t.w1 = Rn<T>::mul(t.w1, wt[j]);
-      t.w2 = Rn<T>::mul(t.w2, wt[j]); t.w3 = Rn<T>::mul(t.w3, wt[j]);
-    }
-    if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) {
-      // non-finite warped coordinate (e.g. zero-length window: dt = 0/0): the reference masks all
-      // four taps and adds vals*0 = NaN to pixel 0.
-      red_add(iwe, Rn<T>::mul(t.w0, (T)0));
+    ok[j] = (unsigned)k < (unsigned)hw;  // false: parked (invalid) event or tail
+    const int kk = ok[j] ? k : 0;
+    f0[j] = __ldg(flow + kk);
+    f1[j] = __ldg(flow + hw + kk);
+  }
+  // current run: floor values of the cell (NaN = none) and the four tap sums
+  T cfr = Rn<T>::div((T)0, (T)0) * (T)0 + (T)NAN, cfc = (T)0;
+  T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    if (!ok[j]) continue;
+    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], f0[j]));
+    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], f1[j]));
+    const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
+    if (!FastFloor<T>::in_range(xb, yb)) {
+      splat_event_exact<T>(iwe, Hp, Wp, pad_h, pad_w, xw, yw, HAS_W ? wt[j] : (T)1);
       continue;
     }
-    if (t.r != cr || t.c != cc) {
-      if (cr != INT_MIN) flush_cell<T>(iwe, Hp, Wp, cr, cc, a0, a1, a2, a3);
-      cr = t.r; cc = t.c;
-      a0 = t.w0; a1 = t.w1; a2 = t.w2; a3 = t.w3;
-    } else {
-      a0 += t.w0; a1 += t.w1; a2 += t.w2; a3 += t.w3;
+    const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
+    const T a = Rn<T>::sub(xw, fr), b = Rn<T>::sub(yw, fc);
+    const T na = Rn<T>::sub((T)1, a), nb = Rn<T>::sub((T)1, b);
+    T w0 = Rn<T>::mul(na, nb), w1 = Rn<T>::mul(a, nb), w2 = Rn<T>::mul(na, b), w3 = Rn<T>::mul(a, b);
+    if (HAS_W) {
+      w0 = Rn<T>::mul(w0, wt[j]); w1 = Rn<T>::mul(w1, wt[j]);
+      w2 = Rn<T>::mul(w2, wt[j]); w3 = Rn<T>::mul(w3, wt[j]);
     }
+    const bool same = (fr == cfr) & (fc == cfc);
+    if (!same) {
+      if (cfr == cfr)
+        flush_cell<T>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w, a0, a1,
+                      a2, a3);
+      cfr = fr; cfc = fc;
+    }
+    a0 = same ? a0 + w0 : w0;
+    a1 = same ? a1 + w1 : w1;
+    a2 = same ? a2 + w2 : w2;
+    a3 = same ? a3 + w3 : w3;
   }
-  if (cr != INT_MIN) flush_cell<T>(iwe, Hp, Wp, cr, cc, a0, a1, a2, a3);
+  if (cfr == cfr)
+    flush_cell<T>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w, a0, a1, a2, a3);
 }
 
 // ---- backward ------------------------------------------------------------------------------------
@@ -201,13 +279,28 @@ __device__ __forceinline__ T fetch_g(const T* __restrict__ g, int Hp, int Wp, in
   return v;
 }
 
-template <typename T, int GSRC, bool HAS_W>
+// Exact handling of an event outside the fast range / on the image border: masked gathers.
+template <typename T, int GSRC>
+__device__ __noinline__ void bwd_event_exact(const T* __restrict__ g, int Hp, int Wp, int pad_h, int pad_w, T xw, T yw,
+                                             VarCoef<T> vc, T& dx, T& dy) {
+  dx = 0; dy = 0;
+  if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) return;  // all taps masked: zero gradient
+  const Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
+  const bool r1ok = t.r != INT_MAX, c1ok = t.c != INT_MAX;
+  const T g00 = fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c, vc);
+  const T g10 = r1ok ? fetch_g<T, GSRC>(g, Hp, Wp, t.r + 1, t.c, vc) : (T)0;
+  const T g01 = c1ok ? fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c + 1, vc) : (T)0;
+  const T g11 = (r1ok && c1ok) ? fetch_g<T, GSRC>(g, Hp, Wp, t.r + 1, t.c + 1, vc) : (T)0;
+  dx = ((T)1 - t.b) * (g10 - g00) + t.b * (g11 - g01);
+  dy = ((T)1 - t.a) * (g01 - g00) + t.a * (g11 - g10);
+}
+
+template <typename T, int GSRC, bool HAS_W, int EPT>
 __global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy,
                                                  const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
                                                  const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
                                                  const T* __restrict__ g, const double* __restrict__ acc, int omit,
                                                  double scale, T* __restrict__ dflow) {
-  constexpr int EPT = Ept<T>::bwd;
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
@@ -218,36 +311,61 @@ __global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const
     vc.mean = (T)(acc[0] / cnt);
     vc.cv = (T)(-2.0 * scale / (cnt - 1.0));
   }
-  T x[EPT], y[EPT], d[EPT], wt[EPT];
+  // fast range of cells whose four taps are all inside (and, for the cropped variance, all counted)
+  const int lo = (GSRC == 1 && omit) ? 1 : 0;
+  const unsigned r_span = (unsigned)max(Hp - 1 - 2 * lo, 0), c_span = (unsigned)max(Wp - 1 - 2 * lo, 0);
+  T x[EPT], y[EPT], d[EPT], wt[EPT], f0[EPT], f1[EPT];
+  int kk[EPT];
   load_block<T, EPT>(sx, base, n, (T)-2, x);
   load_block<T, EPT>(sy, base, n, (T)-2, y);
   load_block<T, EPT>(sd, base, n, (T)0, d);
   if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    const int k = (int)x[j] * W + (int)y[j];
+    kk[j] = (unsigned)k < (unsigned)hw ? k : -1;  // -1: parked (invalid) event or tail
+    const int ks = max(kk[j], 0);
+    f0[j] = __ldg(flow + ks);
+    f1[j] = __ldg(flow + hw + ks);
+  }
   int ck = -1;
   T s0 = 0, s1 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
-    const int k = (int)x[j] * W + (int)y[j];
-    if ((unsigned)k >= (unsigned)hw) continue;
-    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
-    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
-    if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) continue;  // all taps masked: zero gradient
-    const Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
-    const T g00 = fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c, vc);
-    const T g10 = fetch_g<T, GSRC>(g, Hp, Wp, t.r + 1, t.c, vc);
-    const T g01 = fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c + 1, vc);
-    const T g11 = fetch_g<T, GSRC>(g, Hp, Wp, t.r + 1, t.c + 1, vc);
-    T dx = ((T)1 - t.b) * (g10 - g00) + t.b * (g11 - g01);
-    T dy = ((T)1 - t.a) * (g01 - g00) + t.a * (g11 - g10);
+    if (kk[j] < 0) continue;
+    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], f0[j]));
+    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], f1[j]));
+    const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
+    T dx, dy;
+    bool fast = FastFloor<T>::in_range(xb, yb);
+    int r = 0, c = 0;
+    T a = 0, b = 0;
+    if (fast) {
+      const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
+      a = Rn<T>::sub(xw, fr);
+      b = Rn<T>::sub(yw, fc);
+      r = FastFloor<T>::to_int(fr) + pad_h;
+      c = FastFloor<T>::to_int(fc) + pad_w;
+      fast = (unsigned)(r - lo) < r_span && (unsigned)(c - lo) < c_span;
+    }
+    if (fast) {
+      const T* p = g + (r * Wp + c);
+      const T g00 = __ldg(p), g01 = __ldg(p + 1), g10 = __ldg(p + Wp), g11 = __ldg(p + Wp + 1);
+      dx = ((T)1 - b) * (g10 - g00) + b * (g11 - g01);
+      dy = ((T)1 - a) * (g01 - g00) + a * (g11 - g10);
+      if (GSRC == 1) { dx *= vc.cv; dy *= vc.cv; }  // differences: the mean cancels
+    } else {
+      bwd_event_exact<T, GSRC>(g, Hp, Wp, pad_h, pad_w, xw, yw, vc, dx, dy);
+    }
     if (HAS_W) { dx *= wt[j]; dy *= wt[j]; }
-    if (k != ck) {
-      if (ck >= 0) { red_add(dflow + ck, s0); red_add(dflow + hw + ck, s1); }
-      ck = k; s0 = 0; s1 = 0;
+    if (kk[j] != ck) {
+      if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
+      ck = kk[j]; s0 = 0; s1 = 0;
     }
     s0 -= d[j] * dx;
     s1 -= d[j] * dy;
   }
-  if (ck >= 0) { red_add(dflow + ck, s0); red_add(dflow + hw + ck, s1); }
+  if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -320,10 +438,19 @@ int window_splat_t(const void* window, int64_t n, int has_weight, const T* flow,
   const T* sy = reinterpret_cast<const T*>(b + L.off_y);
   const T* sd = reinterpret_cast<const T*>(b + L.off_d);
   const T* sw = reinterpret_cast<const T*>(b + L.off_w);
-  int64_t threads = (n + Ept<T>::splat - 1) / Ept<T>::splat;
+  static const int ept_env = env_int("EBOS_SPLAT_EPT");
+  const int ept = (ept_env == 4 || ept_env == 8 || ept_env == 16) ? ept_env : Ept<T>::splat;
+  int64_t threads = (n + ept - 1) / ept;
   unsigned grid = (unsigned)((threads + 255) / 256);
-  if (has_weight) k_win_splat<T, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);
-  else k_win_splat<T, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);
+#define EBOS_SPLAT_LAUNCH(E)                                                                                         \
+  do {                                                                                                               \
+    if (has_weight) k_win_splat<T, true, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);  \
+    else k_win_splat<T, false, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);            \
+  } while (0)
+  if (ept == 4) EBOS_SPLAT_LAUNCH(4);
+  else if (ept == 16) EBOS_SPLAT_LAUNCH(16);
+  else EBOS_SPLAT_LAUNCH(8);
+#undef EBOS_SPLAT_LAUNCH
   EBOS_LAUNCH_CHECK("ebos_window_splat");
   return EBOS_OK;
 }
@@ -339,20 +466,24 @@ int window_backward_t(const void* window, int64_t n, int has_weight, const T* fl
   const T* sy = reinterpret_cast<const T*>(b + L.off_y);
   const T* sd = reinterpret_cast<const T*>(b + L.off_d);
   const T* sw = reinterpret_cast<const T*>(b + L.off_w);
-  int64_t threads = (n + Ept<T>::bwd - 1) / Ept<T>::bwd;
+  static const int ept_env = env_int("EBOS_BWD_EPT");
+  const int ept = (ept_env == 4 || ept_env == 8) ? ept_env : Ept<T>::bwd;
+  int64_t threads = (n + ept - 1) / ept;
   unsigned grid = (unsigned)((threads + 255) / 256);
   const bool affine = grad_iwe == nullptr;
-  if (affine) {
-    if (kind != EBOS_COST_VARIANCE || !iwe || !acc) {
-      set_error("ebos_window_backward: grad_iwe == NULL needs kind == VARIANCE with iwe and acc");
-      return EBOS_ERR_BAD_ARG;
-    }
-    if (has_weight) k_win_bwd<T, 1, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe, acc, omit_boundary, scale, dflow);
-    else k_win_bwd<T, 1, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe, acc, omit_boundary, scale, dflow);
-  } else {
-    if (has_weight) k_win_bwd<T, 0, true><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, grad_iwe, acc, omit_boundary, scale, dflow);
-    else k_win_bwd<T, 0, false><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, grad_iwe, acc, omit_boundary, scale, dflow);
+  if (affine && (kind != EBOS_COST_VARIANCE || !iwe || !acc)) {
+    set_error("ebos_window_backward: grad_iwe == NULL needs kind == VARIANCE with iwe and acc");
+    return EBOS_ERR_BAD_ARG;
   }
+  const T* gsrc = affine ? iwe : grad_iwe;
+#define EBOS_BWD_LAUNCH(G, E)                                                                                                    \
+  do {                                                                                                                           \
+    if (has_weight) k_win_bwd<T, G, true, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);  \
+    else k_win_bwd<T, G, false, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);            \
+  } while (0)
+  if (affine) { if (ept == 8) EBOS_BWD_LAUNCH(1, 8); else EBOS_BWD_LAUNCH(1, 4); }
+  else { if (ept == 8) EBOS_BWD_LAUNCH(0, 8); else EBOS_BWD_LAUNCH(0, 4); }
+#undef EBOS_BWD_LAUNCH
   EBOS_LAUNCH_CHECK("ebos_window_backward");
   return EBOS_OK;
 }

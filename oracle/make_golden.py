@@ -211,6 +211,30 @@ def main():
         g[f"solve_{tag}/history"] = np.array(hist)
         g[f"solve_{tag}/cfg"] = np.array([H, W, iters, 0.05, 0.5])
 
+    # Same loop from a tie-free initial iterate.  From an all-zero start the objective sits on exact ties
+    # (sign(0) in the TV term, exactly-zero data gradients): a 1e-17 rounding residual is turned by Adam into a
+    # 1e-10 step that breaks the tie and changes the gradient by O(1e-4), so two correct implementations (or two
+    # torch versions) end up +-lr apart at those pixels.  A random initial flow removes the ties.
+    for tag, dt, iters in (("f64", np.float64, 40), ("f32", np.float32, 40), ("f64_long", np.float64, 150)):
+        H, W, N = 24, 32, 4000
+        rng = np.random.default_rng(55)
+        ev = torch.from_numpy(make_events(rng, N, H, W, dtype=dt))
+        init = np.random.default_rng(56).uniform(-0.5, 0.5, (2, H, W)).astype(dt)
+        x0 = torch.from_numpy(init.copy()).requires_grad_()
+        optimizer = torch.optim.Adam([x0], lr=0.05)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, iters, 0.1)
+        hist = []
+        for it in range(iters):
+            optimizer.zero_grad()
+            loss, _ = composed_loss(ev, x0, H, W, "gradient_magnitude", False, 0.5, 0, "64" if dt == np.float64 else "32")
+            hist.append(float(loss.detach()))
+            loss.backward()
+            optimizer.step()
+            scheduler.step()
+        g[f"solve_init_{tag}/events"], g[f"solve_init_{tag}/flow0"] = ev.numpy(), init
+        g[f"solve_init_{tag}/flow"], g[f"solve_init_{tag}/history"] = x0.detach().numpy(), np.array(hist)
+        g[f"solve_init_{tag}/cfg"] = np.array([H, W, iters, 0.05, 0.5])
+
     path = os.path.join(OUT_DIR, "reference_path_v1.npz")
     np.savez_compressed(path, **g)
     print(f"wrote {path}: {len(g)} arrays, {os.path.getsize(path) / 1e6:.2f} MB; torch {torch.__version__}")
