@@ -159,6 +159,11 @@ __device__ __forceinline__ void red_add_nc(float* p, float v) {
 __device__ __forceinline__ void red_add_nc(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
+// 16-byte vector reduction (REDG.E.ADD.F32x4): one LSU lane-op for four consecutive floats.  Measured on
+// B200 (profiles/microbench/r01_red_throughput.txt): a RED lane-op costs ~1.3 SM-cycles whatever its width.
+__device__ __forceinline__ void red_add_v4(float* p16, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p16), "f"(a), "f"(b), "f"(c), "f"(d));
+}
 
 // ---- block reductions (warp shuffle) ----------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -143,46 +143,67 @@ __global__ void __launch_bounds__(256) k_gradmag(const T* __restrict__ iwe, int 
 }
 
 // ---- total variation of the flow: value + gradient -------------------------------------------------
-// torch.gradient (spacing 1, edge_order 1): interior (f[i+1]-f[i-1])/2, edges one-sided.
-template <typename T>
-__device__ __forceinline__ T grad1d(const T* __restrict__ f, int i, int n, int64_t stride) {
-  if (i == 0) return __ldg(f + stride) - __ldg(f);
-  if (i == n - 1) return __ldg(f + (int64_t)(n - 1) * stride) - __ldg(f + (int64_t)(n - 2) * stride);
-  return (__ldg(f + (int64_t)(i + 1) * stride) - __ldg(f + (int64_t)(i - 1) * stride)) * (T)0.5;
-}
+// torch.gradient (spacing 1, edge_order 1): interior G(q) = (f[q+1]-f[q-1])/2, edges one-sided.
+// d/df[i] of sum_q |G(q) w(q)|  =  sum_q s(q) dG(q)/df[i],  s(q) = sign(G(q) w(q)) w(q).  Only q = i-1, i, i+1
+// touch f[i]:   q=i-1: +1/2 (or +1 when q is the first sample);  q=i+1: -1/2 (or -1 when q is the last
+// sample);  q=i: -1 at the first sample, +1 at the last, 0 inside.  The five samples f[i-2..i+2] suffice.
 template <typename T>
 __device__ __forceinline__ T sgn(T v) { return (v > (T)0) ? (T)1 : ((v < (T)0) ? (T)-1 : (T)0); }
 
-// adjoint of grad1d along one axis at index i: sum_q s(q) * d grad(q) / d f[i]
-template <typename T, typename S>
-__device__ __forceinline__ T grad1d_adjoint(int i, int n, S s) {
+// v[0..4] = f[i-2..i+2] (entries outside [0,n) are never used), w[0..2] = weights at i-1, i, i+1.
+// Returns the adjoint at i and the forward |G(i) w(i)| term through `absterm`.
+template <typename T>
+__device__ __forceinline__ T tv_axis(const T v[5], const T w[3], int i, int n, T& absterm) {
+  const bool first = i == 0, last = i == n - 1;
+  // G(i)
+  const T gi = first ? (v[3] - v[2]) : (last ? (v[2] - v[1]) : (v[3] - v[1]) * (T)0.5);
+  const T giw = gi * w[1];
+  absterm = giw < (T)0 ? -giw : giw;
   T out = 0;
-  if (i + 1 <= n - 2) out -= (T)0.5 * s(i + 1);          // interior q = i+1
-  if (i - 1 >= 1) out += (T)0.5 * s(i - 1);              // interior q = i-1
-  if (i == 0) out -= s(0);
-  if (i == 1) out += s(0);
-  if (i == n - 1) out += s(n - 1);
-  if (i == n - 2) out -= s(n - 1);
+  if (first) out -= sgn(giw) * w[1];
+  if (last) out += sgn(giw) * w[1];
+  if (i >= 1) {  // q = i-1
+    const bool qfirst = i - 1 == 0;
+    const T gq = qfirst ? (v[2] - v[1]) : (v[2] - v[0]) * (T)0.5;
+    out += (qfirst ? (T)1 : (T)0.5) * sgn(gq * w[0]) * w[0];
+  }
+  if (i <= n - 2) {  // q = i+1
+    const bool qlast = i + 1 == n - 1;
+    const T gq = qlast ? (v[3] - v[2]) : (v[4] - v[2]) * (T)0.5;
+    out -= (qlast ? (T)1 : (T)0.5) * sgn(gq * w[2]) * w[2];
+  }
   return out;
 }
 
-// grid: (ceil(W/256), H, 2 channels); no integer divisions, rows coalesced, neighbours from L1
+// block (32, 8): 32 columns x 8 rows of one channel; grid (ceil(W/32), ceil(H/8), 2)
 template <typename T, bool HAS_WTS>
 __global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, const T* __restrict__ weights, int H, int W,
                                                  T coef, double* __restrict__ acc, T* __restrict__ dflow) {
   // coef = tv_scale / (2*H*W)
   __shared__ double sm[32];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y, ch = blockIdx.z;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = blockIdx.y * 8 + (threadIdx.x >> 5), ch = blockIdx.z;
   double part = 0.0;
-  if (c < W) {
+  if (c < W && r < H) {
     const T* f = flow + (int64_t)ch * H * W;
-    auto wgt = [&](int rr, int cc) -> T { return HAS_WTS ? __ldg(weights + (int64_t)rr * W + cc) : (T)1; };
-    auto s_row = [&](int q) -> T { const T w = wgt(q, c); return sgn<T>(grad1d<T>(f + c, q, H, W) * w) * w; };
-    auto s_col = [&](int q) -> T { const T w = wgt(r, q); return sgn<T>(grad1d<T>(f + (int64_t)r * W, q, W, 1) * w) * w; };
-    const T w_here = wgt(r, c);
-    const T gr = grad1d<T>(f + c, r, H, W) * w_here, gc = grad1d<T>(f + (int64_t)r * W, c, W, 1) * w_here;
-    part = (double)(gr < 0 ? -gr : gr) + (double)(gc < 0 ? -gc : gc);
-    dflow[(int64_t)ch * H * W + (int64_t)r * W + c] = coef * (grad1d_adjoint<T>(r, H, s_row) + grad1d_adjoint<T>(c, W, s_col));
+    T vr[5], vc[5], wr[3] = {(T)1, (T)1, (T)1}, wc[3] = {(T)1, (T)1, (T)1};
+#pragma unroll
+    for (int o = -2; o <= 2; ++o) {
+      const int rr = min(max(r + o, 0), H - 1), cc = min(max(c + o, 0), W - 1);
+      vr[o + 2] = __ldg(f + (int64_t)rr * W + c);
+      vc[o + 2] = __ldg(f + (int64_t)r * W + cc);
+    }
+    if (HAS_WTS) {
+#pragma unroll
+      for (int o = -1; o <= 1; ++o) {
+        const int rr = min(max(r + o, 0), H - 1), cc = min(max(c + o, 0), W - 1);
+        wr[o + 1] = __ldg(weights + (int64_t)rr * W + c);
+        wc[o + 1] = __ldg(weights + (int64_t)r * W + cc);
+      }
+    }
+    T ar, ac;
+    const T adj = tv_axis<T>(vr, wr, r, H, ar) + tv_axis<T>(vc, wc, c, W, ac);
+    part = (double)ar + (double)ac;
+    dflow[(int64_t)ch * H * W + (int64_t)r * W + c] = coef * adj;
   }
   part = block_sum(part, sm);
   if (threadIdx.x == 0 && acc) atomicAdd(acc + 3, part);
@@ -265,7 +286,7 @@ int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, do
     return EBOS_ERR_BAD_ARG;
   }
   const T coef = (T)(tv_scale / (2.0 * (double)H * (double)W));
-  dim3 grid((W + 255) / 256, H, 2);
+  dim3 grid((W + 31) / 32, (H + 7) / 8, 2);
   if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   EBOS_LAUNCH_CHECK("ebos_flow_tv");

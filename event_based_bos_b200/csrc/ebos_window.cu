@@ -180,12 +180,27 @@ __device__ __noinline__ void splat_event_exact(T* __restrict__ iwe, int Hp, int 
   }
 }
 
-template <typename T>
+// Flush one run: add the four tap sums of cell (r,c).  The kernel is bound by RED lane-ops (LSU), not by
+// bytes: when the row stride allows 16-byte alignment (VEC) the two column-adjacent taps of a row go out
+// as ONE aligned red.v4 (zeros in the unused lanes), i.e. 2 lane-ops per cell instead of 4, unless the
+// pair straddles a 16-byte boundary (c % 4 == 3).
+template <typename T, bool VEC>
 __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, int Hm1, int Wm1, int r, int c, T a0,
                                            T a1, T a2, T a3) {
   if ((unsigned)r < (unsigned)Hm1 && (unsigned)c < (unsigned)Wm1) {
     // all four taps inside: the common case
     T* p = iwe + (r * Wp + c);
+    if constexpr (VEC) {
+      const int j = c & 3;
+      if (j != 3) {
+        float* q = reinterpret_cast<float*>(p) - j;
+        const float z = 0.0f;
+        const bool j0 = j == 0, j1 = j == 1, j2 = j == 2;
+        red_add_v4(q, j0 ? a0 : z, j0 ? a2 : (j1 ? a0 : z), j1 ? a2 : (j2 ? a0 : z), j2 ? a2 : z);
+        red_add_v4(q + Wp, j0 ? a1 : z, j0 ? a3 : (j1 ? a1 : z), j1 ? a3 : (j2 ? a1 : z), j2 ? a3 : z);
+        return;
+      }
+    }
     red_add_nc(p, a0);
     red_add_nc(p + 1, a2);
     p += Wp;
@@ -202,8 +217,8 @@ __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, 
   }
 }
 
-template <typename T, bool HAS_W, int EPT>
-__global__ void __launch_bounds__(256) k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy,
+template <typename T, bool HAS_W, int EPT, bool VEC>
+__global__ void __launch_bounds__(256, (EPT <= 8 && sizeof(T) == 4) ? 6 : 1) k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy,
                                                    const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
                                                    const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
                                                    T* __restrict__ iwe) {
@@ -211,29 +226,20 @@ __global__ void __launch_bounds__(256) k_win_splat(const T* __restrict__ sx, con
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, Hm1 = Hp - 1, Wm1 = Wp - 1;
   const int hw = H * W;
-  T x[EPT], y[EPT], d[EPT], wt[EPT], f0[EPT], f1[EPT];
+  T x[EPT], y[EPT], d[EPT], wt[EPT];
   load_block<T, EPT>(sx, base, n, (T)-2, x);
   load_block<T, EPT>(sy, base, n, (T)-2, y);
   load_block<T, EPT>(sd, base, n, (T)0, d);
   if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
-  // all flow gathers are issued before the first reduction (events of one pixel hit the same sector)
-  bool ok[EPT];
-#pragma unroll
-  for (int j = 0; j < EPT; ++j) {
-    const int k = (int)x[j] * W + (int)y[j];
-    ok[j] = (unsigned)k < (unsigned)hw;  // false: parked (invalid) event or tail
-    const int kk = ok[j] ? k : 0;
-    f0[j] = __ldg(flow + kk);
-    f1[j] = __ldg(flow + hw + kk);
-  }
   // current run: floor values of the cell (NaN = none) and the four tap sums
-  T cfr = Rn<T>::div((T)0, (T)0) * (T)0 + (T)NAN, cfc = (T)0;
+  T cfr = (T)NAN, cfc = (T)0;
   T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
-    if (!ok[j]) continue;
-    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], f0[j]));
-    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], f1[j]));
+    const int k = (int)x[j] * W + (int)y[j];
+    if ((unsigned)k >= (unsigned)hw) continue;  // parked (invalid) event or tail
+    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
+    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
     const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
     if (!FastFloor<T>::in_range(xb, yb)) {
       splat_event_exact<T>(iwe, Hp, Wp, pad_h, pad_w, xw, yw, HAS_W ? wt[j] : (T)1);
@@ -250,8 +256,8 @@ __global__ void __launch_bounds__(256) k_win_splat(const T* __restrict__ sx, con
     const bool same = (fr == cfr) & (fc == cfc);
     if (!same) {
       if (cfr == cfr)
-        flush_cell<T>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w, a0, a1,
-                      a2, a3);
+        flush_cell<T, VEC>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w,
+                           a0, a1, a2, a3);
       cfr = fr; cfc = fc;
     }
     a0 = same ? a0 + w0 : w0;
@@ -260,7 +266,8 @@ __global__ void __launch_bounds__(256) k_win_splat(const T* __restrict__ sx, con
     a3 = same ? a3 + w3 : w3;
   }
   if (cfr == cfr)
-    flush_cell<T>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w, a0, a1, a2, a3);
+    flush_cell<T, VEC>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w, a0, a1,
+                       a2, a3);
 }
 
 // ---- backward ------------------------------------------------------------------------------------
@@ -295,12 +302,31 @@ __device__ __noinline__ void bwd_event_exact(const T* __restrict__ g, int Hp, in
   dy = ((T)1 - t.a) * (g01 - g00) + t.a * (g11 - g10);
 }
 
-template <typename T, int GSRC, bool HAS_W, int EPT>
-__global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy,
-                                                 const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
-                                                 const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
-                                                 const T* __restrict__ g, const double* __restrict__ acc, int omit,
-                                                 double scale, T* __restrict__ dflow) {
+// The backward was bound by L1 wavefronts of its four scalar gathers per event (ncu r01: l1tex 71 %).
+// With a 16-byte aligned plane (VEC) the two column-adjacent taps of a row come from ONE aligned float4
+// load (unless c % 4 == 3), i.e. 2 lane-loads per event instead of 4.
+template <bool VEC>
+__device__ __forceinline__ void load_pair(const float* __restrict__ p, int j, float& lo, float& hi) {
+  if (VEC && j != 3) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p - j));
+    lo = j == 0 ? v.x : (j == 1 ? v.y : v.z);
+    hi = j == 0 ? v.y : (j == 1 ? v.z : v.w);
+  } else {
+    lo = __ldg(p);
+    hi = __ldg(p + 1);
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void load_pair(const double* __restrict__ p, int, double& lo, double& hi) {
+  lo = __ldg(p);
+  hi = __ldg(p + 1);
+}
+
+template <typename T, int GSRC, bool HAS_W, int EPT, bool VEC>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 4) ? 6 : 1)
+k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd, const T* __restrict__ sw,
+          int64_t n, const T* __restrict__ flow, int H, int W, int pad_h, int pad_w, const T* __restrict__ g,
+          const double* __restrict__ acc, int omit, double scale, T* __restrict__ dflow) {
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
@@ -314,27 +340,19 @@ __global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const
   // fast range of cells whose four taps are all inside (and, for the cropped variance, all counted)
   const int lo = (GSRC == 1 && omit) ? 1 : 0;
   const unsigned r_span = (unsigned)max(Hp - 1 - 2 * lo, 0), c_span = (unsigned)max(Wp - 1 - 2 * lo, 0);
-  T x[EPT], y[EPT], d[EPT], wt[EPT], f0[EPT], f1[EPT];
-  int kk[EPT];
+  T x[EPT], y[EPT], d[EPT], wt[EPT];
   load_block<T, EPT>(sx, base, n, (T)-2, x);
   load_block<T, EPT>(sy, base, n, (T)-2, y);
   load_block<T, EPT>(sd, base, n, (T)0, d);
   if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
-#pragma unroll
-  for (int j = 0; j < EPT; ++j) {
-    const int k = (int)x[j] * W + (int)y[j];
-    kk[j] = (unsigned)k < (unsigned)hw ? k : -1;  // -1: parked (invalid) event or tail
-    const int ks = max(kk[j], 0);
-    f0[j] = __ldg(flow + ks);
-    f1[j] = __ldg(flow + hw + ks);
-  }
   int ck = -1;
   T s0 = 0, s1 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
-    if (kk[j] < 0) continue;
-    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], f0[j]));
-    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], f1[j]));
+    const int k = (int)x[j] * W + (int)y[j];
+    if ((unsigned)k >= (unsigned)hw) continue;  // parked (invalid) event or tail
+    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
+    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
     const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
     T dx, dy;
     bool fast = FastFloor<T>::in_range(xb, yb);
@@ -350,7 +368,9 @@ __global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const
     }
     if (fast) {
       const T* p = g + (r * Wp + c);
-      const T g00 = __ldg(p), g01 = __ldg(p + 1), g10 = __ldg(p + Wp), g11 = __ldg(p + Wp + 1);
+      T g00, g01, g10, g11;
+      load_pair<VEC>(p, c & 3, g00, g01);
+      load_pair<VEC>(p + Wp, c & 3, g10, g11);
       dx = ((T)1 - b) * (g10 - g00) + b * (g11 - g01);
       dy = ((T)1 - a) * (g01 - g00) + a * (g11 - g10);
       if (GSRC == 1) { dx *= vc.cv; dy *= vc.cv; }  // differences: the mean cancels
@@ -358,9 +378,9 @@ __global__ void __launch_bounds__(256) k_win_bwd(const T* __restrict__ sx, const
       bwd_event_exact<T, GSRC>(g, Hp, Wp, pad_h, pad_w, xw, yw, vc, dx, dy);
     }
     if (HAS_W) { dx *= wt[j]; dy *= wt[j]; }
-    if (kk[j] != ck) {
+    if (k != ck) {
       if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
-      ck = kk[j]; s0 = 0; s1 = 0;
+      ck = k; s0 = 0; s1 = 0;
     }
     s0 -= d[j] * dx;
     s1 -= d[j] * dy;
@@ -442,14 +462,20 @@ int window_splat_t(const void* window, int64_t n, int has_weight, const T* flow,
   const int ept = (ept_env == 4 || ept_env == 8 || ept_env == 16) ? ept_env : Ept<T>::splat;
   int64_t threads = (n + ept - 1) / ept;
   unsigned grid = (unsigned)((threads + 255) / 256);
-#define EBOS_SPLAT_LAUNCH(E)                                                                                         \
-  do {                                                                                                               \
-    if (has_weight) k_win_splat<T, true, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);  \
-    else k_win_splat<T, false, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);            \
+  // vector REDs need fp32, a 16-byte aligned plane and a row stride that keeps the alignment
+  static const int novec_env = env_int("EBOS_NO_VEC");
+  const bool vec = sizeof(T) == 4 && !novec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(iwe) & 15) == 0);
+#define EBOS_SPLAT_LAUNCH(E, V)                                                                                         \
+  do {                                                                                                                  \
+    if (has_weight) k_win_splat<T, true, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);  \
+    else k_win_splat<T, false, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);            \
   } while (0)
-  if (ept == 4) EBOS_SPLAT_LAUNCH(4);
-  else if (ept == 16) EBOS_SPLAT_LAUNCH(16);
-  else EBOS_SPLAT_LAUNCH(8);
+  if constexpr (sizeof(T) == 4) {
+    if (vec) { if (ept == 4) EBOS_SPLAT_LAUNCH(4, true); else if (ept == 16) EBOS_SPLAT_LAUNCH(16, true); else EBOS_SPLAT_LAUNCH(8, true); }
+    else { if (ept == 4) EBOS_SPLAT_LAUNCH(4, false); else if (ept == 16) EBOS_SPLAT_LAUNCH(16, false); else EBOS_SPLAT_LAUNCH(8, false); }
+  } else {
+    if (ept == 8) EBOS_SPLAT_LAUNCH(8, false); else EBOS_SPLAT_LAUNCH(4, false);
+  }
 #undef EBOS_SPLAT_LAUNCH
   EBOS_LAUNCH_CHECK("ebos_window_splat");
   return EBOS_OK;
@@ -476,13 +502,21 @@ int window_backward_t(const void* window, int64_t n, int has_weight, const T* fl
     return EBOS_ERR_BAD_ARG;
   }
   const T* gsrc = affine ? iwe : grad_iwe;
-#define EBOS_BWD_LAUNCH(G, E)                                                                                                    \
-  do {                                                                                                                           \
-    if (has_weight) k_win_bwd<T, G, true, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);  \
-    else k_win_bwd<T, G, false, E><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);            \
+  static const int novec_env = env_int("EBOS_NO_VEC");
+  const int Wp = W + 2 * pad_w;
+  const bool vec = sizeof(T) == 4 && !novec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
+#define EBOS_BWD_LAUNCH(G, E, V)                                                                                                    \
+  do {                                                                                                                              \
+    if (has_weight) k_win_bwd<T, G, true, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);  \
+    else k_win_bwd<T, G, false, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);            \
   } while (0)
-  if (affine) { if (ept == 8) EBOS_BWD_LAUNCH(1, 8); else EBOS_BWD_LAUNCH(1, 4); }
-  else { if (ept == 8) EBOS_BWD_LAUNCH(0, 8); else EBOS_BWD_LAUNCH(0, 4); }
+#define EBOS_BWD_PICK(G)                                                                       \
+  do {                                                                                         \
+    if (vec) { if (ept == 8) EBOS_BWD_LAUNCH(G, 8, true); else EBOS_BWD_LAUNCH(G, 4, true); }   \
+    else { if (ept == 8) EBOS_BWD_LAUNCH(G, 8, false); else EBOS_BWD_LAUNCH(G, 4, false); }     \
+  } while (0)
+  if (affine) EBOS_BWD_PICK(1); else EBOS_BWD_PICK(0);
+#undef EBOS_BWD_PICK
 #undef EBOS_BWD_LAUNCH
   EBOS_LAUNCH_CHECK("ebos_window_backward");
   return EBOS_OK;
