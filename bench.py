@@ -107,6 +107,28 @@ def cuda_time_ms(fn, reps: int):
     return a.elapsed_time(b) / reps
 
 
+def graph_time_ms(fn, reps: int):
+    """Average device ms per call of `fn`, with `reps` calls captured in ONE CUDA graph so that host launch
+    overhead (ctypes + driver, ~10 us per call) does not hide short kernels.  CUDA events around the replay."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(reps):
+            fn()
+    graph.replay()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def dist_setup(n_gpus: int):
     import torch.distributed as dist
 
@@ -212,7 +234,7 @@ def run_fused(args, rank, world, local):
     flow_host = torch.from_numpy(synthetic_flow((H, W), seed=rank)).pin_memory()
     ev = ev_host.to(dev, non_blocking=True)
     flow = flow_host.to(dev, non_blocking=True)
-    window = ops.PreparedWindow(ev, (H, W), "first", True)
+    window = ops.PreparedWindow(ev, (H, W), "first", True, allow_packed=not args.no_packed)
     ws = ops.CmaxWorkspace(H, W, (0, 0), dev)
 
     def step():
@@ -231,10 +253,10 @@ def run_fused(args, rank, world, local):
         p = _capi.ptr
 
         def splat_only():
-            lib.ebos_window_splat(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, 0, p(ws.iwe), st)
+            lib.ebos_window_splat(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.iwe), st)
 
         def bwd_only():
-            lib.ebos_window_backward(p(window.buffer), window.n, 0, p(flow), H, W, 0, 0, 0, p(ws.grad_iwe),
+            lib.ebos_window_backward(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.grad_iwe),
                                      _capi.COST_GRADMAG, p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), st)
 
         def cost_only():
@@ -243,9 +265,10 @@ def run_fused(args, rank, world, local):
         def tv_only():
             lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws.acc), p(ws.dflow), st)
 
-        k_ms = {name: cuda_time_ms(fn, args.steps) for name, fn in
+        k_ms = {name: graph_time_ms(fn, args.steps) for name, fn in
                 (("window_splat(+memset)", splat_only), ("window_backward", bwd_only), ("iwe_cost_gradmag", cost_only),
                  ("flow_tv", tv_only))}
+        step_graph_ms = max_over_ranks(graph_time_ms(step, args.steps), world)
         clocks.soak(step)
     clk = clocks.summary()
 
@@ -258,7 +281,7 @@ def run_fused(args, rank, world, local):
         def e2e_step():
             e = ev_host.to(dev, non_blocking=True)
             f = flow_host.to(dev, non_blocking=True)
-            win = ops.PreparedWindow(e, (H, W), "first", True, validate=False)
+            win = ops.PreparedWindow(e, (H, W), "first", True, validate=False, allow_packed=not args.no_packed)
             loss, grad = ops.cmax_value_and_grad(win, f, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
             loss_host.copy_(loss, non_blocking=True)
             grad_host.copy_(grad, non_blocking=True)
@@ -293,6 +316,8 @@ def run_fused(args, rank, world, local):
                      "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()}},
         "gpu_launches": 5 * args.steps,
     }
+    line["config"]["window_layout"] = "packed (row,col,dt) 8 B/event" if window.packed else "generic (x,y,dt) 12 B/event"
+    line["step_ms_graph_replay"] = round(step_graph_ms, 4)
     if e2e_ms is not None:
         line["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "events/s", "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": 16 * n + 2 * P_BYTES, "d2h_bytes_per_step": 2 * P_BYTES + 4,
@@ -367,6 +392,7 @@ def main():
     ap.add_argument("--solve-iters", type=int, default=600)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

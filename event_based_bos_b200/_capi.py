@@ -19,6 +19,8 @@ EBOS_F32, EBOS_F64 = 0, 1
 DIR_FIRST, DIR_LAST, DIR_FRAC = 0, 1, 2
 COST_NONE, COST_VARIANCE, COST_GRADMAG = 0, 1, 2
 STATUS_PIXEL_OOB = 1
+STATUS_PACKED = 2
+WIN_HAS_WEIGHT, WIN_PACKED = 1, 2
 
 # name -> (restype, argtypes); every symbol include/ebos.h declares.
 SIGNATURES = {
@@ -40,7 +42,7 @@ SIGNATURES = {
     "ebos_window_bytes": (c_size_t, [c_int64, c_int]),
     "ebos_window_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "ebos_window_prepare": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_int,
-                                    c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                    c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "ebos_window_info": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "ebos_window_splat": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),

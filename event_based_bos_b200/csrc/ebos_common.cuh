@@ -192,6 +192,8 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 struct WindowHeader {
   double t_ref, period, t_min, t_max;       // stored as double; exact for fp32 windows as well
   unsigned long long enc_min, enc_max;      // order-preserving encodings used by the atomic min/max pass
+  int not_packable;                         // some coordinate is not a small non-negative integer
+  int packed;                               // 1: x slot holds (row << 16 | col) as uint32, y slot unused
 };
 static_assert(sizeof(WindowHeader) <= 256, "header must fit its slot");
 

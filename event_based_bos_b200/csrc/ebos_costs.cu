@@ -14,9 +14,9 @@
 
 namespace ebos {
 
-int window_splat_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int window_splat_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                         int pad_w, int dtype, void* iwe, cudaStream_t st);
-int window_backward_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int window_backward_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                            int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
                            int omit_boundary, double scale, void* dflow, cudaStream_t st);
 
@@ -63,8 +63,33 @@ __global__ void __launch_bounds__(256) k_var_grad(const T* __restrict__ iwe, int
 
 // ---- gradient magnitude: Sobel forward + adjoint in one tiled pass ---------------------------------
 constexpr int GTH = 16, GTW = 64;  // output tile (rows x cols); 256 threads, 4 pixels each
+
+// Adjoint at a pixel on the image border: the replicate padding folds the padded positions that clamp
+// to p back onto it.  Rare (perimeter only), kept out of line so that the interior path stays lean.
 template <typename T>
-__global__ void __launch_bounds__(256) k_gradmag(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef,
+__device__ __noinline__ T gradmag_border_adjoint(const T* __restrict__ sDx, const T* __restrict__ sDy, int pitch, int r,
+                                                 int c, int r0, int c0, int Hp, int Wp) {
+  T out = 0;
+  for (int pr = (r == 0 ? -1 : r); pr <= (r == Hp - 1 ? Hp : r); ++pr) {
+    for (int pc = (c == 0 ? -1 : c); pc <= (c == Wp - 1 ? Wp : c); ++pc) {
+      for (int u = -1; u <= 1; ++u) {
+        for (int v = -1; v <= 1; ++v) {
+          const int qr = pr - u, qc = pc - v;
+          if (qr < 0 || qr >= Hp || qc < 0 || qc >= Wp) continue;
+          const int sr = qr - (r0 - 1), sc = qc - (c0 - 1);
+          if (sr < 0 || sr >= GTH + 2 || sc < 0 || sc >= GTW + 2) continue;
+          const T kx = (T)(u * (2 - (v < 0 ? -v : v)));
+          const T ky = (T)(v * (2 - (u < 0 ? -u : u)));
+          out += kx * sDx[sr * pitch + sc] + ky * sDy[sr * pitch + sc];
+        }
+      }
+    }
+  }
+  return out;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) k_gradmag(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef,
                                                  double* __restrict__ acc, T* __restrict__ g) {
   // coef = -2 * scale / (8 * n_el): D = coef * gx is dL/d(Sx) including the forward's 1/8.
   __shared__ T sI[GTH + 4][GTW + 4 + 1];
@@ -120,21 +145,7 @@ __global__ void __launch_bounds__(256) k_gradmag(const T* __restrict__ iwe, int 
             - (sDy[sr + 1][sc + 1] + (T)2 * sDy[sr][sc + 1] + sDy[sr - 1][sc + 1])
             + (sDy[sr + 1][sc - 1] + (T)2 * sDy[sr][sc - 1] + sDy[sr - 1][sc - 1]);
     } else {
-      for (int pr = (r == 0 ? -1 : r); pr <= (r == Hp - 1 ? Hp : r); ++pr) {
-        for (int pc = (c == 0 ? -1 : c); pc <= (c == Wp - 1 ? Wp : c); ++pc) {
-          for (int u = -1; u <= 1; ++u) {
-            for (int v = -1; v <= 1; ++v) {
-              const int qr = pr - u, qc = pc - v;
-              if (qr < 0 || qr >= Hp || qc < 0 || qc >= Wp) continue;
-              const int sr = qr - (r0 - 1), sc = qc - (c0 - 1);
-              if (sr < 0 || sr >= GTH + 2 || sc < 0 || sc >= GTW + 2) continue;
-              const T kx = (T)(u * (2 - (v < 0 ? -v : v)));
-              const T ky = (T)(v * (2 - (u < 0 ? -u : u)));
-              out += kx * sDx[sr][sc] + ky * sDy[sr][sc];
-            }
-          }
-        }
-      }
+      out = gradmag_border_adjoint<T>(&sDx[0][0], &sDy[0][0], GTW + 2 + 1, r, c, r0, c0, Hp, Wp);
     }
     g[(int64_t)r * Wp + c] = out;
   }
@@ -348,7 +359,7 @@ int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W
   return EBOS_OK;
 }
 
-int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                              int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
                              double* acc, void* stream) {
@@ -362,7 +373,7 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, cons
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
-  int rc = window_splat_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, iwe, st);
+  int rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st);
   if (rc) return rc;
   // variance: no gradient plane, the backward derives it from (iwe, acc)
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
@@ -376,7 +387,7 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, cons
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, st);
   }
   if (rc) return rc;
-  rc = window_backward_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc,
+  rc = window_backward_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc,
                               omit_boundary, data_scale, dflow, st);
   if (rc) return rc;
   if (dtype == EBOS_F64)

@@ -39,6 +39,8 @@ static int env_int(const char* name) {
 __global__ void k_win_hdr_init(WindowHeader* h) {
   h->enc_min = ~0ull;
   h->enc_max = 0ull;
+  h->not_packable = 0;
+  h->packed = 0;
 }
 
 template <typename T>
@@ -76,22 +78,30 @@ __global__ void k_win_hdr_final(WindowHeader* h, int direction, double frac, con
 }
 
 // key = origin pixel k (src/warp.py:334); an event whose k is outside the grid is flagged and
-// parked behind all valid pixels.
+// parked behind all valid pixels.  Also records whether any coordinate is NOT a small non-negative
+// integer (then the packed (row,col) layout cannot be used).
 template <typename T>
 __global__ void __launch_bounds__(256) k_win_keys(const T* __restrict__ ev, int64_t n, int H, int W,
                                                   unsigned int* __restrict__ keys, int* __restrict__ idx,
-                                                  int32_t* __restrict__ status) {
+                                                  int32_t* __restrict__ status, WindowHeader* __restrict__ h) {
   const int64_t hw = (int64_t)H * W;
-  bool bad = false;
+  bool bad = false, frac = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     T x = __ldg(ev + 4 * i), y = __ldg(ev + 4 * i + 1);
     int64_t k = (int64_t)x * W + (int64_t)y;
     bool ok = k >= 0 && k < hw && Rn<T>::finite(x) && Rn<T>::finite(y);
     bad |= !ok;
+    frac |= !(ok && x >= (T)0 && y >= (T)0 && x < (T)65536 && y < (T)65536 && x == (T)(int)x && y == (T)(int)y);
     keys[i] = ok ? (unsigned int)k : (unsigned int)hw;
     idx[i] = (int)i;
   }
   if (bad) atomicOr(status, EBOS_STATUS_PIXEL_OOB);
+  if (frac) atomicOr(&h->not_packable, 1);
+}
+
+__global__ void k_win_layout(WindowHeader* h, int allow_packed, int32_t* __restrict__ status) {
+  h->packed = (allow_packed && !h->not_packable) ? 1 : 0;
+  if (h->packed) atomicOr(status, EBOS_STATUS_PACKED);
 }
 
 template <typename T>
@@ -107,10 +117,17 @@ __global__ void __launch_bounds__(256) k_win_gather(const T* __restrict__ ev, co
     const T x = __ldg(ev + 4 * i), y = __ldg(ev + 4 * i + 1), t = __ldg(ev + 4 * i + 2);
     int64_t k = (int64_t)x * W + (int64_t)y;
     bool ok = k >= 0 && k < hw && Rn<T>::finite(x) && Rn<T>::finite(y);
-    // invalid events are parked at a coordinate whose k is negative: the kernels skip them.
-    sx[j] = ok ? x : (T)-2;
-    sy[j] = ok ? y : (T)-2;
-    sd[j] = event_dt<T>(t, tr, normalize_t);
+    const T dt = event_dt<T>(t, tr, normalize_t);
+    if (h->packed) {
+      // packed layout (all events valid, integer coordinates < 65536): (row << 16 | col) in the x slot
+      reinterpret_cast<unsigned int*>(sx)[j] = ((unsigned int)(int)x << 16) | (unsigned int)(int)y;
+    } else {
+      // an invalid event is parked as x = NaN, y = 0: it gathers flow[0] harmlessly, its warped
+      // coordinate is NaN and the exact path drops it (a NaN ORIGIN coordinate has no pixel).
+      sx[j] = ok ? x : (T)NAN;
+      sy[j] = ok ? y : (T)0;
+    }
+    sd[j] = dt;
     if (sw) sw[j] = __ldg(weight + i);
   }
 }
@@ -135,10 +152,55 @@ __device__ __forceinline__ void load_block(const T* __restrict__ p, int64_t base
   }
 }
 
+// The EPT consecutive events of one thread: origin coordinates, dt, weight, and the flow at the origin
+// pixel.  Every load is issued before any of them is used: the first profile (r01) showed each thread
+// doing EPT serial gather -> compute -> RED round trips (41 % of stall samples on the long scoreboard).
+// Two storage layouts: generic (x, y as T) and packed ((row << 16 | col) as uint32; fp32 windows whose
+// coordinates are all integers), which saves a third of the stream and all float->int conversions.
+// Events that must be skipped (tail of the last thread, invalid events parked by prepare) carry x = NaN:
+// they gather flow[0], produce a NaN warped coordinate and are dropped by the exact path.
+template <typename T, int EPT, bool HAS_W, bool PACKED>
+struct EventBlock {
+  T x[EPT], y[EPT], d[EPT], wt[EPT], f0[EPT], f1[EPT];
+  int k[EPT];
+  __device__ __forceinline__ void load(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,
+                                       const T* __restrict__ sw, int64_t base, int64_t n, const T* __restrict__ flow,
+                                       int W, int hw) {
+    load_block<T, EPT>(sd, base, n, (T)0, d);
+    if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
+    if constexpr (PACKED) {
+      float rcf[EPT];
+      load_block<float, EPT>(reinterpret_cast<const float*>(sx), base, n, __uint_as_float(0xffffffffu), rcf);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const unsigned rc = __float_as_uint(rcf[j]);
+        const bool skip = rc == 0xffffffffu;  // only the tail of the very last thread
+        const int r = rc >> 16, c = rc & 0xffff;
+        k[j] = skip ? 0 : r * W + c;
+        // exact int -> float for values below 2^22 on the FP32 pipe
+        x[j] = skip ? (T)NAN : (T)(__int_as_float(0x4B400000 + r) - 12582912.0f);
+        y[j] = (T)(__int_as_float(0x4B400000 + c) - 12582912.0f);
+      }
+    } else {
+      load_block<T, EPT>(sx, base, n, (T)NAN, x);
+      load_block<T, EPT>(sy, base, n, (T)0, y);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int kk = (int)x[j] * W + (int)y[j];   // NaN converts to 0: parked events gather flow[0]
+        k[j] = (unsigned)kk < (unsigned)hw ? kk : 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      f0[j] = __ldg(flow + k[j]);
+      f1[j] = __ldg(flow + hw + k[j]);
+    }
+  }
+};
+
 // ---- forward: fused warp + bilinear vote -----------------------------------------------------
 // The per-event arithmetic is that of make_taps<T> (ebos_common.cuh, i.e. src/event_image_converter.py:
-// 586-614), arranged for instruction issue: the kernels were issue-bound (ncu r01: 61 % issue active,
-// DRAM 31 %), so
+// 586-614), arranged for latency and instruction issue:
 //  * floor() runs on the FP32 pipe: for |v| < 2^22, (v + 1.5*2^23) - 1.5*2^23 is the round-to-nearest
 //    integer and one compare turns it into floor (FRND/F2I run at quarter rate);
 //  * the current cell is tracked as the two floor VALUES (floats); the integer cell is only formed when
@@ -163,9 +225,11 @@ template <> struct FastFloor<double> {
 };
 
 // Exact (reference-order) handling of one event whose warped coordinate is outside the fast range.
+// x0 is the ORIGIN row coordinate: NaN marks an event that must be skipped.
 template <typename T>
-__device__ __noinline__ void splat_event_exact(T* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w, T xw, T yw,
-                                               T wt) {
+__device__ __noinline__ void splat_event_exact(T* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w, T x0, T xw,
+                                               T yw, T wt) {
+  if (x0 != x0) return;
   const Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
   const bool fin = Rn<T>::finite(xw) && Rn<T>::finite(yw);
   const int rr[4] = {t.r, t.r + 1, t.r, t.r + 1}, cc[4] = {t.c, t.c, t.c + 1, t.c + 1};
@@ -180,10 +244,9 @@ __device__ __noinline__ void splat_event_exact(T* __restrict__ iwe, int Hp, int 
   }
 }
 
-// Flush one run: add the four tap sums of cell (r,c).  The kernel is bound by RED lane-ops (LSU), not by
-// bytes: when the row stride allows 16-byte alignment (VEC) the two column-adjacent taps of a row go out
-// as ONE aligned red.v4 (zeros in the unused lanes), i.e. 2 lane-ops per cell instead of 4, unless the
-// pair straddles a 16-byte boundary (c % 4 == 3).
+// Flush one run: add the four tap sums of cell (r,c).  When the row stride allows 16-byte alignment (VEC)
+// the two column-adjacent taps of a row go out as ONE aligned red.v4 (zeros in the unused lanes), i.e.
+// 2 LSU lane-ops per cell instead of 4, unless the pair straddles a 16-byte boundary (c % 4 == 3).
 template <typename T, bool VEC>
 __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, int Hm1, int Wm1, int r, int c, T a0,
                                            T a1, T a2, T a3) {
@@ -217,32 +280,25 @@ __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, 
   }
 }
 
-template <typename T, bool HAS_W, int EPT, bool VEC>
-__global__ void __launch_bounds__(256, (EPT <= 8 && sizeof(T) == 4) ? 6 : 1) k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy,
-                                                   const T* __restrict__ sd, const T* __restrict__ sw, int64_t n,
-                                                   const T* __restrict__ flow, int H, int W, int pad_h, int pad_w,
-                                                   T* __restrict__ iwe) {
+template <typename T, bool HAS_W, int EPT, bool VEC, bool PACKED>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 8) ? 4 : 1)
+k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd, const T* __restrict__ sw,
+            int64_t n, const T* __restrict__ flow, int H, int W, int pad_h, int pad_w, T* __restrict__ iwe) {
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, Hm1 = Hp - 1, Wm1 = Wp - 1;
-  const int hw = H * W;
-  T x[EPT], y[EPT], d[EPT], wt[EPT];
-  load_block<T, EPT>(sx, base, n, (T)-2, x);
-  load_block<T, EPT>(sy, base, n, (T)-2, y);
-  load_block<T, EPT>(sd, base, n, (T)0, d);
-  if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
+  EventBlock<T, EPT, HAS_W, PACKED> e;
+  e.load(sx, sy, sd, sw, base, n, flow, W, H * W);
   // current run: floor values of the cell (NaN = none) and the four tap sums
   T cfr = (T)NAN, cfc = (T)0;
   T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
-    const int k = (int)x[j] * W + (int)y[j];
-    if ((unsigned)k >= (unsigned)hw) continue;  // parked (invalid) event or tail
-    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
-    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
+    const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
+    const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
     const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
     if (!FastFloor<T>::in_range(xb, yb)) {
-      splat_event_exact<T>(iwe, Hp, Wp, pad_h, pad_w, xw, yw, HAS_W ? wt[j] : (T)1);
+      splat_event_exact<T>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], xw, yw, HAS_W ? e.wt[j] : (T)1);
       continue;
     }
     const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
@@ -250,8 +306,8 @@ __global__ void __launch_bounds__(256, (EPT <= 8 && sizeof(T) == 4) ? 6 : 1) k_w
     const T na = Rn<T>::sub((T)1, a), nb = Rn<T>::sub((T)1, b);
     T w0 = Rn<T>::mul(na, nb), w1 = Rn<T>::mul(a, nb), w2 = Rn<T>::mul(na, b), w3 = Rn<T>::mul(a, b);
     if (HAS_W) {
-      w0 = Rn<T>::mul(w0, wt[j]); w1 = Rn<T>::mul(w1, wt[j]);
-      w2 = Rn<T>::mul(w2, wt[j]); w3 = Rn<T>::mul(w3, wt[j]);
+      w0 = Rn<T>::mul(w0, e.wt[j]); w1 = Rn<T>::mul(w1, e.wt[j]);
+      w2 = Rn<T>::mul(w2, e.wt[j]); w3 = Rn<T>::mul(w3, e.wt[j]);
     }
     const bool same = (fr == cfr) & (fc == cfc);
     if (!same) {
@@ -291,7 +347,7 @@ template <typename T, int GSRC>
 __device__ __noinline__ void bwd_event_exact(const T* __restrict__ g, int Hp, int Wp, int pad_h, int pad_w, T xw, T yw,
                                              VarCoef<T> vc, T& dx, T& dy) {
   dx = 0; dy = 0;
-  if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) return;  // all taps masked: zero gradient
+  if (!(Rn<T>::finite(xw) && Rn<T>::finite(yw))) return;  // all taps masked (or a skipped event): zero gradient
   const Taps<T> t = make_taps<T>(xw, yw, pad_h, pad_w);
   const bool r1ok = t.r != INT_MAX, c1ok = t.c != INT_MAX;
   const T g00 = fetch_g<T, GSRC>(g, Hp, Wp, t.r, t.c, vc);
@@ -302,9 +358,8 @@ __device__ __noinline__ void bwd_event_exact(const T* __restrict__ g, int Hp, in
   dy = ((T)1 - t.a) * (g01 - g00) + t.a * (g11 - g10);
 }
 
-// The backward was bound by L1 wavefronts of its four scalar gathers per event (ncu r01: l1tex 71 %).
 // With a 16-byte aligned plane (VEC) the two column-adjacent taps of a row come from ONE aligned float4
-// load (unless c % 4 == 3), i.e. 2 lane-loads per event instead of 4.
+// load (unless c % 4 == 3): 2 lane-loads per event instead of 4.
 template <bool VEC>
 __device__ __forceinline__ void load_pair(const float* __restrict__ p, int j, float& lo, float& hi) {
   if (VEC && j != 3) {
@@ -322,8 +377,8 @@ __device__ __forceinline__ void load_pair(const double* __restrict__ p, int, dou
   hi = __ldg(p + 1);
 }
 
-template <typename T, int GSRC, bool HAS_W, int EPT, bool VEC>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 4) ? 6 : 1)
+template <typename T, int GSRC, bool HAS_W, int EPT, bool VEC, bool PACKED>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 4) ? 4 : 1)
 k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd, const T* __restrict__ sw,
           int64_t n, const T* __restrict__ flow, int H, int W, int pad_h, int pad_w, const T* __restrict__ g,
           const double* __restrict__ acc, int omit, double scale, T* __restrict__ dflow) {
@@ -340,50 +395,58 @@ k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restric
   // fast range of cells whose four taps are all inside (and, for the cropped variance, all counted)
   const int lo = (GSRC == 1 && omit) ? 1 : 0;
   const unsigned r_span = (unsigned)max(Hp - 1 - 2 * lo, 0), c_span = (unsigned)max(Wp - 1 - 2 * lo, 0);
-  T x[EPT], y[EPT], d[EPT], wt[EPT];
-  load_block<T, EPT>(sx, base, n, (T)-2, x);
-  load_block<T, EPT>(sy, base, n, (T)-2, y);
-  load_block<T, EPT>(sd, base, n, (T)0, d);
-  if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
+  EventBlock<T, EPT, HAS_W, PACKED> e;
+  e.load(sx, sy, sd, sw, base, n, flow, W, hw);
+  // phase 1: cells and fractions of all events, then all gathers of dL/dIWE in flight together
+  T a[EPT], b[EPT], g00[EPT], g01[EPT], g10[EPT], g11[EPT];
+  bool fast[EPT];
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
+    const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
+    const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
+    fast[j] = FastFloor<T>::in_range(xb, yb);
+    int r = 0, c = 0;
+    if (fast[j]) {
+      const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
+      a[j] = Rn<T>::sub(xw, fr);
+      b[j] = Rn<T>::sub(yw, fc);
+      r = FastFloor<T>::to_int(fr) + pad_h;
+      c = FastFloor<T>::to_int(fc) + pad_w;
+      fast[j] = (unsigned)(r - lo) < r_span && (unsigned)(c - lo) < c_span;
+    }
+    if (fast[j]) {
+      const T* p = g + (r * Wp + c);
+      load_pair<VEC>(p, c & 3, g00[j], g01[j]);
+      load_pair<VEC>(p + Wp, c & 3, g10[j], g11[j]);
+    } else {
+      // rare: border cell, out-of-range or skipped event -- exact masked gathers, result kept in g00/g01
+      T dx, dy;
+      bwd_event_exact<T, GSRC>(g, Hp, Wp, pad_h, pad_w, e.x[j] == e.x[j] ? xw : (T)NAN, yw, vc, dx, dy);
+      g00[j] = dx; g01[j] = dy; g10[j] = 0; g11[j] = 0; a[j] = 0; b[j] = 0;
+    }
+  }
+  // phase 2: gradients, combined over runs of the same origin pixel
   int ck = -1;
   T s0 = 0, s1 = 0;
 #pragma unroll
   for (int j = 0; j < EPT; ++j) {
-    const int k = (int)x[j] * W + (int)y[j];
-    if ((unsigned)k >= (unsigned)hw) continue;  // parked (invalid) event or tail
-    const T xw = Rn<T>::sub(x[j], Rn<T>::mul(d[j], __ldg(flow + k)));
-    const T yw = Rn<T>::sub(y[j], Rn<T>::mul(d[j], __ldg(flow + hw + k)));
-    const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
     T dx, dy;
-    bool fast = FastFloor<T>::in_range(xb, yb);
-    int r = 0, c = 0;
-    T a = 0, b = 0;
-    if (fast) {
-      const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
-      a = Rn<T>::sub(xw, fr);
-      b = Rn<T>::sub(yw, fc);
-      r = FastFloor<T>::to_int(fr) + pad_h;
-      c = FastFloor<T>::to_int(fc) + pad_w;
-      fast = (unsigned)(r - lo) < r_span && (unsigned)(c - lo) < c_span;
-    }
-    if (fast) {
-      const T* p = g + (r * Wp + c);
-      T g00, g01, g10, g11;
-      load_pair<VEC>(p, c & 3, g00, g01);
-      load_pair<VEC>(p + Wp, c & 3, g10, g11);
-      dx = ((T)1 - b) * (g10 - g00) + b * (g11 - g01);
-      dy = ((T)1 - a) * (g01 - g00) + a * (g11 - g10);
+    if (fast[j]) {
+      dx = ((T)1 - b[j]) * (g10[j] - g00[j]) + b[j] * (g11[j] - g01[j]);
+      dy = ((T)1 - a[j]) * (g01[j] - g00[j]) + a[j] * (g11[j] - g10[j]);
       if (GSRC == 1) { dx *= vc.cv; dy *= vc.cv; }  // differences: the mean cancels
     } else {
-      bwd_event_exact<T, GSRC>(g, Hp, Wp, pad_h, pad_w, xw, yw, vc, dx, dy);
+      dx = g00[j]; dy = g01[j];
     }
-    if (HAS_W) { dx *= wt[j]; dy *= wt[j]; }
-    if (k != ck) {
+    if (HAS_W) { dx *= e.wt[j]; dy *= e.wt[j]; }
+    if (e.x[j] != e.x[j]) continue;  // skipped event
+    if (e.k[j] != ck) {
       if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
-      ck = k; s0 = 0; s1 = 0;
+      ck = e.k[j]; s0 = 0; s1 = 0;
     }
-    s0 -= d[j] * dx;
-    s1 -= d[j] * dy;
+    s0 -= e.d[j] * dx;
+    s1 -= e.d[j] * dy;
   }
   if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
 }
@@ -410,8 +473,8 @@ static PrepWs prep_ws(int64_t n) {
 
 template <typename T>
 int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction, double direction_frac, int normalize_t,
-                        const T* weight, const T* tminmax, void* window, void* workspace, size_t workspace_bytes,
-                        int32_t* status, cudaStream_t st) {
+                        const T* weight, const T* tminmax, int allow_packed, void* window, void* workspace,
+                        size_t workspace_bytes, int32_t* status, cudaStream_t st) {
   WindowHeader* hdr = reinterpret_cast<WindowHeader*>(window);
   k_win_hdr_init<<<1, 1, 0, st>>>(hdr);
   if (n == 0) {
@@ -432,7 +495,8 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   int bx = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
   if (!tminmax) k_win_minmax<T><<<bx, 256, 0, st>>>(events, n, hdr);
   k_win_hdr_final<T><<<1, 1, 0, st>>>(hdr, direction, direction_frac, tminmax);
-  k_win_keys<T><<<bx, 256, 0, st>>>(events, n, H, W, k_in, i_in, status);
+  k_win_keys<T><<<bx, 256, 0, st>>>(events, n, H, W, k_in, i_in, status, hdr);
+  k_win_layout<<<1, 1, 0, st>>>(hdr, allow_packed && sizeof(T) == 4 && H <= 65536 && W <= 65536, status);
   size_t cub_bytes = ws.cub_bytes;
   cudaError_t ce = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k_in, k_out, i_in, perm, (int)n, 0,
                                                    key_bits_for((int64_t)H * W), st);
@@ -446,12 +510,14 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
 }
 
 template <typename T>
-int window_splat_t(const void* window, int64_t n, int has_weight, const T* flow, int H, int W, int pad_h, int pad_w,
-                   T* iwe, cudaStream_t st) {
+int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int H, int W, int pad_h, int pad_w, T* iwe,
+                   cudaStream_t st) {
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   cudaError_t e = cudaMemsetAsync(iwe, 0, (size_t)Hp * Wp * sizeof(T), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_window_splat memset");
   if (n == 0) return EBOS_OK;
+  const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
+  if (packed && sizeof(T) != 4) { set_error("ebos_window_splat: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
   WindowLayout L = window_layout(n, sizeof(T));
   const char* b = reinterpret_cast<const char*>(window);
   const T* sx = reinterpret_cast<const T*>(b + L.off_x);
@@ -459,41 +525,45 @@ int window_splat_t(const void* window, int64_t n, int has_weight, const T* flow,
   const T* sd = reinterpret_cast<const T*>(b + L.off_d);
   const T* sw = reinterpret_cast<const T*>(b + L.off_w);
   static const int ept_env = env_int("EBOS_SPLAT_EPT");
-  const int ept = (ept_env == 4 || ept_env == 8 || ept_env == 16) ? ept_env : Ept<T>::splat;
+  const int ept = (ept_env == 4 || ept_env == 8) ? ept_env : Ept<T>::splat;
   int64_t threads = (n + ept - 1) / ept;
   unsigned grid = (unsigned)((threads + 255) / 256);
   // vector REDs need fp32, a 16-byte aligned plane and a row stride that keeps the alignment
   static const int novec_env = env_int("EBOS_NO_VEC");
   const bool vec = sizeof(T) == 4 && !novec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(iwe) & 15) == 0);
-#define EBOS_SPLAT_LAUNCH(E, V)                                                                                         \
-  do {                                                                                                                  \
-    if (has_weight) k_win_splat<T, true, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);  \
-    else k_win_splat<T, false, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe);            \
-  } while (0)
+#define EBOS_SPLAT_K(WGT, E, V, P) k_win_splat<T, WGT, E, V, P><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe)
+#define EBOS_SPLAT_E(WGT, V, P) do { if (ept == 4) EBOS_SPLAT_K(WGT, 4, V, P); else EBOS_SPLAT_K(WGT, 8, V, P); } while (0)
   if constexpr (sizeof(T) == 4) {
-    if (vec) { if (ept == 4) EBOS_SPLAT_LAUNCH(4, true); else if (ept == 16) EBOS_SPLAT_LAUNCH(16, true); else EBOS_SPLAT_LAUNCH(8, true); }
-    else { if (ept == 4) EBOS_SPLAT_LAUNCH(4, false); else if (ept == 16) EBOS_SPLAT_LAUNCH(16, false); else EBOS_SPLAT_LAUNCH(8, false); }
+    if (has_weight) {   // weighted windows: generic code path only
+      if (packed) { if (vec) EBOS_SPLAT_E(true, true, true); else EBOS_SPLAT_E(true, false, true); }
+      else { if (vec) EBOS_SPLAT_E(true, true, false); else EBOS_SPLAT_E(true, false, false); }
+    } else {
+      if (packed) { if (vec) EBOS_SPLAT_E(false, true, true); else EBOS_SPLAT_E(false, false, true); }
+      else { if (vec) EBOS_SPLAT_E(false, true, false); else EBOS_SPLAT_E(false, false, false); }
+    }
   } else {
-    if (ept == 8) EBOS_SPLAT_LAUNCH(8, false); else EBOS_SPLAT_LAUNCH(4, false);
+    if (has_weight) EBOS_SPLAT_K(true, 4, false, false); else EBOS_SPLAT_K(false, 4, false, false);
   }
-#undef EBOS_SPLAT_LAUNCH
+#undef EBOS_SPLAT_E
+#undef EBOS_SPLAT_K
   EBOS_LAUNCH_CHECK("ebos_window_splat");
   return EBOS_OK;
 }
 
 template <typename T>
-int window_backward_t(const void* window, int64_t n, int has_weight, const T* flow, int H, int W, int pad_h, int pad_w,
+int window_backward_t(const void* window, int64_t n, int flags, const T* flow, int H, int W, int pad_h, int pad_w,
                       const T* grad_iwe, int kind, const T* iwe, const double* acc, int omit_boundary, double scale,
                       T* dflow, cudaStream_t st) {
   if (n == 0) return EBOS_OK;
+  const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
+  if (packed && sizeof(T) != 4) { set_error("ebos_window_backward: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
   WindowLayout L = window_layout(n, sizeof(T));
   const char* b = reinterpret_cast<const char*>(window);
   const T* sx = reinterpret_cast<const T*>(b + L.off_x);
   const T* sy = reinterpret_cast<const T*>(b + L.off_y);
   const T* sd = reinterpret_cast<const T*>(b + L.off_d);
   const T* sw = reinterpret_cast<const T*>(b + L.off_w);
-  static const int ept_env = env_int("EBOS_BWD_EPT");
-  const int ept = (ept_env == 4 || ept_env == 8) ? ept_env : Ept<T>::bwd;
+  const int ept = Ept<T>::bwd;
   int64_t threads = (n + ept - 1) / ept;
   unsigned grid = (unsigned)((threads + 255) / 256);
   const bool affine = grad_iwe == nullptr;
@@ -502,41 +572,43 @@ int window_backward_t(const void* window, int64_t n, int has_weight, const T* fl
     return EBOS_ERR_BAD_ARG;
   }
   const T* gsrc = affine ? iwe : grad_iwe;
-  static const int novec_env = env_int("EBOS_NO_VEC");
+  static const int novec_env = env_int("EBOS_NO_VEC_LOAD");
   const int Wp = W + 2 * pad_w;
   const bool vec = sizeof(T) == 4 && !novec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
-#define EBOS_BWD_LAUNCH(G, E, V)                                                                                                    \
-  do {                                                                                                                              \
-    if (has_weight) k_win_bwd<T, G, true, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);  \
-    else k_win_bwd<T, G, false, E, V><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow);            \
+#define EBOS_BWD_K(G, WGT, V, P) k_win_bwd<T, G, WGT, Ept<T>::bwd, V, P><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow)
+#define EBOS_BWD_G(G)                                                                                              \
+  do {                                                                                                             \
+    if constexpr (sizeof(T) == 4) {                                                                                \
+      if (has_weight) { if (packed) { if (vec) EBOS_BWD_K(G, true, true, true); else EBOS_BWD_K(G, true, false, true); }          \
+                        else { if (vec) EBOS_BWD_K(G, true, true, false); else EBOS_BWD_K(G, true, false, false); } }             \
+      else { if (packed) { if (vec) EBOS_BWD_K(G, false, true, true); else EBOS_BWD_K(G, false, false, true); }                   \
+             else { if (vec) EBOS_BWD_K(G, false, true, false); else EBOS_BWD_K(G, false, false, false); } }                      \
+    } else {                                                                                                       \
+      if (has_weight) EBOS_BWD_K(G, true, false, false); else EBOS_BWD_K(G, false, false, false);                  \
+    }                                                                                                              \
   } while (0)
-#define EBOS_BWD_PICK(G)                                                                       \
-  do {                                                                                         \
-    if (vec) { if (ept == 8) EBOS_BWD_LAUNCH(G, 8, true); else EBOS_BWD_LAUNCH(G, 4, true); }   \
-    else { if (ept == 8) EBOS_BWD_LAUNCH(G, 8, false); else EBOS_BWD_LAUNCH(G, 4, false); }     \
-  } while (0)
-  if (affine) EBOS_BWD_PICK(1); else EBOS_BWD_PICK(0);
-#undef EBOS_BWD_PICK
-#undef EBOS_BWD_LAUNCH
+  if (affine) EBOS_BWD_G(1); else EBOS_BWD_G(0);
+#undef EBOS_BWD_G
+#undef EBOS_BWD_K
   EBOS_LAUNCH_CHECK("ebos_window_backward");
   return EBOS_OK;
 }
 
 // type-erased entry points used by ebos_costs.cu (fused iteration)
-int window_splat_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int window_splat_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                         int pad_w, int dtype, void* iwe, cudaStream_t st) {
   if (dtype == EBOS_F64)
-    return window_splat_t<double>(window, n, has_weight, (const double*)flow, H, W, pad_h, pad_w, (double*)iwe, st);
-  return window_splat_t<float>(window, n, has_weight, (const float*)flow, H, W, pad_h, pad_w, (float*)iwe, st);
+    return window_splat_t<double>(window, n, flags, (const double*)flow, H, W, pad_h, pad_w, (double*)iwe, st);
+  return window_splat_t<float>(window, n, flags, (const float*)flow, H, W, pad_h, pad_w, (float*)iwe, st);
 }
-int window_backward_launch(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int window_backward_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                            int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
                            int omit_boundary, double scale, void* dflow, cudaStream_t st) {
   if (dtype == EBOS_F64)
-    return window_backward_t<double>(window, n, has_weight, (const double*)flow, H, W, pad_h, pad_w,
+    return window_backward_t<double>(window, n, flags, (const double*)flow, H, W, pad_h, pad_w,
                                      (const double*)grad_iwe, kind, (const double*)iwe, acc, omit_boundary, scale,
                                      (double*)dflow, st);
-  return window_backward_t<float>(window, n, has_weight, (const float*)flow, H, W, pad_h, pad_w, (const float*)grad_iwe,
+  return window_backward_t<float>(window, n, flags, (const float*)flow, H, W, pad_h, pad_w, (const float*)grad_iwe,
                                   kind, (const float*)iwe, acc, omit_boundary, scale, (float*)dflow, st);
 }
 
@@ -562,8 +634,8 @@ size_t ebos_window_workspace_bytes(int64_t n, int H, int W) {
 }
 
 int ebos_window_prepare(const void* events, int64_t n, int H, int W, int direction, double direction_frac,
-                        int normalize_t, const void* weight, const void* tminmax, int dtype, void* window,
-                        void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+                        int normalize_t, const void* weight, const void* tminmax, int allow_packed, int dtype,
+                        void* window, void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
   EBOS_REQUIRE(n >= 0 && n < (int64_t)INT_MAX && H > 0 && W > 0 && window && status && (n == 0 || events),
                "ebos_window_prepare: bad argument");
   EBOS_REQUIRE((int64_t)H * W < ((int64_t)1 << 31) - 1, "ebos_window_prepare: grid too large");
@@ -572,11 +644,11 @@ int ebos_window_prepare(const void* events, int64_t n, int H, int W, int directi
   EBOS_CHECK_DTYPE(dtype, "ebos_window_prepare");
   if (dtype == EBOS_F64)
     return window_prepare_impl<double>((const double*)events, n, H, W, direction, direction_frac, normalize_t,
-                                       (const double*)weight, (const double*)tminmax, window, workspace,
+                                       (const double*)weight, (const double*)tminmax, 0, window, workspace,
                                        workspace_bytes, status, as_stream(stream));
   return window_prepare_impl<float>((const float*)events, n, H, W, direction, direction_frac, normalize_t,
-                                    (const float*)weight, (const float*)tminmax, window, workspace, workspace_bytes,
-                                    status, as_stream(stream));
+                                    (const float*)weight, (const float*)tminmax, allow_packed, window, workspace,
+                                    workspace_bytes, status, as_stream(stream));
 }
 
 int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out, double* tinfo_out, void* stream) {
@@ -596,19 +668,19 @@ int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out
   return EBOS_OK;
 }
 
-int ebos_window_splat(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int ebos_window_splat(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                       int pad_w, int dtype, void* iwe, void* stream) {
   EBOS_REQUIRE(window && flow && iwe && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "ebos_window_splat: bad argument");
   EBOS_CHECK_DTYPE(dtype, "ebos_window_splat");
-  return window_splat_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, iwe, as_stream(stream));
+  return window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, as_stream(stream));
 }
 
-int ebos_window_backward(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+int ebos_window_backward(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                          int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
                          int omit_boundary, double scale, void* dflow, void* stream) {
   EBOS_REQUIRE(window && flow && dflow && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "ebos_window_backward: bad argument");
   EBOS_CHECK_DTYPE(dtype, "ebos_window_backward");
-  return window_backward_launch(window, n, has_weight, flow, H, W, pad_h, pad_w, dtype, grad_iwe, kind, iwe, acc,
+  return window_backward_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, grad_iwe, kind, iwe, acc,
                                 omit_boundary, scale, dflow, as_stream(stream));
 }
 

@@ -238,7 +238,7 @@ class PreparedWindow:
 
     def __init__(self, events: torch.Tensor, image_size: Tuple[int, int], direction: Direction = "first",
                  normalize_t: bool = True, weight: Optional[torch.Tensor] = None, validate: bool = True,
-                 t_min_max: Optional[torch.Tensor] = None, dtype=torch.float32):
+                 t_min_max: Optional[torch.Tensor] = None, dtype=torch.float32, allow_packed: bool = True):
         _check_cuda(events, weight, t_min_max)
         if events.dim() != 2 or events.shape[1] != 4:
             raise ValueError(f"events must be [n,4], got {tuple(events.shape)}")
@@ -264,10 +264,14 @@ class PreparedWindow:
         # larger event set (event-sharded multi-GPU path).
         tmm = None if t_min_max is None else t_min_max.to(self.dtype).contiguous()
         check(lib.ebos_window_prepare(ptr(ev), self.n, self.H, self.W, kind, frac, int(self.normalize_t), ptr(w),
-                                      ptr(tmm), self.code, ptr(self.buffer), ptr(ws), ws_bytes, ptr(status),
-                                      current_stream()), "ebos_window_prepare")
-        self._status = status
-        if validate and int(status.item()) & _capi.STATUS_PIXEL_OOB:
+                                      ptr(tmm), int(bool(allow_packed)), self.code, ptr(self.buffer), ptr(ws), ws_bytes,
+                                      ptr(status), current_stream()), "ebos_window_prepare")
+        # One 4-byte read-back per window: which layout prepare chose (packed (row,col,dt) for integer
+        # coordinates) and whether an event's pixel lies outside the grid.
+        st = int(status.item())
+        self.packed = bool(st & _capi.STATUS_PACKED)
+        self.flags = (_capi.WIN_HAS_WEIGHT if self.has_weight else 0) | (_capi.WIN_PACKED if self.packed else 0)
+        if validate and st & _capi.STATUS_PIXEL_OOB:
             raise RuntimeError("index out of bounds: an event's integer pixel lies outside the flow grid "
                                "(the reference's torch.gather raises for the same input)")
 
@@ -300,7 +304,7 @@ def window_splat(window: PreparedWindow, flow: torch.Tensor, outer_padding: Tupl
     ph, pw = int(outer_padding[0]), int(outer_padding[1])
     if out is None:
         out = torch.empty((window.H + 2 * ph, window.W + 2 * pw), dtype=window.dtype, device=flow.device)
-    check(_capi.load().ebos_window_splat(ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), window.H,
+    check(_capi.load().ebos_window_splat(ptr(window.buffer), window.n, window.flags, ptr(flow), window.H,
                                          window.W, ph, pw, window.code, ptr(out), current_stream()), "ebos_window_splat")
     return out
 
@@ -340,7 +344,7 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
         if tuple(tvw.shape) != (window.H, window.W):
             raise ValueError(f"tv_weights must be [{window.H},{window.W}], got {tuple(tvw.shape)}")
     check(_capi.load().ebos_cmax_value_and_grad(
-        ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), window.H, window.W, ws.ph, ws.pw,
+        ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw,
         COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code,
         ptr(ws.iwe), ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), current_stream()),
         "ebos_cmax_value_and_grad")

@@ -176,7 +176,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
 
     def backward(flow, g):
         dflow.zero_()
-        check(lib.ebos_window_backward(ptr(window.buffer), window.n, int(window.has_weight), ptr(flow), H, W, ph, pw,
+        check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
                                        window.code, ptr(g), kind, ptr(iwe), ptr(acc), int(omit_boundary), data_weight,
                                        ptr(dflow), current_stream()), "ebos_window_backward")
         return dflow

@@ -60,6 +60,11 @@ extern "C" {
 
 /* status word bits written by the kernels into the caller's `status` int32 (device) */
 #define EBOS_STATUS_PIXEL_OOB 1 /* an event's integer pixel is outside the flow grid (reference: gather raises) */
+#define EBOS_STATUS_PACKED 2    /* ebos_window_prepare stored the window in the packed (row,col,dt) layout */
+
+/* `flags` of the per-iteration window calls */
+#define EBOS_WIN_HAS_WEIGHT 1 /* the window was prepared with per-event weights */
+#define EBOS_WIN_PACKED 2     /* the window is in the packed layout (status had EBOS_STATUS_PACKED) */
 
 EBOS_API int ebos_version(void);
 EBOS_API const char* ebos_last_error(void);
@@ -134,18 +139,22 @@ EBOS_API size_t ebos_window_workspace_bytes(int64_t n, int H, int W);
  * sensor's time order is kept inside a pixel).  weight: NULL or [n].  status as above.
  * tminmax: NULL, or [2] (device, dtype) = (min t, max t) to use instead of this call's own
  * reduction -- for a window whose events are sharded over several GPUs (global min/max).
+ * allow_packed: when non-zero (fp32 only) and every event is valid with integer coordinates below
+ * 65536 -- raw sensor events -- the window is stored as (row<<16|col, dt) = 8 bytes per event instead
+ * of 12, and EBOS_STATUS_PACKED is OR-ed into `status`; the caller must then pass EBOS_WIN_PACKED in
+ * the `flags` of the per-iteration calls (read `status` once after prepare).
  * window must be 256-byte aligned. */
 EBOS_API int ebos_window_prepare(const void* events, int64_t n, int H, int W, int direction, double direction_frac,
-                        int normalize_t, const void* weight, const void* tminmax, int dtype, void* window,
-                        void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+                        int normalize_t, const void* weight, const void* tminmax, int allow_packed, int dtype,
+                        void* window, void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 
 /* Copy the window's event permutation (int32[n]: sorted position -> original event index) and its
  * time statistics (double[4]: t_ref, period, t_min, t_max) out of the opaque buffer (either may be NULL). */
 EBOS_API int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out, double* tinfo_out, void* stream);
 
 /* Fused warp + bilinear vote of a prepared window into iwe [Hp,Wp] (fully overwritten).
- * `n`, `has_weight` and `dtype` must be the values the window was prepared with. */
-EBOS_API int ebos_window_splat(const void* window, int64_t n, int has_weight, const void* flow, int H, int W, int pad_h,
+ * `n`, `flags` (EBOS_WIN_*) and `dtype` must describe the window as it was prepared. */
+EBOS_API int ebos_window_splat(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                       int pad_w, int dtype, void* iwe, void* stream);
 
 /* Data objective on the IWE: value and gradient scaled by `scale`.
@@ -165,7 +174,7 @@ EBOS_API int ebos_flow_tv(const void* flow, const void* weights, int H, int W, d
 /* Analytic backward of the fused splat: re-warps every event, gathers dL/dIWE at
  * its four taps and accumulates -dt*dL/dx' into dflow[:, k] (ACCUMULATES; run ebos_flow_tv first).
  * grad_iwe: [Hp,Wp] or NULL with kind == EBOS_COST_VARIANCE (then iwe+acc+scale are used). */
-EBOS_API int ebos_window_backward(const void* window, int64_t n, int has_weight, const void* flow, int H, int W,
+EBOS_API int ebos_window_backward(const void* window, int64_t n, int flags, const void* flow, int H, int W,
                          int pad_h, int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe,
                          const double* acc, int omit_boundary, double scale, void* dflow, void* stream);
 
@@ -176,7 +185,7 @@ EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int
 /* One complete objective evaluation: splat -> cost -> TV -> backward -> loss, stream-ordered,
  * no host sync (CUDA-graph capturable).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W],
  * loss [1], acc double[8]. */
-EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int has_weight, const void* flow, int H, int W,
+EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W,
                              int pad_h, int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
                              double* acc, void* stream);

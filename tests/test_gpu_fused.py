@@ -45,6 +45,70 @@ def test_prepared_window_metadata(ops):
         assert info64[0] == float(t_ref64) and info64[1] == float(period64)
 
 
+def test_packed_and_generic_layouts_agree(ops):
+    """Integer-coordinate windows use the packed (row,col,dt) layout; results must equal the generic layout's."""
+    H, W, n = 64, 96, 50000
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=9)).cuda()
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=9, max_val=5.0)).cuda()
+    wp = ops.PreparedWindow(ev, (H, W), "first", True)
+    wg = ops.PreparedWindow(ev, (H, W), "first", True, allow_packed=False)
+    assert wp.packed and not wg.packed
+    frac = ev.clone()
+    frac[7, 0] += 0.25
+    assert not ops.PreparedWindow(frac, (H, W), "first", True).packed  # one fractional coordinate -> generic
+    assert torch.equal(wp.permutation(), wg.permutation())
+    for pad in (0, 3):
+        a, b = ops.window_splat(wp, flow, (pad, pad)).clone(), ops.window_splat(wg, flow, (pad, pad)).clone()
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+        ref = spec.bilinear_vote(spec.warp_dense_flow(ev.cpu(), flow.cpu(), (H, W)), (H, W), (pad, pad))
+        assert rel_err(a.cpu().numpy(), ref.numpy()) <= REL
+        for cost in ("image_variance", "gradient_magnitude"):
+            la, ga = ops.cmax_value_and_grad(wp, flow, cost, 1.0, 0.5, None, False, (pad, pad))
+            la, ga = la.clone(), ga.clone()
+            lb, gb = ops.cmax_value_and_grad(wg, flow, cost, 1.0, 0.5, None, False, (pad, pad))
+            assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))
+            assert rel_err(ga.cpu().numpy(), gb.cpu().numpy()) <= 1e-5
+    # tail handling: n not a multiple of the events-per-thread block
+    for m in (1, 3, 8, 9, 1023):
+        w1 = ops.PreparedWindow(ev[:m + 1], (H, W), "first", True)
+        w2 = ops.PreparedWindow(ev[:m + 1], (H, W), "first", True, allow_packed=False)
+        ref = spec.bilinear_vote(spec.warp_dense_flow(ev[:m + 1].cpu(), flow.cpu(), (H, W)), (H, W))
+        assert rel_err(ops.window_splat(w1, flow).cpu().numpy(), ref.numpy()) <= REL
+        assert rel_err(ops.window_splat(w2, flow).cpu().numpy(), ref.numpy()) <= REL
+        _, g1 = ops.cmax_value_and_grad(w1, flow, "image_variance", 1.0, 0.0)
+        g1 = g1.clone()
+        _, g2 = ops.cmax_value_and_grad(w2, flow, "image_variance", 1.0, 0.0)
+        assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
+
+
+def test_invalid_events_are_skipped_when_not_validating(ops):
+    """validate=False: an event outside the grid is parked and contributes nothing (the reference raises)."""
+    H, W, n = 32, 48, 5000
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=2))
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=2)).cuda()
+    bad = ev.clone()
+    bad[100, 0] = H + 5.0
+    bad[200, 1] = -3.0 * W
+    keep = torch.ones(n, dtype=torch.bool)
+    keep[[100, 200]] = False
+    with pytest.raises(RuntimeError):
+        ops.PreparedWindow(bad.cuda(), (H, W), "first", True)
+    win = ops.PreparedWindow(bad.cuda(), (H, W), "first", True, validate=False)
+    assert not win.packed
+    # time normalisation still spans all events, so compare against the oracle on the kept events with the same dt
+    dt, _, _ = spec.event_dt(bad[:, 2], "first", True)
+    good = bad[keep].clone()
+    k = spec.origin_pixel_index(good[:, 0], good[:, 1], W)
+    f = flow.cpu().reshape(2, -1)
+    warped = good.clone()
+    warped[:, 0] = good[:, 0] - dt[keep] * f[0][k]
+    warped[:, 1] = good[:, 1] - dt[keep] * f[1][k]
+    ref = spec.bilinear_vote(warped, (H, W))
+    assert rel_err(ops.window_splat(win, flow).cpu().numpy(), ref.numpy()) <= REL
+    loss, grad = ops.cmax_value_and_grad(win, flow, "gradient_magnitude", 1.0, 0.5)
+    assert torch.isfinite(loss).all() and torch.isfinite(grad).all()
+
+
 def test_window_splat_vs_golden_and_oracle(golden, ops):
     from tests.conftest import parse_direction
 
