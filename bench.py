@@ -249,21 +249,23 @@ def run_fused(args, rank, world, local):
         ms = max_over_ranks(ms, world)
         # per-kernel timing of the two event-streaming kernels (same stream, CUDA events)
         lib = _capi.load()
-        st = torch.cuda.current_stream().cuda_stream
         p = _capi.ptr
 
+        def cur():
+            return torch.cuda.current_stream().cuda_stream  # evaluated at call time (graph capture stream)
+
         def splat_only():
-            lib.ebos_window_splat(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.iwe), st)
+            lib.ebos_window_splat(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.iwe), cur())
 
         def bwd_only():
             lib.ebos_window_backward(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.grad_iwe),
-                                     _capi.COST_GRADMAG, p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), st)
+                                     _capi.COST_GRADMAG, p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), cur())
 
         def cost_only():
-            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws.iwe), H, W, 0, 1.0, 0, p(ws.acc), p(ws.grad_iwe), st)
+            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws.iwe), H, W, 0, 1.0, 0, p(ws.acc), p(ws.grad_iwe), cur())
 
         def tv_only():
-            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws.acc), p(ws.dflow), st)
+            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws.acc), p(ws.dflow), cur())
 
         k_ms = {name: graph_time_ms(fn, args.steps) for name, fn in
                 (("window_splat(+memset)", splat_only), ("window_backward", bwd_only), ("iwe_cost_gradmag", cost_only),

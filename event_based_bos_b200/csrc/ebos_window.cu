@@ -163,18 +163,57 @@ template <typename T, int EPT, bool HAS_W, bool PACKED>
 struct EventBlock {
   T x[EPT], y[EPT], d[EPT], wt[EPT], f0[EPT], f1[EPT];
   int k[EPT];
-  __device__ __forceinline__ void load(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,
-                                       const T* __restrict__ sw, int64_t base, int64_t n, const T* __restrict__ flow,
-                                       int W, int hw) {
+
+  // raw fields straight from global memory (vectorised, coalesced)
+  __device__ __forceinline__ void load_global(const T* __restrict__ sx, const T* __restrict__ sy,
+                                              const T* __restrict__ sd, const T* __restrict__ sw, int64_t base,
+                                              int64_t n) {
     load_block<T, EPT>(sd, base, n, (T)0, d);
     if (HAS_W) load_block<T, EPT>(sw, base, n, (T)0, wt);
     if constexpr (PACKED) {
-      float rcf[EPT];
-      load_block<float, EPT>(reinterpret_cast<const float*>(sx), base, n, __uint_as_float(0xffffffffu), rcf);
+      load_block<float, EPT>(reinterpret_cast<const float*>(sx), base, n, __uint_as_float(0xffffffffu), x);
+    } else {
+      load_block<T, EPT>(sx, base, n, (T)NAN, x);
+      load_block<T, EPT>(sy, base, n, (T)0, y);
+    }
+  }
+
+  // raw fields from a shared-memory stage filled by the TMA bulk copies: arrays of `ch` elements in the
+  // order (x|rc, [y], d, [w]); `valid` = number of real events of this thread's block (tail of the stream)
+  __device__ __forceinline__ void load_stage(const T* __restrict__ stage, int ch, int off, int valid) {
+    const T* px = stage + off;
+    const T* py = stage + ch + off;
+    const T* pd = stage + (PACKED ? 1 : 2) * ch + off;
+    const T* pw = stage + (PACKED ? 2 : 3) * ch + off;
+#pragma unroll
+    for (int j = 0; j < EPT; j += 4) {
+      load4s(px + j, x + j);
+      if (!PACKED) load4s(py + j, y + j);
+      load4s(pd + j, d + j);
+      if (HAS_W) load4s(pw + j, wt + j);
+    }
+    if (valid < EPT) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+        if (j >= valid) { x[j] = PACKED ? (T)__uint_as_float(0xffffffffu) : (T)NAN; y[j] = 0; d[j] = 0; }
+    }
+  }
+  static __device__ __forceinline__ void load4s(const float* p, float* o) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void load4s(const double* p, double* o) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+
+  // origin pixel, float coordinates and the flow gathers (all issued before any is consumed)
+  __device__ __forceinline__ void finish(const T* __restrict__ flow, int W, int hw) {
+    if constexpr (PACKED) {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        const unsigned rc = __float_as_uint(rcf[j]);
-        const bool skip = rc == 0xffffffffu;  // only the tail of the very last thread
+        const unsigned rc = __float_as_uint(x[j]);
+        const bool skip = rc == 0xffffffffu;  // only past the end of the stream
         const int r = rc >> 16, c = rc & 0xffff;
         k[j] = skip ? 0 : r * W + c;
         // exact int -> float for values below 2^22 on the FP32 pipe
@@ -182,8 +221,6 @@ struct EventBlock {
         y[j] = (T)(__int_as_float(0x4B400000 + c) - 12582912.0f);
       }
     } else {
-      load_block<T, EPT>(sx, base, n, (T)NAN, x);
-      load_block<T, EPT>(sy, base, n, (T)0, y);
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         const int kk = (int)x[j] * W + (int)y[j];   // NaN converts to 0: parked events gather flow[0]
@@ -195,6 +232,13 @@ struct EventBlock {
       f0[j] = __ldg(flow + k[j]);
       f1[j] = __ldg(flow + hw + k[j]);
     }
+  }
+
+  __device__ __forceinline__ void load(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,
+                                       const T* __restrict__ sw, int64_t base, int64_t n, const T* __restrict__ flow,
+                                       int W, int hw) {
+    load_global(sx, sy, sd, sw, base, n);
+    finish(flow, W, hw);
   }
 };
 
@@ -280,15 +324,11 @@ __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, 
   }
 }
 
+// EPT consecutive events of one thread: warp, vote, combine runs of equal cells, flush.
 template <typename T, bool HAS_W, int EPT, bool VEC, bool PACKED>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 8) ? 4 : 1)
-k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd, const T* __restrict__ sw,
-            int64_t n, const T* __restrict__ flow, int H, int W, int pad_h, int pad_w, T* __restrict__ iwe) {
-  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
-  if (base >= n) return;
-  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, Hm1 = Hp - 1, Wm1 = Wp - 1;
-  EventBlock<T, EPT, HAS_W, PACKED> e;
-  e.load(sx, sy, sd, sw, base, n, flow, W, H * W);
+__device__ __forceinline__ void splat_block(const EventBlock<T, EPT, HAS_W, PACKED>& e, T* __restrict__ iwe, int Hp,
+                                            int Wp, int pad_h, int pad_w) {
+  const int Hm1 = Hp - 1, Wm1 = Wp - 1;
   // current run: floor values of the cell (NaN = none) and the four tap sums
   T cfr = (T)NAN, cfc = (T)0;
   T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -324,6 +364,104 @@ k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restr
   if (cfr == cfr)
     flush_cell<T, VEC>(iwe, Hp, Wp, Hm1, Wm1, FastFloor<T>::to_int(cfr) + pad_h, FastFloor<T>::to_int(cfc) + pad_w, a0, a1,
                        a2, a3);
+}
+
+// one-shot variant (fp64 windows, small windows): every thread loads its events straight from global memory
+template <typename T, bool HAS_W, int EPT, bool VEC, bool PACKED>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 8) ? 4 : 1)
+k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd, const T* __restrict__ sw,
+            int64_t n, const T* __restrict__ flow, int H, int W, int pad_h, int pad_w, T* __restrict__ iwe) {
+  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
+  if (base >= n) return;
+  EventBlock<T, EPT, HAS_W, PACKED> e;
+  e.load(sx, sy, sd, sw, base, n, flow, W, H * W);
+  splat_block<T, HAS_W, EPT, VEC, PACKED>(e, iwe, H + 2 * pad_h, W + 2 * pad_w, pad_h, pad_w);
+}
+
+// ---- persistent, TMA-staged streaming (fp32) ---------------------------------------------------------
+// The one-shot kernels were latency-bound: a thread's only loads from HBM sit at its very beginning and
+// nothing else in the thread can run until they land (ncu r01b: 37-46 % of stall samples on the long
+// scoreboard at the first use of the event fields, 44 % occupancy).  Here a persistent CTA walks over
+// chunks of 256 x EPT consecutive events; the chunk's SoA slices are brought into shared memory by the
+// copy engine (cp.async.bulk + mbarrier transaction count), double buffered, so the HBM latency of chunk
+// i+1 and i+2 overlaps the arithmetic of chunk i and the threads only ever wait on shared memory.
+constexpr int kPipeEpt = 8;
+constexpr int kPipeChunk = 256 * kPipeEpt;
+constexpr int kPipeStages = 2;
+
+template <bool HAS_W, bool PACKED> struct PipeCfg {
+  static constexpr int narr = (PACKED ? 2 : 3) + (HAS_W ? 1 : 0);
+  static constexpr int stage_floats = narr * kPipeChunk;
+  static constexpr size_t smem_bytes = (size_t)kPipeStages * stage_floats * sizeof(float);
+};
+
+template <bool HAS_W, bool PACKED>
+__device__ __forceinline__ void pipe_issue(float* __restrict__ stage, unsigned long long* bar, const float* __restrict__ sx,
+                                           const float* __restrict__ sy, const float* __restrict__ sd,
+                                           const float* __restrict__ sw, int64_t chunk, int64_t n) {
+  const int64_t base = chunk * kPipeChunk;
+  const int64_t cnt = min((int64_t)kPipeChunk, n - base);
+  const unsigned bytes = (unsigned)((cnt * 4 + 15) & ~(int64_t)15);  // the window arrays are padded to 256 B
+  mbar_expect_tx(bar, bytes * PipeCfg<HAS_W, PACKED>::narr);
+  int a = 0;
+  bulk_g2s(stage + (a++) * kPipeChunk, sx + base, bytes, bar);
+  if (!PACKED) bulk_g2s(stage + (a++) * kPipeChunk, sy + base, bytes, bar);
+  bulk_g2s(stage + (a++) * kPipeChunk, sd + base, bytes, bar);
+  if (HAS_W) bulk_g2s(stage + (a++) * kPipeChunk, sw + base, bytes, bar);
+}
+
+template <bool HAS_W, bool PACKED, typename BODY>
+__device__ __forceinline__ void pipe_loop(const float* __restrict__ sx, const float* __restrict__ sy,
+                                          const float* __restrict__ sd, const float* __restrict__ sw, int64_t n,
+                                          const float* __restrict__ flow, int W, int hw, BODY body) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ __align__(8) unsigned long long full[kPipeStages];
+  float* stages = reinterpret_cast<float*>(pipe_smem);
+  constexpr int SF = PipeCfg<HAS_W, PACKED>::stage_floats;
+  const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kPipeStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kPipeStages; ++s) {
+      const int64_t c = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (c < n_chunks) pipe_issue<HAS_W, PACKED>(stages + s * SF, &full[s], sx, sy, sd, sw, c, n);
+    }
+  }
+  unsigned it = 0;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    const int s = it % kPipeStages;
+    mbar_wait(&full[s], (it / kPipeStages) & 1);
+    EventBlock<float, kPipeEpt, HAS_W, PACKED> e;
+    const int64_t first = chunk * kPipeChunk + (int64_t)tid * kPipeEpt;
+    const int valid = (int)max((int64_t)0, min((int64_t)kPipeEpt, n - first));
+    e.load_stage(stages + s * SF, kPipeChunk, tid * kPipeEpt, valid);
+    __syncthreads();  // every thread has copied its events out: the stage may be refilled
+    if (tid == 0) {
+      const int64_t nxt = chunk + (int64_t)kPipeStages * gridDim.x;
+      if (nxt < n_chunks) pipe_issue<HAS_W, PACKED>(stages + s * SF, &full[s], sx, sy, sd, sw, nxt, n);
+    }
+    if (valid > 0) {
+      e.finish(flow, W, hw);
+      body(e);
+    }
+  }
+}
+
+template <bool HAS_W, bool VEC, bool PACKED>
+__global__ void __launch_bounds__(256, 3)
+k_win_splat_pipe(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+                 const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h,
+                 int pad_w, float* __restrict__ iwe) {
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  pipe_loop<HAS_W, PACKED>(sx, sy, sd, sw, n, flow, W, H * W, [&](const EventBlock<float, kPipeEpt, HAS_W, PACKED>& e) {
+    splat_block<float, HAS_W, kPipeEpt, VEC, PACKED>(e, iwe, Hp, Wp, pad_h, pad_w);
+  });
 }
 
 // ---- backward ------------------------------------------------------------------------------------
@@ -377,6 +515,94 @@ __device__ __forceinline__ void load_pair(const double* __restrict__ p, int, dou
   hi = __ldg(p + 1);
 }
 
+// EPT consecutive events of one thread, processed in groups of 4: (phase 1) cells and fractions, then all
+// gathers of dL/dIWE of the group in flight together; (phase 2) gradients, combined over runs of the same
+// origin pixel (the run state is carried across groups), one REDG pair per pixel run.
+template <typename T> struct BwdParams {
+  int Hp, Wp, pad_h, pad_w, hw, lo;
+  unsigned r_span, c_span;
+  VarCoef<T> vc;
+};
+template <typename T, int GSRC>
+__device__ __forceinline__ BwdParams<T> make_bwd_params(int H, int W, int pad_h, int pad_w, const double* acc, int omit,
+                                                        double scale) {
+  BwdParams<T> P;
+  P.Hp = H + 2 * pad_h; P.Wp = W + 2 * pad_w; P.pad_h = pad_h; P.pad_w = pad_w; P.hw = H * W;
+  P.vc = VarCoef<T>{(T)0, (T)0, omit};
+  if (GSRC == 1) {
+    const double cnt = omit ? (double)(P.Hp - 2) * (double)(P.Wp - 2) : (double)P.Hp * (double)P.Wp;
+    P.vc.mean = (T)(acc[0] / cnt);
+    P.vc.cv = (T)(-2.0 * scale / (cnt - 1.0));
+  }
+  // fast range of cells whose four taps are all inside (and, for the cropped variance, all counted)
+  P.lo = (GSRC == 1 && omit) ? 1 : 0;
+  P.r_span = (unsigned)max(P.Hp - 1 - 2 * P.lo, 0);
+  P.c_span = (unsigned)max(P.Wp - 1 - 2 * P.lo, 0);
+  return P;
+}
+
+template <typename T, int GSRC, bool HAS_W, int EPT, bool VEC, bool PACKED>
+__device__ __forceinline__ void bwd_block(const EventBlock<T, EPT, HAS_W, PACKED>& e, const BwdParams<T>& P,
+                                          const T* __restrict__ g, T* __restrict__ dflow) {
+  constexpr int G = 4;
+  static_assert(EPT % G == 0, "EPT must be a multiple of the gather group");
+  int ck = -1;
+  T s0 = 0, s1 = 0;
+#pragma unroll
+  for (int h = 0; h < EPT; h += G) {
+    T a[G], b[G], g00[G], g01[G], g10[G], g11[G];
+    bool fast[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int j = h + i;
+      const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
+      const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
+      const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
+      fast[i] = FastFloor<T>::in_range(xb, yb);
+      int r = 0, c = 0;
+      if (fast[i]) {
+        const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
+        a[i] = Rn<T>::sub(xw, fr);
+        b[i] = Rn<T>::sub(yw, fc);
+        r = FastFloor<T>::to_int(fr) + P.pad_h;
+        c = FastFloor<T>::to_int(fc) + P.pad_w;
+        fast[i] = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span;
+      }
+      if (fast[i]) {
+        const T* p = g + (r * P.Wp + c);
+        load_pair<VEC>(p, c & 3, g00[i], g01[i]);
+        load_pair<VEC>(p + P.Wp, c & 3, g10[i], g11[i]);
+      } else {
+        // rare: border cell, out-of-range or skipped event -- exact masked gathers, result kept in g00/g01
+        T dx, dy;
+        bwd_event_exact<T, GSRC>(g, P.Hp, P.Wp, P.pad_h, P.pad_w, e.x[j] == e.x[j] ? xw : (T)NAN, yw, P.vc, dx, dy);
+        g00[i] = dx; g01[i] = dy; g10[i] = 0; g11[i] = 0; a[i] = 0; b[i] = 0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int j = h + i;
+      T dx, dy;
+      if (fast[i]) {
+        dx = ((T)1 - b[i]) * (g10[i] - g00[i]) + b[i] * (g11[i] - g01[i]);
+        dy = ((T)1 - a[i]) * (g01[i] - g00[i]) + a[i] * (g11[i] - g10[i]);
+        if (GSRC == 1) { dx *= P.vc.cv; dy *= P.vc.cv; }  // differences: the mean cancels
+      } else {
+        dx = g00[i]; dy = g01[i];
+      }
+      if (HAS_W) { dx *= e.wt[j]; dy *= e.wt[j]; }
+      if (e.x[j] != e.x[j]) continue;  // skipped event
+      if (e.k[j] != ck) {
+        if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + P.hw + ck, s1); }
+        ck = e.k[j]; s0 = 0; s1 = 0;
+      }
+      s0 -= e.d[j] * dx;
+      s1 -= e.d[j] * dy;
+    }
+  }
+  if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + P.hw + ck, s1); }
+}
+
 template <typename T, int GSRC, bool HAS_W, int EPT, bool VEC, bool PACKED>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 && EPT <= 4) ? 4 : 1)
 k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd, const T* __restrict__ sw,
@@ -384,71 +610,22 @@ k_win_bwd(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restric
           const double* __restrict__ acc, int omit, double scale, T* __restrict__ dflow) {
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * EPT;
   if (base >= n) return;
-  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
-  const int hw = H * W;
-  VarCoef<T> vc{(T)0, (T)0, omit};
-  if (GSRC == 1) {
-    const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
-    vc.mean = (T)(acc[0] / cnt);
-    vc.cv = (T)(-2.0 * scale / (cnt - 1.0));
-  }
-  // fast range of cells whose four taps are all inside (and, for the cropped variance, all counted)
-  const int lo = (GSRC == 1 && omit) ? 1 : 0;
-  const unsigned r_span = (unsigned)max(Hp - 1 - 2 * lo, 0), c_span = (unsigned)max(Wp - 1 - 2 * lo, 0);
+  const BwdParams<T> P = make_bwd_params<T, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
   EventBlock<T, EPT, HAS_W, PACKED> e;
-  e.load(sx, sy, sd, sw, base, n, flow, W, hw);
-  // phase 1: cells and fractions of all events, then all gathers of dL/dIWE in flight together
-  T a[EPT], b[EPT], g00[EPT], g01[EPT], g10[EPT], g11[EPT];
-  bool fast[EPT];
-#pragma unroll
-  for (int j = 0; j < EPT; ++j) {
-    const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
-    const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
-    const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
-    fast[j] = FastFloor<T>::in_range(xb, yb);
-    int r = 0, c = 0;
-    if (fast[j]) {
-      const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
-      a[j] = Rn<T>::sub(xw, fr);
-      b[j] = Rn<T>::sub(yw, fc);
-      r = FastFloor<T>::to_int(fr) + pad_h;
-      c = FastFloor<T>::to_int(fc) + pad_w;
-      fast[j] = (unsigned)(r - lo) < r_span && (unsigned)(c - lo) < c_span;
-    }
-    if (fast[j]) {
-      const T* p = g + (r * Wp + c);
-      load_pair<VEC>(p, c & 3, g00[j], g01[j]);
-      load_pair<VEC>(p + Wp, c & 3, g10[j], g11[j]);
-    } else {
-      // rare: border cell, out-of-range or skipped event -- exact masked gathers, result kept in g00/g01
-      T dx, dy;
-      bwd_event_exact<T, GSRC>(g, Hp, Wp, pad_h, pad_w, e.x[j] == e.x[j] ? xw : (T)NAN, yw, vc, dx, dy);
-      g00[j] = dx; g01[j] = dy; g10[j] = 0; g11[j] = 0; a[j] = 0; b[j] = 0;
-    }
-  }
-  // phase 2: gradients, combined over runs of the same origin pixel
-  int ck = -1;
-  T s0 = 0, s1 = 0;
-#pragma unroll
-  for (int j = 0; j < EPT; ++j) {
-    T dx, dy;
-    if (fast[j]) {
-      dx = ((T)1 - b[j]) * (g10[j] - g00[j]) + b[j] * (g11[j] - g01[j]);
-      dy = ((T)1 - a[j]) * (g01[j] - g00[j]) + a[j] * (g11[j] - g10[j]);
-      if (GSRC == 1) { dx *= vc.cv; dy *= vc.cv; }  // differences: the mean cancels
-    } else {
-      dx = g00[j]; dy = g01[j];
-    }
-    if (HAS_W) { dx *= e.wt[j]; dy *= e.wt[j]; }
-    if (e.x[j] != e.x[j]) continue;  // skipped event
-    if (e.k[j] != ck) {
-      if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
-      ck = e.k[j]; s0 = 0; s1 = 0;
-    }
-    s0 -= e.d[j] * dx;
-    s1 -= e.d[j] * dy;
-  }
-  if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + hw + ck, s1); }
+  e.load(sx, sy, sd, sw, base, n, flow, W, P.hw);
+  bwd_block<T, GSRC, HAS_W, EPT, VEC, PACKED>(e, P, g, dflow);
+}
+
+template <int GSRC, bool HAS_W, bool VEC, bool PACKED>
+__global__ void __launch_bounds__(256, 3)
+k_win_bwd_pipe(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+               const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h,
+               int pad_w, const float* __restrict__ g, const double* __restrict__ acc, int omit, double scale,
+               float* __restrict__ dflow) {
+  const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
+  pipe_loop<HAS_W, PACKED>(sx, sy, sd, sw, n, flow, W, P.hw, [&](const EventBlock<float, kPipeEpt, HAS_W, PACKED>& e) {
+    bwd_block<float, GSRC, HAS_W, kPipeEpt, VEC, PACKED>(e, P, g, dflow);
+  });
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -529,8 +706,35 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   int64_t threads = (n + ept - 1) / ept;
   unsigned grid = (unsigned)((threads + 255) / 256);
   // vector REDs need fp32, a 16-byte aligned plane and a row stride that keeps the alignment
-  static const int novec_env = env_int("EBOS_NO_VEC");
-  const bool vec = sizeof(T) == 4 && !novec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(iwe) & 15) == 0);
+  // (experiment knob, default off: red.v4 was measured slower than four scalar REDs in this kernel)
+  static const int vec_env = env_int("EBOS_VEC_RED");
+  const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(iwe) & 15) == 0);
+  // persistent TMA-staged kernel (fp32) once there are at least ~2 chunks per CTA slot; one-shot otherwise
+  static const int pipe_env = env_int("EBOS_PIPE");   // 0 auto, 1 force on, 2 force off (experiments)
+  if constexpr (sizeof(T) == 4) {
+    const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
+    const int slots = sm_count() * 3;
+    if (pipe_env != 2 && (pipe_env == 1 || n_chunks >= 2 * (int64_t)slots)) {
+      const unsigned pgrid = (unsigned)std::min<int64_t>(n_chunks, slots);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
+      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
+#define EBOS_SPLAT_P(WGT, V, P)                                                                                          \
+  do {                                                                                                                   \
+    auto kern = k_win_splat_pipe<WGT, V, P>;                                                                             \
+    const size_t smem = PipeCfg<WGT, P>::smem_bytes;                                                                     \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
+    kern<<<pgrid, 256, smem, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fi);                                        \
+  } while (0)
+      if (has_weight) { if (packed) { if (vec) EBOS_SPLAT_P(true, true, true); else EBOS_SPLAT_P(true, false, true); }
+                        else { if (vec) EBOS_SPLAT_P(true, true, false); else EBOS_SPLAT_P(true, false, false); } }
+      else { if (packed) { if (vec) EBOS_SPLAT_P(false, true, true); else EBOS_SPLAT_P(false, false, true); }
+             else { if (vec) EBOS_SPLAT_P(false, true, false); else EBOS_SPLAT_P(false, false, false); } }
+#undef EBOS_SPLAT_P
+      EBOS_LAUNCH_CHECK("ebos_window_splat(pipe)");
+      return EBOS_OK;
+    }
+  }
 #define EBOS_SPLAT_K(WGT, E, V, P) k_win_splat<T, WGT, E, V, P><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, iwe)
 #define EBOS_SPLAT_E(WGT, V, P) do { if (ept == 4) EBOS_SPLAT_K(WGT, 4, V, P); else EBOS_SPLAT_K(WGT, 8, V, P); } while (0)
   if constexpr (sizeof(T) == 4) {
@@ -572,9 +776,41 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
     return EBOS_ERR_BAD_ARG;
   }
   const T* gsrc = affine ? iwe : grad_iwe;
-  static const int novec_env = env_int("EBOS_NO_VEC_LOAD");
+  // (experiment knob, default off: float4 pair loads were measured slower -- L1 moves 4x the bytes)
+  static const int vec_env = env_int("EBOS_VEC_LOAD");
   const int Wp = W + 2 * pad_w;
-  const bool vec = sizeof(T) == 4 && !novec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
+  const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
+  static const int pipe_env = env_int("EBOS_PIPE");
+  if constexpr (sizeof(T) == 4) {
+    const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
+    const int slots = sm_count() * 3;
+    if (pipe_env != 2 && (pipe_env == 1 || n_chunks >= 2 * (int64_t)slots)) {
+      const unsigned pgrid = (unsigned)std::min<int64_t>(n_chunks, slots);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
+      const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
+      float* fo = reinterpret_cast<float*>(dflow);
+#define EBOS_BWD_P(G, WGT, V, P)                                                                                         \
+  do {                                                                                                                   \
+    auto kern = k_win_bwd_pipe<G, WGT, V, P>;                                                                            \
+    const size_t smem = PipeCfg<WGT, P>::smem_bytes;                                                                     \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
+    kern<<<pgrid, 256, smem, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo);         \
+  } while (0)
+#define EBOS_BWD_PG(G)                                                                                                   \
+  do {                                                                                                                   \
+    if (has_weight) { if (packed) { if (vec) EBOS_BWD_P(G, true, true, true); else EBOS_BWD_P(G, true, false, true); }    \
+                      else { if (vec) EBOS_BWD_P(G, true, true, false); else EBOS_BWD_P(G, true, false, false); } }       \
+    else { if (packed) { if (vec) EBOS_BWD_P(G, false, true, true); else EBOS_BWD_P(G, false, false, true); }             \
+           else { if (vec) EBOS_BWD_P(G, false, true, false); else EBOS_BWD_P(G, false, false, false); } }                \
+  } while (0)
+      if (affine) EBOS_BWD_PG(1); else EBOS_BWD_PG(0);
+#undef EBOS_BWD_PG
+#undef EBOS_BWD_P
+      EBOS_LAUNCH_CHECK("ebos_window_backward(pipe)");
+      return EBOS_OK;
+    }
+  }
 #define EBOS_BWD_K(G, WGT, V, P) k_win_bwd<T, G, WGT, Ept<T>::bwd, V, P><<<grid, 256, 0, st>>>(sx, sy, sd, sw, n, flow, H, W, pad_h, pad_w, gsrc, acc, omit_boundary, scale, dflow)
 #define EBOS_BWD_G(G)                                                                                              \
   do {                                                                                                             \

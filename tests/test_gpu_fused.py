@@ -81,6 +81,25 @@ def test_packed_and_generic_layouts_agree(ops):
         assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_pipelined_kernels_match_oracle(mode):
+    """EBOS_PIPE=1 forces the persistent TMA-staged streaming kernels (normally used from ~1.8 M events),
+    EBOS_PIPE=2 the one-shot kernels; both must match the oracle on small windows incl. ragged tails."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, EBOS_PIPE=mode)
+    script = os.path.join(os.path.dirname(__file__), "pipe_check.py")
+    res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert len(out) == 24
+    for key, (e_iwe, e_grad, e_loss) in out.items():
+        assert e_iwe <= REL and e_grad <= 2 * REL and e_loss <= REL, (mode, key, e_iwe, e_grad, e_loss)
+
+
 def test_invalid_events_are_skipped_when_not_validating(ops):
     """validate=False: an event outside the grid is parked and contributes nothing (the reference raises)."""
     H, W, n = 32, 48, 5000
