@@ -216,9 +216,8 @@ struct EventBlock {
         const bool skip = rc == 0xffffffffu;  // only past the end of the stream
         const int r = rc >> 16, c = rc & 0xffff;
         k[j] = skip ? 0 : r * W + c;
-        // exact int -> float for values below 2^22 on the FP32 pipe
-        x[j] = skip ? (T)NAN : (T)(__int_as_float(0x4B400000 + r) - 12582912.0f);
-        y[j] = (T)(__int_as_float(0x4B400000 + c) - 12582912.0f);
+        x[j] = skip ? (T)NAN : (T)r;
+        y[j] = (T)c;
       }
     } else {
 #pragma unroll
@@ -251,19 +250,15 @@ struct EventBlock {
 //    a run is flushed;
 //  * anything unusual (|coordinate| >= 2^22, Inf, NaN, parked events) leaves through one out-of-line
 //    exact path.
+// floor()/float->int run on the conversion (XU) pipe: ONE issue slot each.  The kernels are bound by issue
+// slots at ~0.5 IPC (ncu r01b: 45.4 M warp instructions / (592 SMSP x 0.51) = the measured 80 us), so the
+// FP32-pipe emulation of floor (4 slots) that an earlier revision used was a net loss.
 template <typename T> struct FastFloor;
 template <> struct FastFloor<float> {
-  static __device__ __forceinline__ bool in_range(float a, float b) { return fabsf(a) < 4194304.0f && fabsf(b) < 4194304.0f; }
-  static __device__ __forceinline__ float flr(float v) {
-    const float M = 12582912.0f;
-    float f = __fsub_rn(__fadd_rn(v, M), M);
-    return (f > v) ? __fsub_rn(f, 1.0f) : f;
-  }
-  // exact for integer-valued |f| < 2^22
-  static __device__ __forceinline__ int to_int(float f) { return __float_as_int(__fadd_rn(f, 12582912.0f)) - 0x4B400000; }
+  static __device__ __forceinline__ float flr(float v) { return floorf(v); }
+  static __device__ __forceinline__ int to_int(float f) { return (int)f; }  // saturating; NaN -> 0
 };
 template <> struct FastFloor<double> {
-  static __device__ __forceinline__ bool in_range(double a, double b) { return fabs(a) < 1073741824.0 && fabs(b) < 1073741824.0; }
   static __device__ __forceinline__ double flr(double v) { return floor(v); }
   static __device__ __forceinline__ int to_int(double f) { return (int)f; }
 };
@@ -336,15 +331,16 @@ __device__ __forceinline__ void splat_block(const EventBlock<T, EPT, HAS_W, PACK
   for (int j = 0; j < EPT; ++j) {
     const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
     const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
-    const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
-    if (!FastFloor<T>::in_range(xb, yb)) {
-      splat_event_exact<T>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], xw, yw, HAS_W ? e.wt[j] : (T)1);
-      continue;
-    }
-    const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
+    const T fr = FastFloor<T>::flr(Rn<T>::add(xw, Rn<T>::bias())), fc = FastFloor<T>::flr(Rn<T>::add(yw, Rn<T>::bias()));
     const T a = Rn<T>::sub(xw, fr), b = Rn<T>::sub(yw, fc);
     const T na = Rn<T>::sub((T)1, a), nb = Rn<T>::sub((T)1, b);
     T w0 = Rn<T>::mul(na, nb), w1 = Rn<T>::mul(a, nb), w2 = Rn<T>::mul(na, b), w3 = Rn<T>::mul(a, b);
+    if (w0 != w0) {
+      // NaN weight <=> non-finite warped coordinate (NaN, or Inf whose fraction is Inf - Inf), or an event
+      // marked to be skipped (x = NaN): the exact path reproduces the reference (NaN lands on pixel 0).
+      splat_event_exact<T>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], xw, yw, HAS_W ? e.wt[j] : (T)1);
+      continue;
+    }
     if (HAS_W) {
       w0 = Rn<T>::mul(w0, e.wt[j]); w1 = Rn<T>::mul(w1, e.wt[j]);
       w2 = Rn<T>::mul(w2, e.wt[j]); w3 = Rn<T>::mul(w3, e.wt[j]);
@@ -557,17 +553,13 @@ __device__ __forceinline__ void bwd_block(const EventBlock<T, EPT, HAS_W, PACKED
       const int j = h + i;
       const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
       const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
-      const T xb = Rn<T>::add(xw, Rn<T>::bias()), yb = Rn<T>::add(yw, Rn<T>::bias());
-      fast[i] = FastFloor<T>::in_range(xb, yb);
-      int r = 0, c = 0;
-      if (fast[i]) {
-        const T fr = FastFloor<T>::flr(xb), fc = FastFloor<T>::flr(yb);
-        a[i] = Rn<T>::sub(xw, fr);
-        b[i] = Rn<T>::sub(yw, fc);
-        r = FastFloor<T>::to_int(fr) + P.pad_h;
-        c = FastFloor<T>::to_int(fc) + P.pad_w;
-        fast[i] = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span;
-      }
+      const T fr = FastFloor<T>::flr(Rn<T>::add(xw, Rn<T>::bias())), fc = FastFloor<T>::flr(Rn<T>::add(yw, Rn<T>::bias()));
+      a[i] = Rn<T>::sub(xw, fr);
+      b[i] = Rn<T>::sub(yw, fc);
+      // saturating conversions: a huge / Inf coordinate lands outside the fast range; NaN converts to cell 0
+      // and is caught by the fraction test (NaN a or b)
+      const int r = FastFloor<T>::to_int(fr) + P.pad_h, c = FastFloor<T>::to_int(fc) + P.pad_w;
+      fast[i] = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span && (a[i] + b[i] == a[i] + b[i]);
       if (fast[i]) {
         const T* p = g + (r * P.Wp + c);
         load_pair<VEC>(p, c & 3, g00[i], g01[i]);
