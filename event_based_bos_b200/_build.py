@@ -28,6 +28,11 @@ NVCC_FLAGS = [
 ]
 
 
+# No per-file flags at present.  (ptxas 12.9 contracts explicit mul.rn.f32x2 + sub.rn.f32x2 into FFMA2 even with
+# --fmad=false; the exactness-critical warp therefore uses the scalar __fmul_rn/__fsub_rn forms, see ebos_window.cu.)
+PER_FILE_FLAGS = {}
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -55,7 +60,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         obj = os.path.join(build_dir, s.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(s, []), "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

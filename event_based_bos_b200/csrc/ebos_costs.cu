@@ -9,10 +9,34 @@
 // All reductions: per-thread double accumulators -> warp shuffle -> one atomicAdd(double) per CTA.
 // acc layout (double[8]): [0] sum(IWE) [1] sum(IWE^2) [2] sum(gx^2+gy^2) [3] sum(|TV terms|).
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 
 #include "ebos_common.cuh"
 
 namespace ebos {
+
+// The TV term depends only on the flow, the splat only on events + flow: inside the fused evaluation
+// they run concurrently (fork/join on a cached auxiliary stream; the pattern is CUDA-graph capturable).
+// One non-blocking stream and two events per device are created on first use and kept for the process.
+struct AuxLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+static AuxLane* aux_lane() {
+  static AuxLane lanes[64];
+  static std::mutex mu;
+  static const bool disabled = getenv("EBOS_NO_OVERLAP") != nullptr;
+  if (disabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  AuxLane& L = lanes[dev];
+  if (!L.ok) {
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    L.ok = true;
+  }
+  return &L;
+}
 
 int window_splat_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                         int pad_w, int dtype, void* iwe, cudaStream_t st);
@@ -190,43 +214,86 @@ __device__ __forceinline__ T tv_axis(const T v[5], const T w[3], int i, int n, T
   return out;
 }
 
-// A CTA is a 32-column x 8-row patch of one channel; the grid is persistent (a few CTAs per SM looping over
-// the patches) so that the loss partials end in a few hundred same-address atomics instead of thousands
-// (measured: 7200 one-shot CTAs spent 20 us serialised on one atomicAdd(double) address).
+// One thread = 4 consecutive columns of one row of one channel.  Deep-interior quads (two samples away from
+// every edge, unit weights) take a lean path: five float4 row loads + two float4 column neighbours, the
+// adjoint reduces to  0.5*(sgn(f[i]-f[i-2]) - sgn(f[i+2]-f[i]))  per axis.  Everything else (edges, per-pixel
+// weights, unaligned widths) goes through the general per-element code.  The kernel was instruction-bound
+// (~200 instructions per element in the first version).
+template <typename T, bool HAS_WTS>
+__device__ __noinline__ void tv_element_general(const T* __restrict__ f, const T* __restrict__ weights, int H, int W,
+                                                int r, int c, T coef, T* __restrict__ out, double& part) {
+  T vr[5], vc[5], wr[3] = {(T)1, (T)1, (T)1}, wc[3] = {(T)1, (T)1, (T)1};
+#pragma unroll
+  for (int o = -2; o <= 2; ++o) {
+    const int rr = min(max(r + o, 0), H - 1), cc = min(max(c + o, 0), W - 1);
+    vr[o + 2] = __ldg(f + (int64_t)rr * W + c);
+    vc[o + 2] = __ldg(f + (int64_t)r * W + cc);
+  }
+  if (HAS_WTS) {
+#pragma unroll
+    for (int o = -1; o <= 1; ++o) {
+      const int rr = min(max(r + o, 0), H - 1), cc = min(max(c + o, 0), W - 1);
+      wr[o + 1] = __ldg(weights + (int64_t)rr * W + c);
+      wc[o + 1] = __ldg(weights + (int64_t)r * W + cc);
+    }
+  }
+  T ar, ac;
+  const T adj = tv_axis<T>(vr, wr, r, H, ar) + tv_axis<T>(vc, wc, c, W, ac);
+  part += (double)ar + (double)ac;
+  out[(int64_t)r * W + c] = coef * adj;
+}
+
+__device__ __forceinline__ float sgn_diff(float a, float b) {  // sign(a - b) without forming NaN surprises
+  const float d = a - b;
+  return (d > 0.f ? 1.f : 0.f) - (d < 0.f ? 1.f : 0.f);
+}
+
 template <typename T, bool HAS_WTS>
 __global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, const T* __restrict__ weights, int H, int W,
                                                  T coef, double* __restrict__ acc, T* __restrict__ dflow) {
   // coef = tv_scale / (2*H*W)
   __shared__ double sm[32];
-  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
-  const int n_tiles = tiles_x * tiles_y * 2;
+  const int quads = (W + 3) / 4;
+  const int64_t total = (int64_t)2 * H * quads;
+  const bool lean_ok = sizeof(T) == 4 && !HAS_WTS && (W % 4 == 0) && ((reinterpret_cast<size_t>(flow) & 15) == 0) &&
+                       ((reinterpret_cast<size_t>(dflow) & 15) == 0);
   double part = 0.0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int ch = tile / (tiles_x * tiles_y), rem = tile - ch * (tiles_x * tiles_y);
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int c = tx * 32 + (threadIdx.x & 31), r = ty * 8 + (threadIdx.x >> 5);
-    if (!(c < W && r < H)) continue;
+  float fpart = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % quads);
+    const int64_t rest = i / quads;
+    const int r = (int)(rest % H), ch = (int)(rest / H);
+    const int c0 = q * 4;
     const T* f = flow + (int64_t)ch * H * W;
-    T vr[5], vc[5], wr[3] = {(T)1, (T)1, (T)1}, wc[3] = {(T)1, (T)1, (T)1};
+    T* out = dflow + (int64_t)ch * H * W;
+    if constexpr (sizeof(T) == 4) {
+      if (lean_ok && r >= 2 && r <= H - 3 && c0 >= 4 && c0 + 8 <= W) {
+        const float* p = reinterpret_cast<const float*>(f) + (int64_t)r * W + c0;
+        const float4 m2 = __ldg(reinterpret_cast<const float4*>(p - 2 * W)), m1 = __ldg(reinterpret_cast<const float4*>(p - W));
+        const float4 ce = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(p + W)), p2 = __ldg(reinterpret_cast<const float4*>(p + 2 * W));
+        const float4 lf = __ldg(reinterpret_cast<const float4*>(p - 4)), rt = __ldg(reinterpret_cast<const float4*>(p + 4));
+        const float row[12] = {lf.x, lf.y, lf.z, lf.w, ce.x, ce.y, ce.z, ce.w, rt.x, rt.y, rt.z, rt.w};
+        const float um2[4] = {m2.x, m2.y, m2.z, m2.w}, um1[4] = {m1.x, m1.y, m1.z, m1.w};
+        const float up1[4] = {p1.x, p1.y, p1.z, p1.w}, up2[4] = {p2.x, p2.y, p2.z, p2.w};
+        float o[4];
 #pragma unroll
-    for (int o = -2; o <= 2; ++o) {
-      const int rr = min(max(r + o, 0), H - 1), cc = min(max(c + o, 0), W - 1);
-      vr[o + 2] = __ldg(f + (int64_t)rr * W + c);
-      vc[o + 2] = __ldg(f + (int64_t)r * W + cc);
-    }
-    if (HAS_WTS) {
-#pragma unroll
-      for (int o = -1; o <= 1; ++o) {
-        const int rr = min(max(r + o, 0), H - 1), cc = min(max(c + o, 0), W - 1);
-        wr[o + 1] = __ldg(weights + (int64_t)rr * W + c);
-        wc[o + 1] = __ldg(weights + (int64_t)r * W + cc);
+        for (int k = 0; k < 4; ++k) {
+          const float v = row[4 + k];
+          // rows: q = r-1 and r+1 are interior samples here (2 <= r <= H-3)
+          float adj = 0.5f * (sgn_diff(v, um2[k]) - sgn_diff(up2[k], v));
+          // columns: c = c0+k with 4 <= c0 and c0+8 <= W  =>  c-2 >= 2 and c+2 <= W-3: interior
+          adj += 0.5f * (sgn_diff(v, row[2 + k]) - sgn_diff(row[6 + k], v));
+          fpart += 0.5f * (fabsf(up1[k] - um1[k]) + fabsf(row[5 + k] - row[3 + k]));
+          o[k] = (float)coef * adj;
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (int64_t)r * W + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        continue;
       }
     }
-    T ar, ac;
-    const T adj = tv_axis<T>(vr, wr, r, H, ar) + tv_axis<T>(vc, wc, c, W, ac);
-    part += (double)ar + (double)ac;
-    dflow[(int64_t)ch * H * W + (int64_t)r * W + c] = coef * adj;
+    for (int k = 0; k < 4 && c0 + k < W; ++k) tv_element_general<T, HAS_WTS>(f, weights, H, W, r, c0 + k, coef, out, part);
   }
+  part += (double)fpart;
   part = block_sum(part, sm);
   if (threadIdx.x == 0 && acc) atomicAdd(acc + 3, part);
 }
@@ -311,8 +378,8 @@ int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, do
     return EBOS_ERR_BAD_ARG;
   }
   const T coef = (T)(tv_scale / (2.0 * (double)H * (double)W));
-  const int n_tiles = ((W + 31) / 32) * ((H + 7) / 8) * 2;
-  const int grid = std::max(1, std::min(n_tiles, sm_count() * 4));
+  const int64_t quads = (int64_t)2 * H * ((W + 3) / 4);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((quads + 255) / 256, (int64_t)sm_count() * 8));
   if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   EBOS_LAUNCH_CHECK("ebos_flow_tv");
@@ -388,20 +455,33 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
-  int rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st);
+  // fork: TV(flow) -> dflow on the auxiliary lane, concurrently with splat + cost on `st`
+  AuxLane* lane = aux_lane();
+  cudaStream_t tv_st = st;
+  if (lane) {
+    if (cudaEventRecord(lane->fork, st) == cudaSuccess && cudaStreamWaitEvent(lane->stream, lane->fork, 0) == cudaSuccess)
+      tv_st = lane->stream;
+    else
+      lane = nullptr;
+  }
+  int rc;
+  if (dtype == EBOS_F64)
+    rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, tv_st);
+  else
+    rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st);
+  if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(join)");
+  if (rc) return rc;
+  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st);
   if (rc) return rc;
   // variance: no gradient plane, the backward derives it from (iwe, acc)
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
-  if (dtype == EBOS_F64) {
+  if (dtype == EBOS_F64)
     rc = iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)gplane, st);
-    if (rc) return rc;
-    rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, st);
-  } else {
+  else
     rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
-    if (rc) return rc;
-    rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, st);
-  }
   if (rc) return rc;
+  // join: the backward accumulates into the dflow the TV kernel wrote
+  if (lane && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(wait)");
   rc = window_backward_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc,
                               omit_boundary, data_scale, dflow, st);
   if (rc) return rc;

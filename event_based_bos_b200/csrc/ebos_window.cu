@@ -29,6 +29,10 @@ namespace ebos {
 template <typename T> struct Ept;
 template <> struct Ept<float> { static constexpr int splat = 8, bwd = 4; };
 template <> struct Ept<double> { static constexpr int splat = 4, bwd = 4; };
+// Diagnostics: EBOS_ABLATE bit mask removes one cost component from the one-shot streaming kernels so that its
+// share of the run time can be measured directly (results are then WRONG; never set outside profiling):
+//   1 no REDs   2 no flow gathers (constant flow)   4 no event loads (synthetic events)   8 no dL/dIWE gathers
+__device__ int g_ablate = 0;
 // experiment knob (EBOS_SPLAT_EPT / EBOS_BWD_EPT environment variables; 0 = default)
 static int env_int(const char* name) {
   const char* v = getenv(name);
@@ -226,18 +230,56 @@ struct EventBlock {
         k[j] = (unsigned)kk < (unsigned)hw ? kk : 0;
       }
     }
+    // The events are sorted by origin pixel: a thread's consecutive events mostly share it, so a gather is only
+    // issued when the pixel changes (ablation r01c: the redundant gathers cost 15-17 us per pass at 16 Mi events).
+    f0[0] = __ldg(flow + k[0]);
+    f1[0] = __ldg(flow + hw + k[0]);
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-      f0[j] = __ldg(flow + k[j]);
-      f1[j] = __ldg(flow + hw + k[j]);
+    for (int j = 1; j < EPT; ++j) {
+      if (k[j] != k[j - 1]) {
+        f0[j] = __ldg(flow + k[j]);
+        f1[j] = __ldg(flow + hw + k[j]);
+      } else {
+        f0[j] = f0[j - 1];
+        f1[j] = f1[j - 1];
+      }
     }
   }
 
   __device__ __forceinline__ void load(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,
                                        const T* __restrict__ sw, int64_t base, int64_t n, const T* __restrict__ flow,
                                        int W, int hw) {
-    load_global(sx, sy, sd, sw, base, n);
-    finish(flow, W, hw);
+    const int abl = g_ablate;
+    if (abl & 4) {  // diagnostics: synthetic events instead of loads
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const unsigned pix = (unsigned)((base + j) / 17) % (unsigned)hw;
+        if (PACKED) x[j] = (T)__uint_as_float(((pix / W) << 16) | (pix % W)); else { x[j] = (T)(pix / W); y[j] = (T)(pix % W); }
+        d[j] = (T)((base + j) % 17) * (T)0.0588f;
+        if (HAS_W) wt[j] = 1;
+      }
+    } else {
+      load_global(sx, sy, sd, sw, base, n);
+    }
+    if (abl & 2) {  // diagnostics: no flow gathers
+      finish_nogather(W, hw);
+    } else {
+      finish(flow, W, hw);
+    }
+  }
+  __device__ __forceinline__ void finish_nogather(int W, int hw) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      if constexpr (PACKED) {
+        const unsigned rc = __float_as_uint(x[j]);
+        const int r = rc >> 16, c = rc & 0xffff;
+        k[j] = r * W + c; x[j] = (T)r; y[j] = (T)c;
+      } else {
+        const int kk = (int)x[j] * W + (int)y[j];
+        k[j] = (unsigned)kk < (unsigned)hw ? kk : 0;
+      }
+      f0[j] = (T)1.37 + (T)(k[j] & 3) * (T)0.4; f1[j] = (T)-2.11 + (T)(k[j] & 7) * (T)0.3;
+    }
   }
 };
 
@@ -289,6 +331,7 @@ __device__ __noinline__ void splat_event_exact(T* __restrict__ iwe, int Hp, int 
 template <typename T, bool VEC>
 __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, int Hm1, int Wm1, int r, int c, T a0,
                                            T a1, T a2, T a3) {
+  if (g_ablate & 1) { if (a0 + a1 + a2 + a3 == (T)-12345) iwe[0] = a0; return; }  // diagnostics: no REDs
   if ((unsigned)r < (unsigned)Hm1 && (unsigned)c < (unsigned)Wm1) {
     // all four taps inside: the common case
     T* p = iwe + (r * Wp + c);
@@ -319,10 +362,56 @@ __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, 
   }
 }
 
+// fp32 version on packed f32x2 arithmetic: identical per-lane rounding, about half the FP issue slots.
+template <bool HAS_W, int EPT, bool VEC, bool PACKED>
+__device__ __forceinline__ void splat_block_f32(const EventBlock<float, EPT, HAS_W, PACKED>& e, float* __restrict__ iwe,
+                                                int Hp, int Wp, int pad_h, int pad_w) {
+  const int Hm1 = Hp - 1, Wm1 = Wp - 1;
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+  float cfr = NAN, cfc = 0.f;           // current run: floor values of the cell (NaN = none)
+  float2 a01 = zero2, a23 = zero2;      // tap sums (w0, w1), (w2, w3)
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) {
+    // x' = x - (dt * f): the two roundings must stay separate (bit-exact cells).  ptxas 12.9 contracts
+    // mul.rn.f32x2 + sub.rn.f32x2 into FFMA2 (even with --fmad=false), so this step uses the scalar forms.
+    const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+    const float2 wb = add2(w, bias2);
+    const float fr = floorf(wb.x), fc = floorf(wb.y);
+    const float2 ab = sub2(w, make_float2(fr, fc));
+    const float2 nab = sub2(one2, ab);
+    const float2 lhs = make_float2(nab.x, ab.x);                        // (1-a, a)
+    float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));                  // (w0, w1) = ((1-a)(1-b), a(1-b))
+    float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));                    // (w2, w3) = ((1-a)b, ab)
+    if (w01.x != w01.x) {
+      // NaN weight <=> non-finite warped coordinate or an event marked to be skipped (x = NaN)
+      splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, HAS_W ? e.wt[j] : 1.f);
+      continue;
+    }
+    if (HAS_W) {
+      const float2 ww = make_float2(e.wt[j], e.wt[j]);
+      w01 = mul2(w01, ww);
+      w23 = mul2(w23, ww);
+    }
+    if (!((fr == cfr) & (fc == cfc))) {
+      if (cfr == cfr)
+        flush_cell<float, VEC>(iwe, Hp, Wp, Hm1, Wm1, (int)cfr + pad_h, (int)cfc + pad_w, a01.x, a01.y, a23.x, a23.y);
+      cfr = fr; cfc = fc;
+      a01 = zero2; a23 = zero2;
+    }
+    a01 = add2(a01, w01);
+    a23 = add2(a23, w23);
+  }
+  if (cfr == cfr) flush_cell<float, VEC>(iwe, Hp, Wp, Hm1, Wm1, (int)cfr + pad_h, (int)cfc + pad_w, a01.x, a01.y, a23.x, a23.y);
+}
+
 // EPT consecutive events of one thread: warp, vote, combine runs of equal cells, flush.
 template <typename T, bool HAS_W, int EPT, bool VEC, bool PACKED>
 __device__ __forceinline__ void splat_block(const EventBlock<T, EPT, HAS_W, PACKED>& e, T* __restrict__ iwe, int Hp,
                                             int Wp, int pad_h, int pad_w) {
+  if constexpr (sizeof(T) == 4) {
+    splat_block_f32<HAS_W, EPT, VEC, PACKED>(e, iwe, Hp, Wp, pad_h, pad_w);
+    return;
+  }
   const int Hm1 = Hp - 1, Wm1 = Wp - 1;
   // current run: floor values of the cell (NaN = none) and the four tap sums
   T cfr = (T)NAN, cfc = (T)0;
@@ -551,16 +640,27 @@ __device__ __forceinline__ void bwd_block(const EventBlock<T, EPT, HAS_W, PACKED
 #pragma unroll
     for (int i = 0; i < G; ++i) {
       const int j = h + i;
-      const T xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
-      const T yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
-      const T fr = FastFloor<T>::flr(Rn<T>::add(xw, Rn<T>::bias())), fc = FastFloor<T>::flr(Rn<T>::add(yw, Rn<T>::bias()));
-      a[i] = Rn<T>::sub(xw, fr);
-      b[i] = Rn<T>::sub(yw, fc);
+      T xw, yw, fr, fc;
+      if constexpr (sizeof(T) == 4) {
+        const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+        const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
+        fr = floorf(wb.x); fc = floorf(wb.y);
+        const float2 ab = sub2(w, make_float2(fr, fc));
+        xw = w.x; yw = w.y; a[i] = ab.x; b[i] = ab.y;
+      } else {
+        xw = Rn<T>::sub(e.x[j], Rn<T>::mul(e.d[j], e.f0[j]));
+        yw = Rn<T>::sub(e.y[j], Rn<T>::mul(e.d[j], e.f1[j]));
+        fr = FastFloor<T>::flr(Rn<T>::add(xw, Rn<T>::bias())); fc = FastFloor<T>::flr(Rn<T>::add(yw, Rn<T>::bias()));
+        a[i] = Rn<T>::sub(xw, fr);
+        b[i] = Rn<T>::sub(yw, fc);
+      }
       // saturating conversions: a huge / Inf coordinate lands outside the fast range; NaN converts to cell 0
       // and is caught by the fraction test (NaN a or b)
       const int r = FastFloor<T>::to_int(fr) + P.pad_h, c = FastFloor<T>::to_int(fc) + P.pad_w;
       fast[i] = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span && (a[i] + b[i] == a[i] + b[i]);
-      if (fast[i]) {
+      if (fast[i] && (g_ablate & 8)) {  // diagnostics: no dL/dIWE gathers
+        g00[i] = a[i]; g01[i] = b[i]; g10[i] = (T)r; g11[i] = (T)c;
+      } else if (fast[i]) {
         const T* p = g + (r * P.Wp + c);
         load_pair<VEC>(p, c & 3, g00[i], g01[i]);
         load_pair<VEC>(p + P.Wp, c & 3, g10[i], g11[i]);
@@ -576,8 +676,17 @@ __device__ __forceinline__ void bwd_block(const EventBlock<T, EPT, HAS_W, PACKED
       const int j = h + i;
       T dx, dy;
       if (fast[i]) {
-        dx = ((T)1 - b[i]) * (g10[i] - g00[i]) + b[i] * (g11[i] - g01[i]);
-        dy = ((T)1 - a[i]) * (g01[i] - g00[i]) + a[i] * (g11[i] - g10[i]);
+        if constexpr (sizeof(T) == 4) {
+          // (dx, dy) = (1-b, 1-a) * (g10-g00, g01-g00) + (b, a) * (g11-g01, g11-g10)   on packed f32x2
+          const float2 d1 = sub2(make_float2(g10[i], g01[i]), make_float2(g00[i], g00[i]));
+          const float2 d2 = sub2(make_float2(g11[i], g11[i]), make_float2(g01[i], g10[i]));
+          const float2 ba = make_float2(b[i], a[i]);
+          const float2 r = fma2(ba, d2, mul2(sub2(make_float2(1.f, 1.f), ba), d1));
+          dx = r.x; dy = r.y;
+        } else {
+          dx = ((T)1 - b[i]) * (g10[i] - g00[i]) + b[i] * (g11[i] - g01[i]);
+          dy = ((T)1 - a[i]) * (g01[i] - g00[i]) + a[i] * (g11[i] - g10[i]);
+        }
         if (GSRC == 1) { dx *= P.vc.cv; dy *= P.vc.cv; }  // differences: the mean cancels
       } else {
         dx = g00[i]; dy = g01[i];
@@ -585,14 +694,16 @@ __device__ __forceinline__ void bwd_block(const EventBlock<T, EPT, HAS_W, PACKED
       if (HAS_W) { dx *= e.wt[j]; dy *= e.wt[j]; }
       if (e.x[j] != e.x[j]) continue;  // skipped event
       if (e.k[j] != ck) {
-        if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + P.hw + ck, s1); }
+        if (ck >= 0 && !(g_ablate & 1)) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + P.hw + ck, s1); }
+        else if (ck >= 0 && s0 + s1 == (T)-12345) dflow[0] = s0;
         ck = e.k[j]; s0 = 0; s1 = 0;
       }
       s0 -= e.d[j] * dx;
       s1 -= e.d[j] * dy;
     }
   }
-  if (ck >= 0) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + P.hw + ck, s1); }
+  if (ck >= 0 && !(g_ablate & 1)) { red_add_nc(dflow + ck, s0); red_add_nc(dflow + P.hw + ck, s1); }
+  else if (ck >= 0 && s0 + s1 == (T)-12345) dflow[0] = s0;
 }
 
 template <typename T, int GSRC, bool HAS_W, int EPT, bool VEC, bool PACKED>
@@ -678,10 +789,19 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   return EBOS_OK;
 }
 
+static void apply_ablate_env() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const int v = env_int("EBOS_ABLATE");
+  if (v) cudaMemcpyToSymbol(g_ablate, &v, sizeof(int));
+}
+
 template <typename T>
 int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int H, int W, int pad_h, int pad_w, T* iwe,
                    cudaStream_t st) {
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  apply_ablate_env();
   cudaError_t e = cudaMemsetAsync(iwe, 0, (size_t)Hp * Wp * sizeof(T), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_window_splat memset");
   if (n == 0) return EBOS_OK;
