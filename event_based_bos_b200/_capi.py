@@ -39,11 +39,11 @@ SIGNATURES = {
     "ebos_splat_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int]),
     "ebos_iwe_splat_bwd": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_double, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
-    "ebos_window_bytes": (c_size_t, [c_int64, c_int]),
+    "ebos_window_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "ebos_window_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "ebos_window_prepare": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
-    "ebos_window_info": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "ebos_window_info": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ebos_window_splat": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p]),
     "ebos_iwe_cost": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),

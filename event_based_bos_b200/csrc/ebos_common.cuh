@@ -252,15 +252,24 @@ struct WindowHeader {
   unsigned long long enc_min, enc_max;      // order-preserving encodings used by the atomic min/max pass
   int not_packable;                         // some coordinate is not a small non-negative integer
   int packed;                               // 1: x slot holds (row << 16 | col) as uint32, y slot unused
+  int n_items;                              // work items (tile, chunk) of the tile kernels
 };
 static_assert(sizeof(WindowHeader) <= 256, "header must fit its slot");
 
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// Spatial tiling of the ORIGIN pixel grid used by the sort key and the shared-memory tile kernels.
+constexpr int kTileH = 32, kTileW = 32;
+constexpr int kItemEvents = 8192;           // events per work item (a hot tile is split into several items)
+inline int tiles_x(int W) { return (W + kTileW - 1) / kTileW; }
+inline int tiles_y(int H) { return (H + kTileH - 1) / kTileH; }
+inline int64_t max_items(int64_t n, int H, int W) { return n / kItemEvents + (int64_t)tiles_x(W) * tiles_y(H) + 1; }
+
 struct WindowLayout {
-  size_t off_x, off_y, off_d, off_w, off_perm, total;
+  size_t off_x, off_y, off_d, off_w, off_perm, off_tiles, off_items, total;
 };
-inline WindowLayout window_layout(int64_t n, size_t elem) {
+// events sorted by (tile, pixel-in-tile, time); tile_off[t] = first event of tile t; items = int4 (tile, begin, end, 0)
+inline WindowLayout window_layout(int64_t n, size_t elem, int H, int W) {
   WindowLayout L;
   size_t a = align256((size_t)n * elem);
   L.off_x = 256;
@@ -268,7 +277,9 @@ inline WindowLayout window_layout(int64_t n, size_t elem) {
   L.off_d = L.off_y + a;
   L.off_w = L.off_d + a;
   L.off_perm = L.off_w + a;
-  L.total = L.off_perm + align256((size_t)n * 4);
+  L.off_tiles = L.off_perm + align256((size_t)n * 4);
+  L.off_items = L.off_tiles + align256(((size_t)tiles_x(W) * tiles_y(H) + 1) * 4);
+  L.total = L.off_items + align256((size_t)max_items(n, H, W) * 16);
   return L;
 }
 inline size_t dtype_size(int dtype) { return dtype == EBOS_F64 ? 8 : 4; }

@@ -45,6 +45,7 @@ __global__ void k_win_hdr_init(WindowHeader* h) {
   h->enc_max = 0ull;
   h->not_packable = 0;
   h->packed = 0;
+  h->n_items = 0;
 }
 
 template <typename T>
@@ -89,6 +90,8 @@ __global__ void __launch_bounds__(256) k_win_keys(const T* __restrict__ ev, int6
                                                   unsigned int* __restrict__ keys, int* __restrict__ idx,
                                                   int32_t* __restrict__ status, WindowHeader* __restrict__ h) {
   const int64_t hw = (int64_t)H * W;
+  const int tx = (W + kTileW - 1) / kTileW, ty = (H + kTileH - 1) / kTileH;
+  const unsigned int n_keys = (unsigned int)(tx * ty) * (kTileH * kTileW) + 1;
   bool bad = false, frac = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     T x = __ldg(ev + 4 * i), y = __ldg(ev + 4 * i + 1);
@@ -96,7 +99,14 @@ __global__ void __launch_bounds__(256) k_win_keys(const T* __restrict__ ev, int6
     bool ok = k >= 0 && k < hw && Rn<T>::finite(x) && Rn<T>::finite(y);
     bad |= !ok;
     frac |= !(ok && x >= (T)0 && y >= (T)0 && x < (T)65536 && y < (T)65536 && x == (T)(int)x && y == (T)(int)y);
-    keys[i] = ok ? (unsigned int)k : (unsigned int)hw;
+    // tile-major key: (tile, pixel inside the tile); the origin pixel is k -> (k / W, k % W)
+    unsigned int key = n_keys - 1;  // invalid events: after every valid key
+    if (ok) {
+      const int r = (int)(k / W), c = (int)(k - (int64_t)r * W);
+      const int tile = (r / kTileH) * tx + (c / kTileW);
+      key = (unsigned int)tile * (kTileH * kTileW) + (unsigned int)((r % kTileH) * kTileW + (c % kTileW));
+    }
+    keys[i] = key;
     idx[i] = (int)i;
   }
   if (bad) atomicOr(status, EBOS_STATUS_PIXEL_OOB);
@@ -106,6 +116,55 @@ __global__ void __launch_bounds__(256) k_win_keys(const T* __restrict__ ev, int6
 __global__ void k_win_layout(WindowHeader* h, int allow_packed, int32_t* __restrict__ status) {
   h->packed = (allow_packed && !h->not_packable) ? 1 : 0;
   if (h->packed) atomicOr(status, EBOS_STATUS_PACKED);
+}
+
+// tile_off[t] = first sorted position whose key belongs to tile >= t (binary search on the sorted keys)
+__global__ void __launch_bounds__(256) k_win_tile_offsets(const unsigned int* __restrict__ sorted_keys, int64_t n,
+                                                          int n_tiles, int* __restrict__ tile_off) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  const unsigned int target = (unsigned int)t * (kTileH * kTileW);
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(sorted_keys + mid) < target) lo = mid + 1; else hi = mid;
+  }
+  tile_off[t] = (int)lo;   // t == n_tiles: end of the valid events (invalid ones carry the largest key)
+}
+
+// Work items (tile, begin, end): every tile's event range cut into pieces of at most kItemEvents.
+// One CTA: per-tile item counts, block-wide exclusive scan (looped), fill.
+__global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int4* __restrict__ items,
+                                                    WindowHeader* __restrict__ h) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    int cnt = 0, b = 0, e = 0;
+    if (t < n_tiles) { b = tile_off[t]; e = tile_off[t + 1]; cnt = (e - b + kItemEvents - 1) / kItemEvents; }
+    // inclusive scan of cnt over the block
+    int v = cnt;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int excl = carry + (wid ? warp_sums[wid - 1] : 0) + v - cnt;
+    for (int i = 0; i < cnt; ++i) items[excl + i] = make_int4(t, b + i * kItemEvents, min(b + (i + 1) * kItemEvents, e), 0);
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + cnt;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) h->n_items = carry;
 }
 
 template <typename T>
@@ -179,6 +238,31 @@ struct EventBlock {
     } else {
       load_block<T, EPT>(sx, base, n, (T)NAN, x);
       load_block<T, EPT>(sy, base, n, (T)0, y);
+    }
+  }
+
+  // events [base, base+EPT) of the sorted stream, restricted to the half-open range [lo, hi) of one work item;
+  // base is a multiple of EPT (aligned vector loads); events outside the range are marked as skipped
+  __device__ __forceinline__ void load_range(const T* __restrict__ sx, const T* __restrict__ sy,
+                                             const T* __restrict__ sd, const T* __restrict__ sw, int64_t base,
+                                             int64_t lo, int64_t hi) {
+    if (base >= lo && base + EPT <= hi) {
+#pragma unroll
+      for (int j = 0; j < EPT; j += 4) {
+        load4(sd + base + j, d + j);
+        if (HAS_W) load4(sw + base + j, wt + j);
+        load4(sx + base + j, x + j);
+        if (!PACKED) load4(sy + base + j, y + j);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const bool in = base + j >= lo && base + j < hi;
+        d[j] = in ? sd[base + j] : (T)0;
+        if (HAS_W) wt[j] = in ? sw[base + j] : (T)0;
+        if (PACKED) x[j] = in ? sx[base + j] : (T)__uint_as_float(0xffffffffu);
+        else { x[j] = in ? sx[base + j] : (T)NAN; y[j] = in ? sy[base + j] : (T)0; }
+      }
     }
   }
 
@@ -549,6 +633,103 @@ k_win_splat_pipe(const float* __restrict__ sx, const float* __restrict__ sy, con
   });
 }
 
+// ---- shared-memory tile kernels (fp32) ----------------------------------------------------------------
+// The one-shot kernels sit on two LSU walls measured on B200 (profiles/microbench/r01_red_throughput.txt and the
+// r01c ablation): global REDs cost ~1.15 SM-cycles per lane (17 M lane-REDs = 70 us of the 80 us splat) and the
+// four dL/dIWE gathers of the backward 0.24 cycles per lane (67 M lane-loads = 57 us of 90 us).  Shared memory
+// does the same operations 3-4x faster (float atomicAdd 0.42, LDS 0.14 cycles per lane).  Events are therefore
+// sorted by 32x32 TILE of their origin pixel; a CTA takes one work item (tile, <= 8192 events), accumulates /
+// gathers in a shared-memory window of the IWE that covers the tile plus a halo of kHalo pixels, and only taps
+// outside the window (|flow * dt| > kHalo) fall back to global memory, so correctness never depends on the halo.
+constexpr int kHalo = 4;
+constexpr int kSH = kTileH + 2 * kHalo + 1;   // window rows  (taps reach one past the last cell)
+constexpr int kSW = kTileW + 2 * kHalo + 1;   // window cols; 41 is odd: consecutive rows start in different banks
+
+__device__ __forceinline__ void tile_origin(int tile, int W, int pad_h, int pad_w, int& r_org, int& c_org) {
+  const int tx = (W + kTileW - 1) / kTileW;
+  r_org = (tile / tx) * kTileH - kHalo + pad_h;   // padded-image coordinates of window element (0,0)
+  c_org = (tile % tx) * kTileW - kHalo + pad_w;
+}
+
+template <bool HAS_W, bool PACKED>
+__global__ void __launch_bounds__(256, 4)
+k_tile_splat(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+             const float* __restrict__ sw, const int4* __restrict__ items, const WindowHeader* __restrict__ hdr,
+             const float* __restrict__ flow, int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
+  constexpr int EPT = 8;
+  __shared__ float win[kSH * kSW];
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, Hm1 = Hp - 1, Wm1 = Wp - 1, hw = H * W;
+  const int n_items = hdr->n_items;
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int4 it = __ldg(items + item);
+    int r_org, c_org;
+    tile_origin(it.x, W, pad_h, pad_w, r_org, c_org);
+    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0.f;
+    __syncthreads();
+    // one run (cell + four tap sums) goes to the shared window when all four taps are inside it
+    auto flush = [&](float cfr, float cfc, float2 a01, float2 a23) {
+      const int r = (int)cfr + pad_h, c = (int)cfc + pad_w;
+      const int lr = r - r_org, lc = c - c_org;
+      if ((unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1)) {
+        float* p = win + lr * kSW + lc;
+        atomicAdd(p, a01.x);            // (r  , c  )
+        atomicAdd(p + kSW, a01.y);      // (r+1, c  )
+        atomicAdd(p + 1, a23.x);        // (r  , c+1)
+        atomicAdd(p + kSW + 1, a23.y);  // (r+1, c+1)
+      } else {
+        flush_cell<float, false>(iwe, Hp, Wp, Hm1, Wm1, r, c, a01.x, a01.y, a23.x, a23.y);
+      }
+    };
+    const int64_t start = (int64_t)it.y & ~(int64_t)(EPT - 1);
+    for (int64_t base = start + (int64_t)threadIdx.x * EPT; base < it.z; base += (int64_t)blockDim.x * EPT) {
+      EventBlock<float, EPT, HAS_W, PACKED> e;
+      e.load_range(sx, sy, sd, sw, base, it.y, it.z);
+      e.finish(flow, W, hw);
+      float cfr = NAN, cfc = 0.f;
+      float2 a01 = zero2, a23 = zero2;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        // x' = x - (dt * f) with two roundings (see splat_block_f32)
+        const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+        const float2 wb = add2(w, bias2);
+        const float fr = floorf(wb.x), fc = floorf(wb.y);
+        const float2 ab = sub2(w, make_float2(fr, fc));
+        const float2 nab = sub2(one2, ab);
+        const float2 lhs = make_float2(nab.x, ab.x);
+        float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
+        float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
+        if (w01.x != w01.x) {
+          splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, HAS_W ? e.wt[j] : 1.f);
+          continue;
+        }
+        if (HAS_W) {
+          const float2 ww = make_float2(e.wt[j], e.wt[j]);
+          w01 = mul2(w01, ww);
+          w23 = mul2(w23, ww);
+        }
+        if (!((fr == cfr) & (fc == cfc))) {
+          if (cfr == cfr) flush(cfr, cfc, a01, a23);
+          cfr = fr; cfc = fc;
+          a01 = zero2; a23 = zero2;
+        }
+        a01 = add2(a01, w01);
+        a23 = add2(a23, w23);
+      }
+      if (cfr == cfr) flush(cfr, cfc, a01, a23);
+    }
+    __syncthreads();
+    // window -> global (coalesced rows; windows of neighbouring tiles / items overlap, hence REDs)
+    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+      const float v = win[i];
+      const int lr = i / kSW, lc = i - lr * kSW;
+      const int r = r_org + lr, c = c_org + lc;
+      if (v != 0.f && (unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, v);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- backward ------------------------------------------------------------------------------------
 // GSRC 0: dL/dIWE read from a plane.  GSRC 1: variance objective, dL/dIWE = cv * (IWE - mean)
 // derived on the fly from the IWE itself (saves writing and re-reading a gradient plane).
@@ -731,6 +912,86 @@ k_win_bwd_pipe(const float* __restrict__ sx, const float* __restrict__ sy, const
   });
 }
 
+template <int GSRC, bool HAS_W, bool PACKED>
+__global__ void __launch_bounds__(256, 3)
+k_tile_bwd(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+           const float* __restrict__ sw, const int4* __restrict__ items, const WindowHeader* __restrict__ hdr,
+           const float* __restrict__ flow, int H, int W, int pad_h, int pad_w, const float* __restrict__ g,
+           const double* __restrict__ acc, int omit, double scale, float* __restrict__ dflow) {
+  constexpr int EPT = 8, G = 4;
+  __shared__ float win[kSH * kSW];
+  const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
+  const int n_items = hdr->n_items;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int4 it = __ldg(items + item);
+    int r_org, c_org;
+    tile_origin(it.x, W, pad_h, pad_w, r_org, c_org);
+    __syncthreads();  // previous item's gathers are done with the window
+    // dL/dIWE window: masked (0 outside the image / the cropped region), variance objective applied on the fly
+    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+      const int lr = i / kSW, lc = i - lr * kSW;
+      win[i] = fetch_g<float, GSRC>(g, P.Hp, P.Wp, r_org + lr, c_org + lc, P.vc);
+    }
+    __syncthreads();
+    const int64_t start = (int64_t)it.y & ~(int64_t)(EPT - 1);
+    for (int64_t base = start + (int64_t)threadIdx.x * EPT; base < it.z; base += (int64_t)blockDim.x * EPT) {
+      EventBlock<float, EPT, HAS_W, PACKED> e;
+      e.load_range(sx, sy, sd, sw, base, it.y, it.z);
+      e.finish(flow, W, P.hw);
+      int ck = -1;
+      float2 s01 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int h = 0; h < EPT; h += G) {
+        float a[G], b[G], g00[G], g01[G], g10[G], g11[G];
+        bool fast[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int j = h + i;
+          const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+          const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
+          const float fr = floorf(wb.x), fc = floorf(wb.y);
+          const float2 ab = sub2(w, make_float2(fr, fc));
+          a[i] = ab.x; b[i] = ab.y;
+          const int lr = (int)fr + pad_h - r_org, lc = (int)fc + pad_w - c_org;
+          fast[i] = (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1) && (ab.x + ab.y == ab.x + ab.y);
+          if (fast[i]) {
+            const float* p = win + lr * kSW + lc;
+            g00[i] = p[0]; g01[i] = p[1]; g10[i] = p[kSW]; g11[i] = p[kSW + 1];
+          } else {
+            // outside the window (large displacement), non-finite or skipped: exact masked gathers from global
+            float dx, dy;
+            bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, pad_h, pad_w, e.x[j] == e.x[j] ? w.x : NAN, w.y, P.vc, dx, dy);
+            g00[i] = dx; g01[i] = dy; g10[i] = 0.f; g11[i] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int j = h + i;
+          float2 dxy;
+          if (fast[i]) {
+            // (dx, dy) = (1-b, 1-a) * (g10-g00, g01-g00) + (b, a) * (g11-g01, g11-g10); the window already holds dL/dIWE
+            const float2 d1 = sub2(make_float2(g10[i], g01[i]), make_float2(g00[i], g00[i]));
+            const float2 d2 = sub2(make_float2(g11[i], g11[i]), make_float2(g01[i], g10[i]));
+            const float2 ba = make_float2(b[i], a[i]);
+            dxy = fma2(ba, d2, mul2(sub2(make_float2(1.f, 1.f), ba), d1));
+          } else {
+            dxy = make_float2(g00[i], g01[i]);
+          }
+          if (HAS_W) dxy = mul2(dxy, make_float2(e.wt[j], e.wt[j]));
+          if (e.x[j] != e.x[j]) continue;  // skipped event
+          if (e.k[j] != ck) {
+            if (ck >= 0) { red_add_nc(dflow + ck, s01.x); red_add_nc(dflow + P.hw + ck, s01.y); }
+            ck = e.k[j];
+            s01 = make_float2(0.f, 0.f);
+          }
+          s01 = fma2(make_float2(-e.d[j], -e.d[j]), dxy, s01);
+        }
+      }
+      if (ck >= 0) { red_add_nc(dflow + ck, s01.x); red_add_nc(dflow + P.hw + ck, s01.y); }
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static int key_bits_for(int64_t hw) {
   int bits = 1;
@@ -769,7 +1030,7 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   unsigned int* k_out = reinterpret_cast<unsigned int*>(wp + ws.off_kout);
   int* i_in = reinterpret_cast<int*>(wp + ws.off_iin);
   void* cub_tmp = wp + ws.off_cub;
-  WindowLayout L = window_layout(n, sizeof(T));
+  WindowLayout L = window_layout(n, sizeof(T), H, W);
   char* b = reinterpret_cast<char*>(window);
   int* perm = reinterpret_cast<int*>(b + L.off_perm);
   int bx = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
@@ -779,8 +1040,12 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   k_win_layout<<<1, 1, 0, st>>>(hdr, allow_packed && sizeof(T) == 4 && H <= 65536 && W <= 65536, status);
   size_t cub_bytes = ws.cub_bytes;
   cudaError_t ce = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k_in, k_out, i_in, perm, (int)n, 0,
-                                                   key_bits_for((int64_t)H * W), st);
+                                                   key_bits_for((int64_t)tiles_x(W) * tiles_y(H) * kTileH * kTileW + 1), st);
   if (ce != cudaSuccess) return cuda_fail(ce, "ebos_window_prepare(sort)");
+  const int n_tiles = tiles_x(W) * tiles_y(H);
+  int* tile_off = reinterpret_cast<int*>(b + L.off_tiles);
+  k_win_tile_offsets<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(k_out, n, n_tiles, tile_off);
+  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, reinterpret_cast<int4*>(b + L.off_items), hdr);
   k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
                                       reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
                                       reinterpret_cast<T*>(b + L.off_d),
@@ -807,7 +1072,7 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   if (n == 0) return EBOS_OK;
   const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
   if (packed && sizeof(T) != 4) { set_error("ebos_window_splat: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
-  WindowLayout L = window_layout(n, sizeof(T));
+  WindowLayout L = window_layout(n, sizeof(T), H, W);
   const char* b = reinterpret_cast<const char*>(window);
   const T* sx = reinterpret_cast<const T*>(b + L.off_x);
   const T* sy = reinterpret_cast<const T*>(b + L.off_y);
@@ -821,12 +1086,30 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   // (experiment knob, default off: red.v4 was measured slower than four scalar REDs in this kernel)
   static const int vec_env = env_int("EBOS_VEC_RED");
   const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(iwe) & 15) == 0);
-  // persistent TMA-staged kernel (fp32) once there are at least ~2 chunks per CTA slot; one-shot otherwise
-  static const int pipe_env = env_int("EBOS_PIPE");   // 0 auto, 1 force on, 2 force off (experiments)
+  // shared-memory tile kernel (fp32): default from 64 Ki events; EBOS_TILE=1 forces it on, =2 off (experiments/tests)
+  static const int tile_env = env_int("EBOS_TILE");
+  if constexpr (sizeof(T) == 4) {
+    if (tile_env != 2 && (tile_env == 1 || n >= 65536)) {
+      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
+      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
+      const unsigned tgrid = (unsigned)std::min<int64_t>(max_items(n, H, W), (int64_t)sm_count() * 8);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
+      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
+      if (has_weight) { if (packed) k_tile_splat<true, true><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi);
+                        else k_tile_splat<true, false><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi); }
+      else { if (packed) k_tile_splat<false, true><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi);
+             else k_tile_splat<false, false><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi); }
+      EBOS_LAUNCH_CHECK("ebos_window_splat(tile)");
+      return EBOS_OK;
+    }
+  }
+  // persistent TMA-staged kernel (fp32): measured slower than the one-shot kernel, kept as an option (EBOS_PIPE=1)
+  static const int pipe_env = env_int("EBOS_PIPE");
   if constexpr (sizeof(T) == 4) {
     const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
     const int slots = sm_count() * 3;
-    if (pipe_env != 2 && (pipe_env == 1 || n_chunks >= 2 * (int64_t)slots)) {
+    if (pipe_env == 1) {
       const unsigned pgrid = (unsigned)std::min<int64_t>(n_chunks, slots);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
@@ -873,7 +1156,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
   if (n == 0) return EBOS_OK;
   const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
   if (packed && sizeof(T) != 4) { set_error("ebos_window_backward: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
-  WindowLayout L = window_layout(n, sizeof(T));
+  WindowLayout L = window_layout(n, sizeof(T), H, W);
   const char* b = reinterpret_cast<const char*>(window);
   const T* sx = reinterpret_cast<const T*>(b + L.off_x);
   const T* sy = reinterpret_cast<const T*>(b + L.off_y);
@@ -892,11 +1175,31 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
   static const int vec_env = env_int("EBOS_VEC_LOAD");
   const int Wp = W + 2 * pad_w;
   const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
+  static const int tile_env = env_int("EBOS_TILE");
+  if constexpr (sizeof(T) == 4) {
+    if (tile_env != 2 && (tile_env == 1 || n >= 65536)) {
+      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
+      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
+      const unsigned tgrid = (unsigned)std::min<int64_t>(max_items(n, H, W), (int64_t)sm_count() * 8);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
+      const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
+      float* fo = reinterpret_cast<float*>(dflow);
+#define EBOS_TBWD(G, WGT, P) k_tile_bwd<G, WGT, P><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+      if (affine) { if (has_weight) { if (packed) EBOS_TBWD(1, true, true); else EBOS_TBWD(1, true, false); }
+                    else { if (packed) EBOS_TBWD(1, false, true); else EBOS_TBWD(1, false, false); } }
+      else { if (has_weight) { if (packed) EBOS_TBWD(0, true, true); else EBOS_TBWD(0, true, false); }
+             else { if (packed) EBOS_TBWD(0, false, true); else EBOS_TBWD(0, false, false); } }
+#undef EBOS_TBWD
+      EBOS_LAUNCH_CHECK("ebos_window_backward(tile)");
+      return EBOS_OK;
+    }
+  }
   static const int pipe_env = env_int("EBOS_PIPE");
   if constexpr (sizeof(T) == 4) {
     const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
     const int slots = sm_count() * 3;
-    if (pipe_env != 2 && (pipe_env == 1 || n_chunks >= 2 * (int64_t)slots)) {
+    if (pipe_env == 1) {
       const unsigned pgrid = (unsigned)std::min<int64_t>(n_chunks, slots);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
@@ -974,7 +1277,9 @@ using namespace ebos;
 
 extern "C" {
 
-size_t ebos_window_bytes(int64_t n, int dtype) { return n < 0 ? 0 : window_layout(n, dtype_size(dtype)).total; }
+size_t ebos_window_bytes(int64_t n, int H, int W, int dtype) {
+  return (n < 0 || H <= 0 || W <= 0) ? 0 : window_layout(n, dtype_size(dtype), H, W).total;
+}
 
 size_t ebos_window_workspace_bytes(int64_t n, int H, int W) {
   (void)H; (void)W;
@@ -999,13 +1304,14 @@ int ebos_window_prepare(const void* events, int64_t n, int H, int W, int directi
                                     workspace_bytes, status, as_stream(stream));
 }
 
-int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out, double* tinfo_out, void* stream) {
+int ebos_window_info(const void* window, int64_t n, int H, int W, int dtype, int32_t* perm_out, double* tinfo_out,
+                     void* stream) {
   EBOS_REQUIRE(window && n >= 0, "ebos_window_info: bad argument");
   EBOS_CHECK_DTYPE(dtype, "ebos_window_info");
   cudaStream_t st = as_stream(stream);
   const char* b = reinterpret_cast<const char*>(window);
   if (perm_out && n > 0) {
-    cudaError_t e = cudaMemcpyAsync(perm_out, b + window_layout(n, dtype_size(dtype)).off_perm, (size_t)n * 4,
+    cudaError_t e = cudaMemcpyAsync(perm_out, b + window_layout(n, dtype_size(dtype), H, W).off_perm, (size_t)n * 4,
                                     cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_window_info(perm)");
   }

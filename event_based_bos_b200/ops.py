@@ -256,7 +256,7 @@ class PreparedWindow:
         kind, frac = direction_code(direction)
         lib = _capi.load()
         self.code = dtype_code(ev)
-        self.buffer = torch.empty(lib.ebos_window_bytes(self.n, self.code), dtype=torch.uint8, device=ev.device)
+        self.buffer = torch.empty(lib.ebos_window_bytes(self.n, self.H, self.W, self.code), dtype=torch.uint8, device=ev.device)
         ws_bytes = lib.ebos_window_workspace_bytes(self.n, self.H, self.W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ev.device)
         status = torch.zeros(1, dtype=torch.int32, device=ev.device)
@@ -278,14 +278,14 @@ class PreparedWindow:
     def permutation(self) -> torch.Tensor:
         """int32 [n]: sorted position -> index of the event in the array the window was built from."""
         out = torch.empty(self.n, dtype=torch.int32, device=self.device)
-        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, self.code, ptr(out), 0, current_stream()),
+        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, self.H, self.W, self.code, ptr(out), 0, current_stream()),
               "ebos_window_info")
         return out
 
     def time_info(self) -> torch.Tensor:
         """float64 [4]: t_ref, period, t_min, t_max as computed on the device (exact values of `dtype`)."""
         out = torch.empty(4, dtype=torch.float64, device=self.device)
-        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, self.code, 0, ptr(out), current_stream()),
+        check(_capi.load().ebos_window_info(ptr(self.buffer), self.n, self.H, self.W, self.code, 0, ptr(out), current_stream()),
               "ebos_window_info")
         return out
 

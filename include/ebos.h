@@ -131,12 +131,13 @@ EBOS_API int ebos_iwe_splat_bwd(const void* events, int64_t n, int batch, int Hp
  * ---------------------------------------------------------------------------------------- */
 
 /* Bytes of the caller-owned window buffer / of the temporary workspace used by prepare. */
-EBOS_API size_t ebos_window_bytes(int64_t n, int dtype);
+EBOS_API size_t ebos_window_bytes(int64_t n, int H, int W, int dtype);
 EBOS_API size_t ebos_window_workspace_bytes(int64_t n, int H, int W);
 
 /* Build a window from raw events [n,4]: computes t_ref/period on the device
- * (src/warp.py:230-288), dt_i, k_i, and stores (x, y, dt[, weight]) sorted by k (stable, so the
- * sensor's time order is kept inside a pixel).  weight: NULL or [n].  status as above.
+ * (src/warp.py:230-288), dt_i, k_i, and stores (x, y, dt[, weight]) sorted by (32x32 tile of the origin
+ * pixel, pixel inside the tile) -- stable, so the sensor's time order is kept inside a pixel -- plus the
+ * per-tile offsets and work items used by the shared-memory tile kernels.  weight: NULL or [n].  status as above.
  * tminmax: NULL, or [2] (device, dtype) = (min t, max t) to use instead of this call's own
  * reduction -- for a window whose events are sharded over several GPUs (global min/max).
  * allow_packed: when non-zero (fp32 only) and every event is valid with integer coordinates below
@@ -150,7 +151,8 @@ EBOS_API int ebos_window_prepare(const void* events, int64_t n, int H, int W, in
 
 /* Copy the window's event permutation (int32[n]: sorted position -> original event index) and its
  * time statistics (double[4]: t_ref, period, t_min, t_max) out of the opaque buffer (either may be NULL). */
-EBOS_API int ebos_window_info(const void* window, int64_t n, int dtype, int32_t* perm_out, double* tinfo_out, void* stream);
+EBOS_API int ebos_window_info(const void* window, int64_t n, int H, int W, int dtype, int32_t* perm_out,
+                     double* tinfo_out, void* stream);
 
 /* Fused warp + bilinear vote of a prepared window into iwe [Hp,Wp] (fully overwritten).
  * `n`, `flags` (EBOS_WIN_*) and `dtype` must describe the window as it was prepared. */

@@ -1,6 +1,6 @@
-"""Helper for test_gpu_fused.py::test_pipelined_kernels_match_oracle: run with EBOS_PIPE=1 (persistent
-TMA-staged kernels forced on) or EBOS_PIPE=2 (one-shot kernels) in a fresh process, print max relative errors
-of the fused path against the CPU oracle as JSON."""
+"""Helper for test_gpu_fused.py::test_all_streaming_kernel_variants_match_oracle: run in a fresh process with
+EBOS_TILE / EBOS_PIPE set to force one kernel family, print max relative errors of the fused path against the
+CPU oracle as JSON."""
 import json
 import os
 import sys
@@ -20,13 +20,13 @@ def rel(a, b):
 
 out = {}
 H, W = 48, 80
-for n in (1, 7, 2047, 2048, 2049, 70001):        # chunk = 2048 events: exercise tails and multi-chunk CTAs
+for n in (1, 7, 2047, 2048, 2049, 70001):        # tails, multi-chunk CTAs, tiles with several work items (8192 events)
     for packed in (True, False):
         for weighted in (False, True):
             ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=n))
             if not packed:
                 ev[:, 0] = torch.clamp(ev[:, 0] + 0.25, max=H - 0.5)
-            flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=n, max_val=6.0))
+            flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=n, max_val=6.0))   # > halo of the tile kernels
             wts = torch.from_numpy(np.random.default_rng(n).uniform(0.5, 1.5, n).astype(np.float32)) if weighted else None
             f = flow.clone().requires_grad_()
             if n > 1:

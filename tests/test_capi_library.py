@@ -42,9 +42,9 @@ def test_version_and_error_string():
     # argument validation happens before any CUDA call: usable without a device
     assert lib.ebos_time_stats(None, -1, 1, 0, None, None) == -1
     assert "bad argument" in _capi.last_error()
-    assert lib.ebos_window_bytes(1000, 0) >= 5 * 4000 + 256
-    assert lib.ebos_window_bytes(1000, 1) >= 4 * 8000 + 4000 + 256
-    assert lib.ebos_window_bytes(1000, 0) % 256 == 0
+    assert lib.ebos_window_bytes(1000, 64, 96, 0) >= 5 * 4000 + 256
+    assert lib.ebos_window_bytes(1000, 64, 96, 1) >= 4 * 8000 + 4000 + 256
+    assert lib.ebos_window_bytes(1000, 64, 96, 0) % 256 == 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -32,9 +32,11 @@ def test_prepared_window_metadata(ops):
         win = ops.PreparedWindow(tev.cuda(), (H, W), direction, True)
         perm = win.permutation().cpu().numpy()
         assert np.array_equal(np.sort(perm), np.arange(n))
-        k = (ev[:, 0].astype(np.int64) * W + ev[:, 1].astype(np.int64))[perm]
-        assert (np.diff(k) >= 0).all()  # sorted by origin pixel
-        same = np.diff(k) == 0
+        r, c = ev[:, 0].astype(np.int64)[perm], ev[:, 1].astype(np.int64)[perm]
+        tiles_x = (W + 31) // 32
+        key = ((r // 32) * tiles_x + c // 32) * 1024 + (r % 32) * 32 + (c % 32)
+        assert (np.diff(key) >= 0).all()  # sorted by (32x32 tile of the origin pixel, pixel inside the tile)
+        same = np.diff(key) == 0
         assert (np.diff(perm)[same] > 0).all()  # stable: input (time) order kept inside a pixel
         dt, t_ref, period = spec.event_dt(tev[:, 2], direction, True)
         info = win.time_info().cpu().numpy()
@@ -81,16 +83,20 @@ def test_packed_and_generic_layouts_agree(ops):
         assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_pipelined_kernels_match_oracle(mode):
-    """EBOS_PIPE=1 forces the persistent TMA-staged streaming kernels (normally used from ~1.8 M events),
-    EBOS_PIPE=2 the one-shot kernels; both must match the oracle on small windows incl. ragged tails."""
+@pytest.mark.parametrize("mode", ["tile", "pipe", "oneshot"])
+def test_all_streaming_kernel_variants_match_oracle(mode):
+    """The fused path has three kernel families for the event stream: shared-memory tile kernels (default from
+    64 Ki events), one-shot kernels (small windows, fp64) and the optional persistent TMA-staged kernels.  Each is
+    forced on in a fresh process and must match the oracle on small windows incl. ragged tails, multi-item
+    tiles, padding, weights, packed and generic layouts."""
     import json
     import os
     import subprocess
     import sys
 
-    env = dict(os.environ, EBOS_PIPE=mode)
+    env = dict(os.environ)
+    env.update({"tile": {"EBOS_TILE": "1"}, "pipe": {"EBOS_TILE": "2", "EBOS_PIPE": "1"},
+                "oneshot": {"EBOS_TILE": "2", "EBOS_PIPE": "2"}}[mode])
     script = os.path.join(os.path.dirname(__file__), "pipe_check.py")
     res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
