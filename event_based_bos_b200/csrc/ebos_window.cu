@@ -547,6 +547,71 @@ k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restr
   splat_block<T, HAS_W, EPT, VEC, PACKED>(e, iwe, H + 2 * pad_h, W + 2 * pad_w, pad_h, pad_w);
 }
 
+// ---- grouped one-shot kernels (fp32 default) ------------------------------------------------------------
+// Lean instruction stream AND high occupancy: a thread walks over NG groups of 4 consecutive events; only one
+// group lives in registers at a time (<= 40 registers -> 6 CTAs of 256 threads per SM), while the run state
+// (current cell + tap sums, or current origin pixel + gradient sums) is carried across the groups, so the
+// register-level combining sees 4*NG consecutive events.
+struct SplatRun { float cfr, cfc; float2 a01, a23; };
+
+template <bool HAS_W, bool PACKED>
+__device__ __forceinline__ void splat_group4(const EventBlock<float, 4, HAS_W, PACKED>& e, SplatRun& run,
+                                             float* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w) {
+  const int Hm1 = Hp - 1, Wm1 = Wp - 1;
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+    const float2 wb = add2(w, bias2);
+    const float fr = floorf(wb.x), fc = floorf(wb.y);
+    const float2 ab = sub2(w, make_float2(fr, fc));
+    const float2 nab = sub2(one2, ab);
+    const float2 lhs = make_float2(nab.x, ab.x);
+    float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
+    float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
+    if (w01.x != w01.x) {
+      splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, HAS_W ? e.wt[j] : 1.f);
+      continue;
+    }
+    if (HAS_W) {
+      const float2 ww = make_float2(e.wt[j], e.wt[j]);
+      w01 = mul2(w01, ww);
+      w23 = mul2(w23, ww);
+    }
+    if (!((fr == run.cfr) & (fc == run.cfc))) {
+      if (run.cfr == run.cfr)
+        flush_cell<float, false>(iwe, Hp, Wp, Hm1, Wm1, (int)run.cfr + pad_h, (int)run.cfc + pad_w, run.a01.x, run.a01.y,
+                                 run.a23.x, run.a23.y);
+      run.cfr = fr; run.cfc = fc;
+      run.a01 = zero2; run.a23 = zero2;
+    }
+    run.a01 = add2(run.a01, w01);
+    run.a23 = add2(run.a23, w23);
+  }
+}
+
+template <bool HAS_W, bool PACKED, int NG>
+__global__ void __launch_bounds__(256, 6)
+k_win_splat_g(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+              const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h,
+              int pad_w, float* __restrict__ iwe) {
+  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
+  if (base >= n) return;
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
+  SplatRun run{NAN, 0.f, make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 1
+  for (int g = 0; g < NG; ++g) {
+    const int64_t b = base + 4 * g;
+    if (b >= n) break;
+    EventBlock<float, 4, HAS_W, PACKED> e;
+    e.load(sx, sy, sd, sw, b, n, flow, W, hw);
+    splat_group4<HAS_W, PACKED>(e, run, iwe, Hp, Wp, pad_h, pad_w);
+  }
+  if (run.cfr == run.cfr)
+    flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, (int)run.cfr + pad_h, (int)run.cfc + pad_w, run.a01.x, run.a01.y,
+                             run.a23.x, run.a23.y);
+}
+
 // ---- persistent, TMA-staged streaming (fp32) ---------------------------------------------------------
 // The one-shot kernels were latency-bound: a thread's only loads from HBM sit at its very beginning and
 // nothing else in the thread can run until they land (ncu r01b: 37-46 % of stall samples on the long
@@ -912,6 +977,75 @@ k_win_bwd_pipe(const float* __restrict__ sx, const float* __restrict__ sy, const
   });
 }
 
+struct BwdRun { int ck; float2 s01; };
+
+template <int GSRC, bool HAS_W, bool PACKED>
+__device__ __forceinline__ void bwd_group4(const EventBlock<float, 4, HAS_W, PACKED>& e, BwdRun& run,
+                                           const BwdParams<float>& P, const float* __restrict__ g, float* __restrict__ dflow) {
+  float a[4], b[4], g00[4], g01[4], g10[4], g11[4];
+  bool fast[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 w = make_float2(__fsub_rn(e.x[i], __fmul_rn(e.d[i], e.f0[i])), __fsub_rn(e.y[i], __fmul_rn(e.d[i], e.f1[i])));
+    const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
+    const float fr = floorf(wb.x), fc = floorf(wb.y);
+    const float2 ab = sub2(w, make_float2(fr, fc));
+    a[i] = ab.x; b[i] = ab.y;
+    const int r = (int)fr + P.pad_h, c = (int)fc + P.pad_w;
+    fast[i] = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span && (ab.x + ab.y == ab.x + ab.y);
+    if (fast[i]) {
+      const float* p = g + (r * P.Wp + c);
+      g00[i] = __ldg(p); g01[i] = __ldg(p + 1); g10[i] = __ldg(p + P.Wp); g11[i] = __ldg(p + P.Wp + 1);
+    } else {
+      float dx, dy;
+      bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, P.pad_h, P.pad_w, e.x[i] == e.x[i] ? w.x : NAN, w.y, P.vc, dx, dy);
+      g00[i] = dx; g01[i] = dy; g10[i] = 0.f; g11[i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 dxy;
+    if (fast[i]) {
+      const float2 d1 = sub2(make_float2(g10[i], g01[i]), make_float2(g00[i], g00[i]));
+      const float2 d2 = sub2(make_float2(g11[i], g11[i]), make_float2(g01[i], g10[i]));
+      const float2 ba = make_float2(b[i], a[i]);
+      dxy = fma2(ba, d2, mul2(sub2(make_float2(1.f, 1.f), ba), d1));
+      if (GSRC == 1) dxy = mul2(dxy, make_float2(P.vc.cv, P.vc.cv));  // differences: the mean cancels
+    } else {
+      dxy = make_float2(g00[i], g01[i]);
+    }
+    if (HAS_W) dxy = mul2(dxy, make_float2(e.wt[i], e.wt[i]));
+    if (e.x[i] != e.x[i]) continue;  // skipped event
+    if (e.k[i] != run.ck) {
+      if (run.ck >= 0) { red_add_nc(dflow + run.ck, run.s01.x); red_add_nc(dflow + P.hw + run.ck, run.s01.y); }
+      run.ck = e.k[i];
+      run.s01 = make_float2(0.f, 0.f);
+    }
+    run.s01 = fma2(make_float2(-e.d[i], -e.d[i]), dxy, run.s01);
+  }
+}
+
+template <int GSRC, bool HAS_W, bool PACKED, int NG>
+__global__ void __launch_bounds__(256, 5)
+k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+            const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h, int pad_w,
+            const float* __restrict__ g, const double* __restrict__ acc, int omit, double scale,
+            float* __restrict__ dflow) {
+  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
+  if (base >= n) return;
+  const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
+  BwdRun run{-1, make_float2(0.f, 0.f)};
+#pragma unroll 1
+  for (int gi = 0; gi < NG; ++gi) {
+    const int64_t b = base + 4 * gi;
+    if (b >= n) break;
+    EventBlock<float, 4, HAS_W, PACKED> e;
+    e.load(sx, sy, sd, sw, b, n, flow, W, P.hw);
+    bwd_group4<GSRC, HAS_W, PACKED>(e, run, P, g, dflow);
+  }
+  if (run.ck >= 0) { red_add_nc(dflow + run.ck, run.s01.x); red_add_nc(dflow + P.hw + run.ck, run.s01.y); }
+}
+
 template <int GSRC, bool HAS_W, bool PACKED>
 __global__ void __launch_bounds__(256, 3)
 k_tile_bwd(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
@@ -1086,10 +1220,12 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   // (experiment knob, default off: red.v4 was measured slower than four scalar REDs in this kernel)
   static const int vec_env = env_int("EBOS_VEC_RED");
   const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(iwe) & 15) == 0);
-  // shared-memory tile kernel (fp32): default from 64 Ki events; EBOS_TILE=1 forces it on, =2 off (experiments/tests)
+  // shared-memory tile kernel (fp32): opt-in with EBOS_TILE=1.  Measured on B200 at 16 Mi events it is SLOWER than
+  // the one-shot kernel (130 vs 84 us): adjacent lanes flush the same cell, and shared-memory float atomics are a
+  // CAS loop that serialises on same-address conflicts, whereas the L2 RED unit merges them.
   static const int tile_env = env_int("EBOS_TILE");
   if constexpr (sizeof(T) == 4) {
-    if (tile_env != 2 && (tile_env == 1 || n >= 65536)) {
+    if (tile_env == 1) {
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       const unsigned tgrid = (unsigned)std::min<int64_t>(max_items(n, H, W), (int64_t)sm_count() * 8);
@@ -1127,6 +1263,24 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
              else { if (vec) EBOS_SPLAT_P(false, true, false); else EBOS_SPLAT_P(false, false, false); } }
 #undef EBOS_SPLAT_P
       EBOS_LAUNCH_CHECK("ebos_window_splat(pipe)");
+      return EBOS_OK;
+    }
+  }
+  static const int ng_env = env_int("EBOS_GROUPS");   // 0 default (4 groups of 4 events), 2/4/8 groups, -1 legacy kernels
+  if constexpr (sizeof(T) == 4) {
+    if (ng_env >= 0) {
+      const int ng = (ng_env == 2 || ng_env == 8) ? ng_env : 4;
+      const unsigned ggrid = (unsigned)((((n + 4 * ng - 1) / (4 * ng)) + 255) / 256);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
+      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
+#define EBOS_SG(WGT, P, NGV) k_win_splat_g<WGT, P, NGV><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fi)
+#define EBOS_SG_N(WGT, P) do { if (ng == 2) EBOS_SG(WGT, P, 2); else if (ng == 8) EBOS_SG(WGT, P, 8); else EBOS_SG(WGT, P, 4); } while (0)
+      if (has_weight) { if (packed) EBOS_SG_N(true, true); else EBOS_SG_N(true, false); }
+      else { if (packed) EBOS_SG_N(false, true); else EBOS_SG_N(false, false); }
+#undef EBOS_SG_N
+#undef EBOS_SG
+      EBOS_LAUNCH_CHECK("ebos_window_splat(grouped)");
       return EBOS_OK;
     }
   }
@@ -1175,9 +1329,11 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
   static const int vec_env = env_int("EBOS_VEC_LOAD");
   const int Wp = W + 2 * pad_w;
   const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
+  // shared-memory tile kernel (fp32): opt-in with EBOS_TILE=1 (measured 101 vs 90 us at 16 Mi events: coarse work
+  // items and 80 registers cost more than the cheaper LDS gathers save)
   static const int tile_env = env_int("EBOS_TILE");
   if constexpr (sizeof(T) == 4) {
-    if (tile_env != 2 && (tile_env == 1 || n >= 65536)) {
+    if (tile_env == 1) {
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       const unsigned tgrid = (unsigned)std::min<int64_t>(max_items(n, H, W), (int64_t)sm_count() * 8);
@@ -1223,6 +1379,27 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
 #undef EBOS_BWD_PG
 #undef EBOS_BWD_P
       EBOS_LAUNCH_CHECK("ebos_window_backward(pipe)");
+      return EBOS_OK;
+    }
+  }
+  static const int ng_env = env_int("EBOS_GROUPS");
+  if constexpr (sizeof(T) == 4) {
+    if (ng_env >= 0) {
+      const int ng = (ng_env == 2 || ng_env == 8) ? ng_env : 4;
+      const unsigned ggrid = (unsigned)((((n + 4 * ng - 1) / (4 * ng)) + 255) / 256);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
+      const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
+      float* fo = reinterpret_cast<float*>(dflow);
+#define EBOS_BG(G, WGT, P, NGV) k_win_bwd_g<G, WGT, P, NGV><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+#define EBOS_BG_N(G, WGT, P) do { if (ng == 2) EBOS_BG(G, WGT, P, 2); else if (ng == 8) EBOS_BG(G, WGT, P, 8); else EBOS_BG(G, WGT, P, 4); } while (0)
+#define EBOS_BG_W(G) do { if (has_weight) { if (packed) EBOS_BG_N(G, true, true); else EBOS_BG_N(G, true, false); } \
+                          else { if (packed) EBOS_BG_N(G, false, true); else EBOS_BG_N(G, false, false); } } while (0)
+      if (affine) EBOS_BG_W(1); else EBOS_BG_W(0);
+#undef EBOS_BG_W
+#undef EBOS_BG_N
+#undef EBOS_BG
+      EBOS_LAUNCH_CHECK("ebos_window_backward(grouped)");
       return EBOS_OK;
     }
   }

@@ -83,20 +83,20 @@ def test_packed_and_generic_layouts_agree(ops):
         assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", ["tile", "pipe", "oneshot"])
+@pytest.mark.parametrize("mode", ["grouped", "tile", "pipe", "oneshot"])
 def test_all_streaming_kernel_variants_match_oracle(mode):
-    """The fused path has three kernel families for the event stream: shared-memory tile kernels (default from
-    64 Ki events), one-shot kernels (small windows, fp64) and the optional persistent TMA-staged kernels.  Each is
-    forced on in a fresh process and must match the oracle on small windows incl. ragged tails, multi-item
-    tiles, padding, weights, packed and generic layouts."""
+    """The fused fp32 path has four kernel families for the event stream: the default grouped one-shot kernels,
+    the legacy one-shot kernels (also the fp64 path), and two opt-in experiments (shared-memory tile kernels,
+    persistent TMA-staged kernels).  Each is forced on in a fresh process and must match the oracle on small
+    windows incl. ragged tails, multi-item tiles, padding, weights, packed and generic layouts."""
     import json
     import os
     import subprocess
     import sys
 
     env = dict(os.environ)
-    env.update({"tile": {"EBOS_TILE": "1"}, "pipe": {"EBOS_TILE": "2", "EBOS_PIPE": "1"},
-                "oneshot": {"EBOS_TILE": "2", "EBOS_PIPE": "2"}}[mode])
+    env.update({"grouped": {}, "tile": {"EBOS_TILE": "1"}, "pipe": {"EBOS_PIPE": "1"},
+                "oneshot": {"EBOS_GROUPS": "-1"}}[mode])
     script = os.path.join(os.path.dirname(__file__), "pipe_check.py")
     res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
