@@ -251,18 +251,16 @@ __device__ __forceinline__ float sgn_diff(float a, float b) {  // sign(a - b) wi
 template <typename T, bool HAS_WTS>
 __global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, const T* __restrict__ weights, int H, int W,
                                                  T coef, double* __restrict__ acc, T* __restrict__ dflow) {
-  // coef = tv_scale / (2*H*W)
+  // coef = tv_scale / (2*H*W).  Grid (ceil(quads/64), ceil(H/4), 2), block = 64 quads x 4 rows: no div/mod in the
+  // index math (the first lean version spent most of its 111 instructions per element on 64-bit div/mod).
   __shared__ double sm[32];
   const int quads = (W + 3) / 4;
-  const int64_t total = (int64_t)2 * H * quads;
   const bool lean_ok = sizeof(T) == 4 && !HAS_WTS && (W % 4 == 0) && ((reinterpret_cast<size_t>(flow) & 15) == 0) &&
                        ((reinterpret_cast<size_t>(dflow) & 15) == 0);
   double part = 0.0;
   float fpart = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % quads);
-    const int64_t rest = i / quads;
-    const int r = (int)(rest % H), ch = (int)(rest / H);
+  const int q = blockIdx.x * 64 + (threadIdx.x & 63), r = blockIdx.y * 4 + (threadIdx.x >> 6), ch = blockIdx.z;
+  for (int once = 0; once < 1 && q < quads && r < H; ++once) {
     const int c0 = q * 4;
     const T* f = flow + (int64_t)ch * H * W;
     T* out = dflow + (int64_t)ch * H * W;
@@ -378,8 +376,7 @@ int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, do
     return EBOS_ERR_BAD_ARG;
   }
   const T coef = (T)(tv_scale / (2.0 * (double)H * (double)W));
-  const int64_t quads = (int64_t)2 * H * ((W + 3) / 4);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((quads + 255) / 256, (int64_t)sm_count() * 8));
+  const dim3 grid(((W + 3) / 4 + 63) / 64, (H + 3) / 4, 2);
   if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
   EBOS_LAUNCH_CHECK("ebos_flow_tv");

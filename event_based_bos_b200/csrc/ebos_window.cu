@@ -977,42 +977,41 @@ k_win_bwd_pipe(const float* __restrict__ sx, const float* __restrict__ sy, const
   });
 }
 
-struct BwdRun { int ck; float2 s01; };
+// Run state of the backward carried across groups: current origin pixel + gradient sums, and the last
+// gathered cell with its four dL/dIWE values.  Consecutive events of a pixel mostly fall into the same
+// IWE cell, so the four gathers are only issued when the cell changes (the kernel is L1-bound on them:
+// ncu r01c l1tex 78 %).
+struct BwdRun { int ck; float2 s01; int pr, pc; float g00, g01, g10, g11; };
 
 template <int GSRC, bool HAS_W, bool PACKED>
 __device__ __forceinline__ void bwd_group4(const EventBlock<float, 4, HAS_W, PACKED>& e, BwdRun& run,
                                            const BwdParams<float>& P, const float* __restrict__ g, float* __restrict__ dflow) {
-  float a[4], b[4], g00[4], g01[4], g10[4], g11[4];
-  bool fast[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 w = make_float2(__fsub_rn(e.x[i], __fmul_rn(e.d[i], e.f0[i])), __fsub_rn(e.y[i], __fmul_rn(e.d[i], e.f1[i])));
     const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
     const float fr = floorf(wb.x), fc = floorf(wb.y);
     const float2 ab = sub2(w, make_float2(fr, fc));
-    a[i] = ab.x; b[i] = ab.y;
     const int r = (int)fr + P.pad_h, c = (int)fc + P.pad_w;
-    fast[i] = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span && (ab.x + ab.y == ab.x + ab.y);
-    if (fast[i]) {
-      const float* p = g + (r * P.Wp + c);
-      g00[i] = __ldg(p); g01[i] = __ldg(p + 1); g10[i] = __ldg(p + P.Wp); g11[i] = __ldg(p + P.Wp + 1);
-    } else {
-      float dx, dy;
-      bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, P.pad_h, P.pad_w, e.x[i] == e.x[i] ? w.x : NAN, w.y, P.vc, dx, dy);
-      g00[i] = dx; g01[i] = dy; g10[i] = 0.f; g11[i] = 0.f;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
+    const bool fast = (unsigned)(r - P.lo) < P.r_span && (unsigned)(c - P.lo) < P.c_span && (ab.x + ab.y == ab.x + ab.y);
     float2 dxy;
-    if (fast[i]) {
-      const float2 d1 = sub2(make_float2(g10[i], g01[i]), make_float2(g00[i], g00[i]));
-      const float2 d2 = sub2(make_float2(g11[i], g11[i]), make_float2(g01[i], g10[i]));
-      const float2 ba = make_float2(b[i], a[i]);
+    if (fast) {
+      if (r != run.pr || c != run.pc) {
+        const float* p = g + (r * P.Wp + c);
+        run.g00 = __ldg(p); run.g01 = __ldg(p + 1); run.g10 = __ldg(p + P.Wp); run.g11 = __ldg(p + P.Wp + 1);
+        run.pr = r; run.pc = c;
+      }
+      // (dx, dy) = (1-b, 1-a) * (g10-g00, g01-g00) + (b, a) * (g11-g01, g11-g10)
+      const float2 d1 = sub2(make_float2(run.g10, run.g01), make_float2(run.g00, run.g00));
+      const float2 d2 = sub2(make_float2(run.g11, run.g11), make_float2(run.g01, run.g10));
+      const float2 ba = make_float2(ab.y, ab.x);
       dxy = fma2(ba, d2, mul2(sub2(make_float2(1.f, 1.f), ba), d1));
       if (GSRC == 1) dxy = mul2(dxy, make_float2(P.vc.cv, P.vc.cv));  // differences: the mean cancels
     } else {
-      dxy = make_float2(g00[i], g01[i]);
+      // rare: border cell, out-of-range or skipped event -- exact masked gathers
+      float dx, dy;
+      bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, P.pad_h, P.pad_w, e.x[i] == e.x[i] ? w.x : NAN, w.y, P.vc, dx, dy);
+      dxy = make_float2(dx, dy);
     }
     if (HAS_W) dxy = mul2(dxy, make_float2(e.wt[i], e.wt[i]));
     if (e.x[i] != e.x[i]) continue;  // skipped event
@@ -1034,7 +1033,7 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
   if (base >= n) return;
   const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
-  BwdRun run{-1, make_float2(0.f, 0.f)};
+  BwdRun run{-1, make_float2(0.f, 0.f), INT_MIN, INT_MIN, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
   for (int gi = 0; gi < NG; ++gi) {
     const int64_t b = base + 4 * gi;

@@ -1,12 +1,12 @@
 #!/bin/bash
 # Profiling pass for one round (run under gpurun, one GPU):  bash profiles/run_profile.sh <tag>
 # 1. launch list with per-launch device time (cold-cache, serialised: compare SHARES)
-# 2. one full ncu capture of each event-streaming kernel
+# 2. one full ncu capture of each kernel of the fused evaluation
 TAG=${1:-r01}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches.log 2>&1
-for K in k_win_splat k_win_bwd; do
+for K in k_win_splat k_win_bwd k_flow_tv k_gradmag; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o gpurun_out/${TAG}_${K} -f $BENCH > gpurun_out/${TAG}_${K}.log 2>&1
 done
-ls -la gpurun_out | tail -8
+ls -la gpurun_out | tail -12
