@@ -552,13 +552,42 @@ k_win_splat(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restr
 // group lives in registers at a time (<= 40 registers -> 6 CTAs of 256 threads per SM), while the run state
 // (current cell + tap sums, or current origin pixel + gradient sums) is carried across the groups, so the
 // register-level combining sees 4*NG consecutive events.
-struct SplatRun { float cfr, cfc; float2 a01, a23; };
+struct SplatRun { float cfr, cfc; float2 a01, a23; };   // a01 = taps (r,c),(r+1,c);  a23 = taps (r,c+1),(r+1,c+1)
+
+// Cell change of a run.  The events of a pixel march along a line, so the new cell is almost always
+// EDGE-ADJACENT to the old one and shares two of its four taps: those two partial sums are carried over into
+// the new cell's accumulators and only the two taps that leave the 2x2 window are reduced into the image
+// ("sliding window": ~2 REDs per cell change instead of 4; the kernel is bound by RED lane-ops).
+__device__ __forceinline__ void splat_advance(SplatRun& run, float fr, float fc, float* __restrict__ iwe, int Hp, int Wp,
+                                              int pad_h, int pad_w) {
+  const float dr = fr - run.cfr, dc = fc - run.cfc;   // NaN when there is no open run
+  const bool right = (dr == 0.f) & (dc == 1.f), left = (dr == 0.f) & (dc == -1.f);
+  const bool down = (dr == 1.f) & (dc == 0.f), up = (dr == -1.f) & (dc == 0.f);
+  if (run.cfr == run.cfr) {
+    const int r = (int)run.cfr + pad_h, c = (int)run.cfc + pad_w;
+    const float a0 = run.a01.x, a1 = run.a01.y, a2 = run.a23.x, a3 = run.a23.y;
+    if ((unsigned)r < (unsigned)(Hp - 1) && (unsigned)c < (unsigned)(Wp - 1)) {
+      float* p = iwe + (r * Wp + c);
+      if (!(left | up)) red_add_nc(p, a0);             // (r  , c  ) leaves unless the window moves left or up
+      if (!(left | down)) red_add_nc(p + Wp, a1);      // (r+1, c  )
+      if (!(right | up)) red_add_nc(p + 1, a2);        // (r  , c+1)
+      if (!(right | down)) red_add_nc(p + Wp + 1, a3); // (r+1, c+1)
+      // carried taps (exact: the same partial sums continue in the new cell's registers)
+      run.a01 = right ? make_float2(a2, a3) : (down ? make_float2(a1, 0.f) : (up ? make_float2(0.f, a0) : make_float2(0.f, 0.f)));
+      run.a23 = left ? make_float2(a0, a1) : (down ? make_float2(a3, 0.f) : (up ? make_float2(0.f, a2) : make_float2(0.f, 0.f)));
+    } else {
+      flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, r, c, a0, a1, a2, a3);   // border / outside: masked taps
+      run.a01 = make_float2(0.f, 0.f);
+      run.a23 = make_float2(0.f, 0.f);
+    }
+  }
+  run.cfr = fr; run.cfc = fc;
+}
 
 template <bool HAS_W, bool PACKED>
 __device__ __forceinline__ void splat_group4(const EventBlock<float, 4, HAS_W, PACKED>& e, SplatRun& run,
                                              float* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w) {
-  const int Hm1 = Hp - 1, Wm1 = Wp - 1;
-  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
@@ -578,13 +607,7 @@ __device__ __forceinline__ void splat_group4(const EventBlock<float, 4, HAS_W, P
       w01 = mul2(w01, ww);
       w23 = mul2(w23, ww);
     }
-    if (!((fr == run.cfr) & (fc == run.cfc))) {
-      if (run.cfr == run.cfr)
-        flush_cell<float, false>(iwe, Hp, Wp, Hm1, Wm1, (int)run.cfr + pad_h, (int)run.cfc + pad_w, run.a01.x, run.a01.y,
-                                 run.a23.x, run.a23.y);
-      run.cfr = fr; run.cfc = fc;
-      run.a01 = zero2; run.a23 = zero2;
-    }
+    if (!((fr == run.cfr) & (fc == run.cfc))) splat_advance(run, fr, fc, iwe, Hp, Wp, pad_h, pad_w);
     run.a01 = add2(run.a01, w01);
     run.a23 = add2(run.a23, w23);
   }
