@@ -36,6 +36,15 @@ COST = "gradient_magnitude"
 TV_WEIGHT = 0.5
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -314,7 +323,8 @@ def run_fused(args, rank, world, local):
         "step_roofline": {"algorithmic_bytes": alg_bytes_step, "achieved_gbs": alg_bytes_step / (ms * 1e-3) / 1e9,
                           "frac": alg_bytes_step / (ms * 1e-3) / 1e9 / peak},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "frac": achieved / peak, "traffic": measured_traffic(dom) if n == (1 << 24) and window.packed else None,
+                     "peak_source": peak_kind, "algorithmic_bytes": dom_bytes,
                      "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()}},
         "gpu_launches": 5 * args.steps,
     }
