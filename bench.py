@@ -276,9 +276,22 @@ def run_fused(args, rank, world, local):
         def tv_only():
             lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws.acc), p(ws.dflow), cur())
 
+        adam_m, adam_v = torch.zeros_like(flow), torch.zeros_like(flow)
+        adam_p = flow.clone()
+
+        def tv_noloss():
+            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, 0, p(ws.dflow), cur())
+
+        def adam_only():
+            lib.ebos_adam_step(p(adam_p), p(ws.dflow), p(adam_m), p(adam_v), adam_p.numel(), 0.05, 0.9, 0.999, 1e-8, 3, 0, cur())
+
+        def var_only():
+            lib.ebos_iwe_cost(_capi.COST_VARIANCE, p(ws.iwe), H, W, 0, 1.0, 0, p(ws.acc), 0, cur())
+
         k_ms = {name: graph_time_ms(fn, args.steps) for name, fn in
                 (("window_splat(+memset)", splat_only), ("window_backward", bwd_only), ("iwe_cost_gradmag", cost_only),
-                 ("flow_tv", tv_only))}
+                 ("flow_tv", tv_only), ("flow_tv(no loss atomics)", tv_noloss), ("iwe_cost_variance", var_only),
+                 ("adam_step", adam_only))}
         step_graph_ms = max_over_ranks(graph_time_ms(step, args.steps), world)
         clocks.soak(step)
     clk = clocks.summary()

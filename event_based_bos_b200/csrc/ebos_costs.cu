@@ -250,7 +250,11 @@ __device__ __forceinline__ float sgn_diff(float a, float b) {  // sign(a - b) wi
 
 template <typename T, bool HAS_WTS>
 __global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, const T* __restrict__ weights, int H, int W,
-                                                 T coef, double* __restrict__ acc, T* __restrict__ dflow) {
+                                                 T coef, double* __restrict__ acc, T* __restrict__ dflow,
+                                                 int32_t* __restrict__ step_dev) {
+  // fused solver iteration: this kernel also advances the device-side Adam step counter (it runs once per
+  // iteration, strictly before that iteration's Adam kernel)
+  if (step_dev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *step_dev += 1;
   // coef = tv_scale / (2*H*W).  Grid (ceil(quads/64), ceil(H/4), 2), block = 64 quads x 4 rows: no div/mod in the
   // index math (the first lean version spent most of its 111 instructions per element on 64-bit div/mod).
   __shared__ double sm[32];
@@ -317,23 +321,72 @@ __device__ __forceinline__ void adam_one(T& p, T g, T& m, T& v, T b1, T b2, T ep
   p -= step_size * (m / denom);
 }
 
+// Optional tail work of the fused solver iteration, done by one thread of the Adam kernel (it runs after every
+// producer/consumer of `acc`): scalar loss from the accumulators, then reset them for the next iteration.
+struct FinalizeArgs {
+  int enabled, kind, Hp, Wp, H, W, omit;
+  double data_scale, tv_scale;
+  double* acc;
+  void* loss;
+};
+
+template <typename T>
+__device__ __forceinline__ void finalize_loss(const FinalizeArgs& f) {
+  const double cnt = f.omit ? (double)(f.Hp - 2) * (double)(f.Wp - 2) : (double)f.Hp * (double)f.Wp;
+  double data = 0.0;
+  if (f.kind == EBOS_COST_VARIANCE) data = -((f.acc[1] - f.acc[0] * f.acc[0] / cnt) / (cnt - 1.0));
+  else if (f.kind == EBOS_COST_GRADMAG) data = -(f.acc[2] / cnt);
+  const double tv = f.acc[3] / (2.0 * (double)f.H * (double)f.W);
+  reinterpret_cast<T*>(f.loss)[0] = (T)(f.data_scale * data + f.tv_scale * tv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f.acc[i] = 0.0;
+}
+
+// step_mode 0: `step_host`;  1: *step_dev + 1 (bumped afterwards by k_adam_bump);  2: *step_dev (already advanced)
 template <typename T>
 __global__ void __launch_bounds__(256) k_adam(T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
                                               T* __restrict__ v, int64_t n, double lr, double b1, double b2, double eps,
-                                              int step_host, const int32_t* __restrict__ step_dev) {
+                                              int step_host, const int32_t* __restrict__ step_dev, int step_mode,
+                                              FinalizeArgs fin) {
   int step = step_host;
-  if (step_dev) step = *step_dev + 1;  // pre-increment value; bumped afterwards by k_adam_bump
+  if (step_mode == 1) step = *step_dev + 1;
+  else if (step_mode == 2) step = *step_dev;
   const double bc1 = 1.0 - pow(b1, (double)step);
   const double bc2 = 1.0 - pow(b2, (double)step);
   const T step_size = (T)(lr / bc1);
   const T inv_bc2_sqrt = (T)(1.0 / sqrt(bc2));
   const T tb1 = (T)b1, tb2 = (T)b2, teps = (T)eps;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if constexpr (sizeof(T) == 4) {
+    // 16-byte accesses: 7 plane streams, the kernel is pure bandwidth
+    if ((((size_t)p | (size_t)g | (size_t)m | (size_t)v) & 15) == 0) {
+      const int64_t n4 = n >> 2;
+      for (int64_t i = tid; i < n4; i += nth) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        adam_one<float>(pp.x, gg.x, mm.x, vv.x, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+        adam_one<float>(pp.y, gg.y, mm.y, vv.y, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+        adam_one<float>(pp.z, gg.z, mm.z, vv.z, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+        adam_one<float>(pp.w, gg.w, mm.w, vv.w, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+      }
+      for (int64_t i = n4 * 4 + tid; i < n; i += nth) {
+        T pp = p[i], mm = m[i], vv = v[i];
+        adam_one<T>(pp, __ldg(g + i), mm, vv, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+      }
+      if (fin.enabled && tid == 0) finalize_loss<T>(fin);
+      return;
+    }
+  }
   for (int64_t i = tid; i < n; i += nth) {
     T pp = p[i], mm = m[i], vv = v[i];
     adam_one<T>(pp, __ldg(g + i), mm, vv, tb1, tb2, teps, step_size, inv_bc2_sqrt);
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
+  if (fin.enabled && tid == 0) finalize_loss<T>(fin);
 }
 __global__ void k_adam_bump(int32_t* step_dev) { *step_dev += 1; }
 
@@ -367,8 +420,9 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
 }
 
 template <typename T>
-int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, double* acc, T* dflow, cudaStream_t st) {
-  if (tv_scale == 0.0 || H < 2 || W < 2) {
+int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, double* acc, T* dflow, cudaStream_t st,
+              int32_t* step_dev = nullptr) {
+  if ((tv_scale == 0.0 && !step_dev) || H < 2 || W < 2) {
     cudaError_t e = cudaMemsetAsync(dflow, 0, (size_t)2 * H * W * sizeof(T), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_flow_tv memset");
     if (tv_scale == 0.0) return EBOS_OK;
@@ -377,14 +431,14 @@ int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, do
   }
   const T coef = (T)(tv_scale / (2.0 * (double)H * (double)W));
   const dim3 grid(((W + 3) / 4 + 63) / 64, (H + 3) / 4, 2);
-  if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
-  else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow);
+  if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, step_dev);
+  else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, step_dev);
   EBOS_LAUNCH_CHECK("ebos_flow_tv");
   return EBOS_OK;
 }
 
 static int adam_grid(int64_t n) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n / 4 + 255) / 256, (int64_t)sm_count() * 8));
 }
 
 }  // namespace ebos
@@ -490,6 +544,60 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   return EBOS_OK;
 }
 
+int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flow, int H, int W, int pad_h, int pad_w,
+                             int kind, int omit_boundary, double data_scale, double tv_scale, const void* tv_weights,
+                             int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss, double* acc, void* exp_avg,
+                             void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int32_t* step_dev,
+                             void* stream) {
+  EBOS_REQUIRE(window && flow && iwe && dflow && loss && acc && exp_avg && exp_avg_sq && step_dev && n >= 0 && H > 1 &&
+                   W > 1 && pad_h >= 0 && pad_w >= 0,
+               "ebos_cmax_adam_iteration: bad argument");
+  EBOS_REQUIRE(kind == EBOS_COST_VARIANCE || kind == EBOS_COST_GRADMAG, "ebos_cmax_adam_iteration: unknown cost kind");
+  EBOS_REQUIRE(kind != EBOS_COST_GRADMAG || grad_iwe, "ebos_cmax_adam_iteration: GRADMAG needs the grad_iwe scratch plane");
+  EBOS_CHECK_DTYPE(dtype, "ebos_cmax_adam_iteration");
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_adam_iteration: omit_boundary needs an image larger than 2x2");
+  cudaStream_t st = as_stream(stream);
+  // graph nodes of one iteration: [IWE memset] [TV + step++ | splat] [cost] [backward] [Adam + loss + acc reset]
+  AuxLane* lane = aux_lane();
+  cudaStream_t tv_st = st;
+  if (lane) {
+    if (cudaEventRecord(lane->fork, st) == cudaSuccess && cudaStreamWaitEvent(lane->stream, lane->fork, 0) == cudaSuccess)
+      tv_st = lane->stream;
+    else
+      lane = nullptr;
+  }
+  int rc;
+  if (dtype == EBOS_F64)
+    rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, tv_st, step_dev);
+  else
+    rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st, step_dev);
+  if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(join)");
+  if (rc) return rc;
+  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st);
+  if (rc) return rc;
+  void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
+  if (dtype == EBOS_F64)
+    rc = iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)gplane, st);
+  else
+    rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
+  if (rc) return rc;
+  if (lane && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(wait)");
+  rc = window_backward_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc, omit_boundary,
+                              data_scale, dflow, st);
+  if (rc) return rc;
+  const FinalizeArgs fin{1, kind, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, acc, loss};
+  const int64_t np = (int64_t)2 * H * W;
+  if (dtype == EBOS_F64)
+    k_adam<double><<<adam_grid(np), 256, 0, st>>>((double*)flow, (const double*)dflow, (double*)exp_avg, (double*)exp_avg_sq,
+                                                   np, lr, beta1, beta2, eps, 0, step_dev, 2, fin);
+  else
+    k_adam<float><<<adam_grid(np), 256, 0, st>>>((float*)flow, (const float*)dflow, (float*)exp_avg, (float*)exp_avg_sq, np,
+                                                  lr, beta1, beta2, eps, 0, step_dev, 2, fin);
+  EBOS_LAUNCH_CHECK("ebos_cmax_adam_iteration");
+  return EBOS_OK;
+}
+
 int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr, double beta1,
                    double beta2, double eps, int step, int dtype, void* stream) {
   EBOS_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "ebos_adam_step: bad argument");
@@ -497,10 +605,10 @@ int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* exp_avg_s
   if (n == 0) return EBOS_OK;
   if (dtype == EBOS_F64)
     k_adam<double><<<adam_grid(n), 256, 0, as_stream(stream)>>>((double*)param, (const double*)grad, (double*)exp_avg,
-                                                                 (double*)exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr);
+                                                                 (double*)exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr, 0, FinalizeArgs{});
   else
     k_adam<float><<<adam_grid(n), 256, 0, as_stream(stream)>>>((float*)param, (const float*)grad, (float*)exp_avg,
-                                                                (float*)exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr);
+                                                                (float*)exp_avg_sq, n, lr, beta1, beta2, eps, step, nullptr, 0, FinalizeArgs{});
   EBOS_LAUNCH_CHECK("ebos_adam_step");
   return EBOS_OK;
 }
@@ -513,10 +621,10 @@ int ebos_adam_step_graph(void* param, const void* grad, void* exp_avg, void* exp
   if (n > 0) {
     if (dtype == EBOS_F64)
       k_adam<double><<<adam_grid(n), 256, 0, st>>>((double*)param, (const double*)grad, (double*)exp_avg,
-                                                    (double*)exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev);
+                                                    (double*)exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev, 1, FinalizeArgs{});
     else
       k_adam<float><<<adam_grid(n), 256, 0, st>>>((float*)param, (const float*)grad, (float*)exp_avg,
-                                                   (float*)exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev);
+                                                   (float*)exp_avg_sq, n, lr, beta1, beta2, eps, 0, step_dev, 1, FinalizeArgs{});
   }
   k_adam_bump<<<1, 1, 0, st>>>(step_dev);
   EBOS_LAUNCH_CHECK("ebos_adam_step_graph");

@@ -351,6 +351,30 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
     return ws.loss, ws.dflow
 
 
+def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                        step_dev: torch.Tensor, workspace: CmaxWorkspace, cost: str = "gradient_magnitude",
+                        data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
+                        omit_boundary: bool = False, lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999),
+                        eps: float = 1e-8) -> torch.Tensor:
+    """One solver iteration in one C call: objective + gradient (like `cmax_value_and_grad`) and the Adam update of
+    `flow` in place.  `workspace.acc` must be zero on entry (it is left zero), `step_dev` (int32 [1]) counts the
+    completed iterations.  Returns `workspace.loss` (the objective before the update)."""
+    _check_cuda(flow, tv_weights, exp_avg, exp_avg_sq, step_dev)
+    _check_flow(window, flow)
+    ws = workspace
+    if ws.dtype != window.dtype or exp_avg.dtype != window.dtype or exp_avg_sq.dtype != window.dtype:
+        raise TypeError("cmax_adam_iteration: window, workspace, flow and Adam moments must share a dtype")
+    tvw = None
+    if tv_weights is not None:
+        tvw = tv_weights.to(window.dtype).contiguous()
+    check(_capi.load().ebos_cmax_adam_iteration(
+        ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw, COST_KINDS[cost],
+        int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code, ptr(ws.iwe),
+        ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), ptr(exp_avg), ptr(exp_avg_sq), float(lr),
+        float(betas[0]), float(betas[1]), float(eps), ptr(step_dev), current_stream()), "ebos_cmax_adam_iteration")
+    return ws.loss
+
+
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
               lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
               step_dev: Optional[torch.Tensor] = None) -> None:

@@ -98,9 +98,9 @@ class ContrastMaximizationDense(SolverBase):
         hist = torch.zeros(max(self.n_iter, 1), dtype=self._dtype, device=x0.device) if self.store_history else None
 
         def iteration():
-            ops.cmax_value_and_grad(window, x0, self.data_cost, self.data_weight, self.tv_weight, None,
-                                    self.omit_boundary, pad, ws)
-            ops.adam_step(x0, ws.dflow, m, v, 0, self.lr, step_dev=step_dev)
+            # one C call: TV | splat -> cost -> backward -> Adam (+ loss, accumulator reset), six graph nodes
+            ops.cmax_adam_iteration(window, x0, m, v, step_dev, ws, self.data_cost, self.data_weight, self.tv_weight,
+                                    None, self.omit_boundary, self.lr)
 
         if self.use_cuda_graph and not self.store_history and self.n_iter > 2:
             # One captured iteration replayed n_iter times; the Adam step counter lives on the device.
@@ -111,6 +111,7 @@ class ContrastMaximizationDense(SolverBase):
                 m.zero_()
                 v.zero_()
                 step_dev.zero_()
+                ws.acc.zero_()
 
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

@@ -192,6 +192,18 @@ EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, 
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
                              double* acc, void* stream);
 
+/* One complete SOLVER iteration (src/solver/patch_eklt_pyramid2.py:267-285: zero_grad / loss / backward / step):
+ * ebos_cmax_value_and_grad followed by the Adam update of `flow`, as six graph nodes
+ *   [IWE memset] [TV + step counter | splat] [cost] [backward] [Adam + loss + accumulator reset].
+ * `acc` (double[8]) must be ZERO on entry and is left zero on exit; `step_dev` (int32[1]) counts the
+ * iterations done (0 before the first call) and is advanced by the call; `loss` receives this iteration's
+ * objective value (before the update).  Capture once in a CUDA graph, replay n_iter times. */
+EBOS_API int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flow, int H, int W, int pad_h,
+                             int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
+                             const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
+                             double* acc, void* exp_avg, void* exp_avg_sq, double lr, double beta1, double beta2,
+                             double eps, int32_t* step_dev, void* stream);
+
 /* torch.optim.Adam step (src/solver/patch_eklt_pyramid2.py:262-264,284), in place.  `step` is
  * 1-based.  Elementwise over n values. */
 EBOS_API int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr,
