@@ -69,8 +69,15 @@ class ContrastMaximizationDense(SolverBase):
     def estimate(self, events: np.ndarray, *args, flow0: Optional[np.ndarray] = None, **kwargs) -> np.ndarray:
         """[n,4] events (x=row, y=col, t [s], p) -> flow [2,H,W] float64 (pixel displacement over the window)."""
         H, W = self.orig_image_shape
-        # absolute sensor time -> window-relative, in float64, before the fp32 cast
-        ev = torch.from_numpy(utils.rebase_time(np.asarray(events))).to(self._dtype).to(self._device)
+        from .. import _capi
+
+        _capi.require_device()
+        # Absolute sensor time -> window-relative IN FLOAT64, before the cast to the solver dtype (the fp32 ulp at
+        # t = 10 s is 1 us; see utils.rebase_time).  Done on the device: one H2D copy of the raw float64 events.
+        raw = torch.from_numpy(np.ascontiguousarray(events, dtype=np.float64)).to(self._device)
+        if raw.shape[0]:
+            raw[:, 2] -= raw[:, 2].min()
+        ev = raw.to(self._dtype)
         x0 = torch.zeros((2, H, W), dtype=self._dtype, device=self._device)
         if flow0 is not None:
             x0.copy_(torch.from_numpy(np.asarray(flow0)).to(self._dtype))
@@ -79,8 +86,13 @@ class ContrastMaximizationDense(SolverBase):
             flow = self._solve_fused(ev, x0)
         else:
             flow = self._solve_operators(ev, x0)
-        best_x = flow.detach().cpu().numpy().astype(np.float64)
-        return best_x * self._roi_mask()
+        # ROI mask and float64 conversion on the device, one D2H copy of the result
+        out = flow.detach().to(torch.float64)
+        if (self.crop_xmin, self.crop_ymin, self.crop_xmax, self.crop_ymax) != (0, 0, H, W):
+            mask = torch.zeros((H, W), dtype=torch.float64, device=out.device)
+            mask[self.crop_xmin:self.crop_xmax, self.crop_ymin:self.crop_ymax] = 1.0
+            out = out * mask
+        return out.cpu().numpy()
 
     def _roi_mask(self) -> np.ndarray:
         mask = np.zeros(self.orig_image_shape)
@@ -102,7 +114,9 @@ class ContrastMaximizationDense(SolverBase):
             ops.cmax_adam_iteration(window, x0, m, v, step_dev, ws, self.data_cost, self.data_weight, self.tv_weight,
                                     None, self.omit_boundary, self.lr)
 
-        if self.use_cuda_graph and not self.store_history and self.n_iter > 2:
+        # CUDA graph: worth its capture/instantiate cost when iterations are short (launch-bound); for large windows
+        # (>= ~2 Mi events, >100 us of GPU work per iteration) eager launches run ahead of the GPU anyway.
+        if self.use_cuda_graph and not self.store_history and self.n_iter > 2 and window.n < (1 << 21):
             # One captured iteration replayed n_iter times; the Adam step counter lives on the device.
             backup = x0.clone()
 
