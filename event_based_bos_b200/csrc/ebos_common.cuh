@@ -260,7 +260,7 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // Spatial tiling of the ORIGIN pixel grid used by the sort key and the shared-memory tile kernels.
 constexpr int kTileH = 32, kTileW = 32;
-constexpr int kItemEvents = 8192;           // events per work item (a hot tile is split into several items)
+constexpr int kItemEvents = 4080;           // max events per work item = 255 x 16 (a busy tile is split EVENLY into several items)
 inline int tiles_x(int W) { return (W + kTileW - 1) / kTileW; }
 inline int tiles_y(int H) { return (H + kTileH - 1) / kTileH; }
 inline int64_t max_items(int64_t n, int H, int W) { return n / kItemEvents + (int64_t)tiles_x(W) * tiles_y(H) + 1; }

@@ -32,7 +32,14 @@ template <> struct Ept<double> { static constexpr int splat = 4, bwd = 4; };
 // Diagnostics: EBOS_ABLATE bit mask removes one cost component from the one-shot streaming kernels so that its
 // share of the run time can be measured directly (results are then WRONG; never set outside profiling):
 //   1 no REDs   2 no flow gathers (constant flow)   4 no event loads (synthetic events)   8 no dL/dIWE gathers
-__device__ int g_ablate = 0;
+// Compiled in only with -DEBOS_ABLATION (EBOS_BUILD_ABLATION=1 python -m event_based_bos_b200._build --force): the
+// production kernels must not pay a global load + branch per flush for a diagnostic.
+#ifdef EBOS_ABLATION
+__device__ int g_ablate_word = 0;
+#define g_ablate g_ablate_word
+#else
+#define g_ablate 0
+#endif
 // experiment knob (EBOS_SPLAT_EPT / EBOS_BWD_EPT environment variables; 0 = default)
 static int env_int(const char* name) {
   const char* v = getenv(name);
@@ -132,10 +139,11 @@ __global__ void __launch_bounds__(256) k_win_tile_offsets(const unsigned int* __
   tile_off[t] = (int)lo;   // t == n_tiles: end of the valid events (invalid ones carry the largest key)
 }
 
-// Work items (tile, begin, end): every tile's event range cut into pieces of at most kItemEvents.
+// Work items (tile, begin, end): every tile's event range cut EVENLY into ceil(len / kItemEvents) pieces (piece
+// length rounded up to a multiple of 16), so that the items of a busy tile carry the same load.
 // One CTA: per-tile item counts, block-wide exclusive scan (looped), fill.
-__global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int4* __restrict__ items,
-                                                    WindowHeader* __restrict__ h) {
+__global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int tiles_per_row,
+                                                    int4* __restrict__ items, WindowHeader* __restrict__ h) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -159,7 +167,9 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
     }
     __syncthreads();
     const int excl = carry + (wid ? warp_sums[wid - 1] : 0) + v - cnt;
-    for (int i = 0; i < cnt; ++i) items[excl + i] = make_int4(t, b + i * kItemEvents, min(b + (i + 1) * kItemEvents, e), 0);
+    const int piece = cnt ? ((((e - b) + cnt - 1) / cnt + 15) & ~15) : 0;   // <= kItemEvents (a multiple of 16)
+    const int tcoord = ((t / tiles_per_row) << 16) | (t % tiles_per_row);   // (tile row, tile col) for the tile kernels
+    for (int i = 0; i < cnt; ++i) items[excl + i] = make_int4(t, min(b + i * piece, e), min(b + (i + 1) * piece, e), tcoord);
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = excl + cnt;
     __syncthreads();
@@ -796,6 +806,194 @@ k_tile_splat(const float* __restrict__ sx, const float* __restrict__ sy, const f
   }
 }
 
+// ---- shared-memory tile splat with FIXED-POINT accumulation (fp32 default for dense windows) -----------
+// Shared-memory float atomics are a CAS loop on sm_100a, integer ATOMS.ADD is native and 8x cheaper per lane than
+// a global RED (0.14 vs 1.15 SM-cycles, profiles/microbench/r01_red_throughput.txt).  One CTA takes one work item
+// (<= kItemEvents events of one 32x32 tile), every thread walks over 16 consecutive events, combines runs of
+// equal cells in registers exactly like k_win_splat_g and adds each run's four tap sums to an int32 window as
+// round(sum * 2^S).  S is chosen per item so that the window can never overflow:
+//   |tap weight| <= 1 + 2e-6, so every partial sum of an item of cnt events is < 2^(ilog2(cnt)+1), and with
+//   S = 30 - ilog2(cnt) (<= 24) every int32 cell stays below 2^31 in magnitude.
+// Quantisation: one rounding of <= 2^-(S+1) per flushed tap sum (S >= 19 for 4080 events, i.e. <= 9.5e-7: the
+// size of ONE fp32 rounding of a cell value in [8, 16)); integer addition is exact and order independent, so the
+// IWE of this kernel is also run-to-run reproducible.  The window is then added to the global IWE with coalesced
+// fp32 REDs (windows of neighbouring tiles / items overlap).  Taps outside the window (|flow * dt| > kHalo) and
+// non-finite events take the global fp32 path, so correctness never depends on the halo.  Items with fewer than
+// kWinMinEvents events skip the window (zero + flush of 1681 cells would cost more than their REDs).
+constexpr int kWinMinEvents = 1024;
+
+template <bool PACKED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_tile_splat_q(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+               const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
+               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
+  __shared__ int win[kSH * kSW];
+  if ((int)blockIdx.x >= hdr->n_items) return;
+  const int4 it = __ldg(items + blockIdx.x);
+  const int cnt = it.z - it.y;
+  if (cnt <= 0) return;
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
+  const bool use_win = cnt >= kWinMinEvents;
+  int r_org, c_org;
+  tile_origin(it.x, W, pad_h, pad_w, r_org, c_org);
+  const int S = min(24, 30 - (31 - __clz(cnt)));
+  const float qs = __int_as_float((127 + S) << 23);
+  if (use_win) {
+    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0;
+    __syncthreads();
+  }
+  auto flush = [&](const SplatRun& run) {
+    const int r = (int)run.cfr + pad_h, c = (int)run.cfc + pad_w;
+    const int lr = r - r_org, lc = c - c_org;
+    if (use_win && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1)) {
+      int* p = win + lr * kSW + lc;
+      atomicAdd(p, __float2int_rn(run.a01.x * qs));            // (r  , c  )
+      atomicAdd(p + kSW, __float2int_rn(run.a01.y * qs));      // (r+1, c  )
+      atomicAdd(p + 1, __float2int_rn(run.a23.x * qs));        // (r  , c+1)
+      atomicAdd(p + kSW + 1, __float2int_rn(run.a23.y * qs));  // (r+1, c+1)
+    } else {
+      flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, r, c, run.a01.x, run.a01.y, run.a23.x, run.a23.y);
+    }
+  };
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
+  const int64_t start = (int64_t)it.y & ~(int64_t)3;
+  for (int64_t base = start + (int64_t)threadIdx.x * 16; base < it.z; base += (int64_t)blockDim.x * 16) {
+    SplatRun run{NAN, 0.f, make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+      const int64_t b = base + 4 * g;
+      if (b >= it.z) break;
+      EventBlock<float, 4, false, PACKED> e;
+      e.load_range(sx, sy, sd, nullptr, b, it.y, it.z);
+      e.finish(flow, W, hw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // x' = x - (dt * f) with two roundings (see splat_block_f32)
+        const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+        const float2 wb = add2(w, bias2);
+        const float fr = floorf(wb.x), fc = floorf(wb.y);
+        const float2 ab = sub2(w, make_float2(fr, fc));
+        const float2 nab = sub2(one2, ab);
+        const float2 lhs = make_float2(nab.x, ab.x);
+        const float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
+        const float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
+        if (w01.x != w01.x) {
+          splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, 1.f);
+          continue;
+        }
+        if (!((fr == run.cfr) & (fc == run.cfc))) {
+          if (run.cfr == run.cfr) flush(run);
+          run.cfr = fr; run.cfc = fc;
+          run.a01 = make_float2(0.f, 0.f); run.a23 = make_float2(0.f, 0.f);
+        }
+        run.a01 = add2(run.a01, w01);
+        run.a23 = add2(run.a23, w23);
+      }
+    }
+    if (run.cfr == run.cfr) flush(run);
+  }
+  if (!use_win) return;
+  __syncthreads();
+  // window -> global: coalesced rows of fp32 REDs (the conversion of an int32 < 2^31 to fp32 is one rounding)
+  const float inv = __int_as_float((127 - S) << 23);
+  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+    const int v = win[i];
+    const int lr = i / kSW, lc = i - lr * kSW;
+    const int r = r_org + lr, c = c_org + lc;
+    if (v != 0 && (unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, (float)v * inv);
+  }
+}
+
+// Direct variant: NO run tracking.  The divergent "cell changed -> flush" branch of the run-combining kernels is
+// executed by a warp at almost every event step (one lane in four flushes), so its ~25 instructions are paid
+// per event anyway; with native integer shared-memory atomics at 4.5 SM-cycles per warp instruction it is cheaper
+// to add every event's four taps straight to the window: ~45 instead of ~95 issue slots per event.
+// float -> fixed point on the FP32 pipe: fma(w, 2^S, 1.5 * 2^23) leaves round(w * 2^S) in the low mantissa bits
+// (|w * 2^S| < 2^22, i.e. S <= 21); no quarter-rate F2I.
+__device__ __noinline__ void splat_taps_global(float* __restrict__ iwe, int Hp, int Wp, int r, int c, float w0, float w1,
+                                               float w2, float w3) {
+  flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, r, c, w0, w1, w2, w3);
+}
+
+template <bool PACKED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+               const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
+               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
+  // One CTA per item slot (unused slots exit at once): the hardware block scheduler balances the ragged items.  A
+  // persistent variant (static round-robin over items, window re-zeroed by the flush) was measured slower on B200
+  // (78-114 vs 77 us at 16 Mi events: more live state -> spills, and the per-item barriers idle whole CTAs).
+  __shared__ int win[kSH * kSW];
+  const int n_items = hdr->n_items;
+  if ((int)blockIdx.x >= n_items) return;
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
+  const float M = 12582912.0f;   // 1.5 * 2^23
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
+  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0;
+  __syncthreads();
+  const int4 it = __ldg(items + blockIdx.x);
+  {
+    const int cnt = it.z - it.y;
+    if (cnt > 0) {
+      const int r_org = (it.w >> 16) * kTileH - kHalo + pad_h, c_org = (it.w & 0xffff) * kTileW - kHalo + pad_w;
+      const bool use_win = cnt >= kWinMinEvents;
+      const int S = min(21, 30 - (31 - __clz(cnt)));
+      const float qs = __int_as_float((127 + S) << 23);
+      const int64_t start = (int64_t)it.y & ~(int64_t)3;
+      for (int64_t base = start + (int64_t)threadIdx.x * 16; base < it.z; base += (int64_t)blockDim.x * 16) {
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          const int64_t b = base + 4 * g;
+          if (b >= it.z) break;
+          EventBlock<float, 4, false, PACKED> e;
+          e.load_range(sx, sy, sd, nullptr, b, it.y, it.z);
+          e.finish(flow, W, hw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // x' = x - (dt * f) with two roundings (see splat_block_f32)
+            const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+            const float2 wb = add2(w, bias2);
+            const float fr = floorf(wb.x), fc = floorf(wb.y);
+            const float2 ab = sub2(w, make_float2(fr, fc));
+            const float2 nab = sub2(one2, ab);
+            const float2 lhs = make_float2(nab.x, ab.x);
+            const float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
+            const float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
+            if (w01.x != w01.x) {
+              splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, 1.f);
+              continue;
+            }
+            const int r = (int)fr + pad_h, c = (int)fc + pad_w;
+            const int lr = r - r_org, lc = c - c_org;
+            if (use_win && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1)) {
+              int* p = win + lr * kSW + lc;
+              atomicAdd(p, __float_as_int(fmaf(w01.x, qs, M)) - 0x4B400000);            // (r  , c  )
+              atomicAdd(p + kSW, __float_as_int(fmaf(w01.y, qs, M)) - 0x4B400000);      // (r+1, c  )
+              atomicAdd(p + 1, __float_as_int(fmaf(w23.x, qs, M)) - 0x4B400000);        // (r  , c+1)
+              atomicAdd(p + kSW + 1, __float_as_int(fmaf(w23.y, qs, M)) - 0x4B400000);  // (r+1, c+1)
+            } else {
+              splat_taps_global(iwe, Hp, Wp, r, c, w01.x, w01.y, w23.x, w23.y);
+            }
+          }
+        }
+      }
+      if (use_win) {
+        __syncthreads();
+        // window -> global: coalesced rows of fp32 REDs (an int32 -> fp32 conversion is one rounding)
+        const float inv = __int_as_float((127 - S) << 23);
+        for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+          const int v = win[i];
+          if (v != 0) {
+            const int lr = i / kSW, lc = i - lr * kSW;
+            const int r = r_org + lr, c = c_org + lc;
+            if ((unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, (float)v * inv);
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- backward ------------------------------------------------------------------------------------
 // GSRC 0: dL/dIWE read from a plane.  GSRC 1: variance objective, dL/dIWE = cv * (IWE - mean)
 // derived on the fly from the IWE itself (saves writing and re-reading a gradient plane).
@@ -1179,7 +1377,7 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   const int n_tiles = tiles_x(W) * tiles_y(H);
   int* tile_off = reinterpret_cast<int*>(b + L.off_tiles);
   k_win_tile_offsets<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(k_out, n, n_tiles, tile_off);
-  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, reinterpret_cast<int4*>(b + L.off_items), hdr);
+  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), reinterpret_cast<int4*>(b + L.off_items), hdr);
   k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
                                       reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
                                       reinterpret_cast<T*>(b + L.off_d),
@@ -1192,8 +1390,10 @@ static void apply_ablate_env() {
   static bool done = false;
   if (done) return;
   done = true;
+#ifdef EBOS_ABLATION
   const int v = env_int("EBOS_ABLATE");
-  if (v) cudaMemcpyToSymbol(g_ablate, &v, sizeof(int));
+  if (v) cudaMemcpyToSymbol(g_ablate_word, &v, sizeof(int));
+#endif
 }
 
 template <typename T>
@@ -1225,6 +1425,40 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   // CAS loop that serialises on same-address conflicts, whereas the L2 RED unit merges them.
   static const int tile_env = env_int("EBOS_TILE");
   if constexpr (sizeof(T) == 4) {
+    // fixed-point shared-memory tile kernel (direct variant): the default for dense unweighted windows (mean >=
+    // kWinMinEvents events per tile); EBOS_TILE=4 forces it, 2 forces the run-combining variant, 3 the grouped kernel
+    const bool dense = n >= (int64_t)tiles_x(W) * tiles_y(H) * kWinMinEvents;
+    if (!has_weight && (tile_env == 4 || (tile_env == 0 && dense))) {
+      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
+      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
+      static const int occ_env = env_int("EBOS_QOCC");
+      const int occ = (occ_env == 4 || occ_env == 6) ? occ_env : 5;
+      const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd);
+      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
+#define EBOS_SD(P, B) k_tile_splat_d<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
+      if (packed) { if (occ == 4) EBOS_SD(true, 4); else if (occ == 5) EBOS_SD(true, 5); else EBOS_SD(true, 6); }
+      else { if (occ == 4) EBOS_SD(false, 4); else if (occ == 5) EBOS_SD(false, 5); else EBOS_SD(false, 6); }
+#undef EBOS_SD
+      EBOS_LAUNCH_CHECK("ebos_window_splat(tile, direct)");
+      return EBOS_OK;
+    }
+    if (!has_weight && tile_env == 2) {
+      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
+      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
+      const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot; unused slots exit at once
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd);
+      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
+      static const int occ_env = env_int("EBOS_QOCC");   // experiment knob: CTAs per SM the kernel is compiled for
+#define EBOS_SQ(P, B) k_tile_splat_q<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
+      if (packed) { if (occ_env == 4) EBOS_SQ(true, 4); else if (occ_env == 5) EBOS_SQ(true, 5); else EBOS_SQ(true, 6); }
+      else { if (occ_env == 4) EBOS_SQ(false, 4); else if (occ_env == 5) EBOS_SQ(false, 5); else EBOS_SQ(false, 6); }
+#undef EBOS_SQ
+      EBOS_LAUNCH_CHECK("ebos_window_splat(tile, fixed point)");
+      return EBOS_OK;
+    }
     if (tile_env == 1) {
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);

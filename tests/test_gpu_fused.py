@@ -83,11 +83,12 @@ def test_packed_and_generic_layouts_agree(ops):
         assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", ["grouped", "tile", "pipe", "oneshot"])
+@pytest.mark.parametrize("mode", ["default", "tileq", "tiled", "grouped", "tile", "pipe", "oneshot"])
 def test_all_streaming_kernel_variants_match_oracle(mode):
-    """The fused fp32 path has four kernel families for the event stream: the default grouped one-shot kernels,
-    the legacy one-shot kernels (also the fp64 path), and two opt-in experiments (shared-memory tile kernels,
-    persistent TMA-staged kernels).  Each is forced on in a fresh process and must match the oracle on small
+    """The fused fp32 path has several kernel families for the event stream: the default (fixed-point shared-memory
+    tile splat for dense windows, grouped one-shot kernels otherwise; "tileq" forces the former and "grouped" the
+    latter for every window), the legacy one-shot kernels (also the fp64 path), and two opt-in experiments
+    (float shared-memory tile kernels, persistent TMA-staged kernels).  Each is forced on in a fresh process and must match the oracle on small
     windows incl. ragged tails, multi-item tiles, padding, weights, packed and generic layouts."""
     import json
     import os
@@ -95,7 +96,8 @@ def test_all_streaming_kernel_variants_match_oracle(mode):
     import sys
 
     env = dict(os.environ)
-    env.update({"grouped": {}, "tile": {"EBOS_TILE": "1"}, "pipe": {"EBOS_PIPE": "1"},
+    env.update({"default": {}, "tileq": {"EBOS_TILE": "2"}, "tiled": {"EBOS_TILE": "4"}, "grouped": {"EBOS_TILE": "3"}, "tile": {"EBOS_TILE": "1"},
+                "pipe": {"EBOS_PIPE": "1"},
                 "oneshot": {"EBOS_GROUPS": "-1"}}[mode])
     script = os.path.join(os.path.dirname(__file__), "pipe_check.py")
     res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
