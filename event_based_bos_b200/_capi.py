@@ -18,6 +18,7 @@ EBOS_OK = 0
 EBOS_F32, EBOS_F64 = 0, 1
 DIR_FIRST, DIR_LAST, DIR_FRAC = 0, 1, 2
 COST_NONE, COST_VARIANCE, COST_GRADMAG = 0, 1, 2
+ACC_DOUBLES = 40  # EBOS_ACC_DOUBLES (include/ebos.h)
 STATUS_PIXEL_OOB = 1
 STATUS_PACKED = 2
 WIN_HAS_WEIGHT, WIN_PACKED = 1, 2

@@ -7,7 +7,10 @@
 //   Adam                torch.optim.Adam as used at src/solver/patch_eklt_pyramid2.py:262-264,284
 //
 // All reductions: per-thread double accumulators -> warp shuffle -> one atomicAdd(double) per CTA.
-// acc layout (double[8]): [0] sum(IWE) [1] sum(IWE^2) [2] sum(gx^2+gy^2) [3] sum(|TV terms|).
+// acc layout (double[EBOS_ACC_DOUBLES = 40]): [0] sum(IWE) [1] sum(IWE^2) [2] + [8..23] sum(gx^2+gy^2)
+// [3] + [24..39] sum(|TV terms|).  Same-address atomics from different CTAs serialise in the L2 atomic unit
+// (~6 ns each on B200: 3.5 us for the ~600 CTAs of the TV kernel, as long as its real work), so the two plane
+// kernels of the hot path spread their per-CTA partial sums over 16 slots; the consumers add the slots up.
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -15,6 +18,9 @@
 #include "ebos_common.cuh"
 
 namespace ebos {
+
+constexpr int kAccSpread = 16, kAccGradSlots = 8, kAccTvSlots = 24;
+static_assert(kAccTvSlots + kAccSpread == EBOS_ACC_DOUBLES, "accumulator layout");
 
 // The TV term depends only on the flow, the splat only on events + flow: inside the fused evaluation
 // they run concurrently (fork/join on a cached auxiliary stream; the pattern is CUDA-graph capturable).
@@ -181,6 +187,130 @@ __global__ void __launch_bounds__(256, 4) k_gradmag(const T* __restrict__ iwe, i
   if (threadIdx.x == 0) atomicAdd(acc + 2, part);
 }
 
+// ---- gradient magnitude, separable version (default) -------------------------------------------------
+// The tiled kernel above spends ~220 instructions per pixel (ncu r01c: issue-bound at 15 us for 7.4 MB).  Away
+// from the border the whole forward + adjoint collapses into two separable stencils.  With s = [1,2,1] (smooth),
+// d = [-1,0,1] (difference), Sx = d_row (x) s_col, Sy = s_row (x) d_col:
+//   gx = (S[r+1] - S[r-1]) / 8,  gy = (D[r-1] + 2 D[r] + D[r+1]) / 8      S = s_col * I,  D = d_col * I
+//   dL/dI = coef/8 * (Sx^T Sx + Sy^T Sy) I = coef/8 * (a_row (x) b_col + b_row (x) a_col) I
+//   a = d (*) d = [-1,0,2,0,-1],  b = s (*) s = [1,4,6,4,1];   P = b_col * I,  Q = a_col * I
+// A thread owns one column of a 32-row x 64-column tile band and marches down the rows with the last five rows of
+// (P, Q, S, D) in registers: 5 conflict-free LDS + ~35 flops per pixel.  This "fast region" is r in [3, Hp-4],
+// c in [3, Wp-4]: there no tap is clamped by the replicate padding and no g on the (optionally omitted) border
+// ring is involved.  The 3-pixel frame around it is evaluated exactly, straight from the definition, by extra
+// CTAs of the same launch (one thread per frame pixel).
+constexpr int GM_TH = 32, GM_TW = 64, GM_ROWS = 8;   // tile, rows per thread (256 threads = 64 columns x 4 row groups)
+
+// exact value at one frame pixel p = (r, c): sum over the counted positions q in the 3x3 neighbourhood of p and
+// the Sobel taps (u, v) whose clamped target clamp(q + (u, v)) is p.  The 5x5 clamped neighbourhood of p is
+// loaded up front (25 independent loads, one round trip); everything else is register arithmetic with
+// compile-time indices (a first version with nested loops around dependent loads made these few threads the
+// critical path of the whole launch).
+template <typename T>
+__device__ void gradmag_frame_pixel(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, int r, int c,
+                                    T* __restrict__ g, double& part) {
+  T v[5][5];
+#pragma unroll
+  for (int a = -2; a <= 2; ++a)
+#pragma unroll
+    for (int b = -2; b <= 2; ++b)
+      v[a + 2][b + 2] = __ldg(iwe + (int64_t)min(max(r + a, 0), Hp - 1) * Wp + min(max(c + b, 0), Wp - 1));
+  T out = 0;
+#pragma unroll
+  for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+    for (int dc = -1; dc <= 1; ++dc) {
+      const int qr = r + dr, qc = c + dc;
+      if (qr < 0 || qr >= Hp || qc < 0 || qc >= Wp) continue;
+      if (omit && (qr == 0 || qc == 0 || qr == Hp - 1 || qc == Wp - 1)) continue;
+      // Sobel/8 at q from the clamped neighbourhood: I(clamp(q + (u,v))) = v[dr + u + 2][dc + v + 2]
+      const T gx = ((v[dr + 3][dc + 1] - v[dr + 1][dc + 1]) + (T)2 * (v[dr + 3][dc + 2] - v[dr + 1][dc + 2]) +
+                    (v[dr + 3][dc + 3] - v[dr + 1][dc + 3])) * (T)0.125;  // d/drow
+      const T gy = ((v[dr + 1][dc + 3] - v[dr + 1][dc + 1]) + (T)2 * (v[dr + 2][dc + 3] - v[dr + 2][dc + 1]) +
+                    (v[dr + 3][dc + 3] - v[dr + 3][dc + 1])) * (T)0.125;  // d/dcol
+      if (dr == 0 && dc == 0) part += (double)gx * gx + (double)gy * gy;
+#pragma unroll
+      for (int u = -1; u <= 1; ++u) {
+#pragma unroll
+        for (int w = -1; w <= 1; ++w) {
+          if (min(max(qr + u, 0), Hp - 1) != r || min(max(qc + w, 0), Wp - 1) != c) continue;
+          out += (T)(u * (2 - (w < 0 ? -w : w))) * (coef * gx) + (T)(w * (2 - (u < 0 ? -u : u))) * (coef * gy);
+        }
+      }
+    }
+  }
+  g[(int64_t)r * Wp + c] = out;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gradmag_sep(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, double* __restrict__ acc, T* __restrict__ g,
+              int n_frame_ctas, int n_tiles) {
+  __shared__ T sI[GM_TH + 4][GM_TW + 4];
+  __shared__ double sm[32];
+  double part = 0.0;
+  const bool has_fast = Hp >= 7 && Wp >= 7;
+  if ((int)blockIdx.x < n_frame_ctas) {
+    // frame pixels: rows 0..2 and Hp-3..Hp-1 (full width), then columns 0..2 and Wp-3..Wp-1 of the other rows;
+    // images without a fast region are all frame
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = -1, c = -1;
+    if (!has_fast) {
+      if (idx < (int64_t)Hp * Wp) { r = (int)(idx / Wp); c = (int)(idx - (int64_t)r * Wp); }
+    } else if (idx < (int64_t)6 * Wp) {
+      const int k = (int)(idx / Wp);
+      r = k < 3 ? k : Hp - 6 + k; c = (int)(idx - (int64_t)k * Wp);
+    } else if (idx < (int64_t)6 * Wp + (int64_t)6 * (Hp - 6)) {
+      const int64_t j = idx - (int64_t)6 * Wp;
+      const int k = (int)(j % 6);
+      r = 3 + (int)(j / 6); c = k < 3 ? k : Wp - 6 + k;
+    }
+    if (r >= 0) gradmag_frame_pixel<T>(iwe, Hp, Wp, omit, coef, r, c, g, part);
+  } else if ((int)blockIdx.x - n_frame_ctas < n_tiles) {
+    const int tile = blockIdx.x - n_frame_ctas;
+    const int tiles_x = (Wp + GM_TW - 1) / GM_TW;
+    const int r0 = (tile / tiles_x) * GM_TH, c0 = (tile % tiles_x) * GM_TW;
+    // image tile with a 2-pixel halo (clamped reads: values outside the image are never used by the fast region)
+    for (int i = threadIdx.x; i < (GM_TH + 4) * (GM_TW + 4); i += blockDim.x) {
+      const int lr = i / (GM_TW + 4), lc = i - lr * (GM_TW + 4);
+      const int r = min(max(r0 - 2 + lr, 0), Hp - 1), c = min(max(c0 - 2 + lc, 0), Wp - 1);
+      sI[lr][lc] = __ldg(iwe + (int64_t)r * Wp + c);
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & (GM_TW - 1), ty = threadIdx.x / GM_TW;
+    const int c = c0 + tx;
+    const bool col_ok = c >= 3 && c <= Wp - 4;
+    const T c8 = coef * (T)0.125;
+    T P[5], Q[5], S[5], D[5];
+    T tpart = 0;   // at most GM_ROWS terms per thread before the double accumulation
+#pragma unroll
+    for (int k = 0; k < GM_ROWS + 4; ++k) {
+      // horizontal pass on image row r0 + ty*GM_ROWS - 2 + k
+      const T* row = &sI[ty * GM_ROWS + k][tx];
+      const T i0 = row[0], i1 = row[1], i2 = row[2], i3 = row[3], i4 = row[4];
+      const T h0 = i0 + i4, h1 = i1 + i3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { P[j] = P[j + 1]; Q[j] = Q[j + 1]; S[j] = S[j + 1]; D[j] = D[j + 1]; }
+      P[4] = h0 + (T)4 * h1 + (T)6 * i2;
+      Q[4] = (T)2 * i2 - h0;
+      S[4] = h1 + (T)2 * i2;
+      D[4] = i3 - i1;
+      if (k >= 4) {
+        const int r = r0 + ty * GM_ROWS + k - 4;   // centre row of the five-row window
+        if (col_ok && r >= 3 && r <= Hp - 4) {
+          const T gx = (S[3] - S[1]) * (T)0.125, gy = (D[1] + (T)2 * D[2] + D[3]) * (T)0.125;
+          tpart += gx * gx + gy * gy;
+          const T v = ((T)2 * P[2] - P[0] - P[4]) + ((Q[0] + Q[4]) + (T)4 * (Q[1] + Q[3]) + (T)6 * Q[2]);
+          g[(int64_t)r * Wp + c] = c8 * v;
+        }
+      }
+    }
+    part = (double)tpart;
+  }
+  part = block_sum(part, sm);
+  if (threadIdx.x == 0) atomicAdd(acc + kAccGradSlots + (blockIdx.x & (kAccSpread - 1)), part);
+}
+
 // ---- total variation of the flow: value + gradient -------------------------------------------------
 // torch.gradient (spacing 1, edge_order 1): interior G(q) = (f[q+1]-f[q-1])/2, edges one-sided.
 // d/df[i] of sum_q |G(q) w(q)|  =  sum_q s(q) dG(q)/df[i],  s(q) = sign(G(q) w(q)) w(q).  Only q = i-1, i, i+1
@@ -300,15 +430,98 @@ __global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, con
   if (threadIdx.x == 0 && acc) atomicAdd(acc + 3, part);
 }
 
+// Row-marching version for the lean case (fp32, unit weights, W % 4 == 0, 16-byte aligned planes): a thread owns
+// one quad of columns and TV_ROWS consecutive rows and keeps the five rows r-2..r+2 of its quad in registers, so
+// a flow row is loaded ~1.5 times instead of 5, and the index set-up and the block reduction are paid once per
+// 32 elements instead of once per 4 (the one-quad-per-thread kernel above executes ~100 instructions per element).
+constexpr int TV_ROWS = 8;
+
+// frame element idx -> (r, c): rows {0, 1, H-2, H-1} over all columns, then columns {0..3, W-4..W-1} of the rows between
+__device__ __forceinline__ bool tv_frame_coord(int64_t idx, int H, int W, int& r, int& c) {
+  if (idx < (int64_t)4 * W) {
+    const int k = (int)(idx / W);
+    r = k < 2 ? k : H - 4 + k; c = (int)(idx - (int64_t)k * W);
+    return true;
+  }
+  const int64_t j = idx - (int64_t)4 * W;
+  if (j >= (int64_t)8 * (H - 4)) return false;
+  const int k = (int)(j & 7);
+  r = 2 + (int)(j >> 3); c = k < 4 ? k : W - 8 + k;
+  return true;
+}
+
+// grid.x = n_frame_ctas + fast CTAs (64 quads x 2 row strips each), grid.y = channel.  Needs H >= 5, W >= 12.
+__global__ void __launch_bounds__(128) k_flow_tv_march(const float* __restrict__ flow, int H, int W, float coef,
+                                                       double* __restrict__ acc, float* __restrict__ dflow,
+                                                       int32_t* __restrict__ step_dev, int n_frame_ctas, int fast_gx) {
+  if (step_dev && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *step_dev += 1;
+  __shared__ double sm[32];
+  const int ch = blockIdx.y;
+  const float* f = flow + (int64_t)ch * H * W;
+  float* out = dflow + (int64_t)ch * H * W;
+  double part = 0.0;
+  if ((int)blockIdx.x < n_frame_ctas) {
+    // edges: one element per thread through the general code (its ten loads are independent: one round trip)
+    int r, c;
+    if (tv_frame_coord((int64_t)blockIdx.x * blockDim.x + threadIdx.x, H, W, r, c))
+      tv_element_general<float, false>(f, nullptr, H, W, r, c, coef, out, part);
+  } else {
+    const int t = blockIdx.x - n_frame_ctas;
+    const int q = (t % fast_gx) * 64 + (threadIdx.x & 63), rs = 2 + ((t / fast_gx) * 2 + (threadIdx.x >> 6)) * TV_ROWS;
+    const int c0 = q * 4;
+    if (c0 >= 4 && c0 + 8 <= W && rs <= H - 3) {
+      // every load is unconditional (row index clamped), only the stores are guarded: the unrolled loop has no
+      // control flow around its loads, so they are all in flight together
+      auto rowp = [&](int r) { return f + (int64_t)min(r, H - 1) * W + c0; };
+      float4 m2 = __ldg(reinterpret_cast<const float4*>(rowp(rs - 2))), m1 = __ldg(reinterpret_cast<const float4*>(rowp(rs - 1)));
+      float4 ce = __ldg(reinterpret_cast<const float4*>(rowp(rs))), p1 = __ldg(reinterpret_cast<const float4*>(rowp(rs + 1)));
+      float fpart = 0.f;
+#pragma unroll
+      for (int i = 0; i < TV_ROWS; ++i) {
+        const int r = rs + i;
+        const float4 p2 = __ldg(reinterpret_cast<const float4*>(rowp(r + 2)));
+        const float4 lf = __ldg(reinterpret_cast<const float4*>(rowp(r) - 4)), rt = __ldg(reinterpret_cast<const float4*>(rowp(r) + 4));
+        const float row[8] = {lf.z, lf.w, ce.x, ce.y, ce.z, ce.w, rt.x, rt.y};   // columns c0-2 .. c0+5
+        const float um2[4] = {m2.x, m2.y, m2.z, m2.w}, um1[4] = {m1.x, m1.y, m1.z, m1.w};
+        const float up1[4] = {p1.x, p1.y, p1.z, p1.w}, up2[4] = {p2.x, p2.y, p2.z, p2.w};
+        float o[4], rpart = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v = row[2 + k];
+          // rows and columns: every q = i-1, i, i+1 involved is an interior sample here (see k_flow_tv)
+          float adj = 0.5f * (sgn_diff(v, um2[k]) - sgn_diff(up2[k], v));
+          adj += 0.5f * (sgn_diff(v, row[k]) - sgn_diff(row[4 + k], v));
+          rpart += 0.5f * (fabsf(up1[k] - um1[k]) + fabsf(row[3 + k] - row[1 + k]));
+          o[k] = coef * adj;
+        }
+        if (r <= H - 3) {
+          fpart += rpart;
+          *reinterpret_cast<float4*>(out + (int64_t)r * W + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        m2 = m1; m1 = ce; ce = p1; p1 = p2;
+      }
+      part = (double)fpart;   // 64 non-negative terms
+    }
+  }
+  part = block_sum(part, sm);
+  if (threadIdx.x == 0 && acc) atomicAdd(acc + kAccTvSlots + ((blockIdx.x + 5 * blockIdx.y) & (kAccSpread - 1)), part);
+}
+
 // ---- loss scalar -------------------------------------------------------------------------------------
+__device__ __forceinline__ double acc_total(const double* __restrict__ acc, int single, int spread) {
+  double t = acc[single];
+#pragma unroll
+  for (int i = 0; i < kAccSpread; ++i) t += acc[spread + i];
+  return t;
+}
 template <typename T>
 __global__ void k_loss_finalize(int kind, const double* __restrict__ acc, int Hp, int Wp, int H, int W, int omit,
                                 double data_scale, double tv_scale, T* __restrict__ loss) {
   const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
   double data = 0.0;
   if (kind == EBOS_COST_VARIANCE) data = -((acc[1] - acc[0] * acc[0] / cnt) / (cnt - 1.0));
-  else if (kind == EBOS_COST_GRADMAG) data = -(acc[2] / cnt);
-  const double tv = acc[3] / (2.0 * (double)H * (double)W);
+  else if (kind == EBOS_COST_GRADMAG) data = -(acc_total(acc, 2, kAccGradSlots) / cnt);
+  const double tv = acc_total(acc, 3, kAccTvSlots) / (2.0 * (double)H * (double)W);
   loss[0] = (T)(data_scale * data + tv_scale * tv);
 }
 
@@ -335,11 +548,11 @@ __device__ __forceinline__ void finalize_loss(const FinalizeArgs& f) {
   const double cnt = f.omit ? (double)(f.Hp - 2) * (double)(f.Wp - 2) : (double)f.Hp * (double)f.Wp;
   double data = 0.0;
   if (f.kind == EBOS_COST_VARIANCE) data = -((f.acc[1] - f.acc[0] * f.acc[0] / cnt) / (cnt - 1.0));
-  else if (f.kind == EBOS_COST_GRADMAG) data = -(f.acc[2] / cnt);
-  const double tv = f.acc[3] / (2.0 * (double)f.H * (double)f.W);
+  else if (f.kind == EBOS_COST_GRADMAG) data = -(acc_total(f.acc, 2, kAccGradSlots) / cnt);
+  const double tv = acc_total(f.acc, 3, kAccTvSlots) / (2.0 * (double)f.H * (double)f.W);
   reinterpret_cast<T*>(f.loss)[0] = (T)(f.data_scale * data + f.tv_scale * tv);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) f.acc[i] = 0.0;
+  for (int i = 0; i < EBOS_ACC_DOUBLES; ++i) f.acc[i] = 0.0;
 }
 
 // step_mode 0: `step_host`;  1: *step_dev + 1 (bumped afterwards by k_adam_bump);  2: *step_dev (already advanced)
@@ -408,9 +621,18 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
   } else if (kind == EBOS_COST_GRADMAG) {
     if (!grad_iwe) { set_error("ebos_iwe_cost: GRADMAG needs grad_iwe"); return EBOS_ERR_BAD_ARG; }
     const T coef = (T)(-2.0 * scale / (8.0 * cnt));
-    const int n_tiles = ((Wp + GTW - 1) / GTW) * ((Hp + GTH - 1) / GTH);
-    const int grid = std::max(1, std::min(n_tiles, sm_count() * 4));
-    k_gradmag<T><<<grid, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe);
+    static const bool legacy = getenv("EBOS_GRADMAG_LEGACY") != nullptr;   // the tiled kernel, kept for A/B runs
+    if (legacy) {
+      const int n_tiles = ((Wp + GTW - 1) / GTW) * ((Hp + GTH - 1) / GTH);
+      const int grid = std::max(1, std::min(n_tiles, sm_count() * 4));
+      k_gradmag<T><<<grid, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe);
+    } else {
+      const bool has_fast = Hp >= 7 && Wp >= 7;
+      const int64_t n_frame = has_fast ? (int64_t)6 * Wp + (int64_t)6 * (Hp - 6) : (int64_t)Hp * Wp;
+      const int n_frame_ctas = (int)((n_frame + 255) / 256);
+      const int n_tiles = has_fast ? ((Wp + GM_TW - 1) / GM_TW) * ((Hp + GM_TH - 1) / GM_TH) : 0;
+      k_gradmag_sep<T><<<n_frame_ctas + n_tiles, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe, n_frame_ctas, n_tiles);
+    }
   } else if (kind != EBOS_COST_NONE) {
     set_error("ebos_iwe_cost: unknown cost kind");
     return EBOS_ERR_BAD_ARG;
@@ -430,6 +652,19 @@ int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, do
     return EBOS_ERR_BAD_ARG;
   }
   const T coef = (T)(tv_scale / (2.0 * (double)H * (double)W));
+  if constexpr (sizeof(T) == 4) {
+    static const bool legacy = getenv("EBOS_TV_LEGACY") != nullptr;   // the one-quad-per-thread kernel, for A/B runs
+    if (!legacy && !weights && W % 4 == 0 && W >= 12 && H >= 5 &&
+        ((reinterpret_cast<size_t>(flow) | reinterpret_cast<size_t>(dflow)) & 15) == 0) {
+      const int64_t n_frame = (int64_t)4 * W + (int64_t)8 * (H - 4);
+      const int n_frame_ctas = (int)((n_frame + 127) / 128);
+      const int fast_gx = ((W >> 2) + 63) / 64, fast_gy = (H - 4 + 2 * TV_ROWS - 1) / (2 * TV_ROWS);
+      const dim3 mgrid(n_frame_ctas + fast_gx * fast_gy, 2);
+      k_flow_tv_march<<<mgrid, 128, 0, st>>>(flow, H, W, coef, acc, dflow, step_dev, n_frame_ctas, fast_gx);
+      EBOS_LAUNCH_CHECK("ebos_flow_tv");
+      return EBOS_OK;
+    }
+  }
   const dim3 grid(((W + 3) / 4 + 63) / 64, (H + 3) / 4, 2);
   if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, step_dev);
   else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, step_dev);
@@ -462,6 +697,7 @@ int ebos_iwe_cost(int kind, const void* iwe, int Hp, int Wp, int omit_boundary, 
   EBOS_CHECK_DTYPE(dtype, "ebos_iwe_cost");
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(acc, 0, 3 * sizeof(double), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(acc + kAccGradSlots, 0, kAccSpread * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_iwe_cost memset");
   if (dtype == EBOS_F64) return iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, scale, acc, (double*)grad_iwe, st);
   return iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, scale, acc, (float*)grad_iwe, st);
@@ -474,6 +710,7 @@ int ebos_flow_tv(const void* flow, const void* weights, int H, int W, double tv_
   cudaStream_t st = as_stream(stream);
   if (acc) {
     cudaError_t e = cudaMemsetAsync(acc + 3, 0, sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(acc + kAccTvSlots, 0, kAccSpread * sizeof(double), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_flow_tv memset");
   }
   if (dtype == EBOS_F64) return flow_tv_t<double>((const double*)flow, (const double*)weights, H, W, tv_scale, acc, (double*)dflow, st);
@@ -504,7 +741,7 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_value_and_grad: omit_boundary needs an image larger than 2x2");
   cudaStream_t st = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
+  cudaError_t e = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
   // fork: TV(flow) -> dflow on the auxiliary lane, concurrently with splat + cost on `st`
   AuxLane* lane = aux_lane();

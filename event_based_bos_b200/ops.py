@@ -320,7 +320,7 @@ class CmaxWorkspace:
         self.grad_iwe = torch.empty_like(self.iwe)
         self.dflow = torch.empty((2, H, W), dtype=self.dtype, device=device)
         self.loss = torch.zeros(1, dtype=self.dtype, device=device)
-        self.acc = torch.zeros(8, dtype=torch.float64, device=device)
+        self.acc = torch.zeros(_capi.ACC_DOUBLES, dtype=torch.float64, device=device)
 
 
 def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
@@ -400,7 +400,7 @@ class _IweCost(torch.autograd.Function):
         img = iwe.contiguous()
         Hp, Wp = img.shape
         code = dtype_code(img)
-        acc = torch.zeros(8, dtype=torch.float64, device=img.device)
+        acc = torch.zeros(_capi.ACC_DOUBLES, dtype=torch.float64, device=img.device)
         grad = torch.empty_like(img)
         loss = torch.empty(1, dtype=img.dtype, device=img.device)
         lib = _capi.load()
@@ -432,12 +432,12 @@ class _FlowTv(torch.autograd.Function):
     def forward(ctx, flow, weights):
         fl = flow.contiguous()
         _, H, W = fl.shape
-        acc = torch.zeros(8, dtype=torch.float64, device=fl.device)
+        acc = torch.zeros(_capi.ACC_DOUBLES, dtype=torch.float64, device=fl.device)
         dflow = torch.empty_like(fl)
         check(_capi.load().ebos_flow_tv(ptr(fl), ptr(weights), H, W, 1.0, dtype_code(fl), ptr(acc), ptr(dflow),
                                         current_stream()), "ebos_flow_tv")
         ctx.save_for_backward(dflow)
-        return (acc[3] / (2.0 * H * W)).to(fl.dtype)
+        return ((acc[3] + acc[24:40].sum()) / (2.0 * H * W)).to(fl.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):

@@ -157,7 +157,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
     g_iwe = torch.empty_like(iwe)
     dflow = torch.empty((2, H, W), dtype=window.dtype, device=dev)
     dtv = torch.empty_like(dflow)
-    acc = torch.zeros(8, dtype=torch.float64, device=dev)
+    acc = torch.zeros(_capi.ACC_DOUBLES, dtype=torch.float64, device=dev)
     loss = torch.zeros(1, dtype=window.dtype, device=dev)
     kind = ops.COST_KINDS[cost]
     lib = _capi.load()
@@ -170,6 +170,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
         check(lib.ebos_iwe_cost(kind, ptr(img), H + 2 * ph, W + 2 * pw, int(omit_boundary), data_weight, window.code,
                                 ptr(acc), ptr(g_iwe), st), "ebos_iwe_cost")
         acc[3] = 0.0
+        acc[24:40] = 0.0
         check(lib.ebos_loss_finalize(kind, ptr(acc), H + 2 * ph, W + 2 * pw, H, W, int(omit_boundary), data_weight, 0.0,
                                      window.code, ptr(loss), st), "ebos_loss_finalize")
         return loss.clone(), g_iwe
@@ -184,6 +185,6 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
     def regulariser(flow):
         check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight, window.code, ptr(acc), ptr(dtv), current_stream()),
               "ebos_flow_tv")
-        return (acc[3] * (tv_weight / (2.0 * H * W))).to(window.dtype).reshape(1), dtv
+        return ((acc[3] + acc[24:40].sum()) * (tv_weight / (2.0 * H * W))).to(window.dtype).reshape(1), dtv
 
     return EventShardedObjective(splat, cost_fn, backward, regulariser if tv_weight else None)

@@ -54,6 +54,11 @@ extern "C" {
 #define EBOS_DIR_FRAC 2   /* min t + frac * (max t - min t); 'middle'=0.5, 'before'=-1, 'after'=2 */
 
 /* data objectives (not present upstream) */
+/* doubles in the `acc` scratch of the cost / TV / fused entries: [0] sum(IWE) [1] sum(IWE^2), gradient-magnitude
+ * sum in [2] + [8..23], TV sum in [3] + [24..39] (per-CTA partial sums are spread over 16 slots: same-address
+ * atomics serialise in L2).  Read the totals through ebos_loss_finalize. */
+#define EBOS_ACC_DOUBLES 40
+
 #define EBOS_COST_NONE 0
 #define EBOS_COST_VARIANCE 1  /* L = -var(IWE), unbiased */
 #define EBOS_COST_GRADMAG 2   /* L = -mean((Sobel_x/8)^2 + (Sobel_y/8)^2), replicate border */
@@ -127,7 +132,7 @@ EBOS_API int ebos_iwe_splat_bwd(const void* events, int64_t n, int batch, int Hp
  *    splat (warp+vote fused, warped events never materialised) -> cost -> backward -> [Adam].
  * dtype EBOS_F32 is the fast path; EBOS_F64 is the dtype the reference's solvers run in
  * (src/solver/patch_eklt_pyramid2.py:253) and is used for solve-level parity.  All planes, the flow,
- * the events and the loss share `dtype`; `acc` is always double[8].
+ * the events and the loss share `dtype`; `acc` is always double[EBOS_ACC_DOUBLES].
  * ---------------------------------------------------------------------------------------- */
 
 /* Bytes of the caller-owned window buffer / of the temporary workspace used by prepare. */
@@ -160,7 +165,7 @@ EBOS_API int ebos_window_splat(const void* window, int64_t n, int flags, const v
                       int pad_w, int dtype, void* iwe, void* stream);
 
 /* Data objective on the IWE: value and gradient scaled by `scale`.
- * acc: double[8] device scratch (entries 0..2 zeroed by this call).  grad_iwe: [Hp,Wp], required for
+ * acc: double[EBOS_ACC_DOUBLES] device scratch (the data-cost entries are zeroed by this call).  grad_iwe: [Hp,Wp], required for
  * GRADMAG; for VARIANCE it may be NULL -- the backward then derives dL/dIWE = c*(IWE-mean) on the
  * fly from `acc` (pass the same `acc` and `iwe` to ebos_window_backward). */
 EBOS_API int ebos_iwe_cost(int kind, const void* iwe, int Hp, int Wp, int omit_boundary, double scale, int dtype,
@@ -169,7 +174,7 @@ EBOS_API int ebos_iwe_cost(int kind, const void* iwe, int Hp, int Wp, int omit_b
 /* ImageGradient.calculate_torch -- src/costs/image_gradient.py:60-75 (TV-L1 of the flow with
  * torch.gradient semantics) value and gradient:  dflow = tv_scale * dTV/dflow  (OVERWRITES dflow,
  * so it doubles as the zero-fill of the gradient buffer; tv_scale = 0 just zeroes).
- * weights: NULL (1.0) or [H,W].  acc[3] (zeroed by this call) accumulates the un-normalised |.| sum. */
+ * weights: NULL (1.0) or [H,W].  the TV entries of acc (zeroed by this call) accumulate the un-normalised |.| sum. */
 EBOS_API int ebos_flow_tv(const void* flow, const void* weights, int H, int W, double tv_scale, int dtype, double* acc,
                  void* dflow, void* stream);
 
@@ -186,7 +191,7 @@ EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int
 
 /* One complete objective evaluation: splat -> cost -> TV -> backward -> loss, stream-ordered,
  * no host sync (CUDA-graph capturable).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W],
- * loss [1], acc double[8]. */
+ * loss [1], acc double[EBOS_ACC_DOUBLES]. */
 EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W,
                              int pad_h, int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
@@ -195,7 +200,7 @@ EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, 
 /* One complete SOLVER iteration (src/solver/patch_eklt_pyramid2.py:267-285: zero_grad / loss / backward / step):
  * ebos_cmax_value_and_grad followed by the Adam update of `flow`, as six graph nodes
  *   [IWE memset] [TV + step counter | splat] [cost] [backward] [Adam + loss + accumulator reset].
- * `acc` (double[8]) must be ZERO on entry and is left zero on exit; `step_dev` (int32[1]) counts the
+ * `acc` (double[EBOS_ACC_DOUBLES]) must be ZERO on entry and is left zero on exit; `step_dev` (int32[1]) counts the
  * iterations done (0 before the first call) and is advanced by the call; `loss` receives this iteration's
  * objective value (before the update).  Capture once in a CUDA graph, replay n_iter times. */
 EBOS_API int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flow, int H, int W, int pad_h,

@@ -230,6 +230,39 @@ def test_cost_and_tv_kernels_vs_golden(golden, ops):
             assert rel_err(b.grad.cpu().numpy(), a.grad.numpy()) <= REL, (cost, omit)
 
 
+@pytest.mark.parametrize("shape", [(2, 2), (3, 9), (6, 40), (7, 7), (8, 12), (37, 53), (40, 64), (67, 132), (96, 260)])
+def test_plane_kernels_on_awkward_shapes(ops, shape):
+    """The separable gradient-magnitude kernel (fast interior + exact 3-pixel frame; images without an interior are
+    all frame) and the row-marching TV kernel (lean interior quads, general edges, ragged row strips) against the
+    oracle, fp32 and fp64, both crops, with ties (constant regions give sign(0) terms in the TV)."""
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    img = rng.standard_normal((H, W)) * 3 + 1
+    flow = rng.uniform(-3, 3, (2, H, W))
+    flow[:, : H // 2, : W // 3] = 0.25     # plateau: exact ties in the TV signs
+    for dt, tol in ((torch.float32, REL), (torch.float64, 1e-12)):
+        for omit in (False, True):
+            if omit and (H < 3 or W < 3):
+                continue
+            a = torch.from_numpy(img).double().requires_grad_()
+            ref = spec.gradient_magnitude(a, omit)
+            ref.backward()
+            b = torch.from_numpy(img).to(dt).cuda().requires_grad_()
+            out = ops.iwe_cost(b, "gradient_magnitude", omit)
+            out.backward()
+            assert abs(float(out) - float(ref)) <= tol * abs(float(ref)), (shape, dt, omit)
+            assert rel_err(b.grad.cpu().numpy(), a.grad.numpy()) <= tol, (shape, dt, omit)
+        f = torch.from_numpy(flow).to(dt)
+        fr = f.clone().double().requires_grad_()
+        ref = spec.total_variation(fr, 1.0)
+        ref.backward()
+        fg = f.cuda().requires_grad_()
+        out = ops.flow_total_variation(fg)
+        out.backward()
+        assert abs(float(out) - float(ref)) <= max(tol, 2e-6) * abs(float(ref)), (shape, dt)
+        assert rel_err(fg.grad.cpu().numpy(), fr.grad.numpy()) <= tol, (shape, dt)
+
+
 def test_adam_kernel_vs_torch(ops):
     torch.manual_seed(0)
     p = torch.randn(2, 33, 47)
