@@ -1223,8 +1223,8 @@ __device__ __forceinline__ void bwd_group4(const EventBlock<float, 4, HAS_W, PAC
   }
 }
 
-template <int GSRC, bool HAS_W, bool PACKED, int NG>
-__global__ void __launch_bounds__(256, 5)
+template <int GSRC, bool HAS_W, bool PACKED, int NG, int MINB = 5>
+__global__ void __launch_bounds__(256, MINB)
 k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
             const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h, int pad_w,
             const float* __restrict__ g, const double* __restrict__ acc, int omit, double scale,
@@ -1630,6 +1630,15 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
       const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
       float* fo = reinterpret_cast<float*>(dflow);
 #define EBOS_BG(G, WGT, P, NGV) k_win_bwd_g<G, WGT, P, NGV><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+#define EBOS_BGO(G, WGT, P, NGV, O) k_win_bwd_g<G, WGT, P, NGV, O><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+      static const int bocc = env_int("EBOS_BOCC");   // experiment knob (unweighted packed gradient-plane kernel only)
+      if (bocc && !affine && !has_weight && packed) {
+        if (bocc == 4 && ng == 2) EBOS_BGO(0, false, true, 2, 4); else if (bocc == 4) EBOS_BGO(0, false, true, 4, 4);
+        else if (bocc == 3 && ng == 2) EBOS_BGO(0, false, true, 2, 3); else if (bocc == 3) EBOS_BGO(0, false, true, 4, 3);
+        else if (bocc == 6 && ng == 2) EBOS_BGO(0, false, true, 2, 6); else EBOS_BGO(0, false, true, 4, 6);
+        EBOS_LAUNCH_CHECK("ebos_window_backward(grouped, occ)");
+        return EBOS_OK;
+      }
 #define EBOS_BG_N(G, WGT, P) do { if (ng == 2) EBOS_BG(G, WGT, P, 2); else if (ng == 8) EBOS_BG(G, WGT, P, 8); else EBOS_BG(G, WGT, P, 4); } while (0)
 #define EBOS_BG_W(G) do { if (has_weight) { if (packed) EBOS_BG_N(G, true, true); else EBOS_BG_N(G, true, false); } \
                           else { if (packed) EBOS_BG_N(G, false, true); else EBOS_BG_N(G, false, false); } } while (0)

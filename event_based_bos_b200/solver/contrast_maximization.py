@@ -8,7 +8,7 @@ the operators `Warp.warp_event("dense-flow")` + `EventImageConverter.create_iwe(
 backward / step; because `best_x` aliases the optimised leaf upstream, the FINAL iterate is returned).
 """
 import logging
-from typing import Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -68,31 +68,80 @@ class ContrastMaximizationDense(SolverBase):
     # ------------------------------------------------------------------------------------------
     def estimate(self, events: np.ndarray, *args, flow0: Optional[np.ndarray] = None, **kwargs) -> np.ndarray:
         """[n,4] events (x=row, y=col, t [s], p) -> flow [2,H,W] float64 (pixel displacement over the window)."""
-        H, W = self.orig_image_shape
+        return self._enqueue(events, flow0).cpu().numpy()
+
+    def estimate_many(self, windows: Sequence[np.ndarray], concurrency: int = 4,
+                      flow0: Optional[Sequence[Optional[np.ndarray]]] = None) -> List[np.ndarray]:
+        """Solve independent time windows (no inter-window state upstream) with up to `concurrency`
+        solves in flight on separate CUDA streams.  One small window (~0.5 M events) leaves most of the 148 SMs idle
+        -- its splat is ~120 CTAs -- so overlapping windows raises windows/s without touching the per-window result:
+        every window runs exactly the kernels and the order of `estimate` (results are identical)."""
+        n_slots = max(1, min(int(concurrency), len(windows)))
+        if not self.fused or any(len(w) >= (1 << 21) for w in windows):
+            n_slots = 1   # large windows fill the GPU on their own (and take the eager, non-graph path)
+        if n_slots == 1:
+            return [self.estimate(w, flow0=None if flow0 is None else flow0[i]) for i, w in enumerate(windows)]
+        streams = [torch.cuda.Stream(device=self._device) for _ in range(n_slots)]
+        results: List[Optional[np.ndarray]] = [None] * len(windows)
+        for first in range(0, len(windows), n_slots):
+            batch = list(range(first, min(first + n_slots, len(windows))))
+            plans = []
+            for slot, idx in enumerate(batch):
+                with torch.cuda.stream(streams[slot]):
+                    x0 = self._upload_flow0(None if flow0 is None else flow0[idx])
+                    plans.append((x0,) + self._plan_fused(self._upload_events(windows[idx]), x0))
+            # interleaved issue: the launch queue is finite, so queueing one window's whole solve first would stall the
+            # host until it drains and the other streams would stay empty
+            for call in range(max(p[2] for p in plans)):
+                for slot, (x0, advance, n_calls) in enumerate(plans):
+                    if call < n_calls:
+                        with torch.cuda.stream(streams[slot]):
+                            advance()
+            outs = []
+            for slot, (x0, _, _) in enumerate(plans):
+                with torch.cuda.stream(streams[slot]):
+                    outs.append(self._finish(x0))
+            for slot, idx in enumerate(batch):
+                streams[slot].synchronize()
+                results[idx] = outs[slot].cpu().numpy()
+        return results
+
+    def _upload_events(self, events: np.ndarray) -> torch.Tensor:
         from .. import _capi
 
         _capi.require_device()
         # Absolute sensor time -> window-relative IN FLOAT64, before the cast to the solver dtype (the fp32 ulp at
         # t = 10 s is 1 us; see utils.rebase_time).  Done on the device: one H2D copy of the raw float64 events.
-        raw = torch.from_numpy(np.ascontiguousarray(events, dtype=np.float64)).to(self._device)
+        raw = torch.from_numpy(np.ascontiguousarray(events, dtype=np.float64)).to(self._device, non_blocking=True)
         if raw.shape[0]:
             raw[:, 2] -= raw[:, 2].min()
-        ev = raw.to(self._dtype)
+        return raw.to(self._dtype)
+
+    def _upload_flow0(self, flow0: Optional[np.ndarray]) -> torch.Tensor:
+        H, W = self.orig_image_shape
         x0 = torch.zeros((2, H, W), dtype=self._dtype, device=self._device)
         if flow0 is not None:
             x0.copy_(torch.from_numpy(np.asarray(flow0)).to(self._dtype))
-        self.history = {"loss": []}
-        if self.fused:
-            flow = self._solve_fused(ev, x0)
-        else:
-            flow = self._solve_operators(ev, x0)
-        # ROI mask and float64 conversion on the device, one D2H copy of the result
+        return x0
+
+    def _finish(self, flow: torch.Tensor) -> torch.Tensor:
+        """ROI mask and float64 conversion on the device (one D2H copy of the result follows)."""
+        H, W = self.orig_image_shape
         out = flow.detach().to(torch.float64)
         if (self.crop_xmin, self.crop_ymin, self.crop_xmax, self.crop_ymax) != (0, 0, H, W):
             mask = torch.zeros((H, W), dtype=torch.float64, device=out.device)
             mask[self.crop_xmin:self.crop_xmax, self.crop_ymin:self.crop_ymax] = 1.0
             out = out * mask
-        return out.cpu().numpy()
+        return out
+
+    def _enqueue(self, events: np.ndarray, flow0: Optional[np.ndarray] = None) -> torch.Tensor:
+        """Queue one solve on the current CUDA stream; returns the device tensor the result will be in."""
+        ev = self._upload_events(events)
+        x0 = self._upload_flow0(flow0)
+        self.history = {"loss": []}
+        self._hist_dev = None
+        flow = self._solve_fused(ev, x0) if self.fused else self._solve_operators(ev, x0)
+        return self._finish(flow)
 
     def _roi_mask(self) -> np.ndarray:
         mask = np.zeros(self.orig_image_shape)
@@ -100,7 +149,9 @@ class ContrastMaximizationDense(SolverBase):
         return mask[None]
 
     # -- fused CUDA path ---------------------------------------------------------------------------
-    def _solve_fused(self, ev: torch.Tensor, x0: torch.Tensor) -> torch.Tensor:
+    def _plan_fused(self, ev: torch.Tensor, x0: torch.Tensor) -> Tuple[Callable[[], None], int]:
+        """Prepare one window for the fused path on the current stream.  Returns (advance, n_calls): calling
+        `advance()` n_calls times on that stream performs exactly n_iter solver iterations on `x0` in place."""
         H, W = self.orig_image_shape
         window = ops.PreparedWindow(ev, (H, W), self.warp_direction, self.normalize_t_in_batch, dtype=self._dtype)
         pad = (self.padding, self.padding)
@@ -108,43 +159,56 @@ class ContrastMaximizationDense(SolverBase):
         m, v = torch.zeros_like(x0), torch.zeros_like(x0)
         step_dev = torch.zeros(1, dtype=torch.int32, device=x0.device)
         hist = torch.zeros(max(self.n_iter, 1), dtype=self._dtype, device=x0.device) if self.store_history else None
+        self._hist_dev = hist
+        count = [0]
 
         def iteration():
             # one C call: TV | splat -> cost -> backward -> Adam (+ loss, accumulator reset), six graph nodes
             ops.cmax_adam_iteration(window, x0, m, v, step_dev, ws, self.data_cost, self.data_weight, self.tv_weight,
                                     None, self.omit_boundary, self.lr)
+            if hist is not None:
+                hist[count[0]].copy_(ws.loss[0])
+                count[0] += 1
 
         # CUDA graph: worth its capture/instantiate cost when iterations are short (launch-bound); for large windows
         # (>= ~2 Mi events, >100 us of GPU work per iteration) eager launches run ahead of the GPU anyway.
-        if self.use_cuda_graph and not self.store_history and self.n_iter > 2 and window.n < (1 << 21):
-            # One captured iteration replayed n_iter times; the Adam step counter lives on the device.
-            backup = x0.clone()
-
-            def reset():
-                x0.copy_(backup)
-                m.zero_()
-                v.zero_()
-                step_dev.zero_()
-                ws.acc.zero_()
-
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                iteration()  # warm-up outside capture (module loading, allocator)
-            torch.cuda.current_stream().wait_stream(side)
-            reset()          # the solve must perform exactly n_iter updates
+        if not (self.use_cuda_graph and not self.store_history and self.n_iter > 2 and window.n < (1 << 21)):
+            return iteration, self.n_iter
+        # `unroll` captured iterations per graph, replayed n_iter / unroll times; the Adam step counter lives on the
+        # device.  Fewer, longer graph launches keep the host ahead when several solves are in flight.
+        unroll = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if self.n_iter % u == 0)
+        backup = x0.clone()
+        # capture_begin/capture_end on a side stream instead of `with torch.cuda.graph(...)`: the context manager
+        # synchronises the whole device on entry, which would serialise the concurrent solves of estimate_many
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=x0.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            iteration()  # warm-up outside capture (module loading)
+            x0.copy_(backup)   # the solve must perform exactly n_iter updates
+            m.zero_()
+            v.zero_()
+            step_dev.zero_()
+            ws.acc.zero_()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            graph.capture_begin()
+            for _ in range(unroll):
                 iteration()
-            for _ in range(self.n_iter):
-                graph.replay()
-        else:
-            for it in range(self.n_iter):
-                iteration()
-                if hist is not None:
-                    hist[it].copy_(ws.loss[0])
-        if hist is not None:
-            self.history["loss"] = hist.cpu().tolist()
+            graph.capture_end()
+        cur.wait_stream(side)
+        keep = (window, ws, m, v, step_dev, backup)   # buffers the graph points into
+
+        def replay(_keep=keep):
+            graph.replay()
+
+        return replay, self.n_iter // unroll
+
+    def _solve_fused(self, ev: torch.Tensor, x0: torch.Tensor) -> torch.Tensor:
+        advance, n_calls = self._plan_fused(ev, x0)
+        for _ in range(n_calls):
+            advance()
+        if self._hist_dev is not None:
+            self.history["loss"] = self._hist_dev.cpu().tolist()
         return x0
 
     # -- operator-level path: the reference composition with torch autograd + torch.optim.Adam ------------
