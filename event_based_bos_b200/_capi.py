@@ -62,6 +62,10 @@ SIGNATURES = {
                                          c_void_p]),
     "ebos_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
                                c_int, c_int, c_void_p]),
+    "ebos_ingest_workspace_bytes": (c_size_t, [c_int64]),
+    "ebos_ingest_raw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int64,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ebos_time_to_index": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "ebos_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
                                      c_double, c_void_p, c_int, c_void_p]),
 }

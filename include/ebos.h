@@ -219,6 +219,26 @@ EBOS_API int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* 
 EBOS_API int ebos_adam_step_graph(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr,
                          double beta1, double beta2, double eps, int32_t* step_dev, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Event ingestion: raw sensor arrays (x:int16 sensor column, y:int16 sensor row, t:int32 us,
+ * p:bool as uint8; 9 B/event, time ordered -- the `raw_events` datasets of src/data_loader/ccs.py:50-69) ->
+ * the reference's event rows [n,4] = (row = y, col = x, t_us / 1e6, p) of CcsDataLoader.load_event
+ * (src/data_loader/ccs.py:288-296), optionally through the CROP filter row0 <= row < row1, col0 <= col < col1
+ * (order preserved, coordinates not shifted: src/utils/event_utils.py:109-129, src/solver/base.py:123-139).
+ * All pointers are device pointers, already offset to the first event of the window; n < 2^31.
+ * rebase != 0: t = (t_us - t_origin_us) / 1e6 (integer subtraction first; required for useful fp32 rows);
+ * rebase == 0 with EBOS_F64 reproduces the loader's rows bit for bit.
+ * events_out: [n,4] of dtype (16-byte aligned; the first *n_kept rows are written), n_kept: device int64.
+ * workspace: >= ebos_ingest_workspace_bytes(n) bytes (only needed when crop != 0). */
+EBOS_API size_t ebos_ingest_workspace_bytes(int64_t n);
+EBOS_API int ebos_ingest_raw(const int16_t* x, const int16_t* y, const int32_t* t_us, const uint8_t* p, int64_t n, int crop,
+                    int row0, int row1, int col0, int col1, int64_t t_origin_us, int rebase, int dtype, void* events_out,
+                    int64_t* n_kept, void* workspace, size_t workspace_bytes, void* stream);
+
+/* CcsDataLoader.time_to_index (src/data_loader/ccs.py:345-357): *index_out = searchsorted(t_us / 1e6, time) - 1
+ * (left side, float64 comparison like the loader's `_time_cache`); index_out: device int64. */
+EBOS_API int ebos_time_to_index(const int32_t* t_us, int64_t n, double time, int64_t* index_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
