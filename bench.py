@@ -315,6 +315,32 @@ def run_fused(args, rank, world, local):
         barrier(world)
         e2e_ms = max_over_ranks(cuda_time_ms(e2e_step, max(3, min(args.steps, 10))), world)
 
+        # the same evaluation fed with the RAW sensor stream (x,y int16, t int32 us, p bool: 9 B/event) through the
+        # ingestion path: H2D of the compact arrays, rows built on the device, then prepare + evaluation + D2H
+        from event_based_bos_b200 import _capi as capi
+        evn = ev_host.numpy()
+        raw_host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+                    (evn[:, 1].astype(np.int16), evn[:, 0].astype(np.int16),
+                     np.round(evn[:, 2].astype(np.float64) * 1e6).astype(np.int32), evn[:, 3].astype(np.uint8))]
+        rows_dev = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        cnt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        t0_us = int(raw_host[2][0])
+
+        def e2e_raw_step():
+            x, y, t, pp = (a.to(dev, non_blocking=True) for a in raw_host)
+            f = flow_host.to(dev, non_blocking=True)
+            capi.check(lib.ebos_ingest_raw(p(x), p(y), p(t), p(pp), n, 0, 0, 0, 0, 0, t0_us, 1, 0, p(rows_dev), p(cnt_dev), 0, 0,
+                                           cur()), "ebos_ingest_raw")
+            win = ops.PreparedWindow(rows_dev, (H, W), "first", True, validate=False, allow_packed=not args.no_packed)
+            loss, grad = ops.cmax_value_and_grad(win, f, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
+            loss_host.copy_(loss, non_blocking=True)
+            grad_host.copy_(grad, non_blocking=True)
+
+        for _ in range(2):
+            e2e_raw_step()
+        barrier(world)
+        e2e_raw_ms = max_over_ranks(cuda_time_ms(e2e_raw_step, max(3, min(args.steps, 10))), world)
+
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()
@@ -346,7 +372,11 @@ def run_fused(args, rank, world, local):
     if e2e_ms is not None:
         line["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "events/s", "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": 16 * n + 2 * P_BYTES, "d2h_bytes_per_step": 2 * P_BYTES + 4,
-                       "includes": "H2D raw events+flow, window preparation (sort), fused evaluation, D2H loss+gradient"}
+                       "includes": "H2D [N,4] fp32 event rows + flow, window preparation (sort), fused evaluation, D2H loss+gradient",
+                       "raw_stream": {"value": world * n / (e2e_raw_ms * 1e-3), "unit": "events/s", "ms_per_step": e2e_raw_ms,
+                                      "h2d_bytes_per_step": 9 * n + 2 * P_BYTES,
+                                      "includes": "same, fed with the raw sensor stream (int16 x,y; int32 t; bool p = 9 B/event) "
+                                                  "through ebos_ingest_raw"}}
     if not args.no_cpu:
         v, cms, cores = cpu_reference_fused(args.cpu_events, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",

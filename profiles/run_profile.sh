@@ -5,8 +5,9 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
+# (k_adam only appears in the per-kernel timing section of bench.py; the solver uses it every iteration)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches.log 2>&1
-for K in k_win_splat k_win_bwd k_flow_tv k_gradmag; do
+for K in k_tile_splat_d k_win_bwd_g k_flow_tv_march k_gradmag_sep k_adam; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o gpurun_out/${TAG}_${K} -f $BENCH > gpurun_out/${TAG}_${K}.log 2>&1
 done
 ls -la gpurun_out | tail -12
