@@ -316,6 +316,37 @@ def test_full_size_properties(ops):
     assert abs(fd - an) <= 0.05 * abs(an)
 
 
+def test_dense_window_fixed_point_splat_at_benchmark_size(ops):
+    """1280x720, 16 Mi events (the benchmark window: 18 events per pixel -> the fixed-point shared-memory tile kernel
+    is the default).  Size-independent properties: with zero flow the IWE is the exact event histogram; run-to-run
+    bit identity (integer accumulation); agreement with the deterministic operator-level composition (which is
+    bit-exact to the reference) within the atomic-mode tolerance; mass conservation; order invariance; flows far
+    larger than the window halo (every tap takes the global fp32 path)."""
+    H, W, n = 720, 1280, 1 << 24
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=1)).cuda()
+    win = ops.PreparedWindow(ev, (H, W), "first", True)
+    assert win.packed and n >= 16 * H * W
+    zero = torch.zeros((2, H, W), device="cuda")
+    hist = torch.bincount(ev[:, 0].long() * W + ev[:, 1].long(), minlength=H * W).reshape(H, W).float()
+    assert torch.equal(ops.window_splat(win, zero), hist)
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=1)).cuda()
+    iwe = ops.window_splat(win, flow).clone()
+    assert torch.equal(ops.window_splat(win, flow), iwe)
+    det = ops.iwe_splat(ops.warp_dense_flow(ev, flow, (H, W), "first", True), (H, W), deterministic=True)
+    assert rel_err(iwe.cpu().numpy(), det.cpu().numpy()) <= REL
+    del det
+    padded = ops.window_splat(win, flow, (8, 8)).double().sum().item()
+    assert abs(padded - n) / n < 1e-6
+    perm = torch.randperm(n, device="cuda")
+    win2 = ops.PreparedWindow(ev[perm], (H, W), "first", True)
+    assert rel_err(ops.window_splat(win2, flow).cpu().numpy(), iwe.cpu().numpy()) <= 1e-6
+    del win2, perm
+    big = ops.window_splat(win, 10.0 * flow, (32, 32)).double().sum().item()   # |flow * dt| up to 30 px
+    assert abs(big - n) / n < 1e-6
+    loss, grad = ops.cmax_value_and_grad(win, flow, "gradient_magnitude", 1.0, 0.5)
+    assert torch.isfinite(grad).all() and torch.isfinite(loss).all()
+
+
 def test_fp64_value_and_grad_vs_reference_golden(golden, ops):
     """fp64 fused path vs the fp64 reference runs (goldens comp0-3): the reference's solver dtype."""
     for name in golden["comp_cases"]:
