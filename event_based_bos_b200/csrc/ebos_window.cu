@@ -815,9 +815,9 @@ k_tile_splat(const float* __restrict__ sx, const float* __restrict__ sy, const f
 //   |tap weight| <= 1 + 2e-6, so every partial sum of an item of cnt events is < 2^(ilog2(cnt)+1), and with
 //   S = 30 - ilog2(cnt) (<= 24) every int32 cell stays below 2^31 in magnitude.
 // Quantisation: one rounding of <= 2^-(S+1) per flushed tap sum (S >= 19 for 4080 events, i.e. <= 9.5e-7: the
-// size of ONE fp32 rounding of a cell value in [8, 16)); integer addition is exact and order independent, so the
-// IWE of this kernel is also run-to-run reproducible.  The window is then added to the global IWE with coalesced
-// fp32 REDs (windows of neighbouring tiles / items overlap).  Taps outside the window (|flow * dt| > kHalo) and
+// size of ONE fp32 rounding of a cell value in [8, 16)); integer addition is exact and order independent inside an
+// item.  The window is then added to the global IWE with coalesced fp32 REDs (windows of neighbouring tiles / items
+// overlap, so the last few additions per cell are fp32 and unordered like in the other kernels).  Taps outside the window (|flow * dt| > kHalo) and
 // non-finite events take the global fp32 path, so correctness never depends on the halo.  Items with fewer than
 // kWinMinEvents events skip the window (zero + flush of 1681 cells would cost more than their REDs).
 constexpr int kWinMinEvents = 1024;

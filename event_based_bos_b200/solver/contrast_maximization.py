@@ -63,12 +63,26 @@ class ContrastMaximizationDense(SolverBase):
         if self._opt_method != "Adam":
             raise ValueError(f"ContrastMaximizationDense supports optimizer.method = 'Adam', got {self._opt_method!r}")
         self.history: Dict[str, List[float]] = {"loss": []}
+        self._staging: Dict[int, torch.Tensor] = {}
+        self._hist_dev = None
         self.cost_func = costs.HybridCost("minimize", self.cost_with_weight, store_history=self.store_history)
 
     # ------------------------------------------------------------------------------------------
     def estimate(self, events: np.ndarray, *args, flow0: Optional[np.ndarray] = None, **kwargs) -> np.ndarray:
         """[n,4] events (x=row, y=col, t [s], p) -> flow [2,H,W] float64 (pixel displacement over the window)."""
-        return self._enqueue(events, flow0).cpu().numpy()
+        return self._download(self._enqueue(events, flow0))
+
+    def _download(self, out: torch.Tensor, slot: int = 0) -> np.ndarray:
+        """Device result -> numpy through a persistent pinned staging tensor (one per concurrency slot): a pageable
+        `.cpu()` of the 14.7 MB float64 flow took 7 ms, a quarter of a 500 k-event solve; allocating pinned memory per
+        call is worse (cudaHostAlloc synchronises the device)."""
+        stage = self._staging.get(slot)
+        if stage is None or stage.shape != out.shape or stage.dtype != out.dtype:
+            stage = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            self._staging[slot] = stage
+        stage.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(out.device).synchronize()
+        return stage.numpy().copy()
 
     def estimate_many(self, windows: Sequence[np.ndarray], concurrency: int = 4,
                       flow0: Optional[Sequence[Optional[np.ndarray]]] = None) -> List[np.ndarray]:
@@ -102,8 +116,8 @@ class ContrastMaximizationDense(SolverBase):
                 with torch.cuda.stream(streams[slot]):
                     outs.append(self._finish(x0))
             for slot, idx in enumerate(batch):
-                streams[slot].synchronize()
-                results[idx] = outs[slot].cpu().numpy()
+                with torch.cuda.stream(streams[slot]):
+                    results[idx] = self._download(outs[slot], slot)
         return results
 
     def _upload_events(self, events: np.ndarray) -> torch.Tensor:

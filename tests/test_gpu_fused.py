@@ -319,7 +319,7 @@ def test_full_size_properties(ops):
 def test_dense_window_fixed_point_splat_at_benchmark_size(ops):
     """1280x720, 16 Mi events (the benchmark window: 18 events per pixel -> the fixed-point shared-memory tile kernel
     is the default).  Size-independent properties: with zero flow the IWE is the exact event histogram; run-to-run
-    bit identity (integer accumulation); agreement with the deterministic operator-level composition (which is
+    agreement to fp32 rounding (integer accumulation inside an item, fp32 REDs between items); agreement with the deterministic operator-level composition (which is
     bit-exact to the reference) within the atomic-mode tolerance; mass conservation; order invariance; flows far
     larger than the window halo (every tap takes the global fp32 path)."""
     H, W, n = 720, 1280, 1 << 24
@@ -331,7 +331,7 @@ def test_dense_window_fixed_point_splat_at_benchmark_size(ops):
     assert torch.equal(ops.window_splat(win, zero), hist)
     flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=1)).cuda()
     iwe = ops.window_splat(win, flow).clone()
-    assert torch.equal(ops.window_splat(win, flow), iwe)
+    assert rel_err(ops.window_splat(win, flow).cpu().numpy(), iwe.cpu().numpy()) <= 1e-6
     det = ops.iwe_splat(ops.warp_dense_flow(ev, flow, (H, W), "first", True), (H, W), deterministic=True)
     assert rel_err(iwe.cpu().numpy(), det.cpu().numpy()) <= REL
     del det
