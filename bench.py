@@ -402,7 +402,7 @@ def run_solve(args, rank, world, local):
     for _ in range(max(1, min(args.warmup, 2))):
         slv.estimate(windows[0])
     if conc > 1:
-        slv.estimate_many(windows[:conc], concurrency=conc)   # warm-up of every stream slot (staging buffers, graphs)
+        slv.estimate_many(windows[:conc] * 2, concurrency=conc)   # warm-up of every stream slot (staging buffers)
     n_solves = max(args.steps, 4 * conc)
     batch = [windows[i % len(windows)] for i in range(n_solves)]
     barrier(world)
@@ -446,13 +446,69 @@ def run_solve(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
+def run_giant(args, rank, world, local):
+    """BASELINE config 5: ONE window of `--giant-events` events sharded by events over the ranks (strong scaling):
+    partial IWE -> NCCL all-reduce -> cost (redundant) -> partial dflow -> NCCL all-reduce (sharding.py)."""
+    from event_based_bos_b200 import sharding
+    from event_based_bos_b200.utils import synthetic_flow
+
+    n_total = args.giant_events
+    s0, s1 = sharding.shard_events(n_total, rank, world)
+    n = s1 - s0
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    ev = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    ev[:, 0] = torch.randint(0, H, (n,), device=dev, generator=gen).float()
+    ev[:, 1] = torch.randint(0, W, (n,), device=dev, generator=gen).float()
+    ev[:, 2] = torch.sort(torch.rand(n, device=dev, generator=gen) * (1.0 / 120.0))[0]
+    ev[:, 3] = torch.randint(0, 2, (n,), device=dev, generator=gen).float()
+    flow = torch.from_numpy(synthetic_flow((H, W), seed=0)).to(dev)
+    obj = sharding.cuda_event_sharded_objective(ev, (H, W), cost=COST, tv_weight=TV_WEIGHT)
+    del ev
+
+    def step():
+        obj.value_and_grad(flow)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier(world)
+    with ClockSampler(local) as clocks:
+        ms = max_over_ranks(cuda_time_ms(step, args.steps), world)
+        barrier(world)
+        # clock samples under load: a FIXED number of extra steps (the step holds collectives, so a time-based
+        # soak would let the ranks run different counts and dead-lock)
+        for _ in range(max(100, 4 * args.steps)):
+            step()
+        torch.cuda.synchronize()
+        barrier(world)
+    if rank != 0:
+        return
+    peak, peak_kind = measured_peak_gbs()
+    alg = 32 * n_total + world * 11 * P_BYTES   # the plane work is replicated on every rank
+    line = {"metric": "events/s fwd+bwd warp->IWE->cost", "value": n_total / (ms * 1e-3), "unit": "events/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"single giant window of {n_total} synthetic events sharded by events over {world} GPU(s), "
+                                   f"1280x720, fp32, {COST}+{TV_WEIGHT}*TV forward+backward; partial IWE and partial dflow "
+                                   f"all-reduced with NCCL" + ("" if world > 1 else " (no collective at 1 GPU)"),
+                       "events_total": n_total, "events_per_gpu": n, "l2_policy": "inputs larger than L2"},
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "whole evaluation (all kernels + collectives)",
+                         "achieved": alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / world / peak, "traffic": None, "peak_source": peak_kind},
+            "gpu_launches": 8 * args.steps}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fused", choices=["fused", "solve"])
+    ap.add_argument("--workload", default="fused", choices=["fused", "solve", "giant"])
+    ap.add_argument("--giant-events", type=int, default=1 << 27)
     ap.add_argument("--events", type=int, default=1 << 24)
     ap.add_argument("--cpu-events", type=int, default=1 << 22)
     ap.add_argument("--solve-events", type=int, default=500000)
@@ -468,7 +524,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     rank, world, local = dist_setup(args.gpus)
     try:
-        (run_solve if args.workload == "solve" else run_fused)(args, rank, world, local)
+        {"solve": run_solve, "giant": run_giant}.get(args.workload, run_fused)(args, rank, world, local)
     finally:
         if world > 1:
             import torch.distributed as dist
