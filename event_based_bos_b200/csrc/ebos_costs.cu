@@ -25,7 +25,11 @@ static_assert(kAccTvSlots + kAccSpread == EBOS_ACC_DOUBLES, "accumulator layout"
 // The TV term depends only on the flow, the splat only on events + flow: inside the fused evaluation
 // they run concurrently (fork/join on a cached auxiliary stream; the pattern is CUDA-graph capturable).
 // One non-blocking stream and two events per device are created on first use and kept for the process.
-struct AuxLane { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+struct AuxLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, cost_done = nullptr, fin_done = nullptr;
+  bool ok = false;
+};
 static AuxLane* aux_lane() {
   static AuxLane lanes[64];
   static std::mutex mu;
@@ -39,13 +43,15 @@ static AuxLane* aux_lane() {
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&L.cost_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&L.fin_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     L.ok = true;
   }
   return &L;
 }
 
 int window_splat_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
-                        int pad_w, int dtype, void* iwe, cudaStream_t st);
+                        int pad_w, int dtype, void* iwe, cudaStream_t st, bool zero_iwe);
 int window_backward_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                            int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
                            int omit_boundary, double scale, void* dflow, cudaStream_t st);
@@ -763,7 +769,10 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_value_and_grad: omit_boundary needs an image larger than 2x2");
   cudaStream_t st = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double), st);
+  // one memset node for the accumulators AND the IWE when the caller laid them out back to back (ops.CmaxWorkspace does)
+  const size_t iwe_bytes = (size_t)Hp * Wp * dtype_size(dtype);
+  const bool adjacent = reinterpret_cast<char*>(acc) + EBOS_ACC_DOUBLES * sizeof(double) == reinterpret_cast<char*>(iwe);
+  cudaError_t e = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double) + (adjacent ? iwe_bytes : 0), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
   // fork: TV(flow) -> dflow on the auxiliary lane, concurrently with splat + cost on `st`
   AuxLane* lane = aux_lane();
@@ -781,7 +790,7 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(join)");
   if (rc) return rc;
-  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st);
+  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent);
   if (rc) return rc;
   // variance: no gradient plane, the backward derives it from (iwe, acc)
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
@@ -790,15 +799,31 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   else
     rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
   if (rc) return rc;
+  // The scalar loss only needs the accumulators (complete once the cost kernel here and the TV kernel on the lane are
+  // done), not the backward: it is computed on the lane, concurrently with the backward.
+  auto finalize = [&](cudaStream_t s) {
+    if (dtype == EBOS_F64)
+      k_loss_finalize<double><<<1, 1, 0, s>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (double*)loss);
+    else
+      k_loss_finalize<float><<<1, 1, 0, s>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (float*)loss);
+  };
+  bool fin_on_lane = false;
+  if (lane && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
+      cudaStreamWaitEvent(lane->stream, lane->cost_done, 0) == cudaSuccess) {
+    finalize(lane->stream);
+    fin_on_lane = cudaEventRecord(lane->fin_done, lane->stream) == cudaSuccess;
+    if (!fin_on_lane) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(fin)");
+  }
   // join: the backward accumulates into the dflow the TV kernel wrote
   if (lane && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(wait)");
   rc = window_backward_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc,
                               omit_boundary, data_scale, dflow, st);
   if (rc) return rc;
-  if (dtype == EBOS_F64)
-    k_loss_finalize<double><<<1, 1, 0, st>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (double*)loss);
-  else
-    k_loss_finalize<float><<<1, 1, 0, st>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (float*)loss);
+  if (fin_on_lane) {
+    if (cudaStreamWaitEvent(st, lane->fin_done, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(wait fin)");
+  } else {
+    finalize(st);
+  }
   EBOS_LAUNCH_CHECK("ebos_cmax_value_and_grad");
   return EBOS_OK;
 }
@@ -833,7 +858,7 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st, step_dev);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(join)");
   if (rc) return rc;
-  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st);
+  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, true);
   if (rc) return rc;
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
   if (dtype == EBOS_F64)

@@ -1398,11 +1398,13 @@ static void apply_ablate_env() {
 
 template <typename T>
 int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int H, int W, int pad_h, int pad_w, T* iwe,
-                   cudaStream_t st) {
+                   cudaStream_t st, bool zero_iwe = true) {
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   apply_ablate_env();
-  cudaError_t e = cudaMemsetAsync(iwe, 0, (size_t)Hp * Wp * sizeof(T), st);
-  if (e != cudaSuccess) return cuda_fail(e, "ebos_window_splat memset");
+  if (zero_iwe) {   // (the fused entry zeroes the accumulators and an adjacent IWE plane with ONE memset node)
+    cudaError_t e = cudaMemsetAsync(iwe, 0, (size_t)Hp * Wp * sizeof(T), st);
+    if (e != cudaSuccess) return cuda_fail(e, "ebos_window_splat memset");
+  }
   if (n == 0) return EBOS_OK;
   const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
   if (packed && sizeof(T) != 4) { set_error("ebos_window_splat: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
@@ -1671,10 +1673,10 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
 
 // type-erased entry points used by ebos_costs.cu (fused iteration)
 int window_splat_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
-                        int pad_w, int dtype, void* iwe, cudaStream_t st) {
+                        int pad_w, int dtype, void* iwe, cudaStream_t st, bool zero_iwe) {
   if (dtype == EBOS_F64)
-    return window_splat_t<double>(window, n, flags, (const double*)flow, H, W, pad_h, pad_w, (double*)iwe, st);
-  return window_splat_t<float>(window, n, flags, (const float*)flow, H, W, pad_h, pad_w, (float*)iwe, st);
+    return window_splat_t<double>(window, n, flags, (const double*)flow, H, W, pad_h, pad_w, (double*)iwe, st, zero_iwe);
+  return window_splat_t<float>(window, n, flags, (const float*)flow, H, W, pad_h, pad_w, (float*)iwe, st, zero_iwe);
 }
 int window_backward_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                            int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
@@ -1750,7 +1752,7 @@ int ebos_window_splat(const void* window, int64_t n, int flags, const void* flow
                       int pad_w, int dtype, void* iwe, void* stream) {
   EBOS_REQUIRE(window && flow && iwe && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "ebos_window_splat: bad argument");
   EBOS_CHECK_DTYPE(dtype, "ebos_window_splat");
-  return window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, as_stream(stream));
+  return window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, as_stream(stream), true);
 }
 
 int ebos_window_backward(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,

@@ -316,11 +316,16 @@ class CmaxWorkspace:
         ph, pw = int(outer_padding[0]), int(outer_padding[1])
         self.H, self.W, self.ph, self.pw = H, W, ph, pw
         self.dtype = _float_dtype(dtype)
-        self.iwe = torch.empty((H + 2 * ph, W + 2 * pw), dtype=self.dtype, device=device)
+        # accumulators and IWE back to back in one allocation: the fused entry then zeroes both with one memset node
+        Hp, Wp = H + 2 * ph, W + 2 * pw
+        acc_bytes = _capi.ACC_DOUBLES * 8
+        item = torch.empty((), dtype=self.dtype).element_size()
+        self._acc_iwe = torch.zeros(acc_bytes + Hp * Wp * item, dtype=torch.uint8, device=device)
+        self.acc = self._acc_iwe[:acc_bytes].view(torch.float64)
+        self.iwe = self._acc_iwe[acc_bytes:].view(self.dtype).view(Hp, Wp)
         self.grad_iwe = torch.empty_like(self.iwe)
         self.dflow = torch.empty((2, H, W), dtype=self.dtype, device=device)
         self.loss = torch.zeros(1, dtype=self.dtype, device=device)
-        self.acc = torch.zeros(_capi.ACC_DOUBLES, dtype=torch.float64, device=device)
 
 
 def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
