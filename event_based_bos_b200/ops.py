@@ -356,6 +356,38 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
     return ws.loss, ws.dflow
 
 
+class CmaxGraph:
+    """One fused evaluation (`cmax_value_and_grad`) captured as a CUDA graph.
+
+    `replay()` re-runs the captured kernels on the CURRENT contents of `flow` (the same tensor object: update it in
+    place) and returns `(loss, dflow)` aliasing the workspace.  The C entry is capture-safe (no allocation, no host
+    synchronisation; its TV | splat fork/join becomes graph dependencies), and a replay costs one launch instead of
+    seven plus four cross-stream event operations."""
+
+    def __init__(self, window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
+                 data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
+                 omit_boundary: bool = False, outer_padding: Tuple[int, int] = (0, 0),
+                 workspace: Optional[CmaxWorkspace] = None):
+        self.window, self.flow = window, flow
+        self.ws = workspace or CmaxWorkspace(window.H, window.W, outer_padding, flow.device, window.dtype)
+        self._tvw = None if tv_weights is None else tv_weights.to(window.dtype).contiguous()
+        args = (window, flow, cost, data_weight, tv_weight, self._tvw, omit_boundary, outer_padding, self.ws)
+        cur = torch.cuda.current_stream(flow.device)
+        side = torch.cuda.Stream(device=flow.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            cmax_value_and_grad(*args)   # warm-up outside capture (module loading), also validates the arguments
+            self.graph = torch.cuda.CUDAGraph()
+            self.graph.capture_begin()
+            cmax_value_and_grad(*args)
+            self.graph.capture_end()
+        cur.wait_stream(side)
+
+    def replay(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.graph.replay()
+        return self.ws.loss, self.ws.dflow
+
+
 def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
                         step_dev: torch.Tensor, workspace: CmaxWorkspace, cost: str = "gradient_magnitude",
                         data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,

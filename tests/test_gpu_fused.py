@@ -189,6 +189,23 @@ def test_value_and_grad_vs_reference_golden(golden, ops):
         assert rel_err(grad.cpu().numpy(), golden[f"{name}/grad"]) <= (2 * REL if f32 else 5e-3), name
 
 
+def test_captured_evaluation_replays_on_updated_flow(ops):
+    """ops.CmaxGraph: the fused evaluation captured as a CUDA graph gives the eager result, and a replay after an
+    in-place flow update gives the eager result at the new flow."""
+    H, W, n = 64, 96, 30000
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=4)).cuda()
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=4)).cuda()
+    win = ops.PreparedWindow(ev, (H, W), "first", True)
+    cap = ops.CmaxGraph(win, flow, "gradient_magnitude", 1.0, 0.5)
+    for k in range(3):
+        l_e, g_e = ops.cmax_value_and_grad(win, flow, "gradient_magnitude", 1.0, 0.5)
+        l_e, g_e = l_e.clone(), g_e.clone()
+        l_c, g_c = cap.replay()
+        assert abs(float(l_c) - float(l_e)) <= 1e-6 * abs(float(l_e))
+        assert rel_err(g_c.cpu().numpy(), g_e.cpu().numpy()) <= 1e-5
+        flow.add_(0.1 * torch.sign(g_e))   # in place: the graph reads the same tensor
+
+
 def test_weighted_window_and_tv_weights(ops):
     H, W, n = 32, 48, 15000
     rng = np.random.default_rng(11)
