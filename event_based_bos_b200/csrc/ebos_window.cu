@@ -941,12 +941,15 @@ k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const
       const float qs = __int_as_float((127 + S) << 23);
       const int64_t start = (int64_t)it.y & ~(int64_t)3;
       for (int64_t base = start + (int64_t)threadIdx.x * 16; base < it.z; base += (int64_t)blockDim.x * 16) {
+        // software pipelining: the raw fields of group g+1 are requested before group g is processed (the first use
+        // of a freshly loaded group was the top stall site, ncu r01d)
+        EventBlock<float, 4, false, PACKED> e, nxt;
+        e.load_range(sx, sy, sd, nullptr, base, it.y, it.z);
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int64_t b = base + 4 * g;
           if (b >= it.z) break;
-          EventBlock<float, 4, false, PACKED> e;
-          e.load_range(sx, sy, sd, nullptr, b, it.y, it.z);
+          if (g < 3 && b + 4 < it.z) nxt.load_range(sx, sy, sd, nullptr, b + 4, it.y, it.z);
           e.finish(flow, W, hw);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -975,6 +978,8 @@ k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const
               splat_taps_global(iwe, Hp, Wp, r, c, w01.x, w01.y, w23.x, w23.y);
             }
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { e.x[j] = nxt.x[j]; e.y[j] = nxt.y[j]; e.d[j] = nxt.d[j]; }
         }
       }
       if (use_win) {
@@ -1233,13 +1238,22 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
   if (base >= n) return;
   const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
   BwdRun run{-1, make_float2(0.f, 0.f), INT_MIN, INT_MIN, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+  // Software pipelining of the event stream: the raw fields of group g+1 are requested before group g is processed.
+  // ncu r01e showed each group start exposing three dependent latencies (event load -> flow gather -> dL/dIWE
+  // gather); this removes the first (and longest, DRAM) one from every group but a thread's first.
+  EventBlock<float, 4, HAS_W, PACKED> cur, nxt;
+  cur.load_global(sx, sy, sd, sw, base, n);
+#pragma unroll
   for (int gi = 0; gi < NG; ++gi) {
     const int64_t b = base + 4 * gi;
     if (b >= n) break;
-    EventBlock<float, 4, HAS_W, PACKED> e;
-    e.load(sx, sy, sd, sw, b, n, flow, W, P.hw);
-    bwd_group4<GSRC, HAS_W, PACKED>(e, run, P, g, dflow);
+    if (gi + 1 < NG && b + 4 < n) nxt.load_global(sx, sy, sd, sw, b + 4, n);
+    if (g_ablate & 2) cur.finish_nogather(W, P.hw); else cur.finish(flow, W, P.hw);
+    bwd_group4<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow);
+    if (gi + 1 < NG) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cur.x[j] = nxt.x[j]; cur.y[j] = nxt.y[j]; cur.d[j] = nxt.d[j]; if (HAS_W) cur.wt[j] = nxt.wt[j]; }
+    }
   }
   if (run.ck >= 0) { red_add_nc(dflow + run.ck, run.s01.x); red_add_nc(dflow + P.hw + run.ck, run.s01.y); }
 }
@@ -1438,7 +1452,8 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       static const int occ_env = env_int("EBOS_QOCC");
-      const int occ = (occ_env == 4 || occ_env == 6) ? occ_env : 5;
+      // 4 CTAs/SM = 64 registers: with the prefetched next group the 48-register build spills (97 vs 75 us)
+      const int occ = (occ_env == 5 || occ_env == 6) ? occ_env : 4;
       const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
