@@ -1,3 +1,4 @@
+"""Measurement probes used during round 1 (run on the GPU box from the repo root: python profiles/tools/<name>.py)."""
 import os, sys, torch, numpy as np
 sys.path.insert(0, '/root/repo')
 from event_based_bos_b200 import ops

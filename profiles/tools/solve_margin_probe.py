@@ -1,10 +1,10 @@
 """Run-to-run spread of the fp32 solve against the reference goldens (not a test)."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 from test_gpu_fused import _run_solver, _rms
-g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_path_v1.npz"))
+g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "reference_path_v1.npz"))
 H, W, iters, lr, tvw = g["solve_init_f32/cfg"]
 a, b = [], []
 for i in range(12):

@@ -1,7 +1,7 @@
 """Host-side timing probe of the solver phases (not a test)."""
 import sys, time, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from event_based_bos_b200 import solver
 from event_based_bos_b200.utils import smooth_flow, synthetic_bos_events
 H, W = 720, 1280

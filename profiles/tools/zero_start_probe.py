@@ -1,3 +1,4 @@
+"""Measurement probes used during round 1 (run on the GPU box from the repo root: python profiles/tools/<name>.py)."""
 import sys, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 sys.path.insert(0, '/root/repo/tests')

@@ -415,7 +415,7 @@ def test_solver_final_flow_within_1e3_px(golden):
             if tag == "f32":
                 # against the fp64 reference the distance is dominated by the dtype, not by the implementation: the
                 # reference's own fp32 run is 7.9e-4 px from its fp64 run, ours 0.8e-3 .. 1.1e-3 px depending on the
-                # atomic order of the run (tests/solve_margin_probe.py; same-dtype distance above: <= 5.6e-4 px)
+                # atomic order of the run (profiles/tools/solve_margin_probe.py; same-dtype distance above: <= 5.6e-4 px)
                 ref_gap = _rms(golden["solve_init_f32/flow"], golden["solve_init_f64/flow"])
                 assert _rms(flow, golden["solve_init_f64/flow"]) <= ref_gap + 1e-3
             elif tag == "f64":
@@ -459,7 +459,7 @@ def test_solver_from_zero_start_is_ill_conditioned_but_consistent(golden):
     assert _rms(one, ref_one) <= 1e-9
     ref_gap = _rms(golden["solve_f32/flow"], golden["solve_f64/flow"])
     # Chaotic regime: which side of a tie a 1e-8 rounding difference falls on decides +-lr steps.  Measured on B200
-    # (tests/zero_start_probe.py): fp64 2.5e-3 px, fp32 0.18 px from the fp64 reference with the separable
+    # (profiles/tools/zero_start_probe.py): fp64 2.5e-3 px, fp32 0.18 px from the fp64 reference with the separable
     # gradient-magnitude kernel; 0.10 / 0.08 px with the earlier tiled kernel (different rounding, same algorithm);
     # the reference's own fp32 run: 0.016 px.  The gate proper is the tie-free start above (1e-3 px).
     for precision, factor in (("64", 10), ("32", 20)):
