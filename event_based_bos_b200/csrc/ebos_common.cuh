@@ -242,6 +242,33 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// The kernels of one evaluation form a chain (splat -> cost -> backward -> Adam) in which every link needs the
+// COMPLETE output of the previous one, so they cannot be fused; but a plane kernel is ~5 us of work inside ~9 us
+// of launch ramp and drain (ncu r01e: SMs active 54 % of the gradient-magnitude kernel's elapsed time).  With PDL
+// the next kernel's CTAs are scheduled while the last wave of the previous kernel drains, run their prologue (index
+// math, loads that do not depend on the predecessor) and block in pdl_wait() until the predecessor has completed
+// and its writes are visible.  Primaries call pdl_launch_dependents() at their start; launched without the
+// attribute (or after a non-kernel stream operation) both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // EBOS_NO_PDL=1 disables the launch attribute (A/B runs)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- prepared window ----------------------------------------------------------------------------
 // Layout of the caller-owned window buffer (ebos_window_bytes): a 256-byte header followed by
 // 256-byte aligned SoA arrays of the events sorted by origin pixel.

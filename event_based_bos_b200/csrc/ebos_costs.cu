@@ -254,6 +254,7 @@ k_gradmag_sep(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, doubl
               int n_frame_ctas, int n_tiles) {
   __shared__ T sI[GM_TH + 4][GM_TW + 4];
   __shared__ double sm[32];
+  pdl_launch_dependents();   // the backward may be scheduled while this grid drains (it waits before reading g)
   double part = 0.0;
   const bool has_fast = Hp >= 7 && Wp >= 7;
   if ((int)blockIdx.x < n_frame_ctas) {
@@ -271,11 +272,13 @@ k_gradmag_sep(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, doubl
       const int k = (int)(j % 6);
       r = 3 + (int)(j / 6); c = k < 3 ? k : Wp - 6 + k;
     }
+    pdl_wait();   // the IWE (and the zeroed accumulators) of the preceding splat
     if (r >= 0) gradmag_frame_pixel<T>(iwe, Hp, Wp, omit, coef, r, c, g, part);
   } else if ((int)blockIdx.x - n_frame_ctas < n_tiles) {
     const int tile = blockIdx.x - n_frame_ctas;
     const int tiles_x = (Wp + GM_TW - 1) / GM_TW;
     const int r0 = (tile / tiles_x) * GM_TH, c0 = (tile % tiles_x) * GM_TW;
+    pdl_wait();   // the IWE (and the zeroed accumulators) of the preceding splat
     // image tile with a 2-pixel halo (clamped reads: values outside the image are never used by the fast region)
     for (int i = threadIdx.x; i < (GM_TH + 4) * (GM_TW + 4); i += blockDim.x) {
       const int lr = i / (GM_TW + 4), lc = i - lr * (GM_TW + 4);
@@ -312,6 +315,8 @@ k_gradmag_sep(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, doubl
       }
     }
     part = (double)tpart;
+  } else {
+    pdl_wait();
   }
   part = block_sum(part, sm);
   if (threadIdx.x == 0) atomicAdd(acc + kAccGradSlots + (blockIdx.x & (kAccSpread - 1)), part);
@@ -571,6 +576,7 @@ __global__ void __launch_bounds__(256) k_adam(T* __restrict__ p, const T* __rest
   // shared memory (the first version had every thread do them: 163 instructions per float4, ncu r01e).  The first
   // loads of every thread are issued before the barrier so that their latency overlaps the pow().
   __shared__ T s_coef[2];
+  pdl_wait();   // dflow of the preceding backward (fused iteration: launched with the PDL attribute)
   auto coefs = [&]() {
     if (threadIdx.x == 0) {
       int step = step_host;
@@ -659,7 +665,9 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
       const int64_t n_frame = has_fast ? (int64_t)6 * Wp + (int64_t)6 * (Hp - 6) : (int64_t)Hp * Wp;
       const int n_frame_ctas = (int)((n_frame + 255) / 256);
       const int n_tiles = has_fast ? ((Wp + GM_TW - 1) / GM_TW) * ((Hp + GM_TH - 1) / GM_TH) : 0;
-      k_gradmag_sep<T><<<n_frame_ctas + n_tiles, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe, n_frame_ctas, n_tiles);
+      cudaError_t le = launch_pdl(k_gradmag_sep<T>, dim3(n_frame_ctas + n_tiles), dim3(256), st, iwe, Hp, Wp, omit, coef, acc,
+                                  grad_iwe, n_frame_ctas, n_tiles);
+      if (le != cudaSuccess) return cuda_fail(le, "ebos_iwe_cost(gradmag)");
     }
   } else if (kind != EBOS_COST_NONE) {
     set_error("ebos_iwe_cost: unknown cost kind");
@@ -872,12 +880,14 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   if (rc) return rc;
   const FinalizeArgs fin{1, kind, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, acc, loss};
   const int64_t np = (int64_t)2 * H * W;
+  cudaError_t le;
   if (dtype == EBOS_F64)
-    k_adam<double><<<adam_grid(np), 256, 0, st>>>((double*)flow, (const double*)dflow, (double*)exp_avg, (double*)exp_avg_sq,
-                                                   np, lr, beta1, beta2, eps, 0, step_dev, 2, fin);
+    le = launch_pdl(k_adam<double>, dim3(adam_grid(np)), dim3(256), st, (double*)flow, (const double*)dflow, (double*)exp_avg,
+                    (double*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, 2, fin);
   else
-    k_adam<float><<<adam_grid(np), 256, 0, st>>>((float*)flow, (const float*)dflow, (float*)exp_avg, (float*)exp_avg_sq, np,
-                                                  lr, beta1, beta2, eps, 0, step_dev, 2, fin);
+    le = launch_pdl(k_adam<float>, dim3(adam_grid(np)), dim3(256), st, (float*)flow, (const float*)dflow, (float*)exp_avg,
+                    (float*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, 2, fin);
+  if (le != cudaSuccess) return cuda_fail(le, "ebos_cmax_adam_iteration(adam)");
   EBOS_LAUNCH_CHECK("ebos_cmax_adam_iteration");
   return EBOS_OK;
 }

@@ -15,6 +15,11 @@ int cuda_fail(cudaError_t e, const char* where) {
   g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
   return EBOS_ERR_CUDA;
 }
+bool pdl_enabled() {
+  static const bool on = getenv("EBOS_NO_PDL") == nullptr;
+  return on;
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {

@@ -606,6 +606,7 @@ __global__ void __launch_bounds__(256, 6)
 k_win_splat_g(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
               const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h,
               int pad_w, float* __restrict__ iwe) {
+  pdl_launch_dependents();
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
   if (base >= n) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
@@ -924,6 +925,7 @@ k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const
   // persistent variant (static round-robin over items, window re-zeroed by the flush) was measured slower on B200
   // (78-114 vs 77 us at 16 Mi events: more live state -> spills, and the per-item barriers idle whole CTAs).
   __shared__ int win[kSH * kSW];
+  pdl_launch_dependents();   // the cost kernel may be scheduled while this grid drains (it waits before reading the IWE)
   const int n_items = hdr->n_items;
   if ((int)blockIdx.x >= n_items) return;
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
@@ -1234,8 +1236,10 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
             const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h, int pad_w,
             const float* __restrict__ g, const double* __restrict__ acc, int omit, double scale,
             float* __restrict__ dflow) {
+  pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
   if (base >= n) return;
+  if (GSRC == 1) pdl_wait();   // the variance coefficients come from the accumulators of the preceding cost kernel
   const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
   BwdRun run{-1, make_float2(0.f, 0.f), INT_MIN, INT_MIN, 0.f, 0.f, 0.f, 0.f};
   // Software pipelining of the event stream: the raw fields of group g+1 are requested before group g is processed.
@@ -1243,6 +1247,9 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
   // gather); this removes the first (and longest, DRAM) one from every group but a thread's first.
   EventBlock<float, 4, HAS_W, PACKED> cur, nxt;
   cur.load_global(sx, sy, sd, sw, base, n);
+  // PDL: everything above (and the event loads in flight) overlaps the drain of the preceding cost kernel; dL/dIWE
+  // and the dflow accumulation target are only touched below
+  if (GSRC == 0) pdl_wait();
 #pragma unroll
   for (int gi = 0; gi < NG; ++gi) {
     const int64_t b = base + 4 * gi;
@@ -1646,7 +1653,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
       const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
       float* fo = reinterpret_cast<float*>(dflow);
-#define EBOS_BG(G, WGT, P, NGV) k_win_bwd_g<G, WGT, P, NGV><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+#define EBOS_BG(G, WGT, P, NGV) launch_pdl(k_win_bwd_g<G, WGT, P, NGV>, dim3(ggrid), dim3(256), st, fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
 #define EBOS_BGO(G, WGT, P, NGV, O) k_win_bwd_g<G, WGT, P, NGV, O><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
       static const int bocc = env_int("EBOS_BOCC");   // experiment knob (unweighted packed gradient-plane kernel only)
       if (bocc && !affine && !has_weight && packed) {
