@@ -1310,7 +1310,52 @@ __device__ __forceinline__ void bwd_group4(const EventBlock<float, 4, HAS_W, PAC
   }
 }
 
-template <int GSRC, bool HAS_W, bool PACKED, int NG, int MINB = 5>
+// Group of four events that lies entirely inside the stream (no end markers): the cells of all four are computed
+// first; when every one is regular (all taps inside, finite) the per-event exact-path branches disappear from the
+// instruction stream.  Returns false (nothing done) when the group needs the general code.
+template <int GSRC, bool HAS_W, bool PACKED>
+__device__ __forceinline__ bool bwd_group4_regular(const EventBlock<float, 4, HAS_W, PACKED>& e, BwdRun& run,
+                                                   const BwdParams<float>& P, const float* __restrict__ g,
+                                                   float* __restrict__ dflow) {
+  float2 ab[4];
+  int r[4], c[4];
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 w = make_float2(__fsub_rn(e.x[i], __fmul_rn(e.d[i], e.f0[i])), __fsub_rn(e.y[i], __fmul_rn(e.d[i], e.f1[i])));
+    const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
+    const float fr = floorf(wb.x), fc = floorf(wb.y);
+    ab[i] = sub2(w, make_float2(fr, fc));
+    r[i] = (int)fr + P.pad_h; c[i] = (int)fc + P.pad_w;
+    ok = ok && (unsigned)(r[i] - P.lo) < P.r_span && (unsigned)(c[i] - P.lo) < P.c_span && (ab[i].x + ab[i].y == ab[i].x + ab[i].y);
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (r[i] != run.pr || c[i] != run.pc) {
+      const float* p = g + (r[i] * P.Wp + c[i]);
+      run.g00 = __ldg(p); run.g01 = __ldg(p + 1); run.g10 = __ldg(p + P.Wp); run.g11 = __ldg(p + P.Wp + 1);
+      run.pr = r[i]; run.pc = c[i];
+    }
+    // (dx, dy) = (1-b, 1-a) * (g10-g00, g01-g00) + (b, a) * (g11-g01, g11-g10)
+    const float2 d1 = sub2(make_float2(run.g10, run.g01), make_float2(run.g00, run.g00));
+    const float2 d2 = sub2(make_float2(run.g11, run.g11), make_float2(run.g01, run.g10));
+    const float2 ba = make_float2(ab[i].y, ab[i].x);
+    float2 dxy = fma2(ba, d2, mul2(sub2(make_float2(1.f, 1.f), ba), d1));
+    if (GSRC == 1) dxy = mul2(dxy, make_float2(P.vc.cv, P.vc.cv));  // differences: the mean cancels
+    if (HAS_W) dxy = mul2(dxy, make_float2(e.wt[i], e.wt[i]));
+    if (e.k[i] != run.ck) {
+      if (run.ck >= 0) { red_add_nc(dflow + run.ck, run.s01.x); red_add_nc(dflow + P.hw + run.ck, run.s01.y); }
+      run.ck = e.k[i];
+      run.s01 = make_float2(0.f, 0.f);
+    }
+    run.s01 = fma2(make_float2(-e.d[i], -e.d[i]), dxy, run.s01);
+  }
+  return true;
+}
+
+// (4 CTAs/SM = 64 registers: with the prefetched group and the regular-group fast path the 48-register build spills)
+template <int GSRC, bool HAS_W, bool PACKED, int NG, int MINB = 4>
 __global__ void __launch_bounds__(256, MINB)
 k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
             const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h, int pad_w,
@@ -1335,8 +1380,13 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
     const int64_t b = base + 4 * gi;
     if (b >= n) break;
     if (gi + 1 < NG && b + 4 < n) nxt.load_global(sx, sy, sd, sw, b + 4, n);
-    if (g_ablate & 2) cur.finish_nogather(W, P.hw); else cur.finish(flow, W, P.hw);
-    bwd_group4<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow);
+    if (b + 4 <= n) {
+      cur.finish_full(flow, W, P.hw);
+      if (!bwd_group4_regular<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow)) bwd_group4<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow);
+    } else {
+      if (g_ablate & 2) cur.finish_nogather(W, P.hw); else cur.finish(flow, W, P.hw);
+      bwd_group4<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow);
+    }
     if (gi + 1 < NG) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) { cur.x[j] = nxt.x[j]; cur.y[j] = nxt.y[j]; cur.d[j] = nxt.d[j]; if (HAS_W) cur.wt[j] = nxt.wt[j]; }
@@ -1737,7 +1787,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
 #define EBOS_BGO(G, WGT, P, NGV, O) k_win_bwd_g<G, WGT, P, NGV, O><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
       static const int bocc = env_int("EBOS_BOCC");   // experiment knob (unweighted packed gradient-plane kernel only)
       if (bocc && !affine && !has_weight && packed) {
-        if (bocc == 4 && ng == 2) EBOS_BGO(0, false, true, 2, 4); else if (bocc == 4) EBOS_BGO(0, false, true, 4, 4);
+        if (bocc == 5 && ng == 2) EBOS_BGO(0, false, true, 2, 5); else if (bocc == 5) EBOS_BGO(0, false, true, 4, 5);
         else if (bocc == 3 && ng == 2) EBOS_BGO(0, false, true, 2, 3); else if (bocc == 3) EBOS_BGO(0, false, true, 4, 3);
         else if (bocc == 6 && ng == 2) EBOS_BGO(0, false, true, 2, 6); else EBOS_BGO(0, false, true, 4, 6);
         EBOS_LAUNCH_CHECK("ebos_window_backward(grouped, occ)");
