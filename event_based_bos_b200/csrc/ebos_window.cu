@@ -1661,13 +1661,19 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   static const int ng_env = env_int("EBOS_GROUPS");   // 0 default (4 groups of 4 events), 2/4/8 groups, -1 legacy kernels
   if constexpr (sizeof(T) == 4) {
     if (ng_env >= 0) {
-      const int ng = (ng_env == 2 || ng_env == 8) ? ng_env : 4;
+      // events per thread = 4 * ng: 16 by default; small windows take fewer so that the grid still holds >= 2 CTAs per
+      // SM (a 500 k-event window at 16 events per thread is 122 CTAs on 148 SMs: latency-bound, 16.6 us)
+      int ng = (ng_env == 1 || ng_env == 2 || ng_env == 8) ? ng_env : 4;
+      if (ng_env == 0) {
+        const int64_t want = (int64_t)2 * sm_count() * 256;   // threads
+        while (ng > 1 && n / (4 * ng) < want) ng >>= 1;
+      }
       const unsigned ggrid = (unsigned)((((n + 4 * ng - 1) / (4 * ng)) + 255) / 256);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
 #define EBOS_SG(WGT, P, NGV) k_win_splat_g<WGT, P, NGV><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fi)
-#define EBOS_SG_N(WGT, P) do { if (ng == 2) EBOS_SG(WGT, P, 2); else if (ng == 8) EBOS_SG(WGT, P, 8); else EBOS_SG(WGT, P, 4); } while (0)
+#define EBOS_SG_N(WGT, P) do { if (ng == 1) EBOS_SG(WGT, P, 1); else if (ng == 2) EBOS_SG(WGT, P, 2); else if (ng == 8) EBOS_SG(WGT, P, 8); else EBOS_SG(WGT, P, 4); } while (0)
       if (has_weight) { if (packed) EBOS_SG_N(true, true); else EBOS_SG_N(true, false); }
       else { if (packed) EBOS_SG_N(false, true); else EBOS_SG_N(false, false); }
 #undef EBOS_SG_N
@@ -1777,7 +1783,8 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
   static const int ng_env = env_int("EBOS_GROUPS");   // 0 default (2 groups of 4 events: measured best), 4/8, -1 legacy
   if constexpr (sizeof(T) == 4) {
     if (ng_env >= 0) {
-      const int ng = (ng_env == 4 || ng_env == 8) ? ng_env : 2;
+      int ng = (ng_env == 1 || ng_env == 4 || ng_env == 8) ? ng_env : 2;
+      if (ng_env == 0 && n / (4 * ng) < (int64_t)2 * sm_count() * 256) ng = 1;   // small windows: see window_splat_t
       const unsigned ggrid = (unsigned)((((n + 4 * ng - 1) / (4 * ng)) + 255) / 256);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
@@ -1793,7 +1800,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
         EBOS_LAUNCH_CHECK("ebos_window_backward(grouped, occ)");
         return EBOS_OK;
       }
-#define EBOS_BG_N(G, WGT, P) do { if (ng == 2) EBOS_BG(G, WGT, P, 2); else if (ng == 8) EBOS_BG(G, WGT, P, 8); else EBOS_BG(G, WGT, P, 4); } while (0)
+#define EBOS_BG_N(G, WGT, P) do { if (ng == 1) EBOS_BG(G, WGT, P, 1); else if (ng == 2) EBOS_BG(G, WGT, P, 2); else if (ng == 8) EBOS_BG(G, WGT, P, 8); else EBOS_BG(G, WGT, P, 4); } while (0)
 #define EBOS_BG_W(G) do { if (has_weight) { if (packed) EBOS_BG_N(G, true, true); else EBOS_BG_N(G, true, false); } \
                           else { if (packed) EBOS_BG_N(G, false, true); else EBOS_BG_N(G, false, false); } } while (0)
       if (affine) EBOS_BG_W(1); else EBOS_BG_W(0);
