@@ -91,8 +91,10 @@ class ContrastMaximizationDense(SolverBase):
         -- its splat is ~120 CTAs -- so overlapping windows raises windows/s without touching the per-window result:
         every window runs exactly the kernels and the order of `estimate` (results are identical)."""
         n_slots = max(1, min(int(concurrency), len(windows)))
-        if not self.fused or any(len(w) >= (1 << 21) for w in windows):
-            n_slots = 1   # large windows fill the GPU on their own (and take the eager, non-graph path)
+        if not self.fused or self.store_history or any(len(w) >= (1 << 21) for w in windows):
+            # large windows fill the GPU on their own (and take the eager, non-graph path); a loss history is kept per
+            # solver object, i.e. for one window at a time
+            n_slots = 1
         if n_slots == 1:
             return [self.estimate(w, flow0=None if flow0 is None else flow0[i]) for i, w in enumerate(windows)]
         # two sets of streams / staging buffers, used alternately: while the GPU runs batch k, the host prepares
