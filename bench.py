@@ -382,7 +382,7 @@ def run_fused(args, rank, world, local):
                                       "h2d_bytes_per_step": 9 * n + 2 * P_BYTES,
                                       "includes": "same, fed with the raw sensor stream (int16 x,y; int32 t; bool p = 9 B/event) "
                                                   "through ebos_ingest_raw"}}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU baseline is timed on rank 0 at N=1 only
         v, cms, cores = cpu_reference_fused(args.cpu_events, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_events} events, mean of 3 evaluations after 1 warm-up "
@@ -444,7 +444,7 @@ def run_solve(args, rank, world, local):
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": 16 * n,
                     "d2h_bytes_per_step": 2 * P_BYTES},
             "gpu_launches": n_solves * iters * 7}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         s_per_it, cores = cpu_reference_solve(n, 3)
         line["cpu_baseline"] = {"value": 1.0 / (s_per_it * iters), "unit": "windows/s", "cores": cores, "kind": "port",
                                 "sample": f"3 Adam iterations of the oracle loop timed ({s_per_it:.3f} s/it), x{iters}"}
