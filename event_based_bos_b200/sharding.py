@@ -187,4 +187,29 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
               "ebos_flow_tv")
         return ((acc[3] + acc[24:40].sum()) * (tv_weight / (2.0 * H * W))).to(window.dtype).reshape(1), dtv
 
-    return EventShardedObjective(splat, cost_fn, backward, regulariser if tv_weight else None)
+    class _Lean(EventShardedObjective):
+        """Same result with fewer passes: the TV kernel writes (tv_weight / R) * dTV straight into the gradient buffer
+        (every rank computes the identical TV term, the all-reduce over R ranks restores its full weight), the backward
+        accumulates on top, and the scalar loss is formed once from the accumulators -- no separate TV plane, no
+        zero-fill, no plane-sized add."""
+
+        def value_and_grad(self, flow):
+            st = current_stream()
+            R = dist.get_world_size() if is_distributed() else 1
+            Hp, Wp = H + 2 * ph, W + 2 * pw
+            check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(dflow), st), "ebos_flow_tv")
+            ops.window_splat(window, flow, outer_padding, out=iwe)
+            if R > 1:
+                dist.all_reduce(iwe, op=dist.ReduceOp.SUM)       # exchange 1: partial IWEs
+            check(lib.ebos_iwe_cost(kind, ptr(iwe), Hp, Wp, int(omit_boundary), data_weight, window.code, ptr(acc),
+                                    ptr(g_iwe), st), "ebos_iwe_cost")
+            check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
+                                           window.code, ptr(g_iwe), kind, ptr(iwe), ptr(acc), int(omit_boundary),
+                                           data_weight, ptr(dflow), st), "ebos_window_backward")
+            if R > 1:
+                dist.all_reduce(dflow, op=dist.ReduceOp.SUM)     # exchange 2: partial flow gradients (+ TV / R each)
+            check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, H, W, int(omit_boundary), data_weight, tv_weight,
+                                         window.code, ptr(loss), st), "ebos_loss_finalize")
+            return loss, dflow
+
+    return _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
