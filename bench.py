@@ -496,7 +496,7 @@ def run_giant(args, rank, world, local):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"single giant window of {n_total} synthetic events sharded by events over {world} GPU(s), "
                                    f"1280x720, fp32, {COST}+{TV_WEIGHT}*TV forward+backward; partial IWE and partial dflow "
-                                   f"all-reduced with NCCL" + ("" if world > 1 else " (no collective at 1 GPU)"),
+                                   f"exchanged by: {getattr(obj, 'exchange', 'nccl all-reduce')}",
                        "events_total": n_total, "events_per_gpu": n, "l2_policy": "inputs larger than L2"},
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": "whole evaluation (all kernels + collectives)",

@@ -212,15 +212,30 @@ constexpr int GM_TH = 32, GM_TW = 64, GM_ROWS = 8;   // tile, rows per thread (2
 // loaded up front (25 independent loads, one round trip); everything else is register arithmetic with
 // compile-time indices (a first version with nested loops around dependent loads made these few threads the
 // critical path of the whole launch).
+// The IWE as the sum of up to kMaxPeers partial planes (event-sharded windows: every rank's partial IWE lives in
+// symmetric memory, mapped into this process over NVLink).  The partial planes are summed IN RANK ORDER while the
+// tiles are loaded, so the all-reduce of the partial IWEs is fused into the cost kernel and every rank computes
+// bit-identical results.  n == 1 is the ordinary single-plane case.
+constexpr int kMaxPeers = 8;
+template <typename T> struct PeerPlanes {
+  const T* p[kMaxPeers];
+  int n;
+  __device__ __forceinline__ T load(int64_t idx) const {
+    T v = p[0][idx];
+    for (int r = 1; r < n; ++r) v += p[r][idx];
+    return v;
+  }
+};
+
 template <typename T>
-__device__ void gradmag_frame_pixel(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, int r, int c,
+__device__ void gradmag_frame_pixel(const PeerPlanes<T>& iwe, int Hp, int Wp, int omit, T coef, int r, int c,
                                     T* __restrict__ g, double& part) {
   T v[5][5];
 #pragma unroll
   for (int a = -2; a <= 2; ++a)
 #pragma unroll
     for (int b = -2; b <= 2; ++b)
-      v[a + 2][b + 2] = __ldg(iwe + (int64_t)min(max(r + a, 0), Hp - 1) * Wp + min(max(c + b, 0), Wp - 1));
+      v[a + 2][b + 2] = iwe.load((int64_t)min(max(r + a, 0), Hp - 1) * Wp + min(max(c + b, 0), Wp - 1));
   T out = 0;
 #pragma unroll
   for (int dr = -1; dr <= 1; ++dr) {
@@ -250,7 +265,7 @@ __device__ void gradmag_frame_pixel(const T* __restrict__ iwe, int Hp, int Wp, i
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_gradmag_sep(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, double* __restrict__ acc, T* __restrict__ g,
+k_gradmag_sep(const PeerPlanes<T> iwe, int Hp, int Wp, int omit, T coef, double* __restrict__ acc, T* __restrict__ g,
               int n_frame_ctas, int n_tiles) {
   __shared__ T sI[GM_TH + 4][GM_TW + 4];
   __shared__ double sm[32];
@@ -283,7 +298,7 @@ k_gradmag_sep(const T* __restrict__ iwe, int Hp, int Wp, int omit, T coef, doubl
     for (int i = threadIdx.x; i < (GM_TH + 4) * (GM_TW + 4); i += blockDim.x) {
       const int lr = i / (GM_TW + 4), lc = i - lr * (GM_TW + 4);
       const int r = min(max(r0 - 2 + lr, 0), Hp - 1), c = min(max(c0 - 2 + lc, 0), Wp - 1);
-      sI[lr][lc] = __ldg(iwe + (int64_t)r * Wp + c);
+      sI[lr][lc] = iwe.load((int64_t)r * Wp + c);
     }
     __syncthreads();
     const int tx = threadIdx.x & (GM_TW - 1), ty = threadIdx.x / GM_TW;
@@ -639,6 +654,30 @@ __global__ void __launch_bounds__(256, MINB) k_adam(T* __restrict__ p, const T* 
 }
 __global__ void k_adam_bump(int32_t* step_dev) { *step_dev += 1; }
 
+// out[i] = sum over the peer buffers, in rank order (the one-shot all-reduce of the partial flow gradients)
+template <typename T>
+__global__ void __launch_bounds__(256) k_sum_peers(const PeerPlanes<T> pl, int64_t n, T* __restrict__ out) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  bool vec = sizeof(T) == 4 && (reinterpret_cast<size_t>(out) & 15) == 0;
+  for (int r = 0; r < pl.n; ++r) vec = vec && (reinterpret_cast<size_t>(pl.p[r]) & 15) == 0;
+  int64_t done = 0;
+  if constexpr (sizeof(T) == 4) {
+    if (vec) {
+      const int64_t n4 = n >> 2;
+      for (int64_t i = tid; i < n4; i += nth) {
+        float4 a = reinterpret_cast<const float4*>(pl.p[0])[i];
+        for (int r = 1; r < pl.n; ++r) {
+          const float4 b = reinterpret_cast<const float4*>(pl.p[r])[i];
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = a;
+      }
+      done = n4 * 4;
+    }
+  }
+  for (int64_t i = done + tid; i < n; i += nth) out[i] = pl.load(i);
+}
+
 // ---- launch helpers ----------------------------------------------------------------------------------
 // 2-D grid-stride launch shape for plane kernels: about `per_sm` CTAs per SM in total (the reductions end in
 // one same-address atomic per CTA, so fewer, longer-lived CTAs are better).
@@ -649,7 +688,8 @@ static dim3 plane_grid2d(int rows, int cols, int per_sm = 8) {
 }
 
 template <typename T>
-int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, double* acc, T* grad_iwe, cudaStream_t st) {
+int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, double* acc, T* grad_iwe, cudaStream_t st,
+               const void* const* peers = nullptr, int n_peers = 0) {
   const double cnt = omit ? (double)(Hp - 2) * (double)(Wp - 2) : (double)Hp * (double)Wp;
   if (kind == EBOS_COST_VARIANCE) {
     k_var_reduce<T><<<plane_grid2d(Hp, Wp, 2), 256, 0, st>>>(iwe, Hp, Wp, omit, acc);
@@ -667,7 +707,10 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
       const int64_t n_frame = has_fast ? (int64_t)6 * Wp + (int64_t)6 * (Hp - 6) : (int64_t)Hp * Wp;
       const int n_frame_ctas = (int)((n_frame + 255) / 256);
       const int n_tiles = has_fast ? ((Wp + GM_TW - 1) / GM_TW) * ((Hp + GM_TH - 1) / GM_TH) : 0;
-      cudaError_t le = launch_pdl(k_gradmag_sep<T>, dim3(n_frame_ctas + n_tiles), dim3(256), st, iwe, Hp, Wp, omit, coef, acc,
+      PeerPlanes<T> planes{};
+      planes.n = peers ? n_peers : 1;
+      for (int r = 0; r < planes.n; ++r) planes.p[r] = peers ? reinterpret_cast<const T*>(peers[r]) : iwe;
+      cudaError_t le = launch_pdl(k_gradmag_sep<T>, dim3(n_frame_ctas + n_tiles), dim3(256), st, planes, Hp, Wp, omit, coef, acc,
                                   grad_iwe, n_frame_ctas, n_tiles);
       if (le != cudaSuccess) return cuda_fail(le, "ebos_iwe_cost(gradmag)");
     }
@@ -739,6 +782,44 @@ int ebos_iwe_cost(int kind, const void* iwe, int Hp, int Wp, int omit_boundary, 
   if (e != cudaSuccess) return cuda_fail(e, "ebos_iwe_cost memset");
   if (dtype == EBOS_F64) return iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, scale, acc, (double*)grad_iwe, st);
   return iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, scale, acc, (float*)grad_iwe, st);
+}
+
+int ebos_iwe_cost_peers(int kind, const void* const* iwe_peers, int n_peers, int Hp, int Wp, int omit_boundary, double scale,
+                        int dtype, double* acc, void* grad_iwe, void* stream) {
+  EBOS_REQUIRE(iwe_peers && acc && grad_iwe && Hp > 0 && Wp > 0 && n_peers >= 1 && n_peers <= kMaxPeers,
+               "ebos_iwe_cost_peers: bad argument");
+  EBOS_REQUIRE(kind == EBOS_COST_GRADMAG, "ebos_iwe_cost_peers: only the gradient-magnitude objective reads peer planes");
+  EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_iwe_cost_peers: omit_boundary needs an image larger than 2x2");
+  EBOS_REQUIRE(getenv("EBOS_GRADMAG_LEGACY") == nullptr, "ebos_iwe_cost_peers: not available with EBOS_GRADMAG_LEGACY");
+  EBOS_CHECK_DTYPE(dtype, "ebos_iwe_cost_peers");
+  for (int r = 0; r < n_peers; ++r) EBOS_REQUIRE(iwe_peers[r] != nullptr, "ebos_iwe_cost_peers: null peer plane");
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(acc, 0, 3 * sizeof(double), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(acc + kAccGradSlots, 0, kAccSpread * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_iwe_cost_peers memset");
+  if (dtype == EBOS_F64)
+    return iwe_cost_t<double>(kind, (const double*)iwe_peers[0], Hp, Wp, omit_boundary, scale, acc, (double*)grad_iwe, st, iwe_peers, n_peers);
+  return iwe_cost_t<float>(kind, (const float*)iwe_peers[0], Hp, Wp, omit_boundary, scale, acc, (float*)grad_iwe, st, iwe_peers, n_peers);
+}
+
+int ebos_sum_peers(const void* const* peers, int n_peers, int64_t n, int dtype, void* out, void* stream) {
+  EBOS_REQUIRE(peers && out && n >= 0 && n_peers >= 1 && n_peers <= kMaxPeers, "ebos_sum_peers: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_sum_peers");
+  if (n == 0) return EBOS_OK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n / 4 + 255) / 256, (int64_t)sm_count() * 8));
+  if (dtype == EBOS_F64) {
+    PeerPlanes<double> pl{};
+    pl.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) pl.p[r] = (const double*)peers[r];
+    k_sum_peers<double><<<grid, 256, 0, as_stream(stream)>>>(pl, n, (double*)out);
+  } else {
+    PeerPlanes<float> pl{};
+    pl.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) pl.p[r] = (const float*)peers[r];
+    k_sum_peers<float><<<grid, 256, 0, as_stream(stream)>>>(pl, n, (float*)out);
+  }
+  EBOS_LAUNCH_CHECK("ebos_sum_peers");
+  return EBOS_OK;
 }
 
 int ebos_flow_tv(const void* flow, const void* weights, int H, int W, double tv_scale, int dtype, double* acc,

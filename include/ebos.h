@@ -220,6 +220,19 @@ EBOS_API int ebos_adam_step_graph(void* param, const void* grad, void* exp_avg, 
                          double beta1, double beta2, double eps, int32_t* step_dev, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Event-sharded windows: one-shot reductions over peer memory.  `peers` is a HOST array of n_peers
+ * (<= 8) device pointers, one per rank in rank order, each valid in this process (the own buffer, and the other
+ * ranks' buffers mapped over NVLink -- e.g. torch symmetric memory); the caller provides the cross-rank barriers
+ * before (all partial planes complete) and after (nobody overwrites a plane a peer still reads).
+ *   ebos_iwe_cost_peers  = ebos_iwe_cost(EBOS_COST_GRADMAG) on the SUM of the partial IWE planes, summed in rank
+ *                          order while the tiles are loaded: the all-reduce of the partial IWEs fused into the cost
+ *                          kernel; bit-identical on every rank.
+ *   ebos_sum_peers       : out[i] = sum_r peers[r][i] (rank order) -- the partial flow gradients. */
+EBOS_API int ebos_iwe_cost_peers(int kind, const void* const* iwe_peers, int n_peers, int Hp, int Wp, int omit_boundary,
+                        double scale, int dtype, double* acc, void* grad_iwe, void* stream);
+EBOS_API int ebos_sum_peers(const void* const* peers, int n_peers, int64_t n, int dtype, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Event ingestion: raw sensor arrays (x:int16 sensor column, y:int16 sensor row, t:int32 us,
  * p:bool as uint8; 9 B/event, time ordered -- the `raw_events` datasets of src/data_loader/ccs.py:50-69) ->
  * the reference's event rows [n,4] = (row = y, col = x, t_us / 1e6, p) of CcsDataLoader.load_event
