@@ -189,6 +189,41 @@ def test_value_and_grad_vs_reference_golden(golden, ops):
         assert rel_err(grad.cpu().numpy(), golden[f"{name}/grad"]) <= (2 * REL if f32 else 5e-3), name
 
 
+def test_peer_plane_cost_and_sum_match_the_reduced_plane(ops):
+    """ebos_iwe_cost_peers / ebos_sum_peers (the one-shot reductions of the event-sharded path) with the "peers" being
+    local planes: the cost on R partial IWEs summed in the tile load equals the cost on their materialised sum, the
+    gradient plane likewise, and the peer sum equals torch's sum in rank order (bit for bit)."""
+    import ctypes
+
+    from event_based_bos_b200 import _capi
+    from event_based_bos_b200._capi import check, current_stream, ptr
+
+    lib = _capi.load()
+    rng = np.random.default_rng(12)
+    for (Hp, Wp), R in (((37, 53), 2), ((96, 260), 3), ((6, 40), 8)):
+        parts = [torch.from_numpy(rng.standard_normal((Hp, Wp)).astype(np.float32) * 2 + 0.5).cuda() for _ in range(R)]
+        total = parts[0].clone()
+        for q in parts[1:]:
+            total += q
+        ptrs = (ctypes.c_void_p * R)(*[q.data_ptr() for q in parts])
+        for omit in (0, 1):
+            acc = torch.zeros(_capi.ACC_DOUBLES, dtype=torch.float64, device="cuda")
+            acc2 = torch.zeros_like(acc)
+            g1, g2 = torch.empty_like(total), torch.empty_like(total)
+            l1, l2 = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+            st = current_stream()
+            check(lib.ebos_iwe_cost_peers(_capi.COST_GRADMAG, ptrs, R, Hp, Wp, omit, 1.0, 0, ptr(acc), ptr(g1), st))
+            check(lib.ebos_iwe_cost(_capi.COST_GRADMAG, ptr(total), Hp, Wp, omit, 1.0, 0, ptr(acc2), ptr(g2), st))
+            check(lib.ebos_loss_finalize(_capi.COST_GRADMAG, ptr(acc), Hp, Wp, 1, 1, omit, 1.0, 0.0, 0, ptr(l1), st))
+            check(lib.ebos_loss_finalize(_capi.COST_GRADMAG, ptr(acc2), Hp, Wp, 1, 1, omit, 1.0, 0.0, 0, ptr(l2), st))
+            assert torch.equal(g1, g2) and abs(float(l1) - float(l2)) <= 1e-6 * abs(float(l2))
+        out = torch.empty_like(total)
+        check(lib.ebos_sum_peers(ptrs, R, total.numel(), 0, ptr(out), current_stream()))
+        assert torch.equal(out, total)
+    with pytest.raises(RuntimeError):   # the variance objective needs the materialised sum
+        check(lib.ebos_iwe_cost_peers(_capi.COST_VARIANCE, ptrs, R, Hp, Wp, 0, 1.0, 0, ptr(acc), ptr(g1), current_stream()))
+
+
 def test_captured_evaluation_replays_on_updated_flow(ops):
     """ops.CmaxGraph: the fused evaluation captured as a CUDA graph gives the eager result, and a replay after an
     in-place flow update gives the eager result at the new flow."""
