@@ -189,9 +189,11 @@ EBOS_API int ebos_window_backward(const void* window, int64_t n, int flags, cons
 EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W, int omit_boundary,
                        double data_scale, double tv_scale, int dtype, void* loss, void* stream);
 
-/* One complete objective evaluation: splat -> cost -> TV -> backward -> loss, stream-ordered,
- * no host sync (CUDA-graph capturable).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W],
- * loss [1], acc double[EBOS_ACC_DOUBLES]. */
+/* One complete objective evaluation: [TV | splat] -> cost -> [backward | loss], stream-ordered, no host sync
+ * (CUDA-graph capturable; the TV kernel and the scalar-loss kernel run on an internal auxiliary stream that is
+ * forked from and joined back into `stream`).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W], loss [1],
+ * acc double[EBOS_ACC_DOUBLES].  When `iwe` starts exactly at acc + EBOS_ACC_DOUBLES (one allocation, accumulators
+ * first) both are zeroed by a single memset node. */
 EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W,
                              int pad_h, int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
