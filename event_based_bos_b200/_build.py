@@ -31,6 +31,8 @@ NVCC_FLAGS = [
 # No per-file flags at present.  (ptxas 12.9 contracts explicit mul.rn.f32x2 + sub.rn.f32x2 into FFMA2 even with
 # --fmad=false; the exactness-critical warp therefore uses the scalar __fmul_rn/__fsub_rn forms, see ebos_window.cu.)
 PER_FILE_FLAGS = {}
+if os.environ.get("EBOS_BUILD_GM_GROUPS"):      # experiment: row groups per CTA of the gradient-magnitude kernel
+    NVCC_FLAGS.append("-DEBOS_GM_GROUPS=" + os.environ["EBOS_BUILD_GM_GROUPS"])
 if os.environ.get("EBOS_BUILD_ABLATION"):   # diagnostics build: EBOS_ABLATE=<mask> then removes kernel components
     NVCC_FLAGS.append("-DEBOS_ABLATION")
 

@@ -205,7 +205,11 @@ __global__ void __launch_bounds__(256, 4) k_gradmag(const T* __restrict__ iwe, i
 // c in [3, Wp-4]: there no tap is clamped by the replicate padding and no g on the (optionally omitted) border
 // ring is involved.  The 3-pixel frame around it is evaluated exactly, straight from the definition, by extra
 // CTAs of the same launch (one thread per frame pixel).
-constexpr int GM_TH = 32, GM_TW = 64, GM_ROWS = 8;   // tile, rows per thread (256 threads = 64 columns x 4 row groups)
+constexpr int GM_TW = 64, GM_ROWS = 8;               // tile width, rows per thread
+#ifndef EBOS_GM_GROUPS
+#define EBOS_GM_GROUPS 4                              // row groups per CTA (CTA = 64 columns x groups threads)
+#endif
+constexpr int GM_GROUPS = EBOS_GM_GROUPS, GM_TH = GM_GROUPS * GM_ROWS, GM_THREADS = GM_TW * GM_GROUPS;
 
 // exact value at one frame pixel p = (r, c): sum over the counted positions q in the 3x3 neighbourhood of p and
 // the Sobel taps (u, v) whose clamped target clamp(q + (u, v)) is p.  The 5x5 clamped neighbourhood of p is
@@ -264,7 +268,7 @@ __device__ void gradmag_frame_pixel(const PeerPlanes<T>& iwe, int Hp, int Wp, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(GM_THREADS)
 k_gradmag_sep(const PeerPlanes<T> iwe, int Hp, int Wp, int omit, T coef, double* __restrict__ acc, T* __restrict__ g,
               int n_frame_ctas, int n_tiles) {
   __shared__ T sI[GM_TH + 4][GM_TW + 4];
@@ -705,12 +709,12 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
     } else {
       const bool has_fast = Hp >= 7 && Wp >= 7;
       const int64_t n_frame = has_fast ? (int64_t)6 * Wp + (int64_t)6 * (Hp - 6) : (int64_t)Hp * Wp;
-      const int n_frame_ctas = (int)((n_frame + 255) / 256);
+      const int n_frame_ctas = (int)((n_frame + GM_THREADS - 1) / GM_THREADS);
       const int n_tiles = has_fast ? ((Wp + GM_TW - 1) / GM_TW) * ((Hp + GM_TH - 1) / GM_TH) : 0;
       PeerPlanes<T> planes{};
       planes.n = peers ? n_peers : 1;
       for (int r = 0; r < planes.n; ++r) planes.p[r] = peers ? reinterpret_cast<const T*>(peers[r]) : iwe;
-      cudaError_t le = launch_pdl(k_gradmag_sep<T>, dim3(n_frame_ctas + n_tiles), dim3(256), st, planes, Hp, Wp, omit, coef, acc,
+      cudaError_t le = launch_pdl(k_gradmag_sep<T>, dim3(n_frame_ctas + n_tiles), dim3(GM_THREADS), st, planes, Hp, Wp, omit, coef, acc,
                                   grad_iwe, n_frame_ctas, n_tiles);
       if (le != cudaSuccess) return cuda_fail(le, "ebos_iwe_cost(gradmag)");
     }
