@@ -16,8 +16,8 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libebos.so")
-SOURCES = ["ebos_ops.cu", "ebos_window.cu", "ebos_costs.cu", "ebos_ingest.cu"]
-HEADERS = ["ebos_common.cuh", os.path.join("..", "..", "include", "ebos.h")]
+SOURCES = ["ebos_ops.cu", "ebos_window.cu", "ebos_costs.cu", "ebos_ingest.cu", "ebos_eklt.cu"]
+HEADERS = ["ebos_common.cuh", "ebos_eklt_math.cuh", os.path.join("..", "..", "include", "ebos.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -70,6 +70,16 @@ SIGNATURES = {
     "ebos_time_to_index": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "ebos_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
                                      c_double, c_void_p, c_int, c_void_p]),
+    "ebos_eklt_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "ebos_eklt_value_and_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_void_p, c_size_t,
+                                         c_void_p, c_void_p, c_void_p]),
+    "ebos_eklt_adam_iteration": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_void_p, c_size_t,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double,
+                                         c_void_p, c_void_p]),
+    "ebos_eklt_upsample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ebos_eklt_patch_flow": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

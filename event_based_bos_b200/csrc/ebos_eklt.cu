@@ -1,0 +1,427 @@
+// EKLT inner loop of PatchEkltPyramid2: value and gradient of the per-level objective
+//
+//   L(theta) = w_d * ||pred - meas||_1(matrix) + w_tv * TV(flow*M; w_inv) + w_p * mean ||pxy*M||_2
+//
+// for theta [3,ph,pw] = (intensity, p_row, p_col) on the coarse patch grid  (src/solver/patch_eklt_pyramid2.py:345-392).
+// Per-pixel arithmetic lives in ebos_eklt_math.cuh (host+device, checked on the CPU against oracle/spec_eklt.py);
+// this file holds the parallel structure.  One evaluation =
+//
+//   memset(acc, colsum)
+//   k_patch_flow     pf = Sobel(theta[0]) / 8                              [2,ph,pw]       (tiny)
+//   k_forward        per pixel: up-sample pf and theta[1:3], warp the frame gradients, q; writes q and the masked
+//                    flow F = f*M; block-reduces sum q^2 and sum ||t*M||
+//   ebos_flow_tv     TV(F; w_inv) value and w_tv * dTV/dF  (the kernel of the contrast-maximisation path)
+//   k_column_sums    colsum[j] = sum_i |pred - meas|_ij     (needs ||q||)
+//   k_column_max     data term = max_j colsum, tie count, S = <g_pred*M, q>        (one CTA)
+//   k_backward       per pixel: re-evaluates the forward, writes d/d(f0,f1,t0,t1)  [4,H,W]
+//   k_cell_gather    transposed up-sampling, one CTA per padded patch cell          [4,ph+2,pw+2]
+//   k_fold           folds the replicate padding                                    [4,ph,pw]
+//   k_param_grad     Sobel adjoint for the intensity channel, copies the translation channels, writes the loss
+//
+// All plane passes are HBM/L2 streaming work (no dense contraction: tensor cores unused).  Algorithmic bytes per
+// evaluation (P = H*W*sizeof(T)): forward 2P (gradients) + 3P (q, F) ; TV 3P + 2P ; columns 2P ; backward 2P + 2P + P
+// + 4P ; gather 4P  =>  25P.
+#include <algorithm>
+
+#include "ebos_common.cuh"
+#include "ebos_eklt_math.cuh"
+
+namespace ebos {
+namespace eklt {
+
+// acc (double) layout behind the TV accumulators
+constexpr int kAccQ2 = 0, kAccPxy = 1, kAccMax = 2, kAccTieW = 3, kAccS = 4, kAccLoss = 5, kAccData = 6, kAccTv = 7,
+              kAccPxyMean = 8, kAccN = 16;
+
+struct Workspace {
+  double* tv_acc;    // [EBOS_ACC_DOUBLES]
+  double* acc;       // [kAccN]
+  double* colsum;    // [W]
+  char* pf;          // [2,ph,pw] T
+  char* q;           // [H,W] T
+  char* F;           // [2,H,W] T
+  char* dF;          // [2,H,W] T
+  char* dU;          // [4,H,W] T
+  char* dPad;        // [4,ph+2pad,pw+2pad] T
+  char* dP;          // [4,ph,pw] T
+  size_t total;
+};
+static Workspace carve(void* base, int H, int W, int ph, int pw, int pad, size_t elem) {
+  Workspace w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += align256(bytes); return r; };
+  w.tv_acc = reinterpret_cast<double*>(take(EBOS_ACC_DOUBLES * sizeof(double)));
+  // acc and colsum are adjacent: one memset clears both
+  w.acc = reinterpret_cast<double*>(p ? p + off : nullptr);
+  off += kAccN * sizeof(double);
+  w.colsum = reinterpret_cast<double*>(p ? p + off : nullptr);
+  off += (size_t)W * sizeof(double);
+  off = align256(off);
+  const size_t plane = (size_t)H * W * elem, cells = (size_t)ph * pw * elem;
+  w.pf = take(2 * cells);
+  w.q = take(plane);
+  w.F = take(2 * plane);
+  w.dF = take(2 * plane);
+  w.dU = take(4 * plane);
+  w.dPad = take((size_t)4 * (ph + 2 * pad) * (pw + 2 * pad) * elem);
+  w.dP = take(4 * cells);
+  w.total = off;
+  return w;
+}
+
+template <typename T>
+__global__ void k_patch_flow(const T* __restrict__ theta, int ph, int pw, T* __restrict__ pf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ph * pw) return;
+  T o0, o1;
+  sobel_over_8_at(theta, ph, pw, k / pw, k % pw, o0, o1);
+  pf[k] = o0;
+  pf[ph * pw + k] = o1;
+}
+
+// 2-D tiles of 32 x 8 pixels; gridDim.y strides the rows.
+template <typename T>
+__global__ void __launch_bounds__(256) k_forward(Geom g, const T* __restrict__ pf, const T* __restrict__ theta,
+                                                 const T* __restrict__ gx, const T* __restrict__ gy, T* __restrict__ q,
+                                                 T* __restrict__ F, double* __restrict__ acc) {
+  __shared__ double red[32];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  double sq = 0.0, sp = 0.0;
+  if (j < g.W) {
+    for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
+      const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+      const int64_t k = (int64_t)i * g.W + j;
+      q[k] = p.q;
+      F[k] = p.m ? p.f0 : (T)0;
+      F[(int64_t)g.H * g.W + k] = p.m ? p.f1 : (T)0;
+      sq += (double)p.q * (double)p.q;
+      if (p.m) sp += sqrt((double)p.t0 * (double)p.t0 + (double)p.t1 * (double)p.t1);
+    }
+  }
+  sq = block_sum(sq, red);
+  sp = block_sum(sp, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + kAccQ2, sq);
+    atomicAdd(acc + kAccPxy, sp);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_column_sums(Geom g, const T* __restrict__ q, const T* __restrict__ meas,
+                                                     const double* __restrict__ acc, double* __restrict__ colsum) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const T inv = (T)(1.0 / (sqrt(acc[kAccQ2]) + kNormEps));
+  double s = 0.0;
+  if (j < g.W) {
+    for (int i = blockIdx.y * 8 + row; i < g.H; i += gridDim.y * 8) {
+      const int64_t k = (int64_t)i * g.W + j;
+      const T D = residual<T>(q[k], in_roi(g, i, j), meas[k], inv);
+      s += fabs((double)D);
+    }
+  }
+  part[row][lane] = s;
+  __syncthreads();
+  if (row == 0 && j < g.W) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += part[r][lane];
+    atomicAdd(colsum + j, t);
+  }
+}
+
+// One CTA: max column sum, number of ties, S = sum over the maximal columns of sign(D) * M * q * tie_w.
+template <typename T>
+__global__ void __launch_bounds__(256) k_column_max(Geom g, const T* __restrict__ q, const T* __restrict__ meas,
+                                                    const double* __restrict__ colsum, double* __restrict__ acc,
+                                                    double w_data) {
+  __shared__ double red[32];
+  __shared__ double s_mx;
+  __shared__ double s_cnt;
+  double mx = -1.0;
+  for (int j = threadIdx.x; j < g.W; j += blockDim.x) mx = fmax(mx, colsum[j]);
+  // block max via shuffles
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    s_mx = m;
+  }
+  __syncthreads();
+  mx = s_mx;
+  double cnt = 0.0;
+  for (int j = threadIdx.x; j < g.W; j += blockDim.x) cnt += (colsum[j] == mx) ? 1.0 : 0.0;
+  cnt = block_sum(cnt, red);
+  if (threadIdx.x == 0) s_cnt = cnt;
+  __syncthreads();
+  cnt = s_cnt;
+  const double n = sqrt(acc[kAccQ2]);
+  const T inv = (T)(1.0 / (n + kNormEps));
+  const double tie_w = w_data / cnt;
+  double S = 0.0;
+  for (int j = g.y0; j < g.y1; ++j) {          // outside the ROI columns M = 0
+    if (colsum[j] != mx) continue;             // uniform over the CTA
+    for (int i = g.x0 + threadIdx.x; i < g.x1; i += blockDim.x) {
+      const int64_t k = (int64_t)i * g.W + j;
+      const T D = residual<T>(q[k], true, meas[k], inv);
+      S += sgn((double)D) * tie_w * (double)q[k];
+    }
+  }
+  S = block_sum(S, red);
+  if (threadIdx.x == 0) {
+    acc[kAccMax] = mx;
+    acc[kAccTieW] = tie_w;
+    acc[kAccS] = S;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_backward(Geom g, const T* __restrict__ pf, const T* __restrict__ theta,
+                                                  const T* __restrict__ gx, const T* __restrict__ gy,
+                                                  const T* __restrict__ meas, const T* __restrict__ dF,
+                                                  const double* __restrict__ colsum, const double* __restrict__ acc,
+                                                  double w_pxy_hw, T* __restrict__ dU) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (j >= g.W) return;
+  BackScalars s;
+  s.n = sqrt(acc[kAccQ2]);
+  s.mx = acc[kAccMax];
+  s.tie_w = acc[kAccTieW];
+  s.S = acc[kAccS];
+  const bool col_is_max = colsum[j] == s.mx;
+  const int64_t plane = (int64_t)g.H * g.W;
+  for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
+    const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+    const int64_t k = (int64_t)i * g.W + j;
+    T out[4];
+    backward_pixel<T>(p, meas[k], col_is_max, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw, out);
+    dU[k] = out[0];
+    dU[plane + k] = out[1];
+    dU[2 * plane + k] = out[2];
+    dU[3 * plane + k] = out[3];
+  }
+}
+
+// One CTA per padded cell (A,B): sums the four dense gradient planes over the cell's 2*patch x 2*patch support with
+// the separable triangle weights.  Deterministic (no atomics).
+template <typename T>
+__global__ void __launch_bounds__(256) k_cell_gather(Geom g, const T* __restrict__ dU, T* __restrict__ dPad) {
+  __shared__ double red[32];
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  const int A = blockIdx.y, B = blockIdx.x;
+  int i0, i1, j0, j1;
+  cell_support(A, g.patch, g.h1, g.H, i0, i1);
+  cell_support(B, g.patch, g.w1, g.W, j0, j1);
+  const int nj = j1 - j0, ni = i1 - i0;
+  const int64_t plane = (int64_t)g.H * g.W;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  const int total = ni * nj;
+  for (int k = threadIdx.x; k < total; k += blockDim.x) {
+    const int i = i0 + k / nj, j = j0 + k % nj;
+    const double w = (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)cell_weight<T>(B, j, g.w1, g.patch);
+    const int64_t idx = (int64_t)i * g.W + j;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] += w * (double)dU[c * plane + idx];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double t = block_sum(s[c], red);
+    if (threadIdx.x == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)t;
+  }
+}
+
+template <typename T>
+__global__ void k_fold(Geom g, const T* __restrict__ dPad, T* __restrict__ dP) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = g.ph * g.pw;
+  if (k >= 4 * np) return;
+  const int c = k / np, a = (k % np) / g.pw, b = k % g.pw;
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  int a0, a1, b0, b1;
+  fold_range(a, g.ph, g.pad, a0, a1);
+  fold_range(b, g.pw, g.pad, b0, b1);
+  double s = 0.0;
+  for (int A = a0; A < a1; ++A)
+    for (int B = b0; B < b1; ++B) s += (double)dPad[((int64_t)c * PH + A) * PW + B];
+  dP[k] = (T)s;
+}
+
+template <typename T>
+__global__ void k_param_grad(Geom g, const T* __restrict__ dP, const double* __restrict__ tv_acc, double* __restrict__ acc,
+                             double w_data, double w_tv, double w_pxy, T* __restrict__ grad, T* __restrict__ loss) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = g.ph * g.pw;
+  if (k < np) {
+    grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
+    grad[np + k] = dP[2 * np + k];
+    grad[2 * np + k] = dP[3 * np + k];
+  }
+  if (k == 0) {
+    double tv = tv_acc[3];
+    for (int i = 24; i < EBOS_ACC_DOUBLES; ++i) tv += tv_acc[i];     // spread slots of the TV kernel (ebos_costs.cu)
+    const double hw = (double)g.H * (double)g.W;
+    const double tv_mean = tv / (2.0 * hw), pxy_mean = acc[kAccPxy] / hw;
+    const double total = w_data * acc[kAccMax] + w_tv * tv_mean + w_pxy * pxy_mean;
+    acc[kAccData] = acc[kAccMax];          // un-weighted terms, for diagnostics
+    acc[kAccTv] = tv_mean;
+    acc[kAccPxyMean] = pxy_mean;
+    acc[kAccLoss] = total;
+    *loss = (T)total;
+  }
+}
+
+// up-sampling on its own: the dense fields returned to the caller (flow from the intensity, translation)
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample(Geom g, const T* __restrict__ P, int channels, T* __restrict__ out) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (j >= g.W) return;
+  const AxisTap<T> c = axis_tap<T>(j, g.w1, g.patch, g.pw, g.pad);
+  for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
+    const AxisTap<T> r = axis_tap<T>(i, g.h1, g.patch, g.ph, g.pad);
+    for (int ch = 0; ch < channels; ++ch)
+      out[((int64_t)ch * g.H + i) * g.W + j] = upsample_at(P + (int64_t)ch * g.ph * g.pw, g.pw, r, c);
+  }
+}
+
+static dim3 plane_grid(int H, int W) {
+  const int gx = (W + 31) / 32;
+  // enough row groups to fill the machine about four times over, at most one group per 8 rows
+  const int want = std::max(1, (sm_count() * 8 + gx - 1) / gx);
+  return dim3(gx, std::min((H + 7) / 8, want));
+}
+
+static int check_geometry(const Geom& g) {
+  EBOS_REQUIRE(g.H >= 2 && g.W >= 2 && g.ph >= 1 && g.pw >= 1 && g.patch >= 1, "ebos_eklt: bad size");
+  EBOS_REQUIRE(g.ph * g.patch >= g.H && g.pw * g.patch >= g.W &&
+                   (g.ph - 1) * g.patch < g.H && (g.pw - 1) * g.patch < g.W,
+               "ebos_eklt: patch grid must be ceil(H/patch) x ceil(W/patch)");
+  EBOS_REQUIRE(g.x0 >= 0 && g.x0 <= g.x1 && g.x1 <= g.H && g.y0 >= 0 && g.y0 <= g.y1 && g.y1 <= g.W,
+               "ebos_eklt: ROI outside the image");
+  return EBOS_OK;
+}
+
+template <typename T>
+static int value_and_grad_t(const Geom& g, const T* theta, const T* gx, const T* gy, const T* meas, const T* winv,
+                            double w_data, double w_tv, double w_pxy, void* workspace, T* loss, T* grad, cudaStream_t st) {
+  const Workspace w = carve(workspace, g.H, g.W, g.ph, g.pw, g.pad, sizeof(T));
+  cudaError_t e = cudaMemsetAsync(w.acc, 0, (kAccN + (size_t)g.W) * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset");
+  const int np = g.ph * g.pw;
+  const dim3 pg = plane_grid(g.H, g.W);
+  T* pf = reinterpret_cast<T*>(w.pf);
+  T* q = reinterpret_cast<T*>(w.q);
+  T* F = reinterpret_cast<T*>(w.F);
+  T* dF = reinterpret_cast<T*>(w.dF);
+  T* dU = reinterpret_cast<T*>(w.dU);
+  T* dPad = reinterpret_cast<T*>(w.dPad);
+  T* dP = reinterpret_cast<T*>(w.dP);
+  k_patch_flow<T><<<(np + 127) / 128, 128, 0, st>>>(theta, g.ph, g.pw, pf);
+  k_forward<T><<<pg, 256, 0, st>>>(g, pf, theta, gx, gy, q, F, w.acc);
+  EBOS_LAUNCH_CHECK("ebos_eklt forward");
+  const int rc = ebos_flow_tv(F, winv, g.H, g.W, w_tv, sizeof(T) == 8 ? EBOS_F64 : EBOS_F32, w.tv_acc, dF, st);
+  if (rc != EBOS_OK) return rc;
+  k_column_sums<T><<<pg, 256, 0, st>>>(g, q, meas, w.acc, w.colsum);
+  k_column_max<T><<<1, 256, 0, st>>>(g, q, meas, w.colsum, w.acc, w_data);
+  k_backward<T><<<pg, 256, 0, st>>>(g, pf, theta, gx, gy, meas, dF, w.colsum, w.acc, w_pxy / ((double)g.H * g.W), dU);
+  EBOS_LAUNCH_CHECK("ebos_eklt backward");
+  k_cell_gather<T><<<dim3(g.pw + 2 * g.pad, g.ph + 2 * g.pad), 256, 0, st>>>(g, dU, dPad);
+  k_fold<T><<<(4 * np + 127) / 128, 128, 0, st>>>(g, dPad, dP);
+  k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, dP, w.tv_acc, w.acc, w_data, w_tv, w_pxy, grad, loss);
+  EBOS_LAUNCH_CHECK("ebos_eklt gradient");
+  return EBOS_OK;
+}
+
+}  // namespace eklt
+}  // namespace ebos
+
+using namespace ebos;
+using namespace ebos::eklt;
+
+extern "C" {
+
+size_t ebos_eklt_workspace_bytes(int H, int W, int ph, int pw, int patch, int dtype) {
+  if (H < 1 || W < 1 || ph < 1 || pw < 1 || patch < 1) return 0;
+  const Geom g = make_geom(H, W, ph, pw, patch, 0, H, 0, W);
+  return carve(nullptr, H, W, ph, pw, g.pad, dtype_size(dtype)).total;
+}
+
+int ebos_eklt_value_and_grad(const void* theta, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
+                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
+                             size_t workspace_bytes, void* loss, void* grad, void* stream) {
+  EBOS_REQUIRE(theta && grad_x && grad_y && measured && weight_inverse && workspace && loss && grad,
+               "ebos_eklt_value_and_grad: null argument");
+  if (dtype != EBOS_F32 && dtype != EBOS_F64) {
+    set_error("ebos_eklt_value_and_grad: unsupported dtype");
+    return EBOS_ERR_UNSUPPORTED;
+  }
+  const Geom g = make_geom(H, W, ph, pw, patch, roi_x0, roi_x1, roi_y0, roi_y1);
+  const int rc = check_geometry(g);
+  if (rc != EBOS_OK) return rc;
+  if (workspace_bytes < ebos_eklt_workspace_bytes(H, W, ph, pw, patch, dtype)) {
+    set_error("ebos_eklt_value_and_grad: workspace too small");
+    return EBOS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (dtype == EBOS_F64)
+    return value_and_grad_t<double>(g, (const double*)theta, (const double*)grad_x, (const double*)grad_y,
+                                    (const double*)measured, (const double*)weight_inverse, w_data, w_tv, w_pxy,
+                                    workspace, (double*)loss, (double*)grad, st);
+  return value_and_grad_t<float>(g, (const float*)theta, (const float*)grad_x, (const float*)grad_y,
+                                 (const float*)measured, (const float*)weight_inverse, w_data, w_tv, w_pxy, workspace,
+                                 (float*)loss, (float*)grad, st);
+}
+
+int ebos_eklt_adam_iteration(void* theta, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
+                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
+                             size_t workspace_bytes, void* loss, void* grad, void* exp_avg, void* exp_avg_sq, double lr,
+                             double beta1, double beta2, double eps, int32_t* step_dev, void* stream) {
+  EBOS_REQUIRE(exp_avg && exp_avg_sq && step_dev, "ebos_eklt_adam_iteration: null argument");
+  const int rc = ebos_eklt_value_and_grad(theta, grad_x, grad_y, measured, weight_inverse, H, W, ph, pw, patch, roi_x0,
+                                          roi_x1, roi_y0, roi_y1, w_data, w_tv, w_pxy, dtype, workspace, workspace_bytes,
+                                          loss, grad, stream);
+  if (rc != EBOS_OK) return rc;
+  return ebos_adam_step_graph(theta, grad, exp_avg, exp_avg_sq, (int64_t)3 * ph * pw, lr, beta1, beta2, eps, step_dev,
+                              dtype, stream);
+}
+
+int ebos_eklt_upsample(const void* patch_values, int channels, int H, int W, int ph, int pw, int patch, int dtype,
+                       void* dense, void* stream) {
+  EBOS_REQUIRE(patch_values && dense && channels >= 1, "ebos_eklt_upsample: bad argument");
+  if (dtype != EBOS_F32 && dtype != EBOS_F64) {
+    set_error("ebos_eklt_upsample: unsupported dtype");
+    return EBOS_ERR_UNSUPPORTED;
+  }
+  const Geom g = make_geom(H, W, ph, pw, patch, 0, H, 0, W);
+  const int rc = check_geometry(g);
+  if (rc != EBOS_OK) return rc;
+  const dim3 pg = plane_grid(H, W);
+  if (dtype == EBOS_F64)
+    k_upsample<double><<<pg, 256, 0, as_stream(stream)>>>(g, (const double*)patch_values, channels, (double*)dense);
+  else
+    k_upsample<float><<<pg, 256, 0, as_stream(stream)>>>(g, (const float*)patch_values, channels, (float*)dense);
+  EBOS_LAUNCH_CHECK("ebos_eklt_upsample");
+  return EBOS_OK;
+}
+
+int ebos_eklt_patch_flow(const void* intensity, int ph, int pw, int dtype, void* patch_flow, void* stream) {
+  EBOS_REQUIRE(intensity && patch_flow && ph >= 1 && pw >= 1, "ebos_eklt_patch_flow: bad argument");
+  if (dtype != EBOS_F32 && dtype != EBOS_F64) {
+    set_error("ebos_eklt_patch_flow: unsupported dtype");
+    return EBOS_ERR_UNSUPPORTED;
+  }
+  const int np = ph * pw;
+  if (dtype == EBOS_F64)
+    k_patch_flow<double><<<(np + 127) / 128, 128, 0, as_stream(stream)>>>((const double*)intensity, ph, pw, (double*)patch_flow);
+  else
+    k_patch_flow<float><<<(np + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)intensity, ph, pw, (float*)patch_flow);
+  EBOS_LAUNCH_CHECK("ebos_eklt_patch_flow");
+  return EBOS_OK;
+}
+
+}  // extern "C"

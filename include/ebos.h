@@ -254,6 +254,50 @@ EBOS_API int ebos_ingest_raw(const int16_t* x, const int16_t* y, const int32_t* 
  * (left side, float64 comparison like the loader's `_time_cache`); index_out: device int64. */
 EBOS_API int ebos_time_to_index(const int32_t* t_us, int64_t n, double time, int64_t* index_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * EKLT inner loop of PatchEkltPyramid2 (what configs/hot_plate1.yaml runs: poisson_model +
+ * optimize_warp with the costs diff_norm + image_gradient + flow_norm_pxy).  One pyramid level optimises
+ * theta [3,ph,pw] = (intensity, p_row, p_col) on the patch grid ph = ceil(H/patch), pw = ceil(W/patch):
+ *
+ *   pf = Sobel(theta[0]) / 8                       poisson_to_flow, src/solver/patch_eklt_dependent.py:259-281
+ *   f = up(pf), t = up(theta[1:3])                 interpolate_dense_flow_from_patch_tensor, src/solver/patch_eklt.py:173-204
+ *                                                  (replicate pad 1, bilinear x patch, centre crop)
+ *   q = f0 * warp(grad_x, t) + f1 * warp(grad_y, t)   warp_image_forward, src/utils/frame_utils.py:56-89 (grid_sample,
+ *                                                  align_corners=True, zeros; base grid built in float32 as upstream)
+ *   pred = q / (||q||_F + 1e-4) * M                _make_prediction_torch, src/solver/patch_eklt_pyramid2.py:345-365
+ *   L = w_data * max_j sum_i |pred - measured|_ij  DifferenceNorm: torch.linalg.norm(ord=1) of a MATRIX, src/costs/diff_norm.py:52
+ *     + w_tv * mean(|d_row(f M)| w_inv + |d_col(f M)| w_inv)        ImageGradient, src/costs/image_gradient.py:60-75
+ *     + w_pxy * mean_ij sqrt((t0 M)^2 + (t1 M)^2)                   FlowNormPxy, src/costs/flow_norm.py:52
+ *
+ * replaces PatchEkltPyramid2._objective_scipy + loss.backward() (src/solver/patch_eklt_pyramid2.py:267-285, 368-392).
+ * M is the ROI rectangle rows [roi_x0,roi_x1) x cols [roi_y0,roi_y1) (estimate_mask_dense, :50-51).
+ * grad_x / grad_y: [H,W] frame gradients (row / column derivative; cv2.Sobel of _set_frame,
+ * src/solver/generative_max_likelihood.py:194-213); measured: [H,W] normalised event histogram ALREADY multiplied by M;
+ * weight_inverse: [H,W].  All of `dtype`, device pointers.  loss: [1], grad: [3,ph,pw] (fully overwritten).
+ * workspace: >= ebos_eklt_workspace_bytes(...) bytes, 256-byte aligned, contents irrelevant on entry.
+ * Stream-ordered, CUDA-graph capturable (no host synchronisation, no allocation). */
+EBOS_API size_t ebos_eklt_workspace_bytes(int H, int W, int ph, int pw, int patch, int dtype);
+EBOS_API int ebos_eklt_value_and_grad(const void* theta, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
+                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
+                             size_t workspace_bytes, void* loss, void* grad, void* stream);
+
+/* One solver iteration of a level (src/solver/patch_eklt_pyramid2.py:265-285: zero_grad / loss / backward / Adam step):
+ * ebos_eklt_value_and_grad followed by ebos_adam_step_graph on theta (3*ph*pw values).  `step_dev` (int32[1]) counts the
+ * iterations done and is advanced by the call; `loss` receives the objective BEFORE the update. */
+EBOS_API int ebos_eklt_adam_iteration(void* theta, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
+                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
+                             size_t workspace_bytes, void* loss, void* grad, void* exp_avg, void* exp_avg_sq, double lr,
+                             double beta1, double beta2, double eps, int32_t* step_dev, void* stream);
+
+/* interpolate_dense_flow_from_patch_tensor on its own (src/solver/patch_eklt.py:173-204): patch_values [channels,ph,pw]
+ * -> dense [channels,H,W]; and poisson_to_flow (src/solver/patch_eklt_dependent.py:259-281): intensity [ph,pw] ->
+ * patch_flow [2,ph,pw] = Sobel/8 with replicate padding. */
+EBOS_API int ebos_eklt_upsample(const void* patch_values, int channels, int H, int W, int ph, int pw, int patch, int dtype,
+                       void* dense, void* stream);
+EBOS_API int ebos_eklt_patch_flow(const void* intensity, int ph, int pw, int dtype, void* patch_flow, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,141 @@
+// TEST INFRASTRUCTURE (never linked into libebos.so): a serial g++ build of the per-pixel / per-cell functions of
+// event_based_bos_b200/csrc/ebos_eklt_math.cuh, walked in the same order as the kernels of ebos_eklt.cu, so that the
+// arithmetic the GPU executes can be compared with oracle/spec_eklt.py in the GPU-less build container
+// (tests/test_eklt_host_math.py).  The TV term between the forward and the backward is supplied by the caller.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../event_based_bos_b200/csrc/ebos_eklt_math.cuh"
+
+using namespace ebos::eklt;
+
+template <typename T>
+static void forward_t(const Geom& g, const T* theta, const T* gx, const T* gy, T* pf, T* q, T* F, T* trans, double* sums) {
+  const int np = g.ph * g.pw;
+  for (int k = 0; k < np; ++k) sobel_over_8_at(theta, g.ph, g.pw, k / g.pw, k % g.pw, pf[k], pf[np + k]);
+  double sq = 0.0, sp = 0.0;
+  const int64_t plane = (int64_t)g.H * g.W;
+  for (int i = 0; i < g.H; ++i)
+    for (int j = 0; j < g.W; ++j) {
+      const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+      const int64_t k = (int64_t)i * g.W + j;
+      q[k] = p.q;
+      F[k] = p.m ? p.f0 : (T)0;
+      F[plane + k] = p.m ? p.f1 : (T)0;
+      trans[k] = p.t0;
+      trans[plane + k] = p.t1;
+      sq += (double)p.q * (double)p.q;
+      if (p.m) sp += sqrt((double)p.t0 * (double)p.t0 + (double)p.t1 * (double)p.t1);
+    }
+  sums[0] = sq;
+  sums[1] = sp;
+}
+
+template <typename T>
+static void columns_t(const Geom& g, const T* q, const T* meas, double q2, double w_data, double* colsum, double* scal) {
+  const double n = sqrt(q2);
+  const T inv = (T)(1.0 / (n + kNormEps));
+  for (int j = 0; j < g.W; ++j) colsum[j] = 0.0;
+  for (int i = 0; i < g.H; ++i)
+    for (int j = 0; j < g.W; ++j) {
+      const int64_t k = (int64_t)i * g.W + j;
+      const double D = (double)residual<T>(q[k], in_roi(g, i, j), meas[k], inv);
+      colsum[j] += D < 0 ? -D : D;
+    }
+  double mx = -1.0, cnt = 0.0;
+  for (int j = 0; j < g.W; ++j) mx = colsum[j] > mx ? colsum[j] : mx;
+  for (int j = 0; j < g.W; ++j) cnt += colsum[j] == mx ? 1.0 : 0.0;
+  const double tie_w = w_data / cnt;
+  double S = 0.0;
+  for (int j = g.y0; j < g.y1; ++j) {
+    if (colsum[j] != mx) continue;
+    for (int i = g.x0; i < g.x1; ++i) {
+      const int64_t k = (int64_t)i * g.W + j;
+      S += sgn((double)residual<T>(q[k], true, meas[k], inv)) * tie_w * (double)q[k];
+    }
+  }
+  scal[0] = n; scal[1] = mx; scal[2] = tie_w; scal[3] = S;
+}
+
+template <typename T>
+static void backward_t(const Geom& g, const T* theta, const T* pf, const T* gx, const T* gy, const T* meas, const T* dF,
+                       const double* colsum, const double* scal, double w_pxy, T* dU, T* dPad, T* dP, T* grad) {
+  BackScalars s;
+  s.n = scal[0]; s.mx = scal[1]; s.tie_w = scal[2]; s.S = scal[3];
+  const int64_t plane = (int64_t)g.H * g.W;
+  const double w_pxy_hw = w_pxy / ((double)g.H * g.W);
+  for (int i = 0; i < g.H; ++i)
+    for (int j = 0; j < g.W; ++j) {
+      const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+      const int64_t k = (int64_t)i * g.W + j;
+      T out[4];
+      backward_pixel<T>(p, meas[k], colsum[j] == s.mx, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw, out);
+      for (int c = 0; c < 4; ++c) dU[c * plane + k] = out[c];
+    }
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  for (int A = 0; A < PH; ++A)
+    for (int B = 0; B < PW; ++B) {
+      int i0, i1, j0, j1;
+      cell_support(A, g.patch, g.h1, g.H, i0, i1);
+      cell_support(B, g.patch, g.w1, g.W, j0, j1);
+      double acc[4] = {0, 0, 0, 0};
+      for (int i = i0; i < i1; ++i)
+        for (int j = j0; j < j1; ++j) {
+          const double w = (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)cell_weight<T>(B, j, g.w1, g.patch);
+          for (int c = 0; c < 4; ++c) acc[c] += w * (double)dU[c * plane + (int64_t)i * g.W + j];
+        }
+      for (int c = 0; c < 4; ++c) dPad[((int64_t)c * PH + A) * PW + B] = (T)acc[c];
+    }
+  const int np = g.ph * g.pw;
+  for (int k = 0; k < 4 * np; ++k) {
+    const int c = k / np, a = (k % np) / g.pw, b = k % g.pw;
+    int a0, a1, b0, b1;
+    fold_range(a, g.ph, g.pad, a0, a1);
+    fold_range(b, g.pw, g.pad, b0, b1);
+    double sacc = 0.0;
+    for (int A = a0; A < a1; ++A)
+      for (int B = b0; B < b1; ++B) sacc += (double)dPad[((int64_t)c * PH + A) * PW + B];
+    dP[k] = (T)sacc;
+  }
+  for (int k = 0; k < np; ++k) {
+    grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
+    grad[np + k] = dP[2 * np + k];
+    grad[2 * np + k] = dP[3 * np + k];
+  }
+}
+
+extern "C" {
+
+// dims = {H, W, ph, pw, patch, x0, x1, y0, y1}; is_f64 selects the element type of every array argument.
+int eklt_host_forward(const int* dims, int is_f64, const void* theta, const void* gx, const void* gy, void* pf, void* q,
+                      void* F, void* trans, double* sums) {
+  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
+  if (is_f64) forward_t<double>(g, (const double*)theta, (const double*)gx, (const double*)gy, (double*)pf, (double*)q, (double*)F, (double*)trans, sums);
+  else forward_t<float>(g, (const float*)theta, (const float*)gx, (const float*)gy, (float*)pf, (float*)q, (float*)F, (float*)trans, sums);
+  return 0;
+}
+
+int eklt_host_columns(const int* dims, int is_f64, const void* q, const void* meas, double q2, double w_data, double* colsum,
+                      double* scal) {
+  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
+  if (is_f64) columns_t<double>(g, (const double*)q, (const double*)meas, q2, w_data, colsum, scal);
+  else columns_t<float>(g, (const float*)q, (const float*)meas, q2, w_data, colsum, scal);
+  return 0;
+}
+
+int eklt_host_backward(const int* dims, int is_f64, const void* theta, const void* pf, const void* gx, const void* gy,
+                       const void* meas, const void* dF, const double* colsum, const double* scal, double w_pxy, void* dU,
+                       void* dPad, void* dP, void* grad) {
+  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
+  if (is_f64)
+    backward_t<double>(g, (const double*)theta, (const double*)pf, (const double*)gx, (const double*)gy, (const double*)meas,
+                       (const double*)dF, colsum, scal, w_pxy, (double*)dU, (double*)dPad, (double*)dP, (double*)grad);
+  else
+    backward_t<float>(g, (const float*)theta, (const float*)pf, (const float*)gx, (const float*)gy, (const float*)meas,
+                      (const float*)dF, colsum, scal, w_pxy, (float*)dU, (float*)dPad, (float*)dP, (float*)grad);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+"""SURVEY 8f-1, CPU side.
+
+1. oracle/spec_eklt.py against tests/golden/reference_eklt_v1.npz (outputs of the unmodified reference
+   `PatchEkltPyramid2`: objective value, autograd gradient, dense fields, a complete coarse-to-fine estimate).
+2. the per-pixel / per-cell functions the CUDA kernels are built from (csrc/ebos_eklt_math.cuh), compiled by g++
+   into a serial checker (tests/eklt_host_check.cpp) and walked in kernel order, against the oracle and the goldens.
+   This is a check of the ARITHMETIC in the GPU-less build container; the GPU parity tests are in test_gpu_eklt.py.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import spec_eklt as E
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "reference_eklt_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(GOLDEN)
+    d = {k: g[k] for k in g.files}
+    d["roi_t"] = tuple(int(v) for v in d["roi"])
+    d["levels_t"] = [tuple(int(v) for v in l) for l in d["levels"]]
+    return d
+
+
+def _objective(gold, theta, patch, **kw):
+    wd, wtv, wp = gold["cost_weights"]
+    return E.objective(theta, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"], gold["roi_t"],
+                       patch, wd, wtv, wp, **kw)
+
+
+# ---- 1. oracle vs reference -------------------------------------------------------------------------------------
+def test_pyramid_geometry_matches_reference(gold):
+    H, W = (int(v) for v in gold["image"])
+    assert E.pyramid_levels((H, W)) == gold["levels_t"]
+    # hot_plate1 size: 12 x 20 patches of 64 px, 24 rows off the lattice
+    assert E.pyramid_levels((720, 1280)) == [(64, 12, 20), (32, 23, 40), (16, 45, 80), (8, 90, 160)]
+    g = E.upsample_geometry((720, 1280), 12, 20, 64)
+    assert (g["h1"], g["w1"], g["dense_h"]) == (88, 64, 896)
+    assert [E.level_iterations(600, 4, l) for l in range(4)] == [120, 150, 200, 300]
+
+
+@pytest.mark.parametrize("name", ["start", "random", "far"])
+def test_oracle_objective_and_gradient_match_reference_autograd(gold, name):
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        key = f"L{scale}_{name}"
+        r = _objective(gold, gold[key + "_theta"], patch)
+        assert abs(r["loss"] - float(gold[key + "_loss"])) <= 1e-13
+        ref = gold[key + "_grad"]
+        assert np.abs(r["grad"] - ref).max() <= 1e-12 * np.abs(ref).max()
+        if name == "random":
+            assert np.abs(r["flow"] - gold[key + "_flow"]).max() <= 1e-14
+            assert np.abs(r["trans"] - gold[key + "_trans"]).max() <= 1e-14
+            assert np.abs(r["pred"] - gold[key + "_pred"]).max() <= 1e-15
+
+
+def test_oracle_gradient_matches_finite_differences(gold):
+    """Independent of the reference: central differences of the restated forward (smooth directions only)."""
+    patch, ph, pw = gold["levels_t"][2]
+    th = gold["L3_random_theta"].copy()
+    r = _objective(gold, th, patch)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        d = rng.normal(size=th.shape)
+        d[0] = 0                                      # TV of the intensity flow is only piecewise smooth; keep to pxy
+        eps = 1e-7
+        lp = _objective(gold, th + eps * d, patch, want_grad=False)["loss"]
+        lm = _objective(gold, th - eps * d, patch, want_grad=False)["loss"]
+        fd = (lp - lm) / (2 * eps)
+        an = float(np.sum(r["grad"] * d))
+        assert abs(fd - an) <= 2e-5 * max(1.0, abs(an))
+
+
+def test_oracle_solve_matches_reference_estimate(gold):
+    """Coarse-to-fine Adam from the reference's own start.  The first level is reproduced to rounding; later levels
+    drift by ~1e-6 because sign() of rounding-level TV differences (replicate-padded rows) is chaotic -- in the
+    reference itself as much as here."""
+    H, W = (int(v) for v in gold["image"])
+    wd, wtv, wp = gold["cost_weights"]
+    th = gold["solve_x0"].copy()
+    n_iter = int(gold["n_iter"])
+    levels = gold["levels_t"]
+    tol = [1e-12, 1e-4, 1e-4, 1e-4]
+    for li, (patch, ph, pw) in enumerate(levels):
+        if li > 0:
+            th = E.resize_params(th, (ph, pw))
+        th, losses = E.solve_level(th, E.level_iterations(n_iter, len(levels), li), gold["grad_x"], gold["grad_y"],
+                                   gold["measured"], gold["weight_inverse"], gold["roi_t"], patch, w_data=wd, w_tv=wtv,
+                                   w_pxy=wp)
+        assert np.abs(th - gold[f"solve_L{li + 1}"]).max() <= tol[li]
+    patch, ph, pw = levels[-1]
+    dense = E.upsample_patch(E.sobel_over_8(th[0]), patch, (H, W)) * E.roi_mask((H, W), gold["roi_t"])
+    assert np.sqrt(np.mean((dense - gold["solve_flow"]) ** 2)) <= 1e-5
+
+
+# ---- 2. kernel arithmetic (serial g++ build of the device functions) vs oracle -----------------------------------
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = tmp_path_factory.mktemp("eklt") / "libeklt_host_check.so"
+    cmd = [gxx, "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", os.path.join(HERE, "eklt_host_check.cpp"),
+           "-o", str(out)]
+    subprocess.run(cmd, check=True)
+    return ctypes.CDLL(str(out))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dtype=np.float64):
+    H, W = gx.shape
+    _, ph, pw = theta.shape
+    wd, wtv, wp = (float(v) for v in weights)
+    dims = (ctypes.c_int * 9)(H, W, ph, pw, patch, *roi)
+    f64 = int(dtype == np.float64)
+    c = lambda a: np.ascontiguousarray(a, dtype=dtype)
+    theta, gx, gy, meas, winv = c(theta), c(gx), c(gy), c(meas), c(winv)
+    pf = np.zeros((2, ph, pw), dtype)
+    q = np.zeros((H, W), dtype)
+    F = np.zeros((2, H, W), dtype)
+    tr = np.zeros((2, H, W), dtype)
+    sums = np.zeros(2)
+    lib.eklt_host_forward(dims, f64, _p(theta), _p(gx), _p(gy), _p(pf), _p(q), _p(F), _p(tr), _p(sums))
+    colsum = np.zeros(W)
+    scal = np.zeros(4)
+    lib.eklt_host_columns.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+    lib.eklt_host_columns(dims, f64, _p(q), _p(meas), float(sums[0]), wd, _p(colsum), _p(scal))
+    # the TV kernel (ebos_flow_tv) sits between the two passes on the GPU; here: the oracle's TV on the checker's F
+    gxx, gyy = E._tv_parts(F.astype(np.float64), winv.astype(np.float64))
+    tv = np.mean(np.abs(gxx) + np.abs(gyy))
+    dF = c(wtv * E._tv_adjoint(np.sign(gxx) * winv / F.size, np.sign(gyy) * winv / F.size))
+    dU = np.zeros((4, H, W), dtype)
+    dPad = np.zeros((4, ph + 2, pw + 2), dtype)
+    dP = np.zeros((4, ph, pw), dtype)
+    grad = np.zeros((3, ph, pw), dtype)
+    lib.eklt_host_backward.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8 + [ctypes.c_double] + \
+                                      [ctypes.c_void_p] * 4
+    lib.eklt_host_backward(dims, f64, _p(theta), _p(pf), _p(gx), _p(gy), _p(meas), _p(dF), _p(colsum), _p(scal), wp,
+                           _p(dU), _p(dPad), _p(dP), _p(grad))
+    loss = wd * scal[1] + wtv * tv + wp * sums[1] / (H * W)
+    return {"loss": loss, "grad": grad, "q": q, "F": F, "trans": tr, "pf": pf, "colsum": colsum, "n": scal[0], "dU": dU}
+
+
+@pytest.mark.parametrize("name", ["start", "random", "far"])
+def test_kernel_arithmetic_fp64_matches_oracle_and_reference(gold, host_lib, name):
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        key = f"L{scale}_{name}"
+        th = gold[key + "_theta"]
+        h = host_value_and_grad(host_lib, th, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"],
+                                gold["roi_t"], patch, gold["cost_weights"])
+        r = _objective(gold, th, patch)
+        # same operation order as the oracle: the fields agree bit for bit (this is what keeps the sign() of the
+        # rounding-level TV differences identical)
+        assert np.array_equal(h["pf"], E.sobel_over_8(th[0]))
+        assert np.array_equal(h["F"], r["flow"] * E.roi_mask(r["q"].shape, gold["roi_t"])[None])
+        assert np.array_equal(h["trans"], r["trans"])
+        assert np.abs(h["q"] - r["q"]).max() <= 1e-12 * np.abs(r["q"]).max()
+        assert np.abs(h["colsum"] - r["colsum"]).max() <= 1e-13
+        assert abs(h["loss"] - r["loss"]) <= 1e-13
+        assert np.abs(h["grad"] - r["grad"]).max() <= 1e-11 * np.abs(r["grad"]).max()
+        ref = gold[key + "_grad"]
+        assert abs(h["loss"] - float(gold[key + "_loss"])) <= 1e-13
+        assert np.abs(h["grad"] - ref).max() <= 1e-11 * np.abs(ref).max()
+
+
+def test_kernel_arithmetic_fp32_close_to_fp64(gold, host_lib):
+    """The fp32 instantiation (speed path) evaluated on fp32-rounded inputs stays within fp32 accuracy of the fp64
+    oracle at smooth points (random theta: samples are far from the cell boundaries)."""
+    patch, ph, pw = gold["levels_t"][1]
+    th = gold["L2_random_theta"]
+    h = host_value_and_grad(host_lib, th, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"],
+                            gold["roi_t"], patch, gold["cost_weights"], dtype=np.float32)
+    r = _objective(gold, th, patch)
+    assert abs(h["loss"] - r["loss"]) <= 2e-5 * abs(r["loss"])
+    assert np.abs(h["q"] - r["q"]).max() <= 2e-5 * np.abs(r["q"]).max()
+
+
+def test_kernel_arithmetic_general_roi_and_odd_sizes(host_lib):
+    """Sizes that are not multiples of anything, ROI touching the border, patch grid with a single row."""
+    rng = np.random.default_rng(5)
+    for (H, W, patch, roi) in [(37, 53, 8, (0, 37, 0, 53)), (50, 70, 64, (3, 47, 10, 70)), (33, 130, 16, (5, 6, 7, 9))]:
+        ph, pw = E.patch_grid((H, W), patch)
+        th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-2, 2, (2, ph, pw))])
+        gx, gy = rng.normal(size=(2, H, W)) * 50
+        M = E.roi_mask((H, W), roi)
+        meas = rng.normal(size=(H, W)) * M
+        meas /= np.linalg.norm(meas)
+        winv = rng.uniform(0.05, 1.0, (H, W))
+        w = (1.0, 0.5, 0.1)
+        h = host_value_and_grad(host_lib, th, gx, gy, meas, winv, roi, patch, w)
+        r = E.objective(th, gx, gy, meas, winv, roi, patch, *w)
+        assert abs(h["loss"] - r["loss"]) <= 1e-12
+        assert np.abs(h["grad"] - r["grad"]).max() <= 1e-10 * np.abs(r["grad"]).max()
