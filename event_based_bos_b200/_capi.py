@@ -80,6 +80,8 @@ SIGNATURES = {
                                          c_void_p, c_void_p]),
     "ebos_eklt_upsample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ebos_eklt_patch_flow": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ebos_sepconv2d": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                               c_void_p]),
 }
 
 _lib = None

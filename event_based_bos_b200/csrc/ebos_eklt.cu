@@ -287,6 +287,19 @@ __global__ void __launch_bounds__(256) k_upsample(Geom g, const T* __restrict__ 
   }
 }
 
+
+// separable correlation, one pass per axis (axis 1 = along columns first, like cv2's row filter, then axis 0)
+template <typename T>
+__global__ void __launch_bounds__(256) k_correlate(const T* __restrict__ in, int H, int W, ConvTaps taps, int axis, int border,
+                                                   T* __restrict__ out) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (j >= W) return;
+  for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < H; i += gridDim.y * 8) {
+    out[(int64_t)i * W + j] = axis == 1 ? correlate_at<T>(in + (int64_t)i * W, 1, j, W, taps, border)
+                                        : correlate_at<T>(in + j, W, i, H, taps, border);
+  }
+}
+
 static dim3 plane_grid(int H, int W) {
   const int gx = (W + 31) / 32;
   // enough row groups to fill the machine about four times over, at most one group per 8 rows
@@ -421,6 +434,36 @@ int ebos_eklt_patch_flow(const void* intensity, int ph, int pw, int dtype, void*
   else
     k_patch_flow<float><<<(np + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)intensity, ph, pw, (float*)patch_flow);
   EBOS_LAUNCH_CHECK("ebos_eklt_patch_flow");
+  return EBOS_OK;
+}
+
+int ebos_sepconv2d(const void* image, int H, int W, const double* taps_rows, int n_rows, const double* taps_cols,
+                   int n_cols, int border, int dtype, void* tmp, void* out, void* stream) {
+  EBOS_REQUIRE(image && tmp && out && taps_rows && taps_cols && H >= 1 && W >= 1, "ebos_sepconv2d: bad argument");
+  EBOS_REQUIRE(n_rows >= 1 && n_rows <= kMaxTaps && (n_rows & 1) && n_cols >= 1 && n_cols <= kMaxTaps && (n_cols & 1),
+               "ebos_sepconv2d: tap counts must be odd and at most 127");
+  EBOS_REQUIRE(border == 0 || border == 1, "ebos_sepconv2d: border must be 0 (reflect-101) or 1 (reflect)");
+  if (dtype != EBOS_F32 && dtype != EBOS_F64) {
+    set_error("ebos_sepconv2d: unsupported dtype");
+    return EBOS_ERR_UNSUPPORTED;
+  }
+  ConvTaps tr, tc;
+  tr.n = n_rows;
+  tc.n = n_cols;
+  for (int k = 0; k < kMaxTaps; ++k) {
+    tr.w[k] = k < n_rows ? taps_rows[k] : 0.0;
+    tc.w[k] = k < n_cols ? taps_cols[k] : 0.0;
+  }
+  const dim3 pg = plane_grid(H, W);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == EBOS_F64) {
+    k_correlate<double><<<pg, 256, 0, st>>>((const double*)image, H, W, tc, 1, border, (double*)tmp);
+    k_correlate<double><<<pg, 256, 0, st>>>((const double*)tmp, H, W, tr, 0, border, (double*)out);
+  } else {
+    k_correlate<float><<<pg, 256, 0, st>>>((const float*)image, H, W, tc, 1, border, (float*)tmp);
+    k_correlate<float><<<pg, 256, 0, st>>>((const float*)tmp, H, W, tr, 0, border, (float*)out);
+  }
+  EBOS_LAUNCH_CHECK("ebos_sepconv2d");
   return EBOS_OK;
 }
 

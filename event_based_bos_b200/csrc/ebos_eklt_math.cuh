@@ -261,5 +261,31 @@ EK_HD T sobel_over_8_adjoint_at(const T* d0, const T* d1, int ph, int pw, int r,
   return (T)(acc / 8.0);
 }
 
+
+// ---- separable correlation with mirrored borders (per-window preprocessing) --------------------------------------
+// border 0: reflect-101  (cv2.BORDER_REFLECT_101, the default of cv2.Sobel / cv2.GaussianBlur:  c b | a b c | b a)
+// border 1: reflect      (scipy.ndimage mode='reflect':                                         b a | a b c | c b)
+constexpr int kMaxTaps = 127;
+struct ConvTaps {
+  double w[kMaxTaps];
+  int n;
+};
+EK_HD int border_index(int i, int n, int border) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (border == 0) i = i < 0 ? -i : 2 * (n - 1) - i;
+    else i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+  }
+  return i;
+}
+// out = sum_k w[k] * in[border(i + k - (n-1)/2)] along one axis (stride between consecutive samples of that axis)
+template <typename T>
+EK_HD T correlate_at(const T* line, int64_t stride, int i, int n, const ConvTaps& t, int border) {
+  double acc = 0.0;
+  const int r = (t.n - 1) / 2;
+  for (int k = 0; k < t.n; ++k) acc += t.w[k] * (double)line[(int64_t)border_index(i + k - r, n, border) * stride];
+  return (T)acc;
+}
+
 }  // namespace eklt
 }  // namespace ebos

@@ -1,0 +1,144 @@
+"""`PatchEkltPyramid2` -- the solver configs/hot_plate1.yaml selects (`method: patch_eklt_pyramid2`), with the inner
+loop on the GPU.
+
+Mirrors the constructor contract, config keys, start values, level schedule and return convention of
+src/solver/patch_eklt_pyramid2.py (and of its bases patch_eklt_dependent.py, patch_eklt.py,
+generative_max_likelihood.py) for the configuration the reference ships:
+
+    generative_ml: poisson_model = true, optimize_warp = true, no_polarity = false, weight_loss_by_event_hist = false
+    cost_with_weight: diff_norm, image_gradient, flow_norm_pxy          optimizer.method: Adam
+
+Other switch combinations (angle model, scipy/optuna optimisers, event-histogram weights, no_polarity) select different
+objectives upstream and raise NotImplementedError here instead of silently computing something else.
+Visualisation / video hooks of the upstream class are not reproduced.
+"""
+import logging
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _capi, eklt
+from .base import SolverBase
+
+logger = logging.getLogger(__name__)
+
+AVAILABLE_MODEL_IMAGES = ["background", "current", "black"]
+SUPPORTED_COSTS = ("diff_norm", "image_gradient", "flow_norm_pxy")
+
+
+def _flag(cfg: dict, key: str) -> bool:
+    return key in cfg and bool(cfg[key])
+
+
+class PatchEkltPyramid2(SolverBase):
+    """Pyramidal (coarse-to-fine) EKLT estimation; patches of 64 -> 8 px (src/solver/patch_eklt_pyramid2.py:22-51)."""
+
+    def __init__(self, orig_image_shape: tuple, crop_image_shape: tuple, calibration_parameter: dict = {},
+                 solver_config: dict = {}, visualize_module=None) -> None:
+        super().__init__(orig_image_shape, crop_image_shape, calibration_parameter, solver_config, visualize_module)
+        self._frame = None
+        self._opt_config = self.slv_config["optimizer"]
+        self._opt_method = self._opt_config["method"]
+        self._gml_config = self.slv_config["generative_ml"]
+        assert self._gml_config["model_image"] in AVAILABLE_MODEL_IMAGES, \
+            f"the setting 'mode_image' must be in {AVAILABLE_MODEL_IMAGES}."
+        self.is_angle_model = _flag(self._gml_config, "angle_model")
+        self.is_poisson_model = _flag(self._gml_config, "poisson_model")
+        self.do_weight_inverse = _flag(self._gml_config, "weight_loss_by_inverse_event_hist")
+        self.cost_weight = self.slv_config["cost_with_weight"]
+        unsupported = []
+        if self._opt_method != "Adam":
+            unsupported.append(f"optimizer.method={self._opt_method!r} (only 'Adam')")
+        if not self.is_poisson_model or self.is_angle_model:
+            unsupported.append("generative_ml.poisson_model must be true and angle_model false")
+        if not _flag(self._gml_config, "optimize_warp"):
+            unsupported.append("generative_ml.optimize_warp must be true")
+        if _flag(self._gml_config, "no_polarity") or _flag(self._gml_config, "weight_loss_by_event_hist"):
+            unsupported.append("generative_ml.no_polarity / weight_loss_by_event_hist must be false")
+        if _flag(self._gml_config, "px-py_as-angle-magnitude"):
+            unsupported.append("px-py_as-angle-magnitude is optuna-only upstream")
+        if self._gml_config.get("sobel_ksize", 3) != 3:
+            unsupported.append("generative_ml.sobel_ksize must be 3")
+        extra = sorted(set(self.cost_weight) - set(SUPPORTED_COSTS))
+        if extra:
+            unsupported.append(f"cost terms {extra} (supported: {SUPPORTED_COSTS})")
+        if unsupported:
+            raise NotImplementedError("event_based_bos_b200.PatchEkltPyramid2 implements the hot_plate1 objective only: "
+                                      + "; ".join(unsupported))
+        ekc = self.slv_config.get("eklt", {}) or {}
+        self._dtype = torch.float32 if str(ekc.get("precision", "64")) == "32" else torch.float64
+        self.use_cuda_graph = bool(ekc.get("cuda_graph", True))
+        self.store_history = bool(ekc.get("store_history", False))
+        self.history = {}
+        self.levels = eklt.pyramid_levels(tuple(self.orig_image_shape), 64, 8)
+        self.coarest_scale, self.finest_scale = 1, len(self.levels) + 1        # upstream's spelling
+        self.iter_cnt = 0
+        self.estimate_mask_dense_numpy = np.zeros(self.orig_image_shape)
+        self.estimate_mask_dense_numpy[self.crop_xmin:self.crop_xmax, self.crop_ymin:self.crop_ymax] = 1
+
+    # -- per-window preprocessing ---------------------------------------------------------------------------------
+    def _set_frame(self, frame: np.ndarray) -> None:
+        """Frame gradients (src/solver/generative_max_likelihood.py:194-213)."""
+        _capi.require_device()
+        self._frame = frame
+        f = torch.as_tensor(np.asarray(frame), device="cuda").to(self._dtype)
+        self._gradient_x_torch, self._gradient_y_torch = eklt.frame_gradients(
+            f, use_log_intensity=_flag(self._gml_config, "use_log_intensity"))
+
+    def calculate_iwe_cache(self, events: np.ndarray) -> None:
+        """Polarity histogram -> measured increment and weight_inverse (src/solver/patch_eklt.py:271-304)."""
+        pol = self.orig_imager.create_iwe(events, method="polarity", sigma=0)
+        hist = torch.as_tensor(pol[0] - pol[1], device="cuda").to(self._dtype)
+        roi = (self.crop_xmin, self.crop_xmax, self.crop_ymin, self.crop_ymax)
+        self.cache_measured, self.weight_inverse = eklt.measurement_and_weights(
+            hist, roi, iwe_sigma=self._gml_config["iwe_sigma"], weight_inverse=self.do_weight_inverse)
+
+    def _initialize_velocity(self) -> np.ndarray:
+        """src/solver/generative_max_likelihood.py:436-442 (poisson model + optimize_warp)."""
+        return np.array([np.random.random() * 2.0 - 1, 0.0, 0.0], dtype=np.float64)
+
+    def _start_parameters(self, level: int, previous: Optional[torch.Tensor]) -> torch.Tensor:
+        """x0 of a level (src/solver/patch_eklt_pyramid2.py:225-248), drawing from np.random exactly like upstream:
+        one draw to measure the parameter dimension, then -- at the coarsest level -- one per patch; the per-patch
+        triples are concatenated and reshaped to [3,ph,pw] as upstream does (which interleaves them)."""
+        _, ph, pw = self.levels[level]
+        self.n_parameter_dim = len(self._initialize_velocity())
+        if level == 0:
+            x0 = np.concatenate([self._initialize_velocity() for _ in range(ph * pw)]).reshape((3, ph, pw))
+            return torch.as_tensor(x0, device="cuda").to(self._dtype)
+        return eklt.resize_params(previous, (ph, pw))
+
+    # -- main entry --------------------------------------------------------------------------------------------------
+    def estimate(self, events: np.ndarray, *args, **kwargs) -> np.ndarray:
+        """events [n,4] (row, col, t, p) + `frame=` (and `background=`)  ->  dense flow [2,H,W] float64, zero outside
+        the ROI (src/solver/patch_eklt_pyramid2.py:129-190)."""
+        if self._gml_config["model_image"] == "current":
+            self._set_frame(kwargs["frame"])
+        elif self._gml_config["model_image"] == "black":
+            self._set_frame(np.zeros_like(kwargs["frame"]))
+        elif self._frame is None and self._gml_config["model_image"] == "background":
+            self._set_frame(kwargs["background"])
+        self.calculate_iwe_cache(events)
+        roi = (self.crop_xmin, self.crop_xmax, self.crop_ymin, self.crop_ymax)
+        weights = tuple(float(self.cost_weight.get(k, 0.0)) for k in SUPPORTED_COSTS)
+        problem = eklt.EkltProblem(self._gradient_x_torch, self._gradient_y_torch, self.cache_measured,
+                                   self.weight_inverse, roi, weights)
+        theta = None
+        self.best_params_per_scale = {}
+        self.history = {}
+        n_levels = len(self.levels)
+        for li, (patch, ph, pw) in enumerate(self.levels):
+            scale = li + 1
+            logger.info(f"Scale {scale}, patch num {(ph, pw)}, patch shape {(patch, patch)}")
+            x0 = self._start_parameters(li, theta)
+            iters = self._opt_config["n_iter"] // (self.finest_scale - scale + 1)
+            hist = [] if self.store_history else None
+            theta = problem.level(patch).solve(x0, iters, lr=0.05, cuda_graph=self.use_cuda_graph, history=hist)
+            self.best_params_per_scale[scale] = theta
+            if hist is not None:
+                self.history[scale] = hist
+        patch = self.levels[-1][0]
+        dense = eklt.upsample(eklt.patch_flow(theta[0]), patch, tuple(self.orig_image_shape))
+        self.iter_cnt += 1
+        return dense.double().cpu().numpy() * self.estimate_mask_dense_numpy

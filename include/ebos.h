@@ -298,6 +298,16 @@ EBOS_API int ebos_eklt_upsample(const void* patch_values, int channels, int H, i
                        void* dense, void* stream);
 EBOS_API int ebos_eklt_patch_flow(const void* intensity, int ph, int pw, int dtype, void* patch_flow, void* stream);
 
+/* Separable 2-D correlation with mirrored borders -- the per-window preprocessing of the EKLT solvers:
+ *   cv2.Sobel(frame, CV_64F, 0|1, 1|0, ksize=3)        _set_frame, src/solver/generative_max_likelihood.py:194-213
+ *   cv2.GaussianBlur(hist, None, sigma)                calculate_iwe_cache, src/solver/patch_eklt.py:271-293
+ *   scipy.ndimage.gaussian_filter(|hist|, 10)          weight_inverse, src/solver/patch_eklt.py:295-304
+ * out[i,j] = sum_u sum_v taps_rows[u] * taps_cols[v] * image[b(i+u-ru), b(j+v-rv)], columns pass first.
+ * taps_*: HOST arrays (odd length <= 127); border 0 = reflect-101 (cv2 default), 1 = reflect (scipy 'reflect').
+ * image, tmp, out: [H,W] of dtype on the device (tmp is scratch; out may not alias image or tmp). */
+EBOS_API int ebos_sepconv2d(const void* image, int H, int W, const double* taps_rows, int n_rows, const double* taps_cols,
+                   int n_cols, int border, int dtype, void* tmp, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,234 @@
+"""EKLT inner loop of PatchEkltPyramid2 on the GPU against the reference goldens
+(tests/golden/reference_eklt_v1.npz, produced by the unmodified reference) and the CPU oracle (oracle/spec_eklt.py).
+
+Bars: float64 objective / gradient within 1e-9 relative of the reference's autograd (the reference solves in float64);
+float32 instantiation within 1e-4 of it; after a complete coarse-to-fine solve the flow within 1e-3 px RMS
+(BASELINE.json north_star).  The file name sorts last on purpose: these kernels are the newest part of the library.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec_eklt as E
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = __file__.replace("test_gpu_zz_eklt.py", "golden/reference_eklt_v1.npz")
+
+# the `solver:` block of configs/hot_plate1.yaml (reference tree), with the fixture's size, ROI and iteration count
+HOT_PLATE1_SOLVER = {
+    "filter": {"filters": None, "parameters": {"xmin": 8, "xmax": 104, "ymin": 40, "ymax": 136}},
+    "method": "patch_eklt_pyramid2", "warp_direction": "first", "motion_model": "2d-translation",
+    "parameters": ["trans_x", "trans_y"], "cost": "hybrid", "outer_padding": 0,
+    "cost_with_weight": {"diff_norm": 1.0, "image_gradient": 0.5, "flow_norm_pxy": 0.1},
+    "iwe": {"method": "bilinear_vote", "blur_sigma": 3},
+    "optimizer": {"method": "Adam", "n_iter": 24, "parameters": {}},
+    "generative_ml": {"weight_loss_by_event_hist": False, "weight_sigma": 5, "weight_loss_by_inverse_event_hist": True,
+                      "optimize_warp": True, "iwe_sigma": 2, "viz_diff_scale": [-0.25, 0.25], "no_polarity": False,
+                      "model_image": "current", "use_log_intensity": False, "poisson_model": True},
+    "patch_eklt": {"patch_size": 4, "sliding_window": 2, "do_event_thresholding": False, "event_thres": 8},
+}
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(GOLDEN)
+    d = {k: g[k] for k in g.files}
+    d["roi_t"] = tuple(int(v) for v in d["roi"])
+    d["levels_t"] = [tuple(int(v) for v in l) for l in d["levels"]]
+    return d
+
+
+@pytest.fixture(scope="module")
+def eklt():
+    from event_based_bos_b200 import eklt as _eklt
+
+    return _eklt
+
+
+def dev(a, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda").to(dtype).contiguous()
+
+
+def problem_from_gold(eklt, gold, dtype=torch.float64):
+    return eklt.EkltProblem(dev(gold["grad_x"], dtype), dev(gold["grad_y"], dtype), dev(gold["measured"], dtype),
+                            dev(gold["weight_inverse"], dtype), gold["roi_t"], tuple(gold["cost_weights"]))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_patch_flow_and_upsample_match_reference_fields(gold, eklt):
+    H, W = (int(v) for v in gold["image"])
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        th = gold[f"L{scale}_random_theta"]
+        pf = eklt.patch_flow(dev(th[0]))
+        assert np.abs(pf.cpu().numpy() - E.sobel_over_8(th[0])).max() <= 1e-15
+        flow = eklt.upsample(pf, patch, (H, W)).cpu().numpy()
+        trans = eklt.upsample(dev(th[1:3]), patch, (H, W)).cpu().numpy()
+        assert np.abs(flow - gold[f"L{scale}_random_flow"]).max() <= 1e-14
+        assert np.abs(trans - gold[f"L{scale}_random_trans"]).max() <= 1e-14
+
+
+@pytest.mark.parametrize("name", ["start", "random", "far"])
+def test_objective_and_gradient_fp64_match_reference_autograd(gold, eklt, name):
+    prob = problem_from_gold(eklt, gold)
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        key = f"L{scale}_{name}"
+        lvl = prob.level(patch)
+        assert (lvl.ph, lvl.pw) == (ph, pw)
+        loss, grad = lvl.value_and_grad(dev(gold[key + "_theta"]))
+        assert abs(float(loss[0]) - float(gold[key + "_loss"])) <= 1e-11, key
+        assert rel(grad.cpu().numpy(), gold[key + "_grad"]) <= 1e-9, key
+        # evaluating again gives the same answer (workspace contents do not leak between calls)
+        loss2, grad2 = lvl.value_and_grad(dev(gold[key + "_theta"]))
+        assert abs(float(loss2[0]) - float(gold[key + "_loss"])) <= 1e-11, key
+
+
+def test_loss_terms_match_oracle(gold, eklt):
+    prob = problem_from_gold(eklt, gold)
+    patch, ph, pw = gold["levels_t"][2]
+    th = gold["L3_random_theta"]
+    lvl = prob.level(patch)
+    lvl.value_and_grad(dev(th))
+    terms = lvl.loss_terms()
+    wd, wtv, wp = gold["cost_weights"]
+    r = E.objective(th, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"], gold["roi_t"], patch,
+                    wd, wtv, wp, want_grad=False)
+    for k, ref in (("norm", r["n"]), ("data", r["data"]), ("tv", r["tv"]), ("pxy", r["pxy"]), ("loss", r["loss"])):
+        assert abs(terms[k] - ref) <= 1e-11 * max(1.0, abs(ref)), k
+
+
+def test_objective_fp32_close_to_reference(gold, eklt):
+    """fp32 instantiation at generic translations.  (At EXACTLY zero translation the samples sit ~1e-5 px beside the
+    pixel centres in fp64 and fp32 rounds them onto a different side, so the translation gradient there is a
+    different one-sided difference: 3-35 % apart in the serial check -- the reason fp64 is the solver default.)"""
+    prob = problem_from_gold(eklt, gold, torch.float32)
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        key = f"L{scale}_random"
+        loss, grad = prob.level(patch).value_and_grad(dev(gold[key + "_theta"], torch.float32))
+        assert abs(float(loss[0]) - float(gold[key + "_loss"])) <= 1e-5 * abs(float(gold[key + "_loss"])), key
+        assert rel(grad.double().cpu().numpy(), gold[key + "_grad"]) <= 1e-4, key
+
+
+def test_general_sizes_and_rois_match_oracle(eklt):
+    rng = np.random.default_rng(5)
+    cases = [(37, 53, 8, (0, 37, 0, 53)), (50, 70, 64, (3, 47, 10, 70)), (33, 130, 16, (5, 6, 7, 9)),
+             (144, 256, 32, (0, 144, 64, 192))]
+    for (H, W, patch, roi) in cases:
+        ph, pw = E.patch_grid((H, W), patch)
+        th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-2, 2, (2, ph, pw))])
+        gx, gy = rng.normal(size=(2, H, W)) * 50
+        M = E.roi_mask((H, W), roi)
+        meas = rng.normal(size=(H, W)) * M
+        meas /= np.linalg.norm(meas)
+        winv = rng.uniform(0.05, 1.0, (H, W))
+        w = (1.0, 0.5, 0.1)
+        prob = eklt.EkltProblem(dev(gx), dev(gy), dev(meas), dev(winv), roi, w)
+        loss, grad = prob.level(patch).value_and_grad(dev(th))
+        r = E.objective(th, gx, gy, meas, winv, roi, patch, *w)
+        assert abs(float(loss[0]) - r["loss"]) <= 1e-11, (H, W, patch)
+        assert rel(grad.cpu().numpy(), r["grad"]) <= 1e-9, (H, W, patch)
+
+
+def test_benchmark_size_properties(eklt):
+    """1280x720 (hot_plate1): the evaluation is deterministic up to atomic order, the gradient of a translation-only
+    perturbation predicts the finite difference of the loss, and zero cost weights give zero loss."""
+    rng = np.random.default_rng(0)
+    H, W, roi = 720, 1280, (0, 720, 320, 960)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frame = 120 + 60 * np.sin(xx / 11.0) * np.cos(yy / 7.0) + rng.normal(0, 2, (H, W))
+    gx, gy = E.frame_gradients(frame)
+    M = E.roi_mask((H, W), roi)
+    meas = rng.normal(size=(H, W)) * M
+    meas /= np.linalg.norm(meas)
+    winv = rng.uniform(0.05, 1.0, (H, W))
+    prob = eklt.EkltProblem(dev(gx), dev(gy), dev(meas), dev(winv), roi, (1.0, 0.5, 0.1))
+    for patch, ph, pw in eklt.pyramid_levels((H, W)):
+        lvl = prob.level(patch)
+        th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-1.5, 1.5, (2, ph, pw))])
+        t = dev(th)
+        l1 = float(lvl.value_and_grad(t)[0][0])
+        g1 = lvl.grad.cpu().numpy().copy()
+        l2 = float(lvl.value_and_grad(t)[0][0])
+        assert abs(l1 - l2) <= 1e-12 * abs(l1)
+        assert rel(lvl.grad.cpu().numpy(), g1) <= 1e-9
+        d = np.zeros_like(th)
+        d[1:] = rng.normal(size=(2, ph, pw))
+        eps = 1e-6
+        lp = float(lvl.value_and_grad(dev(th + eps * d))[0][0])
+        lm = float(lvl.value_and_grad(dev(th - eps * d))[0][0])
+        fd, an = (lp - lm) / (2 * eps), float(np.sum(g1 * d))
+        assert abs(fd - an) <= 1e-3 * max(abs(an), 1e-3), (patch, fd, an)
+    zero = eklt.EkltProblem(dev(gx), dev(gy), dev(meas), dev(winv), roi, (0.0, 0.0, 0.0))
+    loss, grad = zero.level(64).value_and_grad(dev(np.zeros((3, 12, 20))))
+    assert float(loss[0]) == 0.0 and float(grad.abs().max()) == 0.0
+
+
+def test_preprocessing_matches_reference(gold, eklt):
+    gx, gy = eklt.frame_gradients(dev(gold["frame"].astype(np.float64)))
+    assert np.array_equal(gx.cpu().numpy(), gold["grad_x"])       # integers: exact
+    assert np.array_equal(gy.cpu().numpy(), gold["grad_y"])
+    H, W = (int(v) for v in gold["image"])
+    hist = E.polarity_histogram(gold["events"], (H, W))
+    meas, winv = eklt.measurement_and_weights(dev(hist), gold["roi_t"])
+    assert np.abs(meas.cpu().numpy() - gold["measured"]).max() <= 1e-14
+    assert np.abs(winv.cpu().numpy() - gold["weight_inverse"]).max() <= 1e-12
+    # both border modes against the oracle on an odd-sized image, fp32
+    rng = np.random.default_rng(3)
+    img = rng.normal(size=(19, 45))
+    taps = eklt.gaussian_taps_scipy(10.0)
+    for mode, code in (("reflect101", 0), ("reflect", 1)):
+        out = eklt.sepconv2d(dev(img, torch.float32), taps, taps[20:61], mode).cpu().numpy()
+        ref = E.correlate_separable(img, taps, taps[20:61], code)
+        assert np.abs(out - ref).max() <= 1e-5
+
+
+def test_level_solve_graph_and_eager_match_oracle(gold, eklt):
+    prob = problem_from_gold(eklt, gold)
+    patch, ph, pw = gold["levels_t"][0]
+    wd, wtv, wp = gold["cost_weights"]
+    x0 = gold["solve_x0"]
+    ref, losses = E.solve_level(x0, 12, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"],
+                                gold["roi_t"], patch, w_data=wd, w_tv=wtv, w_pxy=wp)
+    hist = []
+    eager = prob.level(patch).solve(dev(x0), 12, cuda_graph=False, history=hist).cpu().numpy()
+    graph = prob.level(patch).solve(dev(x0), 12, cuda_graph=True).cpu().numpy()
+    assert np.abs(eager - ref).max() <= 1e-8
+    assert np.abs(graph - ref).max() <= 1e-8
+    assert np.abs(np.array(hist) - np.array(losses)).max() <= 1e-10
+
+
+def test_solver_drop_in_matches_reference_estimate(gold):
+    """`solver.collections["patch_eklt_pyramid2"]` with the reference's config block, events and frame in,
+    dense flow out; np.random seeded like the golden run (the intensity start is drawn from np.random upstream)."""
+    from event_based_bos_b200 import solver
+
+    H, W = (int(v) for v in gold["image"])
+    roi = gold["roi_t"]
+    cls = solver.collections["patch_eklt_pyramid2"]
+    s = cls((H, W), (roi[1] - roi[0], roi[3] - roi[2]), {}, HOT_PLATE1_SOLVER, None)
+    np.random.seed(7)
+    flow = s.estimate(gold["events"], frame=gold["frame"])
+    assert flow.shape == (2, H, W) and flow.dtype == np.float64
+    tol = {1: 1e-8, 2: 1e-4, 3: 1e-4, 4: 1e-4}        # level 1 to rounding; later levels: chaotic sign noise (see DESIGN)
+    for scale in (1, 2, 3, 4):
+        got = s.best_params_per_scale[scale].cpu().numpy()
+        assert np.abs(got - gold[f"solve_L{scale}"]).max() <= tol[scale], scale
+    assert np.sqrt(np.mean((flow - gold["solve_flow"]) ** 2)) <= 1e-3          # north_star: 1e-3 px RMS after the solve
+    assert np.all(flow[:, :roi[0]] == 0) and np.all(flow[:, :, roi[3]:] == 0)
+
+
+def test_bad_arguments_raise(gold, eklt):
+    prob = problem_from_gold(eklt, gold)
+    lvl = prob.level(16)
+    with pytest.raises(ValueError):
+        lvl.value_and_grad(torch.zeros((3, 2, 2), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        lvl.value_and_grad(torch.zeros((3, lvl.ph, lvl.pw), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        eklt.EkltProblem(prob.grad_x, prob.grad_y, prob.measured, prob.weight_inverse, (0, 500, 0, 10))
+    with pytest.raises(ValueError):
+        eklt.upsample(torch.zeros((2, 3, 3), dtype=torch.float64, device="cuda"), 8, (112, 176))
