@@ -9,6 +9,8 @@ evaluation (gradient-magnitude objective + 0.5*TV) over one window of 16 Mi synt
 1280x720 grid, fp32.  `value` = events/s with the prepared window resident in HBM (inputs 201 MB > L2);
 `e2e` = the same through the public API from pinned HOST buffers (H2D of the raw events, window
 preparation, evaluation, D2H of loss + gradient inside the timed region).
+Workload "eklt" (BASELINE config 1): one step = one PatchEkltPyramid2.estimate of the hot_plate1 pipeline (EKLT inner
+loop on the GPU, float64 like the reference), value = windows/s.
 Workload "solve" (BASELINE config 3): one step = one full per-window flow solve (500 k events, K_it Adam
 iterations), value = windows/s.
 N > 1: every rank processes its own windows (window sharding, no data-path collective) -> weak scaling.
@@ -216,6 +218,18 @@ def run_reference(args):
                                        f"timed iterations)"},
                 "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
                                  "sample": f"{max(2, min(args.steps, 5))} Adam iterations timed, x{args.solve_iters}"}}
+    elif args.workload == "eklt":
+        iters = sum(args.solve_iters // (4 + 1 - s + 1) for s in range(1, 5))
+        s_eval = cpu_reference_eklt(args.solve_events, evals=max(2, min(args.steps, 5)))
+        value = 1.0 / (s_eval * iters)
+        line = {"metric": "windows/s hot_plate1 EKLT solve (PatchEkltPyramid2)", "value": value, "unit": "windows/s",
+                "ms_per_step": s_eval * iters * 1e3,
+                "config": {"workload": f"configs/hot_plate1.yaml pipeline: PatchEkltPyramid2 objective, {args.solve_events} "
+                                       f"synthetic events + synthetic frame, 1280x720, {iters} iterations (extrapolated "
+                                       f"from timed finest-level evaluations)"},
+                "cpu_baseline": {"value": value, "unit": "windows/s", "cores": 1, "kind": "port",
+                                 "sample": f"{max(2, min(args.steps, 5))} evaluations of the numpy oracle timed (single "
+                                           f"thread; SURVEY measured the reference's own torch loop at ~0.5 s/it), x{iters}"}}
     else:
         value, ms, cores = cpu_reference_fused(n_sample, args.steps, args.warmup)
         line = {"metric": "events/s fwd+bwd warp->IWE->cost", "value": value, "unit": "events/s", "ms_per_step": ms,
@@ -224,7 +238,8 @@ def run_reference(args):
                 "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port",
                                  "sample": f"{n_sample} events per step, {args.steps} steps"}}
     line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                 "dtype": "f64" if args.workload == "eklt" else "f32", "data": "synthetic",
                  "e2e": {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
     print(json.dumps(line), flush=True)
@@ -512,6 +527,115 @@ def run_solve(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# hot_plate1 pipeline (BASELINE config 1): PatchEkltPyramid2, the EKLT inner loop
+HOT_PLATE1_SOLVER = {
+    "filter": {"filters": None, "parameters": {"xmin": 0, "xmax": 720, "ymin": 320, "ymax": 960}},
+    "method": "patch_eklt_pyramid2", "outer_padding": 0,
+    "cost_with_weight": {"diff_norm": 1.0, "image_gradient": 0.5, "flow_norm_pxy": 0.1},
+    "optimizer": {"method": "Adam", "n_iter": 600, "parameters": {}},
+    "generative_ml": {"weight_loss_by_event_hist": False, "weight_sigma": 5, "weight_loss_by_inverse_event_hist": True,
+                      "optimize_warp": True, "iwe_sigma": 2, "no_polarity": False, "model_image": "current",
+                      "use_log_intensity": False, "poisson_model": True},
+    "patch_eklt": {"patch_size": 4, "sliding_window": 2, "do_event_thresholding": False, "event_thres": 8},
+}
+
+
+def eklt_inputs(n_events: int, seed: int = 0):
+    """events over the full sensor, synthetic uint8 frame = smooth texture + noise."""
+    rng = np.random.default_rng(seed)
+    ev = np.stack([rng.integers(0, H, n_events), rng.integers(0, W, n_events),
+                   np.sort(rng.uniform(0, 1.0 / 120.0, n_events)), rng.integers(0, 2, n_events)], axis=1).astype(np.float64)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frame = np.clip(120 + 60 * np.sin(xx / 11.0) * np.cos(yy / 7.0) + rng.normal(0, 4, (H, W)), 0, 255).astype(np.uint8)
+    return ev, frame
+
+
+def cpu_reference_eklt(n_events: int, evals: int = 2):
+    """The oracle port of the level objective (numpy fp64, like the reference's float64 torch loop), per evaluation
+    at the finest level, on the host cores numpy uses."""
+    from oracle import spec_eklt as E
+
+    ev, frame = eklt_inputs(n_events)
+    gx, gy = E.frame_gradients(frame)
+    roi = (0, 720, 320, 960)
+    meas, winv, _ = E.measurement_and_weights(ev, (H, W), roi)
+    patch, ph, pw = E.pyramid_levels((H, W))[-1]
+    th = np.concatenate([np.random.default_rng(1).uniform(-1, 1, (1, ph, pw)), np.zeros((2, ph, pw))])
+    E.objective(th, gx, gy, meas, winv, roi, patch)
+    t0 = time.perf_counter()
+    for _ in range(evals):
+        E.objective(th, gx, gy, meas, winv, roi, patch)
+    return (time.perf_counter() - t0) / evals
+
+
+def run_eklt(args, rank, world, local):
+    """One step = one complete PatchEkltPyramid2.estimate (host events + frame in, host flow out): 4 pyramid levels,
+    120 + 150 + 200 + 300 = 770 objective/gradient/Adam iterations at n_iter = 600, float64 like the reference."""
+    from event_based_bos_b200 import eklt, solver
+
+    cfg = json.loads(json.dumps(HOT_PLATE1_SOLVER))
+    cfg["optimizer"]["n_iter"] = args.solve_iters
+    cfg["eklt"] = {"precision": args.eklt_precision}
+    slv = solver.collections["patch_eklt_pyramid2"]((H, W), (720, 640), {}, cfg, None)
+    ev, frame = eklt_inputs(args.solve_events, seed=rank)
+    for _ in range(max(1, min(args.warmup, 2))):
+        slv.estimate(ev, frame=frame)
+    barrier(world)
+    with ClockSampler(local) as clocks:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            slv.estimate(ev, frame=frame)
+        b.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(a.elapsed_time(b) / args.steps, world)
+        barrier(world)
+        clocks.soak(lambda: None, max_s=0.5)
+    # device time of one evaluation per level (value + gradient, no Adam), 20 evaluations per CUDA graph
+    dt = torch.float32 if args.eklt_precision == "32" else torch.float64
+    prob = eklt.EkltProblem(slv._gradient_x_torch, slv._gradient_y_torch, slv.cache_measured, slv.weight_inverse,
+                            (0, 720, 320, 960), (1.0, 0.5, 0.1))
+    per_level = {}
+    for patch, ph, pw in slv.levels:
+        lvl = prob.level(patch)
+        th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous()
+        per_level[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+    if rank != 0:
+        return
+    iters = [args.solve_iters // (len(slv.levels) + 1 - s + 1) for s in range(1, len(slv.levels) + 1)]
+    elem = 4 if args.eklt_precision == "32" else 8
+    plane = H * W * elem
+    alg_eval = 25 * plane                                    # csrc/ebos_eklt.cu header: 25 plane passes per evaluation
+    alg = sum(iters) * (alg_eval + 14 * 0)                   # Adam on [3,ph,pw] is negligible
+    peak, peak_kind = measured_peak_gbs()
+    worst = max(per_level, key=per_level.get)
+    line = {"metric": "windows/s hot_plate1 EKLT solve (PatchEkltPyramid2)", "value": world / (ms * 1e-3),
+            "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if elem == 4 else "f64", "data": "synthetic",
+            "config": {"workload": f"configs/hot_plate1.yaml pipeline: PatchEkltPyramid2.estimate, {args.solve_events} "
+                                   f"synthetic events + synthetic frame, 1280x720, ROI [0:720,320:960], n_iter "
+                                   f"{args.solve_iters} -> {sum(iters)} iterations over 4 levels; host events + frame in "
+                                   f"-> host flow out", "iterations_per_level": iters,
+                       "l2_policy": "working set 25 planes x 7.4 MB (fp64) > L2"},
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": f"one objective evaluation at patch {worst} (all kernels of the chain)",
+                         "achieved": alg_eval / (per_level[worst] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_kind},
+            "eval_ms_per_level": per_level,
+            "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
+                    "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
+            "gpu_launches": args.steps * sum(iters) * 12}
+    if not args.no_cpu and world == 1:
+        s_eval = cpu_reference_eklt(args.solve_events)
+        line["cpu_baseline"] = {"value": 1.0 / (s_eval * sum(iters)), "unit": "windows/s", "cores": 1,
+                                "kind": "port", "sample": f"2 evaluations of the finest-level objective by the numpy "
+                                                          f"oracle ({s_eval:.3f} s each), x{sum(iters)}"}
+    print(json.dumps(line), flush=True)
+
+
 def run_giant(args, rank, world, local):
     """BASELINE config 5: ONE window of `--giant-events` events sharded by events over the ranks (strong scaling):
     partial IWE -> NCCL all-reduce -> cost (redundant) -> partial dflow -> NCCL all-reduce (sharding.py)."""
@@ -573,13 +697,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fused", choices=["fused", "solve", "giant"])
+    ap.add_argument("--workload", default="fused", choices=["fused", "solve", "giant", "eklt"])
     ap.add_argument("--giant-events", type=int, default=1 << 27)
     ap.add_argument("--events", type=int, default=1 << 24)
     ap.add_argument("--cpu-events", type=int, default=1 << 22)
     ap.add_argument("--solve-events", type=int, default=500000)
     ap.add_argument("--solve-iters", type=int, default=600)
     ap.add_argument("--solve-concurrency", type=int, default=8, help="independent windows in flight per GPU (solve workload)")
+    ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")
@@ -590,7 +715,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     rank, world, local = dist_setup(args.gpus)
     try:
-        {"solve": run_solve, "giant": run_giant}.get(args.workload, run_fused)(args, rank, world, local)
+        {"solve": run_solve, "giant": run_giant, "eklt": run_eklt}.get(args.workload, run_fused)(args, rank, world, local)
     finally:
         if world > 1:
             import torch.distributed as dist

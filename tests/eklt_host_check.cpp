@@ -138,4 +138,32 @@ int eklt_host_backward(const int* dims, int is_f64, const void* theta, const voi
   return 0;
 }
 
+// ebos_sepconv2d walked serially: columns pass into tmp, rows pass into out (is_f64 selects the element type).
+int eklt_host_sepconv(const void* image, int H, int W, const double* taps_rows, int n_rows, const double* taps_cols,
+                      int n_cols, int border, int is_f64, void* tmp, void* out) {
+  ConvTaps tr, tc;
+  tr.n = n_rows;
+  tc.n = n_cols;
+  for (int k = 0; k < kMaxTaps; ++k) {
+    tr.w[k] = k < n_rows ? taps_rows[k] : 0.0;
+    tc.w[k] = k < n_cols ? taps_cols[k] : 0.0;
+  }
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < W; ++j) {
+        if (is_f64) {
+          const double* in = (const double*)(pass == 0 ? image : tmp);
+          double* o = (double*)(pass == 0 ? tmp : out);
+          o[(int64_t)i * W + j] = pass == 0 ? correlate_at<double>(in + (int64_t)i * W, 1, j, W, tc, border)
+                                            : correlate_at<double>(in + j, W, i, H, tr, border);
+        } else {
+          const float* in = (const float*)(pass == 0 ? image : tmp);
+          float* o = (float*)(pass == 0 ? tmp : out);
+          o[(int64_t)i * W + j] = pass == 0 ? correlate_at<float>(in + (int64_t)i * W, 1, j, W, tc, border)
+                                            : correlate_at<float>(in + j, W, i, H, tr, border);
+        }
+      }
+  return 0;
+}
+
 }  // extern "C"

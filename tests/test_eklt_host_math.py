@@ -201,3 +201,77 @@ def test_kernel_arithmetic_general_roi_and_odd_sizes(host_lib):
         r = E.objective(th, gx, gy, meas, winv, roi, patch, *w)
         assert abs(h["loss"] - r["loss"]) <= 1e-12
         assert np.abs(h["grad"] - r["grad"]).max() <= 1e-10 * np.abs(r["grad"]).max()
+
+
+def test_preprocessing_oracle_matches_reference(gold):
+    """`_set_frame` / `calculate_iwe_cache` / `_make_measured_increment` restated (oracle) vs the reference's own
+    cv2.Sobel, cv2.GaussianBlur and scipy gaussian_filter outputs stored in the fixture."""
+    H, W = (int(v) for v in gold["image"])
+    gx, gy = E.frame_gradients(gold["frame"])
+    assert np.array_equal(gx, gold["grad_x"]) and np.array_equal(gy, gold["grad_y"])
+    meas, winv, blurred = E.measurement_and_weights(gold["events"], (H, W), gold["roi_t"])
+    assert np.abs(blurred - gold["histogram_blurred"]).max() <= 1e-14
+    assert np.abs(meas - gold["measured"]).max() <= 1e-15
+    assert np.abs(winv - gold["weight_inverse"]).max() <= 1e-13
+
+
+def test_separable_correlation_arithmetic_matches_oracle(gold, host_lib):
+    """The border indexing and tap loop of ebos_sepconv2d (serial build) vs the oracle, both border modes."""
+    rng = np.random.default_rng(2)
+    for (H, W) in [(19, 45), (1, 7), (6, 1), (112, 176)]:
+        img = rng.normal(size=(H, W))
+        for taps_r, taps_c in [(np.array([-1.0, 0.0, 1.0]), np.array([1.0, 2.0, 1.0])),
+                               (E.cv2_gaussian_taps(2.0), E.cv2_gaussian_taps(2.0)),
+                               (E.scipy_gaussian_taps(10.0), E.scipy_gaussian_taps(3.0))]:
+            for border in (0, 1):
+                tmp, out = np.zeros((H, W)), np.zeros((H, W))
+                tr, tc = np.ascontiguousarray(taps_r), np.ascontiguousarray(taps_c)
+                host_lib.eklt_host_sepconv(_p(img), H, W, _p(tr), len(tr), _p(tc), len(tc), border, 1, _p(tmp), _p(out))
+                ref = E.correlate_separable(img, tr, tc, border)
+                assert np.abs(out - ref).max() <= 1e-13, (H, W, len(tr), border)
+
+
+HOT_PLATE1_SOLVER = {
+    "filter": {"filters": None, "parameters": {"xmin": 0, "xmax": 720, "ymin": 320, "ymax": 960}},
+    "method": "patch_eklt_pyramid2", "cost_with_weight": {"diff_norm": 1.0, "image_gradient": 0.5, "flow_norm_pxy": 0.1},
+    "optimizer": {"method": "Adam", "n_iter": 600, "parameters": {}},
+    "generative_ml": {"weight_loss_by_event_hist": False, "weight_loss_by_inverse_event_hist": True, "optimize_warp": True,
+                      "iwe_sigma": 2, "no_polarity": False, "model_image": "current", "use_log_intensity": False,
+                      "poisson_model": True},
+    "patch_eklt": {"patch_size": 4, "sliding_window": 2, "do_event_thresholding": False, "event_thres": 8},
+}
+
+
+def test_solver_registry_and_config_contract():
+    """Host logic of the drop-in solver (no GPU): registry name, level schedule, start-value draws, and loud failure
+    for objectives other than hot_plate1's."""
+    import copy
+
+    from event_based_bos_b200 import eklt, solver
+
+    cls = solver.collections["patch_eklt_pyramid2"]
+    s = cls((720, 1280), (720, 640), {}, copy.deepcopy(HOT_PLATE1_SOLVER), None)
+    assert s.levels == [(64, 12, 20), (32, 23, 40), (16, 45, 80), (8, 90, 160)] == E.pyramid_levels((720, 1280))
+    assert (s.coarest_scale, s.finest_scale) == (1, 5)
+    assert [600 // (s.finest_scale - sc + 1) for sc in range(1, 5)] == [E.level_iterations(600, 4, l) for l in range(4)]
+    assert s.estimate_mask_dense_numpy.sum() == 720 * 640
+    np.random.seed(3)
+    v = s._initialize_velocity()
+    np.random.seed(3)
+    assert v.shape == (3,) and v[0] == np.random.random() * 2.0 - 1 and v[1] == v[2] == 0.0
+    assert eklt.patch_grid((720, 1280), 64) == E.patch_grid((720, 1280), 64)
+    assert np.allclose(eklt.gaussian_taps_cv2(2.0), E.cv2_gaussian_taps(2.0), rtol=0, atol=0)
+    assert np.allclose(eklt.gaussian_taps_scipy(10.0), E.scipy_gaussian_taps(10.0), rtol=0, atol=0)
+    for path, value in [(("optimizer", "method"), "Newton-CG"), (("generative_ml", "poisson_model"), False),
+                        (("generative_ml", "optimize_warp"), False), (("generative_ml", "no_polarity"), True),
+                        (("generative_ml", "weight_loss_by_event_hist"), True),
+                        (("cost_with_weight", "total_variation"), 3.0)]:
+        cfg = copy.deepcopy(HOT_PLATE1_SOLVER)
+        cfg[path[0]][path[1]] = value
+        with pytest.raises(NotImplementedError):
+            cls((720, 1280), (720, 640), {}, cfg, None)
+    import torch
+
+    if not torch.cuda.is_available():          # no CPU fallback: the estimate needs the device
+        with pytest.raises(RuntimeError):
+            s.estimate(np.zeros((4, 4)), frame=np.zeros((720, 1280), np.uint8))
