@@ -1,6 +1,7 @@
 """Generate tests/golden/reference_eklt_v1.npz by running the UNMODIFIED reference (container-only).
 
-    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden_eklt
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden_eklt            # reference_eklt_v1.npz
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden_eklt variants   # reference_eklt_variants_v1.npz
 
 SURVEY 8f-1: the EKLT inner loop of `PatchEkltPyramid2` (what configs/hot_plate1.yaml runs).  The script builds
 the reference solver from the shipped config (only the image size, ROI and iteration count are changed), lets it
@@ -36,10 +37,13 @@ N_EVENTS = 6000
 N_ITER = 24
 
 
-def build_solver(ref, n_iter):
+def build_solver(ref, n_iter, gml_overrides=None, drop_costs=()):
     cfg = yaml.safe_load(open(os.path.join(ref_import.REFERENCE_ROOT, "configs", "hot_plate1.yaml")))
     slv = copy.deepcopy(cfg["solver"])
     slv["optimizer"]["n_iter"] = n_iter
+    slv["generative_ml"].update(gml_overrides or {})
+    for k in drop_costs:
+        slv["cost_with_weight"].pop(k)
     slv["filter"]["parameters"].update(dict(xmin=ROI[0], xmax=ROI[1], ymin=ROI[2], ymax=ROI[3]))
     vis = mock.MagicMock()
     vis.save_dir = tempfile.mkdtemp()
@@ -158,5 +162,68 @@ def main():
         os.chdir(cwd)
 
 
+OUT_VARIANTS = OUT.replace("reference_eklt_v1", "reference_eklt_variants_v1")
+
+# the other switch combinations of generative_ml.* (same inputs, level of 16-px patches, random theta)
+VARIANTS = {
+    "flow_warp": ({"poisson_model": False}, ()),                                   # theta = (v_x, v_y, p_x, p_y)
+    "poisson_nowarp": ({"optimize_warp": False}, ("flow_norm_pxy",)),              # theta = (intensity)
+    "flow_nowarp": ({"poisson_model": False, "optimize_warp": False}, ("flow_norm_pxy",)),
+    "no_polarity": ({"no_polarity": True}, ()),
+    "hist_weights": ({"weight_loss_by_event_hist": True}, ()),
+    "all": ({"poisson_model": False, "no_polarity": True, "weight_loss_by_event_hist": True}, ()),
+}
+
+
+def make_variants(ref):
+    out = {}
+    events, frame = synthetic_inputs()
+    roi = {"xmin": ROI[0], "xmax": ROI[1], "ymin": ROI[2], "ymax": ROI[3]}
+    rng = np.random.default_rng(11)
+    for name, (gml, drop) in VARIANTS.items():
+        s, slv = build_solver(ref, N_ITER, gml, drop)
+        s._set_frame(frame)
+        s.calculate_iwe_cache(events)
+        s.overload_patch_configuration(3)
+        s.estimate_mask_patch = torch.ones(s.patch_image_size).double()
+        s.n_parameter_dim = len(s._initialize_velocity())
+        meas_np, w_np = s._make_measured_increment(events, roi)
+        meas = torch.from_numpy(meas_np).double() * s.estimate_mask_dense()
+        weights = None if w_np is None else torch.from_numpy(w_np).double() * s.estimate_mask_dense()
+        ph, pw = s.patch_image_size
+        nd = s.n_parameter_dim
+        th = rng.uniform(-1, 1, (nd, ph, pw))
+        if gml.get("optimize_warp", True):
+            th[-2:] *= 1.5
+        x = torch.from_numpy(th).double().requires_grad_()
+        loss = s._objective_scipy(x, meas, roi, weights)
+        loss.backward()
+        out[name + "_theta"] = th
+        out[name + "_loss"] = np.array(loss.item())
+        out[name + "_grad"] = x.grad.numpy().copy()
+        out[name + "_measured"] = meas.numpy().copy()
+        if weights is not None:
+            out[name + "_weights"] = weights.numpy().copy()
+        if gml.get("no_polarity", False):        # weight_inverse comes from |pos + neg| instead of |pos - neg|
+            out[name + "_weight_inverse"] = s.weight_inverse.copy()
+        out[name + "_cost_weights"] = np.array([slv["cost_with_weight"].get(k, 0.0) for k in
+                                                ("diff_norm", "image_gradient", "flow_norm_pxy")], dtype=np.float64)
+        out[name + "_flags"] = np.array([int(gml.get("poisson_model", True)), int(gml.get("optimize_warp", True)),
+                                         int(gml.get("no_polarity", False))])
+    out["patch"] = np.array(16)
+    np.savez_compressed(OUT_VARIANTS, **out)
+    print("wrote", OUT_VARIANTS, os.path.getsize(OUT_VARIANTS), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if "variants" in sys.argv[1:]:
+        cwd = os.getcwd()
+        os.chdir(tempfile.mkdtemp())
+        try:
+            make_variants(ref_import.load())
+        finally:
+            os.chdir(cwd)
+    else:
+        main()

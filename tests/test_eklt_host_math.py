@@ -275,3 +275,35 @@ def test_solver_registry_and_config_contract():
     if not torch.cuda.is_available():          # no CPU fallback: the estimate needs the device
         with pytest.raises(RuntimeError):
             s.estimate(np.zeros((4, 4)), frame=np.zeros((720, 1280), np.uint8))
+
+
+# ---- 3. the other switch combinations of generative_ml.* ---------------------------------------------------------
+VARIANTS = os.path.join(HERE, "golden", "reference_eklt_variants_v1.npz")
+
+
+def _variant_cases(gold):
+    v = np.load(VARIANTS)
+    for name in sorted({k[:-len("_theta")] for k in v.files if k.endswith("_theta")}):
+        poisson, warp, no_pol = (bool(x) for x in v[name + "_flags"])
+        yield {
+            "name": name, "theta": v[name + "_theta"], "loss": float(v[name + "_loss"]), "grad": v[name + "_grad"],
+            "measured": v[name + "_measured"], "cost_weights": tuple(float(x) for x in v[name + "_cost_weights"]),
+            "weights": v[name + "_weights"] if name + "_weights" in v.files else None,
+            "winv": v[name + "_weight_inverse"] if name + "_weight_inverse" in v.files else gold["weight_inverse"],
+            "poisson": poisson, "warp": warp, "no_polarity": no_pol, "patch": int(v["patch"]),
+        }
+
+
+def test_oracle_switch_variants_match_reference_autograd(gold):
+    """poisson_model / optimize_warp / no_polarity / weight_loss_by_event_hist in the combinations of
+    oracle/make_golden_eklt.py (run on the unmodified reference with the shipped config otherwise)."""
+    names = []
+    for c in _variant_cases(gold):
+        wd, wtv, wp = c["cost_weights"]
+        r = E.objective(c["theta"], gold["grad_x"], gold["grad_y"], c["measured"], c["winv"], gold["roi_t"], c["patch"],
+                        wd, wtv, wp, poisson=c["poisson"], warp=c["warp"], no_polarity=c["no_polarity"],
+                        weights=c["weights"])
+        assert abs(r["loss"] - c["loss"]) <= 1e-13, c["name"]
+        assert np.abs(r["grad"] - c["grad"]).max() <= 1e-12 * np.abs(c["grad"]).max(), c["name"]
+        names.append(c["name"])
+    assert names == ["all", "flow_nowarp", "flow_warp", "hist_weights", "no_polarity", "poisson_nowarp"]
