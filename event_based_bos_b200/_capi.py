@@ -22,6 +22,7 @@ ACC_DOUBLES = 40  # EBOS_ACC_DOUBLES (include/ebos.h)
 STATUS_PIXEL_OOB = 1
 STATUS_PACKED = 2
 WIN_HAS_WEIGHT, WIN_PACKED = 1, 2
+EKLT_POISSON, EKLT_WARP, EKLT_NO_POLARITY = 1, 2, 4
 
 # name -> (restype, argtypes); every symbol include/ebos.h declares.
 SIGNATURES = {
@@ -71,11 +72,12 @@ SIGNATURES = {
     "ebos_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
                                      c_double, c_void_p, c_int, c_void_p]),
     "ebos_eklt_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
-    "ebos_eklt_value_and_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                         c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_void_p, c_size_t,
-                                         c_void_p, c_void_p, c_void_p]),
-    "ebos_eklt_adam_iteration": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                         c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_int, c_void_p, c_size_t,
+    "ebos_eklt_value_and_grad": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_int,
+                                         c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "ebos_eklt_adam_iteration": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_int,
+                                         c_void_p, c_size_t,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double,
                                          c_void_p, c_void_p]),
     "ebos_eklt_upsample": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

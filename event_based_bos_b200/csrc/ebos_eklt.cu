@@ -7,7 +7,7 @@
 // this file holds the parallel structure.  One evaluation =
 //
 //   memset(acc, colsum)
-//   k_patch_flow     pf = Sobel(theta[0]) / 8                              [2,ph,pw]       (tiny)
+//   k_patch_flow     pf = Sobel(theta[0]) / 8                              [2,ph,pw]       (tiny; poisson model only)
 //   k_forward        per pixel: up-sample pf and theta[1:3], warp the frame gradients, q; writes q and the masked
 //                    flow F = f*M; block-reduces sum q^2 and sum ||t*M||
 //   ebos_flow_tv     TV(F; w_inv) value and w_tv * dTV/dF  (the kernel of the contrast-maximisation path)
@@ -82,15 +82,16 @@ __global__ void k_patch_flow(const T* __restrict__ theta, int ph, int pw, T* __r
 
 // 2-D tiles of 32 x 8 pixels; gridDim.y strides the rows.
 template <typename T>
-__global__ void __launch_bounds__(256) k_forward(Geom g, const T* __restrict__ pf, const T* __restrict__ theta,
-                                                 const T* __restrict__ gx, const T* __restrict__ gy, T* __restrict__ q,
-                                                 T* __restrict__ F, double* __restrict__ acc) {
+__global__ void __launch_bounds__(256) k_forward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
+                                                 const T* __restrict__ gx, const T* __restrict__ gy,
+                                                 const T* __restrict__ weights, T* __restrict__ q, T* __restrict__ F,
+                                                 double* __restrict__ acc) {
   __shared__ double red[32];
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   double sq = 0.0, sp = 0.0;
   if (j < g.W) {
     for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
-      const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+      const Pixel<T> p = eval_pixel<T>(g, flags, pf, tr, gx, gy, weights, i, j);
       const int64_t k = (int64_t)i * g.W + j;
       q[k] = p.q;
       F[k] = p.m ? p.f0 : (T)0;
@@ -180,9 +181,10 @@ __global__ void __launch_bounds__(256) k_column_max(Geom g, const T* __restrict_
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_backward(Geom g, const T* __restrict__ pf, const T* __restrict__ theta,
+__global__ void __launch_bounds__(256) k_backward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
                                                   const T* __restrict__ gx, const T* __restrict__ gy,
-                                                  const T* __restrict__ meas, const T* __restrict__ dF,
+                                                  const T* __restrict__ weights, const T* __restrict__ meas,
+                                                  const T* __restrict__ dF,
                                                   const double* __restrict__ colsum, const double* __restrict__ acc,
                                                   double w_pxy_hw, T* __restrict__ dU) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -195,21 +197,23 @@ __global__ void __launch_bounds__(256) k_backward(Geom g, const T* __restrict__ 
   const bool col_is_max = colsum[j] == s.mx;
   const int64_t plane = (int64_t)g.H * g.W;
   for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
-    const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+    const Pixel<T> p = eval_pixel<T>(g, flags, pf, tr, gx, gy, weights, i, j);
     const int64_t k = (int64_t)i * g.W + j;
     T out[4];
-    backward_pixel<T>(p, meas[k], col_is_max, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw, out);
+    backward_pixel<T>(p, flags, meas[k], col_is_max, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw, out);
     dU[k] = out[0];
     dU[plane + k] = out[1];
-    dU[2 * plane + k] = out[2];
-    dU[3 * plane + k] = out[3];
+    if (flags & kWarp) {
+      dU[2 * plane + k] = out[2];
+      dU[3 * plane + k] = out[3];
+    }
   }
 }
 
 // One CTA per padded cell (A,B): sums the four dense gradient planes over the cell's 2*patch x 2*patch support with
 // the separable triangle weights.  Deterministic (no atomics).
 template <typename T>
-__global__ void __launch_bounds__(256) k_cell_gather(Geom g, const T* __restrict__ dU, T* __restrict__ dPad) {
+__global__ void __launch_bounds__(256) k_cell_gather(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ dPad) {
   __shared__ double red[32];
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int A = blockIdx.y, B = blockIdx.x;
@@ -225,20 +229,22 @@ __global__ void __launch_bounds__(256) k_cell_gather(Geom g, const T* __restrict
     const double w = (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)cell_weight<T>(B, j, g.w1, g.patch);
     const int64_t idx = (int64_t)i * g.W + j;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) s[c] += w * (double)dU[c * plane + idx];
+    for (int c = 0; c < 4; ++c)
+      if (c < nch) s[c] += w * (double)dU[c * plane + idx];
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
+    if (c >= nch) break;                      // uniform over the CTA
     const double t = block_sum(s[c], red);
     if (threadIdx.x == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)t;
   }
 }
 
 template <typename T>
-__global__ void k_fold(Geom g, const T* __restrict__ dPad, T* __restrict__ dP) {
+__global__ void k_fold(Geom g, int nch, const T* __restrict__ dPad, T* __restrict__ dP) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ph * g.pw;
-  if (k >= 4 * np) return;
+  if (k >= nch * np) return;
   const int c = k / np, a = (k % np) / g.pw, b = k % g.pw;
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   int a0, a1, b0, b1;
@@ -251,20 +257,29 @@ __global__ void k_fold(Geom g, const T* __restrict__ dPad, T* __restrict__ dP) {
 }
 
 template <typename T>
-__global__ void k_param_grad(Geom g, const T* __restrict__ dP, const double* __restrict__ tv_acc, double* __restrict__ acc,
-                             double w_data, double w_tv, double w_pxy, T* __restrict__ grad, T* __restrict__ loss) {
+__global__ void k_param_grad(Geom g, int flags, const T* __restrict__ dP, const double* __restrict__ tv_acc,
+                             double* __restrict__ acc, double w_data, double w_tv, double w_pxy, T* __restrict__ grad,
+                             T* __restrict__ loss) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ph * g.pw;
   if (k < np) {
-    grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
-    grad[np + k] = dP[2 * np + k];
-    grad[2 * np + k] = dP[3 * np + k];
+    const int nf = flow_channels(flags);
+    if (flags & kPoisson) {
+      grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
+    } else {
+      grad[k] = dP[k];
+      grad[np + k] = dP[np + k];
+    }
+    if (flags & kWarp) {
+      grad[nf * np + k] = dP[2 * np + k];
+      grad[(nf + 1) * np + k] = dP[3 * np + k];
+    }
   }
   if (k == 0) {
     double tv = tv_acc[3];
     for (int i = 24; i < EBOS_ACC_DOUBLES; ++i) tv += tv_acc[i];     // spread slots of the TV kernel (ebos_costs.cu)
     const double hw = (double)g.H * (double)g.W;
-    const double tv_mean = tv / (2.0 * hw), pxy_mean = acc[kAccPxy] / hw;
+    const double tv_mean = tv / (2.0 * hw), pxy_mean = (flags & kWarp) ? acc[kAccPxy] / hw : 0.0;
     const double total = w_data * acc[kAccMax] + w_tv * tv_mean + w_pxy * pxy_mean;
     acc[kAccData] = acc[kAccMax];          // un-weighted terms, for diagnostics
     acc[kAccTv] = tv_mean;
@@ -318,32 +333,41 @@ static int check_geometry(const Geom& g) {
 }
 
 template <typename T>
-static int value_and_grad_t(const Geom& g, const T* theta, const T* gx, const T* gy, const T* meas, const T* winv,
-                            double w_data, double w_tv, double w_pxy, void* workspace, T* loss, T* grad, cudaStream_t st) {
+static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* gx, const T* gy, const T* meas,
+                            const T* winv, const T* weights, double w_data, double w_tv, double w_pxy, void* workspace,
+                            T* loss, T* grad, cudaStream_t st) {
   const Workspace w = carve(workspace, g.H, g.W, g.ph, g.pw, g.pad, sizeof(T));
   cudaError_t e = cudaMemsetAsync(w.acc, 0, (kAccN + (size_t)g.W) * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset");
   const int np = g.ph * g.pw;
   const dim3 pg = plane_grid(g.H, g.W);
-  T* pf = reinterpret_cast<T*>(w.pf);
   T* q = reinterpret_cast<T*>(w.q);
   T* F = reinterpret_cast<T*>(w.F);
   T* dF = reinterpret_cast<T*>(w.dF);
   T* dU = reinterpret_cast<T*>(w.dU);
   T* dPad = reinterpret_cast<T*>(w.dPad);
   T* dP = reinterpret_cast<T*>(w.dP);
-  k_patch_flow<T><<<(np + 127) / 128, 128, 0, st>>>(theta, g.ph, g.pw, pf);
-  k_forward<T><<<pg, 256, 0, st>>>(g, pf, theta, gx, gy, q, F, w.acc);
+  const bool warp = flags & kWarp;
+  const int nch = warp ? 4 : 2;
+  if (!warp) w_pxy = 0.0;
+  const T* pf = theta;                                         // flow model: theta[0:2] is the patch flow
+  if (flags & kPoisson) {
+    k_patch_flow<T><<<(np + 127) / 128, 128, 0, st>>>(theta, g.ph, g.pw, reinterpret_cast<T*>(w.pf));
+    pf = reinterpret_cast<const T*>(w.pf);
+  }
+  const T* tr = warp ? theta + (size_t)flow_channels(flags) * np : nullptr;
+  k_forward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, q, F, w.acc);
   EBOS_LAUNCH_CHECK("ebos_eklt forward");
   const int rc = ebos_flow_tv(F, winv, g.H, g.W, w_tv, sizeof(T) == 8 ? EBOS_F64 : EBOS_F32, w.tv_acc, dF, st);
   if (rc != EBOS_OK) return rc;
   k_column_sums<T><<<pg, 256, 0, st>>>(g, q, meas, w.acc, w.colsum);
   k_column_max<T><<<1, 256, 0, st>>>(g, q, meas, w.colsum, w.acc, w_data);
-  k_backward<T><<<pg, 256, 0, st>>>(g, pf, theta, gx, gy, meas, dF, w.colsum, w.acc, w_pxy / ((double)g.H * g.W), dU);
+  k_backward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
+                                    w_pxy / ((double)g.H * g.W), dU);
   EBOS_LAUNCH_CHECK("ebos_eklt backward");
-  k_cell_gather<T><<<dim3(g.pw + 2 * g.pad, g.ph + 2 * g.pad), 256, 0, st>>>(g, dU, dPad);
-  k_fold<T><<<(4 * np + 127) / 128, 128, 0, st>>>(g, dPad, dP);
-  k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, dP, w.tv_acc, w.acc, w_data, w_tv, w_pxy, grad, loss);
+  k_cell_gather<T><<<dim3(g.pw + 2 * g.pad, g.ph + 2 * g.pad), 256, 0, st>>>(g, nch, dU, dPad);
+  k_fold<T><<<(nch * np + 127) / 128, 128, 0, st>>>(g, nch, dPad, dP);
+  k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, flags, dP, w.tv_acc, w.acc, w_data, w_tv, w_pxy, grad, loss);
   EBOS_LAUNCH_CHECK("ebos_eklt gradient");
   return EBOS_OK;
 }
@@ -362,12 +386,13 @@ size_t ebos_eklt_workspace_bytes(int H, int W, int ph, int pw, int patch, int dt
   return carve(nullptr, H, W, ph, pw, g.pad, dtype_size(dtype)).total;
 }
 
-int ebos_eklt_value_and_grad(const void* theta, const void* grad_x, const void* grad_y, const void* measured,
-                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
-                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
-                             size_t workspace_bytes, void* loss, void* grad, void* stream) {
+int ebos_eklt_value_and_grad(const void* theta, int flags, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, const void* weights, int H, int W, int ph, int pw, int patch,
+                             int roi_x0, int roi_x1, int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy,
+                             int dtype, void* workspace, size_t workspace_bytes, void* loss, void* grad, void* stream) {
   EBOS_REQUIRE(theta && grad_x && grad_y && measured && weight_inverse && workspace && loss && grad,
                "ebos_eklt_value_and_grad: null argument");
+  EBOS_REQUIRE((flags & ~(kPoisson | kWarp | kNoPolarity)) == 0, "ebos_eklt_value_and_grad: unknown flag");
   if (dtype != EBOS_F32 && dtype != EBOS_F64) {
     set_error("ebos_eklt_value_and_grad: unsupported dtype");
     return EBOS_ERR_UNSUPPORTED;
@@ -381,26 +406,27 @@ int ebos_eklt_value_and_grad(const void* theta, const void* grad_x, const void* 
   }
   cudaStream_t st = as_stream(stream);
   if (dtype == EBOS_F64)
-    return value_and_grad_t<double>(g, (const double*)theta, (const double*)grad_x, (const double*)grad_y,
-                                    (const double*)measured, (const double*)weight_inverse, w_data, w_tv, w_pxy,
-                                    workspace, (double*)loss, (double*)grad, st);
-  return value_and_grad_t<float>(g, (const float*)theta, (const float*)grad_x, (const float*)grad_y,
-                                 (const float*)measured, (const float*)weight_inverse, w_data, w_tv, w_pxy, workspace,
-                                 (float*)loss, (float*)grad, st);
+    return value_and_grad_t<double>(g, flags, (const double*)theta, (const double*)grad_x, (const double*)grad_y,
+                                    (const double*)measured, (const double*)weight_inverse, (const double*)weights,
+                                    w_data, w_tv, w_pxy, workspace, (double*)loss, (double*)grad, st);
+  return value_and_grad_t<float>(g, flags, (const float*)theta, (const float*)grad_x, (const float*)grad_y,
+                                 (const float*)measured, (const float*)weight_inverse, (const float*)weights, w_data,
+                                 w_tv, w_pxy, workspace, (float*)loss, (float*)grad, st);
 }
 
-int ebos_eklt_adam_iteration(void* theta, const void* grad_x, const void* grad_y, const void* measured,
-                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
-                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
-                             size_t workspace_bytes, void* loss, void* grad, void* exp_avg, void* exp_avg_sq, double lr,
-                             double beta1, double beta2, double eps, int32_t* step_dev, void* stream) {
+int ebos_eklt_adam_iteration(void* theta, int flags, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, const void* weights, int H, int W, int ph, int pw, int patch,
+                             int roi_x0, int roi_x1, int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy,
+                             int dtype, void* workspace, size_t workspace_bytes, void* loss, void* grad, void* exp_avg,
+                             void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int32_t* step_dev,
+                             void* stream) {
   EBOS_REQUIRE(exp_avg && exp_avg_sq && step_dev, "ebos_eklt_adam_iteration: null argument");
-  const int rc = ebos_eklt_value_and_grad(theta, grad_x, grad_y, measured, weight_inverse, H, W, ph, pw, patch, roi_x0,
-                                          roi_x1, roi_y0, roi_y1, w_data, w_tv, w_pxy, dtype, workspace, workspace_bytes,
-                                          loss, grad, stream);
+  const int rc = ebos_eklt_value_and_grad(theta, flags, grad_x, grad_y, measured, weight_inverse, weights, H, W, ph, pw,
+                                          patch, roi_x0, roi_x1, roi_y0, roi_y1, w_data, w_tv, w_pxy, dtype, workspace,
+                                          workspace_bytes, loss, grad, stream);
   if (rc != EBOS_OK) return rc;
-  return ebos_adam_step_graph(theta, grad, exp_avg, exp_avg_sq, (int64_t)3 * ph * pw, lr, beta1, beta2, eps, step_dev,
-                              dtype, stream);
+  return ebos_adam_step_graph(theta, grad, exp_avg, exp_avg_sq, (int64_t)theta_channels(flags) * ph * pw, lr, beta1,
+                              beta2, eps, step_dev, dtype, stream);
 }
 
 int ebos_eklt_upsample(const void* patch_values, int channels, int H, int W, int ph, int pw, int patch, int dtype,

@@ -26,6 +26,13 @@ namespace eklt {
 
 constexpr double kNormEps = 1e-4;   // src/solver/patch_eklt_pyramid2.py:364
 
+// switches of generative_ml.* (mirror EBOS_EKLT_* in include/ebos.h)
+constexpr int kPoisson = 1;      // theta[0] is an intensity, patch flow = Sobel(theta[0])/8; else theta[0:2] is the patch flow
+constexpr int kWarp = 2;         // the last two channels translate the frame gradients (and carry the pxy term)
+constexpr int kNoPolarity = 4;   // q = |q|
+EK_HD int flow_channels(int flags) { return (flags & kPoisson) ? 1 : 2; }
+EK_HD int theta_channels(int flags) { return flow_channels(flags) + ((flags & kWarp) ? 2 : 0); }
+
 // Separately rounded IEEE operations (never contracted into FMA): used wherever a rounding decides a floor() or the
 // sign of a difference of equal-looking numbers (the reference's result depends on both).
 template <typename T> struct Ar;
@@ -153,26 +160,40 @@ EK_HD Sample<T> bilinear_sample(const T* img, int H, int W, T pr, T pc) {
 
 // Everything the forward needs at one pixel.
 template <typename T> struct Pixel {
-  T f0, f1, t0, t1;        // up-sampled flow (from the Sobel'd intensity) and translation
-  Sample<T> sx, sy;        // warped frame gradients (row derivative, column derivative) and their position derivatives
-  T q;                     // predicted increment before normalisation
+  T f0, f1, t0, t1;        // up-sampled flow and translation (0 without kWarp)
+  Sample<T> sx, sy;        // (warped) frame gradients (row derivative, column derivative) and their position derivatives
+  T q0;                    // f0*sx + f1*sy
+  T wgt;                   // histogram weight (1 without weights)
+  T q;                     // predicted increment before normalisation: (|q0| or q0) * wgt
   bool m;                  // inside the ROI
 };
-// pf: [2,ph,pw] Sobel/8 of theta[0];  theta: [3,ph,pw];  gx, gy: [H,W]
+// pf: [2,ph,pw] patch flow (Sobel/8 of the intensity, or theta[0:2]);  tr: [2,ph,pw] patch translation or NULL;
+// gx, gy: [H,W];  weights: [H,W] or NULL
 template <typename T>
-EK_HD Pixel<T> eval_pixel(const Geom& g, const T* pf, const T* theta, const T* gx, const T* gy, int i, int j) {
+EK_HD Pixel<T> eval_pixel(const Geom& g, int flags, const T* pf, const T* tr, const T* gx, const T* gy, const T* weights,
+                          int i, int j) {
   Pixel<T> p;
   const AxisTap<T> r = axis_tap<T>(i, g.h1, g.patch, g.ph, g.pad);
   const AxisTap<T> c = axis_tap<T>(j, g.w1, g.patch, g.pw, g.pad);
   const int np = g.ph * g.pw;
+  const int64_t k = (int64_t)i * g.W + j;
   p.f0 = upsample_at(pf, g.pw, r, c);
   p.f1 = upsample_at(pf + np, g.pw, r, c);
-  p.t0 = upsample_at(theta + np, g.pw, r, c);
-  p.t1 = upsample_at(theta + 2 * np, g.pw, r, c);
-  const T pr = sample_pos<T>(i, p.t0, g.H), pc = sample_pos<T>(j, p.t1, g.W);
-  p.sx = bilinear_sample(gx, g.H, g.W, pr, pc);
-  p.sy = bilinear_sample(gy, g.H, g.W, pr, pc);
-  p.q = Ar<T>::add(Ar<T>::mul(p.f0, p.sx.v), Ar<T>::mul(p.f1, p.sy.v));
+  if (flags & kWarp) {
+    p.t0 = upsample_at(tr, g.pw, r, c);
+    p.t1 = upsample_at(tr + np, g.pw, r, c);
+    const T pr = sample_pos<T>(i, p.t0, g.H), pc = sample_pos<T>(j, p.t1, g.W);
+    p.sx = bilinear_sample(gx, g.H, g.W, pr, pc);
+    p.sy = bilinear_sample(gy, g.H, g.W, pr, pc);
+  } else {                                  // no grid_sample at all upstream: the gradients as they are
+    p.t0 = p.t1 = (T)0;
+    p.sx.v = gx[k]; p.sx.d_r = p.sx.d_c = (T)0;
+    p.sy.v = gy[k]; p.sy.d_r = p.sy.d_c = (T)0;
+  }
+  p.q0 = Ar<T>::add(Ar<T>::mul(p.f0, p.sx.v), Ar<T>::mul(p.f1, p.sy.v));
+  p.q = (flags & kNoPolarity) ? (p.q0 < 0 ? -p.q0 : p.q0) : p.q0;
+  p.wgt = weights ? weights[k] : (T)1;
+  if (weights) p.q = Ar<T>::mul(p.q, p.wgt);
   p.m = in_roi(g, i, j);
   return p;
 }
@@ -194,23 +215,27 @@ struct BackScalars {
 // Dense gradients at one pixel: d/d f0, f1, t0, t1.  dF0/dF1: TV gradient w.r.t. the masked flow, already scaled by
 // w_tv;  w_pxy_hw = w_pxy / (H*W).
 template <typename T>
-EK_HD void backward_pixel(const Pixel<T>& p, T meas, bool col_is_max, const BackScalars& s, T dF0, T dF1,
+EK_HD void backward_pixel(const Pixel<T>& p, int flags, T meas, bool col_is_max, const BackScalars& s, T dF0, T dF1,
                           double w_pxy_hw, T out[4]) {
   const double inv = 1.0 / (s.n + kNormEps);
   const double D = (double)residual<T>(p.q, p.m, meas, (T)inv);
   const double gm = (p.m && col_is_max) ? sgn(D) * s.tie_w : 0.0;
   double dq = gm * inv;
   if (s.n > 0.0) dq -= ((double)p.q / s.n) * (s.S * inv * inv);
+  dq *= (double)p.wgt;                                         // q = (|q0| or q0) * wgt
+  if (flags & kNoPolarity) dq *= sgn((double)p.q0);
   double d0 = dq * (double)p.sx.v, d1 = dq * (double)p.sy.v;
   double e0 = -dq * ((double)p.f0 * (double)p.sx.d_r + (double)p.f1 * (double)p.sy.d_r);
   double e1 = -dq * ((double)p.f0 * (double)p.sx.d_c + (double)p.f1 * (double)p.sy.d_c);
   if (p.m) {
     d0 += (double)dF0;
     d1 += (double)dF1;
-    const double tn = sqrt((double)p.t0 * (double)p.t0 + (double)p.t1 * (double)p.t1);
-    if (tn > 0.0) {
-      e0 += w_pxy_hw * (double)p.t0 / tn;
-      e1 += w_pxy_hw * (double)p.t1 / tn;
+    if (flags & kWarp) {
+      const double tn = sqrt((double)p.t0 * (double)p.t0 + (double)p.t1 * (double)p.t1);
+      if (tn > 0.0) {
+        e0 += w_pxy_hw * (double)p.t0 / tn;
+        e1 += w_pxy_hw * (double)p.t1 / tn;
+      }
     }
   }
   out[0] = (T)d0; out[1] = (T)d1; out[2] = (T)e0; out[3] = (T)e1;

@@ -108,9 +108,14 @@ def frame_gradients(frame: torch.Tensor, use_log_intensity: bool = False) -> Tup
 
 
 def measurement_and_weights(histogram: torch.Tensor, roi: Tuple[int, int, int, int], iwe_sigma: float = 2.0,
-                            weight_inverse: bool = True, inverse_sigma: float = 10.0
-                            ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """From the polarity histogram (positive minus negative IWE) to (measured increment * ROI mask, weight_inverse).
+                            weight_inverse: bool = True, inverse_sigma: float = 10.0, weight_sigma: float = 0.0
+                            ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """From the polarity histogram (positive minus negative IWE; their sum with no_polarity) to
+    (measured increment * ROI mask, weight_inverse, event-histogram weights * ROI mask or None).
+
+    weight_sigma > 0 (weight_loss_by_event_hist): weights = GaussianBlur(|hist|, weight_sigma) are multiplied into the
+    blurred histogram before the normalisation and returned for the prediction (src/solver/patch_eklt.py:283-286,
+    src/solver/patch_eklt_pyramid2.py:333-337, :262-263).
 
     cache_histogram = GaussianBlur(hist, sigma) / ||.||_F;  weight_inverse = 1 - 0.95 * clip(G10(|hist|)) / max
     (src/solver/patch_eklt.py:283-304).  The reductions (norm, mean, std, max) are one-off torch reductions on the
@@ -122,6 +127,11 @@ def measurement_and_weights(histogram: torch.Tensor, roi: Tuple[int, int, int, i
         blurred = sepconv2d(h, g, g, "reflect101")
     else:
         blurred = h.clone()
+    weights = None
+    if weight_sigma:
+        gw = gaussian_taps_cv2(float(weight_sigma))
+        weights = sepconv2d(h.abs(), gw, gw, "reflect101")
+        blurred = weights * blurred
     meas = blurred / torch.linalg.norm(blurred)
     mask = torch.zeros_like(meas)
     mask[roi[0]:roi[1], roi[2]:roi[3]] = 1
@@ -132,7 +142,7 @@ def measurement_and_weights(histogram: torch.Tensor, roi: Tuple[int, int, int, i
         wi = 1.0 - 0.95 * (wi / wi.max())
     else:
         wi = torch.ones_like(h)
-    return meas * mask, wi
+    return meas * mask, wi, (None if weights is None else weights * mask)
 
 
 # ---- one pyramid level --------------------------------------------------------------------------------------------
@@ -140,16 +150,28 @@ class EkltProblem:
     """The per-window constants of the objective, resident on the device."""
 
     def __init__(self, grad_x: torch.Tensor, grad_y: torch.Tensor, measured: torch.Tensor, weight_inverse: torch.Tensor,
-                 roi: Tuple[int, int, int, int], cost_weights: Tuple[float, float, float] = (1.0, 0.5, 0.1)):
-        _check_cuda(grad_x, grad_y, measured, weight_inverse)
+                 roi: Tuple[int, int, int, int], cost_weights: Tuple[float, float, float] = (1.0, 0.5, 0.1),
+                 poisson: bool = True, warp: bool = True, no_polarity: bool = False,
+                 weights: Optional[torch.Tensor] = None):
+        """`poisson`, `warp`, `no_polarity`, `weights` mirror generative_ml.poisson_model / optimize_warp / no_polarity /
+        weight_loss_by_event_hist (hot_plate1: True, True, False, None); they fix the layout of theta:
+        [(1 if poisson else 2) + (2 if warp else 0), ph, pw]."""
+        _check_cuda(grad_x, grad_y, measured, weight_inverse, weights)
         self.dtype = grad_x.dtype
         self.code = dtype_code(grad_x)
         self.H, self.W = (int(v) for v in grad_x.shape)
-        for name, t in (("grad_y", grad_y), ("measured", measured), ("weight_inverse", weight_inverse)):
+        for name, t in (("grad_y", grad_y), ("measured", measured), ("weight_inverse", weight_inverse),
+                        ("weights", weights)):
+            if t is None:
+                continue
             if tuple(t.shape) != (self.H, self.W) or t.dtype != self.dtype:
                 raise ValueError(f"{name} must be [{self.H},{self.W}] {self.dtype}, got {tuple(t.shape)} {t.dtype}")
         self.grad_x, self.grad_y = grad_x.contiguous(), grad_y.contiguous()
         self.measured, self.weight_inverse = measured.contiguous(), weight_inverse.contiguous()
+        self.weights = None if weights is None else weights.contiguous()
+        self.flags = ((_capi.EKLT_POISSON if poisson else 0) | (_capi.EKLT_WARP if warp else 0)
+                      | (_capi.EKLT_NO_POLARITY if no_polarity else 0))
+        self.channels = (1 if poisson else 2) + (2 if warp else 0)
         x0, x1, y0, y1 = (int(v) for v in roi)
         if not (0 <= x0 <= x1 <= self.H and 0 <= y0 <= y1 <= self.W):
             raise ValueError(f"roi {roi} outside the {self.H}x{self.W} image")
@@ -162,7 +184,7 @@ class EkltProblem:
 
 
 class EkltLevel:
-    """Objective of one pyramid level: theta [3,ph,pw] = (intensity, p_row, p_col)."""
+    """Objective of one pyramid level: theta [C,ph,pw] = (intensity | v_row, v_col) (+ p_row, p_col)."""
 
     def __init__(self, problem: EkltProblem, patch: int):
         self.p = problem
@@ -174,21 +196,23 @@ class EkltLevel:
             raise RuntimeError("ebos_eklt_workspace_bytes rejected the geometry")
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=problem.device)
         self.loss = torch.zeros(1, dtype=problem.dtype, device=problem.device)
-        self.grad = torch.zeros((3, self.ph, self.pw), dtype=problem.dtype, device=problem.device)
+        self.grad = torch.zeros((problem.channels, self.ph, self.pw), dtype=problem.dtype, device=problem.device)
 
     def _check_theta(self, theta: torch.Tensor) -> None:
         _check_cuda(theta)
-        if tuple(theta.shape) != (3, self.ph, self.pw) or theta.dtype != self.p.dtype or not theta.is_contiguous():
-            raise ValueError(f"theta must be a contiguous [3,{self.ph},{self.pw}] {self.p.dtype} tensor, "
+        c = self.p.channels
+        if tuple(theta.shape) != (c, self.ph, self.pw) or theta.dtype != self.p.dtype or not theta.is_contiguous():
+            raise ValueError(f"theta must be a contiguous [{c},{self.ph},{self.pw}] {self.p.dtype} tensor, "
                              f"got {tuple(theta.shape)} {theta.dtype}")
 
     def _common_args(self):
         p = self.p
-        return (ptr(p.grad_x), ptr(p.grad_y), ptr(p.measured), ptr(p.weight_inverse), p.H, p.W, self.ph, self.pw,
-                self.patch, *p.roi, p.w_data, p.w_tv, p.w_pxy, p.code, ptr(self.workspace), self.ws_bytes)
+        return (p.flags, ptr(p.grad_x), ptr(p.grad_y), ptr(p.measured), ptr(p.weight_inverse), ptr(p.weights), p.H, p.W,
+                self.ph, self.pw, self.patch, *p.roi, p.w_data, p.w_tv, p.w_pxy, p.code, ptr(self.workspace),
+                self.ws_bytes)
 
     def value_and_grad(self, theta: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(loss [1], dL/dtheta [3,ph,pw]); both alias buffers of this level (overwritten by the next call)."""
+        """(loss [1], dL/dtheta like theta); both alias buffers of this level (overwritten by the next call)."""
         self._check_theta(theta)
         check(_capi.load().ebos_eklt_value_and_grad(ptr(theta), *self._common_args(), ptr(self.loss), ptr(self.grad),
                                                     current_stream()), "ebos_eklt_value_and_grad")

@@ -3,13 +3,14 @@ loop on the GPU.
 
 Mirrors the constructor contract, config keys, start values, level schedule and return convention of
 src/solver/patch_eklt_pyramid2.py (and of its bases patch_eklt_dependent.py, patch_eklt.py,
-generative_max_likelihood.py) for the configuration the reference ships:
+generative_max_likelihood.py).  Supported `generative_ml` switches -- every combination of
 
-    generative_ml: poisson_model = true, optimize_warp = true, no_polarity = false, weight_loss_by_event_hist = false
-    cost_with_weight: diff_norm, image_gradient, flow_norm_pxy          optimizer.method: Adam
+    poisson_model, optimize_warp, no_polarity, weight_loss_by_event_hist, weight_loss_by_inverse_event_hist,
+    use_log_intensity, model_image in {current, black, background}
 
-Other switch combinations (angle model, scipy/optuna optimisers, event-histogram weights, no_polarity) select different
-objectives upstream and raise NotImplementedError here instead of silently computing something else.
+with `cost_with_weight` drawn from {diff_norm, image_gradient, flow_norm_pxy} and `optimizer.method: Adam` (the shipped
+config: poisson + warp, all three costs).  What selects a DIFFERENT algorithm upstream (angle model, scipy / optuna
+optimisers, other cost terms, 5x5 Sobel) raises NotImplementedError instead of silently computing something else.
 Visualisation / video hooks of the upstream class are not reproduced.
 """
 import logging
@@ -50,12 +51,11 @@ class PatchEkltPyramid2(SolverBase):
         unsupported = []
         if self._opt_method != "Adam":
             unsupported.append(f"optimizer.method={self._opt_method!r} (only 'Adam')")
-        if not self.is_poisson_model or self.is_angle_model:
-            unsupported.append("generative_ml.poisson_model must be true and angle_model false")
-        if not _flag(self._gml_config, "optimize_warp"):
-            unsupported.append("generative_ml.optimize_warp must be true")
-        if _flag(self._gml_config, "no_polarity") or _flag(self._gml_config, "weight_loss_by_event_hist"):
-            unsupported.append("generative_ml.no_polarity / weight_loss_by_event_hist must be false")
+        if self.is_angle_model:
+            unsupported.append("generative_ml.angle_model (asserted against upstream as well: pyramid2:300)")
+        self.optimize_warp = _flag(self._gml_config, "optimize_warp")
+        self.no_polarity = _flag(self._gml_config, "no_polarity")
+        self.weight_by_hist = _flag(self._gml_config, "weight_loss_by_event_hist")
         if _flag(self._gml_config, "px-py_as-angle-magnitude"):
             unsupported.append("px-py_as-angle-magnitude is optuna-only upstream")
         if self._gml_config.get("sobel_ksize", 3) != 3:
@@ -64,8 +64,10 @@ class PatchEkltPyramid2(SolverBase):
         if extra:
             unsupported.append(f"cost terms {extra} (supported: {SUPPORTED_COSTS})")
         if unsupported:
-            raise NotImplementedError("event_based_bos_b200.PatchEkltPyramid2 implements the hot_plate1 objective only: "
-                                      + "; ".join(unsupported))
+            raise NotImplementedError("event_based_bos_b200.PatchEkltPyramid2 does not implement: " + "; ".join(unsupported))
+        if "flow_norm_pxy" in self.cost_weight and not self.optimize_warp:
+            # upstream: FlowNormPxy.calculate fails on the missing "pxy" key at the first iteration (costs/base.py)
+            raise KeyError("pxy: cost term flow_norm_pxy needs generative_ml.optimize_warp")
         ekc = self.slv_config.get("eklt", {}) or {}
         self._dtype = torch.float32 if str(ekc.get("precision", "64")) == "32" else torch.float64
         self.use_cuda_graph = bool(ekc.get("cuda_graph", True))
@@ -89,23 +91,27 @@ class PatchEkltPyramid2(SolverBase):
     def calculate_iwe_cache(self, events: np.ndarray) -> None:
         """Polarity histogram -> measured increment and weight_inverse (src/solver/patch_eklt.py:271-304)."""
         pol = self.orig_imager.create_iwe(events, method="polarity", sigma=0)
-        hist = torch.as_tensor(pol[0] - pol[1], device="cuda").to(self._dtype)
+        hist = torch.as_tensor(pol[0] + pol[1] if self.no_polarity else pol[0] - pol[1], device="cuda").to(self._dtype)
         roi = (self.crop_xmin, self.crop_xmax, self.crop_ymin, self.crop_ymax)
-        self.cache_measured, self.weight_inverse = eklt.measurement_and_weights(
-            hist, roi, iwe_sigma=self._gml_config["iwe_sigma"], weight_inverse=self.do_weight_inverse)
+        self.cache_measured, self.weight_inverse, self.cache_weights = eklt.measurement_and_weights(
+            hist, roi, iwe_sigma=self._gml_config["iwe_sigma"], weight_inverse=self.do_weight_inverse,
+            weight_sigma=self._gml_config["weight_sigma"] if self.weight_by_hist else 0.0)
 
     def _initialize_velocity(self) -> np.ndarray:
-        """src/solver/generative_max_likelihood.py:436-442 (poisson model + optimize_warp)."""
-        return np.array([np.random.random() * 2.0 - 1, 0.0, 0.0], dtype=np.float64)
+        """src/solver/generative_max_likelihood.py:425-450: random intensity (one np.random draw) or zero velocity,
+        plus a zero translation with optimize_warp."""
+        head = [np.random.random() * 2.0 - 1] if self.is_poisson_model else [0.0, 0.0]
+        return np.array(head + ([0.0, 0.0] if self.optimize_warp else []), dtype=np.float64)
 
     def _start_parameters(self, level: int, previous: Optional[torch.Tensor]) -> torch.Tensor:
         """x0 of a level (src/solver/patch_eklt_pyramid2.py:225-248), drawing from np.random exactly like upstream:
         one draw to measure the parameter dimension, then -- at the coarsest level -- one per patch; the per-patch
-        triples are concatenated and reshaped to [3,ph,pw] as upstream does (which interleaves them)."""
+        tuples are concatenated and reshaped to [n_dim,ph,pw] as upstream does (which interleaves them)."""
         _, ph, pw = self.levels[level]
         self.n_parameter_dim = len(self._initialize_velocity())
         if level == 0:
-            x0 = np.concatenate([self._initialize_velocity() for _ in range(ph * pw)]).reshape((3, ph, pw))
+            x0 = np.concatenate([self._initialize_velocity() for _ in range(ph * pw)]).reshape(
+                (self.n_parameter_dim, ph, pw))
             return torch.as_tensor(x0, device="cuda").to(self._dtype)
         return eklt.resize_params(previous, (ph, pw))
 
@@ -123,7 +129,8 @@ class PatchEkltPyramid2(SolverBase):
         roi = (self.crop_xmin, self.crop_xmax, self.crop_ymin, self.crop_ymax)
         weights = tuple(float(self.cost_weight.get(k, 0.0)) for k in SUPPORTED_COSTS)
         problem = eklt.EkltProblem(self._gradient_x_torch, self._gradient_y_torch, self.cache_measured,
-                                   self.weight_inverse, roi, weights)
+                                   self.weight_inverse, roi, weights, poisson=self.is_poisson_model,
+                                   warp=self.optimize_warp, no_polarity=self.no_polarity, weights=self.cache_weights)
         theta = None
         self.best_params_per_scale = {}
         self.history = {}
@@ -139,6 +146,7 @@ class PatchEkltPyramid2(SolverBase):
             if hist is not None:
                 self.history[scale] = hist
         patch = self.levels[-1][0]
-        dense = eklt.upsample(eklt.patch_flow(theta[0]), patch, tuple(self.orig_image_shape))
+        patch_flow = eklt.patch_flow(theta[0]) if self.is_poisson_model else theta[:2].contiguous()
+        dense = eklt.upsample(patch_flow, patch, tuple(self.orig_image_shape))
         self.iter_cnt += 1
         return dense.double().cpu().numpy() * self.estimate_mask_dense_numpy

@@ -273,23 +273,36 @@ EBOS_API int ebos_time_to_index(const int32_t* t_us, int64_t n, double time, int
  * M is the ROI rectangle rows [roi_x0,roi_x1) x cols [roi_y0,roi_y1) (estimate_mask_dense, :50-51).
  * grad_x / grad_y: [H,W] frame gradients (row / column derivative; cv2.Sobel of _set_frame,
  * src/solver/generative_max_likelihood.py:194-213); measured: [H,W] normalised event histogram ALREADY multiplied by M;
- * weight_inverse: [H,W].  All of `dtype`, device pointers.  loss: [1], grad: [3,ph,pw] (fully overwritten).
+ * weight_inverse: [H,W].  All of `dtype`, device pointers.  loss: [1], grad: like theta (fully overwritten).
+ * flags (generative_ml.* of the yaml; hot_plate1 = POISSON | WARP) select the reference's other objectives:
+ *   EBOS_EKLT_POISSON      theta[0] is an intensity and the patch flow its Sobel/8; without it theta[0:2] IS the patch
+ *                          flow (`_get_patch_flow`, src/solver/patch_eklt_pyramid2.py:290-303)
+ *   EBOS_EKLT_WARP         the last two channels of theta translate the frame gradients and carry the pxy term; without
+ *                          it the gradients are used as they are and w_pxy is ignored (:354-357)
+ *   EBOS_EKLT_NO_POLARITY  q = |q| (:360-361)
+ * theta: [(POISSON ? 1 : 2) + (WARP ? 2 : 0), ph, pw].  weights: NULL or [H,W] event-histogram weights multiplied into q
+ * before the normalisation (weight_loss_by_event_hist, :363-364).
  * workspace: >= ebos_eklt_workspace_bytes(...) bytes, 256-byte aligned, contents irrelevant on entry.
  * Stream-ordered, CUDA-graph capturable (no host synchronisation, no allocation). */
+#define EBOS_EKLT_POISSON 1
+#define EBOS_EKLT_WARP 2
+#define EBOS_EKLT_NO_POLARITY 4
 EBOS_API size_t ebos_eklt_workspace_bytes(int H, int W, int ph, int pw, int patch, int dtype);
-EBOS_API int ebos_eklt_value_and_grad(const void* theta, const void* grad_x, const void* grad_y, const void* measured,
-                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
-                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
-                             size_t workspace_bytes, void* loss, void* grad, void* stream);
+EBOS_API int ebos_eklt_value_and_grad(const void* theta, int flags, const void* grad_x, const void* grad_y,
+                             const void* measured, const void* weight_inverse, const void* weights, int H, int W, int ph,
+                             int pw, int patch, int roi_x0, int roi_x1, int roi_y0, int roi_y1, double w_data, double w_tv,
+                             double w_pxy, int dtype, void* workspace, size_t workspace_bytes, void* loss, void* grad,
+                             void* stream);
 
 /* One solver iteration of a level (src/solver/patch_eklt_pyramid2.py:265-285: zero_grad / loss / backward / Adam step):
- * ebos_eklt_value_and_grad followed by ebos_adam_step_graph on theta (3*ph*pw values).  `step_dev` (int32[1]) counts the
+ * ebos_eklt_value_and_grad followed by ebos_adam_step_graph on all of theta.  `step_dev` (int32[1]) counts the
  * iterations done and is advanced by the call; `loss` receives the objective BEFORE the update. */
-EBOS_API int ebos_eklt_adam_iteration(void* theta, const void* grad_x, const void* grad_y, const void* measured,
-                             const void* weight_inverse, int H, int W, int ph, int pw, int patch, int roi_x0, int roi_x1,
-                             int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy, int dtype, void* workspace,
-                             size_t workspace_bytes, void* loss, void* grad, void* exp_avg, void* exp_avg_sq, double lr,
-                             double beta1, double beta2, double eps, int32_t* step_dev, void* stream);
+EBOS_API int ebos_eklt_adam_iteration(void* theta, int flags, const void* grad_x, const void* grad_y, const void* measured,
+                             const void* weight_inverse, const void* weights, int H, int W, int ph, int pw, int patch,
+                             int roi_x0, int roi_x1, int roi_y0, int roi_y1, double w_data, double w_tv, double w_pxy,
+                             int dtype, void* workspace, size_t workspace_bytes, void* loss, void* grad, void* exp_avg,
+                             void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int32_t* step_dev,
+                             void* stream);
 
 /* interpolate_dense_flow_from_patch_tensor on its own (src/solver/patch_eklt.py:173-204): patch_values [channels,ph,pw]
  * -> dense [channels,H,W]; and poisson_to_flow (src/solver/patch_eklt_dependent.py:259-281): intensity [ph,pw] ->

@@ -12,14 +12,19 @@
 using namespace ebos::eklt;
 
 template <typename T>
-static void forward_t(const Geom& g, const T* theta, const T* gx, const T* gy, T* pf, T* q, T* F, T* trans, double* sums) {
+static void forward_t(const Geom& g, int flags, const T* theta, const T* gx, const T* gy, const T* weights, T* pf, T* q,
+                      T* F, T* trans, double* sums) {
   const int np = g.ph * g.pw;
-  for (int k = 0; k < np; ++k) sobel_over_8_at(theta, g.ph, g.pw, k / g.pw, k % g.pw, pf[k], pf[np + k]);
+  for (int k = 0; k < np; ++k) {
+    if (flags & kPoisson) sobel_over_8_at(theta, g.ph, g.pw, k / g.pw, k % g.pw, pf[k], pf[np + k]);
+    else { pf[k] = theta[k]; pf[np + k] = theta[np + k]; }
+  }
+  const T* tr = (flags & kWarp) ? theta + flow_channels(flags) * np : nullptr;
   double sq = 0.0, sp = 0.0;
   const int64_t plane = (int64_t)g.H * g.W;
   for (int i = 0; i < g.H; ++i)
     for (int j = 0; j < g.W; ++j) {
-      const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+      const Pixel<T> p = eval_pixel<T>(g, flags, pf, tr, gx, gy, weights, i, j);
       const int64_t k = (int64_t)i * g.W + j;
       q[k] = p.q;
       F[k] = p.m ? p.f0 : (T)0;
@@ -60,18 +65,22 @@ static void columns_t(const Geom& g, const T* q, const T* meas, double q2, doubl
 }
 
 template <typename T>
-static void backward_t(const Geom& g, const T* theta, const T* pf, const T* gx, const T* gy, const T* meas, const T* dF,
-                       const double* colsum, const double* scal, double w_pxy, T* dU, T* dPad, T* dP, T* grad) {
+static void backward_t(const Geom& g, int flags, const T* theta, const T* pf, const T* gx, const T* gy, const T* weights,
+                       const T* meas, const T* dF, const double* colsum, const double* scal, double w_pxy, T* dU, T* dPad,
+                       T* dP, T* grad) {
+  const T* tr = (flags & kWarp) ? theta + flow_channels(flags) * g.ph * g.pw : nullptr;
+  if (!(flags & kWarp)) w_pxy = 0.0;
   BackScalars s;
   s.n = scal[0]; s.mx = scal[1]; s.tie_w = scal[2]; s.S = scal[3];
   const int64_t plane = (int64_t)g.H * g.W;
   const double w_pxy_hw = w_pxy / ((double)g.H * g.W);
   for (int i = 0; i < g.H; ++i)
     for (int j = 0; j < g.W; ++j) {
-      const Pixel<T> p = eval_pixel<T>(g, pf, theta, gx, gy, i, j);
+      const Pixel<T> p = eval_pixel<T>(g, flags, pf, tr, gx, gy, weights, i, j);
       const int64_t k = (int64_t)i * g.W + j;
       T out[4];
-      backward_pixel<T>(p, meas[k], colsum[j] == s.mx, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw, out);
+      backward_pixel<T>(p, flags, meas[k], colsum[j] == s.mx, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw,
+                        out);
       for (int c = 0; c < 4; ++c) dU[c * plane + k] = out[c];
     }
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
@@ -99,21 +108,33 @@ static void backward_t(const Geom& g, const T* theta, const T* pf, const T* gx, 
       for (int B = b0; B < b1; ++B) sacc += (double)dPad[((int64_t)c * PH + A) * PW + B];
     dP[k] = (T)sacc;
   }
+  const int nf = flow_channels(flags);
   for (int k = 0; k < np; ++k) {
-    grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
-    grad[np + k] = dP[2 * np + k];
-    grad[2 * np + k] = dP[3 * np + k];
+    if (flags & kPoisson) {
+      grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
+    } else {
+      grad[k] = dP[k];
+      grad[np + k] = dP[np + k];
+    }
+    if (flags & kWarp) {
+      grad[nf * np + k] = dP[2 * np + k];
+      grad[(nf + 1) * np + k] = dP[3 * np + k];
+    }
   }
 }
 
 extern "C" {
 
 // dims = {H, W, ph, pw, patch, x0, x1, y0, y1}; is_f64 selects the element type of every array argument.
-int eklt_host_forward(const int* dims, int is_f64, const void* theta, const void* gx, const void* gy, void* pf, void* q,
-                      void* F, void* trans, double* sums) {
+int eklt_host_forward(const int* dims, int is_f64, int flags, const void* theta, const void* gx, const void* gy,
+                      const void* weights, void* pf, void* q, void* F, void* trans, double* sums) {
   const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
-  if (is_f64) forward_t<double>(g, (const double*)theta, (const double*)gx, (const double*)gy, (double*)pf, (double*)q, (double*)F, (double*)trans, sums);
-  else forward_t<float>(g, (const float*)theta, (const float*)gx, (const float*)gy, (float*)pf, (float*)q, (float*)F, (float*)trans, sums);
+  if (is_f64)
+    forward_t<double>(g, flags, (const double*)theta, (const double*)gx, (const double*)gy, (const double*)weights,
+                      (double*)pf, (double*)q, (double*)F, (double*)trans, sums);
+  else
+    forward_t<float>(g, flags, (const float*)theta, (const float*)gx, (const float*)gy, (const float*)weights, (float*)pf,
+                     (float*)q, (float*)F, (float*)trans, sums);
   return 0;
 }
 
@@ -125,16 +146,18 @@ int eklt_host_columns(const int* dims, int is_f64, const void* q, const void* me
   return 0;
 }
 
-int eklt_host_backward(const int* dims, int is_f64, const void* theta, const void* pf, const void* gx, const void* gy,
-                       const void* meas, const void* dF, const double* colsum, const double* scal, double w_pxy, void* dU,
-                       void* dPad, void* dP, void* grad) {
+int eklt_host_backward(const int* dims, int is_f64, int flags, const void* theta, const void* pf, const void* gx,
+                       const void* gy, const void* weights, const void* meas, const void* dF, const double* colsum,
+                       const double* scal, double w_pxy, void* dU, void* dPad, void* dP, void* grad) {
   const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
   if (is_f64)
-    backward_t<double>(g, (const double*)theta, (const double*)pf, (const double*)gx, (const double*)gy, (const double*)meas,
-                       (const double*)dF, colsum, scal, w_pxy, (double*)dU, (double*)dPad, (double*)dP, (double*)grad);
+    backward_t<double>(g, flags, (const double*)theta, (const double*)pf, (const double*)gx, (const double*)gy,
+                       (const double*)weights, (const double*)meas, (const double*)dF, colsum, scal, w_pxy, (double*)dU,
+                       (double*)dPad, (double*)dP, (double*)grad);
   else
-    backward_t<float>(g, (const float*)theta, (const float*)pf, (const float*)gx, (const float*)gy, (const float*)meas,
-                      (const float*)dF, colsum, scal, w_pxy, (float*)dU, (float*)dPad, (float*)dP, (float*)grad);
+    backward_t<float>(g, flags, (const float*)theta, (const float*)pf, (const float*)gx, (const float*)gy,
+                      (const float*)weights, (const float*)meas, (const float*)dF, colsum, scal, w_pxy, (float*)dU,
+                      (float*)dPad, (float*)dP, (float*)grad);
   return 0;
 }
 

@@ -116,20 +116,25 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dtype=np.float64):
+def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dtype=np.float64, poisson=True, warp=True,
+                        no_polarity=False, hist_weights=None):
     H, W = gx.shape
-    _, ph, pw = theta.shape
+    nt, ph, pw = theta.shape
     wd, wtv, wp = (float(v) for v in weights)
+    flags = (1 if poisson else 0) | (2 if warp else 0) | (4 if no_polarity else 0)
     dims = (ctypes.c_int * 9)(H, W, ph, pw, patch, *roi)
     f64 = int(dtype == np.float64)
     c = lambda a: np.ascontiguousarray(a, dtype=dtype)
     theta, gx, gy, meas, winv = c(theta), c(gx), c(gy), c(meas), c(winv)
+    hw = None if hist_weights is None else c(hist_weights)
+    hw_p = None if hw is None else _p(hw)
     pf = np.zeros((2, ph, pw), dtype)
     q = np.zeros((H, W), dtype)
     F = np.zeros((2, H, W), dtype)
     tr = np.zeros((2, H, W), dtype)
     sums = np.zeros(2)
-    lib.eklt_host_forward(dims, f64, _p(theta), _p(gx), _p(gy), _p(pf), _p(q), _p(F), _p(tr), _p(sums))
+    lib.eklt_host_forward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 9
+    lib.eklt_host_forward(dims, f64, flags, _p(theta), _p(gx), _p(gy), hw_p, _p(pf), _p(q), _p(F), _p(tr), _p(sums))
     colsum = np.zeros(W)
     scal = np.zeros(4)
     lib.eklt_host_columns.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
@@ -142,12 +147,12 @@ def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dty
     dU = np.zeros((4, H, W), dtype)
     dPad = np.zeros((4, ph + 2, pw + 2), dtype)
     dP = np.zeros((4, ph, pw), dtype)
-    grad = np.zeros((3, ph, pw), dtype)
-    lib.eklt_host_backward.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8 + [ctypes.c_double] + \
-                                      [ctypes.c_void_p] * 4
-    lib.eklt_host_backward(dims, f64, _p(theta), _p(pf), _p(gx), _p(gy), _p(meas), _p(dF), _p(colsum), _p(scal), wp,
-                           _p(dU), _p(dPad), _p(dP), _p(grad))
-    loss = wd * scal[1] + wtv * tv + wp * sums[1] / (H * W)
+    grad = np.zeros((nt, ph, pw), dtype)
+    lib.eklt_host_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 9 + \
+                                      [ctypes.c_double] + [ctypes.c_void_p] * 4
+    lib.eklt_host_backward(dims, f64, flags, _p(theta), _p(pf), _p(gx), _p(gy), hw_p, _p(meas), _p(dF), _p(colsum),
+                           _p(scal), wp, _p(dU), _p(dPad), _p(dP), _p(grad))
+    loss = wd * scal[1] + wtv * tv + (wp * sums[1] / (H * W) if warp else 0.0)
     return {"loss": loss, "grad": grad, "q": q, "F": F, "trans": tr, "pf": pf, "colsum": colsum, "n": scal[0], "dU": dU}
 
 
@@ -262,14 +267,24 @@ def test_solver_registry_and_config_contract():
     assert eklt.patch_grid((720, 1280), 64) == E.patch_grid((720, 1280), 64)
     assert np.allclose(eklt.gaussian_taps_cv2(2.0), E.cv2_gaussian_taps(2.0), rtol=0, atol=0)
     assert np.allclose(eklt.gaussian_taps_scipy(10.0), E.scipy_gaussian_taps(10.0), rtol=0, atol=0)
-    for path, value in [(("optimizer", "method"), "Newton-CG"), (("generative_ml", "poisson_model"), False),
-                        (("generative_ml", "optimize_warp"), False), (("generative_ml", "no_polarity"), True),
-                        (("generative_ml", "weight_loss_by_event_hist"), True),
-                        (("cost_with_weight", "total_variation"), 3.0)]:
+    for path, value in [(("optimizer", "method"), "Newton-CG"), (("generative_ml", "angle_model"), True),
+                        (("generative_ml", "sobel_ksize"), 5), (("cost_with_weight", "total_variation"), 3.0)]:
         cfg = copy.deepcopy(HOT_PLATE1_SOLVER)
         cfg[path[0]][path[1]] = value
         with pytest.raises(NotImplementedError):
             cls((720, 1280), (720, 640), {}, cfg, None)
+    cfg = copy.deepcopy(HOT_PLATE1_SOLVER)
+    cfg["generative_ml"]["optimize_warp"] = False               # flow_norm_pxy without a translation: KeyError upstream too
+    with pytest.raises(KeyError):
+        cls((720, 1280), (720, 640), {}, cfg, None)
+    # start values of the other parameterisations (src/solver/generative_max_likelihood.py:425-450)
+    for poisson, warp, n_dim in [(True, False, 1), (False, True, 4), (False, False, 2)]:
+        cfg = copy.deepcopy(HOT_PLATE1_SOLVER)
+        cfg["generative_ml"].update({"poisson_model": poisson, "optimize_warp": warp, "weight_sigma": 5})
+        if not warp:
+            cfg["cost_with_weight"].pop("flow_norm_pxy")
+        v = cls((720, 1280), (720, 640), {}, cfg, None)._initialize_velocity()
+        assert v.shape == (n_dim,) and (poisson or not v.any())
     import torch
 
     if not torch.cuda.is_available():          # no CPU fallback: the estimate needs the device
@@ -307,3 +322,25 @@ def test_oracle_switch_variants_match_reference_autograd(gold):
         assert np.abs(r["grad"] - c["grad"]).max() <= 1e-12 * np.abs(c["grad"]).max(), c["name"]
         names.append(c["name"])
     assert names == ["all", "flow_nowarp", "flow_warp", "hist_weights", "no_polarity", "poisson_nowarp"]
+
+
+def test_kernel_arithmetic_switch_variants_match_reference(gold, host_lib):
+    """The same combinations through the serial build of the device functions (flags / weights of the C-ABI)."""
+    for c in _variant_cases(gold):
+        h = host_value_and_grad(host_lib, c["theta"], gold["grad_x"], gold["grad_y"], c["measured"], c["winv"],
+                                gold["roi_t"], c["patch"], c["cost_weights"], poisson=c["poisson"], warp=c["warp"],
+                                no_polarity=c["no_polarity"], hist_weights=c["weights"])
+        assert abs(h["loss"] - c["loss"]) <= 1e-13, c["name"]
+        assert np.abs(h["grad"] - c["grad"]).max() <= 1e-11 * np.abs(c["grad"]).max(), c["name"]
+
+
+def test_preprocessing_oracle_variants_match_reference(gold):
+    """no_polarity (|pos + neg| histogram) and weight_loss_by_event_hist (Gaussian-blurred |hist| weights)."""
+    v = np.load(VARIANTS)
+    H, W = (int(x) for x in gold["image"])
+    m, wi, _, w = E.measurement_and_weights(gold["events"], (H, W), gold["roi_t"], weight_sigma=5.0)
+    assert np.abs(m - v["hist_weights_measured"]).max() <= 1e-15
+    assert np.abs(w - v["hist_weights_weights"]).max() <= 1e-14
+    m, wi, _ = E.measurement_and_weights(gold["events"], (H, W), gold["roi_t"], no_polarity=True)
+    assert np.abs(m - v["no_polarity_measured"]).max() <= 1e-15
+    assert np.abs(wi - v["no_polarity_weight_inverse"]).max() <= 1e-13

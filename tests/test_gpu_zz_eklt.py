@@ -173,7 +173,8 @@ def test_preprocessing_matches_reference(gold, eklt):
     assert np.array_equal(gy.cpu().numpy(), gold["grad_y"])
     H, W = (int(v) for v in gold["image"])
     hist = E.polarity_histogram(gold["events"], (H, W))
-    meas, winv = eklt.measurement_and_weights(dev(hist), gold["roi_t"])
+    meas, winv, none = eklt.measurement_and_weights(dev(hist), gold["roi_t"])
+    assert none is None
     assert np.abs(meas.cpu().numpy() - gold["measured"]).max() <= 1e-14
     assert np.abs(winv.cpu().numpy() - gold["weight_inverse"]).max() <= 1e-12
     # both border modes against the oracle on an odd-sized image, fp32
@@ -184,6 +185,38 @@ def test_preprocessing_matches_reference(gold, eklt):
         out = eklt.sepconv2d(dev(img, torch.float32), taps, taps[20:61], mode).cpu().numpy()
         ref = E.correlate_separable(img, taps, taps[20:61], code)
         assert np.abs(out - ref).max() <= 1e-5
+
+
+VARIANTS = GOLDEN.replace("reference_eklt_v1", "reference_eklt_variants_v1")
+
+
+def test_switch_variants_match_reference_autograd(gold, eklt):
+    """poisson_model / optimize_warp / no_polarity / weight_loss_by_event_hist combinations (flags and weights of the
+    C-ABI) against the reference's autograd, plus their preprocessing (|pos + neg| histogram, histogram weights)."""
+    v = np.load(VARIANTS)
+    patch = int(v["patch"])
+    H, W = (int(x) for x in gold["image"])
+    names = sorted({k[:-len("_theta")] for k in v.files if k.endswith("_theta")})
+    assert len(names) == 6
+    for name in names:
+        poisson, warp, no_pol = (bool(x) for x in v[name + "_flags"])
+        weights = dev(v[name + "_weights"]) if name + "_weights" in v.files else None
+        winv = v[name + "_weight_inverse"] if name + "_weight_inverse" in v.files else gold["weight_inverse"]
+        prob = eklt.EkltProblem(dev(gold["grad_x"]), dev(gold["grad_y"]), dev(v[name + "_measured"]), dev(winv),
+                                gold["roi_t"], tuple(float(x) for x in v[name + "_cost_weights"]), poisson=poisson,
+                                warp=warp, no_polarity=no_pol, weights=weights)
+        loss, grad = prob.level(patch).value_and_grad(dev(v[name + "_theta"]))
+        assert grad.shape == v[name + "_grad"].shape, name
+        assert abs(float(loss[0]) - float(v[name + "_loss"])) <= 1e-11, name
+        assert rel(grad.cpu().numpy(), v[name + "_grad"]) <= 1e-9, name
+        # preprocessing of the variant on the device
+        hist = E.polarity_histogram(gold["events"], (H, W), no_polarity=no_pol)
+        meas, wi, w = eklt.measurement_and_weights(dev(hist), gold["roi_t"],
+                                                   weight_sigma=5.0 if weights is not None else 0.0)
+        assert np.abs(meas.cpu().numpy() - v[name + "_measured"]).max() <= 1e-14, name
+        assert np.abs(wi.cpu().numpy() - winv).max() <= 1e-12, name
+        if weights is not None:
+            assert np.abs(w.cpu().numpy() - v[name + "_weights"]).max() <= 1e-13, name
 
 
 def test_level_solve_graph_and_eager_match_oracle(gold, eklt):
