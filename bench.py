@@ -576,7 +576,7 @@ def run_eklt(args, rank, world, local):
 
     cfg = json.loads(json.dumps(HOT_PLATE1_SOLVER))
     cfg["optimizer"]["n_iter"] = args.solve_iters
-    cfg["eklt"] = {"precision": args.eklt_precision}
+    cfg["eklt"] = {"precision": args.eklt_precision, "cuda_graph": not args.eklt_no_graph}
     slv = solver.collections["patch_eklt_pyramid2"]((H, W), (720, 640), {}, cfg, None)
     ev, frame = eklt_inputs(args.solve_events, seed=rank)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -705,6 +705,7 @@ def main():
     ap.add_argument("--solve-iters", type=int, default=600)
     ap.add_argument("--solve-concurrency", type=int, default=8, help="independent windows in flight per GPU (solve workload)")
     ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
+    ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")

@@ -154,8 +154,22 @@ __global__ void __launch_bounds__(256) k_column_max(Geom g, const T* __restrict_
   }
   __syncthreads();
   mx = s_mx;
+  // ties: count all of them; remember those inside the ROI columns (outside, M = 0 and they add nothing to S)
+  constexpr int kList = 32;
+  __shared__ int s_list[kList];
+  __shared__ int s_nlist;
+  if (threadIdx.x == 0) s_nlist = 0;
+  __syncthreads();
   double cnt = 0.0;
-  for (int j = threadIdx.x; j < g.W; j += blockDim.x) cnt += (colsum[j] == mx) ? 1.0 : 0.0;
+  for (int j = threadIdx.x; j < g.W; j += blockDim.x) {
+    if (colsum[j] == mx) {
+      cnt += 1.0;
+      if (j >= g.y0 && j < g.y1) {
+        const int k = atomicAdd(&s_nlist, 1);
+        if (k < kList) s_list[k] = j;
+      }
+    }
+  }
   cnt = block_sum(cnt, red);
   if (threadIdx.x == 0) s_cnt = cnt;
   __syncthreads();
@@ -164,13 +178,19 @@ __global__ void __launch_bounds__(256) k_column_max(Geom g, const T* __restrict_
   const T inv = (T)(1.0 / (n + kNormEps));
   const double tie_w = w_data / cnt;
   double S = 0.0;
-  for (int j = g.y0; j < g.y1; ++j) {          // outside the ROI columns M = 0
-    if (colsum[j] != mx) continue;             // uniform over the CTA
+  const int n_list = s_nlist;
+  auto column = [&](int j) {
     for (int i = g.x0 + threadIdx.x; i < g.x1; i += blockDim.x) {
       const int64_t k = (int64_t)i * g.W + j;
       const T D = residual<T>(q[k], true, meas[k], inv);
       S += sgn((double)D) * tie_w * (double)q[k];
     }
+  };
+  if (n_list <= kList) {
+    for (int t = 0; t < n_list; ++t) column(s_list[t]);
+  } else {                                       // degenerate (e.g. everything zero): walk all ROI columns
+    for (int j = g.y0; j < g.y1; ++j)
+      if (colsum[j] == mx) column(j);            // uniform over the CTA
   }
   S = block_sum(S, red);
   if (threadIdx.x == 0) {
@@ -237,6 +257,37 @@ __global__ void __launch_bounds__(256) k_cell_gather(Geom g, int nch, const T* _
     if (c >= nch) break;                      // uniform over the CTA
     const double t = block_sum(s[c], red);
     if (threadIdx.x == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)t;
+  }
+}
+
+// Same for small supports (patch <= 16: at most 1024 pixels per cell): one WARP per padded cell, eight cells per CTA,
+// shuffle reductions only.  At the finest level (8-px patches, 92 x 162 cells at 1280x720) the CTA-per-cell form
+// would spend its time in four block reductions over one pixel per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) k_cell_gather_warp(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ dPad) {
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  const int cell = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= PW * PH) return;                  // whole warps leave together
+  const int A = cell / PW, B = cell % PW;
+  int i0, i1, j0, j1;
+  cell_support(A, g.patch, g.h1, g.H, i0, i1);
+  cell_support(B, g.patch, g.w1, g.W, j0, j1);
+  const int nj = j1 - j0, total = (i1 - i0) * nj;
+  const int64_t plane = (int64_t)g.H * g.W;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k = lane; k < total; k += 32) {
+    const int i = i0 + k / nj, j = j0 + k % nj;
+    const double w = (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)cell_weight<T>(B, j, g.w1, g.patch);
+    const int64_t idx = (int64_t)i * g.W + j;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < nch) s[c] += w * (double)dU[c * plane + idx];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= nch) break;
+    const double t = warp_sum(s[c]);
+    if (lane == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)t;
   }
 }
 
@@ -365,7 +416,9 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
   k_backward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
                                     w_pxy / ((double)g.H * g.W), dU);
   EBOS_LAUNCH_CHECK("ebos_eklt backward");
-  k_cell_gather<T><<<dim3(g.pw + 2 * g.pad, g.ph + 2 * g.pad), 256, 0, st>>>(g, nch, dU, dPad);
+  const int n_cells = (g.pw + 2 * g.pad) * (g.ph + 2 * g.pad);
+  if (g.patch <= 16) k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
+  else k_cell_gather<T><<<dim3(g.pw + 2 * g.pad, g.ph + 2 * g.pad), 256, 0, st>>>(g, nch, dU, dPad);
   k_fold<T><<<(nch * np + 127) / 128, 128, 0, st>>>(g, nch, dPad, dP);
   k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, flags, dP, w.tv_acc, w.acc, w_data, w_tv, w_pxy, grad, loss);
   EBOS_LAUNCH_CHECK("ebos_eklt gradient");
