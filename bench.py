@@ -596,11 +596,16 @@ def run_eklt(args, rank, world, local):
     dt = torch.float32 if args.eklt_precision == "32" else torch.float64
     prob = eklt.EkltProblem(slv._gradient_x_torch, slv._gradient_y_torch, slv.cache_measured, slv.weight_inverse,
                             (0, 720, 320, 960), (1.0, 0.5, 0.1))
-    per_level = {}
+    per_level, per_level_legacy = {}, {}
     for patch, ph, pw in slv.levels:
         lvl = prob.level(patch)
         th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous()
         per_level[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+        os.environ["EBOS_EKLT_LEGACY"] = "1"          # the first chain (whole-image TV kernel, per-cell 2-D gather)
+        try:
+            per_level_legacy[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+        finally:
+            os.environ.pop("EBOS_EKLT_LEGACY", None)
     if rank != 0:
         return
     iters = [args.solve_iters // (len(slv.levels) + 1 - s + 1) for s in range(1, len(slv.levels) + 1)]
@@ -624,7 +629,7 @@ def run_eklt(args, rank, world, local):
                          "achieved": alg_eval / (per_level[worst] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_kind},
-            "eval_ms_per_level": per_level,
+            "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
             "gpu_launches": args.steps * sum(iters) * 12}

@@ -6,22 +6,25 @@
 // Per-pixel arithmetic lives in ebos_eklt_math.cuh (host+device, checked on the CPU against oracle/spec_eklt.py);
 // this file holds the parallel structure.  One evaluation =
 //
-//   memset(acc, colsum)
+//   memset(acc, colsum, colS)
 //   k_patch_flow     pf = Sobel(theta[0]) / 8                              [2,ph,pw]       (tiny; poisson model only)
 //   k_forward        per pixel: up-sample pf and theta[1:3], warp the frame gradients, q; writes q and the masked
-//                    flow F = f*M; block-reduces sum q^2 and sum ||t*M||
-//   ebos_flow_tv     TV(F; w_inv) value and w_tv * dTV/dF  (the kernel of the contrast-maximisation path)
-//   k_column_sums    colsum[j] = sum_i |pred - meas|_ij     (needs ||q||)
-//   k_column_max     data term = max_j colsum, tie count, S = <g_pred*M, q>        (one CTA)
+//                    flow F = f*M; block-reduces sum q^2 and sum ||t*M|| (16 spread accumulator slots)
+//   k_tv_roi         TV(F; w_inv) value and w_tv * dTV/dF in gather form over the ROI box +-2
+//                    (legacy chain: ebos_flow_tv over the whole image -- 39 us in fp64 on B200, r01h launch list)
+//   k_column_sums    colsum[j] = sum_i |pred - meas|_ij, colS[j] = sum_i sign(.) q_ij     (needs ||q||)
+//   k_column_max     data term = max_j colsum, tie count, S = sum of colS over the arg-max columns   (one CTA)
 //   k_backward       per pixel: re-evaluates the forward, writes d/d(f0,f1,t0,t1)  [4,H,W]
-//   k_cell_gather    transposed up-sampling, one CTA per padded patch cell          [4,ph+2,pw+2]
+//   k_gather_cols/rows  transposed up-sampling as two separable passes (legacy: one CTA / warp per padded cell over its
+//                    2-D support, which reads every gradient plane four times: 33-55 us)
 //   k_fold           folds the replicate padding                                    [4,ph,pw]
 //   k_param_grad     Sobel adjoint for the intensity channel, copies the translation channels, writes the loss
 //
 // All plane passes are HBM/L2 streaming work (no dense contraction: tensor cores unused).  Algorithmic bytes per
 // evaluation (P = H*W*sizeof(T)): forward 2P (gradients) + 3P (q, F) ; TV 3P + 2P ; columns 2P ; backward 2P + 2P + P
-// + 4P ; gather 4P  =>  25P.
+// + 4P ; gather 4P  =>  25P (the figure bench.py credits; the ROI-restricted TV moves less).
 #include <algorithm>
+#include <cstdlib>
 
 #include "ebos_common.cuh"
 #include "ebos_eklt_math.cuh"
@@ -29,14 +32,31 @@
 namespace ebos {
 namespace eklt {
 
-// acc (double) layout behind the TV accumulators
-constexpr int kAccQ2 = 0, kAccPxy = 1, kAccMax = 2, kAccTieW = 3, kAccS = 4, kAccLoss = 5, kAccData = 6, kAccTv = 7,
-              kAccPxyMean = 8, kAccN = 16;
+// acc (double) layout behind the TV accumulators of ebos_flow_tv.  Sums fed by one atomic per CTA are spread over 16
+// slots each (same-address double atomics from ~1000 CTAs serialise in the L2 atomic unit, ~6 ns apiece).
+constexpr int kAccMax = 0, kAccTieW = 1, kAccS = 2, kAccLoss = 3, kAccData = 4, kAccTv = 5, kAccPxyMean = 6;
+constexpr int kSpread = 16, kAccQ2 = 16, kAccPxy = 32, kAccTvSum = 48, kAccN = 64;
+__device__ __forceinline__ double acc_sum(const double* __restrict__ acc, int base) {
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < kSpread; ++i) t += acc[base + i];
+  return t;
+}
+__device__ __forceinline__ int acc_slot() { return (blockIdx.x + 7 * blockIdx.y) & (kSpread - 1); }
+
+// EBOS_EKLT_LEGACY=1: the first (B200-validated) chain -- TV through ebos_flow_tv over the whole image, CTA/warp-per-cell
+// gather -- for A/B runs.
+static bool legacy_chain() {
+  const char* v = getenv("EBOS_EKLT_LEGACY");      // read per call: bench.py times both chains in one process
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
 
 struct Workspace {
   double* tv_acc;    // [EBOS_ACC_DOUBLES]
   double* acc;       // [kAccN]
   double* colsum;    // [W]
+  double* colS;      // [W]  sum_i sign(D) * q over the ROI rows of each column
+  char* T1;          // [4,H,pw+2pad] T: column pass of the transposed up-sampling
   char* pf;          // [2,ph,pw] T
   char* q;           // [H,W] T
   char* F;           // [2,H,W] T
@@ -57,6 +77,8 @@ static Workspace carve(void* base, int H, int W, int ph, int pw, int pad, size_t
   off += kAccN * sizeof(double);
   w.colsum = reinterpret_cast<double*>(p ? p + off : nullptr);
   off += (size_t)W * sizeof(double);
+  w.colS = reinterpret_cast<double*>(p ? p + off : nullptr);
+  off += (size_t)W * sizeof(double);
   off = align256(off);
   const size_t plane = (size_t)H * W * elem, cells = (size_t)ph * pw * elem;
   w.pf = take(2 * cells);
@@ -66,6 +88,7 @@ static Workspace carve(void* base, int H, int W, int ph, int pw, int pad, size_t
   w.dU = take(4 * plane);
   w.dPad = take((size_t)4 * (ph + 2 * pad) * (pw + 2 * pad) * elem);
   w.dP = take(4 * cells);
+  w.T1 = take((size_t)4 * H * (pw + 2 * pad) * elem);
   w.total = off;
   return w;
 }
@@ -103,47 +126,51 @@ __global__ void __launch_bounds__(256) k_forward(Geom g, int flags, const T* __r
   sq = block_sum(sq, red);
   sp = block_sum(sp, red);
   if (threadIdx.x == 0) {
-    atomicAdd(acc + kAccQ2, sq);
-    atomicAdd(acc + kAccPxy, sp);
+    atomicAdd(acc + kAccQ2 + acc_slot(), sq);
+    atomicAdd(acc + kAccPxy + acc_slot(), sp);
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_column_sums(Geom g, const T* __restrict__ q, const T* __restrict__ meas,
-                                                     const double* __restrict__ acc, double* __restrict__ colsum) {
+                                                     const double* __restrict__ acc, double* __restrict__ colsum,
+                                                     double* __restrict__ colS) {
   __shared__ double part[8][33];
+  __shared__ double partS[8][33];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
-  const T inv = (T)(1.0 / (sqrt(acc[kAccQ2]) + kNormEps));
-  double s = 0.0;
+  const T inv = (T)(1.0 / (sqrt(acc_sum(acc, kAccQ2)) + kNormEps));
+  double s = 0.0, sS = 0.0;
   if (j < g.W) {
     for (int i = blockIdx.y * 8 + row; i < g.H; i += gridDim.y * 8) {
       const int64_t k = (int64_t)i * g.W + j;
-      const T D = residual<T>(q[k], in_roi(g, i, j), meas[k], inv);
-      s += fabs((double)D);
+      const bool m = in_roi(g, i, j);
+      const T qk = q[k];
+      const double D = (double)residual<T>(qk, m, meas[k], inv);
+      s += fabs(D);
+      if (m) sS += sgn(D) * (double)qk;
     }
   }
   part[row][lane] = s;
+  partS[row][lane] = sS;
   __syncthreads();
   if (row == 0 && j < g.W) {
-    double t = 0.0;
+    double t = 0.0, tS = 0.0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += part[r][lane];
+    for (int r = 0; r < 8; ++r) { t += part[r][lane]; tS += partS[r][lane]; }
     atomicAdd(colsum + j, t);
+    atomicAdd(colS + j, tS);
   }
 }
 
-// One CTA: max column sum, number of ties, S = sum over the maximal columns of sign(D) * M * q * tie_w.
-template <typename T>
-__global__ void __launch_bounds__(256) k_column_max(Geom g, const T* __restrict__ q, const T* __restrict__ meas,
-                                                    const double* __restrict__ colsum, double* __restrict__ acc,
+// One CTA: max column sum (the data term), number of ties, S = tie_w * sum over the maximal ROI columns of colS.
+__global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const double* __restrict__ colsum,
+                                                    const double* __restrict__ colS, double* __restrict__ acc,
                                                     double w_data) {
   __shared__ double red[32];
   __shared__ double s_mx;
-  __shared__ double s_cnt;
   double mx = -1.0;
-  for (int j = threadIdx.x; j < g.W; j += blockDim.x) mx = fmax(mx, colsum[j]);
-  // block max via shuffles
+  for (int j = threadIdx.x; j < W; j += blockDim.x) mx = fmax(mx, colsum[j]);
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -154,49 +181,20 @@ __global__ void __launch_bounds__(256) k_column_max(Geom g, const T* __restrict_
   }
   __syncthreads();
   mx = s_mx;
-  // ties: count all of them; remember those inside the ROI columns (outside, M = 0 and they add nothing to S)
-  constexpr int kList = 32;
-  __shared__ int s_list[kList];
-  __shared__ int s_nlist;
-  if (threadIdx.x == 0) s_nlist = 0;
-  __syncthreads();
-  double cnt = 0.0;
-  for (int j = threadIdx.x; j < g.W; j += blockDim.x) {
+  double cnt = 0.0, S = 0.0;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
     if (colsum[j] == mx) {
       cnt += 1.0;
-      if (j >= g.y0 && j < g.y1) {
-        const int k = atomicAdd(&s_nlist, 1);
-        if (k < kList) s_list[k] = j;
-      }
+      if (j >= y0 && j < y1) S += colS[j];
     }
   }
   cnt = block_sum(cnt, red);
-  if (threadIdx.x == 0) s_cnt = cnt;
-  __syncthreads();
-  cnt = s_cnt;
-  const double n = sqrt(acc[kAccQ2]);
-  const T inv = (T)(1.0 / (n + kNormEps));
-  const double tie_w = w_data / cnt;
-  double S = 0.0;
-  const int n_list = s_nlist;
-  auto column = [&](int j) {
-    for (int i = g.x0 + threadIdx.x; i < g.x1; i += blockDim.x) {
-      const int64_t k = (int64_t)i * g.W + j;
-      const T D = residual<T>(q[k], true, meas[k], inv);
-      S += sgn((double)D) * tie_w * (double)q[k];
-    }
-  };
-  if (n_list <= kList) {
-    for (int t = 0; t < n_list; ++t) column(s_list[t]);
-  } else {                                       // degenerate (e.g. everything zero): walk all ROI columns
-    for (int j = g.y0; j < g.y1; ++j)
-      if (colsum[j] == mx) column(j);            // uniform over the CTA
-  }
   S = block_sum(S, red);
   if (threadIdx.x == 0) {
+    const double tie_w = w_data / cnt;
     acc[kAccMax] = mx;
     acc[kAccTieW] = tie_w;
-    acc[kAccS] = S;
+    acc[kAccS] = S * tie_w;
   }
 }
 
@@ -210,7 +208,7 @@ __global__ void __launch_bounds__(256) k_backward(Geom g, int flags, const T* __
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   if (j >= g.W) return;
   BackScalars s;
-  s.n = sqrt(acc[kAccQ2]);
+  s.n = sqrt(acc_sum(acc, kAccQ2));
   s.mx = acc[kAccMax];
   s.tie_w = acc[kAccTieW];
   s.S = acc[kAccS];
@@ -258,6 +256,74 @@ __global__ void __launch_bounds__(256) k_cell_gather(Geom g, int nch, const T* _
     const double t = block_sum(s[c], red);
     if (threadIdx.x == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)t;
   }
+}
+
+// TV(F; w_inv) value and w_tv * dTV/dF in gather form over the ROI box +-2 (F = f*M vanishes outside the ROI, and the
+// backward reads dF only inside it).  One thread per pixel of the box, both channels.
+template <typename T>
+__global__ void __launch_bounds__(256) k_tv_roi(Geom g, const T* __restrict__ F, const T* __restrict__ winv, double coef,
+                                                double* __restrict__ acc, T* __restrict__ dF) {
+  __shared__ double red[32];
+  int r0, r1, c0, c1;
+  tv_box(g.x0, g.x1, g.H, r0, r1);
+  tv_box(g.y0, g.y1, g.W, c0, c1);
+  const int j = c0 + blockIdx.x * 32 + (threadIdx.x & 31);
+  const int64_t plane = (int64_t)g.H * g.W;
+  double val = 0.0;
+  if (j < c1) {
+    for (int i = r0 + blockIdx.y * 8 + (threadIdx.x >> 5); i < r1; i += gridDim.y * 8) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        double v, a;
+        tv_pixel<T>(F + c * plane, winv, g.H, g.W, i, j, v, a);
+        val += v;
+        dF[c * plane + (int64_t)i * g.W + j] = (T)(coef * a);
+      }
+    }
+  }
+  val = block_sum(val, red);
+  if (threadIdx.x == 0) atomicAdd(acc + kAccTvSum + acc_slot(), val);
+}
+
+// Transposed up-sampling in two separable passes.  Pass 1 (along columns): one warp per (row i, padded column cell B),
+// lanes over the cell's 2*patch support columns (coalesced), four channels.  T1: [nch, H, PW].
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_cols(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ T1) {
+  const int PW = g.pw + 2 * g.pad;
+  const int B = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, i = blockIdx.y;
+  if (B >= PW) return;
+  int j0, j1;
+  cell_support(B, g.patch, g.w1, g.W, j0, j1);
+  const int64_t plane = (int64_t)g.H * g.W;
+  const T* row = dU + (int64_t)i * g.W;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int j = j0 + lane; j < j1; j += 32) {
+    const double w = (double)cell_weight<T>(B, j, g.w1, g.patch);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < nch) s[c] += w * (double)row[c * plane + j];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= nch) break;
+    const double t = warp_sum(s[c]);
+    if (lane == 0) T1[((int64_t)c * g.H + i) * PW + B] = (T)t;
+  }
+}
+// Pass 2 (along rows): one warp per (channel, padded cell), lanes over the cell's 2*patch support rows of T1.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_rows(Geom g, int nch, const T* __restrict__ T1, T* __restrict__ dPad) {
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= nch * PH * PW) return;
+  const int c = o / (PH * PW), A = (o / PW) % PH, B = o % PW;
+  int i0, i1;
+  cell_support(A, g.patch, g.h1, g.H, i0, i1);
+  double s = 0.0;
+  for (int i = i0 + lane; i < i1; i += 32)
+    s += (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)T1[((int64_t)c * g.H + i) * PW + B];
+  s = warp_sum(s);
+  if (lane == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)s;
 }
 
 // Same for small supports (patch <= 16: at most 1024 pixels per cell): one WARP per padded cell, eight cells per CTA,
@@ -327,10 +393,13 @@ __global__ void k_param_grad(Geom g, int flags, const T* __restrict__ dP, const 
     }
   }
   if (k == 0) {
-    double tv = tv_acc[3];
-    for (int i = 24; i < EBOS_ACC_DOUBLES; ++i) tv += tv_acc[i];     // spread slots of the TV kernel (ebos_costs.cu)
+    double tv = acc_sum(acc, kAccTvSum);                             // k_tv_roi
+    if (tv_acc) {                                                    // legacy chain: ebos_flow_tv's accumulators
+      tv = tv_acc[3];
+      for (int i = 24; i < EBOS_ACC_DOUBLES; ++i) tv += tv_acc[i];
+    }
     const double hw = (double)g.H * (double)g.W;
-    const double tv_mean = tv / (2.0 * hw), pxy_mean = (flags & kWarp) ? acc[kAccPxy] / hw : 0.0;
+    const double tv_mean = tv / (2.0 * hw), pxy_mean = (flags & kWarp) ? acc_sum(acc, kAccPxy) / hw : 0.0;
     const double total = w_data * acc[kAccMax] + w_tv * tv_mean + w_pxy * pxy_mean;
     acc[kAccData] = acc[kAccMax];          // un-weighted terms, for diagnostics
     acc[kAccTv] = tv_mean;
@@ -388,7 +457,7 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
                             const T* winv, const T* weights, double w_data, double w_tv, double w_pxy, void* workspace,
                             T* loss, T* grad, cudaStream_t st) {
   const Workspace w = carve(workspace, g.H, g.W, g.ph, g.pw, g.pad, sizeof(T));
-  cudaError_t e = cudaMemsetAsync(w.acc, 0, (kAccN + (size_t)g.W) * sizeof(double), st);
+  cudaError_t e = cudaMemsetAsync(w.acc, 0, (kAccN + 2 * (size_t)g.W) * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset");
   const int np = g.ph * g.pw;
   const dim3 pg = plane_grid(g.H, g.W);
@@ -409,18 +478,38 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
   const T* tr = warp ? theta + (size_t)flow_channels(flags) * np : nullptr;
   k_forward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, q, F, w.acc);
   EBOS_LAUNCH_CHECK("ebos_eklt forward");
-  const int rc = ebos_flow_tv(F, winv, g.H, g.W, w_tv, sizeof(T) == 8 ? EBOS_F64 : EBOS_F32, w.tv_acc, dF, st);
-  if (rc != EBOS_OK) return rc;
-  k_column_sums<T><<<pg, 256, 0, st>>>(g, q, meas, w.acc, w.colsum);
-  k_column_max<T><<<1, 256, 0, st>>>(g, q, meas, w.colsum, w.acc, w_data);
+  const bool legacy = legacy_chain();
+  if (legacy || w_tv == 0.0) {
+    const int rc = ebos_flow_tv(F, winv, g.H, g.W, w_tv, sizeof(T) == 8 ? EBOS_F64 : EBOS_F32, w.tv_acc, dF, st);
+    if (rc != EBOS_OK) return rc;
+  } else {
+    int r0, r1, c0, c1;
+    tv_box(g.x0, g.x1, g.H, r0, r1);
+    tv_box(g.y0, g.y1, g.W, c0, c1);
+    if (r1 > r0 && c1 > c0) {
+      const dim3 tg = plane_grid(r1 - r0, c1 - c0);
+      k_tv_roi<T><<<tg, 256, 0, st>>>(g, F, winv, w_tv / (2.0 * (double)g.H * (double)g.W), w.acc, dF);
+    }
+  }
+  const bool tv_from_flow_tv = legacy || w_tv == 0.0;
+  k_column_sums<T><<<pg, 256, 0, st>>>(g, q, meas, w.acc, w.colsum, w.colS);
+  k_column_max<<<1, 256, 0, st>>>(g.W, g.y0, g.y1, w.colsum, w.colS, w.acc, w_data);
   k_backward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
                                     w_pxy / ((double)g.H * g.W), dU);
   EBOS_LAUNCH_CHECK("ebos_eklt backward");
-  const int n_cells = (g.pw + 2 * g.pad) * (g.ph + 2 * g.pad);
-  if (g.patch <= 16) k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
-  else k_cell_gather<T><<<dim3(g.pw + 2 * g.pad, g.ph + 2 * g.pad), 256, 0, st>>>(g, nch, dU, dPad);
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  const int n_cells = PW * PH;
+  if (legacy) {
+    if (g.patch <= 16) k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
+    else k_cell_gather<T><<<dim3(PW, PH), 256, 0, st>>>(g, nch, dU, dPad);
+  } else {
+    T* T1 = reinterpret_cast<T*>(w.T1);
+    k_gather_cols<T><<<dim3((PW + 7) / 8, g.H), 256, 0, st>>>(g, nch, dU, T1);
+    k_gather_rows<T><<<(nch * n_cells + 7) / 8, 256, 0, st>>>(g, nch, T1, dPad);
+  }
   k_fold<T><<<(nch * np + 127) / 128, 128, 0, st>>>(g, nch, dPad, dP);
-  k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, flags, dP, w.tv_acc, w.acc, w_data, w_tv, w_pxy, grad, loss);
+  k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, flags, dP, tv_from_flow_tv ? w.tv_acc : nullptr, w.acc, w_data,
+                                                    w_tv, w_pxy, grad, loss);
   EBOS_LAUNCH_CHECK("ebos_eklt gradient");
   return EBOS_OK;
 }

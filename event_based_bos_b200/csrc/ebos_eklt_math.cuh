@@ -287,6 +287,54 @@ EK_HD T sobel_over_8_adjoint_at(const T* d0, const T* d1, int ph, int pw, int r,
 }
 
 
+// ---- TV of the masked flow (ImageGradient.calculate_torch, src/costs/image_gradient.py:60-75), gather form --------
+// torch.gradient along one axis of n samples: one-sided at both ends, (f[m+1] - f[m-1]) / 2 inside.
+template <typename T>
+EK_HD T tv_g(const T* line, int64_t stride, int m, int n) {
+  if (m == 0) return line[stride] - line[0];
+  if (m == n - 1) return line[(int64_t)(n - 1) * stride] - line[(int64_t)(n - 2) * stride];
+  return (line[(int64_t)(m + 1) * stride] - line[(int64_t)(m - 1) * stride]) / (T)2;
+}
+// |g(m) w(m)| and s(m) = sign(g(m) w(m)) w(m)
+template <typename T>
+EK_HD double tv_abs(const T* line, const T* wline, int64_t stride, int m, int n) {
+  const double gw = (double)(tv_g(line, stride, m, n) * wline[(int64_t)m * stride]);
+  return gw < 0 ? -gw : gw;
+}
+template <typename T>
+EK_HD double tv_s(const T* line, const T* wline, int64_t stride, int m, int n) {
+  const T w = wline[(int64_t)m * stride];
+  return sgn((double)(tv_g(line, stride, m, n) * w)) * (double)w;
+}
+// d/d f[k] of sum_m |g(m) w(m)| : the adjoint of torch.gradient applied to s
+template <typename T>
+EK_HD double tv_adjoint(const T* line, const T* wline, int64_t stride, int k, int n) {
+  double a = 0.0;
+  if (k - 1 >= 1 && k - 1 <= n - 2) a += 0.5 * tv_s(line, wline, stride, k - 1, n);
+  if (k + 1 >= 1 && k + 1 <= n - 2) a -= 0.5 * tv_s(line, wline, stride, k + 1, n);
+  if (k == 1) a += tv_s(line, wline, stride, 0, n);
+  if (k == 0) a -= tv_s(line, wline, stride, 0, n);
+  if (k == n - 1) a += tv_s(line, wline, stride, n - 1, n);
+  if (k == n - 2) a -= tv_s(line, wline, stride, n - 1, n);
+  return a;
+}
+// Rows/columns outside [lo, hi) cannot see the ROI through the 5-point support of the adjoint: F = f*M vanishes there
+// together with every difference that touches it.
+EK_HD void tv_box(int a0, int a1, int n, int& lo, int& hi) {
+  lo = a0 - 2 < 0 ? 0 : a0 - 2;
+  hi = a1 + 2 > n ? n : a1 + 2;
+}
+// value and gradient contributions of pixel (i,j), channel plane F (one of the two), weights winv
+template <typename T>
+EK_HD void tv_pixel(const T* F, const T* winv, int H, int W, int i, int j, double& value, double& adjoint) {
+  const T* row = F + (int64_t)i * W;      // along columns: stride 1
+  const T* wrow = winv + (int64_t)i * W;
+  const T* col = F + j;                   // along rows: stride W
+  const T* wcol = winv + j;
+  value = tv_abs(col, wcol, (int64_t)W, i, H) + tv_abs(row, wrow, (int64_t)1, j, W);
+  adjoint = tv_adjoint(col, wcol, (int64_t)W, i, H) + tv_adjoint(row, wrow, (int64_t)1, j, W);
+}
+
 // ---- separable correlation with mirrored borders (per-window preprocessing) --------------------------------------
 // border 0: reflect-101  (cv2.BORDER_REFLECT_101, the default of cv2.Sobel / cv2.GaussianBlur:  c b | a b c | b a)
 // border 1: reflect      (scipy.ndimage mode='reflect':                                         b a | a b c | c b)

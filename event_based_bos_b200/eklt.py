@@ -222,9 +222,10 @@ class EkltLevel:
         """Un-weighted terms of the LAST evaluation (device -> host read; diagnostics)."""
         # acc sits behind the 256-byte aligned TV accumulators (csrc/ebos_eklt.cu: carve)
         off = ((_capi.ACC_DOUBLES * 8 + 255) // 256) * 256
-        acc = self.workspace[off:off + 16 * 8].view(torch.float64).cpu()
-        return {"norm": math.sqrt(float(acc[0])), "data": float(acc[6]), "tv": float(acc[7]), "pxy": float(acc[8]),
-                "loss": float(acc[5])}
+        acc = self.workspace[off:off + 64 * 8].view(torch.float64).cpu()
+        # csrc/ebos_eklt.cu: [3] loss [4] data [5] tv [6] pxy; [16:32] spread slots of sum q^2
+        return {"norm": math.sqrt(float(acc[16:32].sum())), "data": float(acc[4]), "tv": float(acc[5]),
+                "pxy": float(acc[6]), "loss": float(acc[3])}
 
     def adam_iteration(self, theta: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
                        step_dev: torch.Tensor, lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999),

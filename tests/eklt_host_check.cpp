@@ -189,4 +189,30 @@ int eklt_host_sepconv(const void* image, int H, int W, const double* taps_rows, 
   return 0;
 }
 
+// k_tv_roi walked serially over the ROI box: value (un-normalised sum of |g w|) and dF = coef * adjoint inside the box
+// (dF outside the box is left untouched, as on the GPU).
+int eklt_host_tv(const int* dims, int is_f64, const void* F, const void* winv, double coef, void* dF, double* value) {
+  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
+  int r0, r1, c0, c1;
+  tv_box(g.x0, g.x1, g.H, r0, r1);
+  tv_box(g.y0, g.y1, g.W, c0, c1);
+  const int64_t plane = (int64_t)g.H * g.W;
+  double total = 0.0;
+  for (int c = 0; c < 2; ++c)
+    for (int i = r0; i < r1; ++i)
+      for (int j = c0; j < c1; ++j) {
+        double v, a;
+        if (is_f64) {
+          tv_pixel<double>((const double*)F + c * plane, (const double*)winv, g.H, g.W, i, j, v, a);
+          ((double*)dF)[c * plane + (int64_t)i * g.W + j] = coef * a;
+        } else {
+          tv_pixel<float>((const float*)F + c * plane, (const float*)winv, g.H, g.W, i, j, v, a);
+          ((float*)dF)[c * plane + (int64_t)i * g.W + j] = (float)(coef * a);
+        }
+        total += v;
+      }
+  *value = total;
+  return 0;
+}
+
 }  // extern "C"

@@ -140,10 +140,14 @@ def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dty
     lib.eklt_host_columns.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
     lib.eklt_host_columns(dims, f64, _p(q), _p(meas), float(sums[0]), wd, _p(colsum), _p(scal))
-    # the TV kernel (ebos_flow_tv) sits between the two passes on the GPU; here: the oracle's TV on the checker's F
-    gxx, gyy = E._tv_parts(F.astype(np.float64), winv.astype(np.float64))
-    tv = np.mean(np.abs(gxx) + np.abs(gyy))
-    dF = c(wtv * E._tv_adjoint(np.sign(gxx) * winv / F.size, np.sign(gyy) * winv / F.size))
+    # TV of the masked flow: the gather-form functions of k_tv_roi over the ROI box (dF outside the box stays NaN:
+    # the backward must not read it)
+    dF = np.full((2, H, W), np.nan, dtype)
+    tv_sum = ctypes.c_double(0.0)
+    lib.eklt_host_tv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                 ctypes.c_void_p, ctypes.c_void_p]
+    lib.eklt_host_tv(dims, f64, _p(F), _p(winv), wtv / (2.0 * H * W), _p(dF), ctypes.byref(tv_sum))
+    tv = tv_sum.value / (2.0 * H * W)
     dU = np.zeros((4, H, W), dtype)
     dPad = np.zeros((4, ph + 2, pw + 2), dtype)
     dP = np.zeros((4, ph, pw), dtype)
@@ -153,7 +157,8 @@ def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dty
     lib.eklt_host_backward(dims, f64, flags, _p(theta), _p(pf), _p(gx), _p(gy), hw_p, _p(meas), _p(dF), _p(colsum),
                            _p(scal), wp, _p(dU), _p(dPad), _p(dP), _p(grad))
     loss = wd * scal[1] + wtv * tv + (wp * sums[1] / (H * W) if warp else 0.0)
-    return {"loss": loss, "grad": grad, "q": q, "F": F, "trans": tr, "pf": pf, "colsum": colsum, "n": scal[0], "dU": dU}
+    return {"loss": loss, "grad": grad, "q": q, "F": F, "trans": tr, "pf": pf, "colsum": colsum, "n": scal[0], "dU": dU,
+            "dF": dF, "tv": tv}
 
 
 @pytest.mark.parametrize("name", ["start", "random", "far"])
@@ -344,3 +349,26 @@ def test_preprocessing_oracle_variants_match_reference(gold):
     m, wi, _ = E.measurement_and_weights(gold["events"], (H, W), gold["roi_t"], no_polarity=True)
     assert np.abs(m - v["no_polarity_measured"]).max() <= 1e-15
     assert np.abs(wi - v["no_polarity_weight_inverse"]).max() <= 1e-13
+
+
+def test_tv_gather_form_matches_oracle_adjoint(gold, host_lib):
+    """k_tv_roi's arithmetic: value and gradient of the TV term restricted to the ROI box equal the oracle's full-image
+    torch.gradient adjoint wherever the backward reads it (inside the ROI), for ROIs on and off the image border."""
+    rng = np.random.default_rng(9)
+    for (H, W, roi) in [(20, 31, (0, 20, 0, 31)), (20, 31, (1, 19, 2, 30)), (9, 12, (3, 4, 5, 6)), (2, 2, (0, 2, 0, 2)),
+                        (16, 16, (0, 1, 15, 16))]:
+        M = E.roi_mask((H, W), roi)
+        F = rng.normal(size=(2, H, W)) * M[None]
+        F[:, roi[0]:roi[0] + 1] = np.round(F[:, roi[0]:roi[0] + 1])          # exact ties -> sign(0) paths
+        winv = rng.uniform(0.05, 1.0, (H, W))
+        dims = (ctypes.c_int * 9)(H, W, 1, 1, max(H, W), *roi)
+        dF = np.full((2, H, W), np.nan)
+        val = ctypes.c_double(0.0)
+        host_lib.eklt_host_tv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+        host_lib.eklt_host_tv(dims, 1, _p(F), _p(winv), 1.0 / F.size, _p(dF), ctypes.byref(val))
+        gx, gy = E._tv_parts(F, winv)
+        ref = E._tv_adjoint(np.sign(gx) * winv / F.size, np.sign(gy) * winv / F.size)
+        inside = M[None].astype(bool).repeat(2, 0)
+        assert np.abs(dF[inside] - ref[inside]).max() <= 1e-15, (H, W, roi)
+        assert abs(val.value - (np.abs(gx) + np.abs(gy)).sum()) <= 1e-12, (H, W, roi)
