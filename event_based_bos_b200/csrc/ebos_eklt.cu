@@ -414,9 +414,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_upsample(Geom g, const T* __restrict__ P, int channels, T* __restrict__ out) {
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   if (j >= g.W) return;
-  const AxisTap<T> c = axis_tap<T>(j, g.w1, g.patch, g.pw, g.pad);
+  const AxisTap<T> c = axis_tap<T>(j, g.w1, g.patch, g.pw, g.pad, g.inv_patch);
   for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
-    const AxisTap<T> r = axis_tap<T>(i, g.h1, g.patch, g.ph, g.pad);
+    const AxisTap<T> r = axis_tap<T>(i, g.h1, g.patch, g.ph, g.pad, g.inv_patch);
     for (int ch = 0; ch < channels; ++ch)
       out[((int64_t)ch * g.H + i) * g.W + j] = upsample_at(P + (int64_t)ch * g.ph * g.pw, g.pw, r, c);
   }
@@ -499,9 +499,13 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
   EBOS_LAUNCH_CHECK("ebos_eklt backward");
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int n_cells = PW * PH;
-  if (legacy) {
-    if (g.patch <= 16) k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
-    else k_cell_gather<T><<<dim3(PW, PH), 256, 0, st>>>(g, nch, dU, dPad);
+  // B200, 1280x720 fp64 (profiles/eklt/r01i launch list): two separable passes 20 / 25 / 36 / 71 us at patch 64 / 32 /
+  // 16 / 8 against 54 / 33 us (CTA per cell) and 36 / 36 us (warp per cell): a warp of pass 1 covers one 2*patch-pixel
+  // support, which leaves half of it idle at patch 8.
+  if (g.patch <= 16) {
+    k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
+  } else if (legacy) {
+    k_cell_gather<T><<<dim3(PW, PH), 256, 0, st>>>(g, nch, dU, dPad);
   } else {
     T* T1 = reinterpret_cast<T*>(w.T1);
     k_gather_cols<T><<<dim3((PW + 7) / 8, g.H), 256, 0, st>>>(g, nch, dU, T1);

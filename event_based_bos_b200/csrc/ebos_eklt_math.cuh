@@ -70,6 +70,7 @@ EK_HD float f32_sub(float a, float b) { return Ar<float>::sub(a, b); }
 // ((ph+2pad)*patch rows) is centre-cropped to [H,W] starting at (h1,w1); ROI rows [x0,x1) x cols [y0,y1).
 struct Geom {
   int H, W, ph, pw, patch, pad, h1, w1, x0, x1, y0, y1;
+  double inv_patch;   // 1/patch when patch is a power of two (x * inv_patch == x / patch bit for bit), else 0
 };
 EK_HD Geom make_geom(int H, int W, int ph, int pw, int patch, int x0, int x1, int y0, int y1) {
   Geom g;
@@ -78,6 +79,7 @@ EK_HD Geom make_geom(int H, int W, int ph, int pw, int patch, int x0, int x1, in
   g.h1 = ((ph + 2 * g.pad) * patch) / 2 - H / 2;
   g.w1 = ((pw + 2 * g.pad) * patch) / 2 - W / 2;
   g.x0 = x0; g.x1 = x1; g.y0 = y0; g.y1 = y1;
+  g.inv_patch = (patch > 0 && (patch & (patch - 1)) == 0) ? 1.0 / (double)patch : 0.0;
   return g;
 }
 EK_HD bool in_roi(const Geom& g, int i, int j) { return i >= g.x0 && i < g.x1 && j >= g.y0 && j < g.y1; }
@@ -87,9 +89,11 @@ EK_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v)
 // `a` is the cell of the PADDED axis; lo/hi index the unpadded one (replicate pad = clamp).
 template <typename T> struct AxisTap { int a, lo, hi; T fr; };
 template <typename T>
-EK_HD AxisTap<T> axis_tap(int i, int offset, int patch, int n_patch, int pad) {
+EK_HD AxisTap<T> axis_tap(int i, int offset, int patch, int n_patch, int pad, double inv_patch = 0.0) {
   AxisTap<T> t;
-  const T u = Ar<T>::sub(Ar<T>::div(Ar<T>::add((T)(i + offset), (T)0.5), (T)patch), (T)0.5);
+  const T num = Ar<T>::add((T)(i + offset), (T)0.5);
+  // a power-of-two patch (every level of the pyramid) divides exactly by multiplying with its reciprocal
+  const T u = Ar<T>::sub(inv_patch != 0.0 ? Ar<T>::mul(num, (T)inv_patch) : Ar<T>::div(num, (T)patch), (T)0.5);
   const T fl = floor(u);
   t.fr = Ar<T>::sub(u, fl);
   t.a = (int)fl;
@@ -131,7 +135,7 @@ EK_HD T sample_pos(int i, T t, int size) {
   const double half = (double)(size - 1) / 2.0;
   const float base = f32_sub(f32_div((float)i, (float)half), 1.0f);
   const T g = Ar<T>::sub((T)base, Ar<T>::div(t, (T)half));
-  return Ar<T>::mul(Ar<T>::div(Ar<T>::add(g, (T)1), (T)2), (T)(size - 1));
+  return Ar<T>::mul(Ar<T>::mul(Ar<T>::add(g, (T)1), (T)0.5), (T)(size - 1));   // x / 2 == x * 0.5 exactly
 }
 
 // Bilinear sample with zeros outside (grid_sample, align_corners=True once positions are in pixels) and the
@@ -173,8 +177,8 @@ template <typename T>
 EK_HD Pixel<T> eval_pixel(const Geom& g, int flags, const T* pf, const T* tr, const T* gx, const T* gy, const T* weights,
                           int i, int j) {
   Pixel<T> p;
-  const AxisTap<T> r = axis_tap<T>(i, g.h1, g.patch, g.ph, g.pad);
-  const AxisTap<T> c = axis_tap<T>(j, g.w1, g.patch, g.pw, g.pad);
+  const AxisTap<T> r = axis_tap<T>(i, g.h1, g.patch, g.ph, g.pad, g.inv_patch);
+  const AxisTap<T> c = axis_tap<T>(j, g.w1, g.patch, g.pw, g.pad, g.inv_patch);
   const int np = g.ph * g.pw;
   const int64_t k = (int64_t)i * g.W + j;
   p.f0 = upsample_at(pf, g.pw, r, c);
