@@ -129,27 +129,31 @@ EK_HD void sobel_over_8_at(const T* P, int ph, int pw, int a, int b, T& out0, T&
 
 // warp_image_forward sample position of pixel index `i` along an axis of `size` pixels displaced by `t`:
 //   base = float32(i) / float32((size-1)/2) - 1f      (the reference builds the base grid in FLOAT32)
-//   g    = base - t / ((size-1)/2) ;  pos = ((g + 1) / 2) * (size - 1)
+//   g    = base - t / ((size-1)/2) ;  pos = ((g + 1) / 2) * (size - 1)          (float64 from here on upstream)
+// Always evaluated in double, also by the float32 instantiation: at zero translation the sample sits ~1e-5 px beside the
+// pixel centre and float32 position arithmetic would round it onto the other side, i.e. into another bilinear cell (a
+// different one-sided difference in the translation gradient: 3-35 % off in the serial check).
 template <typename T>
-EK_HD T sample_pos(int i, T t, int size) {
+EK_HD double sample_pos(int i, T t, int size) {
   const double half = (double)(size - 1) / 2.0;
   const float base = f32_sub(f32_div((float)i, (float)half), 1.0f);
-  const T g = Ar<T>::sub((T)base, Ar<T>::div(t, (T)half));
-  return Ar<T>::mul(Ar<T>::mul(Ar<T>::add(g, (T)1), (T)0.5), (T)(size - 1));   // x / 2 == x * 0.5 exactly
+  const double g = Ar<double>::sub((double)base, Ar<double>::div((double)t, half));
+  return Ar<double>::mul(Ar<double>::mul(Ar<double>::add(g, 1.0), 0.5), (double)(size - 1));   // x / 2 == x * 0.5
 }
 
 // Bilinear sample with zeros outside (grid_sample, align_corners=True once positions are in pixels) and the
-// derivatives of the sample w.r.t. the sample row / column.
+// derivatives of the sample w.r.t. the sample row / column.  Cell and fractions from the double position; the
+// interpolation itself in T.
 template <typename T> struct Sample { T v, d_r, d_c; };
 template <typename T>
-EK_HD Sample<T> bilinear_sample(const T* img, int H, int W, T pr, T pc) {
+EK_HD Sample<T> bilinear_sample(const T* img, int H, int W, double pr, double pc) {
   Sample<T> s;
   s.v = s.d_r = s.d_c = (T)0;
   // outside (-1, size) every tap is padding; this also keeps the float->int conversions in range (NaN fails both)
-  if (!(pr > (T)-1 && pr < (T)H && pc > (T)-1 && pc < (T)W)) return s;
-  const T fr = floor(pr), fc = floor(pc);
+  if (!(pr > -1.0 && pr < (double)H && pc > -1.0 && pc < (double)W)) return s;
+  const double fr = floor(pr), fc = floor(pc);
   const int r0 = (int)fr, c0 = (int)fc;
-  const T a = pr - fr, b = pc - fc;
+  const T a = (T)(pr - fr), b = (T)(pc - fc);
   const bool r0ok = r0 >= 0, r1ok = r0 + 1 < H, c0ok = c0 >= 0, c1ok = c0 + 1 < W;
   const T v00 = (r0ok && c0ok) ? img[(int64_t)r0 * W + c0] : (T)0;
   const T v01 = (r0ok && c1ok) ? img[(int64_t)r0 * W + c0 + 1] : (T)0;
@@ -186,7 +190,7 @@ EK_HD Pixel<T> eval_pixel(const Geom& g, int flags, const T* pf, const T* tr, co
   if (flags & kWarp) {
     p.t0 = upsample_at(tr, g.pw, r, c);
     p.t1 = upsample_at(tr + np, g.pw, r, c);
-    const T pr = sample_pos<T>(i, p.t0, g.H), pc = sample_pos<T>(j, p.t1, g.W);
+    const double pr = sample_pos<T>(i, p.t0, g.H), pc = sample_pos<T>(j, p.t1, g.W);
     p.sx = bilinear_sample(gx, g.H, g.W, pr, pc);
     p.sy = bilinear_sample(gy, g.H, g.W, pr, pc);
   } else {                                  // no grid_sample at all upstream: the gradients as they are

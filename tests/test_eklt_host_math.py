@@ -184,15 +184,17 @@ def test_kernel_arithmetic_fp64_matches_oracle_and_reference(gold, host_lib, nam
 
 
 def test_kernel_arithmetic_fp32_close_to_fp64(gold, host_lib):
-    """The fp32 instantiation (speed path) evaluated on fp32-rounded inputs stays within fp32 accuracy of the fp64
-    oracle at smooth points (random theta: samples are far from the cell boundaries)."""
-    patch, ph, pw = gold["levels_t"][1]
-    th = gold["L2_random_theta"]
-    h = host_value_and_grad(host_lib, th, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"],
-                            gold["roi_t"], patch, gold["cost_weights"], dtype=np.float32)
-    r = _objective(gold, th, patch)
-    assert abs(h["loss"] - r["loss"]) <= 2e-5 * abs(r["loss"])
-    assert np.abs(h["q"] - r["q"]).max() <= 2e-5 * np.abs(r["q"]).max()
+    """The fp32 instantiation (speed path) on fp32-rounded inputs stays within fp32 accuracy of the fp64 reference --
+    also at the zero-translation start, because the sample positions are evaluated in double in both instantiations
+    (with float32 positions the start gradient was 3-35 % off: another bilinear cell, another one-sided difference)."""
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        for name in ("random", "start"):
+            key = f"L{scale}_{name}"
+            h = host_value_and_grad(host_lib, gold[key + "_theta"], gold["grad_x"], gold["grad_y"], gold["measured"],
+                                    gold["weight_inverse"], gold["roi_t"], patch, gold["cost_weights"], dtype=np.float32)
+            ref = gold[key + "_grad"]
+            assert abs(h["loss"] - float(gold[key + "_loss"])) <= 2e-6 * abs(float(gold[key + "_loss"])), key
+            assert np.abs(h["grad"] - ref).max() <= 5e-6 * np.abs(ref).max(), key
 
 
 def test_kernel_arithmetic_general_roi_and_odd_sizes(host_lib):
