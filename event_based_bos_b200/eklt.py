@@ -107,6 +107,25 @@ def frame_gradients(frame: torch.Tensor, use_log_intensity: bool = False) -> Tup
     return sepconv2d(f, d, s), sepconv2d(f, s, d)
 
 
+def polarity_histogram(events: torch.Tensor, image_size: Tuple[int, int], no_polarity: bool = False) -> torch.Tensor:
+    """`create_iwe(events, method="polarity")[0] - [1]` on the device (their sum with `no_polarity`): the positive and the
+    negative events (p > 0 / not) are voted bilinearly with the numpy branch's arithmetic (float64, floor bias 1e-8;
+    src/event_image_converter.py:355-363, 503-560) by the `ebos_iwe_splat` kernel.  src/solver/patch_eklt.py:277-281."""
+    from . import ops
+    from .event_image_converter import NUMPY_FLOOR_BIAS
+
+    _check_cuda(events)
+    ev = events.to(torch.float64)
+    pos = ev[:, 3] > 0
+    H, W = int(image_size[0]), int(image_size[1])
+    planes = []
+    for sel in (pos, ~pos):
+        part = ev[sel].contiguous()
+        planes.append(ops.iwe_splat(part, (H, W), (0, 0), 1.0, False, NUMPY_FLOOR_BIAS) if part.shape[0] > 0
+                      else torch.zeros((H, W), dtype=torch.float64, device=ev.device))
+    return planes[0] + planes[1] if no_polarity else planes[0] - planes[1]
+
+
 def measurement_and_weights(histogram: torch.Tensor, roi: Tuple[int, int, int, int], iwe_sigma: float = 2.0,
                             weight_inverse: bool = True, inverse_sigma: float = 10.0, weight_sigma: float = 0.0
                             ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:

@@ -90,8 +90,9 @@ class PatchEkltPyramid2(SolverBase):
 
     def calculate_iwe_cache(self, events: np.ndarray) -> None:
         """Polarity histogram -> measured increment and weight_inverse (src/solver/patch_eklt.py:271-304)."""
-        pol = self.orig_imager.create_iwe(events, method="polarity", sigma=0)
-        hist = torch.as_tensor(pol[0] + pol[1] if self.no_polarity else pol[0] - pol[1], device="cuda").to(self._dtype)
+        _capi.require_device()
+        ev = torch.as_tensor(np.asarray(events), device="cuda")
+        hist = eklt.polarity_histogram(ev, tuple(self.orig_image_shape), self.no_polarity).to(self._dtype)
         roi = (self.crop_xmin, self.crop_xmax, self.crop_ymin, self.crop_ymax)
         self.cache_measured, self.weight_inverse, self.cache_weights = eklt.measurement_and_weights(
             hist, roi, iwe_sigma=self._gml_config["iwe_sigma"], weight_inverse=self.do_weight_inverse,
@@ -149,4 +150,6 @@ class PatchEkltPyramid2(SolverBase):
         patch_flow = eklt.patch_flow(theta[0]) if self.is_poisson_model else theta[:2].contiguous()
         dense = eklt.upsample(patch_flow, patch, tuple(self.orig_image_shape))
         self.iter_cnt += 1
-        return dense.double().cpu().numpy() * self.estimate_mask_dense_numpy
+        mask = torch.zeros(tuple(self.orig_image_shape), dtype=torch.float64, device=dense.device)
+        mask[self.crop_xmin:self.crop_xmax, self.crop_ymin:self.crop_ymax] = 1
+        return (dense.double() * mask).cpu().numpy()

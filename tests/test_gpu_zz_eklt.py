@@ -174,6 +174,9 @@ def test_preprocessing_matches_reference(gold, eklt):
     assert np.array_equal(gy.cpu().numpy(), gold["grad_y"])
     H, W = (int(v) for v in gold["image"])
     hist = E.polarity_histogram(gold["events"], (H, W))
+    assert np.array_equal(eklt.polarity_histogram(dev(gold["events"]), (H, W)).cpu().numpy(), hist)   # integer pixels: exact
+    assert np.array_equal(eklt.polarity_histogram(dev(gold["events"]), (H, W), no_polarity=True).cpu().numpy(),
+                          E.polarity_histogram(gold["events"], (H, W), no_polarity=True))
     meas, winv, none = eklt.measurement_and_weights(dev(hist), gold["roi_t"])
     assert none is None
     assert np.abs(meas.cpu().numpy() - gold["measured"]).max() <= 1e-14
