@@ -200,7 +200,9 @@ def test_kernel_arithmetic_fp32_close_to_fp64(gold, host_lib):
 def test_kernel_arithmetic_general_roi_and_odd_sizes(host_lib):
     """Sizes that are not multiples of anything, ROI touching the border, patch grid with a single row."""
     rng = np.random.default_rng(5)
-    for (H, W, patch, roi) in [(37, 53, 8, (0, 37, 0, 53)), (50, 70, 64, (3, 47, 10, 70)), (33, 130, 16, (5, 6, 7, 9))]:
+    # the last three: patch sizes that are not powers of two (true division in the tap arithmetic, odd supports)
+    for (H, W, patch, roi) in [(37, 53, 8, (0, 37, 0, 53)), (50, 70, 64, (3, 47, 10, 70)), (33, 130, 16, (5, 6, 7, 9)),
+                               (37, 53, 5, (2, 30, 0, 53)), (40, 60, 12, (0, 40, 7, 41)), (30, 31, 7, (1, 29, 1, 30))]:
         ph, pw = E.patch_grid((H, W), patch)
         th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-2, 2, (2, ph, pw))])
         gx, gy = rng.normal(size=(2, H, W)) * 50

@@ -117,7 +117,8 @@ def test_objective_fp32_close_to_reference(gold, eklt):
 def test_general_sizes_and_rois_match_oracle(eklt):
     rng = np.random.default_rng(5)
     cases = [(37, 53, 8, (0, 37, 0, 53)), (50, 70, 64, (3, 47, 10, 70)), (33, 130, 16, (5, 6, 7, 9)),
-             (144, 256, 32, (0, 144, 64, 192))]
+             (144, 256, 32, (0, 144, 64, 192)),
+             (37, 53, 5, (2, 30, 0, 53)), (40, 60, 12, (0, 40, 7, 41))]      # patch sizes that are not powers of two
     for (H, W, patch, roi) in cases:
         ph, pw = E.patch_grid((H, W), patch)
         th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-2, 2, (2, ph, pw))])
