@@ -170,14 +170,19 @@ __global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const
   __shared__ double red[32];
   __shared__ double s_mx;
   double mx = -1.0;
-  for (int j = threadIdx.x; j < W; j += blockDim.x) mx = fmax(mx, colsum[j]);
+  int nan = 0;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    const double c = colsum[j];
+    nan |= (c != c);
+    mx = fmax(mx, c);                            // fmax drops NaN: tracked separately
+  }
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-  __syncthreads();
+  const int any_nan = __syncthreads_or(nan);
   if (threadIdx.x == 0) {
     double m = red[0];
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
-    s_mx = m;
+    s_mx = any_nan ? __longlong_as_double(0x7ff8000000000000LL) : m;     // a NaN objective stays NaN, like torch's amax
   }
   __syncthreads();
   mx = s_mx;
