@@ -606,6 +606,19 @@ def run_eklt(args, rank, world, local):
             per_level_legacy[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
         finally:
             os.environ.pop("EBOS_EKLT_LEGACY", None)
+    iter_ms = {}
+    if args.eklt_ab_tail:      # opt-in A/B of the experimental single-kernel tail (EBOS_EKLT_TAIL=1): evaluation + Adam
+        for patch, ph, pw in slv.levels:
+            lvl = prob.level(patch)
+            th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous().clone()
+            m, v = torch.zeros_like(th), torch.zeros_like(th)
+            step = torch.zeros(1, dtype=torch.int32, device=th.device)
+            iter_ms[patch] = {"default": graph_time_ms(lambda: lvl.adam_iteration(th, m, v, step), 20)}
+            os.environ["EBOS_EKLT_TAIL"] = "1"
+            try:
+                iter_ms[patch]["tail_kernel"] = graph_time_ms(lambda: lvl.adam_iteration(th, m, v, step), 20)
+            finally:
+                os.environ.pop("EBOS_EKLT_TAIL", None)
     if rank != 0:
         return
     iters = [args.solve_iters // (len(slv.levels) + 1 - s + 1) for s in range(1, len(slv.levels) + 1)]
@@ -630,6 +643,7 @@ def run_eklt(args, rank, world, local):
                          "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_kind},
             "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy,
+            "iteration_ms_per_level": iter_ms or None,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
             "gpu_launches": args.steps * sum(iters) * 12}
@@ -711,6 +725,7 @@ def main():
     ap.add_argument("--solve-concurrency", type=int, default=8, help="independent windows in flight per GPU (solve workload)")
     ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
+    ap.add_argument("--eklt-ab-tail", action="store_true", help="also time evaluation + Adam with EBOS_EKLT_TAIL=1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")

@@ -295,6 +295,28 @@ EK_HD T sobel_over_8_adjoint_at(const T* d0, const T* d1, int ph, int pw, int r,
 }
 
 
+// ---- Adam (torch.optim.Adam defaults; the arithmetic of k_adam in ebos_costs.cu) -----------------------------------
+// step_size = lr / (1 - b1^step), inv_bc2_sqrt = 1 / sqrt(1 - b2^step)
+template <typename T>
+EK_HD void adam_one(T& p, T g, T& m, T& v, T b1, T b2, T eps, T step_size, T inv_bc2_sqrt) {
+  m = m * b1 + ((T)1 - b1) * g;
+  v = v * b2 + ((T)1 - b2) * g * g;
+  const T denom = (T)sqrt((double)v) * inv_bc2_sqrt + eps;
+  p -= step_size * (m / denom);
+}
+// sum of the padded cells that clamp to unpadded cell (a,b) of channel c
+template <typename T>
+EK_HD T fold_at(const Geom& g, const T* dPad, int c, int a, int b) {
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  int a0, a1, b0, b1;
+  fold_range(a, g.ph, g.pad, a0, a1);
+  fold_range(b, g.pw, g.pad, b0, b1);
+  double s = 0.0;
+  for (int A = a0; A < a1; ++A)
+    for (int B = b0; B < b1; ++B) s += (double)dPad[((int64_t)c * PH + A) * PW + B];
+  return (T)s;
+}
+
 // ---- TV of the masked flow (ImageGradient.calculate_torch, src/costs/image_gradient.py:60-75), gather form --------
 // torch.gradient along one axis of n samples: one-sided at both ends, (f[m+1] - f[m-1]) / 2 inside.
 template <typename T>

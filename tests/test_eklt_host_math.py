@@ -376,3 +376,42 @@ def test_tv_gather_form_matches_oracle_adjoint(gold, host_lib):
         inside = M[None].astype(bool).repeat(2, 0)
         assert np.abs(dF[inside] - ref[inside]).max() <= 1e-15, (H, W, roi)
         assert abs(val.value - (np.abs(gx) + np.abs(gy)).sum()) <= 1e-12, (H, W, roi)
+
+
+def test_tail_arithmetic_matches_torch_adam(gold, host_lib):
+    """The experimental single-kernel tail (EBOS_EKLT_TAIL=1): fold + parameter gradient + Adam, serial build, against
+    the oracle's adjoints and torch.optim.Adam over several steps, for both parameterisations."""
+    import torch
+
+    rng = np.random.default_rng(4)
+    H, W, patch = 50, 70, 16
+    ph, pw = E.patch_grid((H, W), patch)
+    dims = (ctypes.c_int * 9)(H, W, ph, pw, patch, 0, H, 0, W)
+    host_lib.eklt_host_tail.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_double] * 4 + \
+                                       [ctypes.c_int]
+    for flags, nt in ((3, 3), (2, 4), (1, 1), (0, 2)):
+        nch = 4 if flags & 2 else 2
+        theta = rng.normal(size=(nt, ph, pw))
+        ref = torch.from_numpy(theta.copy()).requires_grad_()
+        opt = torch.optim.Adam([ref], lr=0.05)
+        m, v = np.zeros_like(theta), np.zeros_like(theta)
+        for step in range(1, 5):
+            dPad = np.zeros((4, ph + 2, pw + 2))
+            dPad[:nch] = rng.normal(size=(nch, ph + 2, pw + 2))
+            # oracle: fold = adjoint of the replicate padding; Sobel adjoint for the intensity channel
+            folded = np.zeros((nch, ph, pw))
+            rr = np.clip(np.arange(ph + 2) - 1, 0, ph - 1)
+            cc = np.clip(np.arange(pw + 2) - 1, 0, pw - 1)
+            np.add.at(folded, (slice(None), rr[:, None], cc[None, :]), dPad[:nch])
+            parts = [E.sobel_over_8_adjoint(folded[:2])[None] if flags & 1 else folded[:2]]
+            if flags & 2:
+                parts.append(folded[2:4])
+            g_ref = np.concatenate(parts)
+            dP, grad = np.zeros((4, ph, pw)), np.zeros((nt, ph, pw))
+            host_lib.eklt_host_tail(dims, flags, _p(dPad), _p(dP), _p(grad), _p(theta), _p(m), _p(v), 0.05, 0.9, 0.999,
+                                    1e-8, step)
+            assert np.abs(grad - g_ref).max() <= 1e-13
+            opt.zero_grad()
+            ref.grad = torch.from_numpy(g_ref.copy())
+            opt.step()
+            assert np.abs(theta - ref.detach().numpy()).max() <= 1e-14, (flags, step)

@@ -5,6 +5,8 @@ Bars: float64 objective / gradient within 1e-9 relative of the reference's autog
 float32 instantiation within 1e-4 of it; after a complete coarse-to-fine solve the flow within 1e-3 px RMS
 (BASELINE.json north_star).  The file name sorts last on purpose: these kernels are the newest part of the library.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -237,6 +239,22 @@ def test_level_solve_graph_and_eager_match_oracle(gold, eklt):
     assert np.abs(eager - ref).max() <= 1e-8
     assert np.abs(graph - ref).max() <= 1e-8
     assert np.abs(np.array(hist) - np.array(losses)).max() <= 1e-10
+
+
+@pytest.mark.skipif(not os.environ.get("EBOS_TEST_EXPERIMENTAL"), reason="opt-in: EBOS_EKLT_TAIL path, not yet run on hardware")
+def test_experimental_tail_kernel_matches_default_chain(gold, eklt):
+    """EBOS_EKLT_TAIL=1 (fold + parameter gradient + Adam + step counter in one single-CTA kernel) against the default
+    four-launch tail: same iterates."""
+    prob = problem_from_gold(eklt, gold)
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        x0 = gold[f"L{scale}_random_theta"]
+        ref = prob.level(patch).solve(dev(x0), 6, cuda_graph=False).cpu().numpy()
+        os.environ["EBOS_EKLT_TAIL"] = "1"
+        try:
+            got = prob.level(patch).solve(dev(x0), 6, cuda_graph=False).cpu().numpy()
+        finally:
+            os.environ.pop("EBOS_EKLT_TAIL", None)
+        assert np.abs(got - ref).max() <= 1e-10, scale
 
 
 def test_solver_drop_in_matches_reference_estimate(gold):
