@@ -415,3 +415,40 @@ def test_tail_arithmetic_matches_torch_adam(gold, host_lib):
             ref.grad = torch.from_numpy(g_ref.copy())
             opt.step()
             assert np.abs(theta - ref.detach().numpy()).max() <= 1e-14, (flags, step)
+
+
+def test_torch_op_restatement_matches_reference_and_analytic_oracle(gold):
+    """oracle/spec_eklt_torch.py (the reference's torch ops + autograd; what the CPU arm of bench.py times) against the
+    reference goldens, all levels, regimes and switch variants; and against the analytic numpy oracle on fresh inputs."""
+    import torch
+
+    from oracle import spec_eklt_torch as TT
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).double()
+    wd, wtv, wp = (float(x) for x in gold["cost_weights"])
+    planes = [t(gold[k]) for k in ("grad_x", "grad_y", "measured", "weight_inverse")]
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        for name in ("start", "random", "far"):
+            key = f"L{scale}_{name}"
+            loss, grad = TT.value_and_grad(t(gold[key + "_theta"]), *planes, gold["roi_t"], patch, wd, wtv, wp)
+            assert abs(loss - float(gold[key + "_loss"])) <= 1e-13, key
+            assert np.abs(grad.numpy() - gold[key + "_grad"]).max() <= 1e-12 * np.abs(gold[key + "_grad"]).max(), key
+    for c in _variant_cases(gold):
+        loss, grad = TT.value_and_grad(t(c["theta"]), planes[0], planes[1], t(c["measured"]), t(c["winv"]), gold["roi_t"],
+                                       c["patch"], *c["cost_weights"], poisson=c["poisson"], warp=c["warp"],
+                                       no_polarity=c["no_polarity"],
+                                       weights=None if c["weights"] is None else t(c["weights"]))
+        assert abs(loss - c["loss"]) <= 1e-13, c["name"]
+        assert np.abs(grad.numpy() - c["grad"]).max() <= 1e-12 * np.abs(c["grad"]).max(), c["name"]
+    rng = np.random.default_rng(21)
+    H, W, patch, roi = 45, 77, 16, (4, 40, 9, 70)
+    ph, pw = E.patch_grid((H, W), patch)
+    th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-2, 2, (2, ph, pw))])
+    gx, gy = rng.normal(size=(2, H, W)) * 40
+    meas = rng.normal(size=(H, W)) * E.roi_mask((H, W), roi)
+    meas /= np.linalg.norm(meas)
+    winv = rng.uniform(0.05, 1, (H, W))
+    r = E.objective(th, gx, gy, meas, winv, roi, patch)
+    loss, grad = TT.value_and_grad(t(th), t(gx), t(gy), t(meas), t(winv), roi, patch)
+    assert abs(loss - r["loss"]) <= 1e-13
+    assert np.abs(grad.numpy() - r["grad"]).max() <= 1e-12 * np.abs(r["grad"]).max()
