@@ -13,4 +13,10 @@ therefore pinned against OUTPUTS OF THE REFERENCE ITSELF, generated in the build
 compare the oracle with the live reference on seeded inputs.  The IWE-variance and
 gradient-magnitude objectives do not exist upstream; their
 parity is pinned only against the torch-autograd expression built from reference parts.
+
+Modules: ``spec.py`` (contrast-maximisation path), ``spec_eklt.py`` (EKLT inner loop
+of PatchEkltPyramid2, row f-1: numpy float64 with analytic backward and the per-window preprocessing),
+``spec_eklt_torch.py`` (the same objective with the reference's torch ops + autograd: CPU arm of the bench, independent
+cross-check), ``ref_import.py`` / ``make_golden*.py`` (container-only: import the unmodified reference and write the
+fixtures ``tests/golden/reference_{path,ingest,eklt,eklt_variants}_v1.npz``).
 """
