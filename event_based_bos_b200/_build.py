@@ -33,6 +33,8 @@ NVCC_FLAGS = [
 PER_FILE_FLAGS = {}
 if os.environ.get("EBOS_BUILD_GM_GROUPS"):      # experiment: row groups per CTA of the gradient-magnitude kernel
     NVCC_FLAGS.append("-DEBOS_GM_GROUPS=" + os.environ["EBOS_BUILD_GM_GROUPS"])
+if os.environ.get("EBOS_BUILD_EKLT_MINB"):    # experiment: occupancy cap of the EKLT per-pixel kernels (csrc/ebos_eklt.cu)
+    NVCC_FLAGS.append("-DEBOS_EKLT_MINB=" + os.environ["EBOS_BUILD_EKLT_MINB"])
 if os.environ.get("EBOS_BUILD_ABLATION"):   # diagnostics build: EBOS_ABLATE=<mask> then removes kernel components
     NVCC_FLAGS.append("-DEBOS_ABLATION")
 

@@ -29,6 +29,13 @@
 #include "ebos_common.cuh"
 #include "ebos_eklt_math.cuh"
 
+// Build-time knob (python -m event_based_bos_b200._build with EBOS_BUILD_EKLT_MINB=n): minimum resident CTAs per SM of the
+// three per-pixel plane kernels.  They are latency-bound at 33-46 % of the warp slots (62-80 registers; ncu r01i);
+// 4 caps them at 64 registers.  Default 1 = no cap (the measured configuration).
+#ifndef EBOS_EKLT_MINB
+#define EBOS_EKLT_MINB 1
+#endif
+
 namespace ebos {
 namespace eklt {
 
@@ -105,7 +112,7 @@ __global__ void k_patch_flow(const T* __restrict__ theta, int ph, int pw, T* __r
 
 // 2-D tiles of 32 x 8 pixels; gridDim.y strides the rows.
 template <typename T>
-__global__ void __launch_bounds__(256) k_forward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
+__global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_forward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
                                                  const T* __restrict__ gx, const T* __restrict__ gy,
                                                  const T* __restrict__ weights, T* __restrict__ q, T* __restrict__ F,
                                                  double* __restrict__ acc) {
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_backward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
+__global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_backward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
                                                   const T* __restrict__ gx, const T* __restrict__ gy,
                                                   const T* __restrict__ weights, const T* __restrict__ meas,
                                                   const T* __restrict__ dF,
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(256) k_cell_gather(Geom g, int nch, const T* _
 // TV(F; w_inv) value and w_tv * dTV/dF in gather form over the ROI box +-2 (F = f*M vanishes outside the ROI, and the
 // backward reads dF only inside it).  One thread per pixel of the box, both channels.
 template <typename T>
-__global__ void __launch_bounds__(256) k_tv_roi(Geom g, const T* __restrict__ F, const T* __restrict__ winv, double coef,
+__global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_tv_roi(Geom g, const T* __restrict__ F, const T* __restrict__ winv, double coef,
                                                 double* __restrict__ acc, T* __restrict__ dF) {
   __shared__ double red[32];
   int r0, r1, c0, c1;
