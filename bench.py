@@ -581,7 +581,8 @@ def run_eklt(args, rank, world, local):
 
     cfg = json.loads(json.dumps(HOT_PLATE1_SOLVER))
     cfg["optimizer"]["n_iter"] = args.solve_iters
-    cfg["eklt"] = {"precision": args.eklt_precision, "cuda_graph": not args.eklt_no_graph}
+    cfg["eklt"] = {"precision": args.eklt_precision, "cuda_graph": not args.eklt_no_graph,
+                   "cache_graphs": args.eklt_cache_graphs}
     slv = solver.collections["patch_eklt_pyramid2"]((H, W), (720, 640), {}, cfg, None)
     ev, frame = eklt_inputs(args.solve_events, seed=rank)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -640,7 +641,8 @@ def run_eklt(args, rank, world, local):
             "config": {"workload": f"configs/hot_plate1.yaml pipeline: PatchEkltPyramid2.estimate, {args.solve_events} "
                                    f"synthetic events + synthetic frame, 1280x720, ROI [0:720,320:960], n_iter "
                                    f"{args.solve_iters} -> {sum(iters)} iterations over 4 levels; host events + frame in "
-                                   f"-> host flow out", "iterations_per_level": iters,
+                                   f"-> host flow out" + ("; graphs cached across windows" if args.eklt_cache_graphs else ""),
+                       "iterations_per_level": iters,
                        "l2_policy": "working set 25 planes x 7.4 MB (fp64) > L2"},
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": f"one objective evaluation at patch {worst} (all kernels of the chain)",
@@ -732,6 +734,8 @@ def main():
     ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
     ap.add_argument("--eklt-ab-tail", action="store_true", help="also time evaluation + Adam with EBOS_EKLT_TAIL=1")
+    ap.add_argument("--eklt-cache-graphs", action="store_true",
+                    help="experimental: keep buffers and CUDA graphs across windows (solver.eklt.cache_graphs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")

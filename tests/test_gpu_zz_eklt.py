@@ -257,6 +257,33 @@ def test_experimental_tail_kernel_matches_default_chain(gold, eklt):
         assert np.abs(got - ref).max() <= 1e-10, scale
 
 
+@pytest.mark.skipif(not os.environ.get("EBOS_TEST_EXPERIMENTAL"), reason="opt-in: solver.eklt.cache_graphs, not yet run on hardware")
+def test_experimental_cached_graphs_match_default_solver(gold):
+    """solver.eklt.cache_graphs (buffers, levels and CUDA graphs kept across windows) over two different windows in a
+    row against the default per-window capture."""
+    import copy
+
+    from event_based_bos_b200 import solver
+
+    H, W = (int(v) for v in gold["image"])
+    roi = gold["roi_t"]
+    cls = solver.collections["patch_eklt_pyramid2"]
+    cfg = copy.deepcopy(HOT_PLATE1_SOLVER)
+    cfg["eklt"] = {"cache_graphs": True}
+    cached = cls((H, W), (roi[1] - roi[0], roi[3] - roi[2]), {}, cfg, None)
+    plain = cls((H, W), (roi[1] - roi[0], roi[3] - roi[2]), {}, copy.deepcopy(HOT_PLATE1_SOLVER), None)
+    rng = np.random.default_rng(2)
+    windows = [(gold["events"], gold["frame"]),
+               (gold["events"][::2].copy(), np.clip(gold["frame"].astype(np.int32) + rng.integers(-9, 9, (H, W)), 0, 255).astype(np.uint8)),
+               (gold["events"], gold["frame"])]
+    for k, (ev, frame) in enumerate(windows):
+        np.random.seed(7 + k)
+        a = cached.estimate(ev, frame=frame)
+        np.random.seed(7 + k)
+        b = plain.estimate(ev, frame=frame)
+        assert np.sqrt(np.mean((a - b) ** 2)) <= 1e-3, k
+
+
 def test_solver_drop_in_matches_reference_estimate(gold):
     """`solver.collections["patch_eklt_pyramid2"]` with the reference's config block, events and frame in,
     dense flow out; np.random seeded like the golden run (the intensity start is drawn from np.random upstream)."""
