@@ -64,6 +64,7 @@ struct Workspace {
   double* colsum;    // [W]
   double* colS;      // [W]  sum_i sign(D) * q over the ROI rows of each column
   char* T1;          // [4,H,pw+2pad] T: column pass of the transposed up-sampling
+  char* St;          // [6,H,W] T: stored forward planes (EBOS_EKLT_STORED=1)
   char* pf;          // [2,ph,pw] T
   char* q;           // [H,W] T
   char* F;           // [2,H,W] T
@@ -96,6 +97,7 @@ static Workspace carve(void* base, int H, int W, int ph, int pw, int pad, size_t
   w.dPad = take((size_t)4 * (ph + 2 * pad) * (pw + 2 * pad) * elem);
   w.dP = take(4 * cells);
   w.T1 = take((size_t)4 * H * (pw + 2 * pad) * elem);
+  w.St = take(6 * plane);
   w.total = off;
   return w;
 }
@@ -115,7 +117,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_forward(Geom g, int flags, const T* __restrict__ pf, const T* __restrict__ tr,
                                                  const T* __restrict__ gx, const T* __restrict__ gy,
                                                  const T* __restrict__ weights, T* __restrict__ q, T* __restrict__ F,
-                                                 double* __restrict__ acc) {
+                                                 double* __restrict__ acc, T* __restrict__ St) {
   __shared__ double red[32];
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   double sq = 0.0, sp = 0.0;
@@ -126,6 +128,12 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_forward(Geom g, int fla
       q[k] = p.q;
       F[k] = p.m ? p.f0 : (T)0;
       F[(int64_t)g.H * g.W + k] = p.m ? p.f1 : (T)0;
+      if (St) {                                   // uniform: stored-planes backward
+        T pk[6];
+        pack_pixel<T>(p, pk);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) St[c * ((int64_t)g.H * g.W) + k] = pk[c];
+      }
       sq += (double)p.q * (double)p.q;
       if (p.m) sp += sqrt((double)p.t0 * (double)p.t0 + (double)p.t1 * (double)p.t1);
     }
@@ -238,6 +246,46 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_backward(Geom g, int fl
       dU[3 * plane + k] = out[3];
     }
   }
+}
+
+// EXPERIMENTAL (EBOS_EKLT_STORED=1, off by default; not yet run on hardware): the backward from six planes stored by the
+// forward instead of re-evaluating up-sampling, sample positions and the eight gathered taps (530 instructions per pixel in
+// k_backward, ncu r01i; DRAM at 9 % -- instructions are the scarce resource here, bytes are not).
+template <typename T>
+__global__ void __launch_bounds__(256) k_backward_stored(Geom g, int flags, const T* __restrict__ St, const T* __restrict__ q,
+                                                         const T* __restrict__ weights, const T* __restrict__ meas,
+                                                         const T* __restrict__ dF, const double* __restrict__ colsum,
+                                                         const double* __restrict__ acc, double w_pxy_hw,
+                                                         T* __restrict__ dU) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (j >= g.W) return;
+  BackScalars s;
+  s.n = sqrt(acc_sum(acc, kAccQ2));
+  s.mx = acc[kAccMax];
+  s.tie_w = acc[kAccTieW];
+  s.S = acc[kAccS];
+  const bool col_is_max = colsum[j] == s.mx;
+  const int64_t plane = (int64_t)g.H * g.W;
+  for (int i = blockIdx.y * 8 + (threadIdx.x >> 5); i < g.H; i += gridDim.y * 8) {
+    const int64_t k = (int64_t)i * g.W + j;
+    T pk[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) pk[c] = St[c * plane + k];
+    const bool m = in_roi(g, i, j);
+    const Pixel<T> p = unpack_pixel<T>(pk, q[k], weights ? weights[k] : (T)1, m);
+    T out[4];
+    backward_pixel<T>(p, flags, meas[k], col_is_max, s, m ? dF[k] : (T)0, m ? dF[plane + k] : (T)0, w_pxy_hw, out);
+    dU[k] = out[0];
+    dU[plane + k] = out[1];
+    if (flags & kWarp) {
+      dU[2 * plane + k] = out[2];
+      dU[3 * plane + k] = out[3];
+    }
+  }
+}
+static bool stored_planes() {
+  const char* v = getenv("EBOS_EKLT_STORED");
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
 }
 
 // One CTA per padded cell (A,B): sums the four dense gradient planes over the cell's 2*patch x 2*patch support with
@@ -560,7 +608,10 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
     pf = reinterpret_cast<const T*>(w.pf);
   }
   const T* tr = warp ? theta + (size_t)flow_channels(flags) * np : nullptr;
-  k_forward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, q, F, w.acc);
+  // stored-planes backward: not with no_polarity (the sign of q0 is not kept) and not without the warp (nothing to store)
+  const bool stored = stored_planes() && warp && !(flags & kNoPolarity);
+  T* St = stored ? reinterpret_cast<T*>(w.St) : nullptr;
+  k_forward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, q, F, w.acc, St);
   EBOS_LAUNCH_CHECK("ebos_eklt forward");
   const bool legacy = legacy_chain();
   if (legacy || w_tv == 0.0) {
@@ -578,8 +629,12 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
   const bool tv_from_flow_tv = legacy || w_tv == 0.0;
   k_column_sums<T><<<pg, 256, 0, st>>>(g, q, meas, w.acc, w.colsum, w.colS);
   k_column_max<<<1, 256, 0, st>>>(g.W, g.y0, g.y1, w.colsum, w.colS, w.acc, w_data);
-  k_backward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
-                                    w_pxy / ((double)g.H * g.W), dU);
+  if (stored)
+    k_backward_stored<T><<<pg, 256, 0, st>>>(g, flags, St, q, weights, meas, dF, w.colsum, w.acc,
+                                             w_pxy / ((double)g.H * g.W), dU);
+  else
+    k_backward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
+                                      w_pxy / ((double)g.H * g.W), dU);
   EBOS_LAUNCH_CHECK("ebos_eklt backward");
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int n_cells = PW * PH;

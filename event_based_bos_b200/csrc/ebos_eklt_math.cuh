@@ -249,6 +249,31 @@ EK_HD void backward_pixel(const Pixel<T>& p, int flags, T meas, bool col_is_max,
   out[0] = (T)d0; out[1] = (T)d1; out[2] = (T)e0; out[3] = (T)e1;
 }
 
+// ---- stored-planes variant of the backward (EBOS_EKLT_STORED=1, experimental) ---------------------------------------
+// The forward keeps what the backward needs of a pixel in six planes instead of having it re-evaluate the up-sampling and
+// the eight gathered taps:  sx.v, sy.v, A = f0*sx.d_r + f1*sy.d_r, B = f0*sx.d_c + f1*sy.d_c, t0, t1.
+template <typename T>
+EK_HD void pack_pixel(const Pixel<T>& p, T out[6]) {
+  out[0] = p.sx.v;
+  out[1] = p.sy.v;
+  out[2] = (T)((double)p.f0 * (double)p.sx.d_r + (double)p.f1 * (double)p.sy.d_r);
+  out[3] = (T)((double)p.f0 * (double)p.sx.d_c + (double)p.f1 * (double)p.sy.d_c);
+  out[4] = p.t0;
+  out[5] = p.t1;
+}
+// A Pixel that makes backward_pixel reproduce the same expressions from the stored planes (f0 = 1, f1 = 0 turn
+// f0*d + f1*d' into the stored combination).  Not for kNoPolarity (the sign of q0 is not stored).
+template <typename T>
+EK_HD Pixel<T> unpack_pixel(const T s[6], T q, T wgt, bool m) {
+  Pixel<T> p;
+  p.f0 = (T)1; p.f1 = (T)0;
+  p.t0 = s[4]; p.t1 = s[5];
+  p.sx.v = s[0]; p.sx.d_r = s[2]; p.sx.d_c = s[3];
+  p.sy.v = s[1]; p.sy.d_r = (T)0; p.sy.d_c = (T)0;
+  p.q0 = q; p.q = q; p.wgt = wgt; p.m = m;
+  return p;
+}
+
 // Transposed up-sampling, gather form.  Padded cell A of an axis receives from the dense rows
 //   I in [(A-1)*patch + patch/2, (A+1)*patch + patch/2)   with the triangle weight 1 - |u(I) - A|.
 EK_HD void cell_support(int A, int patch, int offset, int size, int& i_begin, int& i_end) {

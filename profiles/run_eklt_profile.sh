@@ -9,7 +9,7 @@ tail -3 gpurun_out/eklt_gpu_tests_r01i.log
 EBOS_TEST_EXPERIMENTAL=1 timeout 40 python -m pytest tests/test_gpu_zz_eklt.py -m gpu -q --tb=short -p no:cacheprovider -k experimental \
   > gpurun_out/eklt_gpu_tests_experimental.log 2>&1
 tail -3 gpurun_out/eklt_gpu_tests_experimental.log
-timeout 40 python bench.py --workload eklt --steps 3 --warmup 1 --no-cpu ${EKLT_AB_TAIL:+--eklt-ab-tail} ${EKLT_CACHE_GRAPHS:+--eklt-cache-graphs} > gpurun_out/eklt_bench_f64_r01i.json 2> gpurun_out/eklt_bench_f64_r01i.err
+timeout 40 python bench.py --workload eklt --steps 3 --warmup 1 --no-cpu ${EKLT_AB_TAIL:+--eklt-ab-tail} ${EKLT_AB_STORED:+--eklt-ab-stored} ${EKLT_CACHE_GRAPHS:+--eklt-cache-graphs} > gpurun_out/eklt_bench_f64_r01i.json 2> gpurun_out/eklt_bench_f64_r01i.err
 tail -c 900 gpurun_out/eklt_bench_f64_r01i.json; tail -3 gpurun_out/eklt_bench_f64_r01i.err
 timeout 40 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/r01i_eklt_launches.csv \
   python bench.py --workload eklt --steps 1 --warmup 1 --solve-iters 20 --eklt-no-graph --no-cpu > gpurun_out/eklt_ncu_run_r01i.log 2>&1

@@ -67,7 +67,7 @@ static void columns_t(const Geom& g, const T* q, const T* meas, double q2, doubl
 template <typename T>
 static void backward_t(const Geom& g, int flags, const T* theta, const T* pf, const T* gx, const T* gy, const T* weights,
                        const T* meas, const T* dF, const double* colsum, const double* scal, double w_pxy, T* dU, T* dPad,
-                       T* dP, T* grad) {
+                       T* dP, T* grad, bool stored = false) {
   const T* tr = (flags & kWarp) ? theta + flow_channels(flags) * g.ph * g.pw : nullptr;
   if (!(flags & kWarp)) w_pxy = 0.0;
   BackScalars s;
@@ -76,8 +76,13 @@ static void backward_t(const Geom& g, int flags, const T* theta, const T* pf, co
   const double w_pxy_hw = w_pxy / ((double)g.H * g.W);
   for (int i = 0; i < g.H; ++i)
     for (int j = 0; j < g.W; ++j) {
-      const Pixel<T> p = eval_pixel<T>(g, flags, pf, tr, gx, gy, weights, i, j);
+      Pixel<T> p = eval_pixel<T>(g, flags, pf, tr, gx, gy, weights, i, j);
       const int64_t k = (int64_t)i * g.W + j;
+      if (stored) {                    // k_forward packs six planes, k_backward_stored rebuilds the pixel from them
+        T pk[6];
+        pack_pixel<T>(p, pk);
+        p = unpack_pixel<T>(pk, p.q, weights ? weights[k] : (T)1, p.m);
+      }
       T out[4];
       backward_pixel<T>(p, flags, meas[k], colsum[j] == s.mx, s, p.m ? dF[k] : (T)0, p.m ? dF[plane + k] : (T)0, w_pxy_hw,
                         out);
@@ -234,6 +239,16 @@ int eklt_host_tail(const int* dims, int flags, const double* dPad, double* dP, d
       adam_one<double>(theta[e], gk[c], m[e], v[e], b1, b2, eps, step_size, inv_bc2_sqrt);
     }
   }
+  return 0;
+}
+
+// the same through the stored-planes backward (EBOS_EKLT_STORED=1), float64
+int eklt_host_backward_stored(const int* dims, int flags, const double* theta, const double* pf, const double* gx,
+                              const double* gy, const double* weights, const double* meas, const double* dF,
+                              const double* colsum, const double* scal, double w_pxy, double* dU, double* dPad, double* dP,
+                              double* grad) {
+  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
+  backward_t<double>(g, flags, theta, pf, gx, gy, weights, meas, dF, colsum, scal, w_pxy, dU, dPad, dP, grad, true);
   return 0;
 }
 

@@ -117,7 +117,7 @@ def _p(a):
 
 
 def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dtype=np.float64, poisson=True, warp=True,
-                        no_polarity=False, hist_weights=None):
+                        no_polarity=False, hist_weights=None, stored=False):
     H, W = gx.shape
     nt, ph, pw = theta.shape
     wd, wtv, wp = (float(v) for v in weights)
@@ -154,8 +154,15 @@ def host_value_and_grad(lib, theta, gx, gy, meas, winv, roi, patch, weights, dty
     grad = np.zeros((nt, ph, pw), dtype)
     lib.eklt_host_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 9 + \
                                       [ctypes.c_double] + [ctypes.c_void_p] * 4
-    lib.eklt_host_backward(dims, f64, flags, _p(theta), _p(pf), _p(gx), _p(gy), hw_p, _p(meas), _p(dF), _p(colsum),
-                           _p(scal), wp, _p(dU), _p(dPad), _p(dP), _p(grad))
+    if stored:
+        assert f64
+        lib.eklt_host_backward_stored.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 9 + \
+                                                 [ctypes.c_double] + [ctypes.c_void_p] * 4
+        lib.eklt_host_backward_stored(dims, flags, _p(theta), _p(pf), _p(gx), _p(gy), hw_p, _p(meas), _p(dF), _p(colsum),
+                                      _p(scal), wp, _p(dU), _p(dPad), _p(dP), _p(grad))
+    else:
+        lib.eklt_host_backward(dims, f64, flags, _p(theta), _p(pf), _p(gx), _p(gy), hw_p, _p(meas), _p(dF), _p(colsum),
+                               _p(scal), wp, _p(dU), _p(dPad), _p(dP), _p(grad))
     loss = wd * scal[1] + wtv * tv + (wp * sums[1] / (H * W) if warp else 0.0)
     return {"loss": loss, "grad": grad, "q": q, "F": F, "trans": tr, "pf": pf, "colsum": colsum, "n": scal[0], "dU": dU,
             "dF": dF, "tv": tv}
@@ -452,3 +459,22 @@ def test_torch_op_restatement_matches_reference_and_analytic_oracle(gold):
     loss, grad = TT.value_and_grad(t(th), t(gx), t(gy), t(meas), t(winv), roi, patch)
     assert abs(loss - r["loss"]) <= 1e-13
     assert np.abs(grad.numpy() - r["grad"]).max() <= 1e-12 * np.abs(r["grad"]).max()
+
+
+def test_stored_planes_backward_arithmetic_matches_reference(gold, host_lib):
+    """EBOS_EKLT_STORED=1 (experimental): the backward rebuilt from the six planes the forward stores gives the
+    reference's gradient at every level and regime, and with event-histogram weights."""
+    for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+        for name in ("start", "random", "far"):
+            key = f"L{scale}_{name}"
+            h = host_value_and_grad(host_lib, gold[key + "_theta"], gold["grad_x"], gold["grad_y"], gold["measured"],
+                                    gold["weight_inverse"], gold["roi_t"], patch, gold["cost_weights"], stored=True)
+            ref = gold[key + "_grad"]
+            assert np.abs(h["grad"] - ref).max() <= 1e-11 * np.abs(ref).max(), key
+    for c in _variant_cases(gold):
+        if c["no_polarity"] or not c["warp"]:
+            continue                                    # the C entry keeps the re-evaluating backward for these
+        h = host_value_and_grad(host_lib, c["theta"], gold["grad_x"], gold["grad_y"], c["measured"], c["winv"],
+                                gold["roi_t"], c["patch"], c["cost_weights"], poisson=c["poisson"], warp=True,
+                                hist_weights=c["weights"], stored=True)
+        assert np.abs(h["grad"] - c["grad"]).max() <= 1e-11 * np.abs(c["grad"]).max(), c["name"]
