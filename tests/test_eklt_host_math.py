@@ -478,3 +478,38 @@ def test_stored_planes_backward_arithmetic_matches_reference(gold, host_lib):
                                 gold["roi_t"], c["patch"], c["cost_weights"], poisson=c["poisson"], warp=True,
                                 hist_weights=c["weights"], stored=True)
         assert np.abs(h["grad"] - c["grad"]).max() <= 1e-11 * np.abs(c["grad"]).max(), c["name"]
+
+
+def test_c_abi_argument_validation_without_a_device():
+    """The EKLT entry points validate before they touch CUDA: bad arguments come back as EBOS_ERR_* with a message, on a
+    machine without a GPU as well (no compute is launched here)."""
+    from event_based_bos_b200 import _capi
+
+    lib = _capi.load()
+    ws64 = lib.ebos_eklt_workspace_bytes(720, 1280, 12, 20, 64, _capi.EBOS_F64)
+    ws32 = lib.ebos_eklt_workspace_bytes(720, 1280, 12, 20, 64, _capi.EBOS_F32)
+    plane = 720 * 1280 * 8
+    assert 15 * plane < ws64 < 16 * plane and ws32 < ws64          # q, F(2), dF(2), dU(4), stored(6) + small arrays
+    assert lib.ebos_eklt_workspace_bytes(0, 1280, 12, 20, 64, _capi.EBOS_F64) == 0
+    one = 1 << 12                                   # any non-null "pointer": validation fails before it is dereferenced
+    common = lambda **kw: dict(dict(theta=one, flags=3, gx=one, gy=one, meas=one, winv=one, weights=0, H=720, W=1280, ph=12,
+                                    pw=20, patch=64, x0=0, x1=720, y0=320, y1=960, dtype=_capi.EBOS_F64, ws=one, ws_bytes=ws64,
+                                    loss=one, grad=one), **kw)
+
+    def call(**kw):
+        a = common(**kw)
+        return lib.ebos_eklt_value_and_grad(a["theta"], a["flags"], a["gx"], a["gy"], a["meas"], a["winv"], a["weights"],
+                                            a["H"], a["W"], a["ph"], a["pw"], a["patch"], a["x0"], a["x1"], a["y0"], a["y1"],
+                                            1.0, 0.5, 0.1, a["dtype"], a["ws"], a["ws_bytes"], a["loss"], a["grad"], 0)
+
+    assert call(theta=0) == -1 and "null" in _capi.last_error()                       # EBOS_ERR_BAD_ARG
+    assert call(flags=8) == -1 and "flag" in _capi.last_error()
+    assert call(dtype=7) == -4                                                       # EBOS_ERR_UNSUPPORTED
+    assert call(ph=11) == -1 and "patch grid" in _capi.last_error()                  # not ceil(720/64)
+    assert call(x1=721) == -1 and "ROI" in _capi.last_error()
+    assert call(ws_bytes=ws64 - 1) == -3 and "workspace" in _capi.last_error()       # EBOS_ERR_WORKSPACE
+    taps = np.array([1.0, 2.0, 1.0])
+    tp = taps.ctypes.data_as(ctypes.c_void_p)
+    assert lib.ebos_sepconv2d(one, 8, 8, tp, 3, tp, 2, 0, _capi.EBOS_F64, one, one, 0) == -1       # even tap count
+    assert lib.ebos_sepconv2d(one, 8, 8, tp, 3, tp, 3, 2, _capi.EBOS_F64, one, one, 0) == -1       # unknown border
+    assert lib.ebos_eklt_upsample(one, 2, 720, 1280, 12, 19, 64, _capi.EBOS_F64, one, 0) == -1     # wrong patch grid
