@@ -513,3 +513,28 @@ def test_c_abi_argument_validation_without_a_device():
     assert lib.ebos_sepconv2d(one, 8, 8, tp, 3, tp, 2, 0, _capi.EBOS_F64, one, one, 0) == -1       # even tap count
     assert lib.ebos_sepconv2d(one, 8, 8, tp, 3, tp, 3, 2, _capi.EBOS_F64, one, one, 0) == -1       # unknown border
     assert lib.ebos_eklt_upsample(one, 2, 720, 1280, 12, 19, 64, _capi.EBOS_F64, one, 0) == -1     # wrong patch grid
+
+
+def test_fp32_arithmetic_solve_within_1e3_px_of_reference(gold, host_lib):
+    """The float32 instantiation of the kernel arithmetic (serial build) driven through the complete coarse-to-fine Adam
+    schedule of the golden `estimate()`: the final flow stays within the north-star bar (1e-3 px RMS) of the float64
+    reference.  Evidence for `solver.eklt.precision: "32"`; the GPU tests gate the float64 default."""
+    H, W = (int(v) for v in gold["image"])
+    n_iter, levels = int(gold["n_iter"]), gold["levels_t"]
+    th = gold["solve_x0"].astype(np.float32)
+    for li, (patch, ph, pw) in enumerate(levels):
+        if li > 0:
+            th = E.resize_params(th.astype(np.float64), (ph, pw)).astype(np.float32)
+        m, v = np.zeros_like(th), np.zeros_like(th)
+        for it in range(E.level_iterations(n_iter, len(levels), li)):
+            h = host_value_and_grad(host_lib, th, gold["grad_x"], gold["grad_y"], gold["measured"], gold["weight_inverse"],
+                                    gold["roi_t"], patch, gold["cost_weights"], dtype=np.float32)
+            g = h["grad"].astype(np.float32)
+            m = np.float32(0.9) * m + np.float32(0.1) * g
+            v = np.float32(0.999) * v + np.float32(0.001) * g * g
+            step = np.float32(0.05 / (1 - 0.9 ** (it + 1)))
+            th = th - step * (m / (np.sqrt(v) * np.float32(1 / np.sqrt(1 - 0.999 ** (it + 1))) + np.float32(1e-8)))
+    patch = levels[-1][0]
+    dense = E.upsample_patch(E.sobel_over_8(th[0].astype(np.float64)), patch, (H, W)) * E.roi_mask((H, W), gold["roi_t"])
+    rms = np.sqrt(np.mean((dense - gold["solve_flow"]) ** 2))
+    assert rms <= 1e-3, rms

@@ -321,6 +321,24 @@ def test_solver_drop_in_matches_reference_estimate(gold):
     assert np.all(flow[:, :roi[0]] == 0) and np.all(flow[:, :, roi[3]:] == 0)
 
 
+def test_solver_drop_in_float32_within_1e3_px(gold):
+    """`solver.eklt.precision: "32"`: the float32 instantiation through the whole drop-in solve stays within the
+    north-star bar of the float64 reference (serial check: 1.2e-7 px RMS on this fixture)."""
+    import copy
+
+    from event_based_bos_b200 import solver
+
+    H, W = (int(v) for v in gold["image"])
+    roi = gold["roi_t"]
+    cfg = copy.deepcopy(HOT_PLATE1_SOLVER)
+    cfg["eklt"] = {"precision": "32"}
+    s = solver.collections["patch_eklt_pyramid2"]((H, W), (roi[1] - roi[0], roi[3] - roi[2]), {}, cfg, None)
+    np.random.seed(7)
+    flow = s.estimate(gold["events"], frame=gold["frame"])
+    assert flow.dtype == np.float64 and flow.shape == (2, H, W)
+    assert np.sqrt(np.mean((flow - gold["solve_flow"]) ** 2)) <= 1e-3
+
+
 def test_bad_arguments_raise(gold, eklt):
     prob = problem_from_gold(eklt, gold)
     lvl = prob.level(16)
