@@ -602,7 +602,7 @@ def run_eklt(args, rank, world, local):
     dt = torch.float32 if args.eklt_precision == "32" else torch.float64
     prob = eklt.EkltProblem(slv._gradient_x_torch, slv._gradient_y_torch, slv.cache_measured, slv.weight_inverse,
                             (0, 720, 320, 960), (1.0, 0.5, 0.1))
-    per_level, per_level_legacy, per_level_stored = {}, {}, {}
+    per_level, per_level_legacy, per_level_stored, per_level_seg = {}, {}, {}, {}
     for patch, ph, pw in slv.levels:
         lvl = prob.level(patch)
         th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous()
@@ -612,6 +612,12 @@ def run_eklt(args, rank, world, local):
             per_level_legacy[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
         finally:
             os.environ.pop("EBOS_EKLT_LEGACY", None)
+        if args.eklt_ab_seg:                          # opt-in: experimental segment-form column pass of the gather
+            os.environ["EBOS_EKLT_GATHER_SEG"] = "1"
+            try:
+                per_level_seg[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+            finally:
+                os.environ.pop("EBOS_EKLT_GATHER_SEG", None)
         if args.eklt_ab_stored:                       # opt-in: experimental stored-planes backward
             os.environ["EBOS_EKLT_STORED"] = "1"
             try:
@@ -656,7 +662,8 @@ def run_eklt(args, rank, world, local):
                          "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_kind},
             "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy,
-            "eval_ms_per_level_stored_planes": per_level_stored or None, "iteration_ms_per_level": iter_ms or None,
+            "eval_ms_per_level_stored_planes": per_level_stored or None,
+            "eval_ms_per_level_segment_gather": per_level_seg or None, "iteration_ms_per_level": iter_ms or None,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
             "gpu_launches": args.steps * sum(iters) * 12}
@@ -741,6 +748,7 @@ def main():
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
     ap.add_argument("--eklt-ab-tail", action="store_true", help="also time evaluation + Adam with EBOS_EKLT_TAIL=1")
     ap.add_argument("--eklt-ab-stored", action="store_true", help="also time the evaluation with EBOS_EKLT_STORED=1")
+    ap.add_argument("--eklt-ab-seg", action="store_true", help="also time the evaluation with EBOS_EKLT_GATHER_SEG=1")
     ap.add_argument("--eklt-cache-graphs", action="store_true",
                     help="experimental: keep buffers and CUDA graphs across windows (solver.eklt.cache_graphs)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -386,6 +386,66 @@ __global__ void __launch_bounds__(256) k_gather_rows(Geom g, int nch, const T* _
   if (lane == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)s;
 }
 
+// EXPERIMENTAL (EBOS_EKLT_GATHER_SEG=1, off by default; not yet run on hardware): column pass for small patches.  A warp
+// reads 32 consecutive pixels of a row ONCE (coalesced, all lanes busy), lane groups of `patch` lanes -- aligned with the
+// runs of equal floor cell -- reduce their lo / hi weighted sums with shuffles, and the group leaders add them to the two
+// column cells of T1 (zeroed first; <= 2 contributions per address).  k_gather_cols leaves half a warp idle at 8-px patches
+// and reads every pixel twice (51 us); the warp-per-cell 2-D form reads it four times (36 us).
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_cols_seg(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ T1) {
+  const int PW = g.pw + 2 * g.pad, p = g.patch;
+  const int start = region_offset(g.w1, p) - p + (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+  if (start >= g.W) return;                      // whole warps leave together
+  const int lane = threadIdx.x & 31, i = blockIdx.y, j = start + lane;
+  const bool valid = j >= 0 && j < g.W;
+  int A;
+  T hi;
+  segment_tap<T>(j, g.w1, p, A, hi);
+  const int64_t plane = (int64_t)g.H * g.W;
+  double lo_s[4], hi_s[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double v = (valid && c < nch) ? (double)dU[c * plane + (int64_t)i * g.W + j] : 0.0;
+    hi_s[c] = v * (double)hi;
+    lo_s[c] = v - hi_s[c];                        // v * (1 - hi)
+  }
+  for (int o = p >> 1; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      lo_s[c] += __shfl_xor_sync(0xffffffffu, lo_s[c], o);
+      hi_s[c] += __shfl_xor_sync(0xffffffffu, hi_s[c], o);
+    }
+  }
+  if ((lane & (p - 1)) == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= nch) break;
+      T* row = T1 + ((int64_t)c * g.H + i) * PW;
+      if (A >= 0 && A < PW) atomicAdd(row + A, (T)lo_s[c]);
+      if (A + 1 >= 0 && A + 1 < PW) atomicAdd(row + A + 1, (T)hi_s[c]);
+    }
+  }
+}
+// Row pass with one THREAD per (channel, padded cell), consecutive lanes on consecutive column cells (coalesced rows of
+// T1): for small patches, where a warp per output would have 2*patch <= 32 rows to share.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_rows_thread(Geom g, int nch, const T* __restrict__ T1, T* __restrict__ dPad) {
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nch * PH * PW) return;
+  const int c = o / (PH * PW), A = (o / PW) % PH, B = o % PW;
+  int i0, i1;
+  cell_support(A, g.patch, g.h1, g.H, i0, i1);
+  double s = 0.0;
+  for (int i = i0; i < i1; ++i)
+    s += (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)T1[((int64_t)c * g.H + i) * PW + B];
+  dPad[((int64_t)c * PH + A) * PW + B] = (T)s;
+}
+static bool gather_segments() {
+  const char* v = getenv("EBOS_EKLT_GATHER_SEG");
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+
 // Same for small supports (patch <= 16: at most 1024 pixels per cell): one WARP per padded cell, eight cells per CTA,
 // shuffle reductions only.  At the finest level (8-px patches, 92 x 162 cells at 1280x720) the CTA-per-cell form
 // would spend its time in four block reductions over one pixel per thread.
@@ -641,7 +701,15 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
   // B200, 1280x720 fp64 (profiles/eklt/r01i launch list): two separable passes 20 / 25 / 36 / 71 us at patch 64 / 32 /
   // 16 / 8 against 54 / 33 us (CTA per cell) and 36 / 36 us (warp per cell): a warp of pass 1 covers one 2*patch-pixel
   // support, which leaves half of it idle at patch 8.
-  if (g.patch <= 16) {
+  if (!legacy && gather_segments() && g.patch >= 2 && g.patch <= 32 && 32 % g.patch == 0) {
+    T* T1 = reinterpret_cast<T*>(w.T1);
+    e = cudaMemsetAsync(T1, 0, (size_t)nch * g.H * PW * sizeof(T), st);
+    if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset T1");
+    const int n_seg = (g.W - (region_offset(g.w1, g.patch) - g.patch) + 31) / 32;
+    k_gather_cols_seg<T><<<dim3((n_seg + 7) / 8, g.H), 256, 0, st>>>(g, nch, dU, T1);
+    if (g.patch <= 16) k_gather_rows_thread<T><<<(nch * n_cells + 255) / 256, 256, 0, st>>>(g, nch, T1, dPad);
+    else k_gather_rows<T><<<(nch * n_cells + 7) / 8, 256, 0, st>>>(g, nch, T1, dPad);
+  } else if (g.patch <= 16) {
     k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
   } else if (legacy) {
     k_cell_gather<T><<<dim3(PW, PH), 256, 0, st>>>(g, nch, dU, dPad);

@@ -292,6 +292,23 @@ EK_HD T cell_weight(int A, int i, int offset, int patch) {
   return w > 0 ? w : (T)0;
 }
 
+// ---- segment form of the column pass (EBOS_EKLT_GATHER_SEG=1, experimental; even patch sizes dividing 32) ----------
+// Columns whose dense index I = j + w1 satisfies (I - patch/2) mod patch == 0 start a run of `patch` columns with the same
+// floor cell A = floor((I - patch/2) / patch) and the up-sampling fractions (r + 0.5) / patch, r = 0 .. patch-1 (both exact
+// for even patch sizes).  Warps start at `region_offset - patch` so that lane groups of `patch` lanes ARE those runs.
+EK_HD int region_offset(int offset, int patch) {
+  const int o = (patch / 2 - offset) % patch;
+  return o < 0 ? o + patch : o;
+}
+EK_HD int floor_div(int n, int d) { return n >= 0 ? n / d : -((-n + d - 1) / d); }
+// padded floor cell and hi-weight of column j (lo-weight = 1 - hi)
+template <typename T>
+EK_HD void segment_tap(int j, int offset, int patch, int& A, T& hi) {
+  const int n = j + offset - patch / 2;
+  A = floor_div(n, patch);
+  hi = ((T)(n - A * patch) + (T)0.5) / (T)patch;
+}
+
 // Fold the replicate padding: sum of the padded cells that clamp to unpadded cell a.  [begin,end) in padded indices.
 EK_HD void fold_range(int a, int n_patch, int pad, int& begin, int& end) {
   begin = (a == 0) ? 0 : a + pad;

@@ -252,4 +252,48 @@ int eklt_host_backward_stored(const int* dims, int flags, const double* theta, c
   return 0;
 }
 
+// k_gather_cols_seg + k_gather_rows_thread walked serially, warp by warp and lane group by lane group (float64): the
+// shuffle reduction of a group becomes a plain sum over its lanes.  T1 must be zero on entry.
+int eklt_host_gather_seg(const int* dims, int nch, const double* dU, double* T1, double* dPad) {
+  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
+  const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad, p = g.patch;
+  if (p < 2 || p > 32 || 32 % p != 0) return -1;
+  const int64_t plane = (int64_t)g.H * g.W;
+  const int first = region_offset(g.w1, p) - p;
+  for (int i = 0; i < g.H; ++i)
+    for (int start = first; start < g.W; start += 32)
+      for (int grp = 0; grp < 32 / p; ++grp) {
+        double lo_s[4] = {0, 0, 0, 0}, hi_s[4] = {0, 0, 0, 0};
+        int A_leader = 0;
+        for (int l = 0; l < p; ++l) {
+          const int lane = grp * p + l, j = start + lane;
+          int A;
+          double hi;
+          segment_tap<double>(j, g.w1, p, A, hi);
+          if (l == 0) A_leader = A;
+          else if (A != A_leader) return -2;          // the alignment claim: one floor cell per lane group
+          const bool valid = j >= 0 && j < g.W;
+          for (int c = 0; c < nch; ++c) {
+            const double v = valid ? dU[c * plane + (int64_t)i * g.W + j] : 0.0;
+            hi_s[c] += v * hi;
+            lo_s[c] += v - v * hi;
+          }
+        }
+        for (int c = 0; c < nch; ++c) {
+          double* row = T1 + ((int64_t)c * g.H + i) * PW;
+          if (A_leader >= 0 && A_leader < PW) row[A_leader] += lo_s[c];
+          if (A_leader + 1 >= 0 && A_leader + 1 < PW) row[A_leader + 1] += hi_s[c];
+        }
+      }
+  for (int o = 0; o < nch * PH * PW; ++o) {
+    const int c = o / (PH * PW), A = (o / PW) % PH, B = o % PW;
+    int i0, i1;
+    cell_support(A, g.patch, g.h1, g.H, i0, i1);
+    double s = 0.0;
+    for (int i = i0; i < i1; ++i) s += cell_weight<double>(A, i, g.h1, g.patch) * T1[((int64_t)c * g.H + i) * PW + B];
+    dPad[((int64_t)c * PH + A) * PW + B] = s;
+  }
+  return 0;
+}
+
 }  // extern "C"

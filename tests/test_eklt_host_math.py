@@ -538,3 +538,33 @@ def test_fp32_arithmetic_solve_within_1e3_px_of_reference(gold, host_lib):
     dense = E.upsample_patch(E.sobel_over_8(th[0].astype(np.float64)), patch, (H, W)) * E.roi_mask((H, W), gold["roi_t"])
     rms = np.sqrt(np.mean((dense - gold["solve_flow"]) ** 2))
     assert rms <= 1e-3, rms
+
+
+def test_segment_gather_arithmetic_matches_transposed_upsampling(host_lib):
+    """EBOS_EKLT_GATHER_SEG=1 (experimental): the warp/lane-group walk of k_gather_cols_seg + k_gather_rows_thread gives the
+    transposed bilinear up-sampling R^T dU C for every even patch size dividing 32, with images that are not multiples of
+    anything; the serial build also checks the alignment claim (one floor cell per lane group)."""
+    rng = np.random.default_rng(12)
+    for (H, W, patch) in [(37, 53, 8), (40, 100, 16), (21, 70, 4), (50, 70, 32), (19, 33, 2), (720 // 8, 1280 // 8, 8)]:
+        ph, pw = E.patch_grid((H, W), patch)
+        geo = E.upsample_geometry((H, W), ph, pw, patch)
+        dims = (ctypes.c_int * 9)(H, W, ph, pw, patch, 0, H, 0, W)
+        dU = rng.normal(size=(4, H, W))
+        T1 = np.zeros((4, H, pw + 2))
+        dPad = np.zeros((4, ph + 2, pw + 2))
+        rc = host_lib.eklt_host_gather_seg(dims, 4, _p(dU), _p(T1), _p(dPad))
+        assert rc == 0, (H, W, patch, rc)
+
+        def tri(n_out, offset, n_cells):          # [cells, pixels] triangle weights of the padded axis
+            u = (np.arange(n_out) + offset + 0.5) / patch - 0.5
+            return np.clip(1.0 - np.abs(u[None, :] - np.arange(n_cells)[:, None]), 0.0, None)
+
+        R, C = tri(H, geo["h1"], ph + 2), tri(W, geo["w1"], pw + 2)
+        ref = np.einsum("ai,cij,bj->cab", R, dU, C)
+        assert np.abs(dPad - ref).max() <= 1e-12 * np.abs(ref).max(), (H, W, patch)
+        # and it is the adjoint the oracle uses (after folding the replicate padding)
+        folded = np.zeros((4, ph, pw))
+        rr = np.clip(np.arange(ph + 2) - 1, 0, ph - 1)
+        cc = np.clip(np.arange(pw + 2) - 1, 0, pw - 1)
+        np.add.at(folded, (slice(None), rr[:, None], cc[None, :]), dPad)
+        assert np.abs(folded - E.upsample_patch_adjoint(dU, patch, ph, pw)).max() <= 1e-12 * np.abs(ref).max()

@@ -257,6 +257,20 @@ def test_experimental_tail_kernel_matches_default_chain(gold, eklt):
         assert np.abs(got - ref).max() <= 1e-10, scale
 
 
+@pytest.mark.skipif(not os.environ.get("EBOS_TEST_EXPERIMENTAL"), reason="opt-in: EBOS_EKLT_GATHER_SEG path, not yet run on hardware")
+def test_experimental_segment_gather_matches_reference(gold, eklt):
+    """EBOS_EKLT_GATHER_SEG=1: segment form of the transposed up-sampling, against the reference's autograd."""
+    prob = problem_from_gold(eklt, gold)
+    os.environ["EBOS_EKLT_GATHER_SEG"] = "1"
+    try:
+        for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
+            key = f"L{scale}_random"
+            loss, grad = prob.level(patch).value_and_grad(dev(gold[key + "_theta"]))
+            assert rel(grad.cpu().numpy(), gold[key + "_grad"]) <= 1e-9, key
+    finally:
+        os.environ.pop("EBOS_EKLT_GATHER_SEG", None)
+
+
 @pytest.mark.skipif(not os.environ.get("EBOS_TEST_EXPERIMENTAL"), reason="opt-in: EBOS_EKLT_STORED path, not yet run on hardware")
 def test_experimental_stored_planes_backward_matches_reference(gold, eklt):
     """EBOS_EKLT_STORED=1: backward from six planes stored by the forward, against the reference's autograd."""
