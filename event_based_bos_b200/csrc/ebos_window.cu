@@ -1081,6 +1081,191 @@ k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const
   }
 }
 
+// ---- run-merging fixed-point tile splat (round 2) --------------------------------------------------------
+// ncu r01g of k_tile_splat_d: the kernel is bound by shared-memory ATOMIC WAVEFRONTS, not by bytes or issue slots:
+// 8.83 M wavefronts for 2.36 M ATOMS warp instructions (the +-3 px random flow sends the 32 lanes of an instruction
+// to random banks: ~3.7-way conflicts) at ~2 cycles per wavefront = 60 of its 72 us.  Two changes:
+//  * Consecutive events of a thread belong to one origin pixel and are time ordered, so they stay in one IWE cell for
+//    runs of ~5 events.  The run's four tap sums are kept in registers and added to the window only when the cell
+//    changes -- WITHOUT a divergent branch (which is what sank k_tile_splat_q: a warp takes the flush branch at nearly
+//    every step because some lane always flushes): the fixed-point conversion is executed unconditionally and the four
+//    `red.shared` are PREDICATED per lane.  An instruction whose predicate is true in ~8 of 32 lanes conflicts ~1.7-way
+//    instead of 3.7-way: half the wavefronts for +4 issue slots per event.
+//  * The flow at the tile's 1024 origin pixels, together with the pixel coordinates as floats, is staged in shared
+//    memory once per CTA (16 KB): the per-event flow gather is one conflict-free LDS.128 (lanes of a warp read the same
+//    few pixels: broadcast) instead of two dependent global loads behind a "pixel changed" branch, and the two
+//    int -> float conversions of the origin coordinates disappear.
+// A run is at most the 16 events of a thread: |sum| <= 16 * (1 + 2e-6), so S = 17 keeps sum * 2^S below 2^22 (the range of
+// the fma(w, 2^S, 1.5 * 2^23) conversion) and 4080 * 2^17 below 2^31 (window overflow).  One rounding of <= 2^-18 per
+// FLUSHED tap sum (a quarter as many roundings as k_tile_splat_d makes, each four times larger).
+constexpr int kMergeS = 17;
+
+// the four tap sums of a finished run -> fixed point -> window (no-return shared-memory reductions).  The caller
+// branches around the call: ptxas never predicates ATOMS on sm_100a (a predicated `red.shared` in inline PTX becomes
+// one BSSY / BRA / BSYNC region PER instruction), so the four reductions share one branch region.
+__device__ __forceinline__ void flush_run_smem(int* __restrict__ win, int off, float2 a01, float2 a23) {
+  const float M = 12582912.0f;   // 1.5 * 2^23
+  const float qs = (float)(1 << kMergeS);
+  const float2 q01 = fma2(a01, make_float2(qs, qs), make_float2(M, M));
+  const float2 q23 = fma2(a23, make_float2(qs, qs), make_float2(M, M));
+  int* p = win + off;
+  atomicAdd(p, __float_as_int(q01.x) - 0x4B400000);            // (r  , c  )
+  atomicAdd(p + kSW, __float_as_int(q01.y) - 0x4B400000);      // (r+1, c  )
+  atomicAdd(p + 1, __float_as_int(q23.x) - 0x4B400000);        // (r  , c+1)
+  atomicAdd(p + kSW + 1, __float_as_int(q23.y) - 0x4B400000);  // (r+1, c+1)
+}
+
+// tile-local index of an origin pixel from the packed (row << 16 | col) word: (row % 32) * 32 + col % 32
+__device__ __forceinline__ int tile_local_pixel(unsigned rc) { return (int)(((rc >> 11) & 0x3e0u) | (rc & 31u)); }
+
+// (f0, f1, row, col) of the tile's origin pixels -> shared memory (pixels outside the image: zeros, never addressed)
+__device__ __forceinline__ void fill_pixel_table(float4* __restrict__ pix, const float* __restrict__ flow, int tr0, int tc0,
+                                                 int H, int W, int hw) {
+  for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
+    const int r = tr0 + (i >> 5), c = tc0 + (i & 31);
+    const bool in = r < H && c < W;
+    const int k = in ? r * W + c : 0;
+    pix[i] = make_float4(in ? __ldg(flow + k) : 0.f, in ? __ldg(flow + hw + k) : 0.f, (float)r, (float)c);
+  }
+}
+
+// One event outside the regular case of k_tile_splat_m (item boundary, cell outside the window, non-finite, item too
+// small for the window): same arithmetic as the fast path, recomputed from the warped coordinate so that the fast path
+// keeps nothing alive for it.  x0 = NaN marks an event that belongs to the neighbouring item.
+__device__ __noinline__ void splat_event_general(float* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w, float x0,
+                                                 float xw, float yw, int* __restrict__ win, int r_org, int c_org, int use_win) {
+  if (x0 != x0) return;
+  const float2 w = make_float2(xw, yw);
+  const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
+  const float fr = floorf(wb.x), fc = floorf(wb.y);
+  const float2 ab = sub2(w, make_float2(fr, fc));
+  const float2 nab = sub2(make_float2(1.f, 1.f), ab);
+  const float2 lhs = make_float2(nab.x, ab.x);
+  const float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
+  const float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
+  if (w01.x != w01.x) {   // non-finite warped coordinate: the reference's NaN lands on pixel 0
+    splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, x0, xw, yw, 1.f);
+    return;
+  }
+  const int r = (int)fr + pad_h, c = (int)fc + pad_w;
+  const int lr = r - r_org, lc = c - c_org;
+  if (use_win && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1))
+    flush_run_smem(win, lr * kSW + lc, w01, w23);
+  else
+    flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, r, c, w01.x, w01.y, w23.x, w23.y);
+}
+
+template <bool PACKED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+               const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
+               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
+  __shared__ int win[kSH * kSW];
+  __shared__ float4 pix[kTileH * kTileW];
+  pdl_launch_dependents();   // the cost kernel may be scheduled while this grid drains (it waits before reading the IWE)
+  if ((int)blockIdx.x >= hdr->n_items) return;
+  const int4 it = __ldg(items + blockIdx.x);
+  const int lo = it.y, hi = it.z;
+  if (hi <= lo) return;
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
+  const int tr0 = (it.w >> 16) * kTileH, tc0 = (it.w & 0xffff) * kTileW;
+  const int r_org = tr0 - kHalo + pad_h, c_org = tc0 - kHalo + pad_w;
+  const int dr = pad_h - r_org, dc = pad_w - c_org;          // window coordinates = floor + (dr, dc)
+  const bool use_win = hi - lo >= kWinMinEvents;
+  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0;
+  fill_pixel_table(pix, flow, tr0, tc0, H, W, hw);
+  __syncthreads();
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
+  const int start = lo & ~3;
+  for (int base = start + (int)threadIdx.x * 16; base < hi; base += (int)blockDim.x * 16) {
+    // pending run: window offset of its cell (-1: none) and the four tap sums
+    int poff = -1;
+    float2 pa01 = make_float2(0.f, 0.f), pa23 = make_float2(0.f, 0.f);
+    auto process = [&](EventBlock<float, 4, false, PACKED>& e, const int b) {
+      const bool full = b >= lo && b + 4 <= hi;
+      float2 w[4], w01[4], w23[4];
+      int off[4];
+      bool ok = full && use_win;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int lp;
+          if constexpr (PACKED) lp = tile_local_pixel(__float_as_uint(e.x[j]));
+          else lp = (((int)e.x[j] & 31) << 5) | ((int)e.y[j] & 31);
+          const float4 q = pix[lp];
+          const float xo = PACKED ? q.z : e.x[j], yo = PACKED ? q.w : e.y[j];
+          // x' = x - (dt * f) with two roundings (see splat_block_f32)
+          w[j] = make_float2(__fsub_rn(xo, __fmul_rn(e.d[j], q.x)), __fsub_rn(yo, __fmul_rn(e.d[j], q.y)));
+        }
+      } else {
+        e.finish(flow, W, hw);   // item boundary: events of the neighbouring item are marked (x = NaN)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          w[j] = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 wb = add2(w[j], bias2);
+        const float fr = floorf(wb.x), fc = floorf(wb.y);
+        const float2 ab = sub2(w[j], make_float2(fr, fc));
+        const float2 nab = sub2(one2, ab);
+        const float2 lhs = make_float2(nab.x, ab.x);
+        w01[j] = mul2(lhs, make_float2(nab.y, nab.y));
+        w23[j] = mul2(lhs, make_float2(ab.y, ab.y));
+        const int lr = (int)fr + dr, lc = (int)fc + dc;
+        off[j] = lr * kSW + lc;
+        // (a NaN weight fails the first test; a huge coordinate saturates the conversion and fails the range tests)
+        ok = ok && (w01[j].x == w01[j].x) && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1);
+      }
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool same = off[j] == poff;
+          if (!same & (poff >= 0)) flush_run_smem(win, poff, pa01, pa23);
+          const float sel = same ? 1.f : 0.f;                 // 1 * sum + w is one rounding of sum + w
+          pa01 = fma2(make_float2(sel, sel), pa01, w01[j]);
+          pa23 = fma2(make_float2(sel, sel), pa23, w23[j]);
+          poff = off[j];
+        }
+      } else {
+        if (poff >= 0) flush_run_smem(win, poff, pa01, pa23);
+        poff = -1;
+        pa01 = make_float2(0.f, 0.f); pa23 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          splat_event_general(iwe, Hp, Wp, pad_h, pad_w, full ? 0.f : e.x[j], w[j].x, w[j].y, win, r_org, c_org, (int)use_win);
+      }
+    };
+    // two event buffers used alternately: the raw fields of group g+1 are requested before group g is processed
+    EventBlock<float, 4, false, PACKED> ea, eb;
+    ea.load_range32(sx, sy, sd, base, lo, hi);
+#pragma unroll 1
+    for (int g = 0; g < 4; g += 2) {
+      const int b0 = base + 4 * g;
+      if (b0 >= hi) break;
+      if (b0 + 4 < hi) eb.load_range32(sx, sy, sd, b0 + 4, lo, hi);
+      process(ea, b0);
+      if (b0 + 4 >= hi) break;
+      if (g == 0 && b0 + 8 < hi) ea.load_range32(sx, sy, sd, b0 + 8, lo, hi);
+      process(eb, b0 + 4);
+    }
+    if (poff >= 0) flush_run_smem(win, poff, pa01, pa23);
+  }
+  if (use_win) {
+    __syncthreads();
+    // window -> global: coalesced rows of fp32 REDs (an int32 -> fp32 conversion is one rounding)
+    const float inv = 1.0f / (float)(1 << kMergeS);
+    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+      const int v = win[i];
+      if (v != 0) {
+        const int lr = i / kSW, lc = i - lr * kSW;
+        const int r = r_org + lr, c = c_org + lc;
+        if ((unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, (float)v * inv);
+      }
+    }
+  }
+}
+
 // ---- backward ------------------------------------------------------------------------------------
 // GSRC 0: dL/dIWE read from a plane.  GSRC 1: variance objective, dL/dIWE = cv * (IWE - mean)
 // derived on the fly from the IWE itself (saves writing and re-reading a gradient plane).
@@ -1475,6 +1660,160 @@ k_tile_bwd(const float* __restrict__ sx, const float* __restrict__ sy, const flo
   }
 }
 
+// ---- shared-memory tile backward, second version (round 2) ----------------------------------------------------
+// ncu r01g of k_win_bwd_g: L1TEX 52 % busy on 20 M gather sectors, `long_scoreboard` the top stall -- three dependent
+// global latencies per group (event load -> flow gather -> dL/dIWE gather).  Here one CTA takes one work item of the
+// tile sort (like the splat): the dL/dIWE window of the tile (41 x 41, masked and -- for the variance objective --
+// already transformed) and the per-pixel table (flow + float coordinates) are staged in shared memory once, so that
+// both gathers of an event are LDS (the four taps only when the cell changes, lane-predicated), and the only global
+// traffic per event is the prefetched stream itself.  All events of an origin pixel are combined in registers; the
+// per-pixel flush is one pair of global REDs per pixel run.  k_tile_bwd (round 1) lost to the
+// one-shot kernel because of its coarse persistent items, 8 events of state in registers (80 registers) and no prefetch.
+template <int GSRC, bool PACKED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
+             const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
+             int H, int W, int pad_h, int pad_w, const float* __restrict__ g, const double* __restrict__ acc, int omit,
+             double scale, float* __restrict__ dflow) {
+  __shared__ float gwin[kSH * kSW];
+  __shared__ float4 pix[kTileH * kTileW];
+  pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
+  if ((int)blockIdx.x >= hdr->n_items) return;
+  const int4 it = __ldg(items + blockIdx.x);
+  const int lo = it.y, hi = it.z;
+  if (hi <= lo) return;
+  const int hw = H * W;
+  const int tr0 = (it.w >> 16) * kTileH, tc0 = (it.w & 0xffff) * kTileW;
+  const int r_org = tr0 - kHalo + pad_h, c_org = tc0 - kHalo + pad_w;
+  const int dr = pad_h - r_org, dc = pad_w - c_org;
+  fill_pixel_table(pix, flow, tr0, tc0, H, W, hw);
+  const int start = lo & ~3;
+  const int base0 = start + (int)threadIdx.x * 16;
+  EventBlock<float, 4, false, PACKED> ea, eb;
+  if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi);
+  // PDL: everything above overlaps the drain of the preceding cost kernel; dL/dIWE (and, for the variance objective,
+  // the accumulators) are only read below
+  pdl_wait();
+  const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
+  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+    const int lr = i / kSW, lc = i - lr * kSW;
+    gwin[i] = fetch_g<float, GSRC>(g, P.Hp, P.Wp, r_org + lr, c_org + lc, P.vc);
+  }
+  __syncthreads();
+  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
+  for (int base = base0; base < hi; base += (int)blockDim.x * 16) {
+    int poff = -1;                                   // cell whose four dL/dIWE values are in registers
+    float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
+    int pk = -1;                                     // origin pixel of the pending gradient sums
+    float2 s01 = make_float2(0.f, 0.f);
+    auto process = [&](EventBlock<float, 4, false, PACKED>& e, const int b) {
+      const bool full = b >= lo && b + 4 <= hi;
+      float2 w[4], ab[4];
+      float x0[4];
+      int off[4], kk[4];
+      bool inw[4];
+      bool ok = full;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int lp;
+          float xo, yo;
+          if constexpr (PACKED) {
+            const unsigned rc = __float_as_uint(e.x[j]);
+            lp = tile_local_pixel(rc);
+            kk[j] = (int)(rc >> 16) * W + (int)(rc & 0xffffu);
+          } else {
+            const int r = (int)e.x[j], c = (int)e.y[j];
+            lp = ((r & 31) << 5) | (c & 31);
+            kk[j] = r * W + c;
+          }
+          const float4 q = pix[lp];
+          if constexpr (PACKED) { xo = q.z; yo = q.w; } else { xo = e.x[j]; yo = e.y[j]; }
+          x0[j] = xo;
+          w[j] = make_float2(__fsub_rn(xo, __fmul_rn(e.d[j], q.x)), __fsub_rn(yo, __fmul_rn(e.d[j], q.y)));
+        }
+      } else {
+        e.finish(flow, W, hw);   // item boundary: events of the neighbouring item are marked (x = NaN)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          x0[j] = e.x[j];
+          kk[j] = e.k[j];
+          w[j] = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 wb = add2(w[j], bias2);
+        const float fr = floorf(wb.x), fc = floorf(wb.y);
+        ab[j] = sub2(w[j], make_float2(fr, fc));
+        const int lr = (int)fr + dr, lc = (int)fc + dc;
+        off[j] = lr * kSW + lc;
+        // inside the window every tap is either in the image or reads the masked zero the window holds for it;
+        // NaN fractions (non-finite coordinates, marked events) and cells outside the window take the exact path
+        inw[j] = (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1) &&
+                 (ab[j].x + ab[j].y == ab[j].x + ab[j].y);
+        ok = ok && inw[j];
+      }
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (off[j] != poff) {
+            const float* p = gwin + off[j];
+            g00 = p[0]; g01 = p[1]; g10 = p[kSW]; g11 = p[kSW + 1];
+            poff = off[j];
+          }
+          // (dx, dy) = (1-b, 1-a) * (g10-g00, g01-g00) + (b, a) * (g11-g01, g11-g10)
+          const float2 d1 = sub2(make_float2(g10, g01), make_float2(g00, g00));
+          const float2 d2 = sub2(make_float2(g11, g11), make_float2(g01, g10));
+          const float2 ba = make_float2(ab[j].y, ab[j].x);
+          const float2 dxy = fma2(ba, d2, mul2(sub2(one2, ba), d1));
+          const bool same = kk[j] == pk;
+          if (!same & (pk >= 0)) { red_add_nc(dflow + pk, s01.x); red_add_nc(dflow + hw + pk, s01.y); }
+          const float sel = same ? 1.f : 0.f;
+          s01 = fma2(make_float2(-e.d[j], -e.d[j]), dxy, mul2(make_float2(sel, sel), s01));
+          pk = kk[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (x0[j] != x0[j]) continue;   // marked event (belongs to the neighbouring item)
+          float2 dxy;
+          if (inw[j]) {
+            const float* p = gwin + off[j];
+            const float h00 = p[0], h01 = p[1], h10 = p[kSW], h11 = p[kSW + 1];
+            const float2 d1 = sub2(make_float2(h10, h01), make_float2(h00, h00));
+            const float2 d2 = sub2(make_float2(h11, h11), make_float2(h01, h10));
+            const float2 ba = make_float2(ab[j].y, ab[j].x);
+            dxy = fma2(ba, d2, mul2(sub2(one2, ba), d1));
+          } else {
+            float dx, dy;
+            bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, pad_h, pad_w, w[j].x, w[j].y, P.vc, dx, dy);
+            dxy = make_float2(dx, dy);
+          }
+          if (kk[j] != pk) {
+            if (pk >= 0) { red_add_nc(dflow + pk, s01.x); red_add_nc(dflow + hw + pk, s01.y); }
+            pk = kk[j];
+            s01 = make_float2(0.f, 0.f);
+          }
+          s01 = fma2(make_float2(-e.d[j], -e.d[j]), dxy, s01);
+        }
+      }
+    };
+    if (base != base0) ea.load_range32(sx, sy, sd, base, lo, hi);
+#pragma unroll 1
+    for (int gi = 0; gi < 4; gi += 2) {
+      const int b0 = base + 4 * gi;
+      if (b0 >= hi) break;
+      if (b0 + 4 < hi) eb.load_range32(sx, sy, sd, b0 + 4, lo, hi);
+      process(ea, b0);
+      if (b0 + 4 >= hi) break;
+      if (gi == 0 && b0 + 8 < hi) ea.load_range32(sx, sy, sd, b0 + 8, lo, hi);
+      process(eb, b0 + 4);
+    }
+    if (pk >= 0) { red_add_nc(dflow + pk, s01.x); red_add_nc(dflow + hw + pk, s01.y); }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static int key_bits_for(int64_t hw) {
   int bits = 1;
@@ -1584,7 +1923,10 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
     // (measured: a 40-iteration Adam solve at 5 events/pixel ends 1.1e-3 px from the fp64 reference instead of
     // 0.8e-3), so sparse windows keep the fp32 REDs.  EBOS_TILE=4 forces it, 2 the run-combining variant, 3 the
     // grouped kernel.
-    const bool dense = n >= (int64_t)16 * H * W;
+    const bool dense_all = n >= (int64_t)16 * H * W;
+    static const int merge_default = env_int("EBOS_SPLAT_MERGE");   // round-2 kernel as the dense default (A/B knob)
+    const bool dense_merge = dense_all && merge_default == 1;
+    const bool dense = dense_all && !dense_merge;
     if (!has_weight && (tile_env == 4 || (tile_env == 0 && dense))) {
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
@@ -1600,6 +1942,23 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       else { if (occ == 4) EBOS_SD(false, 4); else if (occ == 5) EBOS_SD(false, 5); else EBOS_SD(false, 6); }
 #undef EBOS_SD
       EBOS_LAUNCH_CHECK("ebos_window_splat(tile, direct)");
+      return EBOS_OK;
+    }
+    if (!has_weight && (tile_env == 5 || (tile_env == 0 && dense_merge))) {
+      // run-merging fixed-point tile kernel with the per-pixel table in shared memory (round 2)
+      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
+      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
+      static const int occ_env = env_int("EBOS_QOCC");
+      const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
+      const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd);
+      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
+#define EBOS_SM(P, B) k_tile_splat_m<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
+      if (packed) { if (occ == 3) EBOS_SM(true, 3); else if (occ == 4) EBOS_SM(true, 4); else if (occ == 5) EBOS_SM(true, 5); else EBOS_SM(true, 6); }
+      else { if (occ == 3) EBOS_SM(false, 3); else if (occ == 4) EBOS_SM(false, 4); else if (occ == 5) EBOS_SM(false, 5); else EBOS_SM(false, 6); }
+#undef EBOS_SM
+      EBOS_LAUNCH_CHECK("ebos_window_splat(tile, merge)");
       return EBOS_OK;
     }
     if (!has_weight && tile_env == 2) {
@@ -1746,6 +2105,31 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
              else { if (packed) EBOS_TBWD(0, false, true); else EBOS_TBWD(0, false, false); } }
 #undef EBOS_TBWD
       EBOS_LAUNCH_CHECK("ebos_window_backward(tile)");
+      return EBOS_OK;
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    // second tile backward (round 2): dL/dIWE window + per-pixel table in shared memory, one CTA per work item
+    static const int tbwd_env = env_int("EBOS_TILE_BWD");   // 1 force, 2 default for dense windows (A/B knob)
+    const bool dense = n >= (int64_t)16 * H * W;
+    if (!has_weight && (tbwd_env == 1 || (tbwd_env == 2 && dense && tile_env == 0))) {
+      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
+      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
+      static const int occ_env = env_int("EBOS_BOCC");
+      const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
+      const unsigned qgrid = (unsigned)max_items(n, H, W);
+      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
+      const float* fd = reinterpret_cast<const float*>(sd);
+      const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
+      float* fo = reinterpret_cast<float*>(dflow);
+      cudaError_t le;
+#define EBOS_TBM(G, P, B) le = launch_pdl(k_tile_bwd_m<G, P, B>, dim3(qgrid), dim3(256), st, fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+#define EBOS_TBM_O(G, P) do { if (occ == 3) EBOS_TBM(G, P, 3); else if (occ == 4) EBOS_TBM(G, P, 4); else if (occ == 5) EBOS_TBM(G, P, 5); else EBOS_TBM(G, P, 6); } while (0)
+      if (affine) { if (packed) EBOS_TBM_O(1, true); else EBOS_TBM_O(1, false); }
+      else { if (packed) EBOS_TBM_O(0, true); else EBOS_TBM_O(0, false); }
+#undef EBOS_TBM_O
+#undef EBOS_TBM
+      if (le != cudaSuccess) return cuda_fail(le, "ebos_window_backward(tile, round 2)");
       return EBOS_OK;
     }
   }

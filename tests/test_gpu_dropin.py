@@ -98,7 +98,7 @@ def test_costs_and_hybrid_through_autograd(golden):
         loss = cost.calculate({"iwe": iwe, "flow": flow, "weights": 1.0, "omit_boundary": omit})
         loss.backward()
         assert abs(float(loss) - float(golden[f"{name}/loss"])) <= 1e-5 * abs(float(golden[f"{name}/loss"])), name
-        assert rel_err(flow.grad.cpu().numpy(), golden[f"{name}/grad"]) <= 2e-5, name
+        assert rel_err(flow.grad.cpu().numpy(), golden[f"{name}/grad"]) <= 1e-5, name
         hist = cost.get_history()
         assert len(hist["loss"]) == 1 and len(hist[kind]) == 1 and len(hist["image_gradient"]) == 1
     # direction handling of the individual costs

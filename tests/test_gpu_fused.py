@@ -83,12 +83,13 @@ def test_packed_and_generic_layouts_agree(ops):
         assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", ["default", "tileq", "tiled", "grouped", "tile", "pipe", "oneshot"])
+@pytest.mark.parametrize("mode", ["default", "tileq", "tiled", "tilem", "grouped", "tile", "pipe", "oneshot"])
 def test_all_streaming_kernel_variants_match_oracle(mode):
     """The fused fp32 path has several kernel families for the event stream: the default (fixed-point shared-memory
     tile splat for dense windows, grouped one-shot kernels otherwise; "tileq" forces the former and "grouped" the
     latter for every window), the legacy one-shot kernels (also the fp64 path), and two opt-in experiments
-    (float shared-memory tile kernels, persistent TMA-staged kernels).  Each is forced on in a fresh process and must match the oracle on small
+    (float shared-memory tile kernels, persistent TMA-staged kernels); "tilem" forces the round-2 tile kernels (run-merging
+    fixed-point splat + shared-memory backward) for every window.  Each is forced on in a fresh process and must match the oracle on small
     windows incl. ragged tails, multi-item tiles, padding, weights, packed and generic layouts."""
     import json
     import os
@@ -96,7 +97,8 @@ def test_all_streaming_kernel_variants_match_oracle(mode):
     import sys
 
     env = dict(os.environ)
-    env.update({"default": {}, "tileq": {"EBOS_TILE": "2"}, "tiled": {"EBOS_TILE": "4"}, "grouped": {"EBOS_TILE": "3"}, "tile": {"EBOS_TILE": "1"},
+    env.update({"default": {}, "tileq": {"EBOS_TILE": "2"}, "tiled": {"EBOS_TILE": "4"},
+                "tilem": {"EBOS_TILE": "5", "EBOS_TILE_BWD": "1"}, "grouped": {"EBOS_TILE": "3"}, "tile": {"EBOS_TILE": "1"},
                 "pipe": {"EBOS_PIPE": "1"},
                 "oneshot": {"EBOS_GROUPS": "-1"}}[mode])
     script = os.path.join(os.path.dirname(__file__), "pipe_check.py")
@@ -105,7 +107,7 @@ def test_all_streaming_kernel_variants_match_oracle(mode):
     out = json.loads(res.stdout.strip().splitlines()[-1])
     assert len(out) == 24
     for key, (e_iwe, e_grad, e_loss) in out.items():
-        assert e_iwe <= REL and e_grad <= 2 * REL and e_loss <= REL, (mode, key, e_iwe, e_grad, e_loss)
+        assert e_iwe <= REL and e_grad <= REL and e_loss <= REL, (mode, key, e_iwe, e_grad, e_loss)
 
 
 def test_invalid_events_are_skipped_when_not_validating(ops):
@@ -166,7 +168,7 @@ def test_value_and_grad_vs_oracle(ops, cost, omit, pad):
     win = ops.PreparedWindow(ev.cuda(), (H, W), "first", True)
     loss, grad = ops.cmax_value_and_grad(win, flow.cuda(), cost, 1.0, 0.5, None, omit, (pad, pad))
     assert abs(float(loss) - float(ref_loss)) <= REL * abs(float(ref_loss))
-    assert rel_err(grad.cpu().numpy(), ref_grad.numpy()) <= 2 * REL
+    assert rel_err(grad.cpu().numpy(), ref_grad.numpy()) <= REL
     # and the CUDA result is at least as close to the fp64 truth as the fp32 reference path is
     e_cuda = rel_err(grad.cpu().numpy(), tru_grad.numpy())
     e_ref = rel_err(ref_grad.numpy(), tru_grad.numpy())
@@ -184,9 +186,9 @@ def test_value_and_grad_vs_reference_golden(golden, ops):
         loss, grad = ops.cmax_value_and_grad(win, flow, kind, 1.0, float(tvw), None, omit, (pad, pad))
         # goldens 0-3 are fp64 reference runs: fp32 inputs differ by rounding, so the bar is looser there
         f32 = golden[f"{name}/events"].dtype == np.float32
-        tol = 2 * REL if f32 else 5e-4
+        tol = REL if f32 else 5e-4
         assert abs(float(loss) - float(golden[f"{name}/loss"])) <= tol * abs(float(golden[f"{name}/loss"])), name
-        assert rel_err(grad.cpu().numpy(), golden[f"{name}/grad"]) <= (2 * REL if f32 else 5e-3), name
+        assert rel_err(grad.cpu().numpy(), golden[f"{name}/grad"]) <= (REL if f32 else 5e-3), name
 
 
 def test_peer_plane_cost_and_sum_match_the_reduced_plane(ops):
@@ -257,7 +259,7 @@ def test_weighted_window_and_tv_weights(ops):
     assert rel_err(ops.window_splat(win, flow.cuda()).cpu().numpy(), iwe.detach().numpy()) <= REL
     loss, grad = ops.cmax_value_and_grad(win, flow.cuda(), "gradient_magnitude", 2.0, 0.3, tvw.cuda())
     assert abs(float(loss) - float(ref)) <= REL * abs(float(ref))
-    assert rel_err(grad.cpu().numpy(), f.grad.numpy()) <= 2 * REL
+    assert rel_err(grad.cpu().numpy(), f.grad.numpy()) <= REL
 
 
 def test_cost_and_tv_kernels_vs_golden(golden, ops):
@@ -397,6 +399,35 @@ def test_dense_window_fixed_point_splat_at_benchmark_size(ops):
     assert abs(big - n) / n < 1e-6
     loss, grad = ops.cmax_value_and_grad(win, flow, "gradient_magnitude", 1.0, 0.5)
     assert torch.isfinite(grad).all() and torch.isfinite(loss).all()
+
+
+@pytest.mark.parametrize("cost", ["gradient_magnitude", "image_variance"])
+def test_benchmark_window_loss_and_gradient_vs_oracle(ops, cost):
+    """THE configuration bench.py is quoted on (BASELINE config 2 at its largest size: 1280x720, 16 Mi events, flow
+    U(-3,3), objective + 0.5 TV): loss and dL/dflow of the fused CUDA path against the CPU oracle on the same inputs --
+    the fp32 restatement of the reference's torch ops (bar: 1e-5 relative, north_star) and the fp64 truth (the CUDA
+    result must be no further from it than the fp32 reference path is, up to the same bar)."""
+    H, W, n = 720, 1280, 1 << 24
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=0))
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=0))
+    win = ops.PreparedWindow(ev.cuda(), (H, W), "first", True)
+    assert win.packed and n >= 16 * H * W
+    loss, grad = ops.cmax_value_and_grad(win, flow.cuda(), cost, 1.0, 0.5)
+    loss, grad = float(loss), grad.cpu().numpy().copy()
+    iwe = ops.window_splat(win, flow.cuda()).cpu().numpy().copy()
+    del win
+    torch.cuda.empty_cache()
+    kw = dict(cost=cost, tv_weight=0.5, data_weight=1.0)
+    ref_loss, ref_grad = spec.cmax_value_and_grad(ev, flow, (H, W), **kw)                     # fp32 oracle
+    ref_iwe = spec.bilinear_vote(spec.warp_dense_flow(ev, flow, (H, W)), (H, W)).numpy()
+    e_iwe, e_loss, e_grad = rel_err(iwe, ref_iwe), abs(loss - float(ref_loss)) / abs(float(ref_loss)), rel_err(grad, ref_grad.numpy())
+    print(f"[16 Mi {cost}] vs fp32 oracle: iwe {e_iwe:.2e} loss {e_loss:.2e} grad {e_grad:.2e}")
+    assert e_iwe <= REL and e_loss <= REL and e_grad <= REL, (e_iwe, e_loss, e_grad)
+    tru_loss, tru_grad = spec.cmax_value_and_grad(ev.double(), flow.double(), (H, W), **kw)   # fp64 truth
+    t_loss, t_grad = abs(loss - float(tru_loss)) / abs(float(tru_loss)), rel_err(grad, tru_grad.numpy())
+    r_grad = rel_err(ref_grad.numpy(), tru_grad.numpy())
+    print(f"[16 Mi {cost}] vs fp64 truth: loss {t_loss:.2e} grad {t_grad:.2e} (fp32 reference path: grad {r_grad:.2e})")
+    assert t_loss <= REL and t_grad <= max(2 * r_grad, REL)
 
 
 def test_fp64_value_and_grad_vs_reference_golden(golden, ops):

@@ -147,7 +147,7 @@ def test_edge_cases(ops):
     assert float(ops.iwe_splat(far, (4, 4), deterministic=True).abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 1e-5)])
 def test_autograd_of_operators_vs_oracle(ops, dtype, tol):
     """d(loss)/d(flow) through warp_dense_flow -> iwe_splat, CUDA analytic backward vs torch autograd
     on the oracle ops."""

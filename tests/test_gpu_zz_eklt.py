@@ -171,6 +171,36 @@ def test_benchmark_size_properties(eklt):
     assert float(loss[0]) == 0.0 and float(grad.abs().max()) == 0.0
 
 
+def test_benchmark_size_value_and_grad_vs_torch_oracle(eklt):
+    """1280x720 with the hot_plate1 ROI (rows 0:720, cols 320:960) -- the size `bench.py --workload eklt` runs, where
+    12 patches x 64 = 768 != 720 puts the up-sampled fields 24 rows off the patch lattice (a quirk the 112x176 goldens
+    cannot show): objective and gradient at ALL FOUR pyramid levels against `oracle/spec_eklt_torch.py`, the reference's
+    own torch op sequence differentiated by autograd (float64)."""
+    from oracle import spec_eklt_torch as TT
+
+    rng = np.random.default_rng(11)
+    H, W, roi = 720, 1280, (0, 720, 320, 960)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frame = 120 + 60 * np.sin(xx / 11.0) * np.cos(yy / 7.0) + rng.normal(0, 2, (H, W))
+    gx, gy = E.frame_gradients(frame)
+    M = E.roi_mask((H, W), roi)
+    meas = rng.normal(size=(H, W)) * M
+    meas /= np.linalg.norm(meas)
+    winv = rng.uniform(0.05, 1.0, (H, W))
+    w = (1.0, 0.5, 0.1)
+    prob = eklt.EkltProblem(dev(gx), dev(gy), dev(meas), dev(winv), roi, w)
+    planes = [torch.from_numpy(np.ascontiguousarray(a)).double() for a in (gx, gy, meas, winv)]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for patch, ph, pw in eklt.pyramid_levels((H, W)):
+        th = np.concatenate([rng.uniform(-1, 1, (1, ph, pw)), rng.uniform(-1.5, 1.5, (2, ph, pw))])
+        ref_loss, ref_grad = TT.value_and_grad(torch.from_numpy(th), *planes, roi, patch, *w)
+        loss, grad = prob.level(patch).value_and_grad(dev(th))
+        e_l = abs(float(loss[0]) - ref_loss) / abs(ref_loss)
+        e_g = rel(grad.cpu().numpy(), ref_grad.numpy())
+        print(f"[eklt 1280x720 patch {patch}] loss rel {e_l:.2e} grad rel {e_g:.2e}")
+        assert e_l <= 1e-10 and e_g <= 1e-8, (patch, e_l, e_g)
+
+
 def test_preprocessing_matches_reference(gold, eklt):
     gx, gy = eklt.frame_gradients(dev(gold["frame"].astype(np.float64)))
     assert np.array_equal(gx.cpu().numpy(), gold["grad_x"])       # integers: exact
