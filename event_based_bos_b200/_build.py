@@ -16,7 +16,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libebos.so")
-SOURCES = ["ebos_ops.cu", "ebos_window.cu", "ebos_costs.cu", "ebos_ingest.cu", "ebos_eklt.cu"]
+SOURCES = ["ebos_ops.cu", "ebos_window.cu", "ebos_costs.cu", "ebos_ingest.cu", "ebos_eklt.cu", "ebos_metrics.cu"]
 HEADERS = ["ebos_common.cuh", "ebos_eklt_math.cuh", os.path.join("..", "..", "include", "ebos.h")]
 
 NVCC_FLAGS = [
@@ -51,6 +51,7 @@ def is_stale() -> bool:
         return True
     t = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    deps.append(os.path.abspath(__file__))   # the source list and the flags live here
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

@@ -84,6 +84,10 @@ SIGNATURES = {
     "ebos_eklt_patch_flow": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ebos_sepconv2d": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),
+    "ebos_flow_error_workspace_doubles": (c_size_t, [c_int]),
+    "ebos_flow_error": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    "ebos_blur3": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

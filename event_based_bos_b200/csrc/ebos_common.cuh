@@ -295,7 +295,8 @@ inline int64_t max_items(int64_t n, int H, int W) { return n / kItemEvents + (in
 struct WindowLayout {
   size_t off_x, off_y, off_d, off_w, off_perm, off_tiles, off_items, total;
 };
-// events sorted by (tile, pixel-in-tile, time); tile_off[t] = first event of tile t; items = int4 (tile, begin, end, 0)
+// events sorted by (tile, pixel-in-tile, time); tile_off[t] = first event of tile t;
+// items = int4 (first | last << 16 tile-local pixel, begin, end, tile row << 16 | tile col)
 inline WindowLayout window_layout(int64_t n, size_t elem, int H, int W) {
   WindowLayout L;
   size_t a = align256((size_t)n * elem);

@@ -142,7 +142,10 @@ __global__ void __launch_bounds__(256) k_win_tile_offsets(const unsigned int* __
 // Work items (tile, begin, end): every tile's event range cut EVENLY into ceil(len / kItemEvents) pieces (piece
 // length rounded up to a multiple of 16), so that the items of a busy tile carry the same load.
 // One CTA: per-tile item counts, block-wide exclusive scan (looped), fill.
+// items[i] = (first | last << 16 tile-local pixel of the piece, begin, end, tile row << 16 | tile col): the tile kernels
+// stage only the rows of the tile (flow table, IWE / dL/dIWE window) that the piece's origin pixels can reach.
 __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int tiles_per_row,
+                                                    const unsigned int* __restrict__ sorted_keys,
                                                     int4* __restrict__ items, WindowHeader* __restrict__ h) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
@@ -169,7 +172,15 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
     const int excl = carry + (wid ? warp_sums[wid - 1] : 0) + v - cnt;
     const int piece = cnt ? ((((e - b) + cnt - 1) / cnt + 15) & ~15) : 0;   // <= kItemEvents (a multiple of 16)
     const int tcoord = ((t / tiles_per_row) << 16) | (t % tiles_per_row);   // (tile row, tile col) for the tile kernels
-    for (int i = 0; i < cnt; ++i) items[excl + i] = make_int4(t, min(b + i * piece, e), min(b + (i + 1) * piece, e), tcoord);
+    for (int i = 0; i < cnt; ++i) {
+      const int pb = min(b + i * piece, e), pe = min(b + (i + 1) * piece, e);
+      int range = 0;
+      if (pe > pb) {
+        const unsigned int lp0 = __ldg(sorted_keys + pb) & (kTileH * kTileW - 1), lp1 = __ldg(sorted_keys + pe - 1) & (kTileH * kTileW - 1);
+        range = (int)(lp0 | (lp1 << 16));
+      }
+      items[excl + i] = make_int4(range, pb, pe, tcoord);
+    }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = excl + cnt;
     __syncthreads();
@@ -775,91 +786,6 @@ constexpr int kHalo = 4;
 constexpr int kSH = kTileH + 2 * kHalo + 1;   // window rows  (taps reach one past the last cell)
 constexpr int kSW = kTileW + 2 * kHalo + 1;   // window cols; 41 is odd: consecutive rows start in different banks
 
-__device__ __forceinline__ void tile_origin(int tile, int W, int pad_h, int pad_w, int& r_org, int& c_org) {
-  const int tx = (W + kTileW - 1) / kTileW;
-  r_org = (tile / tx) * kTileH - kHalo + pad_h;   // padded-image coordinates of window element (0,0)
-  c_org = (tile % tx) * kTileW - kHalo + pad_w;
-}
-
-template <bool HAS_W, bool PACKED>
-__global__ void __launch_bounds__(256, 4)
-k_tile_splat(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
-             const float* __restrict__ sw, const int4* __restrict__ items, const WindowHeader* __restrict__ hdr,
-             const float* __restrict__ flow, int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
-  constexpr int EPT = 8;
-  __shared__ float win[kSH * kSW];
-  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, Hm1 = Hp - 1, Wm1 = Wp - 1, hw = H * W;
-  const int n_items = hdr->n_items;
-  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int4 it = __ldg(items + item);
-    int r_org, c_org;
-    tile_origin(it.x, W, pad_h, pad_w, r_org, c_org);
-    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0.f;
-    __syncthreads();
-    // one run (cell + four tap sums) goes to the shared window when all four taps are inside it
-    auto flush = [&](float cfr, float cfc, float2 a01, float2 a23) {
-      const int r = (int)cfr + pad_h, c = (int)cfc + pad_w;
-      const int lr = r - r_org, lc = c - c_org;
-      if ((unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1)) {
-        float* p = win + lr * kSW + lc;
-        atomicAdd(p, a01.x);            // (r  , c  )
-        atomicAdd(p + kSW, a01.y);      // (r+1, c  )
-        atomicAdd(p + 1, a23.x);        // (r  , c+1)
-        atomicAdd(p + kSW + 1, a23.y);  // (r+1, c+1)
-      } else {
-        flush_cell<float, false>(iwe, Hp, Wp, Hm1, Wm1, r, c, a01.x, a01.y, a23.x, a23.y);
-      }
-    };
-    const int64_t start = (int64_t)it.y & ~(int64_t)(EPT - 1);
-    for (int64_t base = start + (int64_t)threadIdx.x * EPT; base < it.z; base += (int64_t)blockDim.x * EPT) {
-      EventBlock<float, EPT, HAS_W, PACKED> e;
-      e.load_range(sx, sy, sd, sw, base, it.y, it.z);
-      e.finish(flow, W, hw);
-      float cfr = NAN, cfc = 0.f;
-      float2 a01 = zero2, a23 = zero2;
-#pragma unroll
-      for (int j = 0; j < EPT; ++j) {
-        // x' = x - (dt * f) with two roundings (see splat_block_f32)
-        const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
-        const float2 wb = add2(w, bias2);
-        const float fr = floorf(wb.x), fc = floorf(wb.y);
-        const float2 ab = sub2(w, make_float2(fr, fc));
-        const float2 nab = sub2(one2, ab);
-        const float2 lhs = make_float2(nab.x, ab.x);
-        float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
-        float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
-        if (w01.x != w01.x) {
-          splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, HAS_W ? e.wt[j] : 1.f);
-          continue;
-        }
-        if (HAS_W) {
-          const float2 ww = make_float2(e.wt[j], e.wt[j]);
-          w01 = mul2(w01, ww);
-          w23 = mul2(w23, ww);
-        }
-        if (!((fr == cfr) & (fc == cfc))) {
-          if (cfr == cfr) flush(cfr, cfc, a01, a23);
-          cfr = fr; cfc = fc;
-          a01 = zero2; a23 = zero2;
-        }
-        a01 = add2(a01, w01);
-        a23 = add2(a23, w23);
-      }
-      if (cfr == cfr) flush(cfr, cfc, a01, a23);
-    }
-    __syncthreads();
-    // window -> global (coalesced rows; windows of neighbouring tiles / items overlap, hence REDs)
-    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
-      const float v = win[i];
-      const int lr = i / kSW, lc = i - lr * kSW;
-      const int r = r_org + lr, c = c_org + lc;
-      if (v != 0.f && (unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, v);
-    }
-    __syncthreads();
-  }
-}
-
 // ---- shared-memory tile splat with FIXED-POINT accumulation (fp32 default for dense windows) -----------
 // Shared-memory float atomics are a CAS loop on sm_100a, integer ATOMS.ADD is native and 8x cheaper per lane than
 // a global RED (0.14 vs 1.15 SM-cycles, profiles/microbench/r01_red_throughput.txt).  One CTA takes one work item
@@ -875,88 +801,6 @@ k_tile_splat(const float* __restrict__ sx, const float* __restrict__ sy, const f
 // non-finite events take the global fp32 path, so correctness never depends on the halo.  Items with fewer than
 // kWinMinEvents events skip the window (zero + flush of 1681 cells would cost more than their REDs).
 constexpr int kWinMinEvents = 1024;
-
-template <bool PACKED, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k_tile_splat_q(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
-               const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
-               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
-  __shared__ int win[kSH * kSW];
-  if ((int)blockIdx.x >= hdr->n_items) return;
-  const int4 it = __ldg(items + blockIdx.x);
-  const int cnt = it.z - it.y;
-  if (cnt <= 0) return;
-  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
-  const bool use_win = cnt >= kWinMinEvents;
-  int r_org, c_org;
-  tile_origin(it.x, W, pad_h, pad_w, r_org, c_org);
-  const int S = min(24, 30 - (31 - __clz(cnt)));
-  const float qs = __int_as_float((127 + S) << 23);
-  if (use_win) {
-    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0;
-    __syncthreads();
-  }
-  auto flush = [&](const SplatRun& run) {
-    const int r = (int)run.cfr + pad_h, c = (int)run.cfc + pad_w;
-    const int lr = r - r_org, lc = c - c_org;
-    if (use_win && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1)) {
-      int* p = win + lr * kSW + lc;
-      atomicAdd(p, __float2int_rn(run.a01.x * qs));            // (r  , c  )
-      atomicAdd(p + kSW, __float2int_rn(run.a01.y * qs));      // (r+1, c  )
-      atomicAdd(p + 1, __float2int_rn(run.a23.x * qs));        // (r  , c+1)
-      atomicAdd(p + kSW + 1, __float2int_rn(run.a23.y * qs));  // (r+1, c+1)
-    } else {
-      flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, r, c, run.a01.x, run.a01.y, run.a23.x, run.a23.y);
-    }
-  };
-  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
-  const int64_t start = (int64_t)it.y & ~(int64_t)3;
-  for (int64_t base = start + (int64_t)threadIdx.x * 16; base < it.z; base += (int64_t)blockDim.x * 16) {
-    SplatRun run{NAN, 0.f, make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-      const int64_t b = base + 4 * g;
-      if (b >= it.z) break;
-      EventBlock<float, 4, false, PACKED> e;
-      e.load_range(sx, sy, sd, nullptr, b, it.y, it.z);
-      e.finish(flow, W, hw);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // x' = x - (dt * f) with two roundings (see splat_block_f32)
-        const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
-        const float2 wb = add2(w, bias2);
-        const float fr = floorf(wb.x), fc = floorf(wb.y);
-        const float2 ab = sub2(w, make_float2(fr, fc));
-        const float2 nab = sub2(one2, ab);
-        const float2 lhs = make_float2(nab.x, ab.x);
-        const float2 w01 = mul2(lhs, make_float2(nab.y, nab.y));
-        const float2 w23 = mul2(lhs, make_float2(ab.y, ab.y));
-        if (w01.x != w01.x) {
-          splat_event_exact<float>(iwe, Hp, Wp, pad_h, pad_w, e.x[j], w.x, w.y, 1.f);
-          continue;
-        }
-        if (!((fr == run.cfr) & (fc == run.cfc))) {
-          if (run.cfr == run.cfr) flush(run);
-          run.cfr = fr; run.cfc = fc;
-          run.a01 = make_float2(0.f, 0.f); run.a23 = make_float2(0.f, 0.f);
-        }
-        run.a01 = add2(run.a01, w01);
-        run.a23 = add2(run.a23, w23);
-      }
-    }
-    if (run.cfr == run.cfr) flush(run);
-  }
-  if (!use_win) return;
-  __syncthreads();
-  // window -> global: coalesced rows of fp32 REDs (the conversion of an int32 < 2^31 to fp32 is one rounding)
-  const float inv = __int_as_float((127 - S) << 23);
-  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
-    const int v = win[i];
-    const int lr = i / kSW, lc = i - lr * kSW;
-    const int r = r_org + lr, c = c_org + lc;
-    if (v != 0 && (unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, (float)v * inv);
-  }
-}
 
 // Direct variant: NO run tracking.  The divergent "cell changed -> flush" branch of the run-combining kernels is
 // executed by a warp at almost every event step (one lane in four flushes), so its ~25 instructions are paid
@@ -1081,31 +925,30 @@ k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const
   }
 }
 
-// ---- run-merging fixed-point tile splat (round 2) --------------------------------------------------------
-// ncu r01g of k_tile_splat_d: the kernel is bound by shared-memory ATOMIC WAVEFRONTS, not by bytes or issue slots:
-// 8.83 M wavefronts for 2.36 M ATOMS warp instructions (the +-3 px random flow sends the 32 lanes of an instruction
-// to random banks: ~3.7-way conflicts) at ~2 cycles per wavefront = 60 of its 72 us.  Two changes:
-//  * Consecutive events of a thread belong to one origin pixel and are time ordered, so they stay in one IWE cell for
-//    runs of ~5 events.  The run's four tap sums are kept in registers and added to the window only when the cell
-//    changes -- WITHOUT a divergent branch (which is what sank k_tile_splat_q: a warp takes the flush branch at nearly
-//    every step because some lane always flushes): the fixed-point conversion is executed unconditionally and the four
-//    `red.shared` are PREDICATED per lane.  An instruction whose predicate is true in ~8 of 32 lanes conflicts ~1.7-way
-//    instead of 3.7-way: half the wavefronts for +4 issue slots per event.
-//  * The flow at the tile's 1024 origin pixels, together with the pixel coordinates as floats, is staged in shared
-//    memory once per CTA (16 KB): the per-event flow gather is one conflict-free LDS.128 (lanes of a warp read the same
-//    few pixels: broadcast) instead of two dependent global loads behind a "pixel changed" branch, and the two
-//    int -> float conversions of the origin coordinates disappear.
-// A run is at most the 16 events of a thread: |sum| <= 16 * (1 + 2e-6), so S = 17 keeps sum * 2^S below 2^22 (the range of
-// the fma(w, 2^S, 1.5 * 2^23) conversion) and 4080 * 2^17 below 2^31 (window overflow).  One rounding of <= 2^-18 per
-// FLUSHED tap sum (a quarter as many roundings as k_tile_splat_d makes, each four times larger).
-constexpr int kMergeS = 17;
+// ---- fixed-point tile splat, second version (round 2) --------------------------------------------------------
+// SASS of k_tile_splat_d: of its ~69 instructions per event, ~25 are the origin-pixel unpack + the "gather the flow only
+// when the pixel changes" branch ladder (two dependent global loads behind it), ~7 the zero-fill and flush of the whole
+// 41 x 41 window per 4080-event item, 2 the register copies of the software pipeline.  This version
+//  * stages the flow at the item's origin pixels, together with the pixel coordinates as floats, in shared memory
+//    once per CTA: the per-event gather is ONE conflict-free LDS.128 (the lanes of a warp read the same few pixels:
+//    broadcast) and the two int -> float conversions disappear;
+//  * knows the item's pixel range (prepare stores first | last << 16 tile-local pixel in the item descriptor): an
+//    item of ~224 pixels spans ~7 of the 32 tile rows, so only rows [row0, row1 + 2 * halo + 2) of the window are
+//    zeroed, addressable and flushed, and only the item's pixels are put into the table;
+//  * requests its first event group BEFORE that set-up, so that the DRAM latency of the stream and the L2 latency of
+//    the table overlap; two register buffers used alternately replace the copies;
+//  * converts to fixed point on packed FFMA2.
+// MERGE = true additionally keeps the four tap sums of a run of events that stay in one IWE cell in registers and adds
+// them to the window when the cell changes.  ncu r01g blamed shared-memory atomic wavefronts (8.83 M for 2.36 M ATOMS:
+// the +-3 px random flow sends the 32 lanes to random banks); merging halves them, but ptxas never predicates ATOMS on
+// sm_100a (a predicated `red.shared` becomes one BSSY / BRA / BSYNC region per instruction), a warp takes the flush
+// branch at nearly every event step, and the kernel turned out to be bound by issue slots, not by wavefronts: measured
+// on B200 at 16 Mi events 84 us against 72 us (profiles/README.md, round 2).  Kept as an A/B knob (EBOS_TILE=6).
+constexpr int kMergeS = 17;   // a merged run is at most the 16 events of a thread: 16 * (1 + 2e-6) * 2^17 < 2^22
 
-// the four tap sums of a finished run -> fixed point -> window (no-return shared-memory reductions).  The caller
-// branches around the call: ptxas never predicates ATOMS on sm_100a (a predicated `red.shared` in inline PTX becomes
-// one BSSY / BRA / BSYNC region PER instruction), so the four reductions share one branch region.
-__device__ __forceinline__ void flush_run_smem(int* __restrict__ win, int off, float2 a01, float2 a23) {
-  const float M = 12582912.0f;   // 1.5 * 2^23
-  const float qs = (float)(1 << kMergeS);
+// four tap values of one cell -> fixed point (scale qs = 2^S) -> window
+__device__ __forceinline__ void taps_to_window(int* __restrict__ win, int off, float2 a01, float2 a23, float qs) {
+  const float M = 12582912.0f;   // 1.5 * 2^23: fma(w, 2^S, M) leaves round(w * 2^S) in the low mantissa bits
   const float2 q01 = fma2(a01, make_float2(qs, qs), make_float2(M, M));
   const float2 q23 = fma2(a23, make_float2(qs, qs), make_float2(M, M));
   int* p = win + off;
@@ -1118,22 +961,42 @@ __device__ __forceinline__ void flush_run_smem(int* __restrict__ win, int off, f
 // tile-local index of an origin pixel from the packed (row << 16 | col) word: (row % 32) * 32 + col % 32
 __device__ __forceinline__ int tile_local_pixel(unsigned rc) { return (int)(((rc >> 11) & 0x3e0u) | (rc & 31u)); }
 
-// (f0, f1, row, col) of the tile's origin pixels -> shared memory (pixels outside the image: zeros, never addressed)
-__device__ __forceinline__ void fill_pixel_table(float4* __restrict__ pix, const float* __restrict__ flow, int tr0, int tc0,
+// Geometry of one work item: event range, tile origin, window origin, and the rows of the window its pixels can reach.
+struct ItemGeom {
+  int lo, hi;          // events [lo, hi) of the sorted stream
+  int tr0, tc0;        // image coordinates of the tile's first pixel
+  int r_org, c_org;    // padded-image coordinates of window element (0, 0)
+  int lp0, lp1;        // first / last tile-local origin pixel of the item
+  int row0, nrows;     // window rows [row0, row0 + nrows) are in use (cells: one row fewer)
+};
+__device__ __forceinline__ ItemGeom item_geom(const int4 it, int pad_h, int pad_w) {
+  ItemGeom g;
+  g.lo = it.y; g.hi = it.z;
+  g.tr0 = (it.w >> 16) * kTileH; g.tc0 = (it.w & 0xffff) * kTileW;
+  g.r_org = g.tr0 - kHalo + pad_h; g.c_org = g.tc0 - kHalo + pad_w;
+  g.lp0 = it.x & 0xffff; g.lp1 = (int)((unsigned)it.x >> 16);
+  g.row0 = g.lp0 >> 5;
+  g.nrows = (g.lp1 >> 5) - g.row0 + 2 * kHalo + 2;
+  return g;
+}
+
+// (f0, f1, row, col) of the item's origin pixels -> shared memory
+__device__ __forceinline__ void fill_pixel_table(float4* __restrict__ pix, const float* __restrict__ flow, const ItemGeom& g,
                                                  int H, int W, int hw) {
-  for (int i = threadIdx.x; i < kTileH * kTileW; i += blockDim.x) {
-    const int r = tr0 + (i >> 5), c = tc0 + (i & 31);
+  for (int i = g.lp0 + (int)threadIdx.x; i <= g.lp1; i += blockDim.x) {
+    const int r = g.tr0 + (i >> 5), c = g.tc0 + (i & 31);
     const bool in = r < H && c < W;
     const int k = in ? r * W + c : 0;
     pix[i] = make_float4(in ? __ldg(flow + k) : 0.f, in ? __ldg(flow + hw + k) : 0.f, (float)r, (float)c);
   }
 }
 
-// One event outside the regular case of k_tile_splat_m (item boundary, cell outside the window, non-finite, item too
-// small for the window): same arithmetic as the fast path, recomputed from the warped coordinate so that the fast path
-// keeps nothing alive for it.  x0 = NaN marks an event that belongs to the neighbouring item.
+// One event outside the regular case of the tile splat (item boundary, cell outside the window rows in use, non-finite,
+// item too small for the window): same arithmetic as the fast path, recomputed from the warped coordinate so that the
+// fast path keeps nothing alive for it.  x0 = NaN marks an event that belongs to the neighbouring item.
 __device__ __noinline__ void splat_event_general(float* __restrict__ iwe, int Hp, int Wp, int pad_h, int pad_w, float x0,
-                                                 float xw, float yw, int* __restrict__ win, int r_org, int c_org, int use_win) {
+                                                 float xw, float yw, int* __restrict__ win, int r_org, int c_org, int row0,
+                                                 int nrows, float qs) {
   if (x0 != x0) return;
   const float2 w = make_float2(xw, yw);
   const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
@@ -1149,13 +1012,13 @@ __device__ __noinline__ void splat_event_general(float* __restrict__ iwe, int Hp
   }
   const int r = (int)fr + pad_h, c = (int)fc + pad_w;
   const int lr = r - r_org, lc = c - c_org;
-  if (use_win && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1))
-    flush_run_smem(win, lr * kSW + lc, w01, w23);
+  if (nrows > 0 && (unsigned)(lr - row0) < (unsigned)(nrows - 1) && (unsigned)lc < (unsigned)(kSW - 1))
+    taps_to_window(win, lr * kSW + lc, w01, w23, qs);
   else
     flush_cell<float, false>(iwe, Hp, Wp, Hp - 1, Wp - 1, r, c, w01.x, w01.y, w23.x, w23.y);
 }
 
-template <bool PACKED, int MINB>
+template <bool PACKED, int MINB, bool MERGE>
 __global__ void __launch_bounds__(256, MINB)
 k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
                const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
@@ -1164,28 +1027,35 @@ k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const
   __shared__ float4 pix[kTileH * kTileW];
   pdl_launch_dependents();   // the cost kernel may be scheduled while this grid drains (it waits before reading the IWE)
   if ((int)blockIdx.x >= hdr->n_items) return;
-  const int4 it = __ldg(items + blockIdx.x);
-  const int lo = it.y, hi = it.z;
+  ItemGeom g = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);
+  const int lo = g.lo, hi = g.hi;
   if (hi <= lo) return;
+  const int base0 = (lo & ~3) + (int)threadIdx.x * 16;
+  // two event buffers used alternately: the raw fields of group g+1 are requested before group g is processed; the very
+  // first group is requested before the set-up below
+  EventBlock<float, 4, false, PACKED> ea, eb;
+  if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi);
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
-  const int tr0 = (it.w >> 16) * kTileH, tc0 = (it.w & 0xffff) * kTileW;
-  const int r_org = tr0 - kHalo + pad_h, c_org = tc0 - kHalo + pad_w;
-  const int dr = pad_h - r_org, dc = pad_w - c_org;          // window coordinates = floor + (dr, dc)
-  const bool use_win = hi - lo >= kWinMinEvents;
-  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) win[i] = 0;
-  fill_pixel_table(pix, flow, tr0, tc0, H, W, hw);
+  if (hi - lo < kWinMinEvents) g.nrows = 0;                  // small item: every event takes the global path
+  const int cnt_log = 31 - __clz(hi - lo);
+  const int S = MERGE ? kMergeS : min(21, 30 - cnt_log);     // the int32 window cannot overflow: cnt * 2^S < 2^31
+  const float qs = __int_as_float((127 + S) << 23);
+  for (int i = threadIdx.x; i < g.nrows * kSW; i += blockDim.x) win[g.row0 * kSW + i] = 0;
+  fill_pixel_table(pix, flow, g, H, W, hw);
   __syncthreads();
-  const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
-  const int start = lo & ~3;
-  for (int base = start + (int)threadIdx.x * 16; base < hi; base += (int)blockDim.x * 16) {
-    // pending run: window offset of its cell (-1: none) and the four tap sums
+  const int dr = pad_h - g.r_org - g.row0, dc = pad_w - g.c_org;   // (cell row relative to row0, cell column) = floor + (dr, dc)
+  const unsigned span = (unsigned)max(g.nrows - 1, 0);
+  const int off0 = g.row0 * kSW;
+  const float2 bias2 = make_float2(1e-6f, 1e-6f);
+  for (int base = base0; base < hi; base += (int)blockDim.x * 16) {
+    // MERGE: pending run = window offset of its cell (-1: none) and the four tap sums
     int poff = -1;
     float2 pa01 = make_float2(0.f, 0.f), pa23 = make_float2(0.f, 0.f);
     auto process = [&](EventBlock<float, 4, false, PACKED>& e, const int b) {
       const bool full = b >= lo && b + 4 <= hi;
       float2 w[4], w01[4], w23[4];
       int off[4];
-      bool ok = full && use_win;
+      bool ok = full;
       if (full) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1207,59 +1077,65 @@ k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const
       for (int j = 0; j < 4; ++j) {
         const float2 wb = add2(w[j], bias2);
         const float fr = floorf(wb.x), fc = floorf(wb.y);
-        const float2 ab = sub2(w[j], make_float2(fr, fc));
-        const float2 nab = sub2(one2, ab);
-        const float2 lhs = make_float2(nab.x, ab.x);
-        w01[j] = mul2(lhs, make_float2(nab.y, nab.y));
+        const float2 ab = sub2(w[j], make_float2(fr, fc));                                            // (a, b)
+        // (1 - a, a) in one packed FMA: a * (-1) + 1 is ONE rounding of 1 - a, a * 1 + 0 is a
+        const float2 lhs = fma2(make_float2(ab.x, ab.x), make_float2(-1.f, 1.f), make_float2(1.f, 0.f));
+        const float nb = __fsub_rn(1.f, ab.y);
+        w01[j] = mul2(lhs, make_float2(nb, nb));
         w23[j] = mul2(lhs, make_float2(ab.y, ab.y));
         const int lr = (int)fr + dr, lc = (int)fc + dc;
-        off[j] = lr * kSW + lc;
+        off[j] = lr * kSW + lc + off0;
         // (a NaN weight fails the first test; a huge coordinate saturates the conversion and fails the range tests)
-        ok = ok && (w01[j].x == w01[j].x) && (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1);
+        ok = ok && (w01[j].x == w01[j].x) && (unsigned)lr < span && (unsigned)lc < (unsigned)(kSW - 1);
       }
       if (ok) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool same = off[j] == poff;
-          if (!same & (poff >= 0)) flush_run_smem(win, poff, pa01, pa23);
-          const float sel = same ? 1.f : 0.f;                 // 1 * sum + w is one rounding of sum + w
-          pa01 = fma2(make_float2(sel, sel), pa01, w01[j]);
-          pa23 = fma2(make_float2(sel, sel), pa23, w23[j]);
-          poff = off[j];
+          if constexpr (MERGE) {
+            const bool same = off[j] == poff;
+            if (!same & (poff >= 0)) taps_to_window(win, poff, pa01, pa23, qs);
+            const float sel = same ? 1.f : 0.f;                 // 1 * sum + w is one rounding of sum + w
+            pa01 = fma2(make_float2(sel, sel), pa01, w01[j]);
+            pa23 = fma2(make_float2(sel, sel), pa23, w23[j]);
+            poff = off[j];
+          } else {
+            taps_to_window(win, off[j], w01[j], w23[j], qs);
+          }
         }
       } else {
-        if (poff >= 0) flush_run_smem(win, poff, pa01, pa23);
-        poff = -1;
-        pa01 = make_float2(0.f, 0.f); pa23 = make_float2(0.f, 0.f);
+        if constexpr (MERGE) {
+          if (poff >= 0) taps_to_window(win, poff, pa01, pa23, qs);
+          poff = -1;
+          pa01 = make_float2(0.f, 0.f); pa23 = make_float2(0.f, 0.f);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          splat_event_general(iwe, Hp, Wp, pad_h, pad_w, full ? 0.f : e.x[j], w[j].x, w[j].y, win, r_org, c_org, (int)use_win);
+          splat_event_general(iwe, Hp, Wp, pad_h, pad_w, full ? 0.f : e.x[j], w[j].x, w[j].y, win, g.r_org, g.c_org, g.row0,
+                              g.nrows, qs);
       }
     };
-    // two event buffers used alternately: the raw fields of group g+1 are requested before group g is processed
-    EventBlock<float, 4, false, PACKED> ea, eb;
-    ea.load_range32(sx, sy, sd, base, lo, hi);
+    if (base != base0) ea.load_range32(sx, sy, sd, base, lo, hi);
 #pragma unroll 1
-    for (int g = 0; g < 4; g += 2) {
-      const int b0 = base + 4 * g;
+    for (int gi = 0; gi < 4; gi += 2) {
+      const int b0 = base + 4 * gi;
       if (b0 >= hi) break;
       if (b0 + 4 < hi) eb.load_range32(sx, sy, sd, b0 + 4, lo, hi);
       process(ea, b0);
       if (b0 + 4 >= hi) break;
-      if (g == 0 && b0 + 8 < hi) ea.load_range32(sx, sy, sd, b0 + 8, lo, hi);
+      if (gi == 0 && b0 + 8 < hi) ea.load_range32(sx, sy, sd, b0 + 8, lo, hi);
       process(eb, b0 + 4);
     }
-    if (poff >= 0) flush_run_smem(win, poff, pa01, pa23);
+    if constexpr (MERGE) { if (poff >= 0) taps_to_window(win, poff, pa01, pa23, qs); }
   }
-  if (use_win) {
+  if (g.nrows > 0) {
     __syncthreads();
-    // window -> global: coalesced rows of fp32 REDs (an int32 -> fp32 conversion is one rounding)
-    const float inv = 1.0f / (float)(1 << kMergeS);
-    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
-      const int v = win[i];
+    // window rows in use -> global: coalesced fp32 REDs (an int32 -> fp32 conversion is one rounding)
+    const float inv = __int_as_float((127 - S) << 23);
+    for (int i = threadIdx.x; i < g.nrows * kSW; i += blockDim.x) {
+      const int v = win[off0 + i];
       if (v != 0) {
         const int lr = i / kSW, lc = i - lr * kSW;
-        const int r = r_org + lr, c = c_org + lc;
+        const int r = g.r_org + g.row0 + lr, c = g.c_org + lc;
         if ((unsigned)r < (unsigned)Hp && (unsigned)c < (unsigned)Wp) red_add_nc(iwe + r * Wp + c, (float)v * inv);
       }
     }
@@ -1580,95 +1456,25 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
   if (run.ck >= 0) { red_add_nc(dflow + run.ck, run.s01.x); red_add_nc(dflow + P.hw + run.ck, run.s01.y); }
 }
 
-template <int GSRC, bool HAS_W, bool PACKED>
-__global__ void __launch_bounds__(256, 3)
-k_tile_bwd(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
-           const float* __restrict__ sw, const int4* __restrict__ items, const WindowHeader* __restrict__ hdr,
-           const float* __restrict__ flow, int H, int W, int pad_h, int pad_w, const float* __restrict__ g,
-           const double* __restrict__ acc, int omit, double scale, float* __restrict__ dflow) {
-  constexpr int EPT = 8, G = 4;
-  __shared__ float win[kSH * kSW];
-  const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
-  const int n_items = hdr->n_items;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int4 it = __ldg(items + item);
-    int r_org, c_org;
-    tile_origin(it.x, W, pad_h, pad_w, r_org, c_org);
-    __syncthreads();  // previous item's gathers are done with the window
-    // dL/dIWE window: masked (0 outside the image / the cropped region), variance objective applied on the fly
-    for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
-      const int lr = i / kSW, lc = i - lr * kSW;
-      win[i] = fetch_g<float, GSRC>(g, P.Hp, P.Wp, r_org + lr, c_org + lc, P.vc);
-    }
-    __syncthreads();
-    const int64_t start = (int64_t)it.y & ~(int64_t)(EPT - 1);
-    for (int64_t base = start + (int64_t)threadIdx.x * EPT; base < it.z; base += (int64_t)blockDim.x * EPT) {
-      EventBlock<float, EPT, HAS_W, PACKED> e;
-      e.load_range(sx, sy, sd, sw, base, it.y, it.z);
-      e.finish(flow, W, P.hw);
-      int ck = -1;
-      float2 s01 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int h = 0; h < EPT; h += G) {
-        float a[G], b[G], g00[G], g01[G], g10[G], g11[G];
-        bool fast[G];
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-          const int j = h + i;
-          const float2 w = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
-          const float2 wb = add2(w, make_float2(1e-6f, 1e-6f));
-          const float fr = floorf(wb.x), fc = floorf(wb.y);
-          const float2 ab = sub2(w, make_float2(fr, fc));
-          a[i] = ab.x; b[i] = ab.y;
-          const int lr = (int)fr + pad_h - r_org, lc = (int)fc + pad_w - c_org;
-          fast[i] = (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1) && (ab.x + ab.y == ab.x + ab.y);
-          if (fast[i]) {
-            const float* p = win + lr * kSW + lc;
-            g00[i] = p[0]; g01[i] = p[1]; g10[i] = p[kSW]; g11[i] = p[kSW + 1];
-          } else {
-            // outside the window (large displacement), non-finite or skipped: exact masked gathers from global
-            float dx, dy;
-            bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, pad_h, pad_w, e.x[j] == e.x[j] ? w.x : NAN, w.y, P.vc, dx, dy);
-            g00[i] = dx; g01[i] = dy; g10[i] = 0.f; g11[i] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-          const int j = h + i;
-          float2 dxy;
-          if (fast[i]) {
-            // (dx, dy) = (1-b, 1-a) * (g10-g00, g01-g00) + (b, a) * (g11-g01, g11-g10); the window already holds dL/dIWE
-            const float2 d1 = sub2(make_float2(g10[i], g01[i]), make_float2(g00[i], g00[i]));
-            const float2 d2 = sub2(make_float2(g11[i], g11[i]), make_float2(g01[i], g10[i]));
-            const float2 ba = make_float2(b[i], a[i]);
-            dxy = fma2(ba, d2, mul2(sub2(make_float2(1.f, 1.f), ba), d1));
-          } else {
-            dxy = make_float2(g00[i], g01[i]);
-          }
-          if (HAS_W) dxy = mul2(dxy, make_float2(e.wt[j], e.wt[j]));
-          if (e.x[j] != e.x[j]) continue;  // skipped event
-          if (e.k[j] != ck) {
-            if (ck >= 0) { red_add_nc(dflow + ck, s01.x); red_add_nc(dflow + P.hw + ck, s01.y); }
-            ck = e.k[j];
-            s01 = make_float2(0.f, 0.f);
-          }
-          s01 = fma2(make_float2(-e.d[j], -e.d[j]), dxy, s01);
-        }
-      }
-      if (ck >= 0) { red_add_nc(dflow + ck, s01.x); red_add_nc(dflow + P.hw + ck, s01.y); }
-    }
-  }
-}
-
 // ---- shared-memory tile backward, second version (round 2) ----------------------------------------------------
 // ncu r01g of k_win_bwd_g: L1TEX 52 % busy on 20 M gather sectors, `long_scoreboard` the top stall -- three dependent
 // global latencies per group (event load -> flow gather -> dL/dIWE gather).  Here one CTA takes one work item of the
-// tile sort (like the splat): the dL/dIWE window of the tile (41 x 41, masked and -- for the variance objective --
-// already transformed) and the per-pixel table (flow + float coordinates) are staged in shared memory once, so that
-// both gathers of an event are LDS (the four taps only when the cell changes, lane-predicated), and the only global
-// traffic per event is the prefetched stream itself.  All events of an origin pixel are combined in registers; the
-// per-pixel flush is one pair of global REDs per pixel run.  k_tile_bwd (round 1) lost to the
-// one-shot kernel because of its coarse persistent items, 8 events of state in registers (80 registers) and no prefetch.
+// tile sort (like the splat): the rows of the tile's dL/dIWE window that the item's pixels can reach (masked and --
+// for the variance objective -- already transformed) and the per-pixel table (flow + float coordinates) are staged in
+// shared memory once, so that both gathers of an event are LDS (the four taps only when the cell changes), and the
+// only global traffic per event is the prefetched stream itself.  All events of an origin pixel are combined in
+// registers; the per-pixel flush is one pair of global REDs per pixel run.  The first tile backward (round 1) lost to
+// the one-shot kernel because of its coarse persistent items, the whole 41 x 41 window filled per item, 8 events of
+// state in registers (80 registers) and no prefetch.
+// One event outside the regular case (item boundary handled by the caller; here: cell outside the window rows in use,
+// non-finite coordinate): exact masked gathers from global memory.
+template <int GSRC>
+__device__ __noinline__ float2 bwd_event_general(const float* __restrict__ g, const BwdParams<float>& P, float xw, float yw) {
+  float dx, dy;
+  bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, P.pad_h, P.pad_w, xw, yw, P.vc, dx, dy);
+  return make_float2(dx, dy);
+}
+
 template <int GSRC, bool PACKED, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
@@ -1679,27 +1485,26 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
   __shared__ float4 pix[kTileH * kTileW];
   pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
   if ((int)blockIdx.x >= hdr->n_items) return;
-  const int4 it = __ldg(items + blockIdx.x);
-  const int lo = it.y, hi = it.z;
+  const ItemGeom ig = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);
+  const int lo = ig.lo, hi = ig.hi;
   if (hi <= lo) return;
   const int hw = H * W;
-  const int tr0 = (it.w >> 16) * kTileH, tc0 = (it.w & 0xffff) * kTileW;
-  const int r_org = tr0 - kHalo + pad_h, c_org = tc0 - kHalo + pad_w;
-  const int dr = pad_h - r_org, dc = pad_w - c_org;
-  fill_pixel_table(pix, flow, tr0, tc0, H, W, hw);
-  const int start = lo & ~3;
-  const int base0 = start + (int)threadIdx.x * 16;
+  const int base0 = (lo & ~3) + (int)threadIdx.x * 16;
   EventBlock<float, 4, false, PACKED> ea, eb;
   if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi);
+  fill_pixel_table(pix, flow, ig, H, W, hw);
   // PDL: everything above overlaps the drain of the preceding cost kernel; dL/dIWE (and, for the variance objective,
   // the accumulators) are only read below
   pdl_wait();
   const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
-  for (int i = threadIdx.x; i < kSH * kSW; i += blockDim.x) {
+  const int off0 = ig.row0 * kSW;
+  for (int i = threadIdx.x; i < ig.nrows * kSW; i += blockDim.x) {
     const int lr = i / kSW, lc = i - lr * kSW;
-    gwin[i] = fetch_g<float, GSRC>(g, P.Hp, P.Wp, r_org + lr, c_org + lc, P.vc);
+    gwin[off0 + i] = fetch_g<float, GSRC>(g, P.Hp, P.Wp, ig.r_org + ig.row0 + lr, ig.c_org + lc, P.vc);
   }
   __syncthreads();
+  const int dr = pad_h - ig.r_org - ig.row0, dc = pad_w - ig.c_org;
+  const unsigned span = (unsigned)(ig.nrows - 1);
   const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
   for (int base = base0; base < hi; base += (int)blockDim.x * 16) {
     int poff = -1;                                   // cell whose four dL/dIWE values are in registers
@@ -1709,7 +1514,6 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
     auto process = [&](EventBlock<float, 4, false, PACKED>& e, const int b) {
       const bool full = b >= lo && b + 4 <= hi;
       float2 w[4], ab[4];
-      float x0[4];
       int off[4], kk[4];
       bool inw[4];
       bool ok = full;
@@ -1717,7 +1521,6 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           int lp;
-          float xo, yo;
           if constexpr (PACKED) {
             const unsigned rc = __float_as_uint(e.x[j]);
             lp = tile_local_pixel(rc);
@@ -1728,15 +1531,13 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
             kk[j] = r * W + c;
           }
           const float4 q = pix[lp];
-          if constexpr (PACKED) { xo = q.z; yo = q.w; } else { xo = e.x[j]; yo = e.y[j]; }
-          x0[j] = xo;
+          const float xo = PACKED ? q.z : e.x[j], yo = PACKED ? q.w : e.y[j];
           w[j] = make_float2(__fsub_rn(xo, __fmul_rn(e.d[j], q.x)), __fsub_rn(yo, __fmul_rn(e.d[j], q.y)));
         }
       } else {
         e.finish(flow, W, hw);   // item boundary: events of the neighbouring item are marked (x = NaN)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          x0[j] = e.x[j];
           kk[j] = e.k[j];
           w[j] = make_float2(__fsub_rn(e.x[j], __fmul_rn(e.d[j], e.f0[j])), __fsub_rn(e.y[j], __fmul_rn(e.d[j], e.f1[j])));
         }
@@ -1747,11 +1548,10 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
         const float fr = floorf(wb.x), fc = floorf(wb.y);
         ab[j] = sub2(w[j], make_float2(fr, fc));
         const int lr = (int)fr + dr, lc = (int)fc + dc;
-        off[j] = lr * kSW + lc;
-        // inside the window every tap is either in the image or reads the masked zero the window holds for it;
-        // NaN fractions (non-finite coordinates, marked events) and cells outside the window take the exact path
-        inw[j] = (unsigned)lr < (unsigned)(kSH - 1) && (unsigned)lc < (unsigned)(kSW - 1) &&
-                 (ab[j].x + ab[j].y == ab[j].x + ab[j].y);
+        off[j] = lr * kSW + lc + off0;
+        // inside the window rows in use every tap is either in the image or reads the masked zero the window holds
+        // for it; NaN fractions (non-finite coordinates, marked events) and other cells take the exact path
+        inw[j] = (unsigned)lr < span && (unsigned)lc < (unsigned)(kSW - 1) && (ab[j].x + ab[j].y == ab[j].x + ab[j].y);
         ok = ok && inw[j];
       }
       if (ok) {
@@ -1774,9 +1574,10 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
           pk = kk[j];
         }
       } else {
+        poff = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (x0[j] != x0[j]) continue;   // marked event (belongs to the neighbouring item)
+          if (!full && e.x[j] != e.x[j]) continue;   // marked event (belongs to the neighbouring item)
           float2 dxy;
           if (inw[j]) {
             const float* p = gwin + off[j];
@@ -1786,9 +1587,7 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
             const float2 ba = make_float2(ab[j].y, ab[j].x);
             dxy = fma2(ba, d2, mul2(sub2(one2, ba), d1));
           } else {
-            float dx, dy;
-            bwd_event_exact<float, GSRC>(g, P.Hp, P.Wp, pad_h, pad_w, w[j].x, w[j].y, P.vc, dx, dy);
-            dxy = make_float2(dx, dy);
+            dxy = bwd_event_general<GSRC>(g, P, w[j].x, w[j].y);
           }
           if (kk[j] != pk) {
             if (pk >= 0) { red_add_nc(dflow + pk, s01.x); red_add_nc(dflow + hw + pk, s01.y); }
@@ -1867,7 +1666,7 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   const int n_tiles = tiles_x(W) * tiles_y(H);
   int* tile_off = reinterpret_cast<int*>(b + L.off_tiles);
   k_win_tile_offsets<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(k_out, n, n_tiles, tile_off);
-  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), reinterpret_cast<int4*>(b + L.off_items), hdr);
+  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), k_out, reinterpret_cast<int4*>(b + L.off_items), hdr);
   k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
                                       reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
                                       reinterpret_cast<T*>(b + L.off_d),
@@ -1924,9 +1723,9 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
     // 0.8e-3), so sparse windows keep the fp32 REDs.  EBOS_TILE=4 forces it, 2 the run-combining variant, 3 the
     // grouped kernel.
     const bool dense_all = n >= (int64_t)16 * H * W;
-    static const int merge_default = env_int("EBOS_SPLAT_MERGE");   // round-2 kernel as the dense default (A/B knob)
-    const bool dense_merge = dense_all && merge_default == 1;
-    const bool dense = dense_all && !dense_merge;
+    static const int v2_default = env_int("EBOS_SPLAT_V2");   // round-2 kernel as the dense default (A/B knob)
+    const bool dense_v2 = dense_all && v2_default == 1;
+    const bool dense = dense_all && !dense_v2;
     if (!has_weight && (tile_env == 4 || (tile_env == 0 && dense))) {
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
@@ -1944,50 +1743,24 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       EBOS_LAUNCH_CHECK("ebos_window_splat(tile, direct)");
       return EBOS_OK;
     }
-    if (!has_weight && (tile_env == 5 || (tile_env == 0 && dense_merge))) {
-      // run-merging fixed-point tile kernel with the per-pixel table in shared memory (round 2)
+    if (!has_weight && (tile_env == 5 || tile_env == 6 || (tile_env == 0 && dense_v2))) {
+      // round-2 tile kernel (per-pixel table in shared memory, window rows in use only); EBOS_TILE=6: with run merging
       const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       static const int occ_env = env_int("EBOS_QOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
+      const bool merge = tile_env == 6;
       const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
-#define EBOS_SM(P, B) k_tile_splat_m<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
-      if (packed) { if (occ == 3) EBOS_SM(true, 3); else if (occ == 4) EBOS_SM(true, 4); else if (occ == 5) EBOS_SM(true, 5); else EBOS_SM(true, 6); }
-      else { if (occ == 3) EBOS_SM(false, 3); else if (occ == 4) EBOS_SM(false, 4); else if (occ == 5) EBOS_SM(false, 5); else EBOS_SM(false, 6); }
+#define EBOS_SM(P, B, M) k_tile_splat_m<P, B, M><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
+#define EBOS_SM_O(P, M) do { if (occ == 3) EBOS_SM(P, 3, M); else if (occ == 4) EBOS_SM(P, 4, M); else if (occ == 5) EBOS_SM(P, 5, M); else EBOS_SM(P, 6, M); } while (0)
+      if (packed) { if (merge) EBOS_SM_O(true, true); else EBOS_SM_O(true, false); }
+      else { if (merge) EBOS_SM_O(false, true); else EBOS_SM_O(false, false); }
+#undef EBOS_SM_O
 #undef EBOS_SM
-      EBOS_LAUNCH_CHECK("ebos_window_splat(tile, merge)");
-      return EBOS_OK;
-    }
-    if (!has_weight && tile_env == 2) {
-      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
-      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
-      const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot; unused slots exit at once
-      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
-      const float* fd = reinterpret_cast<const float*>(sd);
-      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
-      static const int occ_env = env_int("EBOS_QOCC");   // experiment knob: CTAs per SM the kernel is compiled for
-#define EBOS_SQ(P, B) k_tile_splat_q<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
-      if (packed) { if (occ_env == 4) EBOS_SQ(true, 4); else if (occ_env == 5) EBOS_SQ(true, 5); else EBOS_SQ(true, 6); }
-      else { if (occ_env == 4) EBOS_SQ(false, 4); else if (occ_env == 5) EBOS_SQ(false, 5); else EBOS_SQ(false, 6); }
-#undef EBOS_SQ
-      EBOS_LAUNCH_CHECK("ebos_window_splat(tile, fixed point)");
-      return EBOS_OK;
-    }
-    if (tile_env == 1) {
-      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
-      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
-      const unsigned tgrid = (unsigned)std::min<int64_t>(max_items(n, H, W), (int64_t)sm_count() * 8);
-      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
-      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
-      const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
-      if (has_weight) { if (packed) k_tile_splat<true, true><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi);
-                        else k_tile_splat<true, false><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi); }
-      else { if (packed) k_tile_splat<false, true><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi);
-             else k_tile_splat<false, false><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fi); }
-      EBOS_LAUNCH_CHECK("ebos_window_splat(tile)");
+      EBOS_LAUNCH_CHECK("ebos_window_splat(tile, round 2)");
       return EBOS_OK;
     }
   }
@@ -2086,28 +1859,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
   static const int vec_env = env_int("EBOS_VEC_LOAD");
   const int Wp = W + 2 * pad_w;
   const bool vec = sizeof(T) == 4 && vec_env && (Wp % 4 == 0) && ((reinterpret_cast<size_t>(gsrc) & 15) == 0);
-  // shared-memory tile kernel (fp32): opt-in with EBOS_TILE=1 (measured 101 vs 90 us at 16 Mi events: coarse work
-  // items and 80 registers cost more than the cheaper LDS gathers save)
   static const int tile_env = env_int("EBOS_TILE");
-  if constexpr (sizeof(T) == 4) {
-    if (tile_env == 1) {
-      const int4* items = reinterpret_cast<const int4*>(b + L.off_items);
-      const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
-      const unsigned tgrid = (unsigned)std::min<int64_t>(max_items(n, H, W), (int64_t)sm_count() * 8);
-      const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
-      const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
-      const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
-      float* fo = reinterpret_cast<float*>(dflow);
-#define EBOS_TBWD(G, WGT, P) k_tile_bwd<G, WGT, P><<<tgrid, 256, 0, st>>>(fx, fy, fd, fw, items, hdr, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
-      if (affine) { if (has_weight) { if (packed) EBOS_TBWD(1, true, true); else EBOS_TBWD(1, true, false); }
-                    else { if (packed) EBOS_TBWD(1, false, true); else EBOS_TBWD(1, false, false); } }
-      else { if (has_weight) { if (packed) EBOS_TBWD(0, true, true); else EBOS_TBWD(0, true, false); }
-             else { if (packed) EBOS_TBWD(0, false, true); else EBOS_TBWD(0, false, false); } }
-#undef EBOS_TBWD
-      EBOS_LAUNCH_CHECK("ebos_window_backward(tile)");
-      return EBOS_OK;
-    }
-  }
   if constexpr (sizeof(T) == 4) {
     // second tile backward (round 2): dL/dIWE window + per-pixel table in shared memory, one CTA per work item
     static const int tbwd_env = env_int("EBOS_TILE_BWD");   // 1 force, 2 default for dense windows (A/B knob)

@@ -75,8 +75,8 @@ class EventImageConverter(object):
     # -- lower layer ----------------------------------------------------------------------------
     def create_image_from_events_numpy(self, events: np.ndarray, method: str = "bilinear_vote",
                                        weight: Union[float, np.ndarray] = 1.0, sigma: int = 1) -> np.ndarray:
-        """numpy branch (src/event_image_converter.py:332-370): float64 image, floor bias 1e-8,
-        optional scipy Gaussian (called on the host exactly like upstream)."""
+        """numpy branch (src/event_image_converter.py:332-370): float64 image, floor bias 1e-8, optional
+        `scipy.ndimage.gaussian_filter(image, sigma)` -- evaluated on the GPU (`gaussian_filter_numpy`)."""
         if method == "count":
             raise NotImplementedError("method='count' is outside the contrast-maximisation path of this package")
         elif method == "bilinear_vote":
@@ -95,9 +95,7 @@ class EventImageConverter(object):
             logger.error(e)
             raise NotImplementedError(e)
         if sigma > 0:
-            from scipy.ndimage import gaussian_filter
-
-            image = gaussian_filter(image, sigma)
+            image = gaussian_filter_numpy(image, sigma)
         return image
 
     def create_image_from_events_tensor(self, events: torch.Tensor, method: str = "bilinear_vote",
@@ -142,11 +140,40 @@ class EventImageConverter(object):
 
 def gaussian_blur3(image: torch.Tensor, sigma: float) -> torch.Tensor:
     """3x3 Gaussian with reflect padding on [b,1,H,W] -- the arithmetic of torchvision's
-    `gaussian_blur(kernel_size=3, sigma)` that upstream calls (src/event_image_converter.py:399-404).
-    A separable 3-tap stencil expressed with torch on the tensor's device."""
-    x = torch.tensor([-1.0, 0.0, 1.0], dtype=image.dtype, device=image.device)
-    k = torch.exp(-0.5 * (x / float(sigma)) ** 2)
-    k = k / k.sum()
-    k2 = (k[:, None] * k[None, :])[None, None]
-    padded = torch.nn.functional.pad(image, (1, 1, 1, 1), mode="reflect")
-    return torch.nn.functional.conv2d(padded, k2)
+    `gaussian_blur(kernel_size=3, sigma)` that upstream calls (src/event_image_converter.py:399-404), as one stencil
+    kernel (`ebos_blur3`); differentiable (the backward is the exact adjoint kernel)."""
+    return ops.blur3(image, float(sigma))
+
+
+def gaussian_filter_numpy(image: np.ndarray, sigma: float) -> np.ndarray:
+    """`scipy.ndimage.gaussian_filter(image, sigma)` as the numpy branch applies it (src/event_image_converter.py:
+    368-369): taps exp(-x^2 / 2 sigma^2) / sum truncated at 4 sigma, 'reflect' borders, along EVERY axis of the array --
+    for a [2,H,W] polarity stack or a [b,H,W] batch upstream therefore also blurs across the leading axis, which is
+    kept.  The [H,W] passes are the separable correlation kernel `ebos_sepconv2d`; the pass over a leading axis is a
+    (tiny) mixing of planes on the device."""
+    from . import eklt
+
+    taps = eklt.gaussian_taps_scipy(float(sigma))
+    if len(taps) > 127:
+        raise ValueError(f"sigma = {sigma}: the separable kernel holds at most 127 taps (sigma <= 15.7)")
+    img = to_device_tensor(image).to(torch.float64 if image.dtype != np.float32 else torch.float32)
+    if img.dim() < 2:
+        raise ValueError(f"expected an image [(...,) H, W], got shape {tuple(image.shape)}")
+    lead = img.shape[:-2]
+    flat = img.reshape((-1,) + tuple(img.shape[-2:]))
+    radius = len(taps) // 2
+    for axis in range(len(lead)):            # leading axes first, like scipy's axis order
+        n = lead[axis]
+        mix = np.zeros((n, n))
+        for i in range(n):
+            for u, t in enumerate(taps):
+                j = i + u - radius
+                while j < 0 or j >= n:       # scipy 'reflect': (d c b a | a b c d | d c b a)
+                    j = -j - 1 if j < 0 else 2 * n - 1 - j
+                mix[i, j] += t
+        m = torch.from_numpy(mix).to(img)
+        full = flat.reshape(tuple(lead) + tuple(img.shape[-2:]))
+        full = torch.movedim(torch.tensordot(m, torch.movedim(full, axis, 0), dims=([1], [0])), 0, axis)
+        flat = full.reshape((-1,) + tuple(img.shape[-2:]))
+    out = torch.stack([eklt.sepconv2d(plane.contiguous(), taps, taps, "reflect") for plane in flat])
+    return out.reshape(tuple(img.shape)).cpu().numpy()

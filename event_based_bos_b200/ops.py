@@ -497,3 +497,36 @@ def flow_total_variation(flow: torch.Tensor, weights: Union[float, torch.Tensor,
     elif weights is not None and float(weights) != 1.0:
         w = torch.full(flow.shape[1:], float(weights), dtype=flow.dtype, device=flow.device)
     return _FlowTv.apply(flow, w)
+
+
+class _Blur3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, sigma):
+        img = image.contiguous()
+        H, W = img.shape[-2:]
+        batch = img.numel() // (H * W)
+        out = torch.empty_like(img)
+        check(_capi.load().ebos_blur3(ptr(img), batch, H, W, sigma, 0, dtype_code(img), ptr(out), current_stream()), "ebos_blur3")
+        ctx.sigma = sigma
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g = grad_out.contiguous()
+        H, W = g.shape[-2:]
+        out = torch.empty_like(g)
+        check(_capi.load().ebos_blur3(ptr(g), g.numel() // (H * W), H, W, ctx.sigma, 1, dtype_code(g), ptr(out), current_stream()),
+              "ebos_blur3(adjoint)")
+        return out, None
+
+
+def blur3(image: torch.Tensor, sigma: float) -> torch.Tensor:
+    """torchvision `gaussian_blur(kernel_size=3, sigma)` over the last two dimensions of `image` [...,H,W] (reflect
+    padding; src/event_image_converter.py:399-404), differentiable: forward and exact adjoint are CUDA stencil kernels."""
+    _check_cuda(image)
+    if image.dim() < 2 or image.shape[-1] < 2 or image.shape[-2] < 2:
+        raise ValueError(f"blur3 needs [...,H,W] with H, W >= 2 (reflect padding), got {tuple(image.shape)}")
+    if not sigma > 0:
+        raise ValueError("sigma must be positive")
+    dtype_code(image)
+    return _Blur3.apply(image, float(sigma))

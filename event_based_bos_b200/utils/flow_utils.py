@@ -1,4 +1,4 @@
-"""Flow helpers (host side, numpy)."""
+"""Flow helpers: synthetic flows (host side, numpy) and the flow-error metrics (GPU reduction kernel)."""
 from typing import Optional, Tuple
 
 import numpy as np
@@ -36,30 +36,58 @@ def smooth_flow(image_size: Tuple[int, int], seed: int = 0, max_val: float = 3.0
     return flow.astype(dtype)
 
 
+ERROR_KEYS = ("EPE", "1PE", "2PE", "3PE", "5PE", "10PE", "20PE", "AE")
+
+
+def _flow_error_device(flow_gt, flow_pred, event_mask, time_scale, tensor_variant: bool):
+    """The eight metrics as a float64 [8] tensor on the device: one reduction kernel (ebos_flow_error)."""
+    import torch
+
+    from .. import _capi
+    from ..ops import dtype_code
+    from ..types import to_device_tensor
+
+    _capi.require_device()
+    if len(flow_gt.shape) != 4 or len(flow_pred.shape) != 4:
+        raise AssertionError("flow_gt and flow_pred must be [B,2,H,W]")   # upstream asserts the same
+    gt = to_device_tensor(flow_gt)
+    if gt.dtype not in (torch.float32, torch.float64):
+        gt = gt.to(torch.float64)
+    pred = to_device_tensor(flow_pred).to(gt.dtype)
+    gt, pred = torch.broadcast_tensors(gt, pred)
+    gt, pred = gt.contiguous(), pred.contiguous()
+    B, _, H, W = gt.shape
+    mask = None
+    if event_mask is not None:
+        m = to_device_tensor(event_mask)
+        mask = torch.broadcast_to(m.reshape((-1, 1) + tuple(m.shape[-2:])) if m.dim() != 4 else m, (B, 1, H, W))
+        mask = (mask != 0).to(torch.uint8).contiguous()
+    ts = None
+    if time_scale is not None:
+        ts = to_device_tensor(time_scale).to(gt.dtype).reshape(-1).contiguous()
+        if ts.numel() != B:
+            raise ValueError(f"time_scale must hold one value per batch row ({B}), got {ts.numel()}")
+    lib = _capi.load()
+    ws = torch.empty(lib.ebos_flow_error_workspace_doubles(B), dtype=torch.float64, device=gt.device)
+    out = torch.empty(8, dtype=torch.float64, device=gt.device)
+    _capi.check(lib.ebos_flow_error(_capi.ptr(gt), _capi.ptr(pred), _capi.ptr(mask), 1, _capi.ptr(ts), int(tensor_variant), B, H, W, dtype_code(gt),
+                                    _capi.ptr(ws), _capi.ptr(out), _capi.current_stream()), "ebos_flow_error")
+    return out, gt.dtype
+
+
+def calculate_flow_error_tensor(flow_gt, flow_pred, event_mask=None, time_scale=None) -> dict:
+    """src/utils/flow_utils.py:705-766 on the GPU: EPE, N-pixel outlier ratios and AE of [B,2,H,W] flows over the pixels
+    whose ground truth is finite and non-zero in both channels (and inside `event_mask` [B,1,H,W]); `time_scale` [B,1]
+    multiplies both flows.  Returns 0-dim tensors on the device (no host synchronisation), keys as upstream."""
+    out, dtype = _flow_error_device(flow_gt, flow_pred, event_mask, time_scale, True)
+    vals = out.to(dtype)
+    return {k: vals[i] for i, k in enumerate(ERROR_KEYS)}
+
+
 def calculate_flow_error_numpy(flow_gt: np.ndarray, flow_pred: np.ndarray,
                                event_mask: Optional[np.ndarray] = None) -> dict:
-    """Flow-error statistics between [b,2,H,W] flows, optionally restricted to pixels with events.
-
-    Same metrics and keys as src/utils/flow_utils.py:769-821: EPE, the 1/2/3/5/10/20-pixel outlier
-    ratios and AE (radians, angle between the (u,v,1) vectors), each summed over valid pixels (ground
-    truth finite and non-zero in both channels, inside the event mask), divided by their count + 1e-5,
-    and averaged over the batch."""
-    assert len(flow_gt.shape) == len(flow_pred.shape) == 4
-    finite = np.logical_and(~np.isinf(flow_gt[:, [0], ...]), ~np.isinf(flow_gt[:, [1], ...]))
-    nonzero = np.logical_and(np.abs(flow_gt[:, [0], ...]) > 0, np.abs(flow_gt[:, [1], ...]) > 0)
-    total_mask = np.logical_and(finite, nonzero)
-    if event_mask is not None:
-        total_mask = np.logical_and(event_mask, total_mask)
-    gt_masked = flow_gt * total_mask
-    pred_masked = flow_pred * total_mask
-    n_points = np.sum(total_mask, axis=(1, 2, 3)) + 1e-5
-    errors = {}
-    endpoint_error = np.linalg.norm(gt_masked - pred_masked, axis=1)
-    errors["EPE"] = np.mean(np.sum(endpoint_error, axis=(1, 2)) / n_points)
-    for thr in (1, 2, 3, 5, 10, 20):
-        errors[f"{thr}PE"] = np.mean(np.sum(endpoint_error > thr, axis=(1, 2)) / n_points)
-    u, v = pred_masked[:, 0, ...], pred_masked[:, 1, ...]
-    u_gt, v_gt = gt_masked[:, 0, ...], gt_masked[:, 1, ...]
-    cosine = (1.0 + u * u_gt + v * v_gt) / (np.sqrt(1 + u * u + v * v) * np.sqrt(1 + u_gt * u_gt + v_gt * v_gt))
-    errors["AE"] = np.mean(np.sum(np.arccos(cosine), axis=(1, 2)) / n_points)
-    return errors
+    """src/utils/flow_utils.py:769-821 with numpy in and floats out (what SolverBase.calculate_flow_error logs,
+    src/solver/base.py:289-317); the reduction itself runs on the GPU (one kernel, one 64-byte read-back)."""
+    out, _ = _flow_error_device(flow_gt, flow_pred, event_mask, None, False)
+    vals = out.cpu().numpy()
+    return {k: vals[i] for i, k in enumerate(ERROR_KEYS)}

@@ -321,6 +321,34 @@ EBOS_API int ebos_eklt_patch_flow(const void* intensity, int ph, int pw, int dty
 EBOS_API int ebos_sepconv2d(const void* image, int H, int W, const double* taps_rows, int n_rows, const double* taps_cols,
                    int n_cols, int border, int dtype, void* tmp, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Either side of the path
+ * ---------------------------------------------------------------------------------------- */
+
+/* calculate_flow_error_numpy / calculate_flow_error_tensor (src/utils/flow_utils.py:769-821, 705-766; call site
+ * SolverBase.calculate_flow_error, src/solver/base.py:289-317): flow_gt, flow_pred [batch,2,H,W] of dtype; event_mask NULL or uint8 (bool)
+ * [batch,H,W] (mask_batched != 0) / [H,W] shared by the batch (mask_batched == 0) -- the squeezed [b,1,H,W] mask of
+ * EventImageConverter.create_eventmask.  A pixel counts when the ground truth is not +-inf and non-zero in BOTH
+ * channels and the mask is set; like upstream the flows are MULTIPLIED by that mask (an infinite value at a
+ * masked-out pixel therefore gives NaN metrics, as it does upstream).  time_scale: NULL, or [batch] of dtype
+ * multiplied into both masked flows (the tensor variant's optional argument); n_points_fp32 != 0 rounds the
+ * denominator n_points + 1e-5 to float32 the way the tensor variant does (an int64 tensor plus a Python float is a
+ * float32 tensor in torch, :741).  errors: device double[8] =
+ * EPE, 1PE, 2PE, 3PE, 5PE, 10PE, 20PE, AE -- each sum / (n_points + 1e-5) per batch row, then the batch mean.
+ * workspace: device double[ebos_flow_error_workspace_doubles(batch)] (zeroed by the call).  Sums in double. */
+EBOS_API size_t ebos_flow_error_workspace_doubles(int batch);
+EBOS_API int ebos_flow_error(const void* flow_gt, const void* flow_pred, const uint8_t* event_mask, int mask_batched,
+                    const void* time_scale, int n_points_fp32, int batch, int H, int W, int dtype, double* workspace,
+                    double* errors, void* stream);
+
+/* torchvision gaussian_blur(image[b,1,H,W], kernel_size=3, sigma) as EventImageConverter.create_image_from_events_tensor
+ * applies it to the IWE (src/event_image_converter.py:399-404): kernel2d = k k^T with k = exp(-x^2 / (2 sigma^2)) /
+ * sum over x = -1, 0, 1 (computed in dtype), reflect padding.  adjoint != 0 applies the TRANSPOSED operator (what
+ * autograd's backward of that call computes; the reflect border makes the operator non-symmetric).
+ * image, out: [batch,H,W] of dtype, out must not alias image; H, W >= 2. */
+EBOS_API int ebos_blur3(const void* image, int batch, int H, int W, double sigma, int adjoint, int dtype, void* out,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

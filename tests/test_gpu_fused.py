@@ -83,24 +83,23 @@ def test_packed_and_generic_layouts_agree(ops):
         assert rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", ["default", "tileq", "tiled", "tilem", "grouped", "tile", "pipe", "oneshot"])
+@pytest.mark.parametrize("mode", ["default", "tiled", "tilev2", "tilev2merge", "grouped", "pipe", "oneshot"])
 def test_all_streaming_kernel_variants_match_oracle(mode):
     """The fused fp32 path has several kernel families for the event stream: the default (fixed-point shared-memory
-    tile splat for dense windows, grouped one-shot kernels otherwise; "tileq" forces the former and "grouped" the
-    latter for every window), the legacy one-shot kernels (also the fp64 path), and two opt-in experiments
-    (float shared-memory tile kernels, persistent TMA-staged kernels); "tilem" forces the round-2 tile kernels (run-merging
-    fixed-point splat + shared-memory backward) for every window.  Each is forced on in a fresh process and must match the oracle on small
-    windows incl. ragged tails, multi-item tiles, padding, weights, packed and generic layouts."""
+    tile kernels for dense windows, grouped one-shot kernels otherwise), "tiled" / "tilev2" / "tilev2merge" force the
+    round-1 direct tile splat, the round-2 tile splat + tile backward, and its run-merging variant for EVERY window,
+    "grouped" the one-shot kernels for every window, "oneshot" the legacy one-shot kernels (also the fp64 path), "pipe"
+    the persistent TMA-staged kernels.  Each is forced on in a fresh process and must match the oracle on small windows
+    incl. ragged tails, multi-item tiles, padding, weights, packed and generic layouts."""
     import json
     import os
     import subprocess
     import sys
 
     env = dict(os.environ)
-    env.update({"default": {}, "tileq": {"EBOS_TILE": "2"}, "tiled": {"EBOS_TILE": "4"},
-                "tilem": {"EBOS_TILE": "5", "EBOS_TILE_BWD": "1"}, "grouped": {"EBOS_TILE": "3"}, "tile": {"EBOS_TILE": "1"},
-                "pipe": {"EBOS_PIPE": "1"},
-                "oneshot": {"EBOS_GROUPS": "-1"}}[mode])
+    env.update({"default": {}, "tiled": {"EBOS_TILE": "4"}, "tilev2": {"EBOS_TILE": "5", "EBOS_TILE_BWD": "1"},
+                "tilev2merge": {"EBOS_TILE": "6", "EBOS_TILE_BWD": "1"}, "grouped": {"EBOS_TILE": "3"},
+                "pipe": {"EBOS_PIPE": "1"}, "oneshot": {"EBOS_GROUPS": "-1"}}[mode])
     script = os.path.join(os.path.dirname(__file__), "pipe_check.py")
     res = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]

@@ -6,7 +6,6 @@ import torch
 import event_based_bos_b200 as ebos
 from event_based_bos_b200 import _capi, ops, sharding, utils
 from event_based_bos_b200.solver.contrast_maximization import split_cost_weights
-from oracle import ref_import
 
 
 def test_direction_mapping_matches_reference_rules():
@@ -101,21 +100,6 @@ def test_utils_generators_and_metrics():
     err_raw = np.abs(raw[:, 2].astype(np.float32).astype(np.float64) - t).max()
     err_reb = np.abs(reb[:, 2].astype(np.float32).astype(np.float64) - (t - t.min())).max()
     assert err_reb < 1e-3 * err_raw
-
-
-@pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted")
-def test_flow_error_matches_reference():
-    ref = ref_import.load()
-    rng = np.random.default_rng(0)
-    gt, pred = rng.uniform(-3, 3, (2, 2, 16, 20)), rng.uniform(-3, 3, (2, 2, 16, 20))
-    gt[0, :, 3, 4] = 0.0
-    mask = rng.uniform(size=(2, 1, 16, 20)) > 0.3
-    for m in (None, mask):
-        a = utils.calculate_flow_error_numpy(gt, pred, m)
-        b = ref.utils.calculate_flow_error_numpy(gt, pred, m)
-        assert a.keys() == b.keys()
-        for k in a:
-            assert a[k] == pytest.approx(b[k], rel=1e-12)
 
 
 def test_shard_assignment():

@@ -1,5 +1,7 @@
 """The CPU oracle (oracle/spec.py) against outputs of the unmodified reference (tests/golden/).
 This is what pins the oracle: the reference itself has no tests for the path."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -146,3 +148,37 @@ def test_edge_cases():
     # a coordinate in (-1, 0) truncates to pixel 0
     neg = torch.tensor([[-0.5, -0.5, 0.0, 1.0], [0.0, 0.0, 1.0, 1.0]])
     assert int(spec.origin_pixel_index(neg[:, 0], neg[:, 1], 4)[0]) == 0
+
+
+# ---- rows f-3 / f-4: flow-error metrics and the blurred IWE (tests/golden/reference_metrics_v1.npz) ----------------
+METRICS_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_metrics_v1.npz")
+ERROR_KEYS = ("EPE", "1PE", "2PE", "3PE", "5PE", "10PE", "20PE", "AE")
+
+
+@pytest.fixture(scope="module")
+def metrics_golden():
+    with np.load(METRICS_GOLDEN, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def test_flow_error_oracle_matches_reference(metrics_golden):
+    g = metrics_golden
+    for name in list(g["cases"]) + ["inf64"]:
+        mask = g.get(f"{name}/mask")
+        got = spec.flow_error(g[f"{name}/gt"], g[f"{name}/pred"], mask)
+        tol = 1e-6 if g[f"{name}/gt"].dtype == np.float32 else 1e-13
+        np.testing.assert_allclose([got[k] for k in ERROR_KEYS], g[f"{name}/numpy"], rtol=tol, atol=0, equal_nan=True)
+        if name != "inf64":
+            got = spec.flow_error(g[f"{name}/gt"], g[f"{name}/pred"], mask, g[f"{name}/time_scale"], tensor_variant=True)
+            np.testing.assert_allclose([got[k] for k in ERROR_KEYS], g[f"{name}/tensor"], rtol=max(tol, 1e-12), atol=0,
+                                       equal_nan=True)
+    assert np.isnan(g["inf64/numpy"][0]) and np.isnan(g["inf64/numpy"][7])   # upstream: inf * 0 = nan poisons EPE and AE
+
+
+def test_blurred_iwe_oracle_matches_reference(metrics_golden):
+    g = metrics_golden
+    for name in g["blur_cases"]:
+        iwe = torch.from_numpy(g[f"{name}/iwe"])
+        out = spec.gaussian_blur3(iwe, float(g[f"{name}/sigma"]))
+        tol = 1e-6 if iwe.dtype == torch.float32 else 1e-14
+        np.testing.assert_allclose(out.numpy(), g[f"{name}/blurred"], rtol=tol, atol=tol * np.abs(g[f"{name}/blurred"]).max())
