@@ -1,6 +1,12 @@
-"""`HybridCost`: weighted sum of registered costs (src/costs/hybrid.py:12-79)."""
+"""`HybridCost`: a weighted sum of registered objectives (contract of src/costs/hybrid.py:12-79).
+
+    HybridCost("minimize", {"diff_norm": 1.0, "image_gradient": 0.5, "flow_norm_pxy": 0.1})
+
+Every term receives the same argument dict; a weight given as the string "inv" contributes 1 / term instead of
+weight * term.  The per-term histories are reported next to the total under the term's registry name.
+"""
 import logging
-from typing import Union
+from typing import Dict, List, Union
 
 import torch
 
@@ -8,65 +14,60 @@ from .base import CostBase
 
 logger = logging.getLogger(__name__)
 
+Weight = Union[float, int, str]
+
 
 class HybridCost(CostBase):
-    """Sum over `cost_with_weight` of weight * cost(arg); the weight "inv" means 1 / cost.
-
-    Args:
-        direction (str) ... 'minimize' or 'maximize'.
-        cost_with_weight (dict) ... {cost name: weight}.
-    """
-
     name = "hybrid"
 
-    def __init__(self, direction: str, cost_with_weight: dict, store_history: bool = False, *args, **kwargs):
+    def __init__(self, direction: str, cost_with_weight: Dict[str, Weight], store_history: bool = False, *args, **kwargs):
         from . import functions
 
+        unknown = [k for k in cost_with_weight if k not in functions]
+        if unknown:
+            raise KeyError(f"unknown cost(s) {unknown}; registered: {sorted(functions)}")
         logger.info(f"Log functions are mix of {cost_with_weight}")
-        self.cost_func = {
-            key: {"func": functions[key](direction=direction, store_history=store_history, *args, **kwargs),
-                  "weight": value}
-            for key, value in cost_with_weight.items()
-        }
+        self.terms: Dict[str, CostBase] = {
+            key: functions[key](direction=direction, store_history=store_history, *args, **kwargs) for key in cost_with_weight}
+        self.weights: Dict[str, Weight] = dict(cost_with_weight)
         super().__init__(direction=direction, store_history=store_history)
-        self.required_keys = []
-        for name in self.cost_func.keys():
-            self.required_keys.extend(self.cost_func[name]["func"].required_keys)
+        self.required_keys: List[str] = [k for term in self.terms.values() for k in term.required_keys]
 
-    def update_weight(self, cost_with_weight):
-        assert set(self.cost_func.keys()) == set(cost_with_weight.keys())
-        for key in cost_with_weight.keys():
-            self.cost_func[key]["weight"] = cost_with_weight[key]
+    @property
+    def cost_func(self) -> Dict[str, dict]:
+        """{name: {"func": cost object, "weight": weight}} -- the view upstream stores as an attribute."""
+        return {k: {"func": self.terms[k], "weight": self.weights[k]} for k in self.terms}
+
+    def update_weight(self, cost_with_weight: Dict[str, Weight]) -> None:
+        assert set(cost_with_weight) == set(self.terms)
+        self.weights.update(cost_with_weight)
 
     @CostBase.register_history
     @CostBase.catch_key_error
     def calculate(self, arg: dict) -> Union[float, torch.Tensor]:
-        loss = 0.0
-        for name in self.cost_func.keys():
-            term = self.cost_func[name]["func"].calculate(arg)
-            if self.cost_func[name]["weight"] == "inv":
-                loss += 1.0 / term
-            else:
-                loss += self.cost_func[name]["weight"] * term
-        return loss
+        total = 0.0
+        for key, term in self.terms.items():
+            value = term.calculate(arg)
+            total = total + (1.0 / value if self.weights[key] == "inv" else self.weights[key] * value)
+        return total
 
+    # the history switches reach every term
     def clear_history(self) -> None:
         self.history = {"loss": []}
-        for name in self.cost_func.keys():
-            self.cost_func[name]["func"].clear_history()
+        for term in getattr(self, "terms", {}).values():
+            term.clear_history()
 
     def get_history(self) -> dict:
-        dic = self.history.copy()
-        for name in self.cost_func.keys():
-            dic.update({name: self.cost_func[name]["func"].get_history()["loss"]})
-        return dic
+        merged = dict(self.history)
+        merged.update({key: term.get_history()["loss"] for key, term in self.terms.items()})
+        return merged
 
     def enable_history_register(self) -> None:
         self.store_history = True
-        for name in self.cost_func.keys():
-            self.cost_func[name]["func"].store_history = True
+        for term in self.terms.values():
+            term.store_history = True
 
     def disable_history_register(self) -> None:
         self.store_history = False
-        for name in self.cost_func.keys():
-            self.cost_func[name]["func"].store_history = False
+        for term in self.terms.values():
+            term.store_history = False

@@ -47,7 +47,4 @@ class ImageGradient(CostBase):
         loss = ops.flow_total_variation(dev_flow, w)
         if loss.device != flow.device:
             loss = loss.to(flow.device)
-        if self.direction == "minimize":
-            return loss
-        logger.warning("The loss is specified as maximize direction")
-        return -loss
+        return self.oriented(loss)

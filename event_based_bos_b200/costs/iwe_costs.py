@@ -35,9 +35,7 @@ class _IweCost(CostBase):
         loss = ops.iwe_cost(dev, self.kernel_name, omit_boundary)   # minimise-direction value: -contrast
         if loss.device != iwe.device:
             loss = loss.to(iwe.device)
-        if self.direction == "minimize":
-            return loss
-        return -loss
+        return loss if self.direction == "minimize" else -loss
 
 
 class ImageVariance(_IweCost):

@@ -287,10 +287,15 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // Spatial tiling of the ORIGIN pixel grid used by the sort key and the shared-memory tile kernels.
 constexpr int kTileH = 32, kTileW = 32;
-constexpr int kItemEvents = 4080;           // max events per work item = 255 x 16 (a busy tile is split EVENLY into several items)
+constexpr int kItemEvents = 4080;           // smallest work-item size = 255 x 16 events (sizes the item array); see item_events()
 inline int tiles_x(int W) { return (W + kTileW - 1) / kTileW; }
 inline int tiles_y(int H) { return (H + kTileH - 1) / kTileH; }
 inline int64_t max_items(int64_t n, int H, int W) { return n / kItemEvents + (int64_t)tiles_x(W) * tiles_y(H) + 1; }
+
+// Events per work item (a busy tile is split EVENLY into items of at most this many events).  4080 = 16 events per
+// thread of a 256-thread CTA; 8176 = 32 per thread: the per-CTA latency chain (item descriptor -> event stream / flow
+// table -> barrier -> ... -> barrier -> flush) is paid once per item, so longer items amortise it (EBOS_ITEM_EVENTS).
+int item_events();
 
 struct WindowLayout {
   size_t off_x, off_y, off_d, off_w, off_perm, off_tiles, off_items, total;

@@ -45,6 +45,10 @@ static int env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
 }
+int item_events() {
+  static const int v = env_int("EBOS_ITEM_EVENTS");
+  return (v >= kItemEvents && v <= 65520) ? (v & ~15) : kItemEvents;
+}
 
 // ---- prepare --------------------------------------------------------------------------------
 __global__ void k_win_hdr_init(WindowHeader* h) {
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(256) k_win_tile_offsets(const unsigned int* __
 // items[i] = (first | last << 16 tile-local pixel of the piece, begin, end, tile row << 16 | tile col): the tile kernels
 // stage only the rows of the tile (flow table, IWE / dL/dIWE window) that the piece's origin pixels can reach.
 __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int tiles_per_row,
-                                                    const unsigned int* __restrict__ sorted_keys,
+                                                    const unsigned int* __restrict__ sorted_keys, int item_events,
                                                     int4* __restrict__ items, WindowHeader* __restrict__ h) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
   for (int base = 0; base < n_tiles; base += blockDim.x) {
     const int t = base + threadIdx.x;
     int cnt = 0, b = 0, e = 0;
-    if (t < n_tiles) { b = tile_off[t]; e = tile_off[t + 1]; cnt = (e - b + kItemEvents - 1) / kItemEvents; }
+    if (t < n_tiles) { b = tile_off[t]; e = tile_off[t + 1]; cnt = (e - b + item_events - 1) / item_events; }
     // inclusive scan of cnt over the block
     int v = cnt;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
     }
     __syncthreads();
     const int excl = carry + (wid ? warp_sums[wid - 1] : 0) + v - cnt;
-    const int piece = cnt ? ((((e - b) + cnt - 1) / cnt + 15) & ~15) : 0;   // <= kItemEvents (a multiple of 16)
+    const int piece = cnt ? ((((e - b) + cnt - 1) / cnt + 15) & ~15) : 0;   // <= item_events (a multiple of 16)
     const int tcoord = ((t / tiles_per_row) << 16) | (t % tiles_per_row);   // (tile row, tile col) for the tile kernels
     for (int i = 0; i < cnt; ++i) {
       const int pb = min(b + i * piece, e), pe = min(b + (i + 1) * piece, e);
@@ -1026,8 +1030,7 @@ k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const
   __shared__ int win[kSH * kSW];
   __shared__ float4 pix[kTileH * kTileW];
   pdl_launch_dependents();   // the cost kernel may be scheduled while this grid drains (it waits before reading the IWE)
-  if ((int)blockIdx.x >= hdr->n_items) return;
-  ItemGeom g = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);
+  ItemGeom g = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);   // (unused slots are empty: no header read before it)
   const int lo = g.lo, hi = g.hi;
   if (hi <= lo) return;
   const int base0 = (lo & ~3) + (int)threadIdx.x * 16;
@@ -1047,7 +1050,7 @@ k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const
   const unsigned span = (unsigned)max(g.nrows - 1, 0);
   const int off0 = g.row0 * kSW;
   const float2 bias2 = make_float2(1e-6f, 1e-6f);
-  for (int base = base0; base < hi; base += (int)blockDim.x * 16) {
+  if (base0 < hi) {
     // MERGE: pending run = window offset of its cell (-1: none) and the four tap sums
     int poff = -1;
     float2 pa01 = make_float2(0.f, 0.f), pa23 = make_float2(0.f, 0.f);
@@ -1114,16 +1117,20 @@ k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const
                               g.nrows, qs);
       }
     };
-    if (base != base0) ea.load_range32(sx, sy, sd, base, lo, hi);
+    // a thread's groups: 4 consecutive groups of 4 events per run of 16, runs 256 * 16 events apart; the raw fields of
+    // the next group (also across runs) are requested before the current one is processed
+    auto group_base = [&](int gi) { return base0 + (gi >> 2) * (int)(blockDim.x * 16) + (gi & 3) * 4; };
 #pragma unroll 1
-    for (int gi = 0; gi < 4; gi += 2) {
-      const int b0 = base + 4 * gi;
+    for (int gi = 0;; gi += 2) {
+      const int b0 = group_base(gi);
       if (b0 >= hi) break;
-      if (b0 + 4 < hi) eb.load_range32(sx, sy, sd, b0 + 4, lo, hi);
+      const int b1 = group_base(gi + 1);
+      if (b1 < hi) eb.load_range32(sx, sy, sd, b1, lo, hi);
       process(ea, b0);
-      if (b0 + 4 >= hi) break;
-      if (gi == 0 && b0 + 8 < hi) ea.load_range32(sx, sy, sd, b0 + 8, lo, hi);
-      process(eb, b0 + 4);
+      if (b1 >= hi) break;
+      const int b2 = group_base(gi + 2);
+      if (b2 < hi) ea.load_range32(sx, sy, sd, b2, lo, hi);
+      process(eb, b1);
     }
     if constexpr (MERGE) { if (poff >= 0) taps_to_window(win, poff, pa01, pa23, qs); }
   }
@@ -1484,8 +1491,7 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
   __shared__ float gwin[kSH * kSW];
   __shared__ float4 pix[kTileH * kTileW];
   pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
-  if ((int)blockIdx.x >= hdr->n_items) return;
-  const ItemGeom ig = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);
+  const ItemGeom ig = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);   // (unused slots are empty)
   const int lo = ig.lo, hi = ig.hi;
   if (hi <= lo) return;
   const int hw = H * W;
@@ -1506,7 +1512,7 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
   const int dr = pad_h - ig.r_org - ig.row0, dc = pad_w - ig.c_org;
   const unsigned span = (unsigned)(ig.nrows - 1);
   const float2 bias2 = make_float2(1e-6f, 1e-6f), one2 = make_float2(1.f, 1.f);
-  for (int base = base0; base < hi; base += (int)blockDim.x * 16) {
+  if (base0 < hi) {
     int poff = -1;                                   // cell whose four dL/dIWE values are in registers
     float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
     int pk = -1;                                     // origin pixel of the pending gradient sums
@@ -1598,16 +1604,18 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
         }
       }
     };
-    if (base != base0) ea.load_range32(sx, sy, sd, base, lo, hi);
+    auto group_base = [&](int gi) { return base0 + (gi >> 2) * (int)(blockDim.x * 16) + (gi & 3) * 4; };
 #pragma unroll 1
-    for (int gi = 0; gi < 4; gi += 2) {
-      const int b0 = base + 4 * gi;
+    for (int gi = 0;; gi += 2) {
+      const int b0 = group_base(gi);
       if (b0 >= hi) break;
-      if (b0 + 4 < hi) eb.load_range32(sx, sy, sd, b0 + 4, lo, hi);
+      const int b1 = group_base(gi + 1);
+      if (b1 < hi) eb.load_range32(sx, sy, sd, b1, lo, hi);
       process(ea, b0);
-      if (b0 + 4 >= hi) break;
-      if (gi == 0 && b0 + 8 < hi) ea.load_range32(sx, sy, sd, b0 + 8, lo, hi);
-      process(eb, b0 + 4);
+      if (b1 >= hi) break;
+      const int b2 = group_base(gi + 2);
+      if (b2 < hi) ea.load_range32(sx, sy, sd, b2, lo, hi);
+      process(eb, b1);
     }
     if (pk >= 0) { red_add_nc(dflow + pk, s01.x); red_add_nc(dflow + hw + pk, s01.y); }
   }
@@ -1666,7 +1674,10 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   const int n_tiles = tiles_x(W) * tiles_y(H);
   int* tile_off = reinterpret_cast<int*>(b + L.off_tiles);
   k_win_tile_offsets<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(k_out, n, n_tiles, tile_off);
-  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), k_out, reinterpret_cast<int4*>(b + L.off_items), hdr);
+  // unused item slots stay empty (begin == end == 0): the tile kernels launch one CTA per slot and read only their slot
+  cudaError_t me = cudaMemsetAsync(b + L.off_items, 0, (size_t)max_items(n, H, W) * 16, st);
+  if (me != cudaSuccess) return cuda_fail(me, "ebos_window_prepare(items)");
+  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), k_out, item_events(), reinterpret_cast<int4*>(b + L.off_items), hdr);
   k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
                                       reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
                                       reinterpret_cast<T*>(b + L.off_d),
@@ -1732,7 +1743,7 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       static const int occ_env = env_int("EBOS_QOCC");
       // 4 CTAs/SM = 64 registers: with the prefetched next group the 48-register build spills (97 vs 75 us)
       const int occ = (occ_env == 5 || occ_env == 6) ? occ_env : 4;
-      const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot
+      const unsigned qgrid = (unsigned)(n / item_events() + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
@@ -1750,7 +1761,7 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       static const int occ_env = env_int("EBOS_QOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
       const bool merge = tile_env == 6;
-      const unsigned qgrid = (unsigned)max_items(n, H, W);   // one CTA per item slot
+      const unsigned qgrid = (unsigned)(n / item_events() + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
@@ -1869,7 +1880,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       static const int occ_env = env_int("EBOS_BOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
-      const unsigned qgrid = (unsigned)max_items(n, H, W);
+      const unsigned qgrid = (unsigned)(n / item_events() + (int64_t)tiles_x(W) * tiles_y(H) + 1);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);

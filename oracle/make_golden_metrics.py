@@ -95,6 +95,33 @@ def main() -> None:
         out[f"{name}/adjoint"] = I.grad.numpy()
         blur_cases.append(name)
     out["blur_cases"] = np.array(blur_cases)
+
+    # the reference's cost registry on the argument dict PatchEkltPyramid2 builds (src/solver/patch_eklt_pyramid2.py:
+    # 380-392), through HybridCost with the weights of configs/hot_plate1.yaml; value, per-term history, autograd gradients
+    H, W = 26, 38
+    pred = torch.from_numpy(rng.normal(size=(H, W))).requires_grad_()
+    meas = torch.from_numpy(rng.normal(size=(H, W)))
+    flow = torch.from_numpy(rng.uniform(-2, 2, (2, H, W))).requires_grad_()
+    pxy = torch.from_numpy(rng.uniform(-2, 2, (2, H, W))).requires_grad_()
+    wts = torch.from_numpy(rng.uniform(0.1, 1.0, (H, W)))
+    cww = {"diff_norm": 1.0, "image_gradient": 0.5, "flow_norm_pxy": 0.1, "flow_norm": 0.25}
+    hybrid = ref.costs.HybridCost("minimize", cww, store_history=True)
+    loss = hybrid.calculate({"prediction": pred, "measurement": meas, "weights": wts, "flow": flow, "omit_boundary": False,
+                             "pxy": pxy})
+    loss.backward()
+    hist = hybrid.get_history()
+    out["costs/prediction"], out["costs/measurement"] = pred.detach().numpy(), meas.numpy()
+    out["costs/flow"], out["costs/pxy"], out["costs/weights"] = flow.detach().numpy(), pxy.detach().numpy(), wts.numpy()
+    out["costs/names"] = np.array(list(cww))
+    out["costs/weight_values"] = np.array(list(cww.values()))
+    out["costs/loss"] = np.float64(loss.item())
+    out["costs/terms"] = np.array([hist[k][0] for k in cww])
+    out["costs/grad_prediction"], out["costs/grad_flow"], out["costs/grad_pxy"] = pred.grad.numpy(), flow.grad.numpy(), pxy.grad.numpy()
+    out["costs/numpy_terms"] = np.array([
+        ref.costs.functions["diff_norm"]("minimize").calculate({"prediction": pred.detach().numpy(), "measurement": meas.numpy(),
+                                                                 "weights": None}),
+        ref.costs.functions["flow_norm_pxy"]("minimize").calculate({"pxy": pxy.detach().numpy()}),
+        ref.costs.functions["flow_norm"]("maximize").calculate({"flow": flow.detach().numpy()})])
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT) / 1e3:.1f} kB")
 

@@ -2,7 +2,7 @@
 # round 2, GPU session B: round-2 tile kernels v2 (table + rows in use), A/B + ncu of the two
 cd "$(dirname "$0")/../.."
 O=gpurun_out/r02b; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_fused.py -q -s -k "variants or benchmark_window" --timeout=600 -p no:cacheprovider > $O/pytest.txt 2>&1; echo "rc=$?" >> $O/pytest.txt
+timeout 900 python -m pytest tests/test_gpu_fused.py tests/test_gpu_metrics.py tests/test_gpu_dropin.py -q -s -k "variants or benchmark_window or metrics or dropin" --timeout=600 -p no:cacheprovider > $O/pytest.txt 2>&1; echo "rc=$?" >> $O/pytest.txt
 B="python bench.py --no-e2e --no-cpu --steps 30"
 timeout 300 $B > $O/bench_base.json 2> $O/bench_base.err
 EBOS_SPLAT_V2=1 timeout 300 $B > $O/bench_v2.json 2> $O/bench_v2.err

@@ -139,3 +139,41 @@ def test_numpy_branch_gaussian_matches_scipy():
     got = imager.create_image_from_events_numpy(ev, "polarity", sigma=1)
     assert got.shape == (2, H, W)
     assert np.abs(got - gaussian_filter(pol, 1)).max() <= 1e-12 * np.abs(pol).max()   # upstream also blurs ACROSS the two channels
+
+
+def test_cost_registry_matches_reference(g):
+    """The reference's whole cost registry through HybridCost with the weights of configs/hot_plate1.yaml:
+    total, per-term history and gradients against the reference's autograd."""
+    import event_based_bos_b200 as ebos
+
+    names = [str(n) for n in g["costs/names"]]
+    cww = dict(zip(names, (float(v) for v in g["costs/weight_values"])))
+    assert set(names) <= set(ebos.costs.functions)
+    hybrid = ebos.costs.HybridCost("minimize", cww, store_history=True)
+    assert set(hybrid.required_keys) == {"prediction", "measurement", "flow", "omit_boundary", "pxy"}
+    pred = torch.from_numpy(g["costs/prediction"]).cuda().requires_grad_()
+    flow = torch.from_numpy(g["costs/flow"]).cuda().requires_grad_()
+    pxy = torch.from_numpy(g["costs/pxy"]).cuda().requires_grad_()
+    arg = {"prediction": pred, "measurement": torch.from_numpy(g["costs/measurement"]).cuda(),
+           "weights": torch.from_numpy(g["costs/weights"]).cuda(), "flow": flow, "omit_boundary": False, "pxy": pxy}
+    loss = hybrid.calculate(arg)
+    loss.backward()
+    assert abs(float(loss) - float(g["costs/loss"])) <= 1e-12 * abs(float(g["costs/loss"]))
+    hist = hybrid.get_history()
+    np.testing.assert_allclose([hist[k][0] for k in names], g["costs/terms"], rtol=1e-12)
+    assert len(hist["loss"]) == 1
+    for t, key in ((pred, "prediction"), (flow, "flow"), (pxy, "pxy")):
+        ref = g[f"costs/grad_{key}"]
+        assert np.abs(t.grad.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max(), key
+    # numpy inputs give floats (upstream's numpy branches never flip the sign)
+    got = [ebos.costs.functions["diff_norm"]("minimize").calculate({"prediction": g["costs/prediction"],
+                                                                     "measurement": g["costs/measurement"], "weights": None}),
+           ebos.costs.functions["flow_norm_pxy"]("minimize").calculate({"pxy": g["costs/pxy"]}),
+           ebos.costs.functions["flow_norm"]("maximize").calculate({"flow": g["costs/flow"]})]
+    np.testing.assert_allclose(got, g["costs/numpy_terms"], rtol=1e-12)
+    with pytest.raises(KeyError):
+        ebos.costs.functions["diff_norm"]().calculate({"prediction": pred, "measurement": pred})   # `weights` is read (:42)
+    with pytest.raises(KeyError):
+        ebos.costs.HybridCost("minimize", {"no_such_cost": 1.0})
+    hybrid.update_weight({k: 2.0 for k in names})
+    assert hybrid.cost_func[names[0]]["weight"] == 2.0 and hybrid.cost_func[names[0]]["func"].name == names[0]

@@ -23,7 +23,8 @@ def test_direction_mapping_matches_reference_rules():
 
 
 def test_registries_and_cost_contract():
-    assert set(ebos.costs.functions) == {"image_gradient", "image_variance", "gradient_magnitude"}
+    assert set(ebos.costs.functions) == {"image_gradient", "image_variance", "gradient_magnitude", "diff_norm", "flow_norm",
+                                         "flow_norm_pxy"}
     assert "contrast_maximization" in ebos.solver.collections
     with pytest.raises(ValueError):
         ebos.costs.functions["image_gradient"](direction="sideways")
