@@ -1,22 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the contrast-maximisation hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fused|solve]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fused|solve|giant|eklt]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload "fused" (default, BASELINE config 2): one step = one fused warp -> IWE -> cost -> backward
-evaluation (gradient-magnitude objective + 0.5*TV) over one window of 16 Mi synthetic events on a
-1280x720 grid, fp32.  `value` = events/s with the prepared window resident in HBM (inputs 201 MB > L2);
-`e2e` = the same through the public API from pinned HOST buffers (H2D of the raw events, window
-preparation, evaluation, D2H of loss + gradient inside the timed region).
-Workload "eklt" (BASELINE config 1): one step = one PatchEkltPyramid2.estimate of the hot_plate1 pipeline (EKLT inner
-loop on the GPU, float64 like the reference), value = windows/s.
-Workload "solve" (BASELINE config 3): one step = one full per-window flow solve (500 k events, K_it Adam
-iterations), value = windows/s.
-N > 1: every rank processes its own windows (window sharding, no data-path collective) -> weak scaling.
+Workload "fused" (default, BASELINE config 2 at its largest single-GPU size): one step = one fused warp -> IWE -> cost ->
+backward evaluation (gradient-magnitude objective + 0.5*TV) over one window of 16 Mi synthetic events on a 1280x720
+grid, fp32.  `value` = events/s with the prepared window resident in HBM (inputs > L2); `e2e` = the same through the
+public API from pinned HOST buffers (H2D of the raw sensor stream, ingestion, window preparation, evaluation, D2H of
+loss + gradient inside the timed region).  The SAME JSON line carries the other BASELINE configurations as
+sub-records, each preceded by an in-process parity self-check whose result is printed in the record:
+  "small_windows"  config 2's small end (1 Mi and 0.5 Mi events),
+  "solve"          configs 3/4: full per-window flow solves, windows/s, window-sharded over the ranks (no collective),
+  "giant"          config 5: ONE 128 Mi-event window sharded by events over the ranks (strong scaling; exchange named).
+`--workload solve|giant|eklt` print one of them as the main line instead (eklt = BASELINE config 1, hot_plate1).
+N > 1 (torchrun): the default workload runs one 16 Mi window per GPU (weak scaling, no data-path collective).
 
-`--impl reference` times the reference's CPU torch path (the oracle port: same torch ops as
-src/warp.py + src/event_image_converter.py + autograd) on the host cores, on a bounded sample.
+`--impl reference` times the reference's CPU torch path (the oracle port: same torch ops as src/warp.py +
+src/event_image_converter.py + autograd) on the host cores, on the SAME configuration (16 Mi events per step).
 """
 import argparse
 import json
@@ -173,6 +174,53 @@ def max_over_ranks(ms: float, world: int) -> float:
     return float(t)
 
 
+def bind_to_gpu_numa(local: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated
+    (cudaHostAlloc places pages by the calling thread's policy): with all ranks on node 0 the round-1 end-to-end numbers
+    stopped scaling at ~110-180 GB/s aggregate H2D.  Returns a short description for the JSON line (or None)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+    return None
+
+
+def all_ranks_equal(t: torch.Tensor, world: int) -> bool:
+    """True when `t` holds bit-identical values on every rank (MAX and MIN all-reduce agree element for element)."""
+    if world == 1:
+        return True
+    import torch.distributed as dist
+
+    hi, lo = t.clone(), t.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return bool(torch.equal(hi, lo))
+
+
+def rel_max(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-300))
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's torch path (oracle port)
 # ------------------------------------------------------------------------------------------------
@@ -207,7 +255,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = args.cpu_events
+    n_sample = args.cpu_events or args.events      # the GPU arm's configuration unless a smaller sample is asked for
     if args.workload == "solve":
         s_per_it, cores = cpu_reference_solve(args.solve_events, max(2, min(args.steps, 5)))
         value = 1.0 / (s_per_it * args.solve_iters)
@@ -232,12 +280,15 @@ def run_reference(args):
                                            f"reference's torch ops in float64, finest level) timed at {s_eval:.3f} s "
                                            f"each, x{iters}"}}
     else:
-        value, ms, cores = cpu_reference_fused(n_sample, args.steps, args.warmup)
+        # a CPU step at 16 Mi events takes ~1 s: the whole --steps/--warmup run stays within a few minutes
+        steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+        value, ms, cores = cpu_reference_fused(n_sample, steps, warmup)
         line = {"metric": "events/s fwd+bwd warp->IWE->cost", "value": value, "unit": "events/s", "ms_per_step": ms,
-                "config": {"workload": f"single-window fused warp->IWE->{COST}+{TV_WEIGHT}*TV fwd+bwd, 1280x720, fp32; "
-                                       f"CPU sample {n_sample} events per step"},
+                "config": fused_config(n_sample, None),
                 "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port",
-                                 "sample": f"{n_sample} events per step, {args.steps} steps"}}
+                                 "sample": f"{n_sample} events per step (the GPU arm's window), {steps} steps after {warmup} "
+                                           f"warm-up; oracle torch-CPU restatement of the reference ops, fp32, all host threads"}}
+        line["config"]["cpu_steps_timed"] = steps
     line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                  "dtype": "f64" if args.workload == "eklt" else "f32", "data": "synthetic",
@@ -246,27 +297,66 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def fused_config(n: int, packed):
+    """`config` of the default workload -- identical for both arms (the driver compares them key by key)."""
+    cfg = {"workload": f"single-window fused warp->IWE->{COST}+{TV_WEIGHT}*TV forward+backward microbench, "
+                       f"{n} synthetic events (uniform, flow U(-3,3)), 1280x720, fp32, atomic mode; one window per GPU",
+           "events_per_window": n,
+           "l2_policy": f"inputs larger than L2 ({8 * n / 1e6:.0f}-{12 * n / 1e6:.0f} MB sorted SoA per pass)"
+           if 8 * n > 126e6 else "inputs fit L2 (warm-L2 number)"}
+    if packed is not None:
+        cfg["window_layout"] = "packed (row,col,dt) 8 B/event" if packed else "generic (x,y,dt) 12 B/event"
+    return cfg
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def small_window_points(args, dev, sizes=(1 << 20, 500_000)):
+    """BASELINE config 2's small end: the same fused evaluation on 1 Mi and 0.5 Mi-event windows (CUDA-graph replay;
+    the working set fits L2, so these are warm-L2 numbers -- stated in the record)."""
+    from event_based_bos_b200 import ops
+    from event_based_bos_b200.utils import synthetic_events, synthetic_flow
+
+    peak, _ = measured_peak_gbs()
+    flow = torch.from_numpy(synthetic_flow((H, W), seed=0)).to(dev)
+    out = []
+    for n in sizes:
+        ev = torch.from_numpy(synthetic_events(n, (H, W), seed=0)).to(dev)
+        win = ops.PreparedWindow(ev, (H, W), "first", True)
+        cap = ops.CmaxGraph(win, flow, COST, 1.0, TV_WEIGHT)
+        for _ in range(5):
+            cap.replay()
+        ms = cuda_time_ms(cap.replay, max(args.steps, 50))
+        alg = 32 * n + 11 * P_BYTES
+        out.append({"events": n, "ms_per_step": round(ms, 5), "value": n / (ms * 1e-3), "unit": "events/s",
+                    "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "l2_policy": "inputs fit L2 (warm-L2 number)"})
+        del cap, win, ev
+    return out
+
+
 def run_fused(args, rank, world, local):
     from event_based_bos_b200 import _capi, ops
     from event_based_bos_b200.utils import synthetic_events, synthetic_flow
 
     n = args.events
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)          # before the pinned allocations below
     ev_host = torch.from_numpy(synthetic_events(n, (H, W), seed=rank)).pin_memory()
     flow_host = torch.from_numpy(synthetic_flow((H, W), seed=rank)).pin_memory()
     ev = ev_host.to(dev, non_blocking=True)
     flow = flow_host.to(dev, non_blocking=True)
     window = ops.PreparedWindow(ev, (H, W), "first", True, allow_packed=not args.no_packed)
-    ws = ops.CmaxWorkspace(H, W, (0, 0), dev)
+    ws = ops.CmaxWorkspace(H, W, (0, 0), dev)      # clean-workspace protocol: zero between evaluations
+    ws_k = ops.CmaxWorkspace(H, W, (0, 0), dev)    # scratch for the per-kernel timings (written directly)
+    ws_k.clean = False
 
     def step():
         ops.cmax_value_and_grad(window, flow, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
 
     # the timed step: the same evaluation captured once as a CUDA graph (public API ops.CmaxGraph) and replayed
     captured = ops.CmaxGraph(window, flow, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
+    launches, other_nodes = ops.count_launches(step)     # counted from a stream capture of the same call
     for _ in range(max(args.warmup, 3)):
         captured.replay()
     barrier(world)
@@ -275,7 +365,7 @@ def run_fused(args, rank, world, local):
         barrier(world)
         ms = max_over_ranks(ms, world)
         eager_ms = max_over_ranks(cuda_time_ms(step, args.steps), world)
-        # per-kernel timing of the two event-streaming kernels (same stream, CUDA events)
+        # per-kernel timing of the kernels of the step (same stream, CUDA events around a graph of `steps` calls)
         lib = _capi.load()
         p = _capi.ptr
 
@@ -283,142 +373,47 @@ def run_fused(args, rank, world, local):
             return torch.cuda.current_stream().cuda_stream  # evaluated at call time (graph capture stream)
 
         def splat_only():
-            lib.ebos_window_splat(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.iwe), cur())
+            lib.ebos_window_splat(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws_k.iwe), cur())
 
         def bwd_only():
-            lib.ebos_window_backward(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws.grad_iwe),
-                                     _capi.COST_GRADMAG, p(ws.iwe), p(ws.acc), 0, 1.0, p(ws.dflow), cur())
+            lib.ebos_window_backward(p(window.buffer), window.n, window.flags, p(flow), H, W, 0, 0, 0, p(ws_k.grad_iwe),
+                                     _capi.COST_GRADMAG, p(ws_k.iwe), p(ws_k.acc), 0, 1.0, p(ws_k.dflow), cur())
 
         def cost_only():
-            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws.iwe), H, W, 0, 1.0, 0, p(ws.acc), p(ws.grad_iwe), cur())
+            lib.ebos_iwe_cost(_capi.COST_GRADMAG, p(ws_k.iwe), H, W, 0, 1.0, 0, p(ws_k.acc), p(ws_k.grad_iwe), cur())
 
         def tv_only():
-            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws.acc), p(ws.dflow), cur())
+            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, p(ws_k.acc), p(ws_k.dflow), cur())
 
         adam_m, adam_v = torch.zeros_like(flow), torch.zeros_like(flow)
         adam_p = flow.clone()
 
-        def tv_noloss():
-            lib.ebos_flow_tv(p(flow), 0, H, W, TV_WEIGHT, 0, 0, p(ws.dflow), cur())
-
         def adam_only():
-            lib.ebos_adam_step(p(adam_p), p(ws.dflow), p(adam_m), p(adam_v), adam_p.numel(), 0.05, 0.9, 0.999, 1e-8, 3, 0, cur())
+            lib.ebos_adam_step(p(adam_p), p(ws_k.dflow), p(adam_m), p(adam_v), adam_p.numel(), 0.05, 0.9, 0.999, 1e-8, 3, 0, cur())
 
         def var_only():
-            lib.ebos_iwe_cost(_capi.COST_VARIANCE, p(ws.iwe), H, W, 0, 1.0, 0, p(ws.acc), 0, cur())
+            lib.ebos_iwe_cost(_capi.COST_VARIANCE, p(ws_k.iwe), H, W, 0, 1.0, 0, p(ws_k.acc), 0, cur())
 
         k_ms = {name: graph_time_ms(fn, args.steps) for name, fn in
                 (("window_splat(+memset)", splat_only), ("window_backward", bwd_only), ("iwe_cost_gradmag", cost_only),
-                 ("flow_tv", tv_only), ("flow_tv(no loss atomics)", tv_noloss), ("iwe_cost_variance", var_only),
-                 ("adam_step", adam_only))}
-        step_graph_ms = max_over_ranks(graph_time_ms(step, args.steps), world)
-        clocks.soak(step)
+                 ("flow_tv", tv_only), ("iwe_cost_variance", var_only), ("adam_step", adam_only))}
+        clocks.soak(captured.replay)
     clk = clocks.summary()
 
     # end to end through the public API with host buffers
-    e2e_ms = None
+    e2e = None
     if not args.no_e2e:
-        loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-        grad_host = torch.empty((2, H, W), dtype=torch.float32).pin_memory()
-
-        def e2e_step():
-            e = ev_host.to(dev, non_blocking=True)
-            f = flow_host.to(dev, non_blocking=True)
-            win = ops.PreparedWindow(e, (H, W), "first", True, validate=False, allow_packed=not args.no_packed)
-            loss, grad = ops.cmax_value_and_grad(win, f, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
-            loss_host.copy_(loss, non_blocking=True)
-            grad_host.copy_(grad, non_blocking=True)
-
-        for _ in range(2):
-            e2e_step()
-        barrier(world)
-        e2e_serial_ms = max_over_ranks(cuda_time_ms(e2e_step, max(3, min(args.steps, 10))), world)
-
-        # The same steps software-pipelined over two streams: the H2D copy of step i+1 (copy stream, second pair of
-        # device buffers) overlaps the preparation + evaluation + D2H of step i.  Every step's copies are inside the
-        # timed region; a step is PCIe-bound (276 MB H2D), so throughput approaches the copy time.
-        copy_stream = torch.cuda.Stream(device=dev)
-        ev_bufs = [torch.empty_like(ev_host, device=dev) for _ in range(2)]
-        fl_bufs = [torch.empty_like(flow_host, device=dev) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-
-        def e2e_pipelined(reps):
-            main = torch.cuda.current_stream()
-            for b in range(2):
-                free[b].record(main)
-
-            def upload(i):
-                b = i % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(free[b])           # the step that used this pair of buffers is done
-                    ev_bufs[b].copy_(ev_host, non_blocking=True)
-                    fl_bufs[b].copy_(flow_host, non_blocking=True)
-                    ready[b].record(copy_stream)
-
-            upload(0)
-            for i in range(reps):
-                b = i % 2
-                if i + 1 < reps:
-                    upload(i + 1)
-                main.wait_event(ready[b])
-                win = ops.PreparedWindow(ev_bufs[b], (H, W), "first", True, validate=False, allow_packed=not args.no_packed)
-                loss, grad = ops.cmax_value_and_grad(win, fl_bufs[b], COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
-                loss_host.copy_(loss, non_blocking=True)
-                grad_host.copy_(grad, non_blocking=True)
-                free[b].record(main)
-
-        e2e_reps = max(6, min(args.steps, 12))
-        e2e_pipelined(4)
-        barrier(world)
-        e2e_ms = max_over_ranks(cuda_time_ms(lambda: e2e_pipelined(e2e_reps), 1) / e2e_reps, world)
-
-        # the same evaluation fed with the RAW sensor stream (x,y int16, t int32 us, p bool: 9 B/event) through the
-        # ingestion path: H2D of the compact arrays, rows built on the device, then prepare + evaluation + D2H
-        from event_based_bos_b200 import _capi as capi
-        evn = ev_host.numpy()
-        raw_host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
-                    (evn[:, 1].astype(np.int16), evn[:, 0].astype(np.int16),
-                     np.round(evn[:, 2].astype(np.float64) * 1e6).astype(np.int32), evn[:, 3].astype(np.uint8))]
-        rows_dev = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        cnt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        t0_us = int(raw_host[2][0])
-
-        raw_bufs = [[torch.empty_like(a, device=dev) for a in raw_host] for _ in range(2)]
-
-        def e2e_raw_pipelined(reps):
-            main = torch.cuda.current_stream()
-            for b in range(2):
-                free[b].record(main)
-
-            def upload(i):
-                b = i % 2
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(free[b])
-                    for dst, src in zip(raw_bufs[b], raw_host):
-                        dst.copy_(src, non_blocking=True)
-                    fl_bufs[b].copy_(flow_host, non_blocking=True)
-                    ready[b].record(copy_stream)
-
-            upload(0)
-            for i in range(reps):
-                b = i % 2
-                if i + 1 < reps:
-                    upload(i + 1)
-                main.wait_event(ready[b])
-                x, y, t, pp = raw_bufs[b]
-                capi.check(lib.ebos_ingest_raw(p(x), p(y), p(t), p(pp), n, 0, 0, 0, 0, 0, t0_us, 1, 0, p(rows_dev), p(cnt_dev),
-                                               0, 0, cur()), "ebos_ingest_raw")
-                win = ops.PreparedWindow(rows_dev, (H, W), "first", True, validate=False, allow_packed=not args.no_packed)
-                loss, grad = ops.cmax_value_and_grad(win, fl_bufs[b], COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
-                loss_host.copy_(loss, non_blocking=True)
-                grad_host.copy_(grad, non_blocking=True)
-                free[b].record(main)
-
-        e2e_raw_pipelined(4)
-        barrier(world)
-        e2e_raw_ms = max_over_ranks(cuda_time_ms(lambda: e2e_raw_pipelined(e2e_reps), 1) / e2e_reps, world)
-
+        e2e = e2e_fused(args, rank, world, local, dev, ev_host, flow_host, ws, lib)
+    small = None if args.no_subrecords else small_window_points(args, dev)
+    packed = bool(window.packed)
+    del captured, window, ev
+    torch.cuda.empty_cache()
+    solve_rec = giant_rec = None
+    if not args.no_subrecords:
+        solve_rec = solve_record(args, rank, world, local, quick=True)
+        torch.cuda.empty_cache()
+        giant_rec = giant_record(args, rank, world, local)
+        torch.cuda.empty_cache()
     if rank != 0:
         return
     peak, peak_kind = measured_peak_gbs()
@@ -432,64 +427,181 @@ def run_fused(args, rank, world, local):
         "metric": "events/s fwd+bwd warp->IWE->cost", "value": world * n / (ms * 1e-3), "unit": "events/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"single-window fused warp->IWE->{COST}+{TV_WEIGHT}*TV forward+backward microbench, "
-                               f"{n} synthetic events (uniform, flow U(-3,3)), 1280x720, fp32, atomic mode; one window per GPU",
-                   "events_per_window": n, "l2_policy": f"inputs larger than L2 ({12 * n / 1e6:.0f} MB sorted SoA per pass)"
-                   if 12 * n > 126e6 else "inputs fit L2 (warm-L2 number)"},
+        "config": fused_config(n, None),
+        "window_layout": "packed (row,col,dt) 8 B/event" if packed else "generic (x,y,dt) 12 B/event",
         "clocks": clk,
         "step_roofline": {"algorithmic_bytes": alg_bytes_step, "achieved_gbs": alg_bytes_step / (ms * 1e-3) / 1e9,
                           "frac": alg_bytes_step / (ms * 1e-3) / 1e9 / peak},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": measured_traffic(dom) if n == (1 << 24) and window.packed else None,
+                     "frac": achieved / peak, "traffic": measured_traffic(dom) if n == (1 << 24) and packed else None,
                      "peak_source": peak_kind, "algorithmic_bytes": dom_bytes,
                      "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()}},
-        "gpu_launches": 6 * args.steps,   # per step: TV, splat, cost, backward, finalize + 1 memset node, in one graph replay
+        # kernels of this library enqueued per step, COUNTED from a stream capture of the step (ops.count_launches),
+        # times the timed steps; memset nodes listed separately
+        "gpu_launches": launches * args.steps,
+        "launches_per_step": {"kernels": launches, "memset_nodes": other_nodes},
+        "ms_per_step_eager": round(eager_ms, 4),
+        "launch": "one CUDA-graph replay per step (ops.CmaxGraph); ms_per_step_eager = the same launches issued eagerly",
+        "host_numa_binding": numa,
     }
-    line["config"]["window_layout"] = "packed (row,col,dt) 8 B/event" if window.packed else "generic (x,y,dt) 12 B/event"
-    line["step_ms_graph_replay"] = round(step_graph_ms, 4)
-    line["ms_per_step_eager"] = round(eager_ms, 4)
-    line["config"]["launch"] = "one CUDA-graph replay per step (ops.CmaxGraph); ms_per_step_eager = seven eager launches per step"
-    if e2e_ms is not None:
-        line["e2e"] = {"value": world * n / (e2e_ms * 1e-3), "unit": "events/s", "ms_per_step": e2e_ms,
-                       "h2d_bytes_per_step": 16 * n + 2 * P_BYTES, "d2h_bytes_per_step": 2 * P_BYTES + 4,
-                       "includes": "H2D [N,4] fp32 event rows + flow, window preparation (sort), fused evaluation, D2H loss+gradient; "
-                                   "software-pipelined over two streams (the H2D of step i+1 overlaps the compute of step i)",
-                       "ms_per_step_serial": e2e_serial_ms,
-                       "raw_stream": {"value": world * n / (e2e_raw_ms * 1e-3), "unit": "events/s", "ms_per_step": e2e_raw_ms,
-                                      "h2d_bytes_per_step": 9 * n + 2 * P_BYTES,
-                                      "includes": "same, fed with the raw sensor stream (int16 x,y; int32 t; bool p = 9 B/event) "
-                                                  "through ebos_ingest_raw"}}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if small is not None:
+        line["small_windows"] = small
+    if solve_rec is not None:
+        line["solve"] = solve_rec
+    if giant_rec is not None:
+        line["giant"] = giant_rec
     if not args.no_cpu and world == 1:   # the CPU baseline is timed on rank 0 at N=1 only
-        v, cms, cores = cpu_reference_fused(args.cpu_events, 3, 1)
+        n_cpu = args.cpu_events or n
+        v, cms, cores = cpu_reference_fused(n_cpu, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_events} events, mean of 3 evaluations after 1 warm-up "
-                                          f"(oracle torch-CPU restatement of the reference ops, fp32)"}
+                                "sample": f"{n_cpu} events (the same window size), mean of 3 evaluations after 1 warm-up "
+                                          f"(oracle torch-CPU restatement of the reference ops, fp32, all host threads)"}
     print(json.dumps(line), flush=True)
 
 
-def run_solve(args, rank, world, local):
-    from event_based_bos_b200 import solver
-    from event_based_bos_b200.utils import smooth_flow, synthetic_bos_events
+def e2e_fused(args, rank, world, local, dev, ev_host, flow_host, ws, lib):
+    """The same evaluation end to end from pinned host buffers, software-pipelined over two streams (the H2D copy of step
+    i+1 overlaps ingestion + preparation + evaluation + D2H of step i; every step's copies are inside the timed region).
+    Primary: the RAW sensor stream (x,y int16; t int32 us; p bool = 9 B/event, what the camera delivers and
+    `ebos_ingest_raw` consumes).  Secondary: the reference loader's [N,4] fp32 rows (16 B/event)."""
+    from event_based_bos_b200 import _capi as capi
+    from event_based_bos_b200 import ops
+
+    n = ev_host.shape[0]
+    p = capi.ptr
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    grad_host = torch.empty((2, H, W), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    fl_bufs = [torch.empty_like(flow_host, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    evn = ev_host.numpy()
+    raw_host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+                (evn[:, 1].astype(np.int16), evn[:, 0].astype(np.int16),
+                 np.round(evn[:, 2].astype(np.float64) * 1e6).astype(np.int32), evn[:, 3].astype(np.uint8))]
+    rows_dev = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    cnt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    t0_us = int(raw_host[2][0])
+
+    def cur():
+        return torch.cuda.current_stream().cuda_stream
+
+    def evaluate(rows, fl):
+        win = ops.PreparedWindow(rows, (H, W), "first", True, validate=False, allow_packed=not args.no_packed)
+        loss, grad = ops.cmax_value_and_grad(win, fl, COST, 1.0, TV_WEIGHT, None, False, (0, 0), ws)
+        loss_host.copy_(loss, non_blocking=True)
+        grad_host.copy_(grad, non_blocking=True)
+
+    def pipelined(reps, bufs, hosts, consume):
+        main = torch.cuda.current_stream()
+        for b in range(2):
+            free[b].record(main)
+
+        def upload(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[b])           # the step that used this pair of buffers is done
+                for dst, src in zip(bufs[b], hosts):
+                    dst.copy_(src, non_blocking=True)
+                fl_bufs[b].copy_(flow_host, non_blocking=True)
+                ready[b].record(copy_stream)
+
+        upload(0)
+        for i in range(reps):
+            b = i % 2
+            if i + 1 < reps:
+                upload(i + 1)
+            main.wait_event(ready[b])
+            consume(bufs[b], fl_bufs[b])
+            free[b].record(main)
+
+    def consume_raw(bufs, fl):
+        x, y, t, pp = bufs
+        capi.check(lib.ebos_ingest_raw(p(x), p(y), p(t), p(pp), n, 0, 0, 0, 0, 0, t0_us, 1, 0, p(rows_dev), p(cnt_dev),
+                                       0, 0, cur()), "ebos_ingest_raw")
+        evaluate(rows_dev, fl)
+
+    reps = max(6, min(args.steps, 12))
+    out = {}
+    raw_bufs = [[torch.empty_like(a, device=dev) for a in raw_host] for _ in range(2)]
+    pipelined(4, raw_bufs, raw_host, consume_raw)
+    barrier(world)
+    raw_ms = max_over_ranks(cuda_time_ms(lambda: pipelined(reps, raw_bufs, raw_host, consume_raw), 1) / reps, world)
+    serial_ms = max_over_ranks(cuda_time_ms(lambda: pipelined(1, raw_bufs, raw_host, consume_raw), max(3, min(args.steps, 6))), world)
+    del raw_bufs
+    row_bufs = [[torch.empty_like(ev_host, device=dev)] for _ in range(2)]
+    pipelined(4, row_bufs, [ev_host], lambda bufs, fl: evaluate(bufs[0], fl))
+    barrier(world)
+    rows_ms = max_over_ranks(cuda_time_ms(lambda: pipelined(reps, row_bufs, [ev_host], lambda bufs, fl: evaluate(bufs[0], fl)), 1) / reps, world)
+    h2d_raw, h2d_rows, d2h = 9 * n + 2 * P_BYTES, 16 * n + 2 * P_BYTES, 2 * P_BYTES + 4
+    out = {"value": world * n / (raw_ms * 1e-3), "unit": "events/s", "ms_per_step": raw_ms,
+           "h2d_bytes_per_step": h2d_raw, "d2h_bytes_per_step": d2h,
+           "h2d_gbs_per_rank": h2d_raw / (raw_ms * 1e-3) / 1e9,
+           "includes": "H2D of the raw sensor stream (int16 x,y; int32 t; bool p = 9 B/event) + flow from pinned host memory, "
+                       "ingestion (ebos_ingest_raw), window preparation (sort), fused evaluation, D2H loss + gradient; "
+                       "software-pipelined over two streams (the H2D of step i+1 overlaps the compute of step i)",
+           "ms_per_step_serial": serial_ms,
+           "rows_fp32": {"value": world * n / (rows_ms * 1e-3), "unit": "events/s", "ms_per_step": rows_ms,
+                         "h2d_bytes_per_step": h2d_rows, "h2d_gbs_per_rank": h2d_rows / (rows_ms * 1e-3) / 1e9,
+                         "includes": "same, fed with the reference loader's [N,4] fp32 event rows (16 B/event)"}}
+    return out
+
+
+def solve_record(args, rank, world, local, quick=False):
+    """BASELINE configs 3/4: full per-window dense flow solves (host events in -> host flow out through the public
+    solver API), independent windows sharded over the ranks with NO data-path collective (weak scaling: every rank
+    solves its own windows).  Returns the record (rank 0) or None."""
+    from event_based_bos_b200 import ops, solver
+    from event_based_bos_b200.utils import smooth_flow, synthetic_bos_events, synthetic_events
 
     n, iters = args.solve_events, args.solve_iters
+    dev = torch.device("cuda", local)
     cfg = {"outer_padding": 0, "warp_direction": "first", "optimizer": {"method": "Adam", "n_iter": iters},
            "cmax": {"cost_with_weight": {COST: 1.0, "image_gradient": TV_WEIGHT}, "lr": 0.05}}
     slv = solver.collections["contrast_maximization"]((H, W), (H, W), {}, cfg, None)
     gt = smooth_flow((H, W), seed=rank)
     conc = max(1, args.solve_concurrency)
+    # parity self-check (window sharding has no numerical coupling between ranks: the check is that a rank's solve of
+    # a window equals rank 0's solve of the same window): every rank solves the SAME probe window from the same
+    # tie-free start; RMS distance of the final flows to rank 0's, bar 1e-3 px (north_star)
+    probe_cfg = {"outer_padding": 0, "warp_direction": "first", "optimizer": {"method": "Adam", "n_iter": 40},
+                 "cmax": {"cost_with_weight": {COST: 1.0, "image_gradient": TV_WEIGHT}, "lr": 0.05}}
+    probe_slv = solver.collections["contrast_maximization"]((H, W), (H, W), {}, probe_cfg, None)
+    probe_ev = synthetic_bos_events(200_000, (H, W), smooth_flow((H, W), seed=99), seed=4242).astype(np.float64)
+    flow0 = np.random.default_rng(7).uniform(-0.5, 0.5, (2, H, W))
+    mine = torch.from_numpy(probe_slv.estimate(probe_ev, flow0=flow0)).to(dev)
+    ref0 = mine.clone()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.broadcast(ref0, src=0)
+    rms = torch.sqrt(torch.mean((mine - ref0) ** 2)).reshape(1)
+    if world > 1:
+        dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+    parity = {"check": "every rank solves the same 200 k-event probe window (40 Adam iterations, tie-free start); "
+                       "max over ranks of the RMS distance to rank 0's flow", "rms_px": float(rms), "bar_px": 1e-3,
+              "ok": bool(float(rms) <= 1e-3)}
+    # launches of ONE solver iteration, counted from a stream capture of the public one-call iteration
+    tiny = ops.PreparedWindow(torch.from_numpy(synthetic_events(4096, (H, W), seed=1)).to(dev), (H, W), "first", True)
+    f_t = torch.zeros((2, H, W), device=dev)
+    m_t, v_t, st_t = torch.zeros_like(f_t), torch.zeros_like(f_t), torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_t = ops.CmaxWorkspace(H, W, (0, 0), dev)
+    it_launches, it_other = ops.count_launches(lambda: ops.cmax_adam_iteration(tiny, f_t, m_t, v_t, st_t, ws_t, COST, 1.0, TV_WEIGHT))
+    del tiny, f_t, m_t, v_t, ws_t
     # pinned host buffers (the e2e contract: inputs come from pinned host memory), handed over as numpy views
     pinned = [torch.from_numpy(synthetic_bos_events(n, (H, W), gt, seed=1000 * rank + i).astype(np.float64)).pin_memory()
               for i in range(max(2, conc))]
     windows = [t.numpy() for t in pinned]
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(1 if quick else max(1, min(args.warmup, 2))):
         slv.estimate(windows[0])
     if conc > 1:
         slv.estimate_many(windows[:conc] * 2, concurrency=conc)   # warm-up of every stream slot (staging buffers)
-    n_solves = max(args.steps, 4 * conc)
+    n_solves = 2 * conc if quick else max(args.steps, 4 * conc)
     batch = [windows[i % len(windows)] for i in range(n_solves)]
     barrier(world)
     with ClockSampler(local) as clocks:
-        t0 = time.perf_counter()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         if conc > 1:
@@ -504,28 +616,38 @@ def run_solve(args, rank, world, local):
         ms = max_over_ranks(ms, world)
         clocks.soak(lambda: None, max_s=0.5)
     if rank != 0:
-        return
+        return None
     peak, peak_kind = measured_peak_gbs()
     alg = iters * (32 * n + 25 * P_BYTES)
-    line = {"metric": "windows/s full per-window flow solve", "value": world / (ms * 1e-3), "unit": "windows/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"full per-window dense flow solve, {n} BOS-like events, 1280x720, {COST}+{TV_WEIGHT}*TV, "
-                                   f"Adam lr 0.05, {iters} iterations, zero init; host events in -> host flow out; "
-                                   f"{conc} independent windows in flight per GPU",
-                       "iterations": iters, "windows_timed": n_solves, "concurrency": conc},
-            "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": "whole solve (all kernels)", "achieved": alg / (ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "peak_source": peak_kind},
-            "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": 16 * n,
-                    "d2h_bytes_per_step": 2 * P_BYTES},
-            "gpu_launches": n_solves * iters * 7}
+    rec = {"metric": "windows/s full per-window flow solve", "value": world / (ms * 1e-3), "unit": "windows/s",
+           "n_gpus": world, "ms_per_window_per_gpu": ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": f"full per-window dense flow solve, {n} BOS-like events, 1280x720, {COST}+{TV_WEIGHT}*TV, "
+                                  f"Adam lr 0.05, K = {iters} iterations, zero init; host events in -> host flow out; "
+                                  f"{conc} independent windows in flight per GPU; windows sharded over the ranks, no collective",
+                      "iterations": iters, "windows_timed_per_gpu": n_solves, "concurrency": conc},
+           "parity_self_check": parity,
+           "clocks": clocks.summary(),
+           "roofline": {"bound": "hbm", "kernel": "whole solve (all kernels)", "achieved": alg / (ms * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                        "peak_source": peak_kind, "algorithmic_bytes_per_window": alg},
+           "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": 32 * n,
+                   "d2h_bytes_per_step": 4 * P_BYTES},
+           "gpu_launches": n_solves * iters * it_launches,
+           "launches_per_iteration": {"kernels": it_launches, "memset_nodes": it_other}}
     if not args.no_cpu and world == 1:
         s_per_it, cores = cpu_reference_solve(n, 3)
-        line["cpu_baseline"] = {"value": 1.0 / (s_per_it * iters), "unit": "windows/s", "cores": cores, "kind": "port",
-                                "sample": f"3 Adam iterations of the oracle loop timed ({s_per_it:.3f} s/it), x{iters}"}
-    print(json.dumps(line), flush=True)
+        rec["cpu_baseline"] = {"value": 1.0 / (s_per_it * iters), "unit": "windows/s", "cores": cores, "kind": "port",
+                               "sample": f"3 Adam iterations of the oracle loop timed ({s_per_it:.3f} s/it), x{iters}"}
+    return rec
+
+
+def run_solve(args, rank, world, local):
+    rec = solve_record(args, rank, world, local)
+    if rank != 0:
+        return
+    rec.update({"steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_window_per_gpu"], "vs_baseline": None})
+    print(json.dumps(rec), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -581,8 +703,7 @@ def run_eklt(args, rank, world, local):
 
     cfg = json.loads(json.dumps(HOT_PLATE1_SOLVER))
     cfg["optimizer"]["n_iter"] = args.solve_iters
-    cfg["eklt"] = {"precision": args.eklt_precision, "cuda_graph": not args.eklt_no_graph,
-                   "cache_graphs": args.eklt_cache_graphs}
+    cfg["eklt"] = {"precision": args.eklt_precision, "cuda_graph": not args.eklt_no_graph}
     slv = solver.collections["patch_eklt_pyramid2"]((H, W), (720, 640), {}, cfg, None)
     ev, frame = eklt_inputs(args.solve_events, seed=rank)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -612,31 +733,12 @@ def run_eklt(args, rank, world, local):
             per_level_legacy[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
         finally:
             os.environ.pop("EBOS_EKLT_LEGACY", None)
-        if args.eklt_ab_seg:                          # opt-in: experimental segment-form column pass of the gather
-            os.environ["EBOS_EKLT_GATHER_SEG"] = "1"
+        for sw, store in (("EBOS_EKLT_GATHER_SEG", per_level_seg), ("EBOS_EKLT_STORED", per_level_stored)):
+            os.environ[sw] = "0"                      # A/B: the pre-round-2 kernels (warp-per-cell gather, re-evaluating backward)
             try:
-                per_level_seg[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+                store[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
             finally:
-                os.environ.pop("EBOS_EKLT_GATHER_SEG", None)
-        if args.eklt_ab_stored:                       # opt-in: experimental stored-planes backward
-            os.environ["EBOS_EKLT_STORED"] = "1"
-            try:
-                per_level_stored[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
-            finally:
-                os.environ.pop("EBOS_EKLT_STORED", None)
-    iter_ms = {}
-    if args.eklt_ab_tail:      # opt-in A/B of the experimental single-kernel tail (EBOS_EKLT_TAIL=1): evaluation + Adam
-        for patch, ph, pw in slv.levels:
-            lvl = prob.level(patch)
-            th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous().clone()
-            m, v = torch.zeros_like(th), torch.zeros_like(th)
-            step = torch.zeros(1, dtype=torch.int32, device=th.device)
-            iter_ms[patch] = {"default": graph_time_ms(lambda: lvl.adam_iteration(th, m, v, step), 20)}
-            os.environ["EBOS_EKLT_TAIL"] = "1"
-            try:
-                iter_ms[patch]["tail_kernel"] = graph_time_ms(lambda: lvl.adam_iteration(th, m, v, step), 20)
-            finally:
-                os.environ.pop("EBOS_EKLT_TAIL", None)
+                os.environ.pop(sw, None)
     if rank != 0:
         return
     iters = [args.solve_iters // (len(slv.levels) + 1 - s + 1) for s in range(1, len(slv.levels) + 1)]
@@ -653,7 +755,7 @@ def run_eklt(args, rank, world, local):
             "config": {"workload": f"configs/hot_plate1.yaml pipeline: PatchEkltPyramid2.estimate, {args.solve_events} "
                                    f"synthetic events + synthetic frame, 1280x720, ROI [0:720,320:960], n_iter "
                                    f"{args.solve_iters} -> {sum(iters)} iterations over 4 levels; host events + frame in "
-                                   f"-> host flow out" + ("; graphs cached across windows" if args.eklt_cache_graphs else ""),
+                                   f"-> host flow out",
                        "iterations_per_level": iters,
                        "l2_policy": "working set 25 planes x 7.4 MB (fp64) > L2"},
             "clocks": clocks.summary(),
@@ -662,8 +764,8 @@ def run_eklt(args, rank, world, local):
                          "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_kind},
             "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy,
-            "eval_ms_per_level_stored_planes": per_level_stored or None,
-            "eval_ms_per_level_segment_gather": per_level_seg or None, "iteration_ms_per_level": iter_ms or None,
+            "eval_ms_per_level_without_stored_planes": per_level_stored or None,
+            "eval_ms_per_level_without_segment_gather": per_level_seg or None,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
             "gpu_launches": args.steps * sum(iters) * 12}
@@ -676,12 +778,43 @@ def run_eklt(args, rank, world, local):
     print(json.dumps(line), flush=True)
 
 
-def run_giant(args, rank, world, local):
+def giant_parity_check(rank, world, local):
+    """In-process self-check of the event-sharded path on a 2 Mi-event probe window: the sharded loss / gradient
+    against the single-GPU fused evaluation of the same window (bar 1e-5, north_star atomic-mode tolerance), and
+    bit-identity of the gradient across ranks (every rank must apply the same Adam step)."""
+    from event_based_bos_b200 import ops, sharding
+    from event_based_bos_b200.utils import synthetic_events, synthetic_flow
+
+    dev = torch.device("cuda", local)
+    n = 1 << 21
+    ev = torch.from_numpy(synthetic_events(n, (H, W), seed=77)).to(dev)
+    flow = torch.from_numpy(synthetic_flow((H, W), seed=77)).to(dev)
+    s0, s1 = sharding.shard_events(n, rank, world)
+    obj = sharding.cuda_event_sharded_objective(ev[s0:s1].contiguous(), (H, W), cost=COST, tv_weight=TV_WEIGHT)
+    loss, grad = obj.value_and_grad(flow)
+    loss, grad = loss.clone(), grad.clone()
+    same = all_ranks_equal(grad, world) and all_ranks_equal(loss, world)
+    out = {"check": "2 Mi-event probe window: event-sharded loss / gradient vs the single-GPU fused evaluation; gradient "
+                    "bit-identical on every rank", "ranks_bit_identical": bool(same), "bar": 1e-5}
+    if rank == 0:
+        win = ops.PreparedWindow(ev, (H, W), "first", True)
+        l1, g1 = ops.cmax_value_and_grad(win, flow, COST, 1.0, TV_WEIGHT)
+        out["loss_rel_err"] = abs(float(loss) - float(l1)) / abs(float(l1))
+        out["grad_rel_err"] = rel_max(grad, g1)
+        out["ok"] = bool(same and out["loss_rel_err"] <= 1e-5 and out["grad_rel_err"] <= 1e-5)
+    del obj
+    barrier(world)
+    return out
+
+
+def giant_record(args, rank, world, local):
     """BASELINE config 5: ONE window of `--giant-events` events sharded by events over the ranks (strong scaling):
-    partial IWE -> NCCL all-reduce -> cost (redundant) -> partial dflow -> NCCL all-reduce (sharding.py)."""
+    partial IWE -> exchange 1 -> cost (redundant) -> partial dflow -> exchange 2 (sharding.py).  At N = 1 the same
+    window runs on one GPU without exchange: the reference point of the strong-scaling curve."""
     from event_based_bos_b200 import sharding
     from event_based_bos_b200.utils import synthetic_flow
 
+    parity = giant_parity_check(rank, world, local)
     n_total = args.giant_events
     s0, s1 = sharding.shard_events(n_total, rank, world)
     n = s1 - s0
@@ -700,35 +833,48 @@ def run_giant(args, rank, world, local):
     def step():
         obj.value_and_grad(flow)
 
+    steps = max(args.steps, 10)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier(world)
     with ClockSampler(local) as clocks:
-        ms = max_over_ranks(cuda_time_ms(step, args.steps), world)
+        ms = max_over_ranks(cuda_time_ms(step, steps), world)
         barrier(world)
         # clock samples under load: a FIXED number of extra steps (the step holds collectives, so a time-based
         # soak would let the ranks run different counts and dead-lock)
-        for _ in range(max(100, 4 * args.steps)):
+        for _ in range(100):
             step()
         torch.cuda.synchronize()
         barrier(world)
+    exchange = getattr(obj, "exchange", "none")
+    launches = getattr(obj, "launches_per_evaluation", None)
+    del obj
     if rank != 0:
-        return
+        return None
     peak, peak_kind = measured_peak_gbs()
     alg = 32 * n_total + world * 11 * P_BYTES   # the plane work is replicated on every rank
-    line = {"metric": "events/s fwd+bwd warp->IWE->cost", "value": n_total / (ms * 1e-3), "unit": "events/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    return {"metric": "events/s fwd+bwd warp->IWE->cost (one event-sharded window)", "value": n_total / (ms * 1e-3),
+            "unit": "events/s", "n_gpus": world, "ms_per_step": ms, "steps": steps, "higher_is_better": True,
+            "scaling": "strong", "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"single giant window of {n_total} synthetic events sharded by events over {world} GPU(s), "
-                                   f"1280x720, fp32, {COST}+{TV_WEIGHT}*TV forward+backward; partial IWE and partial dflow "
-                                   f"exchanged by: {getattr(obj, 'exchange', 'nccl all-reduce')}",
+                                   f"1280x720, fp32, {COST}+{TV_WEIGHT}*TV forward+backward",
                        "events_total": n_total, "events_per_gpu": n, "l2_policy": "inputs larger than L2"},
+            "exchange": exchange,
+            "exchange_bytes_per_evaluation_per_rank": 0 if world == 1 else 3 * P_BYTES,   # partial IWE (P) + partial dflow (2P)
+            "parity_self_check": parity,
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": "whole evaluation (all kernels + collectives)",
+            "roofline": {"bound": "hbm", "kernel": "whole evaluation (all kernels + exchanges)",
                          "achieved": alg / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / world / peak, "traffic": None, "peak_source": peak_kind},
-            "gpu_launches": 8 * args.steps}
-    print(json.dumps(line), flush=True)
+            "gpu_launches": (launches or 7) * steps}
+
+
+def run_giant(args, rank, world, local):
+    rec = giant_record(args, rank, world, local)
+    if rank != 0:
+        return
+    rec.update({"warmup": max(args.warmup, 3), "vs_baseline": None})
+    print(json.dumps(rec), flush=True)
 
 
 def main():
@@ -740,17 +886,13 @@ def main():
     ap.add_argument("--workload", default="fused", choices=["fused", "solve", "giant", "eklt"])
     ap.add_argument("--giant-events", type=int, default=1 << 27)
     ap.add_argument("--events", type=int, default=1 << 24)
-    ap.add_argument("--cpu-events", type=int, default=1 << 22)
+    ap.add_argument("--cpu-events", type=int, default=0, help="events per CPU step (0 = the GPU arm's window size)")
+    ap.add_argument("--no-subrecords", action="store_true", help="default workload: skip small_windows / solve / giant")
     ap.add_argument("--solve-events", type=int, default=500000)
     ap.add_argument("--solve-iters", type=int, default=600)
     ap.add_argument("--solve-concurrency", type=int, default=8, help="independent windows in flight per GPU (solve workload)")
     ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
-    ap.add_argument("--eklt-ab-tail", action="store_true", help="also time evaluation + Adam with EBOS_EKLT_TAIL=1")
-    ap.add_argument("--eklt-ab-stored", action="store_true", help="also time the evaluation with EBOS_EKLT_STORED=1")
-    ap.add_argument("--eklt-ab-seg", action="store_true", help="also time the evaluation with EBOS_EKLT_GATHER_SEG=1")
-    ap.add_argument("--eklt-cache-graphs", action="store_true",
-                    help="experimental: keep buffers and CUDA graphs across windows (solver.eklt.cache_graphs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")

@@ -56,7 +56,7 @@ SIGNATURES = {
                                    c_void_p, c_void_p]),
     "ebos_cmax_value_and_grad": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, c_int, c_void_p]),
     "ebos_cmax_adam_iteration": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double, c_void_p,
@@ -88,6 +88,8 @@ SIGNATURES = {
     "ebos_flow_error": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p]),
     "ebos_blur3": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "ebos_capture_begin": (c_int, [c_void_p]),
+    "ebos_capture_end_count": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -13,7 +13,9 @@
 // kernels of the hot path spread their per-CTA partial sums over 16 slots; the consumers add the slots up.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "ebos_common.cuh"
 
@@ -30,15 +32,20 @@ struct AuxLane {
   cudaEvent_t fork = nullptr, join = nullptr, cost_done = nullptr, fin_done = nullptr;
   bool ok = false;
 };
-static AuxLane* aux_lane() {
-  static AuxLane lanes[64];
+// One lane per (device, caller stream), created on first use and kept for the process: solves that run concurrently on
+// different streams (ContrastMaximizationDense.estimate_many in eager mode, several host threads) must not share
+// the lane's stream and events -- a shared lane adds false cross-window dependencies, and a second thread re-recording
+// `fork` between the first one's record and wait would let its TV kernel read a flow that is still being updated.
+static AuxLane* aux_lane(cudaStream_t caller) {
+  static std::map<std::pair<int, cudaStream_t>, AuxLane> lanes;
   static std::mutex mu;
   static const bool disabled = getenv("EBOS_NO_OVERLAP") != nullptr;
   if (disabled) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  AuxLane& L = lanes[dev];
+  if (lanes.size() > 4096) return nullptr;   // (streams come and go in a long-lived process: fall back to no overlap)
+  AuxLane& L = lanes[std::make_pair(dev, caller)];
   if (!L.ok) {
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -855,7 +862,7 @@ int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W
 int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                              int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
-                             double* acc, void* stream) {
+                             double* acc, int clean_workspace, void* stream) {
   EBOS_REQUIRE(window && flow && iwe && dflow && loss && acc && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0,
                "ebos_cmax_value_and_grad: bad argument");
   EBOS_REQUIRE(kind == EBOS_COST_VARIANCE || kind == EBOS_COST_GRADMAG, "ebos_cmax_value_and_grad: unknown cost kind");
@@ -867,10 +874,19 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   // one memset node for the accumulators AND the IWE when the caller laid them out back to back (ops.CmaxWorkspace does)
   const size_t iwe_bytes = (size_t)Hp * Wp * dtype_size(dtype);
   const bool adjacent = reinterpret_cast<char*>(acc) + EBOS_ACC_DOUBLES * sizeof(double) == reinterpret_cast<char*>(iwe);
-  cudaError_t e = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double) + (adjacent ? iwe_bytes : 0), st);
-  if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
+  // clean_workspace: the caller guarantees acc and iwe are all zero on entry and gets them back all zero -- the zero-fill
+  // for the NEXT evaluation then runs on the auxiliary lane concurrently with the backward instead of in front of the splat
+  auto zero_workspace = [&](cudaStream_t s) -> cudaError_t {
+    cudaError_t z = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double) + (adjacent ? iwe_bytes : 0), s);
+    if (z == cudaSuccess && !adjacent) z = cudaMemsetAsync(iwe, 0, iwe_bytes, s);
+    return z;
+  };
+  if (!clean_workspace) {
+    cudaError_t e = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double) + (adjacent ? iwe_bytes : 0), st);
+    if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
+  }
   // fork: TV(flow) -> dflow on the auxiliary lane, concurrently with splat + cost on `st`
-  AuxLane* lane = aux_lane();
+  AuxLane* lane = aux_lane(st);
   cudaStream_t tv_st = st;
   if (lane) {
     if (cudaEventRecord(lane->fork, st) == cudaSuccess && cudaStreamWaitEvent(lane->stream, lane->fork, 0) == cudaSuccess)
@@ -885,7 +901,7 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(join)");
   if (rc) return rc;
-  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent);
+  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent && !clean_workspace);
   if (rc) return rc;
   // variance: no gradient plane, the backward derives it from (iwe, acc)
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
@@ -902,10 +918,13 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
     else
       k_loss_finalize<float><<<1, 1, 0, s>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (float*)loss);
   };
+  // (the gradient-magnitude backward reads neither the IWE nor the accumulators: their zero-fill follows the loss on the lane)
+  const bool zero_on_lane = clean_workspace && kind == EBOS_COST_GRADMAG;
   bool fin_on_lane = false;
   if (lane && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
       cudaStreamWaitEvent(lane->stream, lane->cost_done, 0) == cudaSuccess) {
     finalize(lane->stream);
+    if (zero_on_lane && zero_workspace(lane->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(zero)");
     fin_on_lane = cudaEventRecord(lane->fin_done, lane->stream) == cudaSuccess;
     if (!fin_on_lane) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(fin)");
   }
@@ -919,6 +938,8 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
   } else {
     finalize(st);
   }
+  if (clean_workspace && !(fin_on_lane && zero_on_lane) && zero_workspace(st) != cudaSuccess)
+    return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(zero)");
   EBOS_LAUNCH_CHECK("ebos_cmax_value_and_grad");
   return EBOS_OK;
 }
@@ -938,7 +959,7 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_adam_iteration: omit_boundary needs an image larger than 2x2");
   cudaStream_t st = as_stream(stream);
   // graph nodes of one iteration: [IWE memset] [TV + step++ | splat] [cost] [backward] [Adam + loss + acc reset]
-  AuxLane* lane = aux_lane();
+  AuxLane* lane = aux_lane(st);
   cudaStream_t tv_st = st;
   if (lane) {
     if (cudaEventRecord(lane->fork, st) == cudaSuccess && cudaStreamWaitEvent(lane->stream, lane->fork, 0) == cudaSuccess)
@@ -953,7 +974,7 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st, step_dev);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(join)");
   if (rc) return rc;
-  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, true);
+  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, false);   // iwe is zero on entry
   if (rc) return rc;
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
   if (dtype == EBOS_F64)
@@ -961,10 +982,22 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   else
     rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
   if (rc) return rc;
+  // zero-fill of the IWE for the next iteration: the gradient-magnitude backward does not read the IWE, so it runs on
+  // the lane concurrently with the backward (2 us off the critical path of a ~30 us iteration); the variance backward
+  // derives dL/dIWE from the IWE, so there it follows the backward
+  const size_t iwe_bytes = (size_t)Hp * Wp * dtype_size(dtype);
+  bool zero_on_lane = false;
+  if (lane && kind == EBOS_COST_GRADMAG && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
+      cudaStreamWaitEvent(lane->stream, lane->cost_done, 0) == cudaSuccess) {
+    if (cudaMemsetAsync(iwe, 0, iwe_bytes, lane->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(zero)");
+    zero_on_lane = cudaEventRecord(lane->fin_done, lane->stream) == cudaSuccess;
+    if (!zero_on_lane) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(zero event)");
+  }
   if (lane && cudaStreamWaitEvent(st, lane->join, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(wait)");
   rc = window_backward_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc, omit_boundary,
                               data_scale, dflow, st);
   if (rc) return rc;
+  if (!zero_on_lane && cudaMemsetAsync(iwe, 0, iwe_bytes, st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(zero)");
   const FinalizeArgs fin{1, kind, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, acc, loss};
   const int64_t np = (int64_t)2 * H * W;
   cudaError_t le;
@@ -975,6 +1008,7 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
     le = launch_pdl(k_adam<float>, dim3(adam_grid(np)), dim3(256), st, (float*)flow, (const float*)dflow, (float*)exp_avg,
                     (float*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, 2, fin);
   if (le != cudaSuccess) return cuda_fail(le, "ebos_cmax_adam_iteration(adam)");
+  if (zero_on_lane && cudaStreamWaitEvent(st, lane->fin_done, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(wait zero)");
   EBOS_LAUNCH_CHECK("ebos_cmax_adam_iteration");
   return EBOS_OK;
 }

@@ -64,7 +64,7 @@ struct Workspace {
   double* colsum;    // [W]
   double* colS;      // [W]  sum_i sign(D) * q over the ROI rows of each column
   char* T1;          // [4,H,pw+2pad] T: column pass of the transposed up-sampling
-  char* St;          // [6,H,W] T: stored forward planes (EBOS_EKLT_STORED=1)
+  char* St;          // [6,H,W] T: stored forward planes (stored-planes backward)
   char* pf;          // [2,ph,pw] T
   char* q;           // [H,W] T
   char* F;           // [2,H,W] T
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_backward(Geom g, int fl
   }
 }
 
-// EXPERIMENTAL (EBOS_EKLT_STORED=1, off by default; not yet run on hardware): the backward from six planes stored by the
+// Default since round 2 (EBOS_EKLT_STORED=0 selects the re-evaluating k_backward): the backward from six planes stored by the
 // forward instead of re-evaluating up-sampling, sample positions and the eight gathered taps (530 instructions per pixel in
 // k_backward, ncu r01i; DRAM at 9 % -- instructions are the scarce resource here, bytes are not).
 template <typename T>
@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(256) k_backward_stored(Geom g, int flags, cons
     }
   }
 }
-static bool stored_planes() {
+static bool stored_planes() {   // default ON (measured on B200: -5 % per evaluation at every level); EBOS_EKLT_STORED=0 disables
   const char* v = getenv("EBOS_EKLT_STORED");
-  return v != nullptr && v[0] != '\0' && v[0] != '0';
+  return v == nullptr || v[0] != '0';
 }
 
 // One CTA per padded cell (A,B): sums the four dense gradient planes over the cell's 2*patch x 2*patch support with
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(Geom g, int nch, const T* _
   if (lane == 0) dPad[((int64_t)c * PH + A) * PW + B] = (T)s;
 }
 
-// EXPERIMENTAL (EBOS_EKLT_GATHER_SEG=1, off by default; not yet run on hardware): column pass for small patches.  A warp
+// Default since round 2 for patch <= 32 (EBOS_EKLT_GATHER_SEG=0 disables): column pass for small patches.  A warp
 // reads 32 consecutive pixels of a row ONCE (coalesced, all lanes busy), lane groups of `patch` lanes -- aligned with the
 // runs of equal floor cell -- reduce their lo / hi weighted sums with shuffles, and the group leaders add them to the two
 // column cells of T1 (zeroed first; <= 2 contributions per address).  k_gather_cols leaves half a warp idle at 8-px patches
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(256) k_gather_rows_thread(Geom g, int nch, con
     s += (double)cell_weight<T>(A, i, g.h1, g.patch) * (double)T1[((int64_t)c * g.H + i) * PW + B];
   dPad[((int64_t)c * PH + A) * PW + B] = (T)s;
 }
-static bool gather_segments() {
+static bool gather_segments() {   // default ON (measured on B200: -6 % per evaluation at patch 16 / 8); EBOS_EKLT_GATHER_SEG=0 disables
   const char* v = getenv("EBOS_EKLT_GATHER_SEG");
-  return v != nullptr && v[0] != '\0' && v[0] != '0';
+  return v == nullptr || v[0] != '0';
 }
 
 // Same for small supports (patch <= 16: at most 1024 pixels per cell): one WARP per padded cell, eight cells per CTA,
@@ -529,78 +529,6 @@ __global__ void k_param_grad(Geom g, int flags, const T* __restrict__ dP, const 
   }
 }
 
-// EXPERIMENTAL (EBOS_EKLT_TAIL=1, off by default; not yet run on hardware): the launch tail of one solver iteration --
-// k_fold + k_param_grad + k_adam + k_adam_bump, four tiny launches (~20 us of fixed cost per iteration in the r01i launch
-// list) -- as ONE single-CTA kernel: fold the padding into dP, barrier, then per patch cell the parameter gradient and
-// the Adam update of its channels; thread 0 writes the loss and advances the step counter.
-struct AdamArgs {
-  void* theta;
-  void* exp_avg;
-  void* exp_avg_sq;
-  double lr, b1, b2, eps;
-  int32_t* step_dev;
-};
-template <typename T>
-__global__ void __launch_bounds__(1024) k_tail(Geom g, int flags, int nch, const T* __restrict__ dPad, T* __restrict__ dP,
-                                               const double* __restrict__ tv_acc, double* __restrict__ acc, double w_data,
-                                               double w_tv, double w_pxy, T* __restrict__ grad, T* __restrict__ loss,
-                                               AdamArgs ad) {
-  __shared__ T s_coef[2];
-  const int np = g.ph * g.pw;
-  for (int k = threadIdx.x; k < nch * np; k += blockDim.x) dP[k] = fold_at<T>(g, dPad, k / np, (k % np) / g.pw, k % g.pw);
-  if (threadIdx.x == 0) {
-    const int step = *ad.step_dev + 1;
-    s_coef[0] = (T)(ad.lr / (1.0 - pow(ad.b1, (double)step)));
-    s_coef[1] = (T)(1.0 / sqrt(1.0 - pow(ad.b2, (double)step)));
-  }
-  __syncthreads();                               // dP (global, written by this CTA) and the coefficients are visible
-  T* theta = reinterpret_cast<T*>(ad.theta);
-  T* m = reinterpret_cast<T*>(ad.exp_avg);
-  T* v = reinterpret_cast<T*>(ad.exp_avg_sq);
-  const T b1 = (T)ad.b1, b2 = (T)ad.b2, eps = (T)ad.eps, step_size = s_coef[0], inv_bc2_sqrt = s_coef[1];
-  const int nf = flow_channels(flags), nt = theta_channels(flags);
-  for (int k = threadIdx.x; k < np; k += blockDim.x) {
-    T gk[4];
-    if (flags & kPoisson) {
-      gk[0] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
-    } else {
-      gk[0] = dP[k];
-      gk[1] = dP[np + k];
-    }
-    if (flags & kWarp) {
-      gk[nf] = dP[2 * np + k];
-      gk[nf + 1] = dP[3 * np + k];
-    }
-    for (int c = 0; c < nt; ++c) {
-      const int64_t e = (int64_t)c * np + k;
-      grad[e] = gk[c];
-      T p1 = theta[e], m1 = m[e], v1 = v[e];
-      adam_one<T>(p1, gk[c], m1, v1, b1, b2, eps, step_size, inv_bc2_sqrt);
-      theta[e] = p1; m[e] = m1; v[e] = v1;
-    }
-  }
-  if (threadIdx.x == 0) {
-    double tv = acc_sum(acc, kAccTvSum);
-    if (tv_acc) {
-      tv = tv_acc[3];
-      for (int i = 24; i < EBOS_ACC_DOUBLES; ++i) tv += tv_acc[i];
-    }
-    const double hw = (double)g.H * (double)g.W;
-    const double tv_mean = tv / (2.0 * hw), pxy_mean = (flags & kWarp) ? acc_sum(acc, kAccPxy) / hw : 0.0;
-    const double total = w_data * acc[kAccMax] + w_tv * tv_mean + w_pxy * pxy_mean;
-    acc[kAccData] = acc[kAccMax];
-    acc[kAccTv] = tv_mean;
-    acc[kAccPxyMean] = pxy_mean;
-    acc[kAccLoss] = total;
-    *loss = (T)total;
-    *ad.step_dev += 1;
-  }
-}
-static bool tail_kernel() {
-  const char* v = getenv("EBOS_EKLT_TAIL");
-  return v != nullptr && v[0] != '\0' && v[0] != '0';
-}
-
 // up-sampling on its own: the dense fields returned to the caller (flow from the intensity, translation)
 template <typename T>
 __global__ void __launch_bounds__(256) k_upsample(Geom g, const T* __restrict__ P, int channels, T* __restrict__ out) {
@@ -647,7 +575,7 @@ static int check_geometry(const Geom& g) {
 template <typename T>
 static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* gx, const T* gy, const T* meas,
                             const T* winv, const T* weights, double w_data, double w_tv, double w_pxy, void* workspace,
-                            T* loss, T* grad, cudaStream_t st, const AdamArgs* adam = nullptr) {
+                            T* loss, T* grad, cudaStream_t st) {
   const Workspace w = carve(workspace, g.H, g.W, g.ph, g.pw, g.pad, sizeof(T));
   cudaError_t e = cudaMemsetAsync(w.acc, 0, (kAccN + 2 * (size_t)g.W) * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset");
@@ -718,12 +646,6 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
     k_gather_cols<T><<<dim3((PW + 7) / 8, g.H), 256, 0, st>>>(g, nch, dU, T1);
     k_gather_rows<T><<<(nch * n_cells + 7) / 8, 256, 0, st>>>(g, nch, T1, dPad);
   }
-  if (adam) {        // experimental single-kernel tail (fold + parameter gradient + Adam + step counter)
-    k_tail<T><<<1, 1024, 0, st>>>(g, flags, nch, dPad, dP, tv_from_flow_tv ? w.tv_acc : nullptr, w.acc, w_data, w_tv,
-                                  w_pxy, grad, loss, *adam);
-    EBOS_LAUNCH_CHECK("ebos_eklt tail");
-    return EBOS_OK;
-  }
   k_fold<T><<<(nch * np + 127) / 128, 128, 0, st>>>(g, nch, dPad, dP);
   k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, flags, dP, tv_from_flow_tv ? w.tv_acc : nullptr, w.acc, w_data,
                                                     w_tv, w_pxy, grad, loss);
@@ -780,25 +702,6 @@ int ebos_eklt_adam_iteration(void* theta, int flags, const void* grad_x, const v
                              void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int32_t* step_dev,
                              void* stream) {
   EBOS_REQUIRE(exp_avg && exp_avg_sq && step_dev, "ebos_eklt_adam_iteration: null argument");
-  if (tail_kernel() && (dtype == EBOS_F32 || dtype == EBOS_F64) && theta && grad_x && grad_y && measured &&
-      weight_inverse && workspace && loss && grad && (flags & ~(kPoisson | kWarp | kNoPolarity)) == 0) {
-    const Geom g = make_geom(H, W, ph, pw, patch, roi_x0, roi_x1, roi_y0, roi_y1);
-    const int rcg = check_geometry(g);
-    if (rcg != EBOS_OK) return rcg;
-    if (workspace_bytes < ebos_eklt_workspace_bytes(H, W, ph, pw, patch, dtype)) {
-      set_error("ebos_eklt_adam_iteration: workspace too small");
-      return EBOS_ERR_WORKSPACE;
-    }
-    const AdamArgs ad{theta, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_dev};
-    cudaStream_t st = as_stream(stream);
-    if (dtype == EBOS_F64)
-      return value_and_grad_t<double>(g, flags, (const double*)theta, (const double*)grad_x, (const double*)grad_y,
-                                      (const double*)measured, (const double*)weight_inverse, (const double*)weights,
-                                      w_data, w_tv, w_pxy, workspace, (double*)loss, (double*)grad, st, &ad);
-    return value_and_grad_t<float>(g, flags, (const float*)theta, (const float*)grad_x, (const float*)grad_y,
-                                   (const float*)measured, (const float*)weight_inverse, (const float*)weights, w_data,
-                                   w_tv, w_pxy, workspace, (float*)loss, (float*)grad, st, &ad);
-  }
   const int rc = ebos_eklt_value_and_grad(theta, flags, grad_x, grad_y, measured, weight_inverse, weights, H, W, ph, pw,
                                           patch, roi_x0, roi_x1, roi_y0, roi_y1, w_data, w_tv, w_pxy, dtype, workspace,
                                           workspace_bytes, loss, grad, stream);

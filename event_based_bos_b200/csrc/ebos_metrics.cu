@@ -180,6 +180,36 @@ int ebos_flow_error(const void* flow_gt, const void* flow_pred, const uint8_t* e
 
 size_t ebos_flow_error_workspace_doubles(int batch) { return batch > 0 ? (size_t)batch * kErrSlots : 0; }
 
+int ebos_capture_begin(void* stream) {
+  cudaError_t e = cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_capture_begin");
+  return EBOS_OK;
+}
+
+int ebos_capture_end_count(void* stream, int32_t* n_kernel_nodes, int32_t* n_other_nodes) {
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(as_stream(stream), &graph);
+  if (e != cudaSuccess || !graph) return cuda_fail(e, "ebos_capture_end_count");
+  size_t n = 0;
+  int32_t kernels = 0, others = 0;
+  e = cudaGraphGetNodes(graph, nullptr, &n);
+  if (e == cudaSuccess && n > 0) {
+    cudaGraphNode_t* nodes = new cudaGraphNode_t[n];
+    e = cudaGraphGetNodes(graph, nodes, &n);
+    for (size_t i = 0; e == cudaSuccess && i < n; ++i) {
+      cudaGraphNodeType t;
+      e = cudaGraphNodeGetType(nodes[i], &t);
+      if (e == cudaSuccess) { if (t == cudaGraphNodeTypeKernel) ++kernels; else ++others; }
+    }
+    delete[] nodes;
+  }
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_capture_end_count(nodes)");
+  if (n_kernel_nodes) *n_kernel_nodes = kernels;
+  if (n_other_nodes) *n_other_nodes = others;
+  return EBOS_OK;
+}
+
 int ebos_blur3(const void* image, int batch, int H, int W, double sigma, int adjoint, int dtype, void* out, void* stream) {
   EBOS_REQUIRE(image && out && batch > 0 && H >= 2 && W >= 2 && sigma > 0.0 && image != out, "ebos_blur3: bad argument");
   if (dtype != EBOS_F32 && dtype != EBOS_F64) { set_error("ebos_blur3: unsupported dtype"); return EBOS_ERR_UNSUPPORTED; }

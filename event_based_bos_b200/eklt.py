@@ -311,58 +311,6 @@ class EkltLevel:
         return theta
 
 
-class PersistentLevelSolver:
-    """EXPERIMENTAL (solver.eklt.cache_graphs, off by default; not yet run on hardware).  One pyramid level whose
-    parameter / Adam buffers and captured CUDA graph outlive a window: `EkltLevel.solve` captures a new graph per level
-    and per window (a few ms of host time each; about a third of `estimate()` is host-side).  Here the graph is captured
-    on the first window and only REPLAYED afterwards; the caller refreshes the problem's planes in place
-    (`EkltProblem.update_`) and hands in the new start values."""
-
-    def __init__(self, problem: "EkltProblem", patch: int, n_iter: int, lr: float = 0.05):
-        self.level = problem.level(patch)
-        self.n_iter, self.lr = int(n_iter), float(lr)
-        shape = (problem.channels, self.level.ph, self.level.pw)
-        self.theta = torch.zeros(shape, dtype=problem.dtype, device=problem.device)
-        self.m, self.v = torch.zeros_like(self.theta), torch.zeros_like(self.theta)
-        self.step = torch.zeros(1, dtype=torch.int32, device=problem.device)
-        self.unroll = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if self.n_iter % u == 0) if self.n_iter > 0 else 1
-        self.graph = None
-
-    def _reset(self, theta0: torch.Tensor) -> None:
-        self.theta.copy_(theta0.to(device=self.theta.device, dtype=self.theta.dtype))
-        self.m.zero_()
-        self.v.zero_()
-        self.step.zero_()
-
-    def _iteration(self) -> None:
-        self.level.adam_iteration(self.theta, self.m, self.v, self.step, self.lr)
-
-    def run(self, theta0: torch.Tensor) -> torch.Tensor:
-        """`n_iter` Adam iterations from theta0 on the CURRENT contents of the problem's planes.  Returns the persistent
-        parameter buffer (clone it to keep the values beyond the next `run`)."""
-        if self.n_iter <= 0:
-            self._reset(theta0)
-            return self.theta
-        if self.graph is None:
-            cur = torch.cuda.current_stream()
-            side = torch.cuda.Stream(device=self.theta.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                self._reset(theta0)
-                self._iteration()                # warm-up outside capture
-                graph = torch.cuda.CUDAGraph()
-                graph.capture_begin()
-                for _ in range(self.unroll):
-                    self._iteration()
-                graph.capture_end()
-            cur.wait_stream(side)
-            self.graph = graph
-        self._reset(theta0)
-        for _ in range(self.n_iter // self.unroll):
-            self.graph.replay()
-        return self.theta
-
-
 def resize_params(theta: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
     """Seed of a finer level: torchvision `resize` of the coarser result (src/solver/patch_eklt_pyramid2.py:243-246) =
     bilinear, align_corners=False.  A [3,h,w] -> [3,2h(-1),2w(-1)] interpolation of at most 90x160 values, once per

@@ -326,16 +326,21 @@ class CmaxWorkspace:
         self.grad_iwe = torch.empty_like(self.iwe)
         self.dflow = torch.empty((2, H, W), dtype=self.dtype, device=device)
         self.loss = torch.zeros(1, dtype=self.dtype, device=device)
+        # "clean workspace" protocol of the fused entries: accumulators and IWE are all zero between calls (they are
+        # zero-filled for the NEXT evaluation concurrently with the backward of the current one).  Cleared for good by a
+        # call that keeps its IWE (`keep_iwe=True`) or by anyone writing into `acc` / `iwe` directly.
+        self.clean = True
 
 
 def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
                         data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
                         omit_boundary: bool = False, outer_padding: Tuple[int, int] = (0, 0),
-                        workspace: Optional[CmaxWorkspace] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                        workspace: Optional[CmaxWorkspace] = None, keep_iwe: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """(loss [1], dL/dflow [2,H,W]) of   data_weight * L_cost(IWE(warp(events, flow))) + tv_weight * TV(flow).
 
     One C call, five kernels, no host synchronisation and no materialised warped events or [4N]
-    temporaries.  The returned tensors alias `workspace` (overwritten by the next call)."""
+    temporaries.  The returned tensors alias `workspace` (overwritten by the next call).  `keep_iwe=True` leaves the
+    IWE of this evaluation in `workspace.iwe` (the workspace then zero-fills at the start of every later call)."""
     _check_cuda(flow, tv_weights)
     _check_flow(window, flow)
     if cost not in COST_KINDS:
@@ -348,10 +353,12 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
         tvw = tv_weights.to(window.dtype).contiguous()
         if tuple(tvw.shape) != (window.H, window.W):
             raise ValueError(f"tv_weights must be [{window.H},{window.W}], got {tuple(tvw.shape)}")
+    if keep_iwe:
+        ws.clean = False
     check(_capi.load().ebos_cmax_value_and_grad(
         ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw,
         COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code,
-        ptr(ws.iwe), ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), current_stream()),
+        ptr(ws.iwe), ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), int(ws.clean), current_stream()),
         "ebos_cmax_value_and_grad")
     return ws.loss, ws.dflow
 
@@ -394,8 +401,9 @@ def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: tor
                         omit_boundary: bool = False, lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999),
                         eps: float = 1e-8) -> torch.Tensor:
     """One solver iteration in one C call: objective + gradient (like `cmax_value_and_grad`) and the Adam update of
-    `flow` in place.  `workspace.acc` must be zero on entry (it is left zero), `step_dev` (int32 [1]) counts the
-    completed iterations.  Returns `workspace.loss` (the objective before the update)."""
+    `flow` in place.  `workspace.acc` and `workspace.iwe` must be zero on entry (a fresh or `clean` CmaxWorkspace; they
+    are left zero), `step_dev` (int32 [1]) counts the completed iterations.  Returns `workspace.loss` (the objective
+    before the update)."""
     _check_cuda(flow, tv_weights, exp_avg, exp_avg_sq, step_dev)
     _check_flow(window, flow)
     ws = workspace
@@ -404,6 +412,8 @@ def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: tor
     tvw = None
     if tv_weights is not None:
         tvw = tv_weights.to(window.dtype).contiguous()
+    if not ws.clean:
+        raise RuntimeError("cmax_adam_iteration needs a clean CmaxWorkspace (accumulators and IWE zero on entry)")
     check(_capi.load().ebos_cmax_adam_iteration(
         ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw, COST_KINDS[cost],
         int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code, ptr(ws.iwe),
@@ -493,7 +503,17 @@ def flow_total_variation(flow: torch.Tensor, weights: Union[float, torch.Tensor,
     dtype_code(flow)
     w = None
     if isinstance(weights, torch.Tensor):
-        w = weights.to(device=flow.device, dtype=flow.dtype).expand(flow.shape[1], flow.shape[2]).contiguous()
+        w = weights.to(device=flow.device, dtype=flow.dtype)
+        # upstream multiplies `torch.gradient(flow)[0]` [2,H,W] by `weights`, i.e. anything that broadcasts against it
+        # (src/costs/image_gradient.py:69-70): scalars, [H,W], [1,H,W] (a `mask[None]` ROI weight) and per-channel [2,H,W]
+        if w.dim() == 3 and w.shape[0] == 2:
+            zero = torch.zeros_like(flow[0])
+            per_channel = w.expand(2, flow.shape[1], flow.shape[2])
+            return (_FlowTv.apply(torch.stack([flow[0], zero]), per_channel[0].contiguous())
+                    + _FlowTv.apply(torch.stack([zero, flow[1]]), per_channel[1].contiguous()))
+        if w.dim() == 3:
+            w = w[0]
+        w = w.expand(flow.shape[1], flow.shape[2]).contiguous()
     elif weights is not None and float(weights) != 1.0:
         w = torch.full(flow.shape[1:], float(weights), dtype=flow.dtype, device=flow.device)
     return _FlowTv.apply(flow, w)
@@ -530,3 +550,23 @@ def blur3(image: torch.Tensor, sigma: float) -> torch.Tensor:
         raise ValueError("sigma must be positive")
     dtype_code(image)
     return _Blur3.apply(image, float(sigma))
+
+
+def count_launches(fn) -> Tuple[int, int]:
+    """(kernel launches, other graph nodes such as memsets) that `fn()` enqueues on the current stream, counted from a
+    throw-away stream capture (nothing runs).  `fn` must be capture-safe: no allocation, no host synchronisation."""
+    import ctypes
+
+    _capi.require_device()
+    lib = _capi.load()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    k, o = ctypes.c_int32(0), ctypes.c_int32(0)
+    with torch.cuda.stream(side):
+        check(lib.ebos_capture_begin(side.cuda_stream), "ebos_capture_begin")
+        try:
+            fn()
+        finally:
+            check(lib.ebos_capture_end_count(side.cuda_stream, ctypes.byref(k), ctypes.byref(o)), "ebos_capture_end_count")
+    torch.cuda.current_stream().wait_stream(side)
+    return int(k.value), int(o.value)

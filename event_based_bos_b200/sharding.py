@@ -59,9 +59,9 @@ def solve_windows(solve_fn: Callable[[int], torch.Tensor], n_windows: int, gathe
     r, R = rank_world()
     per_rank = (n_windows + R - 1) // R
     proto = next(iter(local.values())) if local else None
-    shape = _broadcast_shape(proto)
+    shape, dtype = _broadcast_shape(proto)
     device = proto.device if proto is not None else _default_device()
-    block = torch.zeros((per_rank,) + shape, dtype=torch.float32, device=device)
+    block = torch.zeros((per_rank,) + shape, dtype=dtype, device=device)   # the solvers' own dtype (float64 flows stay float64)
     for j, w in enumerate(mine):
         block[j].copy_(local[w])
     blocks = [torch.empty_like(block) for _ in range(R)]
@@ -77,15 +77,23 @@ def _default_device():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
-def _broadcast_shape(proto: Optional[torch.Tensor]) -> Tuple[int, ...]:
-    """All ranks must agree on the flow shape even if some own no window."""
+_GATHER_DTYPES = (torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int32, torch.int64)
+
+
+def _broadcast_shape(proto: Optional[torch.Tensor]) -> Tuple[Tuple[int, ...], torch.dtype]:
+    """All ranks must agree on the shape AND dtype of a window's result even if some own no window."""
     dev = proto.device if proto is not None else _default_device()
-    shp = torch.zeros(4, dtype=torch.int64, device=dev)
+    shp = torch.zeros(6, dtype=torch.int64, device=dev)
     if proto is not None:
+        if proto.dim() > 4 or proto.dtype not in _GATHER_DTYPES:
+            raise TypeError(f"solve_windows(gather=True) cannot gather a {proto.dtype} tensor of rank {proto.dim()}")
         shp[0] = proto.dim()
         shp[1:1 + proto.dim()] = torch.tensor(proto.shape, device=dev)
+        shp[5] = _GATHER_DTYPES.index(proto.dtype) + 1
     dist.all_reduce(shp, op=dist.ReduceOp.MAX)
-    return tuple(int(v) for v in shp[1:1 + int(shp[0])])
+    if int(shp[5]) == 0:
+        raise RuntimeError("solve_windows(gather=True): no rank produced a result")
+    return tuple(int(v) for v in shp[1:1 + int(shp[0])]), _GATHER_DTYPES[int(shp[5]) - 1]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -268,4 +276,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
 
     obj = _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
     obj.exchange = "peer-memory one-shot" if p2p is not None else ("nccl all-reduce" if R0 > 1 else "none")
+    # kernels of this library per evaluation: TV, splat, cost (with the IWE reduction fused in on the peer path),
+    # backward, [peer sum], loss; the NCCL path adds two library all-reduces instead of the peer sum
+    obj.launches_per_evaluation = 6 if p2p is not None else 5
     return obj

@@ -72,9 +72,6 @@ class PatchEkltPyramid2(SolverBase):
         self._dtype = torch.float32 if str(ekc.get("precision", "64")) == "32" else torch.float64
         self.use_cuda_graph = bool(ekc.get("cuda_graph", True))
         self.store_history = bool(ekc.get("store_history", False))
-        # experimental: keep the problem buffers, levels and captured graphs across windows (eklt.PersistentLevelSolver)
-        self.cache_graphs = bool(ekc.get("cache_graphs", False))
-        self._persistent = None
         self.history = {}
         self.levels = eklt.pyramid_levels(tuple(self.orig_image_shape), 64, 8)
         self.coarest_scale, self.finest_scale = 1, len(self.levels) + 1        # upstream's spelling
@@ -133,21 +130,8 @@ class PatchEkltPyramid2(SolverBase):
         roi = (self.crop_xmin, self.crop_xmax, self.crop_ymin, self.crop_ymax)
         weights = tuple(float(self.cost_weight.get(k, 0.0)) for k in SUPPORTED_COSTS)
         planes = (self._gradient_x_torch, self._gradient_y_torch, self.cache_measured, self.weight_inverse)
-        runners = None
-        if self.cache_graphs and self.use_cuda_graph and not self.store_history:
-            if self._persistent is None:
-                problem = eklt.EkltProblem(*(p.clone() for p in planes), roi, weights, poisson=self.is_poisson_model,
-                                           warp=self.optimize_warp, no_polarity=self.no_polarity,
-                                           weights=None if self.cache_weights is None else self.cache_weights.clone())
-                self._persistent = (problem, {
-                    li: eklt.PersistentLevelSolver(problem, patch,
-                                                   self._opt_config["n_iter"] // (self.finest_scale - (li + 1) + 1), 0.05)
-                    for li, (patch, _, _) in enumerate(self.levels)})
-            problem, runners = self._persistent
-            problem.update_(*planes, self.cache_weights)
-        else:
-            problem = eklt.EkltProblem(*planes, roi, weights, poisson=self.is_poisson_model, warp=self.optimize_warp,
-                                       no_polarity=self.no_polarity, weights=self.cache_weights)
+        problem = eklt.EkltProblem(*planes, roi, weights, poisson=self.is_poisson_model, warp=self.optimize_warp,
+                                   no_polarity=self.no_polarity, weights=self.cache_weights)
         theta = None
         self.best_params_per_scale = {}
         self.history = {}
@@ -157,10 +141,7 @@ class PatchEkltPyramid2(SolverBase):
             x0 = self._start_parameters(li, theta)
             iters = self._opt_config["n_iter"] // (self.finest_scale - scale + 1)
             hist = [] if self.store_history else None
-            if runners is not None:
-                theta = runners[li].run(x0).clone()
-            else:
-                theta = problem.level(patch).solve(x0, iters, lr=0.05, cuda_graph=self.use_cuda_graph, history=hist)
+            theta = problem.level(patch).solve(x0, iters, lr=0.05, cuda_graph=self.use_cuda_graph, history=hist)
             self.best_params_per_scale[scale] = theta
             if hist is not None:
                 self.history[scale] = hist

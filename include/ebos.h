@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define EBOS_VERSION 100
+#define EBOS_VERSION 200
 
 /* error codes */
 #define EBOS_OK 0
@@ -193,16 +193,21 @@ EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int
  * (CUDA-graph capturable; the TV kernel and the scalar-loss kernel run on an internal auxiliary stream that is
  * forked from and joined back into `stream`).  iwe [Hp,Wp], grad_iwe [Hp,Wp] (scratch), dflow [2,H,W], loss [1],
  * acc double[EBOS_ACC_DOUBLES].  When `iwe` starts exactly at acc + EBOS_ACC_DOUBLES (one allocation, accumulators
- * first) both are zeroed by a single memset node. */
+ * first) both are zeroed by a single memset node.
+ * clean_workspace != 0: the caller guarantees that acc and iwe are ALL ZERO on entry and receives them all zero again
+ * (the IWE of this evaluation is then not available afterwards): the zero-fill for the next evaluation runs
+ * concurrently with the backward instead of in front of the splat.  clean_workspace == 0: nothing is assumed, the IWE
+ * of this evaluation is left in `iwe`. */
 EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W,
                              int pad_h, int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
-                             double* acc, void* stream);
+                             double* acc, int clean_workspace, void* stream);
 
 /* One complete SOLVER iteration (src/solver/patch_eklt_pyramid2.py:267-285: zero_grad / loss / backward / step):
  * ebos_cmax_value_and_grad followed by the Adam update of `flow`, as six graph nodes
- *   [IWE memset] [TV + step counter | splat] [cost] [backward] [Adam + loss + accumulator reset].
- * `acc` (double[EBOS_ACC_DOUBLES]) must be ZERO on entry and is left zero on exit; `step_dev` (int32[1]) counts the
+ *   [TV + step counter | splat] [cost] [backward | IWE memset] [Adam + loss + accumulator reset].
+ * `acc` (double[EBOS_ACC_DOUBLES]) AND `iwe` must be ZERO on entry and are left zero on exit (the IWE is zero-filled for
+ * the next iteration concurrently with the backward); `step_dev` (int32[1]) counts the
  * iterations done (0 before the first call) and is advanced by the call; `loss` receives this iteration's
  * objective value (before the update).  Capture once in a CUDA graph, replay n_iter times. */
 EBOS_API int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flow, int H, int W, int pad_h,
@@ -348,6 +353,12 @@ EBOS_API int ebos_flow_error(const void* flow_gt, const void* flow_pred, const u
  * image, out: [batch,H,W] of dtype, out must not alias image; H, W >= 2. */
 EBOS_API int ebos_blur3(const void* image, int batch, int H, int W, double sigma, int adjoint, int dtype, void* out,
                void* stream);
+
+/* Launch accounting (bench.py's `gpu_launches`): capture what the calls made between the two functions enqueue on
+ * `stream` (cudaStreamBeginCapture / EndCapture, relaxed mode) and count the graph's nodes -- kernel nodes (this
+ * library's kernels) and other nodes (memsets).  Nothing is executed; the graph is destroyed.  host pointers. */
+EBOS_API int ebos_capture_begin(void* stream);
+EBOS_API int ebos_capture_end_count(void* stream, int32_t* n_kernel_nodes, int32_t* n_other_nodes);
 
 #ifdef __cplusplus
 }

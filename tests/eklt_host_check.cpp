@@ -220,28 +220,6 @@ int eklt_host_tv(const int* dims, int is_f64, const void* F, const void* winv, d
   return 0;
 }
 
-// k_tail walked serially (float64): fold the padded gradient, parameter gradient, Adam update with 1-based `step`.
-int eklt_host_tail(const int* dims, int flags, const double* dPad, double* dP, double* grad, double* theta, double* m,
-                   double* v, double lr, double b1, double b2, double eps, int step) {
-  const Geom g = make_geom(dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]);
-  const int np = g.ph * g.pw, nch = (flags & kWarp) ? 4 : 2;
-  for (int k = 0; k < nch * np; ++k) dP[k] = fold_at<double>(g, dPad, k / np, (k % np) / g.pw, k % g.pw);
-  const double step_size = lr / (1.0 - pow(b1, (double)step)), inv_bc2_sqrt = 1.0 / sqrt(1.0 - pow(b2, (double)step));
-  const int nf = flow_channels(flags), nt = theta_channels(flags);
-  for (int k = 0; k < np; ++k) {
-    double gk[4];
-    if (flags & kPoisson) gk[0] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
-    else { gk[0] = dP[k]; gk[1] = dP[np + k]; }
-    if (flags & kWarp) { gk[nf] = dP[2 * np + k]; gk[nf + 1] = dP[3 * np + k]; }
-    for (int c = 0; c < nt; ++c) {
-      const int64_t e = (int64_t)c * np + k;
-      grad[e] = gk[c];
-      adam_one<double>(theta[e], gk[c], m[e], v[e], b1, b2, eps, step_size, inv_bc2_sqrt);
-    }
-  }
-  return 0;
-}
-
 // the same through the stored-planes backward (EBOS_EKLT_STORED=1), float64
 int eklt_host_backward_stored(const int* dims, int flags, const double* theta, const double* pf, const double* gx,
                               const double* gy, const double* weights, const double* meas, const double* dF,

@@ -37,7 +37,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _capi.load()
-    assert lib.ebos_version() == 100
+    assert lib.ebos_version() == 200
     assert isinstance(_capi.last_error(), str)
     # argument validation happens before any CUDA call: usable without a device
     assert lib.ebos_time_stats(None, -1, 1, 0, None, None) == -1

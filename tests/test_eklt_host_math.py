@@ -385,45 +385,6 @@ def test_tv_gather_form_matches_oracle_adjoint(gold, host_lib):
         assert abs(val.value - (np.abs(gx) + np.abs(gy)).sum()) <= 1e-12, (H, W, roi)
 
 
-def test_tail_arithmetic_matches_torch_adam(gold, host_lib):
-    """The experimental single-kernel tail (EBOS_EKLT_TAIL=1): fold + parameter gradient + Adam, serial build, against
-    the oracle's adjoints and torch.optim.Adam over several steps, for both parameterisations."""
-    import torch
-
-    rng = np.random.default_rng(4)
-    H, W, patch = 50, 70, 16
-    ph, pw = E.patch_grid((H, W), patch)
-    dims = (ctypes.c_int * 9)(H, W, ph, pw, patch, 0, H, 0, W)
-    host_lib.eklt_host_tail.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_double] * 4 + \
-                                       [ctypes.c_int]
-    for flags, nt in ((3, 3), (2, 4), (1, 1), (0, 2)):
-        nch = 4 if flags & 2 else 2
-        theta = rng.normal(size=(nt, ph, pw))
-        ref = torch.from_numpy(theta.copy()).requires_grad_()
-        opt = torch.optim.Adam([ref], lr=0.05)
-        m, v = np.zeros_like(theta), np.zeros_like(theta)
-        for step in range(1, 5):
-            dPad = np.zeros((4, ph + 2, pw + 2))
-            dPad[:nch] = rng.normal(size=(nch, ph + 2, pw + 2))
-            # oracle: fold = adjoint of the replicate padding; Sobel adjoint for the intensity channel
-            folded = np.zeros((nch, ph, pw))
-            rr = np.clip(np.arange(ph + 2) - 1, 0, ph - 1)
-            cc = np.clip(np.arange(pw + 2) - 1, 0, pw - 1)
-            np.add.at(folded, (slice(None), rr[:, None], cc[None, :]), dPad[:nch])
-            parts = [E.sobel_over_8_adjoint(folded[:2])[None] if flags & 1 else folded[:2]]
-            if flags & 2:
-                parts.append(folded[2:4])
-            g_ref = np.concatenate(parts)
-            dP, grad = np.zeros((4, ph, pw)), np.zeros((nt, ph, pw))
-            host_lib.eklt_host_tail(dims, flags, _p(dPad), _p(dP), _p(grad), _p(theta), _p(m), _p(v), 0.05, 0.9, 0.999,
-                                    1e-8, step)
-            assert np.abs(grad - g_ref).max() <= 1e-13
-            opt.zero_grad()
-            ref.grad = torch.from_numpy(g_ref.copy())
-            opt.step()
-            assert np.abs(theta - ref.detach().numpy()).max() <= 1e-14, (flags, step)
-
-
 def test_torch_op_restatement_matches_reference_and_analytic_oracle(gold):
     """oracle/spec_eklt_torch.py (the reference's torch ops + autograd; what the CPU arm of bench.py times) against the
     reference goldens, all levels, regimes and switch variants; and against the analytic numpy oracle on fresh inputs."""
@@ -462,7 +423,7 @@ def test_torch_op_restatement_matches_reference_and_analytic_oracle(gold):
 
 
 def test_stored_planes_backward_arithmetic_matches_reference(gold, host_lib):
-    """EBOS_EKLT_STORED=1 (experimental): the backward rebuilt from the six planes the forward stores gives the
+    """The stored-planes backward (default since round 2): the backward rebuilt from the six planes the forward stores gives the
     reference's gradient at every level and regime, and with event-histogram weights."""
     for scale, (patch, ph, pw) in enumerate(gold["levels_t"], 1):
         for name in ("start", "random", "far"):
@@ -541,7 +502,7 @@ def test_fp32_arithmetic_solve_within_1e3_px_of_reference(gold, host_lib):
 
 
 def test_segment_gather_arithmetic_matches_transposed_upsampling(host_lib):
-    """EBOS_EKLT_GATHER_SEG=1 (experimental): the warp/lane-group walk of k_gather_cols_seg + k_gather_rows_thread gives the
+    """The segment-form column gather (default since round 2): the warp/lane-group walk of k_gather_cols_seg + k_gather_rows_thread gives the
     transposed bilinear up-sampling R^T dU C for every even patch size dividing 32, with images that are not multiples of
     anything; the serial build also checks the alignment claim (one floor cell per lane group)."""
     rng = np.random.default_rng(12)

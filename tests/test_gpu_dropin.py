@@ -125,3 +125,25 @@ def test_error_behaviour():
         ebos.EventImageConverter((4, 4)).create_iwe(torch.zeros(3, 4).cuda(), method="polarity")
     with pytest.raises(RuntimeError):  # upstream's tensor 'count' is broken and raises
         ebos.EventImageConverter((4, 4)).create_iwe(torch.zeros(3, 4).cuda(), method="count")
+
+
+def test_image_gradient_weight_shapes_broadcast_like_upstream():
+    """`weights` may be anything that broadcasts against the [2,H,W] flow gradient upstream
+    (src/costs/image_gradient.py:69-70): [H,W], [1,H,W] (a `mask[None]` ROI weight), per-channel [2,H,W], scalars."""
+    import event_based_bos_b200 as ebos
+    from oracle import spec
+
+    rng = np.random.default_rng(21)
+    H, W = 19, 27
+    flow = torch.from_numpy(rng.uniform(-3, 3, (2, H, W)))
+    cost = ebos.costs.functions["image_gradient"]("minimize")
+    for w in (torch.from_numpy(rng.uniform(0.1, 2, (H, W))), torch.from_numpy(rng.uniform(0.1, 2, (1, H, W))),
+              torch.from_numpy(rng.uniform(0.1, 2, (2, H, W))), torch.from_numpy(rng.uniform(0.1, 2, (2, 1, 1))), 0.7):
+        f = flow.clone().cuda().requires_grad_()
+        loss = cost.calculate({"flow": f, "omit_boundary": False, "weights": w.cuda() if isinstance(w, torch.Tensor) else w})
+        loss.backward()
+        fr = flow.clone().requires_grad_()
+        ref = torch.mean(torch.abs(torch.gradient(fr, dim=1)[0] * w) + torch.abs(torch.gradient(fr, dim=2)[0] * w))
+        ref.backward()
+        assert abs(float(loss) - float(ref)) <= 1e-12 * abs(float(ref))
+        assert float((f.grad.cpu() - fr.grad).abs().max()) <= 1e-14

@@ -88,6 +88,10 @@ def _worker(rank, world, port, out_dir):
         assert sorted(flows) == [0, 1, 2, 3, 4] and all(float(flows[w][0, 0, 0]) == w for w in flows)
         mine = sharding.solve_windows(lambda w: torch.full((2, 3, 4), float(w)), 5, gather=False)
         assert sorted(mine) == list(range(rank, 5, world))
+        # the gathered flows keep the solvers' dtype (float64 results must not be squeezed through float32), also when
+        # a rank owns no window at all (1 window over 2 ranks)
+        f64 = sharding.solve_windows(lambda w: torch.full((2, 3, 4), 1.0 + 2.0 ** -40, dtype=torch.float64), 1, gather=True)
+        assert f64[0].dtype == torch.float64 and float(f64[0][0, 0, 0]) == 1.0 + 2.0 ** -40
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=loss.numpy(), grad=grad.numpy())
     finally:
         dist.destroy_process_group()
