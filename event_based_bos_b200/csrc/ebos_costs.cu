@@ -22,6 +22,7 @@
 namespace ebos {
 
 constexpr int kAccSpread = 16, kAccGradSlots = 8, kAccTvSlots = 24;
+constexpr int64_t kTvAfterSplatEvents = (int64_t)1 << 22;   // windows from 4 Mi events: TV kernel next to the cost kernel, not the splat
 static_assert(kAccTvSlots + kAccSpread == EBOS_ACC_DOUBLES, "accumulator layout");
 
 // The TV term depends only on the flow, the splat only on events + flow: inside the fused evaluation
@@ -689,6 +690,48 @@ __global__ void __launch_bounds__(256) k_sum_peers(const PeerPlanes<T> pl, int64
   for (int64_t i = done + tid; i < n; i += nth) out[i] = pl.load(i);
 }
 
+// Two-shot form of the same reduction for larger rank counts (the one-shot pass reads R whole planes per rank: 7 remote
+// planes = 52 MB per rank for the flow gradient at R = 8): (1) reduce-scatter -- rank r sums slice r of every peer's
+// buffer, IN PLACE into its own buffer (only rank r ever reads slice r of rank r's buffer); (2) after a barrier,
+// all-gather -- every rank copies slice q from rank q's buffer.  2 (R-1)/R planes per rank instead of R-1.
+template <typename T>
+__global__ void __launch_bounds__(256) k_reduce_slice(const PeerPlanes<T> pl, int64_t begin, int64_t end, T* dst) {   // (dst may alias a peer plane)
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  bool vec = sizeof(T) == 4 && ((begin | end) & 3) == 0 && (reinterpret_cast<size_t>(dst) & 15) == 0;
+  for (int r = 0; r < pl.n; ++r) vec = vec && (reinterpret_cast<size_t>(pl.p[r]) & 15) == 0;
+  if constexpr (sizeof(T) == 4) {
+    if (vec) {
+      for (int64_t i = (begin >> 2) + tid; i < (end >> 2); i += nth) {
+        float4 a = reinterpret_cast<const float4*>(pl.p[0])[i];
+        for (int r = 1; r < pl.n; ++r) {
+          const float4 b = reinterpret_cast<const float4*>(pl.p[r])[i];
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(dst)[i] = a;
+      }
+      return;
+    }
+  }
+  for (int64_t i = begin + tid; i < end; i += nth) dst[i] = pl.load(i);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather_slices(const PeerPlanes<T> pl, int64_t n, int64_t slice, T* __restrict__ out) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  bool vec = sizeof(T) == 4 && (slice & 3) == 0 && (n & 3) == 0 && (reinterpret_cast<size_t>(out) & 15) == 0;
+  for (int r = 0; r < pl.n; ++r) vec = vec && (reinterpret_cast<size_t>(pl.p[r]) & 15) == 0;
+  if constexpr (sizeof(T) == 4) {
+    if (vec) {
+      for (int64_t i = tid; i < (n >> 2); i += nth) {
+        const int owner = (int)min((i << 2) / slice, (int64_t)pl.n - 1);
+        reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(pl.p[owner])[i];
+      }
+      return;
+    }
+  }
+  for (int64_t i = tid; i < n; i += nth) out[i] = pl.p[(int)min(i / slice, (int64_t)pl.n - 1)][i];
+}
+
 // ---- launch helpers ----------------------------------------------------------------------------------
 // 2-D grid-stride launch shape for plane kernels: about `per_sm` CTAs per SM in total (the reductions end in
 // one same-address atomic per CTA, so fewer, longer-lived CTAs are better).
@@ -833,6 +876,48 @@ int ebos_sum_peers(const void* const* peers, int n_peers, int64_t n, int dtype, 
   return EBOS_OK;
 }
 
+int ebos_reduce_peers_slice(const void* const* peers, int n_peers, int64_t begin, int64_t end, int dtype, void* dst,
+                            void* stream) {
+  EBOS_REQUIRE(peers && dst && n_peers >= 1 && n_peers <= kMaxPeers && begin >= 0 && end >= begin, "ebos_reduce_peers_slice: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_reduce_peers_slice");
+  if (end == begin) return EBOS_OK;
+  const int64_t cnt = end - begin;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((cnt / 4 + 255) / 256, (int64_t)sm_count() * 8));
+  if (dtype == EBOS_F64) {
+    PeerPlanes<double> pl{};
+    pl.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) pl.p[r] = (const double*)peers[r];
+    k_reduce_slice<double><<<grid, 256, 0, as_stream(stream)>>>(pl, begin, end, (double*)dst);
+  } else {
+    PeerPlanes<float> pl{};
+    pl.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) pl.p[r] = (const float*)peers[r];
+    k_reduce_slice<float><<<grid, 256, 0, as_stream(stream)>>>(pl, begin, end, (float*)dst);
+  }
+  EBOS_LAUNCH_CHECK("ebos_reduce_peers_slice");
+  return EBOS_OK;
+}
+
+int ebos_gather_peers_slices(const void* const* peers, int n_peers, int64_t n, int64_t slice, int dtype, void* out, void* stream) {
+  EBOS_REQUIRE(peers && out && n_peers >= 1 && n_peers <= kMaxPeers && n >= 0 && slice >= 1, "ebos_gather_peers_slices: bad argument");
+  EBOS_CHECK_DTYPE(dtype, "ebos_gather_peers_slices");
+  if (n == 0) return EBOS_OK;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n / 4 + 255) / 256, (int64_t)sm_count() * 8));
+  if (dtype == EBOS_F64) {
+    PeerPlanes<double> pl{};
+    pl.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) pl.p[r] = (const double*)peers[r];
+    k_gather_slices<double><<<grid, 256, 0, as_stream(stream)>>>(pl, n, slice, (double*)out);
+  } else {
+    PeerPlanes<float> pl{};
+    pl.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) pl.p[r] = (const float*)peers[r];
+    k_gather_slices<float><<<grid, 256, 0, as_stream(stream)>>>(pl, n, slice, (float*)out);
+  }
+  EBOS_LAUNCH_CHECK("ebos_gather_peers_slices");
+  return EBOS_OK;
+}
+
 int ebos_flow_tv(const void* flow, const void* weights, int H, int W, double tv_scale, int dtype, double* acc,
                  void* dflow, void* stream) {
   EBOS_REQUIRE(flow && dflow && H > 0 && W > 0, "ebos_flow_tv: bad argument");
@@ -885,8 +970,17 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
     cudaError_t e = cudaMemsetAsync(acc, 0, EBOS_ACC_DOUBLES * sizeof(double) + (adjacent ? iwe_bytes : 0), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_cmax_value_and_grad memset");
   }
-  // fork: TV(flow) -> dflow on the auxiliary lane, concurrently with splat + cost on `st`
+  // fork: TV(flow) -> dflow on the auxiliary lane.  Small windows: concurrently with the splat (a 500 k-event splat is
+  // ~120 CTAs and leaves most SMs idle).  Large windows: the splat fills the machine on its own and a concurrent TV kernel
+  // only slows it down, so the fork comes AFTER the splat and the TV kernel shares the GPU with the (short, ramp-bound)
+  // cost kernel instead.
   AuxLane* lane = aux_lane(st);
+  const bool tv_after_splat = n >= kTvAfterSplatEvents;
+  int rc;
+  if (tv_after_splat) {
+    rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent && !clean_workspace);
+    if (rc) return rc;
+  }
   cudaStream_t tv_st = st;
   if (lane) {
     if (cudaEventRecord(lane->fork, st) == cudaSuccess && cudaStreamWaitEvent(lane->stream, lane->fork, 0) == cudaSuccess)
@@ -894,15 +988,16 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
     else
       lane = nullptr;
   }
-  int rc;
   if (dtype == EBOS_F64)
     rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, tv_st);
   else
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_value_and_grad(join)");
   if (rc) return rc;
-  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent && !clean_workspace);
-  if (rc) return rc;
+  if (!tv_after_splat) {
+    rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent && !clean_workspace);
+    if (rc) return rc;
+  }
   // variance: no gradient plane, the backward derives it from (iwe, acc)
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
   if (dtype == EBOS_F64)
@@ -958,8 +1053,15 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_adam_iteration: omit_boundary needs an image larger than 2x2");
   cudaStream_t st = as_stream(stream);
-  // graph nodes of one iteration: [IWE memset] [TV + step++ | splat] [cost] [backward] [Adam + loss + acc reset]
+  // graph nodes of one iteration: [TV + step++ | splat] [cost] [backward | IWE memset] [Adam + loss + acc reset]
+  // (large windows: [splat] [TV + step++ | cost] ..., see ebos_cmax_value_and_grad)
   AuxLane* lane = aux_lane(st);
+  const bool tv_after_splat = n >= kTvAfterSplatEvents;
+  int rc;
+  if (tv_after_splat) {
+    rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, false);   // iwe is zero on entry
+    if (rc) return rc;
+  }
   cudaStream_t tv_st = st;
   if (lane) {
     if (cudaEventRecord(lane->fork, st) == cudaSuccess && cudaStreamWaitEvent(lane->stream, lane->fork, 0) == cudaSuccess)
@@ -967,15 +1069,16 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
     else
       lane = nullptr;
   }
-  int rc;
   if (dtype == EBOS_F64)
     rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, tv_st, step_dev);
   else
     rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st, step_dev);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(join)");
   if (rc) return rc;
-  rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, false);   // iwe is zero on entry
-  if (rc) return rc;
+  if (!tv_after_splat) {
+    rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, false);   // iwe is zero on entry
+    if (rc) return rc;
+  }
   void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
   if (dtype == EBOS_F64)
     rc = iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)gplane, st);

@@ -195,12 +195,18 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
               "ebos_flow_tv")
         return ((acc[3] + acc[24:40].sum()) * (tv_weight / (2.0 * H * W))).to(window.dtype).reshape(1), dtv
 
-    # One-shot exchange over peer memory (2..8 ranks of one NVLink domain, gradient-magnitude objective): the partial
-    # IWE and the partial flow gradient live in symmetric memory (every rank's buffer mapped into every process);
-    # the IWE reduction is fused into the cost kernel's tile load (ebos_iwe_cost_peers), the gradient reduction is one
-    # pass over the peers (ebos_sum_peers); cross-rank ordering by the symmetric-memory device barriers.  Measured on
-    # 2 x B200 (profiles/tools/symm_probe.py): 24 / 30 us per exchange against 42 / 47 us for NCCL all-reduce at
-    # these sizes (3.7 / 7.4 MB, latency-bound).  EBOS_NO_P2P=1 or any failure to set it up falls back to NCCL.
+    # Exchange over peer memory (2..8 ranks of one NVLink domain): the partial IWE and the partial flow gradient live in
+    # symmetric memory (every rank's buffer mapped into every process); cross-rank ordering by the symmetric-memory
+    # device barriers.  Two forms:
+    #   one-shot (R <= 2, gradient magnitude): the IWE reduction is fused into the cost kernel's tile load
+    #            (ebos_iwe_cost_peers), the gradient reduction is one pass over the peers (ebos_sum_peers).  Measured on
+    #            2 x B200 (profiles/tools/symm_probe.py): 24 / 30 us per exchange against 42 / 47 us for NCCL all-reduce
+    #            at these sizes (3.7 / 7.4 MB, latency-bound).  Every rank reads R whole planes.
+    #   two-shot (R >= 4, and the variance objective, which needs the reduced IWE materialised): reduce-scatter in place
+    #            (rank r sums slice r of every peer's buffer into its own buffer: ebos_reduce_peers_slice), barrier,
+    #            all-gather (ebos_gather_peers_slices): 2 (R-1)/R planes per rank instead of R-1 -- at R = 8 the
+    #            one-shot gradient pass alone would pull 52 MB per rank over NVLink per evaluation.
+    # EBOS_NO_P2P=1 or any failure to set it up falls back to NCCL; EBOS_P2P_FORM=1|2 forces a form (A/B runs).
     p2p = None
     R0 = dist.get_world_size() if is_distributed() else 1
     if 2 <= R0 <= 8 and dev.type == "cuda" and dist.get_backend() == "nccl":
@@ -209,22 +215,31 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
 
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
-            if os.environ.get("EBOS_NO_P2P") or kind != _capi.COST_GRADMAG:
-                raise RuntimeError("peer-memory exchange not requested / not applicable")
+            if os.environ.get("EBOS_NO_P2P"):
+                raise RuntimeError("peer-memory exchange not requested")
             import torch.distributed._symmetric_memory as symm
 
             s_iwe = symm.empty(tuple(iwe.shape), dtype=window.dtype, device=dev)
-            s_df = symm.empty(tuple(dflow.shape), dtype=window.dtype, device=dev)
+            s_df = [symm.empty(tuple(dflow.shape), dtype=window.dtype, device=dev) for _ in range(2)]
         except Exception:
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank takes the same path
         if int(ok.item()):
             h_iwe = symm.rendezvous(s_iwe, dist.group.WORLD)
-            h_df = symm.rendezvous(s_df, dist.group.WORLD)
-            p2p = {"iwe": s_iwe, "df": s_df, "h_iwe": h_iwe, "h_df": h_df,
+            h_df = [symm.rendezvous(b, dist.group.WORLD) for b in s_df]
+            form = int(os.environ.get("EBOS_P2P_FORM", "0")) or (1 if R0 <= 2 else 2)
+            if kind != _capi.COST_GRADMAG:
+                form = 2
+            p2p = {"iwe": s_iwe, "df": s_df, "h_iwe": h_iwe, "h_df": h_df, "form": form, "count": 0,
                    "iwe_ptrs": (ctypes.c_void_p * R0)(*[int(v) for v in h_iwe.buffer_ptrs]),
-                   "df_ptrs": (ctypes.c_void_p * R0)(*[int(v) for v in h_df.buffer_ptrs])}
+                   "df_ptrs": [(ctypes.c_void_p * R0)(*[int(v) for v in h.buffer_ptrs]) for h in h_df]}
+            iwe_full = iwe                                     # plain plane for the gathered IWE (two-shot form)
             iwe = s_iwe                                        # the splat writes the symmetric plane
+
+    def _slice_bounds(n_elems: int, rank: int):
+        """Slice of a plane owned by `rank` in the two-shot form (multiples of 4 elements: 16-byte vector accesses)."""
+        per = ((n_elems + R0 - 1) // R0 + 3) // 4 * 4
+        return per, min(rank * per, n_elems), min((rank + 1) * per, n_elems)
 
     class _Lean(EventShardedObjective):
         """Same result with fewer passes: the TV kernel writes (tv_weight / R) * dTV straight into the gradient buffer
@@ -234,7 +249,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
 
         def value_and_grad(self, flow):
             if p2p is not None:
-                return self._value_and_grad_p2p(flow)
+                return self._value_and_grad_p2p(flow) if p2p["form"] == 1 else self._value_and_grad_p2p_two_shot(flow)
             st = current_stream()
             R = dist.get_world_size() if is_distributed() else 1
             Hp, Wp = H + 2 * ph, W + 2 * pw
@@ -257,7 +272,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             st = current_stream()
             R = R0
             Hp, Wp = H + 2 * ph, W + 2 * pw
-            part = p2p["df"]
+            part, h_part, part_ptrs = p2p["df"][0], p2p["h_df"][0], p2p["df_ptrs"][0]
             check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(part), st), "ebos_flow_tv")
             ops.window_splat(window, flow, outer_padding, out=p2p["iwe"])
             p2p["h_iwe"].barrier(channel=0)                   # every rank's partial IWE is complete
@@ -267,16 +282,56 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
                                            window.code, ptr(g_iwe), kind, ptr(p2p["iwe"]), ptr(acc), int(omit_boundary),
                                            data_weight, ptr(part), st), "ebos_window_backward")
             # every partial gradient is complete -- and every rank is past its cost kernel, so the IWE planes are free
-            p2p["h_df"].barrier(channel=0)
-            check(lib.ebos_sum_peers(p2p["df_ptrs"], R, dflow.numel(), window.code, ptr(dflow), st), "ebos_sum_peers")
-            p2p["h_df"].barrier(channel=1)                    # nobody refills its gradient plane while a peer reads it
+            h_part.barrier(channel=0)
+            check(lib.ebos_sum_peers(part_ptrs, R, dflow.numel(), window.code, ptr(dflow), st), "ebos_sum_peers")
+            h_part.barrier(channel=1)                         # nobody refills its gradient plane while a peer reads it
+            check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, H, W, int(omit_boundary), data_weight, tv_weight,
+                                         window.code, ptr(loss), st), "ebos_loss_finalize")
+            return loss, dflow
+
+        def _value_and_grad_p2p_two_shot(self, flow):
+            st = current_stream()
+            R, rank = R0, dist.get_rank()
+            Hp, Wp = H + 2 * ph, W + 2 * pw
+            k = p2p["count"] % 2                              # the gradient planes alternate: a peer may still be
+            p2p["count"] += 1                                 # gathering evaluation i while this rank starts i + 1
+            part, h_part, part_ptrs = p2p["df"][k], p2p["h_df"][k], p2p["df_ptrs"][k]
+            s_plane = p2p["iwe"]
+            check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(part), st), "ebos_flow_tv")
+            ops.window_splat(window, flow, outer_padding, out=s_plane)
+            # exchange 1 (partial IWEs): reduce-scatter in place, all-gather into a local plane
+            n_iwe = s_plane.numel()
+            per, b0, b1 = _slice_bounds(n_iwe, rank)
+            p2p["h_iwe"].barrier(channel=0)                   # every rank's partial IWE is complete
+            check(lib.ebos_reduce_peers_slice(p2p["iwe_ptrs"], R, b0, b1, window.code, ptr(s_plane), st), "ebos_reduce_peers_slice")
+            p2p["h_iwe"].barrier(channel=1)                   # every slice is reduced
+            check(lib.ebos_gather_peers_slices(p2p["iwe_ptrs"], R, n_iwe, per, window.code, ptr(iwe_full), st),
+                  "ebos_gather_peers_slices")
+            check(lib.ebos_iwe_cost(kind, ptr(iwe_full), Hp, Wp, int(omit_boundary), data_weight, window.code, ptr(acc),
+                                    ptr(g_iwe), st), "ebos_iwe_cost")
+            check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
+                                           window.code, ptr(g_iwe), kind, ptr(iwe_full), ptr(acc), int(omit_boundary),
+                                           data_weight, ptr(part), st), "ebos_window_backward")
+            # exchange 2 (partial gradients + TV / R each); passing this barrier also means every rank has finished
+            # gathering the IWE, so the symmetric IWE plane may be refilled by the next evaluation
+            n_df = part.numel()
+            per, b0, b1 = _slice_bounds(n_df, rank)
+            h_part.barrier(channel=0)
+            check(lib.ebos_reduce_peers_slice(part_ptrs, R, b0, b1, window.code, ptr(part), st), "ebos_reduce_peers_slice")
+            h_part.barrier(channel=1)
+            check(lib.ebos_gather_peers_slices(part_ptrs, R, n_df, per, window.code, ptr(dflow), st), "ebos_gather_peers_slices")
             check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, H, W, int(omit_boundary), data_weight, tv_weight,
                                          window.code, ptr(loss), st), "ebos_loss_finalize")
             return loss, dflow
 
     obj = _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
-    obj.exchange = "peer-memory one-shot" if p2p is not None else ("nccl all-reduce" if R0 > 1 else "none")
-    # kernels of this library per evaluation: TV, splat, cost (with the IWE reduction fused in on the peer path),
-    # backward, [peer sum], loss; the NCCL path adds two library all-reduces instead of the peer sum
-    obj.launches_per_evaluation = 6 if p2p is not None else 5
+    if p2p is None:
+        obj.exchange = "nccl all-reduce (2 per evaluation)" if R0 > 1 else "none"
+    elif p2p["form"] == 1:
+        obj.exchange = "peer-memory one-shot (IWE reduction fused into the cost kernel; 3 device barriers per evaluation)"
+    else:
+        obj.exchange = "peer-memory two-shot (reduce-scatter in place + all-gather for IWE and gradient; 4 device barriers per evaluation)"
+    # kernels of this library per evaluation: TV, splat, cost, backward, loss + the peer kernels (1 one-shot, 4 two-shot);
+    # the NCCL path uses two library all-reduces instead
+    obj.launches_per_evaluation = 5 if p2p is None else (6 if p2p["form"] == 1 else 9)
     return obj

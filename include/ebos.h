@@ -238,6 +238,15 @@ EBOS_API int ebos_adam_step_graph(void* param, const void* grad, void* exp_avg, 
 EBOS_API int ebos_iwe_cost_peers(int kind, const void* const* iwe_peers, int n_peers, int Hp, int Wp, int omit_boundary,
                         double scale, int dtype, double* acc, void* grad_iwe, void* stream);
 EBOS_API int ebos_sum_peers(const void* const* peers, int n_peers, int64_t n, int dtype, void* out, void* stream);
+/* Two-shot form for larger rank counts (the one-shot pass reads n_peers whole planes per rank):
+ *   ebos_reduce_peers_slice   dst[i] = sum_r peers[r][i] for i in [begin, end) (rank order).  dst may be peers[own rank]
+ *                             (in place: rank r reduces slice r into its own buffer, which only rank r reads there);
+ *   ebos_gather_peers_slices  out[i] = peers[min(i / slice, n_peers - 1)][i]: collect the reduced slices (after a barrier).
+ * Every rank ends with bit-identical values (one rank computes each element). */
+EBOS_API int ebos_reduce_peers_slice(const void* const* peers, int n_peers, int64_t begin, int64_t end, int dtype, void* dst,
+                            void* stream);
+EBOS_API int ebos_gather_peers_slices(const void* const* peers, int n_peers, int64_t n, int64_t slice, int dtype, void* out,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Event ingestion: raw sensor arrays (x:int16 sensor column, y:int16 sensor row, t:int32 us,
