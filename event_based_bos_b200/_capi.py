@@ -56,11 +56,11 @@ SIGNATURES = {
                                    c_void_p, c_void_p]),
     "ebos_cmax_value_and_grad": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_int, c_void_p]),
+                                         c_void_p, c_int, c_double, c_void_p, c_void_p]),
     "ebos_cmax_adam_iteration": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double, c_void_p,
-                                         c_void_p]),
+                                         c_double, c_void_p, c_void_p]),
     "ebos_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
                                c_int, c_int, c_void_p]),
     "ebos_iwe_cost_peers": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),

@@ -60,6 +60,7 @@ static AuxLane* aux_lane(cudaStream_t caller) {
 
 int window_splat_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                         int pad_w, int dtype, void* iwe, cudaStream_t st, bool zero_iwe);
+int blur3_launch(const void* in, int H, int W, double sigma, int adjoint, int dtype, void* out, cudaStream_t st);
 int window_backward_launch(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                            int pad_w, int dtype, const void* grad_iwe, int kind, const void* iwe, const double* acc,
                            int omit_boundary, double scale, void* dflow, cudaStream_t st);
@@ -811,6 +812,32 @@ static int adam_grid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n / 4 + 255) / 256, (int64_t)sm_count() * 8));
 }
 
+// Data objective on the (optionally blurred) IWE.  blur_sigma > 0: B = blur3(IWE) (the sigma > 0 branch of
+// EventImageConverter.create_image_from_events_tensor, src/event_image_converter.py:399-404), cost and dL/dB on B, then
+// dL/dIWE = blur3^T(dL/dB) back into the plane that held B -- the backward reads an explicit gradient plane in that
+// case also for the variance objective.  Returns in *gplane the plane ebos_window_backward must be given (NULL: derive
+// the variance gradient from the IWE on the fly).
+static int cost_with_blur(int kind, const void* iwe, int Hp, int Wp, int omit_boundary, double data_scale, int dtype,
+                          double* acc, void* grad_iwe, double blur_sigma, void* blur_plane, cudaStream_t st, void** gplane) {
+  int rc;
+  if (blur_sigma > 0.0) {
+    if (!blur_plane || !grad_iwe) { set_error("blur_sigma > 0 needs the blur_plane and grad_iwe scratch planes"); return EBOS_ERR_BAD_ARG; }
+    if (Hp < 2 || Wp < 2) { set_error("blur_sigma > 0 needs an image of at least 2 x 2 (reflect padding)"); return EBOS_ERR_BAD_ARG; }
+    rc = blur3_launch(iwe, Hp, Wp, blur_sigma, 0, dtype, blur_plane, st);
+    if (rc) return rc;
+    if (dtype == EBOS_F64) rc = iwe_cost_t<double>(kind, (const double*)blur_plane, Hp, Wp, omit_boundary, data_scale, acc, (double*)grad_iwe, st);
+    else rc = iwe_cost_t<float>(kind, (const float*)blur_plane, Hp, Wp, omit_boundary, data_scale, acc, (float*)grad_iwe, st);
+    if (rc) return rc;
+    rc = blur3_launch(grad_iwe, Hp, Wp, blur_sigma, 1, dtype, blur_plane, st);
+    *gplane = blur_plane;
+    return rc;
+  }
+  // variance: no gradient plane, the backward derives it from (iwe, acc)
+  *gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
+  if (dtype == EBOS_F64) return iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)*gplane, st);
+  return iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)*gplane, st);
+}
+
 }  // namespace ebos
 
 using namespace ebos;
@@ -947,9 +974,10 @@ int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int H, int W
 int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W, int pad_h,
                              int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
-                             double* acc, int clean_workspace, void* stream) {
+                             double* acc, int clean_workspace, double blur_sigma, void* blur_plane, void* stream) {
   EBOS_REQUIRE(window && flow && iwe && dflow && loss && acc && n >= 0 && H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0,
                "ebos_cmax_value_and_grad: bad argument");
+  EBOS_REQUIRE(blur_sigma >= 0.0, "ebos_cmax_value_and_grad: blur_sigma must not be negative");
   EBOS_REQUIRE(kind == EBOS_COST_VARIANCE || kind == EBOS_COST_GRADMAG, "ebos_cmax_value_and_grad: unknown cost kind");
   EBOS_REQUIRE(kind != EBOS_COST_GRADMAG || grad_iwe, "ebos_cmax_value_and_grad: GRADMAG needs the grad_iwe scratch plane");
   EBOS_CHECK_DTYPE(dtype, "ebos_cmax_value_and_grad");
@@ -998,12 +1026,8 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
     rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, !adjacent && !clean_workspace);
     if (rc) return rc;
   }
-  // variance: no gradient plane, the backward derives it from (iwe, acc)
-  void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
-  if (dtype == EBOS_F64)
-    rc = iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)gplane, st);
-  else
-    rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
+  void* gplane = nullptr;
+  rc = cost_with_blur(kind, iwe, Hp, Wp, omit_boundary, data_scale, dtype, acc, grad_iwe, blur_sigma, blur_plane, st, &gplane);
   if (rc) return rc;
   // The scalar loss only needs the accumulators (complete once the cost kernel here and the TV kernel on the lane are
   // done), not the backward: it is computed on the lane, concurrently with the backward.
@@ -1014,7 +1038,7 @@ int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const voi
       k_loss_finalize<float><<<1, 1, 0, s>>>(kind, acc, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, (float*)loss);
   };
   // (the gradient-magnitude backward reads neither the IWE nor the accumulators: their zero-fill follows the loss on the lane)
-  const bool zero_on_lane = clean_workspace && kind == EBOS_COST_GRADMAG;
+  const bool zero_on_lane = clean_workspace && (kind == EBOS_COST_GRADMAG || blur_sigma > 0.0);
   bool fin_on_lane = false;
   if (lane && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
       cudaStreamWaitEvent(lane->stream, lane->cost_done, 0) == cudaSuccess) {
@@ -1043,7 +1067,8 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
                              int kind, int omit_boundary, double data_scale, double tv_scale, const void* tv_weights,
                              int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss, double* acc, void* exp_avg,
                              void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int32_t* step_dev,
-                             void* stream) {
+                             double blur_sigma, void* blur_plane, void* stream) {
+  EBOS_REQUIRE(blur_sigma >= 0.0, "ebos_cmax_adam_iteration: blur_sigma must not be negative");
   EBOS_REQUIRE(window && flow && iwe && dflow && loss && acc && exp_avg && exp_avg_sq && step_dev && n >= 0 && H > 1 &&
                    W > 1 && pad_h >= 0 && pad_w >= 0,
                "ebos_cmax_adam_iteration: bad argument");
@@ -1079,18 +1104,15 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
     rc = window_splat_launch(window, n, flags, flow, H, W, pad_h, pad_w, dtype, iwe, st, false);   // iwe is zero on entry
     if (rc) return rc;
   }
-  void* gplane = kind == EBOS_COST_GRADMAG ? grad_iwe : nullptr;
-  if (dtype == EBOS_F64)
-    rc = iwe_cost_t<double>(kind, (const double*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (double*)gplane, st);
-  else
-    rc = iwe_cost_t<float>(kind, (const float*)iwe, Hp, Wp, omit_boundary, data_scale, acc, (float*)gplane, st);
+  void* gplane = nullptr;
+  rc = cost_with_blur(kind, iwe, Hp, Wp, omit_boundary, data_scale, dtype, acc, grad_iwe, blur_sigma, blur_plane, st, &gplane);
   if (rc) return rc;
   // zero-fill of the IWE for the next iteration: the gradient-magnitude backward does not read the IWE, so it runs on
   // the lane concurrently with the backward (2 us off the critical path of a ~30 us iteration); the variance backward
   // derives dL/dIWE from the IWE, so there it follows the backward
   const size_t iwe_bytes = (size_t)Hp * Wp * dtype_size(dtype);
   bool zero_on_lane = false;
-  if (lane && kind == EBOS_COST_GRADMAG && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
+  if (lane && (kind == EBOS_COST_GRADMAG || blur_sigma > 0.0) && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
       cudaStreamWaitEvent(lane->stream, lane->cost_done, 0) == cudaSuccess) {
     if (cudaMemsetAsync(iwe, 0, iwe_bytes, lane->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(zero)");
     zero_on_lane = cudaEventRecord(lane->fin_done, lane->stream) == cudaSuccess;

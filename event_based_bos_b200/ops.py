@@ -330,17 +330,27 @@ class CmaxWorkspace:
         # zero-filled for the NEXT evaluation concurrently with the backward of the current one).  Cleared for good by a
         # call that keeps its IWE (`keep_iwe=True`) or by anyone writing into `acc` / `iwe` directly.
         self.clean = True
+        self._blur = None
+
+    def blur_plane(self) -> torch.Tensor:
+        """Scratch plane of the blurred-IWE objective (`blur_sigma > 0`), allocated on first use."""
+        if self._blur is None:
+            self._blur = torch.empty_like(self.iwe)
+        return self._blur
 
 
 def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
                         data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
                         omit_boundary: bool = False, outer_padding: Tuple[int, int] = (0, 0),
-                        workspace: Optional[CmaxWorkspace] = None, keep_iwe: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                        workspace: Optional[CmaxWorkspace] = None, keep_iwe: bool = False,
+                        blur_sigma: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """(loss [1], dL/dflow [2,H,W]) of   data_weight * L_cost(IWE(warp(events, flow))) + tv_weight * TV(flow).
 
     One C call, five kernels, no host synchronisation and no materialised warped events or [4N]
     temporaries.  The returned tensors alias `workspace` (overwritten by the next call).  `keep_iwe=True` leaves the
-    IWE of this evaluation in `workspace.iwe` (the workspace then zero-fills at the start of every later call)."""
+    IWE of this evaluation in `workspace.iwe` (the workspace then zero-fills at the start of every later call).
+    `blur_sigma > 0`: the data objective is taken on torchvision's `gaussian_blur(IWE, kernel_size=3, sigma)`
+    (src/event_image_converter.py:399-404) and differentiated through it."""
     _check_cuda(flow, tv_weights)
     _check_flow(window, flow)
     if cost not in COST_KINDS:
@@ -358,8 +368,8 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
     check(_capi.load().ebos_cmax_value_and_grad(
         ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw,
         COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code,
-        ptr(ws.iwe), ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), int(ws.clean), current_stream()),
-        "ebos_cmax_value_and_grad")
+        ptr(ws.iwe), ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), int(ws.clean), float(blur_sigma),
+        ptr(ws.blur_plane()) if blur_sigma > 0 else 0, current_stream()), "ebos_cmax_value_and_grad")
     return ws.loss, ws.dflow
 
 
@@ -374,11 +384,13 @@ class CmaxGraph:
     def __init__(self, window: PreparedWindow, flow: torch.Tensor, cost: str = "gradient_magnitude",
                  data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
                  omit_boundary: bool = False, outer_padding: Tuple[int, int] = (0, 0),
-                 workspace: Optional[CmaxWorkspace] = None):
+                 workspace: Optional[CmaxWorkspace] = None, blur_sigma: float = 0.0):
         self.window, self.flow = window, flow
         self.ws = workspace or CmaxWorkspace(window.H, window.W, outer_padding, flow.device, window.dtype)
         self._tvw = None if tv_weights is None else tv_weights.to(window.dtype).contiguous()
-        args = (window, flow, cost, data_weight, tv_weight, self._tvw, omit_boundary, outer_padding, self.ws)
+        if blur_sigma > 0:
+            self.ws.blur_plane()                          # allocate outside the capture
+        args = (window, flow, cost, data_weight, tv_weight, self._tvw, omit_boundary, outer_padding, self.ws, False, blur_sigma)
         cur = torch.cuda.current_stream(flow.device)
         side = torch.cuda.Stream(device=flow.device)
         side.wait_stream(cur)
@@ -399,7 +411,7 @@ def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: tor
                         step_dev: torch.Tensor, workspace: CmaxWorkspace, cost: str = "gradient_magnitude",
                         data_weight: float = 1.0, tv_weight: float = 0.0, tv_weights: Optional[torch.Tensor] = None,
                         omit_boundary: bool = False, lr: float = 0.05, betas: Tuple[float, float] = (0.9, 0.999),
-                        eps: float = 1e-8) -> torch.Tensor:
+                        eps: float = 1e-8, blur_sigma: float = 0.0) -> torch.Tensor:
     """One solver iteration in one C call: objective + gradient (like `cmax_value_and_grad`) and the Adam update of
     `flow` in place.  `workspace.acc` and `workspace.iwe` must be zero on entry (a fresh or `clean` CmaxWorkspace; they
     are left zero), `step_dev` (int32 [1]) counts the completed iterations.  Returns `workspace.loss` (the objective
@@ -418,7 +430,8 @@ def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: tor
         ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw, COST_KINDS[cost],
         int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code, ptr(ws.iwe),
         ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), ptr(exp_avg), ptr(exp_avg_sq), float(lr),
-        float(betas[0]), float(betas[1]), float(eps), ptr(step_dev), current_stream()), "ebos_cmax_adam_iteration")
+        float(betas[0]), float(betas[1]), float(eps), ptr(step_dev), float(blur_sigma),
+        ptr(ws.blur_plane()) if blur_sigma > 0 else 0, current_stream()), "ebos_cmax_adam_iteration")
     return ws.loss
 
 

@@ -57,6 +57,12 @@ class ContrastMaximizationDense(SolverBase):
             raise ValueError(f"cmax.precision must be '32' or '64', got {self.precision!r}")
         self._dtype = torch.float64 if self.precision == "64" else torch.float32
         self.warp_direction = self.slv_config.get("warp_direction", "first")
+        # `iwe: {method: bilinear_vote, blur_sigma: s}` of the solver configs (configs/hot_plate1.yaml): the data cost is
+        # taken on the 3x3-Gaussian-blurred IWE (src/event_image_converter.py:399-404)
+        iwe_cfg = self.slv_config.get("iwe", {}) or {}
+        if iwe_cfg.get("method", "bilinear_vote") != "bilinear_vote":
+            raise NotImplementedError(f"iwe.method {iwe_cfg['method']!r}: only 'bilinear_vote' has a tensor branch upstream")
+        self.blur_sigma = float(iwe_cfg.get("blur_sigma", 0) or 0)
         opt = self.slv_config.get("optimizer", {})
         self._opt_method = opt.get("method", "Adam")
         self.n_iter = int(opt.get("n_iter", 600))
@@ -184,6 +190,8 @@ class ContrastMaximizationDense(SolverBase):
         window = ops.PreparedWindow(ev, (H, W), self.warp_direction, self.normalize_t_in_batch, dtype=self._dtype)
         pad = (self.padding, self.padding)
         ws = ops.CmaxWorkspace(H, W, pad, x0.device, self._dtype)
+        if self.blur_sigma > 0:
+            ws.blur_plane()                               # allocate outside the graph capture
         m, v = torch.zeros_like(x0), torch.zeros_like(x0)
         step_dev = torch.zeros(1, dtype=torch.int32, device=x0.device)
         hist = torch.zeros(max(self.n_iter, 1), dtype=self._dtype, device=x0.device) if self.store_history else None
@@ -193,7 +201,7 @@ class ContrastMaximizationDense(SolverBase):
         def iteration():
             # one C call: TV | splat -> cost -> backward -> Adam (+ loss, accumulator reset), six graph nodes
             ops.cmax_adam_iteration(window, x0, m, v, step_dev, ws, self.data_cost, self.data_weight, self.tv_weight,
-                                    None, self.omit_boundary, self.lr)
+                                    None, self.omit_boundary, self.lr, blur_sigma=self.blur_sigma)
             if hist is not None:
                 hist[count[0]].copy_(ws.loss[0])
                 count[0] += 1
@@ -248,7 +256,7 @@ class ContrastMaximizationDense(SolverBase):
         for _ in range(self.n_iter):
             optimizer.zero_grad()
             warped, _ = self.orig_warper.warp_event(ev, x0, "dense-flow", direction=self.warp_direction)
-            iwe = imager.create_iwe(warped, method="bilinear_vote", sigma=0)
+            iwe = imager.create_iwe(warped, method="bilinear_vote", sigma=self.blur_sigma)
             loss = self.cost_func.calculate({"iwe": iwe, "flow": x0, "weights": 1.0, "omit_boundary": self.omit_boundary})
             if self.store_history:
                 self.history["loss"].append(float(loss))

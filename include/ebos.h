@@ -197,11 +197,14 @@ EBOS_API int ebos_loss_finalize(int kind, const double* acc, int Hp, int Wp, int
  * clean_workspace != 0: the caller guarantees that acc and iwe are ALL ZERO on entry and receives them all zero again
  * (the IWE of this evaluation is then not available afterwards): the zero-fill for the next evaluation runs
  * concurrently with the backward instead of in front of the splat.  clean_workspace == 0: nothing is assumed, the IWE
- * of this evaluation is left in `iwe`. */
+ * of this evaluation is left in `iwe`.
+ * blur_sigma > 0: the objective is evaluated on gaussian_blur(IWE, kernel_size=3, sigma) -- the `iwe.blur_sigma` of the
+ * solver configs, src/event_image_converter.py:399-404 -- and back-propagated through the blur's exact adjoint;
+ * blur_plane [Hp,Wp] (scratch, required then) holds the blurred IWE and afterwards dL/dIWE. */
 EBOS_API int ebos_cmax_value_and_grad(const void* window, int64_t n, int flags, const void* flow, int H, int W,
                              int pad_h, int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
-                             double* acc, int clean_workspace, void* stream);
+                             double* acc, int clean_workspace, double blur_sigma, void* blur_plane, void* stream);
 
 /* One complete SOLVER iteration (src/solver/patch_eklt_pyramid2.py:267-285: zero_grad / loss / backward / step):
  * ebos_cmax_value_and_grad followed by the Adam update of `flow`, as six graph nodes
@@ -214,7 +217,7 @@ EBOS_API int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, 
                              int pad_w, int kind, int omit_boundary, double data_scale, double tv_scale,
                              const void* tv_weights, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
                              double* acc, void* exp_avg, void* exp_avg_sq, double lr, double beta1, double beta2,
-                             double eps, int32_t* step_dev, void* stream);
+                             double eps, int32_t* step_dev, double blur_sigma, void* blur_plane, void* stream);
 
 /* torch.optim.Adam step (src/solver/patch_eklt_pyramid2.py:262-264,284), in place.  `step` is
  * 1-based.  Elementwise over n values. */

@@ -177,3 +177,48 @@ def test_cost_registry_matches_reference(g):
         ebos.costs.HybridCost("minimize", {"no_such_cost": 1.0})
     hybrid.update_weight({k: 2.0 for k in names})
     assert hybrid.cost_func[names[0]]["weight"] == 2.0 and hybrid.cost_func[names[0]]["func"].name == names[0]
+
+
+@pytest.mark.parametrize("cost", ["gradient_magnitude", "image_variance"])
+def test_fused_objective_on_blurred_iwe_vs_oracle(cost):
+    """`iwe.blur_sigma` inside the fused entries (blur kernel -> cost -> adjoint blur -> backward): value and gradient
+    against autograd through the oracle's restatement of create_iwe(..., sigma) (fp32 1e-5, fp64 1e-11), eager, as a
+    captured graph, and through the solver (`solver.iwe.blur_sigma`)."""
+    from event_based_bos_b200 import ops, solver
+
+    H, W, n, sigma = 40, 56, 30000, 1.5
+    ev = torch.from_numpy(spec.synthetic_events(n, (H, W), seed=6))
+    flow = torch.from_numpy(spec.synthetic_flow((H, W), seed=6, max_val=4.0))
+    for dt, tol in ((torch.float32, 1e-5), (torch.float64, 1e-11)):
+        for omit, pad in ((False, 0), (True, 2)):
+            kw = dict(cost=cost, tv_weight=0.5, data_weight=1.0, omit_boundary=omit, outer_padding=(pad, pad), blur_sigma=sigma)
+            ref_loss, ref_grad = spec.cmax_value_and_grad(ev.to(dt), flow.to(dt), (H, W), **kw)
+            win = ops.PreparedWindow(ev.to(dt).cuda(), (H, W), "first", True, dtype=dt)
+            ws = ops.CmaxWorkspace(H, W, (pad, pad), "cuda", dt)
+            for _ in range(2):     # twice: the clean-workspace protocol must hold with the blur planes in play
+                loss, grad = ops.cmax_value_and_grad(win, flow.to(dt).cuda(), cost, 1.0, 0.5, None, omit, (pad, pad), ws,
+                                                     blur_sigma=sigma)
+                assert abs(float(loss) - float(ref_loss)) <= tol * abs(float(ref_loss)), (dt, omit)
+                err = float((grad.cpu().double() - ref_grad.double()).abs().max() / ref_grad.double().abs().max())
+                assert err <= tol, (dt, omit, err)
+            cap = ops.CmaxGraph(win, flow.to(dt).cuda(), cost, 1.0, 0.5, None, omit, (pad, pad), blur_sigma=sigma)
+            l2, g2 = cap.replay()
+            assert abs(float(l2) - float(ref_loss)) <= tol * abs(float(ref_loss))
+            assert float((g2.cpu().double() - ref_grad.double()).abs().max() / ref_grad.double().abs().max()) <= tol
+    # solver: 20 iterations with the blurred objective in fp64 against the oracle loop
+    cfg = {"outer_padding": 0, "warp_direction": "first", "iwe": {"method": "bilinear_vote", "blur_sigma": sigma},
+           "optimizer": {"method": "Adam", "n_iter": 20},
+           "cmax": {"cost_with_weight": {cost: 1.0, "image_gradient": 0.5}, "lr": 0.05, "precision": "64"}}
+    flow0 = np.random.default_rng(1).uniform(-1, 1, (2, H, W))
+    evd = ev.double()
+    x0 = torch.from_numpy(flow0).requires_grad_()
+    opt = torch.optim.Adam([x0], lr=0.05)
+    for _ in range(20):
+        opt.zero_grad()
+        spec.cmax_loss(evd, x0, (H, W), cost=cost, tv_weight=0.5, blur_sigma=sigma).backward()
+        opt.step()
+    for fused in (True, False):
+        cfg["cmax"]["fused"] = fused
+        slv = solver.collections["contrast_maximization"]((H, W), (H, W), {}, cfg, None)
+        got = slv.estimate(evd.numpy(), flow0=flow0)
+        assert float(np.sqrt(np.mean((got - x0.detach().numpy()) ** 2))) <= 1e-8, fused
