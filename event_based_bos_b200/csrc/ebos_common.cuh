@@ -297,6 +297,21 @@ inline int64_t max_items(int64_t n, int H, int W) { return n / kItemEvents + (in
 // table -> barrier -> ... -> barrier -> flush) is paid once per item, so longer items amortise it (EBOS_ITEM_EVENTS).
 int item_events();
 
+// "Blocked-striped" storage of DENSE fp32 windows (round 2).  The tile kernels give every thread 16 CONSECUTIVE sorted
+// events (so that flow gathers and cells repeat inside a thread) and read them as four 16-byte groups; with the sorted
+// stream stored linearly the 32 lanes of such a load are 64 bytes apart, i.e. 16 L1 wavefronts per LDG.128 instead of 4
+// -- ncu r02: a quarter of the L1 data-pipe wavefronts of the splat, the pipe that bounds it.  In a blocked window the
+// stream is cut into aligned blocks of 512 events (one warp's work); inside a block, group g (0..3) of lane L sits at
+// (g * 32 + L) * 4: a warp's load of group g is one contiguous 512-byte run.  The ragged tail (n % 512) stays linear.
+// Only the ORDER IN MEMORY changes: logical (sorted) indices, item ranges and the exported permutation do not.
+constexpr int kBlockEvents = 512;
+int blocked_limit(int64_t n, int H, int W, size_t elem, bool has_weight);   // events stored blocked (multiple of 512), 0 = linear
+__host__ __device__ __forceinline__ int phys_group(int b /*logical index of a group of 4, multiple of 4*/, int n_blocked) {
+  if (b >= n_blocked) return b;
+  const int r = b & (kBlockEvents - 1);
+  return (b & ~(kBlockEvents - 1)) + ((r >> 2) & 3) * 128 + (r >> 4) * 4;
+}
+
 struct WindowLayout {
   size_t off_x, off_y, off_d, off_w, off_perm, off_tiles, off_items, total;
 };

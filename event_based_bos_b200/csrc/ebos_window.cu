@@ -45,6 +45,11 @@ static int env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
 }
+int blocked_limit(int64_t n, int H, int W, size_t elem, bool has_weight) {
+  static const int off = env_int("EBOS_LINEAR");    // EBOS_LINEAR=1: keep dense windows linear (A/B runs)
+  const bool dense = n >= (int64_t)16 * H * W;
+  return (elem == 4 && !has_weight && dense && !off) ? (int)(n & ~(int64_t)(kBlockEvents - 1)) : 0;
+}
 int item_events() {
   // default 8176 = 32 events per thread: measured on B200 at 16 Mi events the direct tile splat takes 70.7 us with
   // 8176-event items against 72.1 us with 4080 (profiles/README.md, round 2)
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(256) k_win_tile_offsets(const unsigned int* __
 // stage only the rows of the tile (flow table, IWE / dL/dIWE window) that the piece's origin pixels can reach.
 __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int tiles_per_row,
                                                     const unsigned int* __restrict__ sorted_keys, int item_events,
-                                                    int4* __restrict__ items, WindowHeader* __restrict__ h) {
+                                                    int n_blocked, int4* __restrict__ items, WindowHeader* __restrict__ h) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -179,7 +184,13 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
     const int piece = cnt ? ((((e - b) + cnt - 1) / cnt + 15) & ~15) : 0;   // <= item_events (a multiple of 16)
     const int tcoord = ((t / tiles_per_row) << 16) | (t % tiles_per_row);   // (tile row, tile col) for the tile kernels
     for (int i = 0; i < cnt; ++i) {
-      const int pb = min(b + i * piece, e), pe = min(b + (i + 1) * piece, e);
+      int pb = min(b + i * piece, e), pe = min(b + (i + 1) * piece, e);
+      // blocked windows: the cuts INSIDE a tile sit on block boundaries (a CTA then starts on a whole block; only the two
+      // blocks a tile shares with its neighbours are ragged).  item_events leaves room for the rounding (<= 511 events).
+      if (n_blocked > 0) {
+        if (i > 0) pb = min(max((pb + kBlockEvents - 1) & ~(kBlockEvents - 1), b), e);
+        if (i + 1 < cnt) pe = min(max((pe + kBlockEvents - 1) & ~(kBlockEvents - 1), b), e);
+      }
       int range = 0;
       if (pe > pb) {
         const unsigned int lp0 = __ldg(sorted_keys + pb) & (kTileH * kTileW - 1), lp1 = __ldg(sorted_keys + pe - 1) & (kTileH * kTileW - 1);
@@ -197,13 +208,15 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
 template <typename T>
 __global__ void __launch_bounds__(256) k_win_gather(const T* __restrict__ ev, const T* __restrict__ weight, int64_t n,
                                                     int H, int W, const int* __restrict__ perm,
-                                                    const WindowHeader* __restrict__ h, int normalize_t,
+                                                    const WindowHeader* __restrict__ h, int normalize_t, int n_blocked,
                                                     T* __restrict__ sx, T* __restrict__ sy, T* __restrict__ sd,
                                                     T* __restrict__ sw) {
   TimeRef<T> tr{(T)h->t_ref, (T)h->period};
   const int64_t hw = (int64_t)H * W;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = __ldg(perm + j);
+  for (int64_t jl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; jl < n; jl += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = __ldg(perm + jl);
+    // storage position of sorted event jl (blocked-striped inside aligned 512-event blocks, see ebos_common.cuh)
+    const int64_t j = jl < n_blocked ? (int64_t)phys_group((int)(jl & ~(int64_t)3), n_blocked) + (jl & 3) : jl;
     const T x = __ldg(ev + 4 * i), y = __ldg(ev + 4 * i + 1), t = __ldg(ev + 4 * i + 2);
     int64_t k = (int64_t)x * W + (int64_t)y;
     bool ok = k >= 0 && k < hw && Rn<T>::finite(x) && Rn<T>::finite(y);
@@ -294,22 +307,44 @@ struct EventBlock {
   }
 
   // 32-bit index version of load_range (unweighted windows), used by the direct tile splat
+  // (`nb`: events stored blocked-striped, see ebos_common.cuh -- `base` is the LOGICAL index, ph the storage position)
   __device__ __forceinline__ void load_range32(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,
-                                               int base, int lo, int hi) {
+                                               int base, int lo, int hi, int nb = 0) {
+    static_assert(EPT == 4, "load_range32 loads one group of four events");
+    const int ph = phys_group(base, nb);
     if (base >= lo && base + EPT <= hi) {
-#pragma unroll
-      for (int j = 0; j < EPT; j += 4) {
-        load4(sd + base + j, d + j);
-        load4(sx + base + j, x + j);
-        if (!PACKED) load4(sy + base + j, y + j);
-      }
+      load4(sd + ph, d);
+      load4(sx + ph, x);
+      if (!PACKED) load4(sy + ph, y);
     } else {
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         const bool in = base + j >= lo && base + j < hi;
-        d[j] = in ? sd[base + j] : (T)0;
-        if (PACKED) x[j] = in ? sx[base + j] : (T)__uint_as_float(0xffffffffu);
-        else { x[j] = in ? sx[base + j] : (T)NAN; y[j] = in ? sy[base + j] : (T)0; }
+        d[j] = in ? sd[ph + j] : (T)0;
+        if (PACKED) x[j] = in ? sx[ph + j] : (T)__uint_as_float(0xffffffffu);
+        else { x[j] = in ? sx[ph + j] : (T)NAN; y[j] = in ? sy[ph + j] : (T)0; }
+      }
+    }
+  }
+  // one group of four events of the whole stream [0, n) (flat kernels), blocked-aware
+  __device__ __forceinline__ void load_group(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,
+                                             const T* __restrict__ sw, int64_t base, int64_t n, int nb) {
+    static_assert(EPT == 4, "load_group loads one group of four events");
+    if (nb == 0) { load_global(sx, sy, sd, sw, base, n); return; }
+    const int ph = phys_group((int)base, nb);
+    if (base + EPT <= n) {
+      load4(sd + ph, d);
+      if (HAS_W) load4(sw + ph, wt);
+      load4(sx + ph, x);
+      if (!PACKED) load4(sy + ph, y);
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const bool in = base + j < n;
+        d[j] = in ? sd[ph + j] : (T)0;
+        if (HAS_W) wt[j] = in ? sw[ph + j] : (T)0;
+        if (PACKED) x[j] = in ? sx[ph + j] : (T)__uint_as_float(0xffffffffu);
+        else { x[j] = in ? sx[ph + j] : (T)NAN; y[j] = in ? sy[ph + j] : (T)0; }
       }
     }
   }
@@ -823,7 +858,7 @@ template <bool PACKED, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
                const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
-               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
+               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe, int nb) {
   // One CTA per item slot (unused slots exit at once): the hardware block scheduler balances the ragged items.  A
   // persistent variant (static round-robin over items, window re-zeroed by the flush) was measured slower on B200
   // (78-114 vs 77 us at 16 Mi events: more live state -> spills, and the per-item barriers idle whole CTAs).
@@ -849,17 +884,25 @@ k_tile_splat_d(const float* __restrict__ sx, const float* __restrict__ sy, const
       // back; anything else goes through the per-event path.  The per-event NaN / window branches of the first
       // version cost ~8 issue slots per event (ncu r01f: 79 instructions per event, issue-active 75 %).
       const int lo = it.y, hi = it.z;
-      const int start = lo & ~3;
+      // blocked-striped windows (nb > 0): a thread's 16 events must be lane L's slot of an aligned 512-event block, so
+      // the CTA starts on the block that holds `lo` (groups in front of `lo` belong to the previous item: skipped)
+      const int start = nb > 0 ? (lo & ~(kBlockEvents - 1)) : (lo & ~3);
       for (int base = start + (int)threadIdx.x * 16; base < hi; base += (int)blockDim.x * 16) {
+        if (base + 16 <= lo) continue;
         // software pipelining: the raw fields of group g+1 are requested before group g is processed (the first use
         // of a freshly loaded group was the top stall site, ncu r01d)
         EventBlock<float, 4, false, PACKED> e, nxt;
-        e.load_range32(sx, sy, sd, base, lo, hi);
+        e.load_range32(sx, sy, sd, base, lo, hi, nb);
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int b = base + 4 * g;
           if (b >= hi) break;
-          if (g < 3 && b + 4 < hi) nxt.load_range32(sx, sy, sd, b + 4, lo, hi);
+          if (g < 3 && b + 4 < hi) nxt.load_range32(sx, sy, sd, b + 4, lo, hi, nb);
+          if (b + 4 <= lo) {      // whole group in front of the item
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { e.x[j] = nxt.x[j]; e.y[j] = nxt.y[j]; e.d[j] = nxt.d[j]; }
+            continue;
+          }
           const bool full = b >= lo && b + 4 <= hi;
           if (full) e.finish_full(flow, W, hw); else e.finish(flow, W, hw);
           float2 w[4], w01[4], w23[4];
@@ -1028,18 +1071,18 @@ template <bool PACKED, int MINB, bool MERGE>
 __global__ void __launch_bounds__(256, MINB)
 k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
                const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
-               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe) {
+               int H, int W, int pad_h, int pad_w, float* __restrict__ iwe, int nb) {
   __shared__ int win[kSH * kSW];
   __shared__ float4 pix[kTileH * kTileW];
   pdl_launch_dependents();   // the cost kernel may be scheduled while this grid drains (it waits before reading the IWE)
   ItemGeom g = item_geom(__ldg(items + blockIdx.x), pad_h, pad_w);   // (unused slots are empty: no header read before it)
   const int lo = g.lo, hi = g.hi;
   if (hi <= lo) return;
-  const int base0 = (lo & ~3) + (int)threadIdx.x * 16;
+  const int base0 = (nb > 0 ? (lo & ~(kBlockEvents - 1)) : (lo & ~3)) + (int)threadIdx.x * 16;
   // two event buffers used alternately: the raw fields of group g+1 are requested before group g is processed; the very
   // first group is requested before the set-up below
   EventBlock<float, 4, false, PACKED> ea, eb;
-  if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi);
+  if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi, nb);
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w, hw = H * W;
   if (hi - lo < kWinMinEvents) g.nrows = 0;                  // small item: every event takes the global path
   const int cnt_log = 31 - __clz(hi - lo);
@@ -1127,12 +1170,12 @@ k_tile_splat_m(const float* __restrict__ sx, const float* __restrict__ sy, const
       const int b0 = group_base(gi);
       if (b0 >= hi) break;
       const int b1 = group_base(gi + 1);
-      if (b1 < hi) eb.load_range32(sx, sy, sd, b1, lo, hi);
-      process(ea, b0);
+      if (b1 < hi) eb.load_range32(sx, sy, sd, b1, lo, hi, nb);
+      if (b0 + 4 > lo) process(ea, b0);   // (blocked windows: groups in front of the item belong to its predecessor)
       if (b1 >= hi) break;
       const int b2 = group_base(gi + 2);
-      if (b2 < hi) ea.load_range32(sx, sy, sd, b2, lo, hi);
-      process(eb, b1);
+      if (b2 < hi) ea.load_range32(sx, sy, sd, b2, lo, hi, nb);
+      if (b1 + 4 > lo) process(eb, b1);
     }
     if constexpr (MERGE) { if (poff >= 0) taps_to_window(win, poff, pa01, pa23, qs); }
   }
@@ -1430,8 +1473,9 @@ __global__ void __launch_bounds__(256, MINB)
 k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
             const float* __restrict__ sw, int64_t n, const float* __restrict__ flow, int H, int W, int pad_h, int pad_w,
             const float* __restrict__ g, const double* __restrict__ acc, int omit, double scale,
-            float* __restrict__ dflow) {
+            float* __restrict__ dflow, int nb) {
   pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
+  // (nb > 0: blocked-striped window, NG == 4 -- a thread's 16 events are lane L's slot of an aligned 512-event block)
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
   if (base >= n) return;
   if (GSRC == 1) pdl_wait();   // the variance coefficients come from the accumulators of the preceding cost kernel
@@ -1441,7 +1485,7 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
   // ncu r01e showed each group start exposing three dependent latencies (event load -> flow gather -> dL/dIWE
   // gather); this removes the first (and longest, DRAM) one from every group but a thread's first.
   EventBlock<float, 4, HAS_W, PACKED> cur, nxt;
-  cur.load_global(sx, sy, sd, sw, base, n);
+  cur.load_group(sx, sy, sd, sw, base, n, nb);
   // PDL: everything above (and the event loads in flight) overlaps the drain of the preceding cost kernel; dL/dIWE
   // and the dflow accumulation target are only touched below
   if (GSRC == 0) pdl_wait();
@@ -1449,7 +1493,7 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
   for (int gi = 0; gi < NG; ++gi) {
     const int64_t b = base + 4 * gi;
     if (b >= n) break;
-    if (gi + 1 < NG && b + 4 < n) nxt.load_global(sx, sy, sd, sw, b + 4, n);
+    if (gi + 1 < NG && b + 4 < n) nxt.load_group(sx, sy, sd, sw, b + 4, n, nb);
     if (b + 4 <= n) {
       cur.finish_full(flow, W, P.hw);
       if (!bwd_group4_regular<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow)) bwd_group4<GSRC, HAS_W, PACKED>(cur, run, P, g, dflow);
@@ -1489,7 +1533,7 @@ __global__ void __launch_bounds__(256, MINB)
 k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sd,
              const int4* __restrict__ items, const WindowHeader* __restrict__ hdr, const float* __restrict__ flow,
              int H, int W, int pad_h, int pad_w, const float* __restrict__ g, const double* __restrict__ acc, int omit,
-             double scale, float* __restrict__ dflow) {
+             double scale, float* __restrict__ dflow, int nb) {
   __shared__ float gwin[kSH * kSW];
   __shared__ float4 pix[kTileH * kTileW];
   pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
@@ -1497,9 +1541,9 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
   const int lo = ig.lo, hi = ig.hi;
   if (hi <= lo) return;
   const int hw = H * W;
-  const int base0 = (lo & ~3) + (int)threadIdx.x * 16;
+  const int base0 = (nb > 0 ? (lo & ~(kBlockEvents - 1)) : (lo & ~3)) + (int)threadIdx.x * 16;
   EventBlock<float, 4, false, PACKED> ea, eb;
-  if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi);
+  if (base0 < hi) ea.load_range32(sx, sy, sd, base0, lo, hi, nb);
   fill_pixel_table(pix, flow, ig, H, W, hw);
   // PDL: everything above overlaps the drain of the preceding cost kernel; dL/dIWE (and, for the variance objective,
   // the accumulators) are only read below
@@ -1612,12 +1656,12 @@ k_tile_bwd_m(const float* __restrict__ sx, const float* __restrict__ sy, const f
       const int b0 = group_base(gi);
       if (b0 >= hi) break;
       const int b1 = group_base(gi + 1);
-      if (b1 < hi) eb.load_range32(sx, sy, sd, b1, lo, hi);
-      process(ea, b0);
+      if (b1 < hi) eb.load_range32(sx, sy, sd, b1, lo, hi, nb);
+      if (b0 + 4 > lo) process(ea, b0);   // (blocked windows: groups in front of the item belong to its predecessor)
       if (b1 >= hi) break;
       const int b2 = group_base(gi + 2);
-      if (b2 < hi) ea.load_range32(sx, sy, sd, b2, lo, hi);
-      process(eb, b1);
+      if (b2 < hi) ea.load_range32(sx, sy, sd, b2, lo, hi, nb);
+      if (b1 + 4 > lo) process(eb, b1);
     }
     if (pk >= 0) { red_add_nc(dflow + pk, s01.x); red_add_nc(dflow + hw + pk, s01.y); }
   }
@@ -1679,8 +1723,10 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   // unused item slots stay empty (begin == end == 0): the tile kernels launch one CTA per slot and read only their slot
   cudaError_t me = cudaMemsetAsync(b + L.off_items, 0, (size_t)max_items(n, H, W) * 16, st);
   if (me != cudaSuccess) return cuda_fail(me, "ebos_window_prepare(items)");
-  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), k_out, item_events(), reinterpret_cast<int4*>(b + L.off_items), hdr);
-  k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t,
+  const int n_blocked = blocked_limit(n, H, W, sizeof(T), weight != nullptr);
+  k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), k_out, n_blocked ? item_events() - kBlockEvents : item_events(),
+                                  n_blocked, reinterpret_cast<int4*>(b + L.off_items), hdr);
+  k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t, n_blocked,
                                       reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
                                       reinterpret_cast<T*>(b + L.off_d),
                                       weight ? reinterpret_cast<T*>(b + L.off_w) : nullptr);
@@ -1710,6 +1756,7 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
   if (n == 0) return EBOS_OK;
   const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
   if (packed && sizeof(T) != 4) { set_error("ebos_window_splat: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
+  const int nb = blocked_limit(n, H, W, sizeof(T), has_weight);   // same rule as ebos_window_prepare: blocked-striped storage
   WindowLayout L = window_layout(n, sizeof(T), H, W);
   const char* b = reinterpret_cast<const char*>(window);
   const T* sx = reinterpret_cast<const T*>(b + L.off_x);
@@ -1745,11 +1792,11 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       static const int occ_env = env_int("EBOS_QOCC");
       // 4 CTAs/SM = 64 registers: with the prefetched next group the 48-register build spills (97 vs 75 us)
       const int occ = (occ_env == 5 || occ_env == 6) ? occ_env : 4;
-      const unsigned qgrid = (unsigned)(n / item_events() + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
+      const unsigned qgrid = (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
-#define EBOS_SD(P, B) k_tile_splat_d<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
+#define EBOS_SD(P, B) k_tile_splat_d<P, B><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi, nb)
       if (packed) { if (occ == 4) EBOS_SD(true, 4); else if (occ == 5) EBOS_SD(true, 5); else EBOS_SD(true, 6); }
       else { if (occ == 4) EBOS_SD(false, 4); else if (occ == 5) EBOS_SD(false, 5); else EBOS_SD(false, 6); }
 #undef EBOS_SD
@@ -1763,11 +1810,11 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       static const int occ_env = env_int("EBOS_QOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
       const bool merge = tile_env == 6;
-      const unsigned qgrid = (unsigned)(n / item_events() + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
+      const unsigned qgrid = (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
-#define EBOS_SM(P, B, M) k_tile_splat_m<P, B, M><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi)
+#define EBOS_SM(P, B, M) k_tile_splat_m<P, B, M><<<qgrid, 256, 0, st>>>(fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fi, nb)
 #define EBOS_SM_O(P, M) do { if (occ == 3) EBOS_SM(P, 3, M); else if (occ == 4) EBOS_SM(P, 4, M); else if (occ == 5) EBOS_SM(P, 5, M); else EBOS_SM(P, 6, M); } while (0)
       if (packed) { if (merge) EBOS_SM_O(true, true); else EBOS_SM_O(true, false); }
       else { if (merge) EBOS_SM_O(false, true); else EBOS_SM_O(false, false); }
@@ -1853,6 +1900,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
   if (n == 0) return EBOS_OK;
   const bool has_weight = flags & EBOS_WIN_HAS_WEIGHT, packed = flags & EBOS_WIN_PACKED;
   if (packed && sizeof(T) != 4) { set_error("ebos_window_backward: the packed layout exists for fp32 windows only"); return EBOS_ERR_BAD_ARG; }
+  const int nb = blocked_limit(n, H, W, sizeof(T), has_weight);
   WindowLayout L = window_layout(n, sizeof(T), H, W);
   const char* b = reinterpret_cast<const char*>(window);
   const T* sx = reinterpret_cast<const T*>(b + L.off_x);
@@ -1882,13 +1930,13 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       static const int occ_env = env_int("EBOS_BOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
-      const unsigned qgrid = (unsigned)(n / item_events() + (int64_t)tiles_x(W) * tiles_y(H) + 1);
+      const unsigned qgrid = (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + (int64_t)tiles_x(W) * tiles_y(H) + 1);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
       float* fo = reinterpret_cast<float*>(dflow);
       cudaError_t le;
-#define EBOS_TBM(G, P, B) le = launch_pdl(k_tile_bwd_m<G, P, B>, dim3(qgrid), dim3(256), st, fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+#define EBOS_TBM(G, P, B) le = launch_pdl(k_tile_bwd_m<G, P, B>, dim3(qgrid), dim3(256), st, fx, fy, fd, items, hdr, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo, nb)
 #define EBOS_TBM_O(G, P) do { if (occ == 3) EBOS_TBM(G, P, 3); else if (occ == 4) EBOS_TBM(G, P, 4); else if (occ == 5) EBOS_TBM(G, P, 5); else EBOS_TBM(G, P, 6); } while (0)
       if (affine) { if (packed) EBOS_TBM_O(1, true); else EBOS_TBM_O(1, false); }
       else { if (packed) EBOS_TBM_O(0, true); else EBOS_TBM_O(0, false); }
@@ -1934,15 +1982,16 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
     if (ng_env >= 0) {
       int ng = (ng_env == 1 || ng_env == 4 || ng_env == 8) ? ng_env : 2;
       if (ng_env == 0 && n / (4 * ng) < (int64_t)2 * sm_count() * 256) ng = 1;   // small windows: see window_splat_t
+      if (nb > 0) ng = 4;                                                         // blocked-striped window: 16 events per thread
       const unsigned ggrid = (unsigned)((((n + 4 * ng - 1) / (4 * ng)) + 255) / 256);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
       const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
       float* fo = reinterpret_cast<float*>(dflow);
-#define EBOS_BG(G, WGT, P, NGV) launch_pdl(k_win_bwd_g<G, WGT, P, NGV>, dim3(ggrid), dim3(256), st, fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
-#define EBOS_BGO(G, WGT, P, NGV, O) k_win_bwd_g<G, WGT, P, NGV, O><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo)
+#define EBOS_BG(G, WGT, P, NGV) launch_pdl(k_win_bwd_g<G, WGT, P, NGV>, dim3(ggrid), dim3(256), st, fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo, nb)
+#define EBOS_BGO(G, WGT, P, NGV, O) k_win_bwd_g<G, WGT, P, NGV, O><<<ggrid, 256, 0, st>>>(fx, fy, fd, fw, n, ff, H, W, pad_h, pad_w, fg, acc, omit_boundary, scale, fo, nb)
       static const int bocc = env_int("EBOS_BOCC");   // experiment knob (unweighted packed gradient-plane kernel only)
-      if (bocc && !affine && !has_weight && packed) {
+      if (bocc && !affine && !has_weight && packed && (ng == 2 || ng == 4)) {
         if (bocc == 5 && ng == 2) EBOS_BGO(0, false, true, 2, 5); else if (bocc == 5) EBOS_BGO(0, false, true, 4, 5);
         else if (bocc == 3 && ng == 2) EBOS_BGO(0, false, true, 2, 3); else if (bocc == 3) EBOS_BGO(0, false, true, 4, 3);
         else if (bocc == 6 && ng == 2) EBOS_BGO(0, false, true, 2, 6); else EBOS_BGO(0, false, true, 4, 6);

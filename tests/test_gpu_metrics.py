@@ -211,7 +211,7 @@ def test_fused_objective_on_blurred_iwe_vs_oracle(cost):
            "cmax": {"cost_with_weight": {cost: 1.0, "image_gradient": 0.5}, "lr": 0.05, "precision": "64"}}
     flow0 = np.random.default_rng(1).uniform(-1, 1, (2, H, W))
     evd = ev.double()
-    x0 = torch.from_numpy(flow0).requires_grad_()
+    x0 = torch.from_numpy(flow0.copy()).requires_grad_()      # (a copy: Adam updates the leaf in place)
     opt = torch.optim.Adam([x0], lr=0.05)
     for _ in range(20):
         opt.zero_grad()
