@@ -1475,8 +1475,15 @@ k_win_bwd_g(const float* __restrict__ sx, const float* __restrict__ sy, const fl
             const float* __restrict__ g, const double* __restrict__ acc, int omit, double scale,
             float* __restrict__ dflow, int nb) {
   pdl_launch_dependents();   // (fused solver iteration: Adam follows and waits before reading dflow)
-  // (nb > 0: blocked-striped window, NG == 4 -- a thread's 16 events are lane L's slot of an aligned 512-event block)
-  const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * (4 * NG);
+  // Blocked-striped windows (nb > 0, NG in {1, 2, 4}): lane L of block B owns the 16 logical events B * 512 + L * 16 ...;
+  // a warp takes the SAME run of 4 * NG events of all 32 lanes of one block, so that its group loads are contiguous.
+  const int64_t tid_g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t base = tid_g * (4 * NG);
+  if (NG <= 4 && base < nb) {
+    constexpr int kRuns = 4 / (NG <= 4 ? NG : 4);                  // runs of 4 * NG events per lane slot
+    const int64_t warp = tid_g >> 5;
+    base = (warp / kRuns) * kBlockEvents + (tid_g & 31) * 16 + (warp % kRuns) * (4 * NG);
+  }
   if (base >= n) return;
   if (GSRC == 1) pdl_wait();   // the variance coefficients come from the accumulators of the preceding cost kernel
   const BwdParams<float> P = make_bwd_params<float, GSRC>(H, W, pad_h, pad_w, acc, omit, scale);
@@ -1982,7 +1989,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
     if (ng_env >= 0) {
       int ng = (ng_env == 1 || ng_env == 4 || ng_env == 8) ? ng_env : 2;
       if (ng_env == 0 && n / (4 * ng) < (int64_t)2 * sm_count() * 256) ng = 1;   // small windows: see window_splat_t
-      if (nb > 0) ng = 4;                                                         // blocked-striped window: 16 events per thread
+      if (nb > 0 && ng == 8) ng = 4;                                              // blocked-striped windows: at most one lane slot per thread
       const unsigned ggrid = (unsigned)((((n + 4 * ng - 1) / (4 * ng)) + 255) / 256);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd); const float* fw = reinterpret_cast<const float*>(sw);
