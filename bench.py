@@ -847,6 +847,7 @@ def giant_record(args, rank, world, local):
         torch.cuda.synchronize()
         barrier(world)
     exchange = getattr(obj, "exchange", "none")
+    autotune = getattr(obj, "exchange_autotune", None)
     launches = getattr(obj, "launches_per_evaluation", None)
     del obj
     if rank != 0:
@@ -860,6 +861,7 @@ def giant_record(args, rank, world, local):
                                    f"1280x720, fp32, {COST}+{TV_WEIGHT}*TV forward+backward",
                        "events_total": n_total, "events_per_gpu": n, "l2_policy": "inputs larger than L2"},
             "exchange": exchange,
+            "exchange_start_up_timing_ms": autotune,
             "exchange_bytes_per_evaluation_per_rank": 0 if world == 1 else 3 * P_BYTES,   # partial IWE (P) + partial dflow (2P)
             "parity_self_check": parity,
             "clocks": clocks.summary(),

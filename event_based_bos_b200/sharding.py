@@ -248,9 +248,11 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
         zero-fill, no plane-sized add."""
 
         def value_and_grad(self, flow):
-            if p2p is not None:
-                return self._value_and_grad_p2p(flow) if p2p["form"] == 1 else self._value_and_grad_p2p_two_shot(flow)
-            st = current_stream()
+            if p2p is not None and p2p["form"] == 1:
+                return self._value_and_grad_p2p(flow)
+            if p2p is not None and p2p["form"] == 2:
+                return self._value_and_grad_p2p_two_shot(flow)
+            st = current_stream()      # form 0: NCCL all-reduce
             R = dist.get_world_size() if is_distributed() else 1
             Hp, Wp = H + 2 * ph, W + 2 * pw
             check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(dflow), st), "ebos_flow_tv")
@@ -325,13 +327,44 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             return loss, dflow
 
     obj = _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
-    if p2p is None:
+    # Which exchange is fastest depends on the rank count and on what NCCL can do on the box (in-switch NVLS reductions):
+    # measured on B200s, 128 Mi events -- 2 ranks: one-shot 0.593 / two-shot 0.607 / NCCL 0.625 ms; 4 ranks: one-shot
+    # 0.415 / two-shot 0.371 / NCCL 0.368 ms.  Unless a form is forced, every available form is timed for a few
+    # evaluations on this window (all ranks in lock-step, the slowest rank decides) and the fastest is kept.
+    obj.exchange_autotune = None
+    if p2p is not None and not __import__("os").environ.get("EBOS_P2P_FORM"):
+        forms = ([1] if kind == _capi.COST_GRADMAG else []) + [2, 0]
+        probe = torch.zeros((2, H, W), dtype=window.dtype, device=dev)
+        timings = {}
+        for form in forms:
+            p2p["form"] = form
+            for _ in range(2):
+                obj.value_and_grad(probe)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a.record()
+            for _ in range(5):
+                obj.value_and_grad(probe)
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / 5], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            timings[form] = float(t)
+        p2p["form"] = min(timings, key=timings.get)
+        names = {0: "nccl", 1: "peer one-shot", 2: "peer two-shot"}
+        obj.exchange_autotune = {names[f]: round(v, 4) for f, v in timings.items()}
+        if p2p["form"] == 0:
+            pass
+    if p2p is None or p2p["form"] == 0:
         obj.exchange = "nccl all-reduce (2 per evaluation)" if R0 > 1 else "none"
+        if p2p is not None:
+            obj.exchange += "; chosen by the start-up timing over the peer-memory forms"
     elif p2p["form"] == 1:
         obj.exchange = "peer-memory one-shot (IWE reduction fused into the cost kernel; 3 device barriers per evaluation)"
     else:
         obj.exchange = "peer-memory two-shot (reduce-scatter in place + all-gather for IWE and gradient; 4 device barriers per evaluation)"
     # kernels of this library per evaluation: TV, splat, cost, backward, loss + the peer kernels (1 one-shot, 4 two-shot);
     # the NCCL path uses two library all-reduces instead
-    obj.launches_per_evaluation = 5 if p2p is None else (6 if p2p["form"] == 1 else 9)
+    obj.launches_per_evaluation = 5 if (p2p is None or p2p["form"] == 0) else (6 if p2p["form"] == 1 else 9)
     return obj
