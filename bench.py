@@ -175,14 +175,23 @@ def max_over_ranks(ms: float, world: int) -> float:
 
 
 def bind_to_gpu_numa(local: int):
-    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated
-    (cudaHostAlloc places pages by the calling thread's policy): with all ranks on node 0 the round-1 end-to-end numbers
-    stopped scaling at ~110-180 GB/s aggregate H2D.  Returns a short description for the JSON line (or None)."""
+    """Pin this process to the CPUs closest to its GPU BEFORE any pinned host buffer is allocated (cudaHostAlloc places
+    pages by the calling thread's policy: first touch on the local NUMA node): with all ranks on node 0 the round-1
+    end-to-end numbers stopped scaling at ~110-180 GB/s aggregate H2D.  NVML's ideal-CPU set for the device (what
+    `nvidia-smi topo -m` prints as CPU affinity), sysfs as fallback.  Returns a short description for the JSON line."""
+    before = len(os.sched_getaffinity(0))
     try:
         import pynvml
 
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        try:
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            after = len(os.sched_getaffinity(0))
+            if 0 < after <= before:
+                return {"source": "nvml ideal cpu set", "cpus": after, "cpus_before": before}
+        except Exception:
+            pass
         bus = pynvml.nvmlDeviceGetPciInfo(h).busId
         bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
         if len(bus.split(":")[0]) == 8:
@@ -199,10 +208,28 @@ def bind_to_gpu_numa(local: int):
         allowed = cpus & os.sched_getaffinity(0)
         if allowed:
             os.sched_setaffinity(0, allowed)
-            return {"numa_node": node, "cpus": len(allowed)}
+            return {"source": "sysfs numa_node", "numa_node": node, "cpus": len(allowed), "cpus_before": before}
     except Exception:
         return None
     return None
+
+
+class near_gpu:
+    """`with near_gpu(local) as info:` -- allocate pinned host buffers inside; the process's CPU affinity is restored on
+    exit (the CPU baseline must see all host cores again)."""
+
+    def __init__(self, local: int):
+        self.local, self.saved = local, None
+
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0)
+        return bind_to_gpu_numa(self.local)
+
+    def __exit__(self, *a):
+        try:
+            os.sched_setaffinity(0, self.saved)
+        except Exception:
+            pass
 
 
 def all_ranks_equal(t: torch.Tensor, world: int) -> bool:
@@ -341,9 +368,11 @@ def run_fused(args, rank, world, local):
 
     n = args.events
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa(local)          # before the pinned allocations below
-    ev_host = torch.from_numpy(synthetic_events(n, (H, W), seed=rank)).pin_memory()
-    flow_host = torch.from_numpy(synthetic_flow((H, W), seed=rank)).pin_memory()
+    events_np, flow_np = synthetic_events(n, (H, W), seed=rank), synthetic_flow((H, W), seed=rank)
+    with near_gpu(local) as numa:           # pinned pages land on the GPU's NUMA node (first touch)
+        ev_host = torch.from_numpy(events_np).pin_memory()
+        flow_host = torch.from_numpy(flow_np).pin_memory()
+    del events_np, flow_np
     ev = ev_host.to(dev, non_blocking=True)
     flow = flow_host.to(dev, non_blocking=True)
     window = ops.PreparedWindow(ev, (H, W), "first", True, allow_packed=not args.no_packed)
@@ -471,16 +500,19 @@ def e2e_fused(args, rank, world, local, dev, ev_host, flow_host, ws, lib):
 
     n = ev_host.shape[0]
     p = capi.ptr
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
-    grad_host = torch.empty((2, H, W), dtype=torch.float32).pin_memory()
+    evn = ev_host.numpy()
+    raw_np = [np.ascontiguousarray(a) for a in (evn[:, 1].astype(np.int16), evn[:, 0].astype(np.int16),
+                                                np.round(evn[:, 2].astype(np.float64) * 1e6).astype(np.int32),
+                                                evn[:, 3].astype(np.uint8))]
+    with near_gpu(local):
+        loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        grad_host = torch.zeros((2, H, W), dtype=torch.float32).pin_memory()
+        raw_host = [torch.from_numpy(a).pin_memory() for a in raw_np]
+    del raw_np
     copy_stream = torch.cuda.Stream(device=dev)
     fl_bufs = [torch.empty_like(flow_host, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
-    evn = ev_host.numpy()
-    raw_host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
-                (evn[:, 1].astype(np.int16), evn[:, 0].astype(np.int16),
-                 np.round(evn[:, 2].astype(np.float64) * 1e6).astype(np.int32), evn[:, 3].astype(np.uint8))]
     rows_dev = torch.empty((n, 4), dtype=torch.float32, device=dev)
     cnt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     t0_us = int(raw_host[2][0])
@@ -591,13 +623,15 @@ def solve_record(args, rank, world, local, quick=False):
     it_launches, it_other = ops.count_launches(lambda: ops.cmax_adam_iteration(tiny, f_t, m_t, v_t, st_t, ws_t, COST, 1.0, TV_WEIGHT))
     del tiny, f_t, m_t, v_t, ws_t
     # pinned host buffers (the e2e contract: inputs come from pinned host memory), handed over as numpy views
-    pinned = [torch.from_numpy(synthetic_bos_events(n, (H, W), gt, seed=1000 * rank + i).astype(np.float64)).pin_memory()
-              for i in range(max(2, conc))]
-    windows = [t.numpy() for t in pinned]
-    for _ in range(1 if quick else max(1, min(args.warmup, 2))):
-        slv.estimate(windows[0])
-    if conc > 1:
-        slv.estimate_many(windows[:conc] * 2, concurrency=conc)   # warm-up of every stream slot (staging buffers)
+    host_events = [synthetic_bos_events(n, (H, W), gt, seed=1000 * rank + i).astype(np.float64) for i in range(max(2, conc))]
+    with near_gpu(local):    # pinned inputs and the solver's pinned staging buffers land on the GPU's NUMA node
+        pinned = [torch.from_numpy(a).pin_memory() for a in host_events]
+        windows = [t.numpy() for t in pinned]
+        for _ in range(1 if quick else max(1, min(args.warmup, 2))):
+            slv.estimate(windows[0])
+        if conc > 1:
+            slv.estimate_many(windows[:conc] * 2, concurrency=conc)   # warm-up of every stream slot (staging buffers)
+    del host_events
     n_solves = 2 * conc if quick else max(args.steps, 4 * conc)
     batch = [windows[i % len(windows)] for i in range(n_solves)]
     barrier(world)

@@ -241,6 +241,19 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
         per = ((n_elems + R0 - 1) // R0 + 3) // 4 * 4
         return per, min(rank * per, n_elems), min((rank + 1) * per, n_elems)
 
+    side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def tv_beside_exchange(flow, target):
+        """The TV kernel ((tv_weight / R) * dTV -> `target`, the buffer the backward accumulates on top of) needs only the
+        flow: it runs on a side stream while this rank waits in the barriers of exchange 1, instead of in front of the
+        splat.  Returns the stream to join before the backward."""
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / max(R0, 1), window.code, ptr(acc), ptr(target),
+                                   current_stream()), "ebos_flow_tv")
+        return side
+
     class _Lean(EventShardedObjective):
         """Same result with fewer passes: the TV kernel writes (tv_weight / R) * dTV straight into the gradient buffer
         (every rank computes the identical TV term, the all-reduce over R ranks restores its full weight), the backward
@@ -255,12 +268,13 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             st = current_stream()      # form 0: NCCL all-reduce
             R = dist.get_world_size() if is_distributed() else 1
             Hp, Wp = H + 2 * ph, W + 2 * pw
-            check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(dflow), st), "ebos_flow_tv")
             ops.window_splat(window, flow, outer_padding, out=iwe)
+            tv_stream = tv_beside_exchange(flow, dflow)
             if R > 1:
                 dist.all_reduce(iwe, op=dist.ReduceOp.SUM)       # exchange 1: partial IWEs
             check(lib.ebos_iwe_cost(kind, ptr(iwe), Hp, Wp, int(omit_boundary), data_weight, window.code, ptr(acc),
                                     ptr(g_iwe), st), "ebos_iwe_cost")
+            torch.cuda.current_stream().wait_stream(tv_stream)
             check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
                                            window.code, ptr(g_iwe), kind, ptr(iwe), ptr(acc), int(omit_boundary),
                                            data_weight, ptr(dflow), st), "ebos_window_backward")
@@ -275,11 +289,12 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             R = R0
             Hp, Wp = H + 2 * ph, W + 2 * pw
             part, h_part, part_ptrs = p2p["df"][0], p2p["h_df"][0], p2p["df_ptrs"][0]
-            check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(part), st), "ebos_flow_tv")
             ops.window_splat(window, flow, outer_padding, out=p2p["iwe"])
+            tv_stream = tv_beside_exchange(flow, part)
             p2p["h_iwe"].barrier(channel=0)                   # every rank's partial IWE is complete
             check(lib.ebos_iwe_cost_peers(kind, p2p["iwe_ptrs"], R, Hp, Wp, int(omit_boundary), data_weight, window.code,
                                           ptr(acc), ptr(g_iwe), st), "ebos_iwe_cost_peers")
+            torch.cuda.current_stream().wait_stream(tv_stream)
             check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
                                            window.code, ptr(g_iwe), kind, ptr(p2p["iwe"]), ptr(acc), int(omit_boundary),
                                            data_weight, ptr(part), st), "ebos_window_backward")
@@ -299,8 +314,8 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             p2p["count"] += 1                                 # gathering evaluation i while this rank starts i + 1
             part, h_part, part_ptrs = p2p["df"][k], p2p["h_df"][k], p2p["df_ptrs"][k]
             s_plane = p2p["iwe"]
-            check(lib.ebos_flow_tv(ptr(flow), 0, H, W, tv_weight / R, window.code, ptr(acc), ptr(part), st), "ebos_flow_tv")
             ops.window_splat(window, flow, outer_padding, out=s_plane)
+            tv_stream = tv_beside_exchange(flow, part)
             # exchange 1 (partial IWEs): reduce-scatter in place, all-gather into a local plane
             n_iwe = s_plane.numel()
             per, b0, b1 = _slice_bounds(n_iwe, rank)
@@ -311,6 +326,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
                   "ebos_gather_peers_slices")
             check(lib.ebos_iwe_cost(kind, ptr(iwe_full), Hp, Wp, int(omit_boundary), data_weight, window.code, ptr(acc),
                                     ptr(g_iwe), st), "ebos_iwe_cost")
+            torch.cuda.current_stream().wait_stream(tv_stream)
             check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
                                            window.code, ptr(g_iwe), kind, ptr(iwe_full), ptr(acc), int(omit_boundary),
                                            data_weight, ptr(part), st), "ebos_window_backward")
