@@ -632,7 +632,9 @@ def solve_record(args, rank, world, local, quick=False):
         if conc > 1:
             slv.estimate_many(windows[:conc] * 2, concurrency=conc)   # warm-up of every stream slot (staging buffers)
     del host_events
-    n_solves = 2 * conc if quick else max(args.steps, 4 * conc)
+    # (sub-record of the default line: 6 rounds of the slots, ~1 s -- the start-up of the rolling schedule, ~4 ms of host
+    #  planning before the first graph replay, must not weigh on a steady-state rate)
+    n_solves = 6 * conc if quick else max(args.steps, 6 * conc)
     batch = [windows[i % len(windows)] for i in range(n_solves)]
     barrier(world)
     with ClockSampler(local) as clocks:
@@ -660,6 +662,7 @@ def solve_record(args, rank, world, local, quick=False):
                                   f"Adam lr 0.05, K = {iters} iterations, zero init; host events in -> host flow out; "
                                   f"{conc} independent windows in flight per GPU; windows sharded over the ranks, no collective",
                       "iterations": iters, "windows_timed_per_gpu": n_solves, "concurrency": conc},
+           "host_ms_per_window": {k: round(v, 3) for k, v in slv.last_many_stats.items()},
            "parity_self_check": parity,
            "clocks": clocks.summary(),
            "roofline": {"bound": "hbm", "kernel": "whole solve (all kernels)", "achieved": alg / (ms * 1e-3) / 1e9,
@@ -740,17 +743,33 @@ def run_eklt(args, rank, world, local):
     cfg["eklt"] = {"precision": args.eklt_precision, "cuda_graph": not args.eklt_no_graph}
     slv = solver.collections["patch_eklt_pyramid2"]((H, W), (720, 640), {}, cfg, None)
     ev, frame = eklt_inputs(args.solve_events, seed=rank)
+    conc = max(1, args.eklt_concurrency)
     for _ in range(max(1, min(args.warmup, 2))):
         slv.estimate(ev, frame=frame)
+    if conc > 1:
+        slv.estimate_many([ev] * conc, frames=[frame] * conc, concurrency=conc)      # warm-up of every slot
+    barrier(world)
+    # latency of ONE estimate() (nothing else on the GPU), then the throughput with `conc` windows in flight
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(max(2, args.steps // 4)):
+        slv.estimate(ev, frame=frame)
+    b.record()
+    torch.cuda.synchronize()
+    ms_single = a.elapsed_time(b) / max(2, args.steps // 4)
+    n_windows = max(args.steps, 4 * conc) if conc > 1 else args.steps
     barrier(world)
     with ClockSampler(local) as clocks:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(args.steps):
-            slv.estimate(ev, frame=frame)
+        if conc > 1:
+            slv.estimate_many([ev] * n_windows, frames=[frame] * n_windows, concurrency=conc)
+        else:
+            for _ in range(n_windows):
+                slv.estimate(ev, frame=frame)
         b.record()
         torch.cuda.synchronize()
-        ms = max_over_ranks(a.elapsed_time(b) / args.steps, world)
+        ms = max_over_ranks(a.elapsed_time(b) / n_windows, world)
         barrier(world)
         clocks.soak(lambda: None, max_s=0.5)
     # device time of one evaluation per level (value + gradient, no Adam), 20 evaluations per CUDA graph
@@ -789,20 +808,21 @@ def run_eklt(args, rank, world, local):
             "config": {"workload": f"configs/hot_plate1.yaml pipeline: PatchEkltPyramid2.estimate, {args.solve_events} "
                                    f"synthetic events + synthetic frame, 1280x720, ROI [0:720,320:960], n_iter "
                                    f"{args.solve_iters} -> {sum(iters)} iterations over 4 levels; host events + frame in "
-                                   f"-> host flow out",
-                       "iterations_per_level": iters,
+                                   f"-> host flow out; {conc} independent windows in flight (estimate_many)",
+                       "iterations_per_level": iters, "windows_timed_per_gpu": n_windows, "concurrency": conc,
                        "l2_policy": "working set 25 planes x 7.4 MB (fp64) > L2"},
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "kernel": f"one objective evaluation at patch {worst} (all kernels of the chain)",
                          "achieved": alg_eval / (per_level[worst] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_kind},
+            "ms_per_window_single": ms_single, "host_ms_per_window": {k: round(v, 3) for k, v in slv.last_many_stats.items()},
             "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy,
             "eval_ms_per_level_without_stored_planes": per_level_stored or None,
             "eval_ms_per_level_without_segment_gather": per_level_seg or None,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
-            "gpu_launches": args.steps * sum(iters) * 12}
+            "gpu_launches": n_windows * sum(iters) * 12}
     if not args.no_cpu and world == 1:
         s_eval, cores = cpu_reference_eklt(args.solve_events)
         line["cpu_baseline"] = {"value": 1.0 / (s_eval * sum(iters)), "unit": "windows/s", "cores": cores,
@@ -928,6 +948,7 @@ def main():
     ap.add_argument("--solve-iters", type=int, default=600)
     ap.add_argument("--solve-concurrency", type=int, default=8, help="independent windows in flight per GPU (solve workload)")
     ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
+    ap.add_argument("--eklt-concurrency", type=int, default=4, help="independent windows in flight per GPU (eklt workload)")
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -92,6 +92,9 @@ SIGNATURES = {
     "ebos_blur3": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p, c_void_p]),
     "ebos_capture_begin": (c_int, [c_void_p]),
     "ebos_capture_end_count": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ebos_capture_end_exec": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ebos_exec_launch": (c_int, [c_void_p, c_void_p]),
+    "ebos_exec_destroy": (c_int, [c_void_p]),
 }
 
 _lib = None

@@ -210,6 +210,57 @@ int ebos_capture_end_count(void* stream, int32_t* n_kernel_nodes, int32_t* n_oth
   return EBOS_OK;
 }
 
+// ---- replayable launch sequences (solver loops) ------------------------------------------------------------------
+// A solver captures `unroll` iterations once per window and replays them n_iter / unroll times.  Instantiating and
+// destroying an executable graph per window was measured to cost more than it looks (B200, r02l): destroying an
+// executable graph (and freeing the per-graph memory pool torch.cuda.CUDAGraph attaches) waits for ALL work in flight on
+// the device, which serialised the "concurrent" windows of estimate_many completely.  Here the executable graph
+// belongs to a SLOT that lives as long as the solver: a new window is captured into a throw-away cudaGraph_t (host
+// object) and the slot's executable is UPDATED in place (cudaGraphExecUpdate: same topology, new pointers / sizes /
+// grids) -- no instantiation, no destruction, no device synchronisation in steady state.  When the topology differs
+// (another kernel variant, another unroll) the executable is rebuilt.
+int ebos_capture_end_exec(void* stream, void** exec_inout, int32_t* updated_in_place) {
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(as_stream(stream), &graph);
+  if (e != cudaSuccess || !graph) return cuda_fail(e == cudaSuccess ? cudaErrorUnknown : e, "ebos_capture_end_exec");
+  if (!exec_inout) { cudaGraphDestroy(graph); set_error("ebos_capture_end_exec: exec_inout is NULL"); return EBOS_ERR_BAD_ARG; }
+  cudaGraphExec_t exec = reinterpret_cast<cudaGraphExec_t>(*exec_inout);
+  int32_t updated = 0;
+  if (exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(exec, graph, &info) == cudaSuccess) {
+      updated = 1;
+    } else {
+      (void)cudaGetLastError();          // not an error of ours: the executable no longer matches, rebuild it
+      cudaGraphExecDestroy(exec);
+      exec = nullptr;
+      *exec_inout = nullptr;
+    }
+  }
+  if (!exec) {
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_fail(e, "ebos_capture_end_exec(instantiate)"); }
+    *exec_inout = exec;
+  }
+  cudaGraphDestroy(graph);
+  if (updated_in_place) *updated_in_place = updated;
+  return EBOS_OK;
+}
+
+int ebos_exec_launch(void* exec, void* stream) {
+  EBOS_REQUIRE(exec, "ebos_exec_launch: no executable (capture first)");
+  cudaError_t e = cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(exec), as_stream(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_exec_launch");
+  return EBOS_OK;
+}
+
+int ebos_exec_destroy(void* exec) {
+  if (!exec) return EBOS_OK;
+  cudaError_t e = cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec));
+  if (e != cudaSuccess) return cuda_fail(e, "ebos_exec_destroy");
+  return EBOS_OK;
+}
+
 int ebos_blur3(const void* image, int batch, int H, int W, double sigma, int adjoint, int dtype, void* out, void* stream) {
   EBOS_REQUIRE(image && out && batch > 0 && H >= 2 && W >= 2 && sigma > 0.0 && image != out, "ebos_blur3: bad argument");
   if (dtype != EBOS_F32 && dtype != EBOS_F64) { set_error("ebos_blur3: unsupported dtype"); return EBOS_ERR_UNSUPPORTED; }

@@ -157,7 +157,8 @@ def measurement_and_weights(histogram: torch.Tensor, roi: Tuple[int, int, int, i
     if weight_inverse:
         s = gaussian_taps_scipy(float(inverse_sigma))
         wi = sepconv2d(h.abs(), s, s, "reflect")
-        wi = torch.clamp(wi, 0, float(wi.mean() + wi.std(unbiased=False) / 2.0))
+        # (bounds as device tensors: a Python-float bound would be a host read-back in the middle of the window's queue)
+        wi = torch.minimum(torch.clamp(wi, min=0), wi.mean() + wi.std(unbiased=False) / 2.0)
         wi = 1.0 - 0.95 * (wi / wi.max())
     else:
         wi = torch.ones_like(h)
@@ -269,9 +270,13 @@ class EkltLevel:
         return self.loss
 
     def solve(self, theta0: torch.Tensor, n_iter: int, lr: float = 0.05, cuda_graph: bool = True,
-              history: Optional[list] = None) -> torch.Tensor:
+              history: Optional[list] = None, replay=None) -> torch.Tensor:
         """`n_iter` Adam iterations from theta0; returns the FINAL iterate (upstream's `best_x` aliases the leaf).
-        With `cuda_graph`, 10 iterations are captured per graph and replayed; a loss `history` forces eager mode."""
+        With `cuda_graph`, 10 iterations are captured once and replayed; a loss `history` forces eager mode.  `replay`:
+        an `ops.ReplaySlot` that outlives this level (the solver keeps one per pyramid level and stream slot), so that
+        its executable is updated for the new window instead of being built and destroyed (see ops.ReplaySlot)."""
+        from . import ops
+
         theta = theta0.to(device=self.p.device, dtype=self.p.dtype).contiguous().clone()
         self._check_theta(theta)
         m, v = torch.zeros_like(theta), torch.zeros_like(theta)
@@ -290,25 +295,36 @@ class EkltLevel:
             return theta
         unroll = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if n_iter % u == 0)
         backup = theta.clone()
+        if replay is None:
+            replay = ops.ReplaySlot()
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=theta.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
+
+        def run():
             iteration()                      # warm-up outside capture
             theta.copy_(backup)
             m.zero_()
             v.zero_()
             step_dev.zero_()
-            graph = torch.cuda.CUDAGraph()
-            graph.capture_begin()
-            for _ in range(unroll):
-                iteration()
-            graph.capture_end()
+            replay.capture(lambda: [iteration() for _ in range(unroll)])
             for _ in range(n_iter // unroll):
-                graph.replay()
-        cur.wait_stream(side)
-        self._keep = (graph, m, v, step_dev, backup)
+                replay.launch()
+
+        if cur == torch.cuda.default_stream(theta.device):
+            # the default stream cannot be captured: one side stream per process
+            global _SIDE
+            if _SIDE is None or _SIDE.device != theta.device:
+                _SIDE = torch.cuda.Stream(device=theta.device)
+            _SIDE.wait_stream(cur)
+            with torch.cuda.stream(_SIDE):
+                run()
+            cur.wait_stream(_SIDE)
+        else:
+            run()
+        self._keep = (replay, m, v, step_dev, backup)
         return theta
+
+
+_SIDE = None
 
 
 def resize_params(theta: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:

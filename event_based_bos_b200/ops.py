@@ -565,6 +565,57 @@ def blur3(image: torch.Tensor, sigma: float) -> torch.Tensor:
     return _Blur3.apply(image, float(sigma))
 
 
+class ReplaySlot:
+    """A replayable launch sequence that outlives the window it was captured for (include/ebos.h:
+    ebos_capture_begin / ebos_capture_end_exec / ebos_exec_launch).
+
+    `capture(fn)` records what `fn()` enqueues on the CURRENT stream (which must not be the default stream; `fn` must be
+    capture-safe: no allocation, no host synchronisation) and makes it this slot's executable: the first call
+    instantiates it, later calls update it in place to the new pointers / sizes -- no instantiation, no destruction and
+    hence no device-wide synchronisation per window (a torch.cuda.CUDAGraph per window costs two: its private memory
+    pool and its executable are freed with device-synchronising calls, which serialised estimate_many's windows).
+    `launch()` enqueues one replay on the current stream."""
+
+    def __init__(self):
+        import ctypes
+
+        self._exec = ctypes.c_void_p(0)
+        self.updates = 0            # captures that updated the executable in place
+        self.instantiations = 0     # captures that had to (re)build it
+
+    def capture(self, fn) -> None:
+        import ctypes
+
+        lib = _capi.load()
+        stream = current_stream()
+        check(lib.ebos_capture_begin(stream), "ebos_capture_begin")
+        updated = ctypes.c_int32(0)
+        try:
+            fn()
+        except BaseException:
+            lib.ebos_capture_end_count(stream, None, None)      # leave capture mode, discard the partial graph
+            raise
+        check(lib.ebos_capture_end_exec(stream, ctypes.byref(self._exec), ctypes.byref(updated)), "ebos_capture_end_exec")
+        if updated.value:
+            self.updates += 1
+        else:
+            self.instantiations += 1
+
+    def launch(self) -> None:
+        check(_capi.load().ebos_exec_launch(self._exec, current_stream()), "ebos_exec_launch")
+
+    def close(self) -> None:
+        if self._exec:
+            _capi.load().ebos_exec_destroy(self._exec)
+            self._exec.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def count_launches(fn) -> Tuple[int, int]:
     """(kernel launches, other graph nodes such as memsets) that `fn()` enqueues on the current stream, counted from a
     throw-away stream capture (nothing runs).  `fn` must be capture-safe: no allocation, no host synchronisation."""

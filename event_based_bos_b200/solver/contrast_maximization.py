@@ -8,6 +8,7 @@ the operators `Warp.warp_event("dense-flow")` + `EventImageConverter.create_iwe(
 backward / step; because `best_x` aliases the optimised leaf upstream, the FINAL iterate is returned).
 """
 import logging
+import time
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -71,6 +72,12 @@ class ContrastMaximizationDense(SolverBase):
         self.history: Dict[str, List[float]] = {"loss": []}
         self._staging: Dict[int, torch.Tensor] = {}
         self._hist_dev = None
+        self.last_many_stats: Dict[str, float] = {}
+        self._side = None                       # capture stream of `estimate` on the default stream
+        self._replay = None                     # ops.ReplaySlot of `estimate`
+        self._replays: List = []                # ... of the estimate_many slots
+        self._streams: List = []
+        self._join = lambda: None
         self.cost_func = costs.HybridCost("minimize", self.cost_with_weight, store_history=self.store_history)
 
     # ------------------------------------------------------------------------------------------
@@ -82,20 +89,31 @@ class ContrastMaximizationDense(SolverBase):
         """Device result -> numpy through a persistent pinned staging tensor (one per concurrency slot): a pageable
         `.cpu()` of the 14.7 MB float64 flow took 7 ms, a quarter of a 500 k-event solve; allocating pinned memory per
         call is worse (cudaHostAlloc synchronises the device)."""
+        stage = self._stage(out, slot)
+        stage.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(out.device).synchronize()
+        return stage.numpy().copy()
+
+    def _stage(self, out: torch.Tensor, slot: int = 0) -> torch.Tensor:
         stage = self._staging.get(slot)
         if stage is None or stage.shape != out.shape or stage.dtype != out.dtype:
             stage = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
             self._staging[slot] = stage
-        stage.copy_(out, non_blocking=True)
-        torch.cuda.current_stream(out.device).synchronize()
-        return stage.numpy().copy()
+        return stage
 
     def estimate_many(self, windows: Sequence[np.ndarray], concurrency: int = 4,
                       flow0: Optional[Sequence[Optional[np.ndarray]]] = None) -> List[np.ndarray]:
         """Solve independent time windows (no inter-window state upstream) with up to `concurrency`
         solves in flight on separate CUDA streams.  One small window (~0.5 M events) leaves most of the 148 SMs idle
         -- its splat is ~120 CTAs -- so overlapping windows raises windows/s without touching the per-window result:
-        every window runs exactly the kernels and the order of `estimate` (results are identical)."""
+        every window runs exactly the kernels and the order of `estimate` (results are identical).
+
+        Rolling schedule: window i goes to slot i mod `concurrency`.  A slot's whole solve (H2D, prepare, the graph
+        replays, ROI mask, D2H into the slot's pinned staging buffer) is queued in one go; the host then moves on to
+        the next slot and comes back to this one `concurrency` windows later, when it retires the result (event wait +
+        one host copy) and queues the next window.  The other slots keep the GPU busy while the host plans a window
+        (~4 ms), and the solves run staggered (one window's Adam next to another's splat) instead of in lock step.
+        `self.last_many_stats` holds the host-side time per window of the last call."""
         n_slots = max(1, min(int(concurrency), len(windows)))
         if not self.fused or self.store_history or any(len(w) >= (1 << 21) for w in windows):
             # large windows fill the GPU on their own (and take the eager, non-graph path); a loss history is kept per
@@ -103,41 +121,52 @@ class ContrastMaximizationDense(SolverBase):
             n_slots = 1
         if n_slots == 1:
             return [self.estimate(w, flow0=None if flow0 is None else flow0[i]) for i, w in enumerate(windows)]
-        # two sets of streams / staging buffers, used alternately: while the GPU runs batch k, the host prepares
-        # batch k+1 (H2D, sort, warm-up, graph capture: ~3.5 ms of host time per window) on the other set
-        streams = [torch.cuda.Stream(device=self._device) for _ in range(2 * n_slots)]
+        while len(self._streams) < n_slots:      # slot streams and executables live as long as the solver
+            self._streams.append(torch.cuda.Stream(device=self._device))
+            self._replays.append(ops.ReplaySlot())
+        streams = self._streams
         results: List[Optional[np.ndarray]] = [None] * len(windows)
+        busy: List[Optional[tuple]] = [None] * n_slots
+        t_plan = t_wait = t_copy = t_free = 0.0
+        t_begin = time.perf_counter()
 
-        def collect(job) -> None:
-            for slot, idx, out in job:
-                with torch.cuda.stream(streams[slot]):
-                    results[idx] = self._download(out, slot)
+        def retire(slot: int) -> None:
+            nonlocal t_wait, t_copy, t_free
+            idx, stage, done, keep = busy[slot]
+            busy[slot] = None
+            t0 = time.perf_counter()
+            done.synchronize()
+            t1 = time.perf_counter()
+            results[idx] = stage.numpy().copy()
+            t2 = time.perf_counter()
+            del keep            # the window's CUDA graph and buffers go here
+            t_wait += t1 - t0
+            t_copy += t2 - t1
+            t_free += time.perf_counter() - t2
 
-        pending = None
-        for b, first in enumerate(range(0, len(windows), n_slots)):
-            batch = list(range(first, min(first + n_slots, len(windows))))
-            base = (b % 2) * n_slots
-            plans = []
-            for j, idx in enumerate(batch):
-                with torch.cuda.stream(streams[base + j]):
-                    x0 = self._upload_flow0(None if flow0 is None else flow0[idx])
-                    plans.append((x0,) + self._plan_fused(self._upload_events(windows[idx]), x0))
-            # interleaved issue: the launch queue is finite, so queueing one window's whole solve first would stall the
-            # host until it drains and the other streams would stay empty
-            for call in range(max(p[2] for p in plans)):
-                for j, (x0, advance, n_calls) in enumerate(plans):
-                    if call < n_calls:
-                        with torch.cuda.stream(streams[base + j]):
-                            advance()
-            job = []
-            for j, (x0, _, _) in enumerate(plans):
-                with torch.cuda.stream(streams[base + j]):
-                    job.append((base + j, batch[j], self._finish(x0)))
-            if pending is not None:
-                collect(pending)
-            pending = job
-        if pending is not None:
-            collect(pending)
+        for idx, events in enumerate(windows):
+            slot = idx % n_slots
+            if busy[slot] is not None:
+                retire(slot)
+            t0 = time.perf_counter()
+            with torch.cuda.stream(streams[slot]):
+                x0 = self._upload_flow0(None if flow0 is None else flow0[idx])
+                advance, n_calls = self._plan_fused(self._upload_events(events), x0, self._replays[slot])
+                for _ in range(n_calls):
+                    advance()
+                out = self._finish(x0)
+                stage = self._stage(out, slot)
+                stage.copy_(out, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+            busy[slot] = (idx, stage, done, (advance, out))   # (the graph and its buffers live until the slot retires)
+            t_plan += time.perf_counter() - t0
+        for slot in sorted((s for s in range(n_slots) if busy[s] is not None), key=lambda s: busy[s][0]):
+            retire(slot)
+        k = 1e3 / len(windows)
+        self.last_many_stats = {"windows": len(windows), "slots": n_slots, "host_plan_and_queue_ms": t_plan * k,
+                                "host_wait_for_gpu_ms": t_wait * k, "host_result_copy_ms": t_copy * k,
+                                "host_release_ms": t_free * k, "host_total_ms": (time.perf_counter() - t_begin) * k}
         return results
 
     def _upload_events(self, events: np.ndarray) -> torch.Tensor:
@@ -183,10 +212,11 @@ class ContrastMaximizationDense(SolverBase):
         return mask[None]
 
     # -- fused CUDA path ---------------------------------------------------------------------------
-    def _plan_fused(self, ev: torch.Tensor, x0: torch.Tensor) -> Tuple[Callable[[], None], int]:
+    def _plan_fused(self, ev: torch.Tensor, x0: torch.Tensor, replay=None) -> Tuple[Callable[[], None], int]:
         """Prepare one window for the fused path on the current stream.  Returns (advance, n_calls): calling
         `advance()` n_calls times on that stream performs exactly n_iter solver iterations on `x0` in place."""
         H, W = self.orig_image_shape
+        self._join = lambda: None
         window = ops.PreparedWindow(ev, (H, W), self.warp_direction, self.normalize_t_in_batch, dtype=self._dtype)
         pad = (self.padding, self.padding)
         ws = ops.CmaxWorkspace(H, W, pad, x0.device, self._dtype)
@@ -206,43 +236,64 @@ class ContrastMaximizationDense(SolverBase):
                 hist[count[0]].copy_(ws.loss[0])
                 count[0] += 1
 
-        # CUDA graph: worth its capture/instantiate cost when iterations are short (launch-bound); for large windows
+        # Replayed launch sequence: worth its capture cost when iterations are short (launch-bound); for large windows
         # (>= ~2 Mi events, >100 us of GPU work per iteration) eager launches run ahead of the GPU anyway.
         if not (self.use_cuda_graph and not self.store_history and self.n_iter > 2 and window.n < (1 << 21)):
             return iteration, self.n_iter
-        # `unroll` captured iterations per graph, replayed n_iter / unroll times; the Adam step counter lives on the
-        # device.  Fewer, longer graph launches keep the host ahead when several solves are in flight.
+        # `unroll` captured iterations per executable, replayed n_iter / unroll times; the Adam step counter lives on
+        # the device.  Fewer, longer launches keep the host ahead when several solves are in flight.  The executable
+        # belongs to `replay` (one per estimate_many slot / per solver) and is UPDATED for each new window, never
+        # destroyed while windows are in flight (ops.ReplaySlot).
         unroll = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if self.n_iter % u == 0)
         backup = x0.clone()
-        # capture_begin/capture_end on a side stream instead of `with torch.cuda.graph(...)`: the context manager
-        # synchronises the whole device on entry, which would serialise the concurrent solves of estimate_many
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=x0.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            iteration()  # warm-up outside capture (module loading)
+        side = None
+        if cur == torch.cuda.default_stream(x0.device):
+            # the default stream cannot be captured: one persistent side stream per solver
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=x0.device)
+            side = self._side
+            side.wait_stream(cur)
+        if replay is None:
+            if self._replay is None:
+                self._replay = ops.ReplaySlot()
+            replay = self._replay
+
+        def capture():
+            iteration()        # warm-up outside capture (module loading, the auxiliary lane of this stream)
             x0.copy_(backup)   # the solve must perform exactly n_iter updates
             m.zero_()
             v.zero_()
             step_dev.zero_()
             ws.acc.zero_()
-            graph = torch.cuda.CUDAGraph()
-            graph.capture_begin()
-            for _ in range(unroll):
-                iteration()
-            graph.capture_end()
-        cur.wait_stream(side)
-        keep = (window, ws, m, v, step_dev, backup)   # buffers the graph points into
+            replay.capture(lambda: [iteration() for _ in range(unroll)])
 
-        def replay(_keep=keep):
-            graph.replay()
+        if side is None:
+            capture()
+        else:
+            with torch.cuda.stream(side):
+                capture()
+        keep = (window, ws, m, v, step_dev, backup)   # buffers the executable points into
 
-        return replay, self.n_iter // unroll
+        def advance(_keep=keep):
+            if side is None:
+                replay.launch()
+            else:
+                with torch.cuda.stream(side):
+                    replay.launch()
+
+        def join():
+            if side is not None:
+                cur.wait_stream(side)
+
+        self._join = join
+        return advance, self.n_iter // unroll
 
     def _solve_fused(self, ev: torch.Tensor, x0: torch.Tensor) -> torch.Tensor:
         advance, n_calls = self._plan_fused(ev, x0)
         for _ in range(n_calls):
             advance()
+        self._join()
         if self._hist_dev is not None:
             self.history["loss"] = self._hist_dev.cpu().tolist()
         return x0

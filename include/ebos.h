@@ -372,6 +372,17 @@ EBOS_API int ebos_blur3(const void* image, int batch, int H, int W, double sigma
 EBOS_API int ebos_capture_begin(void* stream);
 EBOS_API int ebos_capture_end_count(void* stream, int32_t* n_kernel_nodes, int32_t* n_other_nodes);
 
+/* Replayable launch sequences for the solver loops (the Adam loop idiom of src/solver/patch_eklt_pyramid2.py:259-288 runs
+ * the same launches n_iter times): ebos_capture_begin(stream) ... the calls of `unroll` iterations ... then
+ * ebos_capture_end_exec turns what was captured into an executable graph.  *exec_inout is a SLOT: NULL on first use; on
+ * later calls the existing executable is updated in place to the new window's pointers and sizes
+ * (cudaGraphExecUpdate; *updated_in_place = 1) or, if the launch sequence changed shape, rebuilt (= 0).  No device
+ * synchronisation in the update path.  ebos_exec_launch enqueues one replay on `stream`; ebos_exec_destroy frees the slot
+ * (may wait for work in flight on the device).  exec_inout / updated_in_place are host pointers. */
+EBOS_API int ebos_capture_end_exec(void* stream, void** exec_inout, int32_t* updated_in_place);
+EBOS_API int ebos_exec_launch(void* exec, void* stream);
+EBOS_API int ebos_exec_destroy(void* exec);
+
 #ifdef __cplusplus
 }
 #endif

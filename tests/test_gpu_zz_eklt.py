@@ -311,6 +311,31 @@ def test_solver_drop_in_matches_reference_estimate(gold):
     assert np.all(flow[:, :roi[0]] == 0) and np.all(flow[:, :, roi[3]:] == 0)
 
 
+def test_estimate_many_matches_sequential_estimates(gold):
+    """Several windows in flight on separate streams (`estimate_many`) give the per-window results of consecutive
+    `estimate` calls: same np.random stream for the start values (window order), same kernels per window.  The double
+    atomics of the reductions are unordered, so later levels agree like two runs of the same window do."""
+    from event_based_bos_b200 import solver
+
+    H, W = (int(v) for v in gold["image"])
+    roi = gold["roi_t"]
+    cls = solver.collections["patch_eklt_pyramid2"]
+    ev = gold["events"]
+    windows = [ev, ev[: len(ev) // 2], ev[len(ev) // 3:], ev, ev[::2]]
+    frames = [gold["frame"]] * len(windows)
+    s = cls((H, W), (roi[1] - roi[0], roi[3] - roi[2]), {}, HOT_PLATE1_SOLVER, None)
+    np.random.seed(7)
+    seq = [s.estimate(w, frame=f) for w, f in zip(windows, frames)]
+    np.random.seed(7)
+    many = s.estimate_many(windows, frames=frames, concurrency=3)
+    assert len(many) == len(windows) and s.last_many_stats["slots"] == 3
+    for a, b in zip(seq, many):
+        assert b.shape == (2, H, W) and b.dtype == np.float64
+        assert np.sqrt(np.mean((a - b) ** 2)) <= 1e-3
+    assert np.sqrt(np.mean((many[0] - gold["solve_flow"]) ** 2)) <= 1e-3      # window 0 is the golden window
+    assert not np.allclose(many[0], many[1])                                  # (the windows do differ)
+
+
 def test_solver_drop_in_float32_within_1e3_px(gold):
     """`solver.eklt.precision: "32"`: the float32 instantiation through the whole drop-in solve stays within the
     north-star bar of the float64 reference (serial check: 1.2e-7 px RMS on this fixture)."""
