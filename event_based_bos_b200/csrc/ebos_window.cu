@@ -50,6 +50,19 @@ int blocked_limit(int64_t n, int H, int W, size_t elem, bool has_weight) {
   const bool dense = n >= (int64_t)16 * H * W;
   return (elem == 4 && !has_weight && dense && !off) ? (int)(n & ~(int64_t)(kBlockEvents - 1)) : 0;
 }
+int item_events();
+// blocks of a full work item of a blocked-striped window (0: even cut, see k_win_items); EBOS_ITEM_CUT=0 disables
+int item_blocks() {
+  static const int off = getenv("EBOS_ITEM_CUT") && atoi(getenv("EBOS_ITEM_CUT")) == 0;
+  const int per = (item_events() + 16) / kBlockEvents;
+  return (off || per < 8) ? 0 : per;
+}
+// CTAs of a tile-kernel launch = an upper bound of the number of work items (one CTA per item slot)
+static unsigned item_slots(int64_t n, int H, int W, int nb) {
+  const int64_t tiles = (int64_t)tiles_x(W) * tiles_y(H);
+  if (nb > 0 && item_blocks() > 0) return (unsigned)(n / ((int64_t)item_blocks() * kBlockEvents) + 2 * tiles + 1);
+  return (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + tiles + 1);
+}
 int item_events() {
   // default 8176 = 32 events per thread: measured on B200 at 16 Mi events the direct tile splat takes 70.7 us with
   // 8176-event items against 72.1 us with 4080 (profiles/README.md, round 2)
@@ -155,9 +168,16 @@ __global__ void __launch_bounds__(256) k_win_tile_offsets(const unsigned int* __
 // One CTA: per-tile item counts, block-wide exclusive scan (looped), fill.
 // items[i] = (first | last << 16 tile-local pixel of the piece, begin, end, tile row << 16 | tile col): the tile kernels
 // stage only the rows of the tile (flow table, IWE / dL/dIWE window) that the piece's origin pixels can reach.
+//
+// Blocked-striped windows with `blocks_per_item` > 0 (default, round 2): a tile's range is cut on ABSOLUTE block
+// boundaries into pieces of `blocks_per_item` whole 512-event blocks plus one remainder piece.  A CTA of 8 warps takes 8
+// blocks per pass, so a piece of 16 blocks is two passes with every warp busy, whereas the even cut leaves a typical
+// benchmark tile (36 blocks -> 3 pieces of 12) with four of the eight warps idle in the second pass, waiting at the
+// flush barrier (ncu r02: 16 % of the splat's stall samples): 5 instead of 6 CTA passes per tile.
 __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile_off, int n_tiles, int tiles_per_row,
                                                     const unsigned int* __restrict__ sorted_keys, int item_events,
-                                                    int n_blocked, int4* __restrict__ items, WindowHeader* __restrict__ h) {
+                                                    int n_blocked, int blocks_per_item, int4* __restrict__ items,
+                                                    WindowHeader* __restrict__ h) {
   __shared__ int warp_sums[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -165,7 +185,17 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
   for (int base = 0; base < n_tiles; base += blockDim.x) {
     const int t = base + threadIdx.x;
     int cnt = 0, b = 0, e = 0;
-    if (t < n_tiles) { b = tile_off[t]; e = tile_off[t + 1]; cnt = (e - b + item_events - 1) / item_events; }
+    const bool by_blocks = n_blocked > 0 && blocks_per_item > 0;
+    int fbk = 0;
+    if (t < n_tiles) {
+      b = tile_off[t]; e = tile_off[t + 1];
+      if (by_blocks) {
+        fbk = b / kBlockEvents;
+        cnt = e > b ? ((e - 1) / kBlockEvents - fbk + blocks_per_item) / blocks_per_item : 0;
+      } else {
+        cnt = (e - b + item_events - 1) / item_events;
+      }
+    }
     // inclusive scan of cnt over the block
     int v = cnt;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -185,9 +215,12 @@ __global__ void __launch_bounds__(1024) k_win_items(const int* __restrict__ tile
     const int tcoord = ((t / tiles_per_row) << 16) | (t % tiles_per_row);   // (tile row, tile col) for the tile kernels
     for (int i = 0; i < cnt; ++i) {
       int pb = min(b + i * piece, e), pe = min(b + (i + 1) * piece, e);
-      // blocked windows: the cuts INSIDE a tile sit on block boundaries (a CTA then starts on a whole block; only the two
-      // blocks a tile shares with its neighbours are ragged).  item_events leaves room for the rounding (<= 511 events).
-      if (n_blocked > 0) {
+      if (by_blocks) {
+        pb = max(b, (fbk + i * blocks_per_item) * kBlockEvents);
+        pe = min(e, (fbk + (i + 1) * blocks_per_item) * kBlockEvents);
+      } else if (n_blocked > 0) {
+        // even cut: the cuts INSIDE a tile sit on block boundaries (a CTA then starts on a whole block; only the two
+        // blocks a tile shares with its neighbours are ragged).  item_events leaves room for the rounding (<= 511 events).
         if (i > 0) pb = min(max((pb + kBlockEvents - 1) & ~(kBlockEvents - 1), b), e);
         if (i + 1 < cnt) pe = min(max((pe + kBlockEvents - 1) & ~(kBlockEvents - 1), b), e);
       }
@@ -1732,7 +1765,7 @@ int window_prepare_impl(const T* events, int64_t n, int H, int W, int direction,
   if (me != cudaSuccess) return cuda_fail(me, "ebos_window_prepare(items)");
   const int n_blocked = blocked_limit(n, H, W, sizeof(T), weight != nullptr);
   k_win_items<<<1, 1024, 0, st>>>(tile_off, n_tiles, tiles_x(W), k_out, n_blocked ? item_events() - kBlockEvents : item_events(),
-                                  n_blocked, reinterpret_cast<int4*>(b + L.off_items), hdr);
+                                  n_blocked, item_blocks(), reinterpret_cast<int4*>(b + L.off_items), hdr);
   k_win_gather<T><<<bx, 256, 0, st>>>(events, weight, n, H, W, perm, hdr, normalize_t, n_blocked,
                                       reinterpret_cast<T*>(b + L.off_x), reinterpret_cast<T*>(b + L.off_y),
                                       reinterpret_cast<T*>(b + L.off_d),
@@ -1799,7 +1832,7 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       static const int occ_env = env_int("EBOS_QOCC");
       // 4 CTAs/SM = 64 registers: with the prefetched next group the 48-register build spills (97 vs 75 us)
       const int occ = (occ_env == 5 || occ_env == 6) ? occ_env : 4;
-      const unsigned qgrid = (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
+      const unsigned qgrid = item_slots(n, H, W, nb);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
@@ -1817,7 +1850,7 @@ int window_splat_t(const void* window, int64_t n, int flags, const T* flow, int 
       static const int occ_env = env_int("EBOS_QOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
       const bool merge = tile_env == 6;
-      const unsigned qgrid = (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + (int64_t)tiles_x(W) * tiles_y(H) + 1);   // one CTA per item slot
+      const unsigned qgrid = item_slots(n, H, W, nb);   // one CTA per item slot
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); float* fi = reinterpret_cast<float*>(iwe);
@@ -1937,7 +1970,7 @@ int window_backward_t(const void* window, int64_t n, int flags, const T* flow, i
       const WindowHeader* hdr = reinterpret_cast<const WindowHeader*>(b);
       static const int occ_env = env_int("EBOS_BOCC");
       const int occ = (occ_env == 3 || occ_env == 5 || occ_env == 6) ? occ_env : 4;
-      const unsigned qgrid = (unsigned)(n / (item_events() - (nb > 0 ? kBlockEvents : 0)) + (int64_t)tiles_x(W) * tiles_y(H) + 1);
+      const unsigned qgrid = item_slots(n, H, W, nb);
       const float* fx = reinterpret_cast<const float*>(sx); const float* fy = reinterpret_cast<const float*>(sy);
       const float* fd = reinterpret_cast<const float*>(sd);
       const float* ff = reinterpret_cast<const float*>(flow); const float* fg = reinterpret_cast<const float*>(gsrc);
