@@ -437,11 +437,13 @@ def run_fused(args, rank, world, local):
     packed = bool(window.packed)
     del captured, window, ev
     torch.cuda.empty_cache()
-    solve_rec = giant_rec = None
+    solve_rec = giant_rec = eklt_rec = None
     if not args.no_subrecords:
         solve_rec = solve_record(args, rank, world, local, quick=True)
         torch.cuda.empty_cache()
         giant_rec = giant_record(args, rank, world, local)
+        torch.cuda.empty_cache()
+        eklt_rec = eklt_record(args, rank, world, local, quick=True)
         torch.cuda.empty_cache()
     if rank != 0:
         return
@@ -481,6 +483,8 @@ def run_fused(args, rank, world, local):
         line["solve"] = solve_rec
     if giant_rec is not None:
         line["giant"] = giant_rec
+    if eklt_rec is not None:
+        line["eklt"] = eklt_rec
     if not args.no_cpu and world == 1:   # the CPU baseline is timed on rank 0 at N=1 only
         n_cpu = args.cpu_events or n
         v, cms, cores = cpu_reference_fused(n_cpu, 3, 1)
@@ -734,8 +738,15 @@ def cpu_reference_eklt(n_events: int, evals: int = 2):
 
 
 def run_eklt(args, rank, world, local):
+    line = eklt_record(args, rank, world, local)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def eklt_record(args, rank, world, local, quick=False):
     """One step = one complete PatchEkltPyramid2.estimate (host events + frame in, host flow out): 4 pyramid levels,
-    120 + 150 + 200 + 300 = 770 objective/gradient/Adam iterations at n_iter = 600, float64 like the reference."""
+    120 + 150 + 200 + 300 = 770 objective/gradient/Adam iterations at n_iter = 600, float64 like the reference.
+    `quick` (sub-record of the default line): no A/B timings of the alternative kernel chains, no CPU baseline."""
     from event_based_bos_b200 import eklt, solver
 
     cfg = json.loads(json.dumps(HOT_PLATE1_SOLVER))
@@ -781,6 +792,8 @@ def run_eklt(args, rank, world, local):
         lvl = prob.level(patch)
         th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous()
         per_level[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+        if quick:
+            continue
         os.environ["EBOS_EKLT_LEGACY"] = "1"          # the first chain (whole-image TV kernel, per-cell 2-D gather)
         try:
             per_level_legacy[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
@@ -793,7 +806,7 @@ def run_eklt(args, rank, world, local):
             finally:
                 os.environ.pop(sw, None)
     if rank != 0:
-        return
+        return None
     iters = [args.solve_iters // (len(slv.levels) + 1 - s + 1) for s in range(1, len(slv.levels) + 1)]
     elem = 4 if args.eklt_precision == "32" else 8
     plane = H * W * elem
@@ -817,19 +830,19 @@ def run_eklt(args, rank, world, local):
                          "frac": alg_eval / (per_level[worst] * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_kind},
             "ms_per_window_single": ms_single, "host_ms_per_window": {k: round(v, 3) for k, v in slv.last_many_stats.items()},
-            "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy,
+            "eval_ms_per_level": per_level, "eval_ms_per_level_legacy_chain": per_level_legacy or None,
             "eval_ms_per_level_without_stored_planes": per_level_stored or None,
             "eval_ms_per_level_without_segment_gather": per_level_seg or None,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
             "gpu_launches": n_windows * sum(iters) * 12}
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and not quick:
         s_eval, cores = cpu_reference_eklt(args.solve_events)
         line["cpu_baseline"] = {"value": 1.0 / (s_eval * sum(iters)), "unit": "windows/s", "cores": cores,
                                 "kind": "port", "sample": f"2 iterations (objective + autograd backward with the "
                                                           f"reference's torch ops, float64, finest level) at "
                                                           f"{s_eval:.3f} s each, x{sum(iters)}"}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def giant_parity_check(rank, world, local):
