@@ -595,7 +595,8 @@ def solve_record(args, rank, world, local, quick=False):
     n, iters = args.solve_events, args.solve_iters
     dev = torch.device("cuda", local)
     cfg = {"outer_padding": 0, "warp_direction": "first", "optimizer": {"method": "Adam", "n_iter": iters},
-           "cmax": {"cost_with_weight": {COST: 1.0, "image_gradient": TV_WEIGHT}, "lr": 0.05}}
+           "cmax": {"cost_with_weight": {COST: 1.0, "image_gradient": TV_WEIGHT}, "lr": 0.05,
+                    "fold_tv": args.fold_tv}}
     slv = solver.collections["contrast_maximization"]((H, W), (H, W), {}, cfg, None)
     gt = smooth_flow((H, W), seed=rank)
     conc = max(1, args.solve_concurrency)
@@ -624,7 +625,13 @@ def solve_record(args, rank, world, local, quick=False):
     f_t = torch.zeros((2, H, W), device=dev)
     m_t, v_t, st_t = torch.zeros_like(f_t), torch.zeros_like(f_t), torch.zeros(1, dtype=torch.int32, device=dev)
     ws_t = ops.CmaxWorkspace(H, W, (0, 0), dev)
-    it_launches, it_other = ops.count_launches(lambda: ops.cmax_adam_iteration(tiny, f_t, m_t, v_t, st_t, ws_t, COST, 1.0, TV_WEIGHT))
+    if slv.fold_tv and ops.fused_tv_supported(tiny) and iters % 2 == 0:     # the iteration the solver issues (TV inside Adam)
+        f_o = torch.zeros_like(f_t)
+        ws_t.zero_dflow()
+        it_launches, it_other = ops.count_launches(
+            lambda: ops.cmax_adam_iteration_fused_tv(tiny, f_t, f_o, m_t, v_t, st_t, ws_t, COST, 1.0, TV_WEIGHT))
+    else:
+        it_launches, it_other = ops.count_launches(lambda: ops.cmax_adam_iteration(tiny, f_t, m_t, v_t, st_t, ws_t, COST, 1.0, TV_WEIGHT))
     del tiny, f_t, m_t, v_t, ws_t
     # pinned host buffers (the e2e contract: inputs come from pinned host memory), handed over as numpy views
     host_events = [synthetic_bos_events(n, (H, W), gt, seed=1000 * rank + i).astype(np.float64) for i in range(max(2, conc))]
@@ -961,6 +968,7 @@ def main():
     ap.add_argument("--solve-iters", type=int, default=600)
     ap.add_argument("--solve-concurrency", type=int, default=8, help="independent windows in flight per GPU (solve workload)")
     ap.add_argument("--eklt-precision", default="64", choices=["32", "64"], help="dtype of the eklt workload (reference: 64)")
+    ap.add_argument("--fold-tv", action="store_true", help="solve workload: the fused Adam + TV kernel instead of TV kernel + Adam kernel (A/B)")
     ap.add_argument("--eklt-concurrency", type=int, default=4, help="independent windows in flight per GPU (eklt workload)")
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -61,6 +61,10 @@ SIGNATURES = {
                                          c_double, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double, c_void_p,
                                          c_double, c_void_p, c_void_p]),
+    "ebos_cmax_adam_iteration_fused_tv": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                  c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double,
+                                                  c_double, c_void_p, c_double, c_void_p, c_void_p]),
     "ebos_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
                                c_int, c_int, c_void_p]),
     "ebos_iwe_cost_peers": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),

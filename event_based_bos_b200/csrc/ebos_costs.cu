@@ -419,8 +419,8 @@ __device__ __forceinline__ T tv_axis(const T v[5], const T w[3], int i, int n, T
 // weights, unaligned widths) goes through the general per-element code.  The kernel was instruction-bound
 // (~200 instructions per element in the first version).
 template <typename T, bool HAS_WTS>
-__device__ __noinline__ void tv_element_general(const T* __restrict__ f, const T* __restrict__ weights, int H, int W,
-                                                int r, int c, T coef, T* __restrict__ out, double& part) {
+__device__ __noinline__ T tv_element_value(const T* __restrict__ f, const T* __restrict__ weights, int H, int W,
+                                           int r, int c, T coef, double& part) {
   T vr[5], vc[5], wr[3] = {(T)1, (T)1, (T)1}, wc[3] = {(T)1, (T)1, (T)1};
 #pragma unroll
   for (int o = -2; o <= 2; ++o) {
@@ -439,7 +439,12 @@ __device__ __noinline__ void tv_element_general(const T* __restrict__ f, const T
   T ar, ac;
   const T adj = tv_axis<T>(vr, wr, r, H, ar) + tv_axis<T>(vc, wc, c, W, ac);
   part += (double)ar + (double)ac;
-  out[(int64_t)r * W + c] = coef * adj;
+  return coef * adj;
+}
+template <typename T, bool HAS_WTS>
+__device__ __forceinline__ void tv_element_general(const T* __restrict__ f, const T* __restrict__ weights, int H, int W,
+                                                   int r, int c, T coef, T* __restrict__ out, double& part) {
+  out[(int64_t)r * W + c] = tv_element_value<T, HAS_WTS>(f, weights, H, W, r, c, coef, part);
 }
 
 __device__ __forceinline__ float sgn_diff(float a, float b) {  // sign(a - b) without forming NaN surprises
@@ -696,6 +701,144 @@ __global__ void __launch_bounds__(256, MINB) k_adam(T* __restrict__ p, const T* 
   if (fin.enabled && tid == 0) finalize_loss<T>(fin);
 }
 __global__ void k_adam_bump(int32_t* step_dev) { *step_dev += 1; }
+
+// ---- Adam with the TV term folded in (fused solver iteration, fp32 lean case) -----------------------------------
+// The unfused iteration spends a whole launch and 4P of traffic on the TV kernel (read the flow, write lambda * dTV as
+// the start value of the gradient plane) before the Adam kernel reads that plane back.  Here the Adam kernel evaluates
+// the TV stencil itself: it marches over the OLD flow exactly like k_flow_tv_march (rows r-2..r+2 of a quad of columns
+// in registers), adds lambda * dTV to the data gradient the backward accumulated on a ZEROED plane, applies the Adam
+// update, writes the NEW flow to a second buffer (neighbouring threads still need the old values: ping-pong) and
+// zero-fills the gradient plane for the next iteration.  16P instead of 14P + 4P per iteration, one launch less.
+// The TV value of this iteration's loss is summed here as well, so the scalar loss, the accumulator reset and the step
+// counter are done by whichever CTA finishes last (ticket in acc[kAccTicket]).
+constexpr int kAccTicket = 4;   // acc[4] (unused by the sums) reinterpreted as the unsigned ticket counter
+constexpr int ADAM_ROWS = 2;    // rows per thread of the fused Adam + TV kernel
+
+__global__ void __launch_bounds__(128) k_adam_tv_march(const float* __restrict__ flow_in, float* __restrict__ flow_out,
+                                                       float* __restrict__ dflow, float* __restrict__ em,
+                                                       float* __restrict__ ev, int H, int W, float coef, double lr,
+                                                       double b1, double b2, double eps, int32_t* __restrict__ step_dev,
+                                                       FinalizeArgs fin, int n_frame_ctas, int fast_gx) {
+  __shared__ double sm[32];
+  __shared__ float s_coef[2];
+  const int ch = blockIdx.y;
+  const int64_t plane = (int64_t)ch * H * W;
+  const float* f = flow_in + plane;
+  float* fo = flow_out + plane;
+  float* g = dflow + plane;
+  float* pm = em + plane;
+  float* pv = ev + plane;
+  const float tb1 = (float)b1, tb2 = (float)b2, teps = (float)eps;
+  double part = 0.0;
+  const bool frame = (int)blockIdx.x < n_frame_ctas;
+  // geometry of the fast region: like k_flow_tv_march, but only ADAM_ROWS rows per thread -- this kernel streams seven
+  // planes from HBM and wants every load of a thread in flight at once (a first version marched over 8 rows with the
+  // loads of row i+1 behind the stores of row i: 12 warps per SM, eight serial memory round trips each, slower than the
+  // two kernels it replaced)
+  const int t = blockIdx.x - n_frame_ctas;
+  const int q = (t % fast_gx) * 64 + (threadIdx.x & 63), rs = 2 + ((t / fast_gx) * 2 + (threadIdx.x >> 6)) * ADAM_ROWS;
+  const int c0 = q * 4;
+  const bool fast = !frame && c0 >= 4 && c0 + 8 <= W && rs <= H - 3;
+  auto rowp = [&](int r) { return f + (int64_t)min(r, H - 1) * W + c0; };
+  // everything that does not depend on the backward is requested before the grid dependency is awaited: the old flow
+  // is read-only during the iteration, the moments are touched by this kernel only
+  float4 rows[ADAM_ROWS + 4], lf[ADAM_ROWS], rt[ADAM_ROWS], m4[ADAM_ROWS], v4[ADAM_ROWS], g4[ADAM_ROWS];
+  int64_t idx[ADAM_ROWS];
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < ADAM_ROWS + 4; ++j) rows[j] = __ldg(reinterpret_cast<const float4*>(rowp(rs - 2 + j)));
+#pragma unroll
+    for (int i = 0; i < ADAM_ROWS; ++i) {
+      lf[i] = __ldg(reinterpret_cast<const float4*>(rowp(rs + i) - 4));
+      rt[i] = __ldg(reinterpret_cast<const float4*>(rowp(rs + i) + 4));
+      idx[i] = (int64_t)min(rs + i, H - 3) * W + c0;
+      m4[i] = *reinterpret_cast<const float4*>(pm + idx[i]);
+      v4[i] = *reinterpret_cast<const float4*>(pv + idx[i]);
+    }
+  }
+  int fr = -1, fc = -1;
+  float ftv = 0.f;
+  if (frame && tv_frame_coord((int64_t)blockIdx.x * blockDim.x + threadIdx.x, H, W, fr, fc))
+    ftv = tv_element_value<float, false>(f, nullptr, H, W, fr, fc, coef, part);
+  else
+    fr = -1;
+  if (threadIdx.x == 0) {
+    const int step = *step_dev + 1;
+    const double bc1 = 1.0 - pow(b1, (double)step);
+    const double bc2 = 1.0 - pow(b2, (double)step);
+    s_coef[0] = (float)(lr / bc1);
+    s_coef[1] = (float)(1.0 / sqrt(bc2));
+  }
+  pdl_wait();          // dflow of the preceding backward
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < ADAM_ROWS; ++i) g4[i] = *reinterpret_cast<const float4*>(g + idx[i]);
+  }
+  __syncthreads();
+  const float step_size = s_coef[0], inv_bc2_sqrt = s_coef[1];
+  if (fr >= 0) {
+    const int64_t i = (int64_t)fr * W + fc;
+    float x = f[i], mm = pm[i], vv = pv[i];
+    adam_one<float>(x, g[i] + ftv, mm, vv, tb1, tb2, teps, step_size, inv_bc2_sqrt);
+    fo[i] = x; pm[i] = mm; pv[i] = vv; g[i] = 0.f;
+  }
+  if (fast) {
+    float fpart = 0.f;
+#pragma unroll
+    for (int i = 0; i < ADAM_ROWS; ++i) {
+      const int r = rs + i;
+      const float4 m2 = rows[i], m1 = rows[i + 1], ce = rows[i + 2], p1 = rows[i + 3], p2 = rows[i + 4];
+      const float row[8] = {lf[i].z, lf[i].w, ce.x, ce.y, ce.z, ce.w, rt[i].x, rt[i].y};   // columns c0-2 .. c0+5
+      const float um2[4] = {m2.x, m2.y, m2.z, m2.w}, um1[4] = {m1.x, m1.y, m1.z, m1.w};
+      const float up1[4] = {p1.x, p1.y, p1.z, p1.w}, up2[4] = {p2.x, p2.y, p2.z, p2.w};
+      const float gd[4] = {g4[i].x, g4[i].y, g4[i].z, g4[i].w};
+      float xm[4] = {m4[i].x, m4[i].y, m4[i].z, m4[i].w}, xv[4] = {v4[i].x, v4[i].y, v4[i].z, v4[i].w}, xo[4];
+      float rpart = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float val = row[2 + k];
+        float adj = 0.5f * (sgn_diff(val, um2[k]) - sgn_diff(up2[k], val));
+        adj += 0.5f * (sgn_diff(val, row[k]) - sgn_diff(row[4 + k], val));
+        rpart += 0.5f * (fabsf(up1[k] - um1[k]) + fabsf(row[3 + k] - row[1 + k]));
+        xo[k] = val;
+        adam_one<float>(xo[k], gd[k] + coef * adj, xm[k], xv[k], tb1, tb2, teps, step_size, inv_bc2_sqrt);
+      }
+      if (r <= H - 3) {
+        fpart += rpart;
+        *reinterpret_cast<float4*>(fo + idx[i]) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+        *reinterpret_cast<float4*>(pm + idx[i]) = make_float4(xm[0], xm[1], xm[2], xm[3]);
+        *reinterpret_cast<float4*>(pv + idx[i]) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        *reinterpret_cast<float4*>(g + idx[i]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    part = (double)fpart;
+  }
+  part = block_sum(part, sm);
+  if (threadIdx.x == 0) {
+    atomicAdd(fin.acc + kAccTvSlots + ((blockIdx.x + 5 * blockIdx.y) & (kAccSpread - 1)), part);
+    __threadfence();
+    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(fin.acc + kAccTicket), 1u);
+    if (ticket == total - 1) {
+      __threadfence();
+      // every CTA's sums are in: scalar loss (reads through L2), reset of ALL accumulators incl. the ticket, step++
+      const volatile double* a = fin.acc;
+      const double cnt = fin.omit ? (double)(fin.Hp - 2) * (double)(fin.Wp - 2) : (double)fin.Hp * (double)fin.Wp;
+      double data = 0.0, tv = a[3];
+      if (fin.kind == EBOS_COST_VARIANCE) data = -((a[1] - a[0] * a[0] / cnt) / (cnt - 1.0));
+      else if (fin.kind == EBOS_COST_GRADMAG) {
+        double sgm = a[2];
+        for (int i = 0; i < kAccSpread; ++i) sgm += a[kAccGradSlots + i];
+        data = -(sgm / cnt);
+      }
+      for (int i = 0; i < kAccSpread; ++i) tv += a[kAccTvSlots + i];
+      tv /= 2.0 * (double)fin.H * (double)fin.W;
+      reinterpret_cast<float*>(fin.loss)[0] = (float)(fin.data_scale * data + fin.tv_scale * tv);
+      for (int i = 0; i < EBOS_ACC_DOUBLES; ++i) fin.acc[i] = 0.0;
+      *step_dev += 1;
+    }
+  }
+}
 
 // out[i] = sum over the peer buffers, in rank order (the one-shot all-reduce of the partial flow gradients)
 template <typename T>
@@ -1165,6 +1308,60 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   if (le != cudaSuccess) return cuda_fail(le, "ebos_cmax_adam_iteration(adam)");
   if (zero_on_lane && cudaStreamWaitEvent(st, lane->fin_done, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(wait zero)");
   EBOS_LAUNCH_CHECK("ebos_cmax_adam_iteration");
+  return EBOS_OK;
+}
+
+int ebos_cmax_adam_iteration_fused_tv(const void* window, int64_t n, int flags, const void* flow_in, void* flow_out, int H,
+                                      int W, int pad_h, int pad_w, int kind, int omit_boundary, double data_scale,
+                                      double tv_scale, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss,
+                                      double* acc, void* exp_avg, void* exp_avg_sq, double lr, double beta1, double beta2,
+                                      double eps, int32_t* step_dev, double blur_sigma, void* blur_plane, void* stream) {
+  EBOS_REQUIRE(blur_sigma >= 0.0, "ebos_cmax_adam_iteration_fused_tv: blur_sigma must not be negative");
+  EBOS_REQUIRE(window && flow_in && flow_out && iwe && dflow && loss && acc && exp_avg && exp_avg_sq && step_dev && n >= 0 &&
+                   H > 1 && W > 1 && pad_h >= 0 && pad_w >= 0 && flow_in != flow_out,
+               "ebos_cmax_adam_iteration_fused_tv: bad argument");
+  EBOS_REQUIRE(kind == EBOS_COST_VARIANCE || kind == EBOS_COST_GRADMAG, "ebos_cmax_adam_iteration_fused_tv: unknown cost kind");
+  EBOS_REQUIRE(kind != EBOS_COST_GRADMAG || grad_iwe, "ebos_cmax_adam_iteration_fused_tv: GRADMAG needs the grad_iwe scratch plane");
+  const size_t align = reinterpret_cast<size_t>(flow_in) | reinterpret_cast<size_t>(flow_out) | reinterpret_cast<size_t>(dflow) |
+                       reinterpret_cast<size_t>(exp_avg) | reinterpret_cast<size_t>(exp_avg_sq);
+  if (dtype != EBOS_F32 || (W & 3) || W < 12 || H < 5 || (align & 15)) {
+    set_error("ebos_cmax_adam_iteration_fused_tv: needs fp32, W % 4 == 0, W >= 12, H >= 5 and 16-byte aligned planes "
+              "(use ebos_cmax_adam_iteration)");
+    return EBOS_ERR_UNSUPPORTED;
+  }
+  const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
+  EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_adam_iteration_fused_tv: omit_boundary needs an image larger than 2x2");
+  cudaStream_t st = as_stream(stream);
+  // graph nodes of one iteration: [splat] [cost] [backward | IWE memset] [Adam + TV + loss + accumulator reset + step++]
+  AuxLane* lane = aux_lane(st);
+  int rc = window_splat_launch(window, n, flags, flow_in, H, W, pad_h, pad_w, dtype, iwe, st, false);   // iwe is zero on entry
+  if (rc) return rc;
+  void* gplane = nullptr;
+  rc = cost_with_blur(kind, iwe, Hp, Wp, omit_boundary, data_scale, dtype, acc, grad_iwe, blur_sigma, blur_plane, st, &gplane);
+  if (rc) return rc;
+  const size_t iwe_bytes = (size_t)Hp * Wp * sizeof(float);
+  bool zero_on_lane = false;
+  if (lane && (kind == EBOS_COST_GRADMAG || blur_sigma > 0.0) && cudaEventRecord(lane->cost_done, st) == cudaSuccess &&
+      cudaStreamWaitEvent(lane->stream, lane->cost_done, 0) == cudaSuccess) {
+    if (cudaMemsetAsync(iwe, 0, iwe_bytes, lane->stream) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration_fused_tv(zero)");
+    zero_on_lane = cudaEventRecord(lane->fin_done, lane->stream) == cudaSuccess;
+    if (!zero_on_lane) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration_fused_tv(zero event)");
+  }
+  rc = window_backward_launch(window, n, flags, flow_in, H, W, pad_h, pad_w, dtype, gplane, kind, iwe, acc, omit_boundary,
+                              data_scale, dflow, st);
+  if (rc) return rc;
+  if (!zero_on_lane && cudaMemsetAsync(iwe, 0, iwe_bytes, st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration_fused_tv(zero)");
+  const FinalizeArgs fin{1, kind, Hp, Wp, H, W, omit_boundary, data_scale, tv_scale, acc, loss};
+  const float coef = (float)(tv_scale / (2.0 * (double)H * (double)W));
+  const int64_t n_frame = (int64_t)4 * W + (int64_t)8 * (H - 4);
+  const int n_frame_ctas = (int)((n_frame + 127) / 128);
+  const int fast_gx = ((W >> 2) + 63) / 64, fast_gy = (H - 4 + 2 * ADAM_ROWS - 1) / (2 * ADAM_ROWS);
+  cudaError_t le = launch_pdl(k_adam_tv_march, dim3(n_frame_ctas + fast_gx * fast_gy, 2), dim3(128), st, (const float*)flow_in,
+                              (float*)flow_out, (float*)dflow, (float*)exp_avg, (float*)exp_avg_sq, H, W, coef, lr, beta1, beta2,
+                              eps, step_dev, fin, n_frame_ctas, fast_gx);
+  if (le != cudaSuccess) return cuda_fail(le, "ebos_cmax_adam_iteration_fused_tv(adam)");
+  if (zero_on_lane && cudaStreamWaitEvent(st, lane->fin_done, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration_fused_tv(wait zero)");
+  EBOS_LAUNCH_CHECK("ebos_cmax_adam_iteration_fused_tv");
   return EBOS_OK;
 }
 

@@ -330,7 +330,12 @@ class CmaxWorkspace:
         # zero-filled for the NEXT evaluation concurrently with the backward of the current one).  Cleared for good by a
         # call that keeps its IWE (`keep_iwe=True`) or by anyone writing into `acc` / `iwe` directly.
         self.clean = True
+        self.dflow_clean = False     # `dflow` all zero between calls (contract of cmax_adam_iteration_fused_tv)
         self._blur = None
+
+    def zero_dflow(self) -> None:
+        self.dflow.zero_()
+        self.dflow_clean = True
 
     def blur_plane(self) -> torch.Tensor:
         """Scratch plane of the blurred-IWE objective (`blur_sigma > 0`), allocated on first use."""
@@ -365,6 +370,7 @@ def cmax_value_and_grad(window: PreparedWindow, flow: torch.Tensor, cost: str = 
             raise ValueError(f"tv_weights must be [{window.H},{window.W}], got {tuple(tvw.shape)}")
     if keep_iwe:
         ws.clean = False
+    ws.dflow_clean = False
     check(_capi.load().ebos_cmax_value_and_grad(
         ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw,
         COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code,
@@ -426,12 +432,51 @@ def cmax_adam_iteration(window: PreparedWindow, flow: torch.Tensor, exp_avg: tor
         tvw = tv_weights.to(window.dtype).contiguous()
     if not ws.clean:
         raise RuntimeError("cmax_adam_iteration needs a clean CmaxWorkspace (accumulators and IWE zero on entry)")
+    ws.dflow_clean = False
     check(_capi.load().ebos_cmax_adam_iteration(
         ptr(window.buffer), window.n, window.flags, ptr(flow), window.H, window.W, ws.ph, ws.pw, COST_KINDS[cost],
         int(bool(omit_boundary)), float(data_weight), float(tv_weight), ptr(tvw), window.code, ptr(ws.iwe),
         ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), ptr(exp_avg), ptr(exp_avg_sq), float(lr),
         float(betas[0]), float(betas[1]), float(eps), ptr(step_dev), float(blur_sigma),
         ptr(ws.blur_plane()) if blur_sigma > 0 else 0, current_stream()), "ebos_cmax_adam_iteration")
+    return ws.loss
+
+
+def fused_tv_supported(window: PreparedWindow, tv_weights: Optional[torch.Tensor] = None) -> bool:
+    """Whether `cmax_adam_iteration_fused_tv` applies: fp32, unit TV weights, W % 4 == 0, W >= 12, H >= 5."""
+    return (window.dtype == torch.float32 and tv_weights is None and window.W % 4 == 0 and window.W >= 12
+            and window.H >= 5)
+
+
+def cmax_adam_iteration_fused_tv(window: PreparedWindow, flow_in: torch.Tensor, flow_out: torch.Tensor,
+                                 exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step_dev: torch.Tensor,
+                                 workspace: CmaxWorkspace, cost: str = "gradient_magnitude", data_weight: float = 1.0,
+                                 tv_weight: float = 0.0, omit_boundary: bool = False, lr: float = 0.05,
+                                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                                 blur_sigma: float = 0.0) -> torch.Tensor:
+    """`cmax_adam_iteration` with the TV term folded into the Adam kernel (one launch and 2 of 18 plane passes less per
+    iteration): reads `flow_in`, writes the updated flow to `flow_out` (another [2,H,W] tensor; callers alternate the
+    two).  On top of the clean-workspace contract, `workspace.dflow` must be zero on entry (`workspace.zero_dflow()`
+    once) and is left zero.  Returns `workspace.loss` (the objective before the update)."""
+    _check_cuda(flow_in, flow_out, exp_avg, exp_avg_sq, step_dev)
+    _check_flow(window, flow_in)
+    _check_flow(window, flow_out)
+    ws = workspace
+    if not fused_tv_supported(window):
+        raise ValueError("cmax_adam_iteration_fused_tv needs an fp32 window with W % 4 == 0, W >= 12, H >= 5")
+    if flow_in.data_ptr() == flow_out.data_ptr():
+        raise ValueError("cmax_adam_iteration_fused_tv: flow_in and flow_out must be different tensors")
+    if ws.dtype != window.dtype or exp_avg.dtype != window.dtype or exp_avg_sq.dtype != window.dtype:
+        raise TypeError("cmax_adam_iteration_fused_tv: window, workspace, flows and Adam moments must share a dtype")
+    if not ws.clean or not ws.dflow_clean:
+        raise RuntimeError("cmax_adam_iteration_fused_tv needs a clean CmaxWorkspace with a zeroed gradient plane "
+                           "(workspace.zero_dflow())")
+    check(_capi.load().ebos_cmax_adam_iteration_fused_tv(
+        ptr(window.buffer), window.n, window.flags, ptr(flow_in), ptr(flow_out), window.H, window.W, ws.ph, ws.pw,
+        COST_KINDS[cost], int(bool(omit_boundary)), float(data_weight), float(tv_weight), window.code, ptr(ws.iwe),
+        ptr(ws.grad_iwe), ptr(ws.dflow), ptr(ws.loss), ptr(ws.acc), ptr(exp_avg), ptr(exp_avg_sq), float(lr),
+        float(betas[0]), float(betas[1]), float(eps), ptr(step_dev), float(blur_sigma),
+        ptr(ws.blur_plane()) if blur_sigma > 0 else 0, current_stream()), "ebos_cmax_adam_iteration_fused_tv")
     return ws.loss
 
 

@@ -38,7 +38,7 @@ class ContrastMaximizationDense(SolverBase):
     Reads from `solver_config` (yaml `solver:` block): `warp_direction`, `outer_padding`, `optimizer.n_iter`,
     `optimizer.method` ("Adam"), and the sub-dict `cmax` with `cost_with_weight` (default
     {gradient_magnitude: 1.0, image_gradient: 0.5}), `lr` (0.05), `omit_boundary` (False), `fused` (True),
-    `cuda_graph` (True), `store_history` (False), `precision` ("32" fast path | "64" = the dtype the
+    `cuda_graph` (True), `fold_tv` (False), `store_history` (False), `precision` ("32" fast path | "64" = the dtype the
     reference's solvers run in, src/solver/patch_eklt_pyramid2.py:253).
     """
 
@@ -53,6 +53,11 @@ class ContrastMaximizationDense(SolverBase):
         self.fused = bool(cm.get("fused", True))
         self.use_cuda_graph = bool(cm.get("cuda_graph", True))
         self.store_history = bool(cm.get("store_history", False))
+        # TV term inside the Adam kernel (ebos_cmax_adam_iteration_fused_tv).  Off by default: measured on B200 (r02r) the
+        # fused kernel is L2-bandwidth bound on its 3x re-read of the flow rows (17 us against 10.7 us for Adam alone,
+        # with the separate TV kernel hidden beside the splat): 41.0 vs 49.0 windows/s with one window in flight,
+        # 56.6 vs 66.2 with eight
+        self.fold_tv = bool(cm.get("fold_tv", False))
         self.precision = str(cm.get("precision", "32"))
         if self.precision not in ("32", "64"):
             raise ValueError(f"cmax.precision must be '32' or '64', got {self.precision!r}")
@@ -226,12 +231,27 @@ class ContrastMaximizationDense(SolverBase):
         step_dev = torch.zeros(1, dtype=torch.int32, device=x0.device)
         hist = torch.zeros(max(self.n_iter, 1), dtype=self._dtype, device=x0.device) if self.store_history else None
         self._hist_dev = hist
-        count = [0]
+        count = [0, 0]     # (loss-history slot, iterations issued: parity selects the source flow plane)
+
+        # opt-in: TV term folded into the Adam kernel (fp32, W % 4 == 0; an even iteration count, so that the two flow
+        # planes the kernel alternates between end on `x0`): one launch and 2 of 18 plane passes less per iteration
+        fold = self.fold_tv and ops.fused_tv_supported(window) and self.n_iter % 2 == 0
+        flows = [x0, torch.empty_like(x0)] if fold else [x0]
+        if fold:
+            ws.zero_dflow()
 
         def iteration():
-            # one C call: TV | splat -> cost -> backward -> Adam (+ loss, accumulator reset), six graph nodes
-            ops.cmax_adam_iteration(window, x0, m, v, step_dev, ws, self.data_cost, self.data_weight, self.tv_weight,
-                                    None, self.omit_boundary, self.lr, blur_sigma=self.blur_sigma)
+            if fold:
+                # one C call: splat -> cost -> backward -> Adam + TV (+ loss, accumulator reset), five graph nodes
+                src = count[1] & 1
+                ops.cmax_adam_iteration_fused_tv(window, flows[src], flows[1 - src], m, v, step_dev, ws, self.data_cost,
+                                                 self.data_weight, self.tv_weight, self.omit_boundary, self.lr,
+                                                 blur_sigma=self.blur_sigma)
+                count[1] += 1
+            else:
+                # one C call: TV | splat -> cost -> backward -> Adam (+ loss, accumulator reset), six graph nodes
+                ops.cmax_adam_iteration(window, x0, m, v, step_dev, ws, self.data_cost, self.data_weight, self.tv_weight,
+                                        None, self.omit_boundary, self.lr, blur_sigma=self.blur_sigma)
             if hist is not None:
                 hist[count[0]].copy_(ws.loss[0])
                 count[0] += 1
@@ -244,7 +264,7 @@ class ContrastMaximizationDense(SolverBase):
         # the device.  Fewer, longer launches keep the host ahead when several solves are in flight.  The executable
         # belongs to `replay` (one per estimate_many slot / per solver) and is UPDATED for each new window, never
         # destroyed while windows are in flight (ops.ReplaySlot).
-        unroll = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if self.n_iter % u == 0)
+        unroll = next(u for u in ((10, 8, 6, 4, 2) if fold else (10, 8, 6, 5, 4, 3, 2, 1)) if self.n_iter % u == 0)
         backup = x0.clone()
         cur = torch.cuda.current_stream()
         side = None
@@ -266,6 +286,7 @@ class ContrastMaximizationDense(SolverBase):
             v.zero_()
             step_dev.zero_()
             ws.acc.zero_()
+            count[1] = 0
             replay.capture(lambda: [iteration() for _ in range(unroll)])
 
         if side is None:
@@ -273,7 +294,7 @@ class ContrastMaximizationDense(SolverBase):
         else:
             with torch.cuda.stream(side):
                 capture()
-        keep = (window, ws, m, v, step_dev, backup)   # buffers the executable points into
+        keep = (window, ws, m, v, step_dev, backup, flows)   # buffers the executable points into
 
         def advance(_keep=keep):
             if side is None:

@@ -219,6 +219,20 @@ EBOS_API int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, 
                              double* acc, void* exp_avg, void* exp_avg_sq, double lr, double beta1, double beta2,
                              double eps, int32_t* step_dev, double blur_sigma, void* blur_plane, void* stream);
 
+/* The same solver iteration with the TV term folded into the Adam kernel (fp32, unit TV weights): five graph nodes
+ *   [splat] [cost] [backward | IWE memset] [Adam + lambda dTV + loss + accumulator reset + step counter].
+ * The Adam kernel evaluates the TV stencil (src/costs/image_gradient.py:60-75) on `flow_in` itself, adds it to the data
+ * gradient the backward accumulated in `dflow`, and writes the updated flow to `flow_out` (a second [2,H,W] plane, must
+ * not alias flow_in: neighbouring pixels still read the old values).  Contract on top of ebos_cmax_adam_iteration's:
+ * `dflow` must be ZERO on entry and is left zero on exit.  Callers alternate the two flow planes between iterations.
+ * Returns EBOS_ERR_UNSUPPORTED (nothing enqueued) unless dtype is fp32, W % 4 == 0, W >= 12, H >= 5 and the planes are
+ * 16-byte aligned -- use ebos_cmax_adam_iteration then. */
+EBOS_API int ebos_cmax_adam_iteration_fused_tv(const void* window, int64_t n, int flags, const void* flow_in, void* flow_out,
+                             int H, int W, int pad_h, int pad_w, int kind, int omit_boundary, double data_scale,
+                             double tv_scale, int dtype, void* iwe, void* grad_iwe, void* dflow, void* loss, double* acc,
+                             void* exp_avg, void* exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                             int32_t* step_dev, double blur_sigma, void* blur_plane, void* stream);
+
 /* torch.optim.Adam step (src/solver/patch_eklt_pyramid2.py:262-264,284), in place.  `step` is
  * 1-based.  Elementwise over n values. */
 EBOS_API int ebos_adam_step(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, double lr,

@@ -446,6 +446,44 @@ def test_fp64_value_and_grad_vs_reference_golden(golden, ops):
         assert rel_err(grad.cpu().numpy(), golden[f"{name}/grad"]) <= 1e-11, name
 
 
+@pytest.mark.parametrize("shape,n", [((5, 12), 300), ((37, 52), 4000), ((64, 96), 20000), ((96, 128), 250000)])
+@pytest.mark.parametrize("cost", ["gradient_magnitude", "image_variance"])
+def test_adam_iteration_with_folded_tv_matches_the_unfused_iteration(ops, shape, n, cost):
+    """`cmax_adam_iteration_fused_tv` (TV stencil inside the Adam kernel, two flow planes used alternately, gradient
+    plane kept zero) against `cmax_adam_iteration` (TV kernel + Adam kernel) on the same window: flow, both Adam
+    moments, the loss of every iteration and the step counter, over several iterations incl. the frame rows / columns of
+    the TV stencil (5 x 12 is all frame).  The two differ only in the order the data and TV gradients are added."""
+    from event_based_bos_b200.utils import synthetic_events
+
+    H, W = shape
+    ev = torch.from_numpy(synthetic_events(n, (H, W), seed=3)).cuda()
+    window = ops.PreparedWindow(ev, (H, W), "first", True)
+    assert ops.fused_tv_supported(window)
+    g = torch.Generator().manual_seed(5)
+    x_ref = (torch.rand((2, H, W), generator=g) * 4 - 2).cuda()
+    xa, xb = x_ref.clone(), torch.full_like(x_ref, float("nan"))
+    st_ref, st = (torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(2))
+    m_ref, v_ref, m, v = (torch.zeros_like(x_ref) for _ in range(4))
+    ws_ref, ws = ops.CmaxWorkspace(H, W, (0, 0), "cuda"), ops.CmaxWorkspace(H, W, (0, 0), "cuda")
+    ws.zero_dflow()
+    for it in range(6):
+        l_ref = ops.cmax_adam_iteration(window, x_ref, m_ref, v_ref, st_ref, ws_ref, cost, 1.0, 0.5).clone()
+        src, dst = (xa, xb) if it % 2 == 0 else (xb, xa)
+        l = ops.cmax_adam_iteration_fused_tv(window, src, dst, m, v, st, ws, cost, 1.0, 0.5).clone()
+        assert abs(float(l) - float(l_ref)) <= 1e-5 * max(abs(float(l_ref)), 1e-12), it
+        assert int(st) == int(st_ref) == it + 1
+        assert float(ws.dflow.abs().max()) == 0.0 and float(ws.acc.abs().max()) == 0.0      # left clean
+        # first moments are linear in the gradient: tight; the flow moves by ~lr per step whatever |g| is, and where the
+        # gradient is at rounding level the sign of the step may differ, so it is compared through the second moment too
+        assert rel_err(m.cpu().numpy(), m_ref.cpu().numpy()) <= 2e-5, it
+        assert rel_err(v.cpu().numpy(), v_ref.cpu().numpy()) <= 2e-5, it
+        moved = (dst - x_ref).abs()
+        assert float((moved > 2e-3).float().mean()) <= 2e-3, (it, float(moved.max()))
+        dst.copy_(x_ref)                     # keep the two runs on the same trajectory (Adam amplifies rounding noise)
+        m.copy_(m_ref)
+        v.copy_(v_ref)
+
+
 def _run_solver(events, H, W, iters, lr, tvw, precision, fused, graph, flow0=None):
     from event_based_bos_b200 import solver
 
@@ -485,6 +523,23 @@ def test_solver_final_flow_within_1e3_px(golden):
                 assert _rms(flow, golden["solve_init_f64/flow"]) <= ref_gap + 1e-3
             elif tag == "f64":
                 assert r <= 1e-8  # fp64: rounding-level agreement
+
+
+def test_solver_with_folded_tv_within_1e3_px(golden):
+    """`cmax.fold_tv: true` (TV stencil inside the Adam kernel, opt-in) through a whole solve: same bar as the default
+    iteration against the reference's fp32 loop from the tie-free start, captured and eager."""
+    from event_based_bos_b200 import solver
+
+    H, W, iters, lr, tvw = golden["solve_init_f32/cfg"]
+    H, W = int(H), int(W)
+    for graph in (True, False):
+        cfg = {"outer_padding": 0, "warp_direction": "first", "optimizer": {"method": "Adam", "n_iter": int(iters)},
+               "cmax": {"cost_with_weight": {"gradient_magnitude": 1.0, "image_gradient": float(tvw)}, "lr": float(lr),
+                        "precision": "32", "cuda_graph": graph, "fold_tv": True}}
+        assert int(iters) % 2 == 0
+        slv = solver.collections["contrast_maximization"]((H, W), (H, W), {}, cfg, None)
+        flow = slv.estimate(np.asarray(golden["solve_init_f32/events"], dtype=np.float64), flow0=golden["solve_init_f32/flow0"])
+        assert _rms(flow, golden["solve_init_f32/flow"]) <= 1e-3, graph
 
 
 def test_estimate_many_matches_sequential_estimates(golden):
