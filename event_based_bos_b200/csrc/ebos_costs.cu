@@ -8,7 +8,8 @@
 //
 // All reductions: per-thread double accumulators -> warp shuffle -> one atomicAdd(double) per CTA.
 // acc layout (double[EBOS_ACC_DOUBLES = 40]): [0] sum(IWE) [1] sum(IWE^2) [2] + [8..23] sum(gx^2+gy^2)
-// [3] + [24..39] sum(|TV terms|).  Same-address atomics from different CTAs serialise in the L2 atomic unit
+// [3] + [24..39] sum(|TV terms|); [4] ticket counter of the fused Adam + TV kernel; [5], [6] the Adam bias-correction
+// factors of the current iteration (written by the TV kernel, NOT reset).  Same-address atomics from different CTAs serialise in the L2 atomic unit
 // (~6 ns each on B200: 3.5 us for the ~600 CTAs of the TV kernel, as long as its real work), so the two plane
 // kernels of the hot path spread their per-CTA partial sums over 16 slots; the consumers add the slots up.
 #include <algorithm>
@@ -236,6 +237,10 @@ template <typename T> struct PeerPlanes {
   int n;
   __device__ __forceinline__ T load(int64_t idx) const {
     T v = p[0][idx];
+    // (not unrolled: the compiler otherwise expands the seven optional peers at every call site -- 5000 of the 7160 SASS
+    //  instructions of k_gradmag_sep were this loop, 25 times over in the frame-pixel code, and the kernel stalled on
+    //  instruction fetches; with one plane the loop body never runs)
+#pragma unroll 1
     for (int r = 1; r < n; ++r) v += p[r][idx];
     return v;
   }
@@ -251,6 +256,8 @@ __device__ void gradmag_frame_pixel(const PeerPlanes<T>& iwe, int Hp, int Wp, in
     for (int b = -2; b <= 2; ++b)
       v[a + 2][b + 2] = iwe.load((int64_t)min(max(r + a, 0), Hp - 1) * Wp + min(max(c + b, 0), Wp - 1));
   T out = 0;
+  // (fully unrolled on purpose: with the outer loop rolled the 5 x 5 neighbourhood moves to local memory and these few
+  //  threads become the critical path of the launch -- measured, r02t: 12.1 instead of 10.5 us)
 #pragma unroll
   for (int dr = -1; dr <= 1; ++dr) {
 #pragma unroll
@@ -452,13 +459,30 @@ __device__ __forceinline__ float sgn_diff(float a, float b) {  // sign(a - b) wi
   return (d > 0.f ? 1.f : 0.f) - (d < 0.f ? 1.f : 0.f);
 }
 
+// Fused solver iteration: the TV kernel runs once per iteration, strictly before that iteration's Adam kernel and off
+// the critical path (beside the splat).  Its first thread therefore also advances the device-side Adam step counter and
+// evaluates the two bias-correction factors (two double pow() calls, ~1 us) into dst[0..1] = acc[kAccAdamCoefs..]:
+// the Adam kernel used to do that itself, one thread per CTA with the other 255 waiting at a barrier (ncu r02s: 25 % of
+// its stall samples).
+constexpr int kAccAdamCoefs = 5;   // acc[5], acc[6]: lr / (1 - b1^t), 1 / sqrt(1 - b2^t) of the current iteration
+struct StepCoefs {
+  int32_t* step_dev;
+  double lr, b1, b2;
+  double* dst;
+};
+__device__ __forceinline__ void advance_step(const StepCoefs& sc) {
+  const int step = *sc.step_dev + 1;
+  *sc.step_dev = step;
+  if (sc.dst) {
+    sc.dst[0] = sc.lr / (1.0 - pow(sc.b1, (double)step));
+    sc.dst[1] = 1.0 / sqrt(1.0 - pow(sc.b2, (double)step));
+  }
+}
+
 template <typename T, bool HAS_WTS>
 __global__ void __launch_bounds__(256) k_flow_tv(const T* __restrict__ flow, const T* __restrict__ weights, int H, int W,
-                                                 T coef, double* __restrict__ acc, T* __restrict__ dflow,
-                                                 int32_t* __restrict__ step_dev) {
-  // fused solver iteration: this kernel also advances the device-side Adam step counter (it runs once per
-  // iteration, strictly before that iteration's Adam kernel)
-  if (step_dev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *step_dev += 1;
+                                                 T coef, double* __restrict__ acc, T* __restrict__ dflow, StepCoefs sc) {
+  if (sc.step_dev && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) advance_step(sc);
   // coef = tv_scale / (2*H*W).  Grid (ceil(quads/64), ceil(H/4), 2), block = 64 quads x 4 rows: no div/mod in the
   // index math (the first lean version spent most of its 111 instructions per element on 64-bit div/mod).
   __shared__ double sm[32];
@@ -527,8 +551,8 @@ __device__ __forceinline__ bool tv_frame_coord(int64_t idx, int H, int W, int& r
 // grid.x = n_frame_ctas + fast CTAs (64 quads x 2 row strips each), grid.y = channel.  Needs H >= 5, W >= 12.
 __global__ void __launch_bounds__(128) k_flow_tv_march(const float* __restrict__ flow, int H, int W, float coef,
                                                        double* __restrict__ acc, float* __restrict__ dflow,
-                                                       int32_t* __restrict__ step_dev, int n_frame_ctas, int fast_gx) {
-  if (step_dev && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *step_dev += 1;
+                                                       StepCoefs sc, int n_frame_ctas, int fast_gx) {
+  if (sc.step_dev && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) advance_step(sc);
   __shared__ double sm[32];
   const int ch = blockIdx.y;
   const float* f = flow + (int64_t)ch * H * W;
@@ -625,24 +649,33 @@ __device__ __forceinline__ void finalize_loss(const FinalizeArgs& f) {
   else if (f.kind == EBOS_COST_GRADMAG) data = -(acc_total(f.acc, 2, kAccGradSlots) / cnt);
   const double tv = acc_total(f.acc, 3, kAccTvSlots) / (2.0 * (double)f.H * (double)f.W);
   reinterpret_cast<T*>(f.loss)[0] = (T)(f.data_scale * data + f.tv_scale * tv);
+  // (the Adam coefficients of this iteration stay: other CTAs of the Adam kernel may not have read them yet)
 #pragma unroll
-  for (int i = 0; i < EBOS_ACC_DOUBLES; ++i) f.acc[i] = 0.0;
+  for (int i = 0; i < EBOS_ACC_DOUBLES; ++i)
+    if (i != kAccAdamCoefs && i != kAccAdamCoefs + 1) f.acc[i] = 0.0;
 }
 
-// step_mode 0: `step_host`;  1: *step_dev + 1 (bumped afterwards by k_adam_bump);  2: *step_dev (already advanced)
+// step_mode 0: `step_host`;  1: *step_dev + 1 (bumped afterwards by k_adam_bump);  2: *step_dev (already advanced);
+// 3: the two factors are read from coefs_dev (written by the TV kernel of the same iteration, see advance_step)
 // (4 CTAs/SM = 62 registers: 10.7 us on the [2,720,1280] flow; 13.4 us unconstrained at 78 registers / 3 CTAs, 11.2 us at 40
 //  registers with spills)
 template <typename T, int MINB = 4>
 __global__ void __launch_bounds__(256, MINB) k_adam(T* __restrict__ p, const T* __restrict__ g, T* __restrict__ m,
                                               T* __restrict__ v, int64_t n, double lr, double b1, double b2, double eps,
                                               int step_host, const int32_t* __restrict__ step_dev, int step_mode,
-                                              FinalizeArgs fin) {
+                                              FinalizeArgs fin, const double* __restrict__ coefs_dev = nullptr) {
   // bias corrections: two double pow() calls cost ~300 instructions; done by one thread per CTA and shared through
   // shared memory (the first version had every thread do them: 163 instructions per float4, ncu r01e).  The first
   // loads of every thread are issued before the barrier so that their latency overlaps the pow().
   __shared__ T s_coef[2];
   pdl_wait();   // dflow of the preceding backward (fused iteration: launched with the PDL attribute)
   auto coefs = [&]() {
+    if (step_mode == 3) {        // block-uniform: no barrier, every thread reads the two factors (L2 hits)
+      s_coef[0] = (T)coefs_dev[0];
+      s_coef[1] = (T)coefs_dev[1];
+      __syncwarp();
+      return;
+    }
     if (threadIdx.x == 0) {
       int step = step_host;
       if (step_mode == 1) step = *step_dev + 1;
@@ -952,7 +985,8 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
 
 template <typename T>
 int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, double* acc, T* dflow, cudaStream_t st,
-              int32_t* step_dev = nullptr) {
+              StepCoefs sc = StepCoefs{}) {
+  int32_t* step_dev = sc.step_dev;
   if ((tv_scale == 0.0 && !step_dev) || H < 2 || W < 2) {
     cudaError_t e = cudaMemsetAsync(dflow, 0, (size_t)2 * H * W * sizeof(T), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_flow_tv memset");
@@ -969,14 +1003,14 @@ int flow_tv_t(const T* flow, const T* weights, int H, int W, double tv_scale, do
       const int n_frame_ctas = (int)((n_frame + 127) / 128);
       const int fast_gx = ((W >> 2) + 63) / 64, fast_gy = (H - 4 + 2 * TV_ROWS - 1) / (2 * TV_ROWS);
       const dim3 mgrid(n_frame_ctas + fast_gx * fast_gy, 2);
-      k_flow_tv_march<<<mgrid, 128, 0, st>>>(flow, H, W, coef, acc, dflow, step_dev, n_frame_ctas, fast_gx);
+      k_flow_tv_march<<<mgrid, 128, 0, st>>>(flow, H, W, coef, acc, dflow, sc, n_frame_ctas, fast_gx);
       EBOS_LAUNCH_CHECK("ebos_flow_tv");
       return EBOS_OK;
     }
   }
   const dim3 grid(((W + 3) / 4 + 63) / 64, (H + 3) / 4, 2);
-  if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, step_dev);
-  else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, step_dev);
+  if (weights) k_flow_tv<T, true><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, sc);
+  else k_flow_tv<T, false><<<grid, 256, 0, st>>>(flow, weights, H, W, coef, acc, dflow, sc);
   EBOS_LAUNCH_CHECK("ebos_flow_tv");
   return EBOS_OK;
 }
@@ -1251,8 +1285,10 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   const int Hp = H + 2 * pad_h, Wp = W + 2 * pad_w;
   EBOS_REQUIRE(!omit_boundary || (Hp > 2 && Wp > 2), "ebos_cmax_adam_iteration: omit_boundary needs an image larger than 2x2");
   cudaStream_t st = as_stream(stream);
-  // graph nodes of one iteration: [TV + step++ | splat] [cost] [backward | IWE memset] [Adam + loss + acc reset]
+  // graph nodes of one iteration: [TV + step++ + Adam factors | splat] [cost] [backward | IWE memset] [Adam + loss + acc reset]
   // (large windows: [splat] [TV + step++ | cost] ..., see ebos_cmax_value_and_grad)
+  static const bool coefs_in_adam = getenv("EBOS_ADAM_OWN_COEFS") != nullptr;   // A/B: pow() + barrier inside k_adam as before
+  const StepCoefs sc{step_dev, lr, beta1, beta2, coefs_in_adam ? nullptr : acc + kAccAdamCoefs};
   AuxLane* lane = aux_lane(st);
   const bool tv_after_splat = n >= kTvAfterSplatEvents;
   int rc;
@@ -1268,9 +1304,9 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
       lane = nullptr;
   }
   if (dtype == EBOS_F64)
-    rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, tv_st, step_dev);
+    rc = flow_tv_t<double>((const double*)flow, (const double*)tv_weights, H, W, tv_scale, acc, (double*)dflow, tv_st, sc);
   else
-    rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st, step_dev);
+    rc = flow_tv_t<float>((const float*)flow, (const float*)tv_weights, H, W, tv_scale, acc, (float*)dflow, tv_st, sc);
   if (lane && cudaEventRecord(lane->join, tv_st) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(join)");
   if (rc) return rc;
   if (!tv_after_splat) {
@@ -1301,10 +1337,12 @@ int ebos_cmax_adam_iteration(const void* window, int64_t n, int flags, void* flo
   cudaError_t le;
   if (dtype == EBOS_F64)
     le = launch_pdl(k_adam<double>, dim3(adam_grid(np)), dim3(256), st, (double*)flow, (const double*)dflow, (double*)exp_avg,
-                    (double*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, 2, fin);
+                    (double*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, coefs_in_adam ? 2 : 3, fin,
+                    (const double*)(acc + kAccAdamCoefs));
   else
     le = launch_pdl(k_adam<float>, dim3(adam_grid(np)), dim3(256), st, (float*)flow, (const float*)dflow, (float*)exp_avg,
-                    (float*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, 2, fin);
+                    (float*)exp_avg_sq, np, lr, beta1, beta2, eps, 0, (const int32_t*)step_dev, coefs_in_adam ? 2 : 3, fin,
+                    (const double*)(acc + kAccAdamCoefs));
   if (le != cudaSuccess) return cuda_fail(le, "ebos_cmax_adam_iteration(adam)");
   if (zero_on_lane && cudaStreamWaitEvent(st, lane->fin_done, 0) != cudaSuccess) return cuda_fail(cudaGetLastError(), "ebos_cmax_adam_iteration(wait zero)");
   EBOS_LAUNCH_CHECK("ebos_cmax_adam_iteration");

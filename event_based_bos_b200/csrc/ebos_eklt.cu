@@ -36,6 +36,17 @@
 #define EBOS_EKLT_MINB 1
 #endif
 
+
+// Programmatic dependent launch along the evaluation chain: ten short kernels, each waiting for its predecessor at its
+// very top, but scheduled (and through its prologue) while the predecessor drains -- the launch gaps between one-wave
+// kernels were a fifth of an evaluation.  EBOS_NO_PDL=1 disables the launch attribute (the prologue is then a no-op).
+#define EKLT_PDL_PROLOGUE() do { ebos::pdl_launch_dependents(); ebos::pdl_wait(); } while (0)
+#define EKLT_LAUNCH(kern, grid, block, st, ...)                                                       \
+  do {                                                                                                \
+    cudaError_t le__ = ebos::launch_pdl(kern, dim3(grid), dim3(block), st, __VA_ARGS__);              \
+    if (le__ != cudaSuccess) return ebos::cuda_fail(le__, "ebos_eklt launch");                        \
+  } while (0)
+
 namespace ebos {
 namespace eklt {
 
@@ -104,6 +115,7 @@ static Workspace carve(void* base, int H, int W, int ph, int pw, int pad, size_t
 
 template <typename T>
 __global__ void k_patch_flow(const T* __restrict__ theta, int ph, int pw, T* __restrict__ pf) {
+  EKLT_PDL_PROLOGUE();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ph * pw) return;
   T o0, o1;
@@ -118,6 +130,7 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_forward(Geom g, int fla
                                                  const T* __restrict__ gx, const T* __restrict__ gy,
                                                  const T* __restrict__ weights, T* __restrict__ q, T* __restrict__ F,
                                                  double* __restrict__ acc, T* __restrict__ St) {
+  EKLT_PDL_PROLOGUE();
   __shared__ double red[32];
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   double sq = 0.0, sp = 0.0;
@@ -150,6 +163,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_column_sums(Geom g, const T* __restrict__ q, const T* __restrict__ meas,
                                                      const double* __restrict__ acc, double* __restrict__ colsum,
                                                      double* __restrict__ colS) {
+  EKLT_PDL_PROLOGUE();
   __shared__ double part[8][33];
   __shared__ double partS[8][33];
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(256) k_column_sums(Geom g, const T* __restrict
 __global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const double* __restrict__ colsum,
                                                     const double* __restrict__ colS, double* __restrict__ acc,
                                                     double w_data) {
+  EKLT_PDL_PROLOGUE();
   __shared__ double red[32];
   __shared__ double s_mx;
   double mx = -1.0;
@@ -225,6 +240,7 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_backward(Geom g, int fl
                                                   const T* __restrict__ dF,
                                                   const double* __restrict__ colsum, const double* __restrict__ acc,
                                                   double w_pxy_hw, T* __restrict__ dU) {
+  EKLT_PDL_PROLOGUE();
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   if (j >= g.W) return;
   BackScalars s;
@@ -257,6 +273,7 @@ __global__ void __launch_bounds__(256) k_backward_stored(Geom g, int flags, cons
                                                          const T* __restrict__ dF, const double* __restrict__ colsum,
                                                          const double* __restrict__ acc, double w_pxy_hw,
                                                          T* __restrict__ dU) {
+  EKLT_PDL_PROLOGUE();
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   if (j >= g.W) return;
   BackScalars s;
@@ -292,6 +309,7 @@ static bool stored_planes() {   // default ON (measured on B200: -5 % per evalua
 // the separable triangle weights.  Deterministic (no atomics).
 template <typename T>
 __global__ void __launch_bounds__(256) k_cell_gather(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ dPad) {
+  EKLT_PDL_PROLOGUE();
   __shared__ double red[32];
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int A = blockIdx.y, B = blockIdx.x;
@@ -323,6 +341,7 @@ __global__ void __launch_bounds__(256) k_cell_gather(Geom g, int nch, const T* _
 template <typename T>
 __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_tv_roi(Geom g, const T* __restrict__ F, const T* __restrict__ winv, double coef,
                                                 double* __restrict__ acc, T* __restrict__ dF) {
+  EKLT_PDL_PROLOGUE();
   __shared__ double red[32];
   int r0, r1, c0, c1;
   tv_box(g.x0, g.x1, g.H, r0, r1);
@@ -349,6 +368,7 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_tv_roi(Geom g, const T*
 // lanes over the cell's 2*patch support columns (coalesced), four channels.  T1: [nch, H, PW].
 template <typename T>
 __global__ void __launch_bounds__(256) k_gather_cols(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ T1) {
+  EKLT_PDL_PROLOGUE();
   const int PW = g.pw + 2 * g.pad;
   const int B = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, i = blockIdx.y;
   if (B >= PW) return;
@@ -373,6 +393,7 @@ __global__ void __launch_bounds__(256) k_gather_cols(Geom g, int nch, const T* _
 // Pass 2 (along rows): one warp per (channel, padded cell), lanes over the cell's 2*patch support rows of T1.
 template <typename T>
 __global__ void __launch_bounds__(256) k_gather_rows(Geom g, int nch, const T* __restrict__ T1, T* __restrict__ dPad) {
+  EKLT_PDL_PROLOGUE();
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (o >= nch * PH * PW) return;
@@ -393,6 +414,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(Geom g, int nch, const T* _
 // and reads every pixel twice (51 us); the warp-per-cell 2-D form reads it four times (36 us).
 template <typename T>
 __global__ void __launch_bounds__(256) k_gather_cols_seg(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ T1) {
+  EKLT_PDL_PROLOGUE();
   const int PW = g.pw + 2 * g.pad, p = g.patch;
   const int start = region_offset(g.w1, p) - p + (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
   if (start >= g.W) return;                      // whole warps leave together
@@ -430,6 +452,7 @@ __global__ void __launch_bounds__(256) k_gather_cols_seg(Geom g, int nch, const 
 // T1): for small patches, where a warp per output would have 2*patch <= 32 rows to share.
 template <typename T>
 __global__ void __launch_bounds__(256) k_gather_rows_thread(Geom g, int nch, const T* __restrict__ T1, T* __restrict__ dPad) {
+  EKLT_PDL_PROLOGUE();
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= nch * PH * PW) return;
@@ -451,6 +474,7 @@ static bool gather_segments() {   // default ON (measured on B200: -6 % per eval
 // would spend its time in four block reductions over one pixel per thread.
 template <typename T>
 __global__ void __launch_bounds__(256) k_cell_gather_warp(Geom g, int nch, const T* __restrict__ dU, T* __restrict__ dPad) {
+  EKLT_PDL_PROLOGUE();
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
   const int cell = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (cell >= PW * PH) return;                  // whole warps leave together
@@ -479,6 +503,7 @@ __global__ void __launch_bounds__(256) k_cell_gather_warp(Geom g, int nch, const
 
 template <typename T>
 __global__ void k_fold(Geom g, int nch, const T* __restrict__ dPad, T* __restrict__ dP) {
+  EKLT_PDL_PROLOGUE();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ph * g.pw;
   if (k >= nch * np) return;
@@ -497,6 +522,7 @@ template <typename T>
 __global__ void k_param_grad(Geom g, int flags, const T* __restrict__ dP, const double* __restrict__ tv_acc,
                              double* __restrict__ acc, double w_data, double w_tv, double w_pxy, T* __restrict__ grad,
                              T* __restrict__ loss) {
+  EKLT_PDL_PROLOGUE();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ph * g.pw;
   if (k < np) {
@@ -592,14 +618,14 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
   if (!warp) w_pxy = 0.0;
   const T* pf = theta;                                         // flow model: theta[0:2] is the patch flow
   if (flags & kPoisson) {
-    k_patch_flow<T><<<(np + 127) / 128, 128, 0, st>>>(theta, g.ph, g.pw, reinterpret_cast<T*>(w.pf));
+    EKLT_LAUNCH(k_patch_flow<T>, (np + 127) / 128, 128, st, theta, g.ph, g.pw, reinterpret_cast<T*>(w.pf));
     pf = reinterpret_cast<const T*>(w.pf);
   }
   const T* tr = warp ? theta + (size_t)flow_channels(flags) * np : nullptr;
   // stored-planes backward: not with no_polarity (the sign of q0 is not kept) and not without the warp (nothing to store)
   const bool stored = stored_planes() && warp && !(flags & kNoPolarity);
   T* St = stored ? reinterpret_cast<T*>(w.St) : nullptr;
-  k_forward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, q, F, w.acc, St);
+  EKLT_LAUNCH(k_forward<T>, pg, 256, st, g, flags, pf, tr, gx, gy, weights, q, F, w.acc, St);
   EBOS_LAUNCH_CHECK("ebos_eklt forward");
   const bool legacy = legacy_chain();
   if (legacy || w_tv == 0.0) {
@@ -611,17 +637,17 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
     tv_box(g.y0, g.y1, g.W, c0, c1);
     if (r1 > r0 && c1 > c0) {
       const dim3 tg = plane_grid(r1 - r0, c1 - c0);
-      k_tv_roi<T><<<tg, 256, 0, st>>>(g, F, winv, w_tv / (2.0 * (double)g.H * (double)g.W), w.acc, dF);
+      EKLT_LAUNCH(k_tv_roi<T>, tg, 256, st, g, F, winv, w_tv / (2.0 * (double)g.H * (double)g.W), w.acc, dF);
     }
   }
   const bool tv_from_flow_tv = legacy || w_tv == 0.0;
-  k_column_sums<T><<<pg, 256, 0, st>>>(g, q, meas, w.acc, w.colsum, w.colS);
-  k_column_max<<<1, 256, 0, st>>>(g.W, g.y0, g.y1, w.colsum, w.colS, w.acc, w_data);
+  EKLT_LAUNCH(k_column_sums<T>, pg, 256, st, g, q, meas, w.acc, w.colsum, w.colS);
+  EKLT_LAUNCH(k_column_max, 1, 256, st, g.W, g.y0, g.y1, w.colsum, w.colS, w.acc, w_data);
   if (stored)
-    k_backward_stored<T><<<pg, 256, 0, st>>>(g, flags, St, q, weights, meas, dF, w.colsum, w.acc,
+    EKLT_LAUNCH(k_backward_stored<T>, pg, 256, st, g, flags, St, q, weights, meas, dF, w.colsum, w.acc,
                                              w_pxy / ((double)g.H * g.W), dU);
   else
-    k_backward<T><<<pg, 256, 0, st>>>(g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
+    EKLT_LAUNCH(k_backward<T>, pg, 256, st, g, flags, pf, tr, gx, gy, weights, meas, dF, w.colsum, w.acc,
                                       w_pxy / ((double)g.H * g.W), dU);
   EBOS_LAUNCH_CHECK("ebos_eklt backward");
   const int PW = g.pw + 2 * g.pad, PH = g.ph + 2 * g.pad;
@@ -634,20 +660,20 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
     e = cudaMemsetAsync(T1, 0, (size_t)nch * g.H * PW * sizeof(T), st);
     if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset T1");
     const int n_seg = (g.W - (region_offset(g.w1, g.patch) - g.patch) + 31) / 32;
-    k_gather_cols_seg<T><<<dim3((n_seg + 7) / 8, g.H), 256, 0, st>>>(g, nch, dU, T1);
-    if (g.patch <= 16) k_gather_rows_thread<T><<<(nch * n_cells + 255) / 256, 256, 0, st>>>(g, nch, T1, dPad);
-    else k_gather_rows<T><<<(nch * n_cells + 7) / 8, 256, 0, st>>>(g, nch, T1, dPad);
+    EKLT_LAUNCH(k_gather_cols_seg<T>, dim3((n_seg + 7) / 8, g.H), 256, st, g, nch, dU, T1);
+    if (g.patch <= 16) EKLT_LAUNCH(k_gather_rows_thread<T>, (nch * n_cells + 255) / 256, 256, st, g, nch, T1, dPad);
+    else EKLT_LAUNCH(k_gather_rows<T>, (nch * n_cells + 7) / 8, 256, st, g, nch, T1, dPad);
   } else if (g.patch <= 16) {
-    k_cell_gather_warp<T><<<(n_cells + 7) / 8, 256, 0, st>>>(g, nch, dU, dPad);
+    EKLT_LAUNCH(k_cell_gather_warp<T>, (n_cells + 7) / 8, 256, st, g, nch, dU, dPad);
   } else if (legacy) {
-    k_cell_gather<T><<<dim3(PW, PH), 256, 0, st>>>(g, nch, dU, dPad);
+    EKLT_LAUNCH(k_cell_gather<T>, dim3(PW, PH), 256, st, g, nch, dU, dPad);
   } else {
     T* T1 = reinterpret_cast<T*>(w.T1);
-    k_gather_cols<T><<<dim3((PW + 7) / 8, g.H), 256, 0, st>>>(g, nch, dU, T1);
-    k_gather_rows<T><<<(nch * n_cells + 7) / 8, 256, 0, st>>>(g, nch, T1, dPad);
+    EKLT_LAUNCH(k_gather_cols<T>, dim3((PW + 7) / 8, g.H), 256, st, g, nch, dU, T1);
+    EKLT_LAUNCH(k_gather_rows<T>, (nch * n_cells + 7) / 8, 256, st, g, nch, T1, dPad);
   }
-  k_fold<T><<<(nch * np + 127) / 128, 128, 0, st>>>(g, nch, dPad, dP);
-  k_param_grad<T><<<(np + 127) / 128, 128, 0, st>>>(g, flags, dP, tv_from_flow_tv ? w.tv_acc : nullptr, w.acc, w_data,
+  EKLT_LAUNCH(k_fold<T>, (nch * np + 127) / 128, 128, st, g, nch, dPad, dP);
+  EKLT_LAUNCH(k_param_grad<T>, (np + 127) / 128, 128, st, g, flags, dP, tv_from_flow_tv ? w.tv_acc : nullptr, w.acc, w_data,
                                                     w_tv, w_pxy, grad, loss);
   EBOS_LAUNCH_CHECK("ebos_eklt gradient");
   return EBOS_OK;

@@ -47,6 +47,27 @@ def test_version_and_error_string():
     assert lib.ebos_window_bytes(1000, 64, 96, 0) % 256 == 0
 
 
+def test_replay_slot_entries_validate_their_arguments_without_a_device():
+    """The executable-graph slot API (ebos_capture_end_exec / ebos_exec_launch / ebos_exec_destroy): argument validation
+    happens before any CUDA call, an empty slot cannot be launched, destroying an empty slot is a no-op."""
+    lib = _capi.load()
+    assert lib.ebos_exec_launch(None, None) == -1
+    assert "no executable" in _capi.last_error()
+    assert lib.ebos_exec_destroy(None) == 0
+    from event_based_bos_b200 import ops
+
+    slot = ops.ReplaySlot()
+    assert slot.updates == 0 and slot.instantiations == 0
+    slot.close()                                   # empty slot: nothing to free, no CUDA call
+    with pytest.raises(RuntimeError, match="no executable"):
+        slot.launch() if torch.cuda.is_available() else _capi.check(lib.ebos_exec_launch(None, None), "ebos_exec_launch")
+    # the fused-TV iteration refuses what its kernel does not cover (nothing is enqueued): fp64, odd width
+    for dtype, W in ((1, 96), (0, 97)):
+        rc = lib.ebos_cmax_adam_iteration_fused_tv(1, 10, 0, 16, 32, 64, W, 0, 0, 2, 0, 1.0, 0.5, dtype, 48, 64, 80, 96, 112, 128,
+                                                   144, 0.05, 0.9, 0.999, 1e-8, 160, 0.0, None, None)
+        assert rc == -4 and "ebos_cmax_adam_iteration" in _capi.last_error()      # EBOS_ERR_UNSUPPORTED
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback_without_a_device():
     import numpy as np
