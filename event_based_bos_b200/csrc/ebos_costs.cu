@@ -221,6 +221,8 @@ constexpr int GM_TW = 64, GM_ROWS = 8;               // tile width, rows per thr
 #endif
 constexpr int GM_GROUPS = EBOS_GM_GROUPS, GM_TH = GM_GROUPS * GM_ROWS, GM_THREADS = GM_TW * GM_GROUPS;
 constexpr int GM_LW = GM_TW + 8;                      // shared tile row: columns c0 - 4 .. c0 + 67 (18 aligned float4)
+constexpr int GM_STRIP = 64;                          // pixels along a frame strip (3 deep): one CTA each
+static_assert((GM_TH + 4) * GM_LW >= 7 * (GM_STRIP + 4) + 2 * 5 * (GM_STRIP + 2), "frame strips reuse the tile's shared memory");
 
 // exact value at one frame pixel p = (r, c): sum over the counted positions q in the 3x3 neighbourhood of p and
 // the Sobel taps (u, v) whose clamped target clamp(q + (u, v)) is p.  The 5x5 clamped neighbourhood of p is
@@ -284,6 +286,69 @@ __device__ void gradmag_frame_pixel(const PeerPlanes<T>& iwe, int Hp, int Wp, in
   g[(int64_t)r * Wp + c] = out;
 }
 
+// The frame, one STRIP per CTA (3 x <= 64 pixels of the top / bottom band, <= 64 x 3 of the left / right band).  With one
+// thread per frame pixel running the function above, the 374 frame warps of a 1280 x 720 launch lived eight times as long
+// as the 3680 tile warps (ncu r02s: 9 % of the warps, 36 % of the stall samples) and set the duration of the whole kernel:
+// every thread re-derived the Sobel pair of its nine neighbours, ~2000 dependent instructions.  Here the strip's clamped
+// image tile goes to shared memory, phase 1 evaluates coef * (gx, gy) ONCE per position q of the strip dilated by one
+// (zero where q is outside the image or on the omitted ring, so phase 2 needs no validity tests) and sums the loss terms of
+// the positions the strip owns, phase 2 gathers the adjoint for the strip's pixels.  Same expressions and the same
+// summation order per pixel as gradmag_frame_pixel.
+template <typename T>
+__device__ void gradmag_frame_strip(const PeerPlanes<T>& iwe, int Hp, int Wp, int omit, T coef, int r0, int nr, int c0,
+                                    int nc, T* __restrict__ g, double& part, T* __restrict__ sm) {
+  const int tw = nc + 4, th = nr + 4;   // clamped image tile, origin (r0 - 2, c0 - 2)
+  const int gw = nc + 2, gh = nr + 2;   // Sobel pairs, origin (r0 - 1, c0 - 1)
+  T* sImg = sm;
+  T* sGx = sm + th * tw;
+  T* sGy = sGx + gh * gw;
+  for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+    const int lr = i / tw, lc = i - lr * tw;
+    sImg[i] = iwe.load((int64_t)min(max(r0 - 2 + lr, 0), Hp - 1) * Wp + min(max(c0 - 2 + lc, 0), Wp - 1));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < gh * gw; i += blockDim.x) {
+    const int lr = i / gw, lc = i - lr * gw;
+    const int qr = r0 - 1 + lr, qc = c0 - 1 + lc;
+    T cgx = 0, cgy = 0;
+    const bool counted = qr >= 0 && qr < Hp && qc >= 0 && qc < Wp &&
+                         !(omit && (qr == 0 || qc == 0 || qr == Hp - 1 || qc == Wp - 1));
+    if (counted) {
+      const T* a = sImg + lr * tw + lc;   // a[(u + 1) * tw + (w + 1)] = I(clamp(q + (u, w)))
+      const T gx = ((a[2 * tw] - a[0]) + (T)2 * (a[2 * tw + 1] - a[1]) + (a[2 * tw + 2] - a[2])) * (T)0.125;          // d/drow
+      const T gy = ((a[2] - a[0]) + (T)2 * (a[tw + 2] - a[tw]) + (a[2 * tw + 2] - a[2 * tw])) * (T)0.125;              // d/dcol
+      if (lr >= 1 && lr <= nr && lc >= 1 && lc <= nc) part += (double)gx * gx + (double)gy * gy;
+      cgx = coef * gx;
+      cgy = coef * gy;
+    }
+    sGx[i] = cgx;
+    sGy[i] = cgy;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nr * nc; i += blockDim.x) {
+    const int pl = i / nc, pc = i - pl * nc;
+    const int r = r0 + pl, c = c0 + pc;
+    T out = 0;
+#pragma unroll
+    for (int dr = -1; dr <= 1; ++dr) {
+#pragma unroll
+      for (int dc = -1; dc <= 1; ++dc) {
+        const int qr = r + dr, qc = c + dc;
+        const T cgx = sGx[(pl + 1 + dr) * gw + pc + 1 + dc], cgy = sGy[(pl + 1 + dr) * gw + pc + 1 + dc];
+#pragma unroll
+        for (int u = -1; u <= 1; ++u) {
+#pragma unroll
+          for (int w = -1; w <= 1; ++w) {
+            if (min(max(qr + u, 0), Hp - 1) != r || min(max(qc + w, 0), Wp - 1) != c) continue;
+            out += (T)(u * (2 - (w < 0 ? -w : w))) * cgx + (T)(w * (2 - (u < 0 ? -u : u))) * cgy;
+          }
+        }
+      }
+    }
+    g[(int64_t)r * Wp + c] = out;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(GM_THREADS)
 k_gradmag_sep(const PeerPlanes<T> iwe, int Hp, int Wp, int omit, T coef, double* __restrict__ acc, T* __restrict__ g,
@@ -296,22 +361,29 @@ k_gradmag_sep(const PeerPlanes<T> iwe, int Hp, int Wp, int omit, T coef, double*
   double part = 0.0;
   const bool has_fast = Hp >= 7 && Wp >= 7;
   if ((int)blockIdx.x < n_frame_ctas) {
-    // frame pixels: rows 0..2 and Hp-3..Hp-1 (full width), then columns 0..2 and Wp-3..Wp-1 of the other rows;
-    // images without a fast region are all frame
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int r = -1, c = -1;
-    if (!has_fast) {
-      if (idx < (int64_t)Hp * Wp) { r = (int)(idx / Wp); c = (int)(idx - (int64_t)r * Wp); }
-    } else if (idx < (int64_t)6 * Wp) {
-      const int k = (int)(idx / Wp);
-      r = k < 3 ? k : Hp - 6 + k; c = (int)(idx - (int64_t)k * Wp);
-    } else if (idx < (int64_t)6 * Wp + (int64_t)6 * (Hp - 6)) {
-      const int64_t j = idx - (int64_t)6 * Wp;
-      const int k = (int)(j % 6);
-      r = 3 + (int)(j / 6); c = k < 3 ? k : Wp - 6 + k;
-    }
     pdl_wait();   // the IWE (and the zeroed accumulators) of the preceding splat
-    if (r >= 0) gradmag_frame_pixel<T>(iwe, Hp, Wp, omit, coef, r, c, g, part);
+    if (!has_fast) {
+      // images without a fast region are all frame: one pixel per thread
+      const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (idx < (int64_t)Hp * Wp) {
+        const int r = (int)(idx / Wp), c = (int)(idx - (int64_t)r * Wp);
+        gradmag_frame_pixel<T>(iwe, Hp, Wp, omit, coef, r, c, g, part);
+      }
+    } else {
+      // frame strips: rows 0..2 and Hp-3..Hp-1 in 64-column segments, then columns 0..2 and Wp-3..Wp-1 of the other
+      // rows in 64-row segments (same order as the host's count: 2 * nsx + 2 * nsy)
+      const int nsx = (Wp + GM_STRIP - 1) / GM_STRIP, nsy = (Hp - 6 + GM_STRIP - 1) / GM_STRIP;
+      int sidx = blockIdx.x, r0, nr, c0, nc;
+      if (sidx < 2 * nsx) {
+        r0 = sidx < nsx ? 0 : Hp - 3; nr = 3;
+        c0 = (sidx % nsx) * GM_STRIP; nc = min(GM_STRIP, Wp - c0);
+      } else {
+        sidx -= 2 * nsx;
+        c0 = sidx < nsy ? 0 : Wp - 3; nc = 3;
+        r0 = 3 + (sidx % nsy) * GM_STRIP; nr = min(GM_STRIP, Hp - 3 - r0);
+      }
+      gradmag_frame_strip<T>(iwe, Hp, Wp, omit, coef, r0, nr, c0, nc, g, part, &sI[0][0]);
+    }
   } else if ((int)blockIdx.x - n_frame_ctas < n_tiles) {
     const int tile = blockIdx.x - n_frame_ctas;
     const int tiles_x = (Wp + GM_TW - 1) / GM_TW;
@@ -965,8 +1037,8 @@ int iwe_cost_t(int kind, const T* iwe, int Hp, int Wp, int omit, double scale, d
       k_gradmag<T><<<grid, 256, 0, st>>>(iwe, Hp, Wp, omit, coef, acc, grad_iwe);
     } else {
       const bool has_fast = Hp >= 7 && Wp >= 7;
-      const int64_t n_frame = has_fast ? (int64_t)6 * Wp + (int64_t)6 * (Hp - 6) : (int64_t)Hp * Wp;
-      const int n_frame_ctas = (int)((n_frame + GM_THREADS - 1) / GM_THREADS);
+      const int n_frame_ctas = has_fast ? 2 * ((Wp + GM_STRIP - 1) / GM_STRIP) + 2 * ((Hp - 6 + GM_STRIP - 1) / GM_STRIP)
+                                        : (int)(((int64_t)Hp * Wp + GM_THREADS - 1) / GM_THREADS);
       const int n_tiles = has_fast ? ((Wp + GM_TW - 1) / GM_TW) * ((Hp + GM_TH - 1) / GM_TH) : 0;
       PeerPlanes<T> planes{};
       planes.n = peers ? n_peers : 1;
