@@ -908,16 +908,33 @@ def giant_record(args, rank, world, local):
         obj.value_and_grad(flow)
 
     steps = max(args.steps, 10)
+    steps += steps % 2
     for _ in range(max(args.warmup, 3)):
         step()
+    # the evaluation as ONE executable graph (two evaluations per replay: the two-shot form alternates its gradient planes)
+    replay = None
+    if world > 1 and not args.giant_eager and hasattr(obj, "replayable"):
+        replay = obj.replayable(flow, 2)
+    launch_mode = "eager launches from Python"
+    if replay is not None:
+        launch_mode = "two evaluations per executable-graph replay (ops.ReplaySlot)"
+        for _ in range(2):
+            replay()
     barrier(world)
     with ClockSampler(local) as clocks:
-        ms = max_over_ranks(cuda_time_ms(step, steps), world)
+        if replay is not None:
+            ms = max_over_ranks(cuda_time_ms(replay, steps // 2) / 2.0, world)
+        else:
+            ms = max_over_ranks(cuda_time_ms(step, steps), world)
         barrier(world)
         # clock samples under load: a FIXED number of extra steps (the step holds collectives, so a time-based
         # soak would let the ranks run different counts and dead-lock)
-        for _ in range(100):
-            step()
+        for _ in range(50):
+            if replay is not None:
+                replay()
+            else:
+                step()
+                step()
         torch.cuda.synchronize()
         barrier(world)
     exchange = getattr(obj, "exchange", "none")
@@ -934,7 +951,7 @@ def giant_record(args, rank, world, local):
             "config": {"workload": f"single giant window of {n_total} synthetic events sharded by events over {world} GPU(s), "
                                    f"1280x720, fp32, {COST}+{TV_WEIGHT}*TV forward+backward",
                        "events_total": n_total, "events_per_gpu": n, "l2_policy": "inputs larger than L2"},
-            "exchange": exchange,
+            "exchange": exchange, "launch": launch_mode,
             "exchange_start_up_timing_ms": autotune,
             "exchange_bytes_per_evaluation_per_rank": 0 if world == 1 else 3 * P_BYTES,   # partial IWE (P) + partial dflow (2P)
             "parity_self_check": parity,
@@ -971,6 +988,7 @@ def main():
     ap.add_argument("--fold-tv", action="store_true", help="solve workload: the fused Adam + TV kernel instead of TV kernel + Adam kernel (A/B)")
     ap.add_argument("--eklt-concurrency", type=int, default=4, help="independent windows in flight per GPU (eklt workload)")
     ap.add_argument("--eklt-no-graph", action="store_true", help="eager launches in the eklt workload (for ncu launch lists)")
+    ap.add_argument("--giant-eager", action="store_true", help="giant workload: eager launches instead of the captured evaluation (A/B)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="force the generic 12 B/event window layout")

@@ -35,6 +35,10 @@ if os.environ.get("EBOS_BUILD_GM_GROUPS"):      # experiment: row groups per CTA
     NVCC_FLAGS.append("-DEBOS_GM_GROUPS=" + os.environ["EBOS_BUILD_GM_GROUPS"])
 if os.environ.get("EBOS_BUILD_EKLT_MINB"):    # experiment: occupancy cap of the EKLT per-pixel kernels (csrc/ebos_eklt.cu)
     NVCC_FLAGS.append("-DEBOS_EKLT_MINB=" + os.environ["EBOS_BUILD_EKLT_MINB"])
+if os.environ.get("EBOS_BUILD_GATHER_SELECT"):   # experiment: flow gathers into registers of their own + selects (ebos_window.cu)
+    NVCC_FLAGS.append("-DEBOS_GATHER_SELECT")
+if os.environ.get("EBOS_BUILD_OUT"):             # A/B builds: write the library somewhere else (EBOS_LIBRARY selects it at run time)
+    LIB_PATH = os.environ["EBOS_BUILD_OUT"]
 if os.environ.get("EBOS_BUILD_ABLATION"):   # diagnostics build: EBOS_ABLATE=<mask> then removes kernel components
     NVCC_FLAGS.append("-DEBOS_ABLATION")
 
@@ -61,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(PKG_DIR, "csrc", "build")
+    build_dir = os.path.join(PKG_DIR, "csrc", "build" + ("_alt" if os.environ.get("EBOS_BUILD_OUT") else ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for s in SOURCES:

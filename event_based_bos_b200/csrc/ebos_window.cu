@@ -382,6 +382,52 @@ struct EventBlock {
     }
   }
 
+  // The events are sorted by origin pixel: a thread's consecutive events mostly share it, so a gather is only issued
+  // when the pixel changes (ablation r01c: the redundant gathers cost 15-17 us per pass at 16 Mi events).
+  // EBOS_GATHER_SELECT (build flag, A/B): the conditional gathers go to registers of their own, preset with a constant,
+  // and the "same pixel -> previous value" choice is made by selects afterwards.  Written as `f[j] = changed ? load :
+  // f[j-1]` the compiler emits MOV f[j], f[j-1]; @P LDG f[j] -- and the MOV waits for the FIRST gather to land before the
+  // second can even issue: two to four serial L2 round trips per group (ncu r02s: 5-11 % of the stall samples of the two
+  // event kernels sit on those MOVs).
+  __device__ __forceinline__ void gather_flow(const T* __restrict__ flow, int hw) {
+#if defined(EBOS_GATHER_SELECT)
+    T a0[EPT], a1[EPT];
+    bool ch[EPT];
+    a0[0] = __ldg(flow + k[0]);
+    a1[0] = __ldg(flow + hw + k[0]);
+#pragma unroll
+    for (int j = 1; j < EPT; ++j) {
+      ch[j] = k[j] != k[j - 1];
+      a0[j] = (T)0;
+      a1[j] = (T)0;
+      if (ch[j]) {
+        a0[j] = __ldg(flow + k[j]);
+        a1[j] = __ldg(flow + hw + k[j]);
+      }
+    }
+    f0[0] = a0[0];
+    f1[0] = a1[0];
+#pragma unroll
+    for (int j = 1; j < EPT; ++j) {
+      f0[j] = ch[j] ? a0[j] : f0[j - 1];
+      f1[j] = ch[j] ? a1[j] : f1[j - 1];
+    }
+#else
+    f0[0] = __ldg(flow + k[0]);
+    f1[0] = __ldg(flow + hw + k[0]);
+#pragma unroll
+    for (int j = 1; j < EPT; ++j) {
+      if (k[j] != k[j - 1]) {
+        f0[j] = __ldg(flow + k[j]);
+        f1[j] = __ldg(flow + hw + k[j]);
+      } else {
+        f0[j] = f0[j - 1];
+        f1[j] = f1[j - 1];
+      }
+    }
+#endif
+  }
+
   // finish() for a group that lies entirely inside its item: no end-of-stream markers to test
   __device__ __forceinline__ void finish_full(const T* __restrict__ flow, int W, int hw) {
     if constexpr (PACKED) {
@@ -400,18 +446,7 @@ struct EventBlock {
         k[j] = (unsigned)kk < (unsigned)hw ? kk : 0;
       }
     }
-    f0[0] = __ldg(flow + k[0]);
-    f1[0] = __ldg(flow + hw + k[0]);
-#pragma unroll
-    for (int j = 1; j < EPT; ++j) {
-      if (k[j] != k[j - 1]) {
-        f0[j] = __ldg(flow + k[j]);
-        f1[j] = __ldg(flow + hw + k[j]);
-      } else {
-        f0[j] = f0[j - 1];
-        f1[j] = f1[j - 1];
-      }
-    }
+    gather_flow(flow, hw);
   }
 
   // raw fields from a shared-memory stage filled by the TMA bulk copies: arrays of `ch` elements in the
@@ -462,20 +497,7 @@ struct EventBlock {
         k[j] = (unsigned)kk < (unsigned)hw ? kk : 0;
       }
     }
-    // The events are sorted by origin pixel: a thread's consecutive events mostly share it, so a gather is only
-    // issued when the pixel changes (ablation r01c: the redundant gathers cost 15-17 us per pass at 16 Mi events).
-    f0[0] = __ldg(flow + k[0]);
-    f1[0] = __ldg(flow + hw + k[0]);
-#pragma unroll
-    for (int j = 1; j < EPT; ++j) {
-      if (k[j] != k[j - 1]) {
-        f0[j] = __ldg(flow + k[j]);
-        f1[j] = __ldg(flow + hw + k[j]);
-      } else {
-        f0[j] = f0[j - 1];
-        f1[j] = f1[j - 1];
-      }
-    }
+    gather_flow(flow, hw);
   }
 
   __device__ __forceinline__ void load(const T* __restrict__ sx, const T* __restrict__ sy, const T* __restrict__ sd,

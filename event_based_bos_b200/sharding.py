@@ -342,6 +342,45 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
                                          window.code, ptr(loss), st), "ebos_loss_finalize")
             return loss, dflow
 
+    def replayable(self_obj, flow, evaluations: int = 2):
+        """A callable that replays `evaluations` captured evaluations of `flow` (a fixed tensor, updated in place by the
+        caller between replays) as ONE executable graph -- the sharded evaluation is ~14 launches incl. four cross-rank
+        barriers, issued from Python, and with eight ranks sharing a host the issue rate, not the GPU, can set the pace.
+        Peer-memory forms only (the symmetric-memory barriers are ordinary kernels); `evaluations` must be even for the
+        two-shot form (its gradient planes alternate; for the same reason do not put an ODD number of eager `value_and_grad`
+        calls between two replays).  Every rank must call this; returns None on ALL ranks if any rank
+        could not capture (the caller then keeps calling `value_and_grad`)."""
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        slot = None
+        if p2p is None or p2p["form"] == 0 or evaluations % 2:
+            ok.zero_()
+        else:
+            try:
+                cap = torch.cuda.Stream(device=dev)
+                cap.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cap):
+                    slot = ops.ReplaySlot()
+                    slot.capture(lambda: [self_obj.value_and_grad(flow) for _ in range(evaluations)])
+                torch.cuda.current_stream().wait_stream(cap)
+            except Exception:
+                slot = None
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            return None
+
+        def replay():
+            cur = torch.cuda.current_stream()
+            cap.wait_stream(cur)
+            with torch.cuda.stream(cap):
+                slot.launch()
+            cur.wait_stream(cap)
+            return loss, dflow
+
+        replay.slot = slot
+        return replay
+
+    _Lean.replayable = replayable
     obj = _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
     # Which exchange is fastest depends on the rank count and on what NCCL can do on the box (in-switch NVLS reductions):
     # measured on B200s, 128 Mi events -- 2 ranks: one-shot 0.593 / two-shot 0.607 / NCCL 0.625 ms; 4 ranks: one-shot

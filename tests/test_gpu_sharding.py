@@ -49,6 +49,19 @@ def _worker(rank, world, port, out_dir):
                     torch.cuda.synchronize()
                     np.savez(os.path.join(out_dir, f"{tag}_{cost}_r{rank}.npz"), loss=loss.cpu().numpy(), grad=grad.cpu().numpy(),
                              exchange=np.array(obj.exchange))
+                    # the same evaluation replayed as one executable graph (peer-memory forms): an even number of eager
+                    # evaluations first (the two-shot planes alternate), then two replays of two evaluations each
+                    obj.value_and_grad(flow)
+                    replay = obj.replayable(flow, 2)
+                    assert (replay is not None) == obj.exchange.startswith("peer-memory"), (tag, obj.exchange)
+                    if replay is not None:
+                        replay()
+                        l2, g2 = replay()
+                        torch.cuda.synchronize()
+                        assert torch.equal(l2, loss) or abs(float(l2) - float(loss)) <= 1e-6 * abs(float(loss))
+                        err = float((g2 - grad).abs().max() / grad.abs().max())
+                        assert err <= 1e-5, (tag, cost, err)           # (atomics: run-to-run differences of the same size)
+                        np.savez(os.path.join(out_dir, f"replay_{tag}_{cost}_r{rank}.npz"), grad=g2.cpu().numpy())
                     del obj
             finally:
                 for k in env:
@@ -90,4 +103,7 @@ def test_event_sharded_objective_matches_single_gpu(tmp_path):
                 assert err <= 1e-5, (tag, cost, r, err)
             a, b = np.load(tmp_path / f"{tag}_{cost}_r0.npz"), np.load(tmp_path / f"{tag}_{cost}_r1.npz")
             assert np.array_equal(a["grad"], b["grad"]), (tag, cost)  # identical update on every rank
+            if os.path.exists(tmp_path / f"replay_{tag}_{cost}_r0.npz"):    # ... also from the replayed evaluation
+                ra, rb = np.load(tmp_path / f"replay_{tag}_{cost}_r0.npz"), np.load(tmp_path / f"replay_{tag}_{cost}_r1.npz")
+                assert np.array_equal(ra["grad"], rb["grad"]), (tag, cost)
     assert {"peer-memory one-shot", "peer-memory two-shot", "nccl all-reduce"} <= seen, seen
