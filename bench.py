@@ -795,10 +795,16 @@ def eklt_record(args, rank, world, local, quick=False):
     prob = eklt.EkltProblem(slv._gradient_x_torch, slv._gradient_y_torch, slv.cache_measured, slv.weight_inverse,
                             (0, 720, 320, 960), (1.0, 0.5, 0.1))
     per_level, per_level_legacy, per_level_stored, per_level_seg = {}, {}, {}, {}
+    launches_per_level = {}
+    from event_based_bos_b200 import ops as _ops
     for patch, ph, pw in slv.levels:
         lvl = prob.level(patch)
         th = slv.best_params_per_scale[slv.levels.index((patch, ph, pw)) + 1].to(dt).contiguous()
         per_level[patch] = graph_time_ms(lambda: lvl.value_and_grad(th), 20)
+        # kernels / memset nodes of ONE solver iteration at this level, counted from a stream capture (nothing runs)
+        th_c, m_c, v_c = th.clone(), torch.zeros_like(th), torch.zeros_like(th)
+        st_c = torch.zeros(1, dtype=torch.int32, device=th.device)
+        launches_per_level[patch] = _ops.count_launches(lambda: lvl.adam_iteration(th_c, m_c, v_c, st_c, 0.05))
         if quick:
             continue
         os.environ["EBOS_EKLT_LEGACY"] = "1"          # the first chain (whole-image TV kernel, per-cell 2-D gather)
@@ -842,7 +848,8 @@ def eklt_record(args, rank, world, local, quick=False):
             "eval_ms_per_level_without_segment_gather": per_level_seg or None,
             "e2e": {"value": world / (ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(ev.nbytes + frame.nbytes), "d2h_bytes_per_step": 2 * H * W * 8},
-            "gpu_launches": n_windows * sum(iters) * 12}
+            "gpu_launches": n_windows * sum(it * launches_per_level[patch][0] for it, (patch, _, _) in zip(iters, slv.levels)),
+            "launches_per_iteration_per_level": {str(k): {"kernels": v[0], "memset_nodes": v[1]} for k, v in launches_per_level.items()}}
     if not args.no_cpu and world == 1 and not quick:
         s_eval, cores = cpu_reference_eklt(args.solve_events)
         line["cpu_baseline"] = {"value": 1.0 / (s_eval * sum(iters)), "unit": "windows/s", "cores": cores,

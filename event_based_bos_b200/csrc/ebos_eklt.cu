@@ -54,6 +54,7 @@ namespace eklt {
 // slots each (same-address double atomics from ~1000 CTAs serialise in the L2 atomic unit, ~6 ns apiece).
 constexpr int kAccMax = 0, kAccTieW = 1, kAccS = 2, kAccLoss = 3, kAccData = 4, kAccTv = 5, kAccPxyMean = 6;
 constexpr int kSpread = 16, kAccQ2 = 16, kAccPxy = 32, kAccTvSum = 48, kAccN = 64;
+constexpr int kAccTicketCols = 8, kAccTicketTail = 9;   // free slots reinterpreted as unsigned "CTAs done" counters
 __device__ __forceinline__ double acc_sum(const double* __restrict__ acc, int base) {
   double t = 0.0;
 #pragma unroll
@@ -159,13 +160,20 @@ __global__ void __launch_bounds__(256, EBOS_EKLT_MINB) k_forward(Geom g, int fla
   }
 }
 
+__device__ __forceinline__ void column_max_body(int W, int y0, int y1, const double* __restrict__ colsum,
+                                                const double* __restrict__ colS, double* __restrict__ acc,
+                                                double w_data, double* red, double* s_mx);
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_column_sums(Geom g, const T* __restrict__ q, const T* __restrict__ meas,
-                                                     const double* __restrict__ acc, double* __restrict__ colsum,
-                                                     double* __restrict__ colS) {
+                                                     double* __restrict__ acc, double* __restrict__ colsum,
+                                                     double* __restrict__ colS, int fuse_max, double w_data) {
   EKLT_PDL_PROLOGUE();
   __shared__ double part[8][33];
   __shared__ double partS[8][33];
+  __shared__ double red[32];
+  __shared__ double s_mx;
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   const T inv = (T)(1.0 / (sqrt(acc_sum(acc, kAccQ2)) + kNormEps));
@@ -190,19 +198,32 @@ __global__ void __launch_bounds__(256) k_column_sums(Geom g, const T* __restrict
     atomicAdd(colsum + j, t);
     atomicAdd(colS + j, tS);
   }
+  if (fuse_max) {
+    // the CTA that finishes last (ticket in acc[kAccTicketCols], zeroed with the accumulators) also takes the maximum
+    // over the columns: one launch and one single-CTA kernel less on the critical path of every evaluation
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(acc + kAccTicketCols), 1u);
+      s_last = t == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      column_max_body(g.W, g.y0, g.y1, colsum, colS, acc, w_data, red, &s_mx);
+    }
+  }
 }
 
 // One CTA: max column sum (the data term), number of ties, S = tie_w * sum over the maximal ROI columns of colS.
-__global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const double* __restrict__ colsum,
-                                                    const double* __restrict__ colS, double* __restrict__ acc,
-                                                    double w_data) {
-  EKLT_PDL_PROLOGUE();
-  __shared__ double red[32];
-  __shared__ double s_mx;
+// (colsum / colS are read through L2: the kernel that accumulated them with atomics may be this very launch)
+__device__ __forceinline__ void column_max_body(int W, int y0, int y1, const double* __restrict__ colsum,
+                                                const double* __restrict__ colS, double* __restrict__ acc,
+                                                double w_data, double* red, double* s_mx) {
   double mx = -1.0;
   int nan = 0;
   for (int j = threadIdx.x; j < W; j += blockDim.x) {
-    const double c = colsum[j];
+    const double c = __ldcg(colsum + j);
     nan |= (c != c);
     mx = fmax(mx, c);                            // fmax drops NaN: tracked separately
   }
@@ -212,15 +233,15 @@ __global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const
   if (threadIdx.x == 0) {
     double m = red[0];
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
-    s_mx = any_nan ? __longlong_as_double(0x7ff8000000000000LL) : m;     // a NaN objective stays NaN, like torch's amax
+    *s_mx = any_nan ? __longlong_as_double(0x7ff8000000000000LL) : m;     // a NaN objective stays NaN, like torch's amax
   }
   __syncthreads();
-  mx = s_mx;
+  mx = *s_mx;
   double cnt = 0.0, S = 0.0;
   for (int j = threadIdx.x; j < W; j += blockDim.x) {
-    if (colsum[j] == mx) {
+    if (__ldcg(colsum + j) == mx) {
       cnt += 1.0;
-      if (j >= y0 && j < y1) S += colS[j];
+      if (j >= y0 && j < y1) S += __ldcg(colS + j);
     }
   }
   cnt = block_sum(cnt, red);
@@ -231,6 +252,15 @@ __global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const
     acc[kAccTieW] = tie_w;
     acc[kAccS] = S * tie_w;
   }
+}
+
+__global__ void __launch_bounds__(256) k_column_max(int W, int y0, int y1, const double* __restrict__ colsum,
+                                                    const double* __restrict__ colS, double* __restrict__ acc,
+                                                    double w_data) {
+  EKLT_PDL_PROLOGUE();
+  __shared__ double red[32];
+  __shared__ double s_mx;
+  column_max_body(W, y0, y1, colsum, colS, acc, w_data, red, &s_mx);
 }
 
 template <typename T>
@@ -299,6 +329,10 @@ __global__ void __launch_bounds__(256) k_backward_stored(Geom g, int flags, cons
       dU[3 * plane + k] = out[3];
     }
   }
+}
+static bool fused_tail() {   // default ON; EBOS_EKLT_FUSED_TAIL=0: separate k_column_max / k_adam / k_adam_bump launches (A/B)
+  static const bool on = !(getenv("EBOS_EKLT_FUSED_TAIL") && atoi(getenv("EBOS_EKLT_FUSED_TAIL")) == 0);
+  return on;
 }
 static bool stored_planes() {   // default ON (measured on B200: -5 % per evaluation at every level); EBOS_EKLT_STORED=0 disables
   const char* v = getenv("EBOS_EKLT_STORED");
@@ -518,24 +552,66 @@ __global__ void k_fold(Geom g, int nch, const T* __restrict__ dPad, T* __restric
   dP[k] = (T)s;
 }
 
+// Adam update fused into the last kernel of the evaluation (ebos_eklt_adam_iteration): theta / moments of the cell this
+// thread just computed the gradient of; the step counter is advanced by whichever CTA finishes last.
+template <typename T> struct AdamFuse {
+  T* theta;
+  T* m;
+  T* v;
+  double lr, b1, b2, eps;
+  int32_t* step_dev;     // nullptr: plain value_and_grad, no update
+};
+template <typename T>
+__device__ __forceinline__ void eklt_adam_one(T& p, T g, T& m, T& v, T b1, T b2, T eps, T step_size, T inv_bc2_sqrt) {
+  m = m * b1 + ((T)1 - b1) * g;                       // same expressions as ebos_costs.cu: adam_one
+  v = v * b2 + ((T)1 - b2) * g * g;
+  const T denom = sqrt(v) * inv_bc2_sqrt + eps;
+  p -= step_size * (m / denom);
+}
+
 template <typename T>
 __global__ void k_param_grad(Geom g, int flags, const T* __restrict__ dP, const double* __restrict__ tv_acc,
                              double* __restrict__ acc, double w_data, double w_tv, double w_pxy, T* __restrict__ grad,
-                             T* __restrict__ loss) {
+                             T* __restrict__ loss, AdamFuse<T> ad) {
   EKLT_PDL_PROLOGUE();
+  __shared__ T s_coef[2];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = g.ph * g.pw;
+  if (ad.step_dev) {
+    if (threadIdx.x == 0) {
+      const int step = *ad.step_dev + 1;
+      s_coef[0] = (T)(ad.lr / (1.0 - pow(ad.b1, (double)step)));
+      s_coef[1] = (T)(1.0 / sqrt(1.0 - pow(ad.b2, (double)step)));
+    }
+    __syncthreads();
+  }
+  auto put = [&](int idx, T gv) {
+    grad[idx] = gv;
+    if (ad.step_dev) {
+      T p = ad.theta[idx], mm = ad.m[idx], vv = ad.v[idx];
+      eklt_adam_one<T>(p, gv, mm, vv, (T)ad.b1, (T)ad.b2, (T)ad.eps, s_coef[0], s_coef[1]);
+      ad.theta[idx] = p; ad.m[idx] = mm; ad.v[idx] = vv;
+    }
+  };
   if (k < np) {
     const int nf = flow_channels(flags);
     if (flags & kPoisson) {
-      grad[k] = sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw);
+      put(k, sobel_over_8_adjoint_at(dP, dP + np, g.ph, g.pw, k / g.pw, k % g.pw));
     } else {
-      grad[k] = dP[k];
-      grad[np + k] = dP[np + k];
+      put(k, dP[k]);
+      put(np + k, dP[np + k]);
     }
     if (flags & kWarp) {
-      grad[nf * np + k] = dP[2 * np + k];
-      grad[(nf + 1) * np + k] = dP[3 * np + k];
+      put(nf * np + k, dP[2 * np + k]);
+      put((nf + 1) * np + k, dP[3 * np + k]);
+    }
+  }
+  if (ad.step_dev) {
+    __syncthreads();                 // every thread of this CTA has read the step counter's factors
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(acc + kAccTicketTail), 1u);
+      if (t == gridDim.x - 1) *ad.step_dev += 1;
     }
   }
   if (k == 0) {
@@ -601,7 +677,7 @@ static int check_geometry(const Geom& g) {
 template <typename T>
 static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* gx, const T* gy, const T* meas,
                             const T* winv, const T* weights, double w_data, double w_tv, double w_pxy, void* workspace,
-                            T* loss, T* grad, cudaStream_t st) {
+                            T* loss, T* grad, cudaStream_t st, const AdamFuse<T>* adam = nullptr) {
   const Workspace w = carve(workspace, g.H, g.W, g.ph, g.pw, g.pad, sizeof(T));
   cudaError_t e = cudaMemsetAsync(w.acc, 0, (kAccN + 2 * (size_t)g.W) * sizeof(double), st);
   if (e != cudaSuccess) return cuda_fail(e, "ebos_eklt memset");
@@ -641,8 +717,9 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
     }
   }
   const bool tv_from_flow_tv = legacy || w_tv == 0.0;
-  EKLT_LAUNCH(k_column_sums<T>, pg, 256, st, g, q, meas, w.acc, w.colsum, w.colS);
-  EKLT_LAUNCH(k_column_max, 1, 256, st, g.W, g.y0, g.y1, w.colsum, w.colS, w.acc, w_data);
+  const bool fuse = fused_tail();
+  EKLT_LAUNCH(k_column_sums<T>, pg, 256, st, g, q, meas, w.acc, w.colsum, w.colS, fuse ? 1 : 0, w_data);
+  if (!fuse) EKLT_LAUNCH(k_column_max, 1, 256, st, g.W, g.y0, g.y1, w.colsum, w.colS, w.acc, w_data);
   if (stored)
     EKLT_LAUNCH(k_backward_stored<T>, pg, 256, st, g, flags, St, q, weights, meas, dF, w.colsum, w.acc,
                                              w_pxy / ((double)g.H * g.W), dU);
@@ -673,8 +750,10 @@ static int value_and_grad_t(const Geom& g, int flags, const T* theta, const T* g
     EKLT_LAUNCH(k_gather_rows<T>, (nch * n_cells + 7) / 8, 256, st, g, nch, T1, dPad);
   }
   EKLT_LAUNCH(k_fold<T>, (nch * np + 127) / 128, 128, st, g, nch, dPad, dP);
+  AdamFuse<T> ad{};
+  if (adam && fuse) ad = *adam;
   EKLT_LAUNCH(k_param_grad<T>, (np + 127) / 128, 128, st, g, flags, dP, tv_from_flow_tv ? w.tv_acc : nullptr, w.acc, w_data,
-                                                    w_tv, w_pxy, grad, loss);
+                                                    w_tv, w_pxy, grad, loss, ad);
   EBOS_LAUNCH_CHECK("ebos_eklt gradient");
   return EBOS_OK;
 }
@@ -728,6 +807,31 @@ int ebos_eklt_adam_iteration(void* theta, int flags, const void* grad_x, const v
                              void* exp_avg_sq, double lr, double beta1, double beta2, double eps, int32_t* step_dev,
                              void* stream) {
   EBOS_REQUIRE(exp_avg && exp_avg_sq && step_dev, "ebos_eklt_adam_iteration: null argument");
+  if (fused_tail()) {
+    // same checks as ebos_eklt_value_and_grad, then the evaluation with the Adam update inside its last kernel
+    EBOS_REQUIRE(theta && grad_x && grad_y && measured && weight_inverse && workspace && loss && grad,
+                 "ebos_eklt_adam_iteration: null argument");
+    EBOS_REQUIRE((flags & ~(kPoisson | kWarp | kNoPolarity)) == 0, "ebos_eklt_adam_iteration: unknown flag");
+    if (dtype != EBOS_F32 && dtype != EBOS_F64) { set_error("ebos_eklt_adam_iteration: unsupported dtype"); return EBOS_ERR_UNSUPPORTED; }
+    const Geom g = make_geom(H, W, ph, pw, patch, roi_x0, roi_x1, roi_y0, roi_y1);
+    const int grc = check_geometry(g);
+    if (grc != EBOS_OK) return grc;
+    if (workspace_bytes < ebos_eklt_workspace_bytes(H, W, ph, pw, patch, dtype)) {
+      set_error("ebos_eklt_adam_iteration: workspace too small");
+      return EBOS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (dtype == EBOS_F64) {
+      const AdamFuse<double> ad{(double*)theta, (double*)exp_avg, (double*)exp_avg_sq, lr, beta1, beta2, eps, step_dev};
+      return value_and_grad_t<double>(g, flags, (const double*)theta, (const double*)grad_x, (const double*)grad_y,
+                                      (const double*)measured, (const double*)weight_inverse, (const double*)weights,
+                                      w_data, w_tv, w_pxy, workspace, (double*)loss, (double*)grad, st, &ad);
+    }
+    const AdamFuse<float> ad{(float*)theta, (float*)exp_avg, (float*)exp_avg_sq, lr, beta1, beta2, eps, step_dev};
+    return value_and_grad_t<float>(g, flags, (const float*)theta, (const float*)grad_x, (const float*)grad_y,
+                                   (const float*)measured, (const float*)weight_inverse, (const float*)weights, w_data,
+                                   w_tv, w_pxy, workspace, (float*)loss, (float*)grad, st, &ad);
+  }
   const int rc = ebos_eklt_value_and_grad(theta, flags, grad_x, grad_y, measured, weight_inverse, weights, H, W, ph, pw,
                                           patch, roi_x0, roi_x1, roi_y0, roi_y1, w_data, w_tv, w_pxy, dtype, workspace,
                                           workspace_bytes, loss, grad, stream);
