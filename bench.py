@@ -883,7 +883,11 @@ def giant_parity_check(rank, world, local):
         out["loss_rel_err"] = abs(float(loss) - float(l1)) / abs(float(l1))
         out["grad_rel_err"] = rel_max(grad, g1)
         out["ok"] = bool(same and out["loss_rel_err"] <= 1e-5 and out["grad_rel_err"] <= 1e-5)
+    if hasattr(obj, "close"):
+        obj.close()
     del obj
+    import gc
+    gc.collect()
     barrier(world)
     return out
 
@@ -947,7 +951,15 @@ def giant_record(args, rank, world, local):
     exchange = getattr(obj, "exchange", "none")
     autotune = getattr(obj, "exchange_autotune", None)
     launches = getattr(obj, "launches_per_evaluation", None)
+    # release the symmetric-memory planes deterministically, on every rank, before anything else captures a stream
+    del replay
+    if hasattr(obj, "close"):
+        obj.close()
     del obj
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    barrier(world)
     if rank != 0:
         return None
     peak, peak_kind = measured_peak_gbs()

@@ -208,6 +208,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
     #            one-shot gradient pass alone would pull 52 MB per rank over NVLink per evaluation.
     # EBOS_NO_P2P=1 or any failure to set it up falls back to NCCL; EBOS_P2P_FORM=1|2 forces a form (A/B runs).
     p2p = None
+    iwe_full = None
     R0 = dist.get_world_size() if is_distributed() else 1
     if 2 <= R0 <= 8 and dev.type == "cuda" and dist.get_backend() == "nccl":
         import ctypes
@@ -380,7 +381,20 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
         replay.slot = slot
         return replay
 
+    def close(self_obj):
+        """Release the symmetric-memory planes and their rendezvous handles NOW (every rank, after its last evaluation).
+        The closures of this objective keep them alive until Python's cycle collector gets round to the local class --
+        at an arbitrary later moment, and unmapping symmetric memory is illegal while any stream of the process is
+        being captured (it aborted a later CUDA-graph capture of the same process in the 2-GPU bench)."""
+        nonlocal iwe, iwe_full
+        torch.cuda.synchronize(dev)
+        if p2p is not None:
+            p2p.clear()
+        iwe = iwe_full = None
+        self_obj.closed = True
+
     _Lean.replayable = replayable
+    _Lean.close = close
     obj = _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
     # Which exchange is fastest depends on the rank count and on what NCCL can do on the box (in-switch NVLS reductions):
     # measured on B200s, 128 Mi events -- 2 ranks: one-shot 0.593 / two-shot 0.607 / NCCL 0.625 ms; 4 ranks: one-shot

@@ -62,6 +62,8 @@ def _worker(rank, world, port, out_dir):
                         err = float((g2 - grad).abs().max() / grad.abs().max())
                         assert err <= 1e-5, (tag, cost, err)           # (atomics: run-to-run differences of the same size)
                         np.savez(os.path.join(out_dir, f"replay_{tag}_{cost}_r{rank}.npz"), grad=g2.cpu().numpy())
+                    del replay
+                    obj.close()                                # symmetric memory released here, not by the cycle collector
                     del obj
             finally:
                 for k in env:
