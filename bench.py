@@ -354,11 +354,24 @@ def small_window_points(args, dev, sizes=(1 << 20, 500_000)):
         cap = ops.CmaxGraph(win, flow, COST, 1.0, TV_WEIGHT)
         for _ in range(5):
             cap.replay()
-        ms = cuda_time_ms(cap.replay, max(args.steps, 50))
+        ms_single = cuda_time_ms(cap.replay, max(args.steps, 50))
+        # ten evaluations per executable graph, as the solver issues its iterations (ops.ReplaySlot): at this size one
+        # graph launch per evaluation costs as much as one of its kernels
+        ws = ops.CmaxWorkspace(H, W, (0, 0), dev)
+        slot, side = ops.ReplaySlot(), torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.cmax_value_and_grad(win, flow, COST, 1.0, TV_WEIGHT, workspace=ws)
+            slot.capture(lambda: [ops.cmax_value_and_grad(win, flow, COST, 1.0, TV_WEIGHT, workspace=ws) for _ in range(10)])
+            for _ in range(3):
+                slot.launch()
+            ms = cuda_time_ms(slot.launch, max(args.steps, 50) // 5) / 10.0
+        torch.cuda.current_stream().wait_stream(side)
         alg = 32 * n + 11 * P_BYTES
         out.append({"events": n, "ms_per_step": round(ms, 5), "value": n / (ms * 1e-3), "unit": "events/s",
-                    "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "l2_policy": "inputs fit L2 (warm-L2 number)"})
-        del cap, win, ev
+                    "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "l2_policy": "inputs fit L2 (warm-L2 number)",
+                    "launch": "ten evaluations per executable-graph replay", "ms_per_step_one_evaluation_per_replay": round(ms_single, 5)})
+        del cap, slot, ws, win, ev
     return out
 
 
@@ -394,6 +407,16 @@ def run_fused(args, rank, world, local):
         barrier(world)
         ms = max_over_ranks(ms, world)
         eager_ms = max_over_ranks(cuda_time_ms(step, args.steps), world)
+        # the same evaluations issued five per executable graph (how the solvers issue their iterations, ops.ReplaySlot)
+        slot5, side5 = ops.ReplaySlot(), torch.cuda.Stream(device=dev)
+        side5.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side5):
+            slot5.capture(lambda: [step() for _ in range(5)])
+            slot5.launch()
+            ms5 = cuda_time_ms(slot5.launch, max(1, args.steps // 5)) / 5.0
+        torch.cuda.current_stream().wait_stream(side5)
+        ms5 = max_over_ranks(ms5, world)
+        del slot5
         # per-kernel timing of the kernels of the step (same stream, CUDA events around a graph of `steps` calls)
         lib = _capi.load()
         p = _capi.ptr
@@ -471,7 +494,7 @@ def run_fused(args, rank, world, local):
         # times the timed steps; memset nodes listed separately
         "gpu_launches": launches * args.steps,
         "launches_per_step": {"kernels": launches, "memset_nodes": other_nodes},
-        "ms_per_step_eager": round(eager_ms, 4),
+        "ms_per_step_eager": round(eager_ms, 4), "ms_per_step_five_evaluations_per_replay": round(ms5, 4),
         "launch": "one CUDA-graph replay per step (ops.CmaxGraph); ms_per_step_eager = the same launches issued eagerly",
         "host_numa_binding": numa,
     }
