@@ -37,6 +37,8 @@ if os.environ.get("EBOS_BUILD_EKLT_MINB"):    # experiment: occupancy cap of the
     NVCC_FLAGS.append("-DEBOS_EKLT_MINB=" + os.environ["EBOS_BUILD_EKLT_MINB"])
 if os.environ.get("EBOS_BUILD_GATHER_SELECT"):   # experiment: flow gathers into registers of their own + selects (ebos_window.cu)
     NVCC_FLAGS.append("-DEBOS_GATHER_SELECT")
+if os.environ.get("EBOS_BUILD_NO_RED_V2"):       # A/B: scalar reductions only (default: red.global.add.v2.f32 for column pairs, ebos_window.cu)
+    NVCC_FLAGS.append("-DEBOS_NO_RED_V2")
 if os.environ.get("EBOS_BUILD_OUT"):             # A/B builds: write the library somewhere else (EBOS_LIBRARY selects it at run time)
     LIB_PATH = os.environ["EBOS_BUILD_OUT"]
 if os.environ.get("EBOS_BUILD_ABLATION"):   # diagnostics build: EBOS_ABLATE=<mask> then removes kernel components

@@ -161,6 +161,10 @@ __device__ __forceinline__ void red_add_nc(double* p, double v) {
 }
 // 16-byte vector reduction (REDG.E.ADD.F32x4): one LSU lane-op for four consecutive floats.  Measured on
 // B200 (profiles/microbench/r01_red_throughput.txt): a RED lane-op costs ~1.3 SM-cycles whatever its width.
+// two horizontally adjacent cells in one reduction (8-byte aligned address: even column, even row stride)
+__device__ __forceinline__ void red_add_v2(float* p8, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p8), "f"(a), "f"(b));
+}
 __device__ __forceinline__ void red_add_v4(float* p16, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p16), "f"(a), "f"(b), "f"(c), "f"(d));
 }

@@ -600,6 +600,18 @@ __device__ __forceinline__ void flush_cell(T* __restrict__ iwe, int Hp, int Wp, 
         return;
       }
     }
+#if !defined(EBOS_NO_RED_V2)
+    // the two column-adjacent taps of a row as ONE 8-byte vector reduction when the cell's column is even (no zero lanes,
+    // unlike the red.v4 form above): 2 instead of 4 reductions for half of the cells.  Measured on B200 (r02d2, build flag
+    // A/B): sparse splat 12.5 -> 11.9 us at 500 k events, 1 Mi-event evaluation 46.1 -> 44.9 us, solve +1 %
+    if constexpr (sizeof(T) == 4) {
+      if (!((c | Wp) & 1) && (reinterpret_cast<size_t>(iwe) & 7) == 0) {
+        red_add_v2(reinterpret_cast<float*>(p), a0, a2);
+        red_add_v2(reinterpret_cast<float*>(p + Wp), a1, a3);
+        return;
+      }
+    }
+#endif
     red_add_nc(p, a0);
     red_add_nc(p + 1, a2);
     p += Wp;
