@@ -69,6 +69,7 @@ SIGNATURES = {
                                c_int, c_int, c_void_p]),
     "ebos_iwe_cost_peers": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "ebos_sum_peers": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "ebos_multimem_allreduce_slice": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "ebos_reduce_peers_slice": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "ebos_gather_peers_slices": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "ebos_ingest_workspace_bytes": (c_size_t, [c_int64]),

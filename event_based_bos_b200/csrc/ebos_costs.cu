@@ -1011,6 +1011,23 @@ __global__ void __launch_bounds__(256) k_gather_slices(const PeerPlanes<T> pl, i
   for (int64_t i = tid; i < n; i += nth) out[i] = pl.p[(int)min(i / slice, (int64_t)pl.n - 1)][i];
 }
 
+// In-switch form (NVLS): `mc` is the MULTICAST mapping of a symmetric buffer -- one address that stands for the same
+// offset in every rank's copy.  multimem.ld_reduce has the NVSwitch fetch and add the R copies of an element and return the
+// sum; multimem.st writes a value into all R copies.  Rank r does both for slice r only (one reducer per element: every
+// rank ends with bit-identical values): the reduce-scatter, the barrier between the two shots and the all-gather of the
+// two-shot form collapse into this one pass, and a rank moves 2/R of a plane over its links instead of 2 (R-1)/R.
+__global__ void __launch_bounds__(256) k_multimem_allreduce_slice(float* __restrict__ mc, int64_t begin4, int64_t end4) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = begin4 + tid; i < end4; i += nth) {
+    float* a = mc + 4 * i;
+    float x, y, z, w;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(a) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+  }
+  __threadfence_system();   // the broadcast stores are performed before this rank enters the barrier that follows
+}
+
 // ---- launch helpers ----------------------------------------------------------------------------------
 // 2-D grid-stride launch shape for plane kernels: about `per_sm` CTAs per SM in total (the reductions end in
 // one same-address atomic per CTA, so fewer, longer-lived CTAs are better).
@@ -1201,6 +1218,20 @@ int ebos_reduce_peers_slice(const void* const* peers, int n_peers, int64_t begin
     k_reduce_slice<float><<<grid, 256, 0, as_stream(stream)>>>(pl, begin, end, (float*)dst);
   }
   EBOS_LAUNCH_CHECK("ebos_reduce_peers_slice");
+  return EBOS_OK;
+}
+
+int ebos_multimem_allreduce_slice(void* multicast_base, int64_t begin, int64_t end, int dtype, void* stream) {
+  EBOS_REQUIRE(multicast_base && begin >= 0 && end >= begin, "ebos_multimem_allreduce_slice: bad argument");
+  if (dtype != EBOS_F32 || ((begin | end) & 3) || (reinterpret_cast<size_t>(multicast_base) & 15)) {
+    set_error("ebos_multimem_allreduce_slice: needs fp32, a 16-byte aligned multicast address and a slice on multiples of 4 elements");
+    return EBOS_ERR_UNSUPPORTED;
+  }
+  if (end == begin) return EBOS_OK;
+  const int64_t n4 = (end - begin) >> 2;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 4));
+  k_multimem_allreduce_slice<<<grid, 256, 0, as_stream(stream)>>>((float*)multicast_base, begin >> 2, end >> 2);
+  EBOS_LAUNCH_CHECK("ebos_multimem_allreduce_slice");
   return EBOS_OK;
 }
 

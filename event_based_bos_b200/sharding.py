@@ -229,9 +229,16 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             h_iwe = symm.rendezvous(s_iwe, dist.group.WORLD)
             h_df = [symm.rendezvous(b, dist.group.WORLD) for b in s_df]
             form = int(os.environ.get("EBOS_P2P_FORM", "0")) or (1 if R0 <= 2 else 2)
-            if kind != _capi.COST_GRADMAG:
+            if kind != _capi.COST_GRADMAG and form == 1:
+                form = 2
+            mc_iwe = int(getattr(h_iwe, "multicast_ptr", 0) or 0)
+            mc_df = [int(getattr(h, "multicast_ptr", 0) or 0) for h in h_df]
+            has_mc = (bool(mc_iwe and all(mc_df)) and window.dtype == torch.float32 and s_iwe.numel() % 4 == 0
+                      and s_df[0].numel() % 4 == 0 and not os.environ.get("EBOS_NO_MULTIMEM"))
+            if form == 3 and not has_mc:
                 form = 2
             p2p = {"iwe": s_iwe, "df": s_df, "h_iwe": h_iwe, "h_df": h_df, "form": form, "count": 0,
+                   "mc_iwe": mc_iwe, "mc_df": mc_df, "has_mc": has_mc,
                    "iwe_ptrs": (ctypes.c_void_p * R0)(*[int(v) for v in h_iwe.buffer_ptrs]),
                    "df_ptrs": [(ctypes.c_void_p * R0)(*[int(v) for v in h.buffer_ptrs]) for h in h_df]}
             iwe_full = iwe                                     # plain plane for the gathered IWE (two-shot form)
@@ -266,6 +273,8 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
                 return self._value_and_grad_p2p(flow)
             if p2p is not None and p2p["form"] == 2:
                 return self._value_and_grad_p2p_two_shot(flow)
+            if p2p is not None and p2p["form"] == 3:
+                return self._value_and_grad_multimem(flow)
             st = current_stream()      # form 0: NCCL all-reduce
             R = dist.get_world_size() if is_distributed() else 1
             Hp, Wp = H + 2 * ph, W + 2 * pw
@@ -359,9 +368,10 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             try:
                 cap = torch.cuda.Stream(device=dev)
                 cap.wait_stream(torch.cuda.current_stream())
+                outs = []
                 with torch.cuda.stream(cap):
                     slot = ops.ReplaySlot()
-                    slot.capture(lambda: [self_obj.value_and_grad(flow) for _ in range(evaluations)])
+                    slot.capture(lambda: outs.extend(self_obj.value_and_grad(flow) for _ in range(evaluations)))
                 torch.cuda.current_stream().wait_stream(cap)
             except Exception:
                 slot = None
@@ -376,7 +386,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             with torch.cuda.stream(cap):
                 slot.launch()
             cur.wait_stream(cap)
-            return loss, dflow
+            return outs[-1]          # (loss, gradient) tensors of the last captured evaluation
 
         replay.slot = slot
         return replay
@@ -395,6 +405,39 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
 
     _Lean.replayable = replayable
     _Lean.close = close
+    def _value_and_grad_multimem(self_obj, flow):
+        """In-switch form (NVLS): rank r has the NVSwitch sum slice r of every rank's plane and write the sum back into every
+        copy (ebos_multimem_allreduce_slice on the multicast mapping of the symmetric buffer): one pass between two barriers
+        per exchange, no gather, 2/R of a plane per rank on the links.  The reduced IWE / gradient end up in the symmetric
+        planes themselves."""
+        st = current_stream()
+        rank = dist.get_rank()
+        Hp, Wp = H + 2 * ph, W + 2 * pw
+        k = p2p["count"] % 2
+        p2p["count"] += 1
+        part, h_part, mc_part = p2p["df"][k], p2p["h_df"][k], p2p["mc_df"][k]
+        s_plane = p2p["iwe"]
+        ops.window_splat(window, flow, outer_padding, out=s_plane)
+        tv_stream = tv_beside_exchange(flow, part)
+        _, b0, b1 = _slice_bounds(s_plane.numel(), rank)
+        p2p["h_iwe"].barrier(channel=0)                   # every rank's partial IWE is complete
+        check(lib.ebos_multimem_allreduce_slice(p2p["mc_iwe"], b0, b1, window.code, st), "ebos_multimem_allreduce_slice")
+        p2p["h_iwe"].barrier(channel=1)                   # every slice is reduced and written to every copy
+        check(lib.ebos_iwe_cost(kind, ptr(s_plane), Hp, Wp, int(omit_boundary), data_weight, window.code, ptr(acc),
+                                ptr(g_iwe), st), "ebos_iwe_cost")
+        torch.cuda.current_stream().wait_stream(tv_stream)
+        check(lib.ebos_window_backward(ptr(window.buffer), window.n, window.flags, ptr(flow), H, W, ph, pw,
+                                       window.code, ptr(g_iwe), kind, ptr(s_plane), ptr(acc), int(omit_boundary),
+                                       data_weight, ptr(part), st), "ebos_window_backward")
+        _, b0, b1 = _slice_bounds(part.numel(), rank)
+        h_part.barrier(channel=0)                         # every partial gradient is complete (and every rank is past its
+        check(lib.ebos_multimem_allreduce_slice(mc_part, b0, b1, window.code, st), "ebos_multimem_allreduce_slice")   # IWE reads)
+        h_part.barrier(channel=1)
+        check(lib.ebos_loss_finalize(kind, ptr(acc), Hp, Wp, H, W, int(omit_boundary), data_weight, tv_weight,
+                                     window.code, ptr(loss), st), "ebos_loss_finalize")
+        return loss, part
+
+    _Lean._value_and_grad_multimem = _value_and_grad_multimem
     obj = _Lean(splat, cost_fn, backward, regulariser if tv_weight else None)
     # Which exchange is fastest depends on the rank count and on what NCCL can do on the box (in-switch NVLS reductions):
     # measured on B200s, 128 Mi events -- 2 ranks: one-shot 0.593 / two-shot 0.607 / NCCL 0.625 ms; 4 ranks: one-shot
@@ -402,7 +445,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
     # evaluations on this window (all ranks in lock-step, the slowest rank decides) and the fastest is kept.
     obj.exchange_autotune = None
     if p2p is not None and not __import__("os").environ.get("EBOS_P2P_FORM"):
-        forms = ([1] if kind == _capi.COST_GRADMAG else []) + [2, 0]
+        forms = ([1] if kind == _capi.COST_GRADMAG else []) + [2] + ([3] if p2p["has_mc"] else []) + [0]
         probe = torch.zeros((2, H, W), dtype=window.dtype, device=dev)
         timings = {}
         for form in forms:
@@ -428,7 +471,7 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
             if peer is not None and timings[peer] <= 1.05 * timings[0]:
                 best = peer
         p2p["form"] = best
-        names = {0: "nccl", 1: "peer one-shot", 2: "peer two-shot"}
+        names = {0: "nccl", 1: "peer one-shot", 2: "peer two-shot", 3: "in-switch multimem"}
         obj.exchange_autotune = {names[f]: round(v, 4) for f, v in timings.items()}
         if p2p["form"] == 0:
             pass
@@ -436,11 +479,14 @@ def cuda_event_sharded_objective(events_local: torch.Tensor, image_size: Tuple[i
         obj.exchange = "nccl all-reduce (2 per evaluation)" if R0 > 1 else "none"
         if p2p is not None:
             obj.exchange += "; chosen by the start-up timing over the peer-memory forms"
+    elif p2p["form"] == 3:
+        obj.exchange = ("peer-memory in-switch (NVLS multimem.ld_reduce + multimem.st on the multicast mapping, one pass per plane; "
+                        "4 device barriers per evaluation)")
     elif p2p["form"] == 1:
         obj.exchange = "peer-memory one-shot (IWE reduction fused into the cost kernel; 3 device barriers per evaluation)"
     else:
         obj.exchange = "peer-memory two-shot (reduce-scatter in place + all-gather for IWE and gradient; 4 device barriers per evaluation)"
     # kernels of this library per evaluation: TV, splat, cost, backward, loss + the peer kernels (1 one-shot, 4 two-shot);
     # the NCCL path uses two library all-reduces instead
-    obj.launches_per_evaluation = 5 if (p2p is None or p2p["form"] == 0) else (6 if p2p["form"] == 1 else 9)
+    obj.launches_per_evaluation = 5 if (p2p is None or p2p["form"] == 0) else {1: 6, 2: 9, 3: 7}[p2p["form"]]
     return obj

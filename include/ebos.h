@@ -260,6 +260,12 @@ EBOS_API int ebos_sum_peers(const void* const* peers, int n_peers, int64_t n, in
  *                             (in place: rank r reduces slice r into its own buffer, which only rank r reads there);
  *   ebos_gather_peers_slices  out[i] = peers[min(i / slice, n_peers - 1)][i]: collect the reduced slices (after a barrier).
  * Every rank ends with bit-identical values (one rank computes each element). */
+/* In-switch form (NVLS multicast): multicast_base is the MULTICAST mapping of a symmetric fp32 buffer (one address for the
+ * same offset in every rank's copy, e.g. torch symmetric memory's `multicast_ptr`).  For i in [begin, end): the NVSwitch
+ * sums the ranks' copies of element i (multimem.ld_reduce) and the result is written into every copy (multimem.st).  Rank r
+ * calls it for slice r between the same two barriers as above: afterwards every rank's own buffer holds the reduced plane,
+ * bit-identical everywhere.  begin / end multiples of 4 elements, 16-byte aligned base; EBOS_ERR_UNSUPPORTED otherwise. */
+EBOS_API int ebos_multimem_allreduce_slice(void* multicast_base, int64_t begin, int64_t end, int dtype, void* stream);
 EBOS_API int ebos_reduce_peers_slice(const void* const* peers, int n_peers, int64_t begin, int64_t end, int dtype, void* dst,
                             void* stream);
 EBOS_API int ebos_gather_peers_slices(const void* const* peers, int n_peers, int64_t n, int64_t slice, int dtype, void* out,

@@ -39,7 +39,7 @@ def _worker(rank, world, port, out_dir):
         # every exchange: the default (the fastest form by the start-up timing), and each form forced: peer-memory
         # one-shot (gradient magnitude only; the variance objective falls to two-shot), peer-memory two-shot, NCCL
         for tag, env in (("default", {}), ("oneshot", {"EBOS_P2P_FORM": "1"}), ("twoshot", {"EBOS_P2P_FORM": "2"}),
-                         ("nccl", {"EBOS_NO_P2P": "1"})):
+                         ("multimem", {"EBOS_P2P_FORM": "3"}), ("nccl", {"EBOS_NO_P2P": "1"})):
             os.environ.update(env)
             try:
                 for cost in ("gradient_magnitude", "image_variance"):
@@ -95,7 +95,7 @@ def test_event_sharded_objective_matches_single_gpu(tmp_path):
     for cost in ("gradient_magnitude", "image_variance"):
         loss, grad = ops.cmax_value_and_grad(win, flow, cost, 1.0, 0.5)
         loss, grad = float(loss), grad.cpu().numpy().copy()
-        for tag in ("default", "oneshot", "twoshot", "nccl"):
+        for tag in ("default", "oneshot", "twoshot", "multimem", "nccl"):   # (multimem falls back to two-shot without NVLS multicast)
             for r in range(world):
                 z = np.load(tmp_path / f"{tag}_{cost}_r{r}.npz")
                 seen.add(str(z["exchange"]).split(" (")[0])
